@@ -1,0 +1,199 @@
+/*
+ * nsc_b200.h -- C ABI of libnsc_b200.so: the B200 (sm_100a) implementation of NSC's batched
+ * frame-wise codec pass.
+ *
+ * The reference (/root/reference) has no FFI: its operator surface is plain Python functions
+ * (nn_core_operator.py, lpc_utilities.py, loss_terms_and_measures.py) whose arithmetic runs inside
+ * TensorFlow / audiolazy / spectrum.  Each entry point below names the reference function (file:line)
+ * it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory,
+ *     including workspaces (size queried with the matching *_workspace_bytes call);
+ *   - all tensors are dense float32 unless stated; "frames" B is the batch dimension;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work and never synchronise;
+ *   - return value: 0 = ok, <0 = error (NSC_E_*), message via nsc_last_error() (thread local);
+ *   - the library keeps no global mutable state besides per-kernel attribute caches.
+ */
+#ifndef NSC_B200_H_
+#define NSC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSC_OK 0
+#define NSC_E_INVALID (-1)      /* bad argument / unsupported configuration */
+#define NSC_E_CUDA (-2)         /* a CUDA runtime call failed               */
+#define NSC_E_WORKSPACE (-3)    /* workspace too small                      */
+
+#define NSC_FRAME_LENGTH 512    /* constants.py:25 */
+#define NSC_LPC_ORDER 16        /* neural_speech_coding_module.py:50 */
+#define NSC_MAX_BLOCKS 8
+#define NSC_MAX_STRIDES 4
+#define NSC_MAX_CODECS 8
+
+int nsc_version(void);
+const char* nsc_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Activations of nn_core_operator.py: None, tf.nn.tanh, activation_func (= leaky_relu 0.2, :24-31)
+ * ---------------------------------------------------------------------------------------------- */
+enum { NSC_ACT_NONE = 0, NSC_ACT_TANH = 1, NSC_ACT_LRELU = 2 };
+
+/* ------------------------------------------------------------------------------------------------
+ * conv1d  (nn_core_operator.py:6-14; also change_channel :45-54)
+ *   x (B, Lin, Cin) channels-last, w (k, Cin, Cout) [TF kernel layout], b (Cout) -> y (B, ceil(Lin/stride), Cout)
+ *   SAME padding, cross-correlation, bias always, optional fused activation.
+ * ---------------------------------------------------------------------------------------------- */
+int nsc_conv1d(const float* x, const float* w, const float* b, float* y, int64_t B, int32_t Lin, int32_t Cin,
+               int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation, void* stream);
+
+/* conv1d_depth (nn_core_operator.py:17-21): Keras SeparableConv1D, depth multiplier 1.
+ *   dw (k, Cin, 1), pw (1, Cin, Cout), b (Cout); tmp is a (B, Lout, Cin) scratch buffer. */
+int nsc_conv1d_depth(const float* x, const float* dw, const float* pw, const float* b, float* tmp, float* y,
+                     int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation,
+                     int32_t stride, int32_t activation, void* stream);
+
+/* the_bottleneck (nn_core_operator.py:57-79) and gated_bottleneck (:82-112) on channels-last tensors.
+ *   params: the block's conv parameters back to back in creation order, each kernel (k,cin,cout) then bias.
+ *   the_bottleneck : 3 convs;  gated_bottleneck : 4 convs (1x1, k15 left, k15 right(tanh), k_plain).
+ *   x (B, L, Cin) with Cin == wide or Cin == 1 (residual add broadcasts, :77);  y (B, L, wide).
+ *   workspace: nsc_block_workspace_bytes(B, L, wide, narrow) bytes. */
+int64_t nsc_block_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t narrow);
+int nsc_bottleneck_block(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t Cin,
+                         int32_t wide, int32_t narrow, int32_t k_plain, int32_t k_dilated, int32_t dilation,
+                         int32_t is_last_flat, int32_t gated, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * scalar_softmax_quantization (nn_core_operator.py:140-164) + quan_loss (loss_terms_and_measures.py:257-259)
+ * + the soft histogram that entropy_coding_loss (:262-267) reduces.
+ *   x (rows = B*L) floating codes; bins (n); alpha: device scalar.
+ *   idx[r]   = first argmax_k fp32(alpha * fp32(|x[r]-bins[k]|))   (uint8 when n <= 256, stored as int32 otherwise)
+ *   use_soft = the_share (1: value path uses the soft assignment; 0: one-hot)
+ *   out[r]   = (1-is_quan_on)*x[r] + is_quan_on*q[r]
+ *   soft     (rows, n) or NULL;   hist (n) += sum_r soft[r,:] or NULL (caller zeroes it);
+ *   qloss    (B) = mean_L sum_k sqrt(soft+1e-20) or NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int nsc_quantize_scalar(const float* x, int64_t B, int32_t L, const float* bins, int32_t n, const float* alpha,
+                        float is_quan_on, int32_t use_soft, float* out, uint8_t* idx, float* soft, float* hist,
+                        float* qloss, void* stream);
+
+/* decode side of a hard code: out[r] = bins[idx[r]] */
+int nsc_dequantize_scalar(const uint8_t* idx, int64_t rows, const float* bins, int32_t n, float* out, void* stream);
+
+/* quan_loss (loss_terms_and_measures.py:257-259) on a materialised soft assignment (B, L, n) -> (B). */
+int nsc_quan_loss(const float* soft, int64_t B, int32_t L, int32_t n, float* qloss, void* stream);
+/* hist (n) += column sums of a materialised soft assignment (rows, n); the caller zeroes hist. */
+int nsc_soft_histogram(const float* soft, int64_t rows, int32_t n, float* hist, void* stream);
+
+/* entropy_coding_loss (loss_terms_and_measures.py:262-267) from a soft histogram: one scalar (bits). */
+int nsc_entropy_from_hist(const float* hist, int32_t n, float* entropy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LPC  (lpc_utilities.py)
+ * ---------------------------------------------------------------------------------------------- */
+/* lpc_analysis_at_test loop body (:112-124): windows (N,1024) -> LSF (N,16) radians ascending.
+ *   window = [rising half-Hann(512), 512 ones, falling half-Hann(512)], autocorrelation LPC order 16,
+ *   poly2lsf.  float64 arithmetic; lsf_out is float64 like the reference's np.empty array.
+ *   status (int32, may be NULL) is incremented for every frame that is not analysable (zero energy /
+ *   non-minimum-phase); such rows are filled with NaN (the reference raises). */
+int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, int32_t* status, void* stream);
+
+/* lpc_analysis_at_train (:14-25): frames (B,512) -> highpass, pre-emphasis (zero state), LPC, LSF (B,16). */
+int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, int32_t* status, void* stream);
+
+/* lsf2poly_after_quan (:28-33): lsf (B,16) float32 -> poly (B,17) float32, a[0] = 1.
+ *   rows with an LSF outside [0, pi] become NaN and bump *status (the reference raises ValueError). */
+int nsc_lsf2poly(const float* lsf, int64_t B, float* poly, int32_t* status, void* stream);
+
+/* lpc_analysis_get_residual (:37-77): x (B,512), poly (B,17) -> residual (B,512);
+ *   7 zero-state sub-frame FIRs with Hann overlap-add, float64 accumulation, float32 result. */
+int nsc_lpc_residual(const float* x, const float* poly, int64_t B, float* res, void* stream);
+
+/* lpc_synthesizer_tr (:137-156): poly (B,17), res (B,512) -> y (B,512); zero-state all-pole IIR in float64. */
+int nsc_lpc_synth(const float* poly, const float* res, int64_t B, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses (loss_terms_and_measures.py)
+ * ---------------------------------------------------------------------------------------------- */
+/* mel filterbank of mfcc_transform (:130-148): fills melw (257 x 184) = 4 HTK banks {8,16,32,128} side by side. */
+#define NSC_MEL_BINS 257
+#define NSC_MEL_TOTAL 184
+/* melw buffer: 257*184 float weights followed by int32 lo[184], hi[184] (row support of every column) */
+#define NSC_MEL_BUFFER_FLOATS (NSC_MEL_BINS * NSC_MEL_TOTAL + 2 * NSC_MEL_TOTAL)
+int nsc_mel_filterbank(float* melw, void* stream);
+/* mse_loss (:77-79) -> time_loss (B);  mfcc_loss (:151-175) -> freq_loss (B).  Either output may be NULL. */
+int nsc_losses_forward(const float* decoded, const float* original, int64_t B, const float* melw,
+                       float* time_loss, float* freq_loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One codec (neural_speech_coding_module.py:219-335) and the CMRL cascade (cmrl.py:513-543, :770-858)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nsc_codec_cfg {
+  int32_t k_dilated;                 /* bottleneck_kernel_and_dilation[0]                         */
+  int32_t k_plain;                   /* [1]                                                      */
+  int32_t wide;                      /* [2]                                                      */
+  int32_t narrow;                    /* [3]                                                      */
+  int32_t n_blocks;                  /* len(list) - 4                                            */
+  int32_t dilations[NSC_MAX_BLOCKS]; /* [4:]                                                     */
+  int32_t n_strides;                 /* the_strides expanded: '2' -> {2}, '4' -> {2,2}           */
+  int32_t strides[NSC_MAX_STRIDES];
+  int32_t resnet_type;               /* 0 = 'bottleneck', 1 = 'gln' (constants.py:13-14)         */
+  int32_t num_bins;                  /* num_bins_for_follower[i]                                 */
+} nsc_codec_cfg;
+
+/* Flat parameter image of one codec: conv parameters in TF creation order (kernel (k,cin,cout) then bias,
+ * separable convs: depthwise (k,cin,1), pointwise (1,cin,cout), bias), then alpha (1), then bins (num_bins). */
+int64_t nsc_codec_param_count(const nsc_codec_cfg* cfg);
+/* Describes conv layer `i` (creation order): fills k,cin,cout,separable, offset of its first float. Returns
+ * the number of conv layers when i < 0. */
+int32_t nsc_codec_layer_info(const nsc_codec_cfg* cfg, int32_t i, int32_t* k, int32_t* cin, int32_t* cout,
+                             int32_t* separable, int64_t* offset);
+int64_t nsc_codec_workspace_bytes(const nsc_codec_cfg* cfg, int64_t B);
+
+/* Whole codec, computational_graph_end2end_quan_on[_lpc]:
+ *   x (B,512) -> floating_code (B,Lc) [may be NULL], idx (B,Lc) uint8 [may be NULL], code (B,Lc) [may be NULL],
+ *   out (B,512).  soft/hist/qloss as in nsc_quantize_scalar (may be NULL).
+ *   in_scale multiplies the input, out_scale the output (res_scalar handling of cmrl.py:810-830). */
+int nsc_codec_forward(const nsc_codec_cfg* cfg, const float* params, const float* x, int64_t B, float is_quan_on,
+                      int32_t use_soft, float* floating_code, uint8_t* idx, float* code, float* out, float* soft,
+                      float* hist, float* qloss, void* workspace, int64_t workspace_bytes, void* stream);
+/* Encoder only (x -> floating code -> idx/code) and decoder only (code -> out). */
+int nsc_codec_encode(const nsc_codec_cfg* cfg, const float* params, const float* x, int64_t B, float is_quan_on,
+                     int32_t use_soft, float* floating_code, uint8_t* idx, float* code, float* soft, float* hist,
+                     float* qloss, void* workspace, int64_t workspace_bytes, void* stream);
+int nsc_codec_decode(const nsc_codec_cfg* cfg, const float* params, const float* code, int64_t B, float* out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* CMRL cascade, all_modules_feedforward (lpc_variant = 0) / loop of all_modules_feedforward_lpc (= 1):
+ *   in_0 = x (times res_scalar if lpc_variant); in_i = res_scalar * (x - sum_{j<i} out_j);
+ *   out_i = dec_i(Q(enc_i(in_i))) / res_scalar (codec 0 undivided when lpc_variant = 0); decoded = sum_i out_i.
+ *   params_ptrs_host: host array of n_codecs device pointers; cfgs: host array of n_codecs configs.
+ *   idx / hist / qloss / outs: host arrays of n_codecs device pointers (array or entries may be NULL). */
+int64_t nsc_cascade_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B);
+int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
+                        const float* x, int64_t B, float res_scalar, int32_t lpc_variant, float is_quan_on,
+                        int32_t use_soft, uint8_t* const* idx_ptrs_host, float* const* hist_ptrs_host,
+                        float* const* qloss_ptrs_host, float* const* outs_ptrs_host, float* decoded,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Collaborative-quantisation feed-forward (cmrl.py:770-858): LSF codebook -> lsf2poly -> residual -> cascade ->
+ * synthesis.  lsf (B,16) float32 (from nsc_lpc_analyze, cast), lsf_params = {alpha, bins[n_lsf_bins]}.
+ *   outputs: lsf_idx (B,16) uint8, poly (B,17), res_x (B,512), decoded (B,512), synthesized (B,512); any may be NULL
+ *   except decoded.  */
+int64_t nsc_cq_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B);
+int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
+                   const float* lsf_params, int32_t n_lsf_bins, const float* x, const float* lsf, int64_t B,
+                   float res_scalar, float is_quan_on, int32_t use_soft, uint8_t* lsf_idx, float* lsf_hist,
+                   float* lsf_qloss, uint8_t* const* idx_ptrs_host, float* const* hist_ptrs_host,
+                   float* const* qloss_ptrs_host, float* poly, float* res_x, float* decoded, float* synthesized,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSC_B200_H_ */

@@ -1,0 +1,354 @@
+"""Thin host harness over the C ABI for one neural codec and the CMRL cascade.
+
+Mirrors the *dataflow* of the reference's graph builders -- nothing of their training loops, dataset paths or
+checkpoint I/O:
+    neural_speech_coding_module.py:262-335   computational_graph_end2end_quan_on[_lpc]  -> NeuralCodec
+    cmrl.py:513-543                          all_modules_feedforward                   -> CMRL.all_modules_feedforward
+    cmrl.py:770-858                          all_modules_feedforward_lpc/_feedforward_lpc -> CMRL.feedforward_lpc
+Weights live in ONE flat float32 device buffer per codec (TF creation order; layout owned by the C library:
+nsc_codec_layer_info), which is also the unit the data-parallel training step all-reduces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import constants as _c
+
+FRAME = _c.frame_length
+
+
+@dataclass(frozen=True)
+class CodecConfig:
+    """The command-line knobs that parameterise one codec (main.py:5-27, parsed at nscm.py:28-36, :56-70)."""
+    bottleneck_kernel_and_dilation: Tuple[int, ...] = (9, 9, 100, 20, 1, 2)   # README.md:75
+    the_strides: Tuple[int, ...] = (2,)          # already expanded: '2' -> (2,), '4' -> (2, 2) (cmrl.py:32)
+    resnet_type: str = 'bottleneck'              # constants.py:13-14
+    num_bins: int = 32                           # num_bins_for_follower[i]
+
+    @staticmethod
+    def from_args(bottleneck_kernel_and_dilation: str = '9 9 100 20 1 2', the_strides: str = '2',
+                  num_bins: int = 32, resnet_type: str = 'bottleneck') -> "CodecConfig":
+        """Parses the reference's string flags (nscm.py:33, :69; stride expansion cmrl.py:32, :168)."""
+        bkd = tuple(int(v) for v in bottleneck_kernel_and_dilation.split())
+        s = [int(v) for v in the_strides.split()]
+        strides = (2, 2) if s[0] == 4 else (2,)
+        return CodecConfig(bkd, strides, resnet_type, num_bins)
+
+    @property
+    def code_length(self) -> int:
+        return FRAME // int(np.prod(self.the_strides))
+
+    def to_struct(self) -> _lib.CodecCfgStruct:
+        b = self.bottleneck_kernel_and_dilation
+        if len(b) < 5:
+            raise ValueError("bottleneck_kernel_and_dilation needs at least 5 entries")
+        if len(b) - 4 > _lib.MAX_BLOCKS or len(self.the_strides) > _lib.MAX_STRIDES:
+            raise ValueError("too many blocks / strides")
+        s = _lib.CodecCfgStruct()
+        s.k_dilated, s.k_plain, s.wide, s.narrow = b[0], b[1], b[2], b[3]
+        s.n_blocks = len(b) - 4
+        for i, d in enumerate(b[4:]):
+            s.dilations[i] = d
+        s.n_strides = len(self.the_strides)
+        for i, v in enumerate(self.the_strides):
+            s.strides[i] = v
+        if self.resnet_type not in ('bottleneck', 'gln'):
+            raise ValueError("resnet_type must be 'bottleneck' or 'gln'")
+        s.resnet_type = 0 if self.resnet_type == 'bottleneck' else 1
+        s.num_bins = self.num_bins
+        return s
+
+
+@dataclass
+class LayerSpec:
+    k: int
+    cin: int
+    cout: int
+    separable: bool
+    offset: int
+
+
+def layer_table(cfg: CodecConfig) -> List[LayerSpec]:
+    """Conv layers of one codec in TF creation order with their offsets in the flat parameter image."""
+    lib = _lib.load()
+    st = cfg.to_struct()
+    n = lib.nsc_codec_layer_info(C.byref(st), -1, None, None, None, None, None)
+    if n < 0:
+        _lib.check(-1, 'layer_table')
+    out = []
+    k, cin, cout, sep, off = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    for i in range(n):
+        lib.nsc_codec_layer_info(C.byref(st), i, C.byref(k), C.byref(cin), C.byref(cout), C.byref(sep), C.byref(off))
+        out.append(LayerSpec(k.value, cin.value, cout.value, bool(sep.value), off.value))
+    return out
+
+
+def param_count(cfg: CodecConfig) -> int:
+    st = cfg.to_struct()
+    n = _lib.load().nsc_codec_param_count(C.byref(st))
+    if n < 0:
+        _lib.check(-1, 'param_count')
+    return int(n)
+
+
+def init_params_numpy(cfg: CodecConfig, seed: int = 0, zero_bias: bool = True) -> np.ndarray:
+    """Flat parameter image initialised the way TF would: Glorot-uniform kernels, zero biases [LIB],
+    alpha = init_alpha (constants.py:5), bins = linspace(-1, 1, n) (nscm.py:269, :308)."""
+    rng = np.random.RandomState(seed)
+    flat = np.zeros(param_count(cfg), dtype=np.float32)
+
+    def glorot(shape, fan_in, fan_out):
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+    for L in layer_table(cfg):
+        o = L.offset
+        if L.separable:
+            dw = glorot((L.k, L.cin, 1), L.k * L.cin, L.k)
+            pw = glorot((1, L.cin, L.cout), L.cin, L.cout)
+            flat[o:o + dw.size] = dw.ravel(); o += dw.size
+            flat[o:o + pw.size] = pw.ravel(); o += pw.size
+        else:
+            w = glorot((L.k, L.cin, L.cout), L.k * L.cin, L.k * L.cout)
+            flat[o:o + w.size] = w.ravel(); o += w.size
+        if not zero_bias:
+            flat[o:o + L.cout] = rng.uniform(-0.05, 0.05, size=L.cout).astype(np.float32)
+    n = cfg.num_bins
+    flat[-(n + 1)] = np.float32(_c.init_alpha)
+    flat[-n:] = np.linspace(-_c.beta_boundary, _c.beta_boundary, n).astype(np.float32)
+    return flat
+
+
+def pack_params_numpy(cfg: CodecConfig, conv_params: Sequence[Sequence[np.ndarray]], alpha, bins) -> np.ndarray:
+    """Packs per-layer arrays (TF creation order: (kernel, bias) or (dw, pw, bias)) into the flat image."""
+    table = layer_table(cfg)
+    if len(conv_params) != len(table):
+        raise ValueError(f"expected {len(table)} conv layers, got {len(conv_params)}")
+    flat = np.zeros(param_count(cfg), dtype=np.float32)
+    for L, arrs in zip(table, conv_params):
+        o = L.offset
+        shapes = [(L.k, L.cin, 1), (1, L.cin, L.cout), (L.cout,)] if L.separable else [(L.k, L.cin, L.cout), (L.cout,)]
+        if len(arrs) != len(shapes):
+            raise ValueError("separable / dense mismatch")
+        for a, shp in zip(arrs, shapes):
+            a = np.asarray(a, dtype=np.float32)
+            if a.shape != shp:
+                raise ValueError(f"layer shape {a.shape} != {shp}")
+            flat[o:o + a.size] = a.ravel()
+            o += a.size
+    n = cfg.num_bins
+    flat[-(n + 1)] = np.float32(alpha)
+    flat[-n:] = np.asarray(bins, dtype=np.float32)
+    return flat
+
+
+class NeuralCodec:
+    """One `scope_k` of the reference graph on one GPU: flat parameters + the fused forward."""
+
+    def __init__(self, cfg: CodecConfig, params: Optional[torch.Tensor] = None, device='cuda', seed: int = 0):
+        self.cfg = cfg
+        self._st = cfg.to_struct()
+        self.n_params = param_count(cfg)
+        if params is None:
+            params = torch.from_numpy(init_params_numpy(cfg, seed)).to(device)
+        if params.dtype != torch.float32 or params.numel() != self.n_params or not params.is_cuda:
+            raise ValueError("params must be a float32 CUDA tensor of nsc_codec_param_count elements")
+        self.params = params.contiguous()
+        self._ws: Optional[torch.Tensor] = None
+
+    # views into the flat image ---------------------------------------------------------------
+    @property
+    def alpha(self) -> torch.Tensor:
+        return self.params[-(self.cfg.num_bins + 1)]
+
+    @property
+    def bins(self) -> torch.Tensor:
+        return self.params[-self.cfg.num_bins:]
+
+    def layer_views(self) -> List[Tuple[torch.Tensor, ...]]:
+        out = []
+        for L in layer_table(self.cfg):
+            o = L.offset
+            if L.separable:
+                dw = self.params[o:o + L.k * L.cin].view(L.k, L.cin, 1); o += L.k * L.cin
+                pw = self.params[o:o + L.cin * L.cout].view(1, L.cin, L.cout); o += L.cin * L.cout
+                out.append((dw, pw, self.params[o:o + L.cout]))
+            else:
+                w = self.params[o:o + L.k * L.cin * L.cout].view(L.k, L.cin, L.cout); o += L.k * L.cin * L.cout
+                out.append((w, self.params[o:o + L.cout]))
+        return out
+
+    def _workspace(self, B: int) -> torch.Tensor:
+        need = int(_lib.load().nsc_codec_workspace_bytes(C.byref(self._st), B))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
+        return self._ws
+
+    # nscm.py:262-335 -------------------------------------------------------------------------
+    def computational_graph_end2end_quan_on(self, encoded, the_share, is_quan_on, *, want_soft=False,
+                                            want_stats=False) -> Dict[str, torch.Tensor]:
+        """x (B,512,1) or (B,512) -> dict with
+             'out' (B,512)                the decoder output          (expand_back[:, :, 0])
+             'floating_code' (B,Lc)       encoder output before quantisation
+             'code' (B,Lc)                the_final_code for ALL frames (the reference returns frame 0 only)
+             'idx' (B,Lc) uint8           the implicit integer code
+             'soft' (B,Lc,n)              only when want_soft (the reference always materialises it)
+             'hist' (n,), 'qloss' (B,)    only when want_stats: soft histogram / quan_loss from the same kernel
+        """
+        x = _lib.require_f32(encoded, 'encoded').reshape(-1, FRAME)
+        B, Lc, n, dev = x.shape[0], self.cfg.code_length, self.cfg.num_bins, x.device
+        r = {
+            'out': torch.empty((B, FRAME), dtype=torch.float32, device=dev),
+            'floating_code': torch.empty((B, Lc), dtype=torch.float32, device=dev),
+            'code': torch.empty((B, Lc), dtype=torch.float32, device=dev),
+            'idx': torch.empty((B, Lc), dtype=torch.uint8, device=dev),
+        }
+        if want_soft:
+            r['soft'] = torch.empty((B, Lc, n), dtype=torch.float32, device=dev)
+        if want_stats:
+            r['hist'] = torch.zeros(n, dtype=torch.float32, device=dev)
+            r['qloss'] = torch.empty(B, dtype=torch.float32, device=dev)
+        ws = self._workspace(B)
+        rc = _lib.load().nsc_codec_forward(C.byref(self._st), _lib.ptr(self.params), _lib.ptr(x), B, float(is_quan_on),
+                                           int(bool(the_share)), _lib.ptr(r['floating_code']), _lib.ptr(r['idx']),
+                                           _lib.ptr(r['code']), _lib.ptr(r['out']), _lib.ptr(r.get('soft')),
+                                           _lib.ptr(r.get('hist')), _lib.ptr(r.get('qloss')), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr())
+        _lib.check(rc, 'computational_graph_end2end_quan_on')
+        return r
+
+    computational_graph_end2end_quan_on_lpc = computational_graph_end2end_quan_on   # nscm.py:297-335, same dataflow
+
+    def encode(self, x, the_share=False, is_quan_on=1.0) -> Dict[str, torch.Tensor]:
+        """_the_encoder_in_each_module + quantiser: x (B,512) -> idx (B,Lc) uint8, code, floating_code."""
+        x = _lib.require_f32(x, 'x').reshape(-1, FRAME)
+        B, Lc, dev = x.shape[0], self.cfg.code_length, x.device
+        r = {'floating_code': torch.empty((B, Lc), dtype=torch.float32, device=dev),
+             'code': torch.empty((B, Lc), dtype=torch.float32, device=dev),
+             'idx': torch.empty((B, Lc), dtype=torch.uint8, device=dev)}
+        ws = self._workspace(B)
+        rc = _lib.load().nsc_codec_encode(C.byref(self._st), _lib.ptr(self.params), _lib.ptr(x), B, float(is_quan_on),
+                                          int(bool(the_share)), _lib.ptr(r['floating_code']), _lib.ptr(r['idx']),
+                                          _lib.ptr(r['code']), None, None, None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, 'encode')
+        return r
+
+    def decode_indices(self, idx) -> torch.Tensor:
+        """Hard codes (B,Lc) uint8 -> decoder output (B,512): bins[idx] then _the_decoder_in_each_module."""
+        if idx.dtype != torch.uint8:
+            raise ValueError("idx must be uint8")
+        idx = idx.contiguous()
+        B = idx.shape[0]
+        code = torch.empty(idx.shape, dtype=torch.float32, device=idx.device)
+        lib = _lib.load()
+        _lib.check(lib.nsc_dequantize_scalar(_lib.ptr(idx), idx.numel(), _lib.ptr(self.bins.contiguous()), self.cfg.num_bins,
+                                             _lib.ptr(code), _lib.stream_ptr()), 'dequantize')
+        return self.decode(code)
+
+    def decode(self, code) -> torch.Tensor:
+        code = _lib.require_f32(code, 'code').reshape(-1, self.cfg.code_length)
+        B = code.shape[0]
+        out = torch.empty((B, FRAME), dtype=torch.float32, device=code.device)
+        ws = self._workspace(B)
+        rc = _lib.load().nsc_codec_decode(C.byref(self._st), _lib.ptr(self.params), _lib.ptr(code), B, _lib.ptr(out),
+                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, 'decode')
+        return out
+
+
+class CMRL:
+    """Cascade of codecs (cmrl.py class CMRL) -- feed-forward dataflow only."""
+
+    def __init__(self, codecs: Sequence[NeuralCodec], res_scalar: float = 1.0,
+                 lsf_alpha: Optional[float] = None, lsf_bins: Optional[np.ndarray] = None):
+        if not 1 <= len(codecs) <= _lib.MAX_CODECS:
+            raise ValueError("1..8 codecs")
+        self.codecs = list(codecs)
+        self.res_scalar = float(res_scalar)
+        dev = self.codecs[0].params.device
+        # `lpc_quan` scope (cmrl.py:778-781): alpha then the 256 LSF bins, one flat buffer
+        a = _c.init_alpha if lsf_alpha is None else lsf_alpha
+        b = np.asarray(_c.lpc_coeff_lsf_bins if lsf_bins is None else lsf_bins, dtype=np.float32)
+        self.lsf_params = torch.from_numpy(np.concatenate([[np.float32(a)], b]).astype(np.float32)).to(dev)
+        self._cfgs = (_lib.CodecCfgStruct * len(self.codecs))(*[c.cfg.to_struct() for c in self.codecs])
+        self._ws: Optional[torch.Tensor] = None
+
+    @property
+    def n_lsf_bins(self) -> int:
+        return self.lsf_params.numel() - 1
+
+    def _workspace(self, B: int, cq: bool) -> torch.Tensor:
+        lib = _lib.load()
+        fn = lib.nsc_cq_workspace_bytes if cq else lib.nsc_cascade_workspace_bytes
+        need = int(fn(self._cfgs, len(self.codecs), B))
+        if need < 0:
+            _lib.check(-1, 'workspace')
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.lsf_params.device)
+        return self._ws
+
+    def _per_codec_outputs(self, B, dev, want_stats, want_outs):
+        idx = [torch.empty((B, c.cfg.code_length), dtype=torch.uint8, device=dev) for c in self.codecs]
+        hist = [torch.zeros(c.cfg.num_bins, dtype=torch.float32, device=dev) for c in self.codecs] if want_stats else None
+        qloss = [torch.empty(B, dtype=torch.float32, device=dev) for _ in self.codecs] if want_stats else None
+        outs = [torch.empty((B, FRAME), dtype=torch.float32, device=dev) for _ in self.codecs] if want_outs else None
+        return idx, hist, qloss, outs
+
+    # cmrl.py:513-543 -----------------------------------------------------------------------------
+    def all_modules_feedforward(self, x, the_share=False, is_quan_on=1.0, *, lpc_variant=False, want_stats=False,
+                                want_outs=False) -> Dict[str, object]:
+        """x (B,512[,1]) -> 'decoded' (B,512) = sum_i out_i, 'idx' [ (B,Lc) uint8 per codec ], optional
+        'hist'/'qloss' per codec and 'outs' (the residual_coding_x list)."""
+        x = _lib.require_f32(x, 'x').reshape(-1, FRAME)
+        B, dev = x.shape[0], x.device
+        idx, hist, qloss, outs = self._per_codec_outputs(B, dev, want_stats, want_outs)
+        decoded = torch.empty((B, FRAME), dtype=torch.float32, device=dev)
+        ws = self._workspace(B, False)
+        rc = _lib.load().nsc_cascade_forward(
+            self._cfgs, len(self.codecs), _lib.ptr_array([c.params for c in self.codecs]), _lib.ptr(x), B,
+            self.res_scalar, int(bool(lpc_variant)), float(is_quan_on), int(bool(the_share)), _lib.ptr_array(idx),
+            _lib.ptr_array(hist), _lib.ptr_array(qloss), _lib.ptr_array(outs), _lib.ptr(decoded), _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, 'all_modules_feedforward')
+        return {'decoded': decoded, 'idx': idx, 'hist': hist, 'qloss': qloss, 'outs': outs}
+
+    # cmrl.py:770-858 -----------------------------------------------------------------------------
+    def feedforward_lpc(self, x, lpc_x, the_share=False, is_quan_on=1.0, *, want_stats=False) -> Dict[str, object]:
+        """Collaborative-quantisation pass: x (B,512[,1]) frames, lpc_x (B,16[,1]) LSFs ->
+        'lsf_idx' (B,16) uint8, 'poly' (B,17), 'res_x' (B,512), 'decoded' (B,512) (residual domain),
+        'synthesized' (B,512), 'idx' per codec; optional soft histograms / quan losses."""
+        x = _lib.require_f32(x, 'x').reshape(-1, FRAME)
+        lsf = _lib.require_f32(lpc_x, 'lpc_x').reshape(-1, _lib.LPC_ORDER)
+        B, dev = x.shape[0], x.device
+        if lsf.shape[0] != B:
+            raise ValueError("x / lpc_x batch mismatch")
+        idx, hist, qloss, _ = self._per_codec_outputs(B, dev, want_stats, False)
+        r = {
+            'lsf_idx': torch.empty((B, _lib.LPC_ORDER), dtype=torch.uint8, device=dev),
+            'poly': torch.empty((B, _lib.LPC_ORDER + 1), dtype=torch.float32, device=dev),
+            'res_x': torch.empty((B, FRAME), dtype=torch.float32, device=dev),
+            'decoded': torch.empty((B, FRAME), dtype=torch.float32, device=dev),
+            'synthesized': torch.empty((B, FRAME), dtype=torch.float32, device=dev),
+            'idx': idx, 'hist': hist, 'qloss': qloss,
+        }
+        if want_stats:
+            r['lsf_hist'] = torch.zeros(self.n_lsf_bins, dtype=torch.float32, device=dev)
+            r['lsf_qloss'] = torch.empty(B, dtype=torch.float32, device=dev)
+        ws = self._workspace(B, True)
+        rc = _lib.load().nsc_cq_forward(
+            self._cfgs, len(self.codecs), _lib.ptr_array([c.params for c in self.codecs]), _lib.ptr(self.lsf_params),
+            self.n_lsf_bins, _lib.ptr(x), _lib.ptr(lsf), B, self.res_scalar, float(is_quan_on), int(bool(the_share)),
+            _lib.ptr(r['lsf_idx']), _lib.ptr(r.get('lsf_hist')), _lib.ptr(r.get('lsf_qloss')), _lib.ptr_array(idx),
+            _lib.ptr_array(hist), _lib.ptr_array(qloss), _lib.ptr(r['poly']), _lib.ptr(r['res_x']), _lib.ptr(r['decoded']),
+            _lib.ptr(r['synthesized']), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, 'feedforward_lpc')
+        return r
+
+    all_modules_feedforward_lpc = feedforward_lpc

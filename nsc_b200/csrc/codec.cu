@@ -1,0 +1,548 @@
+// K6 (host side) -- one neural codec (neural_speech_coding_module.py:152-335), the CMRL cascade
+// (cmrl.py:513-543, :806-830) and the collaborative-quantisation feed-forward (cmrl.py:770-858) as a stream of
+// kernel launches.  The topology is written ONCE (struct Walker): a dry walk enumerates the conv layers in the
+// order TensorFlow would create their variables -- which defines the flat parameter image -- and the live walk
+// issues the launches.  Frames are processed in chunks so the activation workspace stays bounded.
+#include <vector>
+
+#include "conv.cuh"
+
+namespace nsc {
+
+namespace {
+
+constexpr int kFrameLen = NSC_FRAME_LENGTH;
+constexpr int64_t kChunkFrames = 2048;   // frames per internal pass (bounds the activation workspace)
+
+struct LayerInfo {
+  int k, cin, cout, separable;
+  int64_t off;  // first float of the layer inside the flat parameter image
+};
+
+int validate_cfg(const nsc_codec_cfg* c) {
+  NSC_CHECK_ARG(c != nullptr, "codec cfg is null");
+  NSC_CHECK_ARG(c->wide >= 1 && c->narrow >= 1 && c->k_plain >= 1 && c->k_dilated >= 1, "codec cfg: bad sizes");
+  NSC_CHECK_ARG(c->n_blocks >= 1 && c->n_blocks <= NSC_MAX_BLOCKS, "codec cfg: n_blocks=%d", c->n_blocks);
+  NSC_CHECK_ARG(c->n_strides >= 1 && c->n_strides <= NSC_MAX_STRIDES, "codec cfg: n_strides=%d", c->n_strides);
+  NSC_CHECK_ARG(c->resnet_type == 0 || c->resnet_type == 1, "codec cfg: resnet_type=%d", c->resnet_type);
+  NSC_CHECK_ARG(c->num_bins >= 1 && c->num_bins <= 256, "codec cfg: num_bins=%d", c->num_bins);
+  int L = kFrameLen, C = c->wide;
+  for (int i = 0; i < c->n_strides; ++i) {
+    NSC_CHECK_ARG(c->strides[i] >= 1 && L % c->strides[i] == 0, "codec cfg: stride %d does not divide %d", c->strides[i], L);
+    L /= c->strides[i];
+  }
+  for (int i = 0; i < c->n_strides; ++i) {
+    NSC_CHECK_ARG(C % c->strides[i] == 0, "codec cfg: decoder channels %d not divisible by stride %d", C, c->strides[i]);
+    C /= c->strides[i];
+  }
+  for (int i = 0; i < c->n_blocks; ++i) NSC_CHECK_ARG(c->dilations[i] >= 1, "codec cfg: dilation[%d]=%d", i, c->dilations[i]);
+  return NSC_OK;
+}
+
+int code_length(const nsc_codec_cfg& c) {
+  int L = kFrameLen;
+  for (int i = 0; i < c.n_strides; ++i) L /= c.strides[i];
+  return L;
+}
+
+struct Walker {
+  nsc_codec_cfg cfg;
+  bool dry = true;
+  const float* params = nullptr;
+  int64_t B = 0;
+  cudaStream_t st = nullptr;
+  std::vector<LayerInfo> layers;
+  size_t cursor = 0;
+  int64_t off = 0;
+  float* wide[3] = {nullptr, nullptr, nullptr};
+  float* nar[3] = {nullptr, nullptr, nullptr};
+  int rc = NSC_OK;
+
+  const LayerInfo* next_layer(int k, int cin, int cout, int separable) {
+    if (dry) {
+      LayerInfo li{k, cin, cout, separable, off};
+      off += separable ? ((int64_t)k * cin + (int64_t)cin * cout + cout) : ((int64_t)k * cin * cout + cout);
+      layers.push_back(li);
+      return nullptr;
+    }
+    const LayerInfo* li = &layers[cursor++];
+    if (li->k != k || li->cin != cin || li->cout != cout || li->separable != separable) {
+      set_error("internal: layer table mismatch at %zu", cursor - 1);
+      rc = NSC_E_INVALID;
+    }
+    return li;
+  }
+
+  void conv(const float* x, float* y, int Lin, int Cin, int Cout, int K, int dil, int stride, int act,
+            const float* res = nullptr, int res_mode = RES_NONE, int post_act = NSC_ACT_NONE, int shuffle = 1) {
+    const LayerInfo* li = next_layer(K, Cin, Cout, 0);
+    if (dry || rc != NSC_OK) return;
+    ConvArgs a;
+    a.x = x; a.y = y;
+    a.w = params + li->off;
+    a.bias = a.w + (int64_t)K * Cin * Cout;
+    a.res = res; a.res_mode = res_mode; a.post_act = post_act; a.shuffle = shuffle;
+    a.B = B; a.Lin = Lin; a.Cin = Cin; a.Cout = Cout; a.K = K; a.dil = dil; a.stride = stride; a.act = act;
+    rc = launch_conv(a, st);
+  }
+
+  // Keras SeparableConv1D: depthwise (k, cin, 1) -> pointwise (1, cin, cout) + bias + activation
+  void sepconv(const float* x, float* tmp, float* y, int Lin, int Cin, int Cout, int K, int act, int shuffle) {
+    const LayerInfo* li = next_layer(K, Cin, Cout, 1);
+    if (dry || rc != NSC_OK) return;
+    const float* dw = params + li->off;
+    const float* pw = dw + (int64_t)K * Cin;
+    const float* bias = pw + (int64_t)Cin * Cout;
+    rc = launch_depthwise(x, dw, tmp, B, Lin, Cin, K, 1, 1, 0, 0, st);
+    if (rc != NSC_OK) return;
+    ConvArgs a;
+    a.x = tmp; a.y = y; a.w = pw; a.bias = bias;
+    a.B = B; a.Lin = Lin; a.Cin = Cin; a.Cout = Cout; a.K = 1; a.act = act; a.shuffle = shuffle;
+    rc = launch_conv(a, st);
+  }
+
+  // _stack_bottleneck_blocks (nscm.py:183-217).  `in` lives in wide[in_idx] or is external (in_idx = -1).
+  int stack(const float* in, int in_idx, int& C, int L) {
+    const int wide_layer = (C == 1) ? cfg.wide : C;   // nscm.py:189-192 (is_post_up_samling is always False)
+    const float* cur = in;
+    int cur_idx = in_idx;
+    for (int i = 0; i < cfg.n_blocks; ++i) {
+      const bool flat = (i == cfg.n_blocks - 1);     // `flag`, nscm.py:196
+      const int out_idx = cur_idx < 0 ? 0 : (cur_idx + 1) % 3;
+      float* out = wide[out_idx];
+      const int d = cfg.dilations[i];
+      const int rmode = (C == wide_layer) ? RES_ADD : RES_ADD_BCAST;  // 1-channel input broadcasts (:77)
+      const int post = flat ? NSC_ACT_NONE : NSC_ACT_LRELU;
+      if (cfg.resnet_type == 0) {   // the_bottleneck, nn_core_operator.py:57-79
+        conv(cur, nar[0], L, C, cfg.narrow, cfg.k_plain, 1, 1, NSC_ACT_LRELU);
+        conv(nar[0], nar[1], L, cfg.narrow, cfg.narrow, cfg.k_dilated, d, 1, NSC_ACT_LRELU);
+        conv(nar[1], out, L, cfg.narrow, wide_layer, cfg.k_plain, 1, 1, NSC_ACT_NONE, cur, rmode, post);
+      } else {                      // gated_bottleneck, nn_core_operator.py:82-112 (gate kernel 15 hard-coded)
+        conv(cur, nar[0], L, C, cfg.narrow, 1, 1, 1, NSC_ACT_LRELU);
+        conv(nar[0], nar[1], L, cfg.narrow, cfg.narrow, 15, d, 1, NSC_ACT_NONE);
+        conv(nar[0], nar[2], L, cfg.narrow, cfg.narrow, 15, d, 1, NSC_ACT_TANH, nar[1], RES_MUL);
+        conv(nar[2], out, L, cfg.narrow, wide_layer, cfg.k_plain, 1, 1, NSC_ACT_NONE, cur, rmode, post);
+      }
+      cur = out;
+      cur_idx = out_idx;
+      C = wide_layer;
+    }
+    return cur_idx;
+  }
+
+  // _the_encoder_in_each_module (nscm.py:219-237): x (B,512) -> floating code (B,Lc), tanh
+  void encoder(const float* x, float* fcode) {
+    int L = kFrameLen, C = cfg.wide;
+    conv(x, wide[0], L, 1, cfg.wide, 55, 1, 1, NSC_ACT_LRELU);
+    int cur = 0;
+    for (int s = 0; s < cfg.n_strides; ++s) {
+      cur = stack(wide[cur], cur, C, L);
+      const int o = (cur + 1) % 3;
+      conv(wide[cur], wide[o], L, C, cfg.wide, 9, 1, cfg.strides[s], NSC_ACT_LRELU);   // _down_sampling_mod :152-156
+      cur = o;
+      C = cfg.wide;
+      L = (L + cfg.strides[s] - 1) / cfg.strides[s];
+    }
+    cur = stack(wide[cur], cur, C, L);
+    conv(wide[cur], fcode, L, C, 1, 55, 1, 1, NSC_ACT_TANH);
+  }
+
+  // _the_decoder_in_each_module (nscm.py:239-260): code (B,Lc) -> out (B,512)
+  void decoder(const float* code, float* out) {
+    int L = code_length(cfg), C = 1;
+    const float* in = code;
+    int cur = -1;
+    for (int s = 0; s < cfg.n_strides; ++s) {
+      cur = stack(in, cur, C, L);
+      const int o = (cur + 1) % 3, t = (cur + 2) % 3;
+      const int r = cfg.strides[s];
+      if (cfg.resnet_type == 0) conv(wide[cur], wide[o], L, C, C, 9, 1, 1, NSC_ACT_LRELU, nullptr, RES_NONE, NSC_ACT_NONE, r);
+      else sepconv(wide[cur], wide[t], wide[o], L, C, C, 9, NSC_ACT_LRELU, r);   // _up_sampling_mod :169-181
+      cur = o;
+      in = wide[cur];
+      C /= r;
+      L *= r;
+    }
+    cur = stack(in, cur, C, L);
+    conv(wide[cur], out, L, C, 1, 55, 1, 1, NSC_ACT_NONE);
+  }
+};
+
+struct CodecLayout {
+  std::vector<LayerInfo> layers;
+  int64_t conv_floats = 0;   // alpha sits at conv_floats, bins at conv_floats + 1
+  int code_len = 0;
+};
+
+CodecLayout make_layout(const nsc_codec_cfg& cfg) {
+  Walker w;
+  w.cfg = cfg;
+  w.dry = true;
+  w.encoder(nullptr, nullptr);
+  w.decoder(nullptr, nullptr);
+  CodecLayout l;
+  l.layers = w.layers;
+  l.conv_floats = w.off;
+  l.code_len = code_length(cfg);
+  return l;
+}
+
+// ---- workspace carving -------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  int64_t used = 0, cap;
+  Carver(void* p, int64_t c) : base(static_cast<char*>(p)), cap(c) {}
+  float* take(int64_t floats) {
+    const int64_t bytes = align_up(floats * (int64_t)sizeof(float), 256);
+    float* r = reinterpret_cast<float*>(base + used);
+    used += bytes;
+    return r;
+  }
+};
+
+int64_t codec_ws_floats_per_frame(const nsc_codec_cfg& c) {
+  return 3LL * c.wide * kFrameLen + 3LL * c.narrow * kFrameLen + 2LL * code_length(c);
+}
+
+int64_t codec_ws_bytes(const nsc_codec_cfg& c, int64_t Bc) {
+  // 8 carved buffers, each rounded up to 256 bytes
+  return codec_ws_floats_per_frame(c) * Bc * (int64_t)sizeof(float) + 8 * 256;
+}
+
+struct CodecBuffers {
+  float* wide[3];
+  float* nar[3];
+  float* fcode;
+  float* code;
+};
+
+CodecBuffers carve_codec(Carver& cv, const nsc_codec_cfg& c, int64_t Bc) {
+  CodecBuffers b;
+  for (int i = 0; i < 3; ++i) b.wide[i] = cv.take(Bc * c.wide * kFrameLen);
+  for (int i = 0; i < 3; ++i) b.nar[i] = cv.take(Bc * c.narrow * kFrameLen);
+  b.fcode = cv.take(Bc * code_length(c));
+  b.code = cv.take(Bc * code_length(c));
+  return b;
+}
+
+// one chunk of frames through one codec; any of fcode/idx/code/soft/hist/qloss may be null.
+// which: bit0 = encoder+quantiser, bit1 = decoder
+int run_codec_chunk(const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* params, const CodecBuffers& buf,
+                    const float* x, int64_t Bc, float iq, int use_soft, float* fcode, uint8_t* idx, float* code,
+                    float* out, float* soft, float* hist, float* qloss, int which, cudaStream_t st) {
+  Walker w;
+  w.cfg = cfg;
+  w.dry = false;
+  w.params = params;
+  w.B = Bc;
+  w.st = st;
+  w.layers = lay.layers;
+  for (int i = 0; i < 3; ++i) { w.wide[i] = buf.wide[i]; w.nar[i] = buf.nar[i]; }
+  float* fc = fcode ? fcode : buf.fcode;
+  float* cd = code ? code : buf.code;
+  if (which & 1) {
+    w.encoder(x, fc);
+    NSC_TRY(w.rc);
+    const float* alpha = params + lay.conv_floats;
+    const float* bins = alpha + 1;
+    NSC_TRY(launch_quantize(fc, Bc, lay.code_len, bins, cfg.num_bins, alpha, iq, use_soft, cd, idx, soft, hist, qloss, st));
+  } else {
+    // skip the encoder's layers in the table
+    Walker d;
+    d.cfg = cfg;
+    d.dry = true;
+    d.encoder(nullptr, nullptr);
+    w.cursor = d.layers.size();
+  }
+  if (which & 2) {
+    w.decoder(cd, out);
+    NSC_TRY(w.rc);
+  }
+  return NSC_OK;
+}
+
+}  // namespace
+}  // namespace nsc
+
+using nsc::kChunkFrames;
+using nsc::kFrameLen;
+
+extern "C" {
+
+int64_t nsc_codec_param_count(const nsc_codec_cfg* cfg) {
+  if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
+  return nsc::make_layout(*cfg).conv_floats + 1 + cfg->num_bins;
+}
+
+int32_t nsc_codec_layer_info(const nsc_codec_cfg* cfg, int32_t i, int32_t* k, int32_t* cin, int32_t* cout,
+                             int32_t* separable, int64_t* offset) {
+  if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
+  nsc::CodecLayout l = nsc::make_layout(*cfg);
+  if (i < 0) return (int32_t)l.layers.size();
+  if (i >= (int32_t)l.layers.size()) {
+    nsc::set_error("nsc_codec_layer_info: layer %d out of range (%zu)", i, l.layers.size());
+    return -1;
+  }
+  if (k) *k = l.layers[i].k;
+  if (cin) *cin = l.layers[i].cin;
+  if (cout) *cout = l.layers[i].cout;
+  if (separable) *separable = l.layers[i].separable;
+  if (offset) *offset = l.layers[i].off;
+  return (int32_t)l.layers.size();
+}
+
+int64_t nsc_codec_workspace_bytes(const nsc_codec_cfg* cfg, int64_t B) {
+  if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
+  const int64_t Bc = B < kChunkFrames ? (B < 1 ? 1 : B) : kChunkFrames;
+  return nsc::codec_ws_bytes(*cfg, Bc);
+}
+
+static int codec_run(const nsc_codec_cfg* cfg, const float* params, const float* x, const float* code_in, int64_t B,
+                     float iq, int32_t use_soft, float* fcode, uint8_t* idx, float* code, float* out, float* soft,
+                     float* hist, float* qloss, void* workspace, int64_t workspace_bytes, void* stream, int which) {
+  NSC_TRY(nsc::validate_cfg(cfg));
+  NSC_CHECK_ARG(params != nullptr && workspace != nullptr, "codec: null params/workspace");
+  NSC_CHECK_ARG(B >= 0, "codec: negative batch");
+  if (B == 0) return NSC_OK;
+  const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
+  if (workspace_bytes < nsc::codec_ws_bytes(*cfg, Bc)) {
+    nsc::set_error("codec: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)nsc::codec_ws_bytes(*cfg, Bc));
+    return NSC_E_WORKSPACE;
+  }
+  const nsc::CodecLayout lay = nsc::make_layout(*cfg);
+  const int Lc = lay.code_len, n = cfg->num_bins;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
+    nsc::Carver cv(workspace, workspace_bytes);
+    nsc::CodecBuffers buf = nsc::carve_codec(cv, *cfg, Bc);
+    const float* code_src = code_in ? code_in + b0 * Lc : nullptr;
+    float* code_dst = code ? code + b0 * Lc : nullptr;
+    if (which == 2) {
+      // decoder only: the code comes from the caller
+      NSC_TRY(nsc::run_codec_chunk(*cfg, lay, params, buf, nullptr, nb, iq, use_soft, nullptr, nullptr,
+                                   const_cast<float*>(code_src), out + b0 * kFrameLen, nullptr, nullptr, nullptr, 2, st));
+    } else {
+      NSC_TRY(nsc::run_codec_chunk(*cfg, lay, params, buf, x + b0 * kFrameLen, nb, iq, use_soft,
+                                   fcode ? fcode + b0 * Lc : nullptr, idx ? idx + b0 * Lc : nullptr, code_dst,
+                                   out ? out + b0 * kFrameLen : nullptr, soft ? soft + b0 * Lc * n : nullptr, hist,
+                                   qloss ? qloss + b0 : nullptr, which, st));
+    }
+  }
+  return NSC_OK;
+}
+
+int nsc_codec_forward(const nsc_codec_cfg* cfg, const float* params, const float* x, int64_t B, float is_quan_on,
+                      int32_t use_soft, float* floating_code, uint8_t* idx, float* code, float* out, float* soft,
+                      float* hist, float* qloss, void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_CHECK_ARG(x != nullptr && out != nullptr, "nsc_codec_forward: null x/out");
+  return codec_run(cfg, params, x, nullptr, B, is_quan_on, use_soft, floating_code, idx, code, out, soft, hist, qloss,
+                   workspace, workspace_bytes, stream, 3);
+}
+
+int nsc_codec_encode(const nsc_codec_cfg* cfg, const float* params, const float* x, int64_t B, float is_quan_on,
+                     int32_t use_soft, float* floating_code, uint8_t* idx, float* code, float* soft, float* hist,
+                     float* qloss, void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_CHECK_ARG(x != nullptr, "nsc_codec_encode: null x");
+  return codec_run(cfg, params, x, nullptr, B, is_quan_on, use_soft, floating_code, idx, code, nullptr, soft, hist,
+                   qloss, workspace, workspace_bytes, stream, 1);
+}
+
+int nsc_codec_decode(const nsc_codec_cfg* cfg, const float* params, const float* code, int64_t B, float* out,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_CHECK_ARG(code != nullptr && out != nullptr, "nsc_codec_decode: null code/out");
+  return codec_run(cfg, params, nullptr, code, B, 1.0f, 0, nullptr, nullptr, nullptr, out, nullptr, nullptr, nullptr,
+                   workspace, workspace_bytes, stream, 2);
+}
+
+// ---- cascade -------------------------------------------------------------------------------------
+static int64_t cascade_ws_bytes(const nsc_codec_cfg* cfgs, int32_t n, int64_t Bc) {
+  int64_t worst = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t b = nsc::codec_ws_bytes(cfgs[i], Bc);
+    if (b > worst) worst = b;
+  }
+  // + codec input, codec output (pre-division)
+  return worst + 2 * (Bc * kFrameLen * (int64_t)sizeof(float) + 256);
+}
+
+int64_t nsc_cascade_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B) {
+  if (cfgs == nullptr || n_codecs < 1 || n_codecs > NSC_MAX_CODECS) return -1;
+  for (int i = 0; i < n_codecs; ++i)
+    if (nsc::validate_cfg(&cfgs[i]) != NSC_OK) return -1;
+  const int64_t Bc = B < kChunkFrames ? (B < 1 ? 1 : B) : kChunkFrames;
+  return cascade_ws_bytes(cfgs, n_codecs, Bc);
+}
+
+// one chunk of the cascade; decoded (Bc,512) is also the running sum of the codec outputs
+static int cascade_chunk(const nsc_codec_cfg* cfgs, const nsc::CodecLayout* lays, int32_t n,
+                         const float* const* params, const float* x, int64_t b0, int64_t nb, int64_t Bc,
+                         float res_scalar, int lpc_variant, float iq, int use_soft, uint8_t* const* idx,
+                         float* const* hist, float* const* qloss, float* const* outs, float* decoded,
+                         void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const int64_t nfl = nb * kFrameLen;
+  for (int i = 0; i < n; ++i) {
+    nsc::Carver cv(workspace, workspace_bytes);
+    float* cin = cv.take(Bc * kFrameLen);
+    float* cout = cv.take(Bc * kFrameLen);
+    nsc::CodecBuffers buf = nsc::carve_codec(cv, cfgs[i], Bc);
+    const float* xin = x;
+    if (i == 0) {
+      if (lpc_variant && res_scalar != 1.0f) {       // res_x * res_scalar, cmrl.py:810
+        NSC_TRY(nsc::launch_axpby(cin, x, res_scalar, nullptr, 0.f, nfl, st));
+        xin = cin;
+      }
+    } else {                                          // res_scalar * (x - sum_{j<i} out_j), cmrl.py:529-531 / :822-823
+      NSC_TRY(nsc::launch_axpby(cin, x, res_scalar, decoded, 1.0f, nfl, st));
+      xin = cin;
+    }
+    const int Lc = lays[i].code_len;
+    NSC_TRY(nsc::run_codec_chunk(cfgs[i], lays[i], params[i], buf, xin, nb, iq, use_soft, nullptr,
+                                 (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, cout, nullptr,
+                                 (hist && hist[i]) ? hist[i] : nullptr, (qloss && qloss[i]) ? qloss[i] + b0 : nullptr, 3, st));
+    const bool divide = (i > 0) || lpc_variant;       // codec 0 of the plain cascade is not divided (cmrl.py:522-528)
+    const float d = divide ? res_scalar : 1.0f;
+    if (outs && outs[i]) NSC_TRY(nsc::launch_div(outs[i] + b0 * kFrameLen, cout, d, nfl, st));
+    NSC_TRY(nsc::launch_accum_div(decoded, cout, d, i == 0 ? 1 : 0, nfl, st));
+  }
+  return NSC_OK;
+}
+
+static int check_cascade_args(const nsc_codec_cfg* cfgs, int32_t n, const float* const* params, const float* x,
+                              float* decoded, void* workspace, float res_scalar) {
+  NSC_CHECK_ARG(cfgs != nullptr && n >= 1 && n <= NSC_MAX_CODECS, "cascade: n_codecs=%d", n);
+  NSC_CHECK_ARG(params != nullptr && x != nullptr && decoded != nullptr && workspace != nullptr, "cascade: null pointer");
+  NSC_CHECK_ARG(res_scalar != 0.0f, "cascade: res_scalar is zero");
+  for (int i = 0; i < n; ++i) {
+    NSC_TRY(nsc::validate_cfg(&cfgs[i]));
+    NSC_CHECK_ARG(params[i] != nullptr, "cascade: params[%d] is null", i);
+  }
+  return NSC_OK;
+}
+
+int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
+                        const float* x, int64_t B, float res_scalar, int32_t lpc_variant, float is_quan_on,
+                        int32_t use_soft, uint8_t* const* idx_ptrs_host, float* const* hist_ptrs_host,
+                        float* const* qloss_ptrs_host, float* const* outs_ptrs_host, float* decoded,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_TRY(check_cascade_args(cfgs, n_codecs, params_ptrs_host, x, decoded, workspace, res_scalar));
+  if (B == 0) return NSC_OK;
+  const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
+  if (workspace_bytes < cascade_ws_bytes(cfgs, n_codecs, Bc)) {
+    nsc::set_error("cascade: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                   (long long)cascade_ws_bytes(cfgs, n_codecs, Bc));
+    return NSC_E_WORKSPACE;
+  }
+  std::vector<nsc::CodecLayout> lays;
+  for (int i = 0; i < n_codecs; ++i) lays.push_back(nsc::make_layout(cfgs[i]));
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
+    NSC_TRY(cascade_chunk(cfgs, lays.data(), n_codecs, params_ptrs_host, x + b0 * kFrameLen, b0, nb, Bc, res_scalar,
+                          lpc_variant, is_quan_on, use_soft, idx_ptrs_host, hist_ptrs_host, qloss_ptrs_host,
+                          outs_ptrs_host, decoded + b0 * kFrameLen, workspace, workspace_bytes, (cudaStream_t)stream));
+  }
+  return NSC_OK;
+}
+
+// ---- collaborative quantisation feed-forward -----------------------------------------------------
+static int64_t cq_extra_bytes(int64_t Bc) {
+  // quantised LSF (16), poly (17), residual (512) per frame
+  return (Bc * NSC_LPC_ORDER + Bc * (NSC_LPC_ORDER + 1) + Bc * kFrameLen) * (int64_t)sizeof(float) + 3 * 256;
+}
+
+int64_t nsc_cq_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B) {
+  const int64_t c = nsc_cascade_workspace_bytes(cfgs, n_codecs, B);
+  if (c < 0) return c;
+  const int64_t Bc = B < kChunkFrames ? (B < 1 ? 1 : B) : kChunkFrames;
+  return c + cq_extra_bytes(Bc);
+}
+
+int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
+                   const float* lsf_params, int32_t n_lsf_bins, const float* x, const float* lsf, int64_t B,
+                   float res_scalar, float is_quan_on, int32_t use_soft, uint8_t* lsf_idx, float* lsf_hist,
+                   float* lsf_qloss, uint8_t* const* idx_ptrs_host, float* const* hist_ptrs_host,
+                   float* const* qloss_ptrs_host, float* poly, float* res_x, float* decoded, float* synthesized,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_TRY(check_cascade_args(cfgs, n_codecs, params_ptrs_host, x, decoded, workspace, res_scalar));
+  NSC_CHECK_ARG(lsf_params != nullptr && lsf != nullptr, "nsc_cq_forward: null LSF input");
+  NSC_CHECK_ARG(n_lsf_bins >= 1 && n_lsf_bins <= 256, "nsc_cq_forward: n_lsf_bins=%d", n_lsf_bins);
+  if (B == 0) return NSC_OK;
+  const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
+  const int64_t need = cascade_ws_bytes(cfgs, n_codecs, Bc) + cq_extra_bytes(Bc);
+  if (workspace_bytes < need) {
+    nsc::set_error("nsc_cq_forward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    return NSC_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<nsc::CodecLayout> lays;
+  for (int i = 0; i < n_codecs; ++i) lays.push_back(nsc::make_layout(cfgs[i]));
+  const int P = NSC_LPC_ORDER;
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
+    nsc::Carver cv(workspace, workspace_bytes);
+    float* qlsf = cv.take(Bc * P);
+    float* poly_ws = cv.take(Bc * (P + 1));
+    float* res_ws = cv.take(Bc * kFrameLen);
+    void* rest = static_cast<char*>(workspace) + cv.used;
+    const int64_t rest_bytes = workspace_bytes - cv.used;
+    float* poly_c = poly ? poly + b0 * (P + 1) : poly_ws;
+    float* res_c = res_x ? res_x + b0 * kFrameLen : res_ws;
+    // LSF codebook: scalar_softmax_quantization(lpc_x, alpha, lpc_bins, ...) cmrl.py:782-788
+    NSC_TRY(nsc::launch_quantize(lsf + b0 * P, nb, P, lsf_params + 1, n_lsf_bins, lsf_params, is_quan_on, use_soft, qlsf,
+                                 lsf_idx ? lsf_idx + b0 * P : nullptr, nullptr, lsf_hist,
+                                 lsf_qloss ? lsf_qloss + b0 : nullptr, st));
+    NSC_TRY(nsc_lsf2poly(qlsf, nb, poly_c, nullptr, stream));                              // cmrl.py:793
+    NSC_TRY(nsc_lpc_residual(x + b0 * kFrameLen, poly_c, nb, res_c, stream));               // cmrl.py:796
+    NSC_TRY(cascade_chunk(cfgs, lays.data(), n_codecs, params_ptrs_host, res_c, b0, nb, Bc, res_scalar, 1, is_quan_on,
+                          use_soft, idx_ptrs_host, hist_ptrs_host, qloss_ptrs_host, nullptr, decoded + b0 * kFrameLen,
+                          rest, rest_bytes, st));
+    if (synthesized)                                                                         // cmrl.py:843
+      NSC_TRY(nsc_lpc_synth(poly_c, decoded + b0 * kFrameLen, nb, synthesized + b0 * kFrameLen, stream));
+  }
+  return NSC_OK;
+}
+
+// ---- single blocks on channels-last tensors (operator surface of nn_core_operator.py) ---------------
+int64_t nsc_block_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t narrow) {
+  (void)wide;
+  return 3 * (nsc::align_up(B * (int64_t)L * narrow * (int64_t)sizeof(float), 256));
+}
+
+int nsc_bottleneck_block(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t Cin,
+                         int32_t wide, int32_t narrow, int32_t k_plain, int32_t k_dilated, int32_t dilation,
+                         int32_t is_last_flat, int32_t gated, void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_CHECK_ARG(x && params && y && workspace, "nsc_bottleneck_block: null pointer");
+  NSC_CHECK_ARG(Cin == wide || Cin == 1, "nsc_bottleneck_block: residual add needs Cin == wide or Cin == 1 (got %d vs %d)", Cin, wide);
+  NSC_CHECK_ARG(workspace_bytes >= nsc_block_workspace_bytes(B, L, wide, narrow), "nsc_bottleneck_block: workspace too small");
+  if (B == 0) return NSC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  nsc::Carver cv(workspace, workspace_bytes);
+  float* n0 = cv.take(B * (int64_t)L * narrow);
+  float* n1 = cv.take(B * (int64_t)L * narrow);
+  float* n2 = cv.take(B * (int64_t)L * narrow);
+  const int rmode = (Cin == wide) ? nsc::RES_ADD : nsc::RES_ADD_BCAST;
+  const int post = is_last_flat ? NSC_ACT_NONE : NSC_ACT_LRELU;
+  const float* p = params;
+  auto conv = [&](const float* in, float* out, int cin, int cout, int K, int dil, int act, const float* res, int res_mode,
+                  int post_act, int in_cl, int out_cl, int r_cl) -> int {
+    nsc::ConvArgs a;
+    a.x = in; a.y = out; a.w = p; a.bias = p + (int64_t)K * cin * cout;
+    p += (int64_t)K * cin * cout + cout;
+    a.B = B; a.Lin = L; a.Cin = cin; a.Cout = cout; a.K = K; a.dil = dil; a.act = act;
+    a.res = res; a.res_mode = res_mode; a.post_act = post_act; a.x_cl = in_cl; a.y_cl = out_cl; a.res_cl = r_cl;
+    return nsc::launch_conv(a, st);
+  };
+  if (!gated) {
+    NSC_TRY(conv(x, n0, Cin, narrow, k_plain, 1, NSC_ACT_LRELU, nullptr, nsc::RES_NONE, NSC_ACT_NONE, 1, 0, 0));
+    NSC_TRY(conv(n0, n1, narrow, narrow, k_dilated, dilation, NSC_ACT_LRELU, nullptr, nsc::RES_NONE, NSC_ACT_NONE, 0, 0, 0));
+    NSC_TRY(conv(n1, y, narrow, wide, k_plain, 1, NSC_ACT_NONE, x, rmode, post, 0, 1, 1));
+  } else {
+    NSC_TRY(conv(x, n0, Cin, narrow, 1, 1, NSC_ACT_LRELU, nullptr, nsc::RES_NONE, NSC_ACT_NONE, 1, 0, 0));
+    NSC_TRY(conv(n0, n1, narrow, narrow, 15, dilation, NSC_ACT_NONE, nullptr, nsc::RES_NONE, NSC_ACT_NONE, 0, 0, 0));
+    NSC_TRY(conv(n0, n2, narrow, narrow, 15, dilation, NSC_ACT_TANH, n1, nsc::RES_MUL, NSC_ACT_NONE, 0, 0, 0));
+    NSC_TRY(conv(n2, y, narrow, wide, k_plain, 1, NSC_ACT_NONE, x, rmode, post, 0, 1, 1));
+  }
+  return NSC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// Internal interface of the fp32 conv engine (conv.cu) used by the codec program (codec.cu).
+#pragma once
+#include "common.cuh"
+
+namespace nsc {
+
+enum { RES_NONE = 0, RES_ADD = 1, RES_ADD_BCAST = 2, RES_MUL = 3 };
+
+// One conv layer with its fused epilogue.  Internal activations are channel-major planes ("NCL":
+// [frame][channel][position]) so that position tiles are contiguous for both the smem staging loads and
+// the vectorised stores; the *_cl flags switch a tensor to the reference's channels-last (B, L, C)
+// addressing for API-level buffers.
+struct ConvArgs {
+  const float* x = nullptr;     // input
+  const float* w = nullptr;     // (K, Cin, Cout)  TF kernel layout
+  const float* bias = nullptr;  // (Cout)
+  const float* res = nullptr;   // residual / gate operand (RES_*), shape of the conv output before shuffling
+  float* y = nullptr;           // output
+  int64_t B = 0;
+  int Lin = 0, Cin = 0, Cout = 0, K = 1, dil = 1, stride = 1;
+  int act = NSC_ACT_NONE;       // conv1d's own activation (after bias)
+  int res_mode = RES_NONE;
+  int post_act = NSC_ACT_NONE;  // after the residual add (activation_func(y + x), nn_core_operator.py:76-79)
+  int shuffle = 1;              // sub-pixel factor r: out[b, c/r, l*r + c%r] (nscm.py:158-167)
+  int x_cl = 0, y_cl = 0, res_cl = 0;
+};
+
+int launch_conv(const ConvArgs& a, cudaStream_t st);
+
+// depthwise part of SeparableConv1D: y[b,c,p] = sum_t x[b,c,p*s + t*d - padL] * dw[t,c]   (no bias)
+int launch_depthwise(const float* x, const float* dw, float* y, int64_t B, int Lin, int C, int K, int dil,
+                     int stride, int x_cl, int y_cl, cudaStream_t st);
+
+// y = a * (x - b*z)  (z may be null -> y = a*x), elementwise over n floats
+int launch_axpby(float* y, const float* x, float a, const float* z, float b, int64_t n, cudaStream_t st);
+// y = x / d
+int launch_div(float* y, const float* x, float d, int64_t n, cudaStream_t st);
+// acc (+)= x / d ; first = 1 overwrites
+int launch_accum_div(float* acc, const float* x, float d, int first, int64_t n, cudaStream_t st);
+
+int launch_quantize(const float* x, int64_t B, int L, const float* bins, int n, const float* alpha, float iq,
+                    int use_soft, float* out, uint8_t* idx, float* soft, float* hist, float* qloss,
+                    cudaStream_t st);
+
+}  // namespace nsc
