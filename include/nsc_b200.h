@@ -38,6 +38,14 @@ extern "C" {
 int nsc_version(void);
 const char* nsc_last_error(void);
 
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches evidence). */
+long long nsc_launch_count(void);
+/* Optional per-launch timing for bench.py's roofline line: between begin and end every launch records a
+ * CUDA-event pair on its stream together with its algorithmic flops and bytes.  nsc_profile_end synchronises on
+ * the recorded events and returns up to `cap` records: names (cap x 32 chars), milliseconds, flops, bytes. */
+int nsc_profile_begin(int32_t max_records);
+int nsc_profile_end(int32_t* n_records, char* names, float* ms, double* flops, double* bytes, int32_t cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Activations of nn_core_operator.py: None, tf.nn.tanh, activation_func (= leaky_relu 0.2, :24-31)
  * ---------------------------------------------------------------------------------------------- */
@@ -98,13 +106,16 @@ int nsc_entropy_from_hist(const float* hist, int32_t n, float* entropy, void* st
  * ---------------------------------------------------------------------------------------------- */
 /* lpc_analysis_at_test loop body (:112-124): windows (N,1024) -> LSF (N,16) radians ascending.
  *   window = [rising half-Hann(512), 512 ones, falling half-Hann(512)], autocorrelation LPC order 16,
- *   poly2lsf.  float64 arithmetic; lsf_out is float64 like the reference's np.empty array.
+ *   poly2lsf.  float64 arithmetic; lsf_out is float64 like the reference's np.empty array, lsf_out_f32 its float32
+ *   cast (what the `lpc_x` float32 placeholder receives, cmrl.py:699-702); either may be NULL.
  *   status (int32, may be NULL) is incremented for every frame that is not analysable (zero energy /
  *   non-minimum-phase); such rows are filled with NaN (the reference raises). */
-int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, int32_t* status, void* stream);
+int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, float* lsf_out_f32, int32_t* status,
+                    void* stream);
 
 /* lpc_analysis_at_train (:14-25): frames (B,512) -> highpass, pre-emphasis (zero state), LPC, LSF (B,16). */
-int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, int32_t* status, void* stream);
+int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, float* lsf_out_f32, int32_t* status,
+                          void* stream);
 
 /* lsf2poly_after_quan (:28-33): lsf (B,16) float32 -> poly (B,17) float32, a[0] = 1.
  *   rows with an LSF outside [0, pi] become NaN and bump *status (the reference raises ValueError). */

@@ -40,6 +40,9 @@ _ppv = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "nsc_version": (_i32, []),
     "nsc_last_error": (C.c_char_p, []),
+    "nsc_launch_count": (C.c_longlong, []),
+    "nsc_profile_begin": (_i32, [_i32]),
+    "nsc_profile_end": (_i32, [C.POINTER(_i32), C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "nsc_conv1d": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nsc_conv1d_depth": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nsc_block_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
@@ -49,8 +52,8 @@ SIGNATURES = {
     "nsc_quan_loss": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "nsc_soft_histogram": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "nsc_entropy_from_hist": (_i32, [_vp, _i32, _vp, _vp]),
-    "nsc_lpc_analyze": (_i32, [_vp, _i64, _vp, _vp, _vp]),
-    "nsc_lpc_analyze_train": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "nsc_lpc_analyze": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "nsc_lpc_analyze_train": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "nsc_lsf2poly": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "nsc_lpc_residual": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "nsc_lpc_synth": (_i32, [_vp, _vp, _i64, _vp, _vp]),

@@ -1,6 +1,9 @@
 // Library-wide pieces of the C ABI: version, thread-local error message, device attribute cache.
+#include <atomic>
 #include <mutex>
+#include <string>
 #include <string.h>
+#include <vector>
 
 #include "common.cuh"
 
@@ -27,9 +30,77 @@ int sm_count() {
   return cached[dev];
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- profiling records ---------------------------------------------------------------------------
+struct ProfRec {
+  char name[32];
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static int g_prof_cap = 0;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(cudaStream_t s, const char* name, double flops, double bytes) : slot(-1), st(s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on || (int)g_prof.size() >= g_prof_cap) return;
+  ProfRec r;
+  strncpy(r.name, name, sizeof(r.name) - 1);
+  r.name[sizeof(r.name) - 1] = 0;
+  r.flops = flops;
+  r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, st);
+}
+
 }  // namespace nsc
 
 extern "C" {
+
+long long nsc_launch_count(void) { return nsc::g_launches.load(); }
+
+int nsc_profile_begin(int32_t max_records) {
+  std::lock_guard<std::mutex> lk(nsc::g_prof_mu);
+  for (auto& r : nsc::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  nsc::g_prof.clear();
+  nsc::g_prof_cap = max_records;
+  nsc::g_prof_on = max_records > 0;
+  return NSC_OK;
+}
+
+int nsc_profile_end(int32_t* n_records, char* names, float* ms, double* flops, double* bytes, int32_t cap) {
+  std::lock_guard<std::mutex> lk(nsc::g_prof_mu);
+  nsc::g_prof_on = false;
+  int n = 0;
+  for (auto& r : nsc::g_prof) {
+    if (n < cap) {
+      float t = 0.f;
+      if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) t = -1.f;
+      if (names) memcpy(names + (size_t)n * 32, r.name, 32);
+      if (ms) ms[n] = t;
+      if (flops) flops[n] = r.flops;
+      if (bytes) bytes[n] = r.bytes;
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  nsc::g_prof.clear();
+  if (n_records) *n_records = n;
+  return NSC_OK;
+}
 
 int nsc_version(void) { return 100; /* 0.1.0 */ }
 

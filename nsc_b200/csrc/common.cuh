@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...);
 
 #define NSC_LAUNCH_OK()                                                                       \
   do {                                                                                        \
+    nsc::count_launch();                                                                      \
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) {                                                                  \
       nsc::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -65,5 +66,15 @@ __host__ __device__ inline void same_padding(int L, int k, int d, int s, int* ou
 }
 
 int sm_count();
+void count_launch();
+
+// Optional per-launch timing (nsc_profile_begin / nsc_profile_end): a ProfScope around a launch records a
+// CUDA-event pair on the launching stream plus the launch's ALGORITHMIC flops and bytes.  Inactive = free.
+struct ProfScope {
+  ProfScope(cudaStream_t st, const char* name, double flops, double bytes);
+  ~ProfScope();
+  int slot;
+  cudaStream_t st;
+};
 
 }  // namespace nsc

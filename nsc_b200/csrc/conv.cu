@@ -267,6 +267,12 @@ int launch_one(KernelT kernel, const ConvLaunch& p, int threads, size_t smem, cu
     set_error("conv grid too large (%lld CTAs)", (long long)grid);
     return NSC_E_INVALID;
   }
+  char name[32];
+  snprintf(name, sizeof(name), "conv_k%dd%ds%d_c%dto%d", p.a.K, p.a.dil, p.a.stride, p.a.Cin, p.a.Cout);
+  const double macs = (double)p.a.B * p.Lout * p.a.K * p.a.Cin * p.a.Cout;
+  const double bytes = 4.0 * ((double)p.a.B * ((double)p.a.Lin * p.a.Cin + (double)p.Lout * p.a.Cout) +
+                              (double)p.a.K * p.a.Cin * p.a.Cout);
+  ProfScope prof(st, name, 2.0 * macs, bytes);
   kernel<<<(unsigned)grid, threads, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;
@@ -391,6 +397,7 @@ int launch_depthwise(const float* x, const float* dw, float* y, int64_t B, int L
   same_padding(Lin, K, dil, stride, &Lout, &padL);
   const int64_t total = B * C * (int64_t)Lout;
   if (total == 0) return NSC_OK;
+  ProfScope prof(st, "depthwise", 2.0 * (double)total * K, 8.0 * (double)total);
   depthwise_kernel<<<ew_grid(total), 256, 0, st>>>(x, dw, y, B, Lin, Lout, C, K, dil, stride, padL, x_cl, y_cl);
   NSC_LAUNCH_OK();
   return NSC_OK;
@@ -398,6 +405,7 @@ int launch_depthwise(const float* x, const float* dw, float* y, int64_t B, int L
 
 int launch_axpby(float* y, const float* x, float a, const float* z, float b, int64_t n, cudaStream_t st) {
   if (n == 0) return NSC_OK;
+  ProfScope prof(st, "cascade_input", 2.0 * (double)n, (z ? 12.0 : 8.0) * (double)n);
   axpby_kernel<<<ew_grid(n), 256, 0, st>>>(y, x, a, z, b, n);
   NSC_LAUNCH_OK();
   return NSC_OK;
@@ -405,6 +413,7 @@ int launch_axpby(float* y, const float* x, float a, const float* z, float b, int
 
 int launch_div(float* y, const float* x, float d, int64_t n, cudaStream_t st) {
   if (n == 0) return NSC_OK;
+  ProfScope prof(st, "cascade_div", (double)n, 8.0 * (double)n);
   div_kernel<<<ew_grid(n), 256, 0, st>>>(y, x, d, n);
   NSC_LAUNCH_OK();
   return NSC_OK;
@@ -412,6 +421,7 @@ int launch_div(float* y, const float* x, float d, int64_t n, cudaStream_t st) {
 
 int launch_accum_div(float* acc, const float* x, float d, int first, int64_t n, cudaStream_t st) {
   if (n == 0) return NSC_OK;
+  ProfScope prof(st, "cascade_accum", 2.0 * (double)n, (first ? 8.0 : 12.0) * (double)n);
   accum_div_kernel<<<ew_grid(n), 256, 0, st>>>(acc, x, d, first, n);
   NSC_LAUNCH_OK();
   return NSC_OK;

@@ -114,8 +114,7 @@ __device__ __forceinline__ bool warp_poly2lsf(const double a[kOrder + 1], int la
   __syncwarp();
   // scan: lane owns kGrid/32 consecutive intervals; ordered compaction keeps each list ascending.
   constexpr int PER = kGrid / 32;
-  double brk_lo[2][2];  // at most a couple of roots per lane in practice; overflow handled by count check
-  int nb[2] = {0, 0};
+  double brk_lo[2][8];  // a polynomial has 8 roots in total, so a lane can never hold more than 8 brackets
   int total_found[2];
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
@@ -127,13 +126,12 @@ __device__ __forceinline__ bool warp_poly2lsf(const double a[kOrder + 1], int la
       const double w1 = kPi * (double)(lane * PER + i) / (double)kGrid;
       const double f1 = cheb_eval(c, cos(w1));
       if ((f0 > 0.0) != (f1 > 0.0)) {
-        if (found < 2) brk_lo[which][found] = w0;
+        if (found < 8) brk_lo[which][found] = w0;
         ++found;
       }
       w0 = w1;
       f0 = f1;
     }
-    nb[which] = found;
     // exclusive prefix over lanes
     int incl = found;
 #pragma unroll
@@ -143,7 +141,7 @@ __device__ __forceinline__ bool warp_poly2lsf(const double a[kOrder + 1], int la
     }
     const int excl = incl - found;
     total_found[which] = __shfl_sync(0xffffffffu, incl, 31);
-    const bool lane_overflow = found > 2;
+    const bool lane_overflow = found > 8;
     const unsigned any_over = __ballot_sync(0xffffffffu, lane_overflow);
     if (any_over) total_found[which] = -1;
     if (total_found[which] == 8) {
@@ -186,7 +184,8 @@ constexpr int kAWarps = 4;
 
 template <int MODE>
 __global__ void __launch_bounds__(kAWarps * 32)
-lpc_analyze_kernel(const float* __restrict__ in, int64_t N, double* __restrict__ lsf, int* __restrict__ status) {
+lpc_analyze_kernel(const float* __restrict__ in, int64_t N, double* __restrict__ lsf, float* __restrict__ lsf32,
+                   int* __restrict__ status) {
   constexpr int LEN = MODE == 0 ? 1024 : 512;
   __shared__ double sig_s[kAWarps][LEN + kOrder + 2];
   __shared__ double roots_s[kAWarps][16];
@@ -225,13 +224,17 @@ lpc_analyze_kernel(const float* __restrict__ in, int64_t N, double* __restrict__
   double r[kOrder + 1], a[kOrder + 1];
   warp_autocorr(s, LEN, lane, r);
   bool ok = levinson(r, a);
-  double* out = lsf + frame * kOrder;
+  __shared__ double out_s[kAWarps][kOrder];
+  double* out = out_s[warp];
   bool ok2 = false;
   if (ok) ok2 = warp_poly2lsf(a, lane, roots_s[warp], count_s[warp], out);
-  if (!(ok && ok2)) {
-    if (lane < kOrder) out[lane] = nan("");
-    if (lane == 0 && status) atomicAdd(status, 1);
+  __syncwarp();
+  if (lane < kOrder) {
+    const double v = (ok && ok2) ? out[lane] : nan("");
+    if (lsf) lsf[frame * kOrder + lane] = v;
+    if (lsf32) lsf32[frame * kOrder + lane] = (float)v;   // the cast the reference does when feeding lpc_x (float32 placeholder)
   }
+  if (!(ok && ok2) && lane == 0 && status) atomicAdd(status, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,20 +374,23 @@ lpc_synth_kernel(const float* __restrict__ poly, const float* __restrict__ res, 
 
 extern "C" {
 
-int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, int32_t* status, void* stream) {
-  NSC_CHECK_ARG(windows && lsf_out, "nsc_lpc_analyze: null pointer");
+int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, float* lsf_out_f32, int32_t* status,
+                    void* stream) {
+  NSC_CHECK_ARG(windows && (lsf_out || lsf_out_f32), "nsc_lpc_analyze: null pointer");
   if (N == 0) return NSC_OK;
+  nsc::ProfScope prof((cudaStream_t)stream, "lpc_analyze", (double)N * 2.0 * 17.0 * 1024.0, (double)N * (4096.0 + 128.0));
   nsc::lpc_analyze_kernel<0><<<(unsigned)nsc::ceil_div64(N, nsc::kAWarps), nsc::kAWarps * 32, 0,
-                               (cudaStream_t)stream>>>(windows, N, lsf_out, status);
+                               (cudaStream_t)stream>>>(windows, N, lsf_out, lsf_out_f32, status);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
 
-int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, int32_t* status, void* stream) {
-  NSC_CHECK_ARG(frames && lsf_out, "nsc_lpc_analyze_train: null pointer");
+int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, float* lsf_out_f32, int32_t* status,
+                          void* stream) {
+  NSC_CHECK_ARG(frames && (lsf_out || lsf_out_f32), "nsc_lpc_analyze_train: null pointer");
   if (B == 0) return NSC_OK;
   nsc::lpc_analyze_kernel<1><<<(unsigned)nsc::ceil_div64(B, nsc::kAWarps), nsc::kAWarps * 32, 0,
-                               (cudaStream_t)stream>>>(frames, B, lsf_out, status);
+                               (cudaStream_t)stream>>>(frames, B, lsf_out, lsf_out_f32, status);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
@@ -392,6 +398,7 @@ int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, int32
 int nsc_lsf2poly(const float* lsf, int64_t B, float* poly, int32_t* status, void* stream) {
   NSC_CHECK_ARG(lsf && poly, "nsc_lsf2poly: null pointer");
   if (B == 0) return NSC_OK;
+  nsc::ProfScope prof((cudaStream_t)stream, "lsf2poly", (double)B * 600.0, (double)B * (64.0 + 68.0));
   nsc::lsf2poly_kernel<<<(unsigned)nsc::ceil_div64(B, 128), 128, 0, (cudaStream_t)stream>>>(lsf, B, poly, status);
   NSC_LAUNCH_OK();
   return NSC_OK;
@@ -400,6 +407,7 @@ int nsc_lsf2poly(const float* lsf, int64_t B, float* poly, int32_t* status, void
 int nsc_lpc_residual(const float* x, const float* poly, int64_t B, float* res, void* stream) {
   NSC_CHECK_ARG(x && poly && res, "nsc_lpc_residual: null pointer");
   if (B == 0) return NSC_OK;
+  nsc::ProfScope prof((cudaStream_t)stream, "lpc_residual", (double)B * 2.0 * 15232.0, (double)B * 4164.0);
   nsc::lpc_residual_kernel<<<(unsigned)B, nsc::kFrame, 0, (cudaStream_t)stream>>>(x, poly, B, res);
   NSC_LAUNCH_OK();
   return NSC_OK;
@@ -408,6 +416,7 @@ int nsc_lpc_residual(const float* x, const float* poly, int64_t B, float* res, v
 int nsc_lpc_synth(const float* poly, const float* res, int64_t B, float* y, void* stream) {
   NSC_CHECK_ARG(poly && res && y, "nsc_lpc_synth: null pointer");
   if (B == 0) return NSC_OK;
+  nsc::ProfScope prof((cudaStream_t)stream, "lpc_synth", (double)B * 2.0 * 8192.0, (double)B * 4164.0);
   nsc::lpc_synth_kernel<<<(unsigned)nsc::ceil_div64(B, nsc::kSynFrames), nsc::kSynFrames, 0,
                           (cudaStream_t)stream>>>(poly, res, B, y);
   NSC_LAUNCH_OK();

@@ -201,6 +201,10 @@ int launch_quantize(const float* x, int64_t B, int L, const float* bins, int n, 
 #define NSC_Q_LAUNCH(NPL)                                                                                   \
   quantize_kernel<NPL><<<(unsigned)grid, kQWarps * 32, smem, st>>>(x, B, L, frames_per_cta, bins, n, alpha, iq, \
                                                                    use_soft, out, idx, soft, hist, qloss)
+  char name[32];
+  snprintf(name, sizeof(name), "quantize_n%d_L%d", n, L);
+  // algorithmic traffic: code in, value out, uint8 index (2,304 B / frame / codec at L = 256)
+  ProfScope prof(st, name, (double)B * L * n * 4.0, (double)B * L * 9.0 + (soft ? (double)B * L * n * 4.0 : 0.0));
   switch (npl) {
     case 1: NSC_Q_LAUNCH(1); break;
     case 2: NSC_Q_LAUNCH(2); break;

@@ -73,15 +73,18 @@ def lpc_windows_at_test(raw_data):
     return flat.unfold(0, frame_length * 2, frame_length)[:count].contiguous()
 
 
-def lpc_analysis_windows(windows, order=16, *, strict: bool = False):
-    """Loop body of lpc_utilities.py:112-124 on already-cut (N,1024) windows -> (N,16) float64 LSFs."""
+def lpc_analysis_windows(windows, order=16, *, strict: bool = False, dtype=torch.float64):
+    """Loop body of lpc_utilities.py:112-124 on already-cut (N,1024) windows -> (N,16) LSFs.
+    float64 like the reference's array by default; dtype=torch.float32 returns the cast that the float32
+    `lpc_x` placeholder receives (cmrl.py:699-702) straight from the kernel."""
     if order != _lib.LPC_ORDER:
         raise ValueError("the hot path is order 16")
     w = _lib.require_f32(windows, 'windows').reshape(-1, frame_length * 2)
     N = w.shape[0]
-    lsf = torch.empty((N, order), dtype=torch.float64, device=w.device)
+    lsf = torch.empty((N, order), dtype=dtype, device=w.device)
     st = _status(w.device) if strict else None
-    _lib.check(_lib.load().nsc_lpc_analyze(_lib.ptr(w), N, _lib.ptr(lsf), _lib.ptr(st), _lib.stream_ptr()), 'lpc_analysis')
+    p64, p32 = (_lib.ptr(lsf), None) if dtype == torch.float64 else (None, _lib.ptr(lsf))
+    _lib.check(_lib.load().nsc_lpc_analyze(_lib.ptr(w), N, p64, p32, _lib.ptr(st), _lib.stream_ptr()), 'lpc_analysis')
     if strict and int(st.item()) != 0:
         raise ZeroDivisionError('LPC analysis failed on %d frame(s) (silent or non-minimum-phase)' % int(st.item()))
     return lsf
@@ -100,7 +103,7 @@ def lpc_analysis_at_train(raw_data_one_batch, order=16, *, strict: bool = False)
     B = x.shape[0]
     lsf = torch.empty((B, order), dtype=torch.float64, device=x.device)
     st = _status(x.device) if strict else None
-    _lib.check(_lib.load().nsc_lpc_analyze_train(_lib.ptr(x), B, _lib.ptr(lsf), _lib.ptr(st), _lib.stream_ptr()),
+    _lib.check(_lib.load().nsc_lpc_analyze_train(_lib.ptr(x), B, _lib.ptr(lsf), None, _lib.ptr(st), _lib.stream_ptr()),
                'lpc_analysis_at_train')
     if strict and int(st.item()) != 0:
         raise ZeroDivisionError('LPC analysis failed on %d frame(s)' % int(st.item()))

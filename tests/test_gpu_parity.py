@@ -1,0 +1,393 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json:north_star): quantiser codes bit-exact given identical pre-quantisation inputs; waveforms,
+LPC coefficients and losses within 1e-4 relative error in fp32 (rel_err = max|a-b| / max|b|).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_codec, ref_loss, ref_lpc, ref_nn
+from util import ar_frames, quantizer_edge_codes, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+TOL = 1e-4
+DEV = 'cuda'
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(DEV)
+
+
+def lsf_bins():
+    return np.load(os.path.join(GOLD, 'lsf_bins_f64.npy')).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ quantiser
+def _quant_case(x, bins, alpha, L):
+    from nsc_b200 import nn_core_operator as nn
+    n = len(bins)
+    xt = torch.from_numpy(x)
+    out = {}
+    for share in (False, True):
+        soft_o, code_o = ref_nn.scalar_softmax_quantization(xt, alpha, bins, 1.0, share, L, n)
+        soft_g, code_g, idx_g = nn.scalar_softmax_quantization(cu(x), alpha, cu(bins), 1.0, share, L, n,
+                                                               return_indices=True)
+        idx_o = ref_nn.quantizer_indices(xt, alpha, bins)
+        assert np.array_equal(idx_g.cpu().numpy(), idx_o.numpy().astype(np.uint8)), "codes not bit-exact"
+        assert np.abs(soft_g.cpu().numpy() - soft_o.numpy()).max() < 1e-5
+        if share:
+            assert rel_err(code_g.cpu().numpy(), code_o.numpy()) < 1e-5
+        else:
+            assert np.array_equal(code_g.cpu().numpy(), code_o.numpy()), "hard value must be bins[idx] exactly"
+        out[share] = (soft_g, code_g, idx_g)
+    return out
+
+
+def test_quantizer_32_bins_random_and_edges():
+    bins = np.linspace(-1, 1, 32).astype(np.float32)
+    rng = np.random.RandomState(0)
+    x = np.concatenate([quantizer_edge_codes(bins), rng.uniform(-1.1, 1.1, 256 * 37).astype(np.float32)])
+    x = x[: (len(x) // 256) * 256].reshape(-1, 256, 1)
+    _quant_case(x, bins, -300.0, 256)
+
+
+def test_quantizer_other_bin_counts_alphas_unsorted_duplicates():
+    rng = np.random.RandomState(1)
+    for n, L, alpha in ((64, 128, -300.0), (16, 256, -150.0), (33, 50, -40.0), (128, 16, -300.0)):
+        bins = np.linspace(-1, 1, n).astype(np.float32)
+        rng.shuffle(bins)                 # unsorted
+        bins[3] = bins[7]                 # duplicate: the lower index must win
+        x = np.concatenate([quantizer_edge_codes(bins), rng.uniform(-1.2, 1.2, L * 9).astype(np.float32)])
+        x = x[: (len(x) // L) * L].reshape(-1, L, 1)
+        _quant_case(x, bins, alpha, L)
+
+
+def test_quantizer_lsf_codebook_256_unsorted():
+    bins = lsf_bins()
+    rng = np.random.RandomState(2)
+    x = np.concatenate([quantizer_edge_codes(bins), rng.uniform(0, np.pi, 16 * 200).astype(np.float32)])
+    x = x[: (len(x) // 16) * 16].reshape(-1, 16, 1)
+    _quant_case(x, bins, -300.0, 16)
+
+
+def test_quantizer_golden_fixture_and_pretrain_blend():
+    from nsc_b200 import nn_core_operator as nn
+    g = np.load(os.path.join(GOLD, 'quantizer.npz'))
+    bins = np.linspace(-1, 1, 32).astype(np.float32)
+    _, code, idx = nn.scalar_softmax_quantization(cu(g['x32']), -300.0, cu(bins), 1.0, False, 64, 32, return_indices=True)
+    assert np.array_equal(idx.cpu().numpy(), g['idx32']) and np.array_equal(code.cpu().numpy(), g['code32'])
+    _, code, idx = nn.scalar_softmax_quantization(cu(g['xl']), -300.0, cu(lsf_bins()), 1.0, False, 16, 256, return_indices=True)
+    assert np.array_equal(idx.cpu().numpy(), g['idx_l']) and np.array_equal(code.cpu().numpy(), g['code_l'])
+    # is_quan_on = 0 (pre-training epochs, nscm.py:560-568): the value path is the floating code itself
+    _, code0 = nn.scalar_softmax_quantization(cu(g['x32']), -300.0, cu(bins), 0.0, True, 64, 32)
+    assert np.array_equal(code0.cpu().numpy(), g['x32'])
+
+
+def test_quantizer_stats_hist_qloss_entropy():
+    from nsc_b200 import _lib, loss_terms_and_measures as lt
+    bins = np.linspace(-1, 1, 32).astype(np.float32)
+    x = np.random.RandomState(3).uniform(-1, 1, (9, 256, 1)).astype(np.float32)
+    soft_o, _ = ref_nn.scalar_softmax_quantization(torch.from_numpy(x), -20.0, bins, 1.0, True, 256, 32)
+    xt = cu(x)
+    hist = torch.zeros(32, device=DEV)
+    ql = torch.empty(9, device=DEV)
+    alpha = torch.tensor([-20.0], device=DEV)
+    rc = _lib.load().nsc_quantize_scalar(_lib.ptr(xt), 9, 256, _lib.ptr(cu(bins)), 32, _lib.ptr(alpha), 1.0, 1, None, None, None,
+                                         _lib.ptr(hist), _lib.ptr(ql), _lib.stream_ptr())
+    assert rc == 0
+    assert rel_err(hist.cpu().numpy(), soft_o.reshape(-1, 32).sum(0).numpy()) < TOL
+    assert rel_err(ql.cpu().numpy(), ref_loss.quan_loss(soft_o).numpy()) < TOL
+    ent = lt.entropy_from_hist(hist)
+    assert abs(float(ent) - float(ref_loss.entropy_coding_loss(soft_o))) < 1e-4
+    # surface functions on a materialised soft tensor
+    sg = cu(soft_o.numpy())
+    assert rel_err(lt.quan_loss(sg).cpu().numpy(), ref_loss.quan_loss(soft_o).numpy()) < TOL
+    assert abs(float(lt.entropy_coding_loss(sg)) - float(ref_loss.entropy_coding_loss(soft_o))) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ convs
+CONV_CASES = [
+    # B, L, cin, cout, k, dil, stride, act
+    (3, 512, 1, 100, 55, 1, 1, None),
+    (2, 512, 100, 20, 9, 1, 1, 'leaky_relu'),
+    (2, 512, 20, 20, 9, 2, 1, 'leaky_relu'),
+    (2, 256, 20, 100, 9, 1, 1, None),
+    (2, 512, 100, 100, 9, 1, 2, 'leaky_relu'),
+    (2, 256, 100, 1, 55, 1, 1, 'tanh'),
+    (2, 512, 50, 1, 55, 1, 1, None),
+    (2, 256, 1, 20, 9, 1, 1, None),
+    (2, 512, 50, 20, 9, 1, 1, 'tanh'),
+    (2, 128, 20, 20, 15, 2, 1, 'tanh'),
+    (2, 128, 100, 20, 1, 1, 1, 'leaky_relu'),
+    (1, 500, 7, 13, 9, 4, 1, None),      # generic fallback kernel, ragged length, odd channels
+    (2, 37, 3, 5, 3, 1, 1, 'tanh'),      # tiny ragged
+    (1, 511, 6, 10, 5, 1, 3, None),      # stride 3 generic
+    (2, 100, 25, 25, 9, 1, 1, None),     # stride-[2,2] decoder width
+]
+
+
+@pytest.mark.parametrize('B,L,cin,cout,k,dil,stride,act', CONV_CASES)
+def test_conv1d_vs_oracle(B, L, cin, cout, k, dil, stride, act):
+    from nsc_b200 import nn_core_operator as nn
+    rng = np.random.RandomState(k * 1000 + cin + cout)
+    x = rng.randn(B, L, cin).astype(np.float32)
+    w = (rng.randn(k, cin, cout) / np.sqrt(k * cin)).astype(np.float32)
+    b = rng.randn(cout).astype(np.float32) * 0.1
+    ref = ref_nn.conv1d_explicit(torch.from_numpy(x), w, b, dil, stride, act).numpy()
+    got = nn.conv1d(cu(x), cout, k, dilation_rate=dil, strides=stride, activation=act, params=(cu(w), cu(b)))
+    assert got.shape == ref.shape
+    assert rel_err(got.cpu().numpy(), ref) < 2e-5
+
+
+def test_conv1d_depth_vs_oracle():
+    from nsc_b200 import nn_core_operator as nn
+    rng = np.random.RandomState(5)
+    x = rng.randn(2, 256, 100).astype(np.float32)
+    dw = (rng.randn(9, 100, 1) / 3).astype(np.float32)
+    pw = (rng.randn(1, 100, 100) / 10).astype(np.float32)
+    b = rng.randn(100).astype(np.float32) * 0.1
+    ref = ref_nn.conv1d_depth_explicit(torch.from_numpy(x), dw, pw, b, 1, 1, 'leaky_relu').numpy()
+    got = nn.conv1d_depth(cu(x), 100, 9, activation='leaky_relu', params=(cu(dw), cu(pw), cu(b)))
+    assert rel_err(got.cpu().numpy(), ref) < 2e-5
+
+
+@pytest.mark.parametrize('gated', [False, True])
+@pytest.mark.parametrize('cin,wide,L,dil,flat', [(100, 100, 512, 1, False), (100, 100, 256, 2, True),
+                                                 (1, 100, 256, 1, False), (50, 50, 512, 2, True)])
+def test_blocks_vs_oracle(gated, cin, wide, L, dil, flat):
+    from nsc_b200 import nn_core_operator as nn
+    ps = ref_nn.ParamStream(seed=wide + cin + dil)
+    x = np.random.RandomState(8).randn(2, L, cin).astype(np.float32)
+    fn_o = ref_nn.gated_bottleneck if gated else ref_nn.the_bottleneck
+    ref = fn_o(torch.from_numpy(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=flat, ps=ps).numpy()
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    fn_g = nn.gated_bottleneck if gated else nn.the_bottleneck
+    got = fn_g(cu(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=flat, params=params)
+    assert rel_err(got.cpu().numpy(), ref) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ LPC
+def test_lpc_golden_and_oracle():
+    from nsc_b200 import lpc_utilities as lu
+    g = np.load(os.path.join(GOLD, 'lpc.npz'))
+    lsf = lu.lpc_analysis_windows(cu(g['windows']), 16, strict=True)
+    assert lsf.dtype == torch.float64
+    assert rel_err(lsf.cpu().numpy(), g['lsf']) < 1e-8
+    poly = lu.lsf2poly_after_quan(cu(g['lsf'].astype(np.float32)), 16, strict=True)
+    assert rel_err(poly.cpu().numpy(), g['poly']) < TOL          # the reference path is complex64 inside np.poly
+    p64 = np.stack([ref_lpc.lsf2poly(r.astype(np.float64)) for r in g['lsf'].astype(np.float32)])
+    assert rel_err(poly.cpu().numpy(), p64) < 1e-6                  # vs float64 truth: float32 output rounding only
+    res = lu.lpc_analysis_get_residual(cu(g['frames'])[:, :, None], cu(g['poly']))
+    assert np.abs(res.cpu().numpy() - g['res']).max() <= 1e-6 * np.abs(g['res']).max()
+    syn = lu.lpc_synthesizer_tr(cu(g['poly']), cu(g['res']))
+    assert rel_err(syn.cpu().numpy(), g['syn']) < 1e-6
+    lsf_tr = lu.lpc_analysis_at_train(cu(g['frames'])[:, :, None], 16, strict=True)
+    assert rel_err(lsf_tr.cpu().numpy(), g['lsf_train']) < 1e-8
+
+
+def test_lpc_analysis_at_test_windowing_quirk():
+    from nsc_b200 import lpc_utilities as lu
+    seg = ar_frames(9, 512, seed=77)
+    ref = ref_lpc.lpc_analysis_at_test(seg, 16)
+    got = lu.lpc_analysis_at_test(cu(seg), 16)
+    assert got.shape == ref.shape == (7, 16)
+    assert rel_err(got.cpu().numpy(), ref) < 1e-8
+
+
+def test_lpc_error_behaviour():
+    from nsc_b200 import lpc_utilities as lu
+    bad = np.full((2, 16), 0.5, dtype=np.float32); bad[1, 3] = 3.5     # > pi
+    with pytest.raises(ValueError):
+        lu.lsf2poly_after_quan(cu(bad), 16, strict=True)
+    out = lu.lsf2poly_after_quan(cu(bad), 16)
+    assert torch.isfinite(out[0]).all() and torch.isnan(out[1]).all()
+    with pytest.raises(ZeroDivisionError):
+        lu.lpc_analysis_windows(torch.zeros(1, 1024, device=DEV), 16, strict=True)
+    assert lu.lpc_analysis_windows(torch.zeros(0, 1024, device=DEV)).shape == (0, 16)    # empty batch
+
+
+def test_lpc_full_size_roundtrip_and_linearity():
+    """Size-independent properties at a production batch: synthesis undoes a zero-state analysis FIR over the
+    whole frame is NOT what the sub-framed residual is, so check (a) linearity of the residual in x and
+    (b) analysis windows -> LSF sortedness, (c) lsf2poly(poly2lsf) fixed point through the GPU path."""
+    from nsc_b200 import lpc_utilities as lu
+    B = 4096
+    win = cu(ar_frames(B, 1024, seed=101))
+    lsf = lu.lpc_analysis_windows(win, 16, strict=True)
+    assert bool((lsf[:, 1:] > lsf[:, :-1]).all()) and float(lsf.min()) > 0 and float(lsf.max()) < np.pi
+    poly = lu.lsf2poly_after_quan(lsf.float(), 16)
+    x1 = cu(ar_frames(B, 512, seed=102)); x2 = cu(ar_frames(B, 512, seed=103))
+    r1 = lu.lpc_analysis_get_residual(x1, poly); r2 = lu.lpc_analysis_get_residual(x2, poly)
+    r12 = lu.lpc_analysis_get_residual(x1 + x2, poly)
+    assert float((r12 - (r1 + r2)).abs().max()) < 1e-4 * float(r12.abs().max())
+    # synthesis is the inverse of the un-subframed analysis filter: check via the impulse response identity
+    imp = torch.zeros(B, 512, device=DEV); imp[:, 0] = 1.0
+    h = lu.lpc_synthesizer_tr(poly, imp)                       # h = 1/A
+    # A * h = delta  (first 512 samples)
+    a = poly.double(); hd = h.double()
+    conv = torch.zeros(B, 64, dtype=torch.float64, device=DEV)
+    for k in range(17):
+        conv[:, k:] += a[:, k:k + 1] * hd[:, :64 - k]
+    conv[:, 0] -= 1.0
+    assert float(conv.abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def test_losses_vs_oracle_and_golden():
+    from nsc_b200 import loss_terms_and_measures as lt
+    g = np.load(os.path.join(GOLD, 'losses.npz'))
+    t, f = lt.losses(cu(g['dec']), cu(g['ori']))
+    assert rel_err(t.cpu().numpy(), g['time_loss']) < TOL
+    assert rel_err(f.cpu().numpy(), g['freq_loss']) < TOL
+    assert rel_err(lt.mse_loss(cu(g['dec']), cu(g['ori'])).cpu().numpy(), g['time_loss']) < TOL
+    assert rel_err(lt.mfcc_loss(cu(g['dec']), cu(g['ori'])).cpu().numpy(), g['freq_loss']) < TOL
+    a = ar_frames(300, 512, seed=55, std=0.2)
+    b = (a * 0.9 + 0.02 * np.random.RandomState(56).randn(*a.shape)).astype(np.float32)
+    t, f = lt.losses(cu(b), cu(a))
+    assert rel_err(t.cpu().numpy(), ref_loss.mse_loss(torch.from_numpy(b), torch.from_numpy(a)).numpy()) < TOL
+    assert rel_err(f.cpu().numpy(), ref_loss.mfcc_loss(torch.from_numpy(b), torch.from_numpy(a)).numpy()) < TOL
+    # identical signals: both losses are sqrt(1e-7)
+    t, f = lt.losses(cu(a), cu(a))
+    assert np.allclose(t.cpu().numpy(), np.sqrt(1e-7), rtol=1e-5) and np.allclose(f.cpu().numpy(), np.sqrt(1e-7), rtol=1e-5)
+
+
+def test_mel_filterbank_matches_oracle():
+    from nsc_b200 import _lib, loss_terms_and_measures as lt
+    buf = lt.mel_filterbank(DEV).cpu().numpy()
+    m = buf[:257 * 184].reshape(257, 184)
+    ref = np.concatenate([ref_loss.linear_to_mel_weight_matrix(n, 257, 16000, 0.0, 8000.0) for n in (8, 16, 32, 128)], axis=1)
+    assert np.abs(m - ref).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ codec / cascade / CQ
+def _make_pair(rt, st, seed, nbins=32):
+    from nsc_b200 import codec
+    oc = ref_codec.OracleCodec(ref_codec.OracleCodecCfg(resnet_type=rt, strides=st, num_bins=nbins), seed=seed)
+    cfg = codec.CodecConfig(resnet_type=rt, the_strides=st, num_bins=nbins)
+    flat = codec.pack_params_numpy(cfg, oc.conv_params, oc.alpha, oc.bins)
+    return oc, codec.NeuralCodec(cfg, torch.from_numpy(flat).to(DEV))
+
+
+def _check_codec(oc, gc, x, the_share):
+    r_o = oc.forward(torch.from_numpy(x)[:, :, None], the_share, 1.0)
+    r_g = gc.computational_graph_end2end_quan_on(cu(x), the_share, 1.0, want_soft=True, want_stats=True)
+    fl_g = r_g['floating_code'].cpu().numpy()
+    assert rel_err(fl_g, r_o['floating_code'].numpy()[:, :, 0]) < TOL
+    # codes: bit-exact given identical pre-quantisation inputs -> re-quantise the GPU's floating code with the oracle
+    idx_o = ref_nn.quantizer_indices(torch.from_numpy(fl_g)[:, :, None], oc.alpha, oc.bins).numpy()
+    assert np.array_equal(r_g['idx'].cpu().numpy(), idx_o.astype(np.uint8))
+    # decoder parity on identical codes
+    code_g = r_g['code'].cpu().numpy()
+    oc.ps._cursor = _enc_layers(oc)
+    out_o = oc.decoder(torch.from_numpy(code_g)[:, :, None])[:, :, 0].numpy()
+    assert rel_err(r_g['out'].cpu().numpy(), out_o) < TOL
+    return r_o, r_g
+
+
+def _enc_layers(oc):
+    n = 1 + len(oc.cfg.strides) * (1) + 1
+    per_block = 3 if oc.cfg.resnet_type == 'bottleneck' else 4
+    nb = len(oc.cfg.bottleneck_kernel_and_dilation) - 4
+    return n + (len(oc.cfg.strides) + 1) * nb * per_block
+
+
+@pytest.mark.parametrize('rt,st', [('bottleneck', (2,)), ('gln', (2,)), ('bottleneck', (2, 2)), ('gln', (2, 2))])
+@pytest.mark.parametrize('the_share', [False, True])
+def test_codec_forward_vs_oracle(rt, st, the_share):
+    oc, gc = _make_pair(rt, st, seed=3)
+    x = ar_frames(3, 512, seed=31, std=0.3)
+    r_o, r_g = _check_codec(oc, gc, x, the_share)
+    if the_share:   # the soft path has no discontinuity: end-to-end output must agree directly
+        assert rel_err(r_g['out'].cpu().numpy(), r_o['out'].numpy()) < TOL
+
+
+def test_codec_golden_fixture():
+    g = np.load(os.path.join(GOLD, 'codec.npz'))
+    for name, rt, st in [('bn2', 'bottleneck', (2,)), ('gln2', 'gln', (2,)), ('bn4', 'bottleneck', (2, 2))]:
+        oc, gc = _make_pair(rt, st, seed=3)
+        r = gc.computational_graph_end2end_quan_on(cu(g[name + '_x']), False, 1.0)
+        assert rel_err(r['floating_code'].cpu().numpy(), g[name + '_floating']) < TOL
+        same = r['code'].cpu().numpy() == g[name + '_code']
+        if same.all():
+            assert rel_err(r['out'].cpu().numpy(), g[name + '_out']) < TOL
+
+
+def test_codec_encode_decode_split_equals_fused_and_chunking():
+    """Properties at a production batch (B > the 2048-frame internal chunk, ragged last chunk)."""
+    oc, gc = _make_pair('bottleneck', (2,), seed=4)
+    B = 2048 + 300
+    x = cu(ar_frames(B, 512, seed=61, std=0.3))
+    full = gc.computational_graph_end2end_quan_on(x, False, 1.0)
+    enc = gc.encode(x)
+    assert torch.equal(enc['idx'], full['idx']) and torch.equal(enc['code'], full['code'])
+    dec = gc.decode_indices(enc['idx'])
+    assert torch.equal(dec, full['out'])
+    # batch invariance: the first 7 frames alone give the same bits as inside the big batch
+    small = gc.computational_graph_end2end_quan_on(x[:7].contiguous(), False, 1.0)
+    assert torch.equal(small['idx'], full['idx'][:7]) and torch.equal(small['out'], full['out'][:7])
+    # hard value is a codebook entry
+    assert torch.equal(full['code'], gc.bins[full['idx'].long()])
+
+
+def test_cascade_vs_oracle():
+    from nsc_b200 import codec
+    pairs = [_make_pair('bottleneck', (2,), seed=5), _make_pair('bottleneck', (2,), seed=6), _make_pair('gln', (2,), seed=7, nbins=64)]
+    x = ar_frames(3, 512, seed=71, std=0.3)
+    for lpc_variant, rs in ((False, 1.0), (False, 2.0), (True, 2.0)):
+        cm = codec.CMRL([p[1] for p in pairs], res_scalar=rs)
+        r = cm.all_modules_feedforward(cu(x), True, 1.0, lpc_variant=lpc_variant, want_stats=True, want_outs=True)
+        dec_o, outs_o, per_o = ref_codec.cascade_forward([p[0] for p in pairs], torch.from_numpy(x)[:, :, None], True, 1.0,
+                                                         res_scalar=rs, lpc_variant=lpc_variant)
+        assert rel_err(r['decoded'].cpu().numpy(), dec_o.numpy()) < TOL
+        for i in range(3):
+            assert rel_err(r['outs'][i].cpu().numpy(), outs_o[i].numpy()) < 2 * TOL
+            assert rel_err(r['hist'][i].cpu().numpy(), per_o[i]['soft'].reshape(-1, per_o[i]['soft'].shape[2]).sum(0).numpy()) < 1e-3
+            assert rel_err(r['qloss'][i].cpu().numpy(), ref_loss.quan_loss(per_o[i]['soft']).numpy()) < 1e-3
+        assert torch.allclose(r['decoded'], sum(r['outs']), atol=1e-6)
+
+
+def test_cq_feedforward_vs_oracle_and_golden():
+    from nsc_b200 import codec, loss_terms_and_measures as lt
+    g = np.load(os.path.join(GOLD, 'cq.npz'))
+    pairs = [_make_pair('bottleneck', (2,), seed=5), _make_pair('bottleneck', (2,), seed=6)]
+    cm = codec.CMRL([p[1] for p in pairs], res_scalar=1.0)
+    r = cm.feedforward_lpc(cu(g['x']), cu(g['lsf']), False, 1.0, want_stats=True)
+    assert rel_err(r['poly'].cpu().numpy(), g['poly']) < TOL
+    assert rel_err(r['res_x'].cpu().numpy(), g['res_x']) < TOL
+    # LSF codes bit-exact
+    idx_o = ref_nn.quantizer_indices(torch.from_numpy(g['lsf'])[:, :, None], -300.0, lsf_bins()).numpy()
+    assert np.array_equal(r['lsf_idx'].cpu().numpy(), idx_o.astype(np.uint8))
+    # soft path end to end (no discontinuity) against the oracle run on the same inputs
+    rs = cm.feedforward_lpc(cu(g['x']), cu(g['lsf']), True, 1.0, want_stats=True)
+    o = ref_codec.cq_feedforward([p[0] for p in pairs], -300.0, lsf_bins(), torch.from_numpy(g['x'])[:, :, None],
+                                 torch.from_numpy(g['lsf'])[:, :, None], True, 1.0, res_scalar=1.0)
+    assert rel_err(rs['decoded'].cpu().numpy(), o['decoded'].numpy()) < TOL
+    assert rel_err(rs['synthesized'].cpu().numpy(), o['synthesized']) < TOL
+    t, f = lt.losses(rs['decoded'], rs['res_x'])
+    assert rel_err(t.cpu().numpy(), o['time_loss'].numpy()) < TOL
+    assert rel_err(f.cpu().numpy(), o['freq_loss'].numpy()) < TOL
+    assert abs(float(lt.entropy_from_hist(rs['lsf_hist'])) - float(o['ent_lpc'])) < 1e-3
+    for i in range(2):
+        assert abs(float(lt.entropy_from_hist(rs['hist'][i])) - float(o['ent'][i])) < 1e-3
+    # hard path: synthesis parity given the GPU's own decoded residual and poly
+    syn_o = ref_lpc.lpc_synthesizer_tr(r['poly'].cpu().numpy(), r['decoded'].cpu().numpy())
+    assert rel_err(r['synthesized'].cpu().numpy(), syn_o) < 1e-5
+    # golden: first codec's floating code (before any quantiser decision) on the golden residual
+    e0 = pairs[0][1].encode(cu(g['res_x']))
+    assert rel_err(e0['floating_code'].cpu().numpy(), g['floating0']) < TOL
+
+
+def test_empty_batch_and_errors():
+    from nsc_b200 import codec, nn_core_operator as nn
+    oc, gc = _make_pair('bottleneck', (2,), seed=4)
+    r = gc.computational_graph_end2end_quan_on(torch.zeros(0, 512, device=DEV), False, 1.0)
+    assert r['out'].shape == (0, 512) and r['idx'].shape == (0, 256)
+    with pytest.raises(ValueError):
+        nn.conv1d(torch.zeros(1, 8, 3, device=DEV), 4, 3, params=(torch.zeros(3, 2, 4, device=DEV), torch.zeros(4, device=DEV)))
+    with pytest.raises(ValueError):
+        nn.conv1d(torch.zeros(1, 8, 3, device=DEV), 4, 3, dilation_rate=2, strides=2,
+                  params=(torch.zeros(3, 3, 4, device=DEV), torch.zeros(4, device=DEV)))
