@@ -335,6 +335,7 @@ static int codec_run(const nsc_codec_cfg* cfg, const float* params, const float*
 int nsc_codec_forward(const nsc_codec_cfg* cfg, const float* params, const float* x, int64_t B, float is_quan_on,
                       int32_t use_soft, float* floating_code, uint8_t* idx, float* code, float* out, float* soft,
                       float* hist, float* qloss, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch
   NSC_CHECK_ARG(x != nullptr && out != nullptr, "nsc_codec_forward: null x/out");
   return codec_run(cfg, params, x, nullptr, B, is_quan_on, use_soft, floating_code, idx, code, out, soft, hist, qloss,
                    workspace, workspace_bytes, stream, 3);
@@ -343,6 +344,7 @@ int nsc_codec_forward(const nsc_codec_cfg* cfg, const float* params, const float
 int nsc_codec_encode(const nsc_codec_cfg* cfg, const float* params, const float* x, int64_t B, float is_quan_on,
                      int32_t use_soft, float* floating_code, uint8_t* idx, float* code, float* soft, float* hist,
                      float* qloss, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch
   NSC_CHECK_ARG(x != nullptr, "nsc_codec_encode: null x");
   return codec_run(cfg, params, x, nullptr, B, is_quan_on, use_soft, floating_code, idx, code, nullptr, soft, hist,
                    qloss, workspace, workspace_bytes, stream, 1);
@@ -350,6 +352,7 @@ int nsc_codec_encode(const nsc_codec_cfg* cfg, const float* params, const float*
 
 int nsc_codec_decode(const nsc_codec_cfg* cfg, const float* params, const float* code, int64_t B, float* out,
                      void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch
   NSC_CHECK_ARG(code != nullptr && out != nullptr, "nsc_codec_decode: null code/out");
   return codec_run(cfg, params, nullptr, code, B, 1.0f, 0, nullptr, nullptr, nullptr, out, nullptr, nullptr, nullptr,
                    workspace, workspace_bytes, stream, 2);
@@ -425,8 +428,8 @@ int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float
                         int32_t use_soft, uint8_t* const* idx_ptrs_host, float* const* hist_ptrs_host,
                         float* const* qloss_ptrs_host, float* const* outs_ptrs_host, float* decoded,
                         void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_TRY(check_cascade_args(cfgs, n_codecs, params_ptrs_host, x, decoded, workspace, res_scalar));
-  if (B == 0) return NSC_OK;
   const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
   if (workspace_bytes < cascade_ws_bytes(cfgs, n_codecs, Bc)) {
     nsc::set_error("cascade: workspace %lld < %lld bytes", (long long)workspace_bytes,
@@ -463,10 +466,10 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
                    float* lsf_qloss, uint8_t* const* idx_ptrs_host, float* const* hist_ptrs_host,
                    float* const* qloss_ptrs_host, float* poly, float* res_x, float* decoded, float* synthesized,
                    void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_TRY(check_cascade_args(cfgs, n_codecs, params_ptrs_host, x, decoded, workspace, res_scalar));
   NSC_CHECK_ARG(lsf_params != nullptr && lsf != nullptr, "nsc_cq_forward: null LSF input");
   NSC_CHECK_ARG(n_lsf_bins >= 1 && n_lsf_bins <= 256, "nsc_cq_forward: n_lsf_bins=%d", n_lsf_bins);
-  if (B == 0) return NSC_OK;
   const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
   const int64_t need = cascade_ws_bytes(cfgs, n_codecs, Bc) + cq_extra_bytes(Bc);
   if (workspace_bytes < need) {
@@ -511,10 +514,10 @@ int64_t nsc_block_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t na
 int nsc_bottleneck_block(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t Cin,
                          int32_t wide, int32_t narrow, int32_t k_plain, int32_t k_dilated, int32_t dilation,
                          int32_t is_last_flat, int32_t gated, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(x && params && y && workspace, "nsc_bottleneck_block: null pointer");
   NSC_CHECK_ARG(Cin == wide || Cin == 1, "nsc_bottleneck_block: residual add needs Cin == wide or Cin == 1 (got %d vs %d)", Cin, wide);
   NSC_CHECK_ARG(workspace_bytes >= nsc_block_workspace_bytes(B, L, wide, narrow), "nsc_bottleneck_block: workspace too small");
-  if (B == 0) return NSC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   nsc::Carver cv(workspace, workspace_bytes);
   float* n0 = cv.take(B * (int64_t)L * narrow);

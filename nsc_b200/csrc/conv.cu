@@ -326,6 +326,7 @@ inline unsigned ew_grid(int64_t n) {
 }  // namespace
 
 int launch_conv(const ConvArgs& a, cudaStream_t st) {
+  if (a.B == 0) return NSC_OK;   // empty batch
   NSC_CHECK_ARG(a.x && a.w && a.y, "conv: null pointer");
   NSC_CHECK_ARG(a.Lin >= 1 && a.Cin >= 1 && a.Cout >= 1 && a.K >= 1 && a.dil >= 1 && a.stride >= 1,
                 "conv: bad shape Lin=%d Cin=%d Cout=%d K=%d dil=%d stride=%d", a.Lin, a.Cin, a.Cout, a.K, a.dil, a.stride);

@@ -159,9 +159,9 @@ int nsc_mel_filterbank(float* melw, void* stream) {
 
 int nsc_losses_forward(const float* decoded, const float* original, int64_t B, const float* melw,
                        float* time_loss, float* freq_loss, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(decoded && original, "nsc_losses_forward: null signal");
   NSC_CHECK_ARG(freq_loss == nullptr || melw != nullptr, "nsc_losses_forward: mel loss requested without filterbank");
-  if (B == 0) return NSC_OK;
   nsc::ProfScope prof((cudaStream_t)stream, "losses", (double)B * 2.0e5, (double)B * 4104.0);
   nsc::losses_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(decoded, original, B, melw, time_loss, freq_loss);
   NSC_LAUNCH_OK();

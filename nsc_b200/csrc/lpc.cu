@@ -376,8 +376,8 @@ extern "C" {
 
 int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, float* lsf_out_f32, int32_t* status,
                     void* stream) {
+  if (N == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(windows && (lsf_out || lsf_out_f32), "nsc_lpc_analyze: null pointer");
-  if (N == 0) return NSC_OK;
   nsc::ProfScope prof((cudaStream_t)stream, "lpc_analyze", (double)N * 2.0 * 17.0 * 1024.0, (double)N * (4096.0 + 128.0));
   nsc::lpc_analyze_kernel<0><<<(unsigned)nsc::ceil_div64(N, nsc::kAWarps), nsc::kAWarps * 32, 0,
                                (cudaStream_t)stream>>>(windows, N, lsf_out, lsf_out_f32, status);
@@ -387,8 +387,8 @@ int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, float* lsf
 
 int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, float* lsf_out_f32, int32_t* status,
                           void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(frames && (lsf_out || lsf_out_f32), "nsc_lpc_analyze_train: null pointer");
-  if (B == 0) return NSC_OK;
   nsc::lpc_analyze_kernel<1><<<(unsigned)nsc::ceil_div64(B, nsc::kAWarps), nsc::kAWarps * 32, 0,
                                (cudaStream_t)stream>>>(frames, B, lsf_out, lsf_out_f32, status);
   NSC_LAUNCH_OK();
@@ -396,8 +396,8 @@ int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, float
 }
 
 int nsc_lsf2poly(const float* lsf, int64_t B, float* poly, int32_t* status, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(lsf && poly, "nsc_lsf2poly: null pointer");
-  if (B == 0) return NSC_OK;
   nsc::ProfScope prof((cudaStream_t)stream, "lsf2poly", (double)B * 600.0, (double)B * (64.0 + 68.0));
   nsc::lsf2poly_kernel<<<(unsigned)nsc::ceil_div64(B, 128), 128, 0, (cudaStream_t)stream>>>(lsf, B, poly, status);
   NSC_LAUNCH_OK();
@@ -405,8 +405,8 @@ int nsc_lsf2poly(const float* lsf, int64_t B, float* poly, int32_t* status, void
 }
 
 int nsc_lpc_residual(const float* x, const float* poly, int64_t B, float* res, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(x && poly && res, "nsc_lpc_residual: null pointer");
-  if (B == 0) return NSC_OK;
   nsc::ProfScope prof((cudaStream_t)stream, "lpc_residual", (double)B * 2.0 * 15232.0, (double)B * 4164.0);
   nsc::lpc_residual_kernel<<<(unsigned)B, nsc::kFrame, 0, (cudaStream_t)stream>>>(x, poly, B, res);
   NSC_LAUNCH_OK();
@@ -414,8 +414,8 @@ int nsc_lpc_residual(const float* x, const float* poly, int64_t B, float* res, v
 }
 
 int nsc_lpc_synth(const float* poly, const float* res, int64_t B, float* y, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(poly && res && y, "nsc_lpc_synth: null pointer");
-  if (B == 0) return NSC_OK;
   nsc::ProfScope prof((cudaStream_t)stream, "lpc_synth", (double)B * 2.0 * 8192.0, (double)B * 4164.0);
   nsc::lpc_synth_kernel<<<(unsigned)nsc::ceil_div64(B, nsc::kSynFrames), nsc::kSynFrames, 0,
                           (cudaStream_t)stream>>>(poly, res, B, y);

@@ -190,6 +190,7 @@ soft_hist_kernel(const float* __restrict__ soft, int64_t rows, int n, int rows_p
 int launch_quantize(const float* x, int64_t B, int L, const float* bins, int n, const float* alpha, float iq,
                     int use_soft, float* out, uint8_t* idx, float* soft, float* hist, float* qloss,
                     cudaStream_t st) {
+  if (B == 0) return NSC_OK;   // empty batch
   NSC_CHECK_ARG(n >= 1 && n <= 256, "nsc_quantize_scalar: num bins %d not in [1,256]", n);
   NSC_CHECK_ARG(L >= 1 && L <= 4096, "nsc_quantize_scalar: code length %d not in [1,4096]", L);
   NSC_CHECK_ARG(x && bins && alpha, "nsc_quantize_scalar: null input");
@@ -228,8 +229,8 @@ int nsc_quantize_scalar(const float* x, int64_t B, int32_t L, const float* bins,
 }
 
 int nsc_dequantize_scalar(const uint8_t* idx, int64_t rows, const float* bins, int32_t n, float* out, void* stream) {
+  if (rows == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(n >= 1 && n <= 256, "nsc_dequantize_scalar: num bins %d not in [1,256]", n);
-  if (rows == 0) return NSC_OK;
   int64_t grid = nsc::ceil_div64(rows, 256);
   if (grid > 148 * 16) grid = 148 * 16;
   nsc::dequantize_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(idx, rows, bins, n, out);
@@ -238,16 +239,16 @@ int nsc_dequantize_scalar(const uint8_t* idx, int64_t rows, const float* bins, i
 }
 
 int nsc_quan_loss(const float* soft, int64_t B, int32_t L, int32_t n, float* qloss, void* stream) {
+  if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(soft && qloss && L >= 1 && n >= 1, "nsc_quan_loss: bad argument");
-  if (B == 0) return NSC_OK;
   nsc::quan_loss_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(soft, L, n, qloss);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
 
 int nsc_soft_histogram(const float* soft, int64_t rows, int32_t n, float* hist, void* stream) {
+  if (rows == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(soft && hist && n >= 1 && n <= 256, "nsc_soft_histogram: bad argument (n=%d)", n);
-  if (rows == 0) return NSC_OK;
   const int rows_per_cta = 1024;
   nsc::soft_hist_kernel<<<(unsigned)nsc::ceil_div64(rows, rows_per_cta), 256, 0, (cudaStream_t)stream>>>(
       soft, rows, n, rows_per_cta, hist);
