@@ -155,6 +155,9 @@ typedef struct nsc_codec_cfg {
   int32_t strides[NSC_MAX_STRIDES];
   int32_t resnet_type;               /* 0 = 'bottleneck', 1 = 'gln' (constants.py:13-14)         */
   int32_t num_bins;                  /* num_bins_for_follower[i]                                 */
+  int32_t precision;                 /* conv arithmetic: 0 = fp32 FFMA (CUDA cores, exact fp32)
+                                      *   1 = tcgen05 tensor cores, fp16 hi/lo split (3 MMAs, fp32-class results)
+                                      *   2 = tcgen05 tensor cores, fp16 inputs / fp32 accumulate (REDUCED precision) */
 } nsc_codec_cfg;
 
 /* Flat parameter image of one codec: conv parameters in TF creation order (kernel (k,cin,cout) then bias,

@@ -28,7 +28,7 @@ class CodecCfgStruct(C.Structure):
         ("k_dilated", C.c_int32), ("k_plain", C.c_int32), ("wide", C.c_int32), ("narrow", C.c_int32),
         ("n_blocks", C.c_int32), ("dilations", C.c_int32 * MAX_BLOCKS),
         ("n_strides", C.c_int32), ("strides", C.c_int32 * MAX_STRIDES),
-        ("resnet_type", C.c_int32), ("num_bins", C.c_int32),
+        ("resnet_type", C.c_int32), ("num_bins", C.c_int32), ("precision", C.c_int32),
     ]
 
 

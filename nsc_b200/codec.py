@@ -22,6 +22,7 @@ from . import _lib
 from . import constants as _c
 
 FRAME = _c.frame_length
+PRECISIONS = {'fp32': 0, 'tc_f16x3': 1, 'tc_f16': 2}
 
 
 @dataclass(frozen=True)
@@ -31,15 +32,18 @@ class CodecConfig:
     the_strides: Tuple[int, ...] = (2,)          # already expanded: '2' -> (2,), '4' -> (2, 2) (cmrl.py:32)
     resnet_type: str = 'bottleneck'              # constants.py:13-14
     num_bins: int = 32                           # num_bins_for_follower[i]
+    # conv arithmetic (not a reference knob): 'fp32' = FFMA on CUDA cores (exact fp32); 'tc_f16x3' = tcgen05 tensor
+    # cores with the fp16 hi/lo split (fp32-class results, the default); 'tc_f16' = plain fp16 inputs (reduced)
+    precision: str = 'tc_f16x3'
 
     @staticmethod
     def from_args(bottleneck_kernel_and_dilation: str = '9 9 100 20 1 2', the_strides: str = '2',
-                  num_bins: int = 32, resnet_type: str = 'bottleneck') -> "CodecConfig":
+                  num_bins: int = 32, resnet_type: str = 'bottleneck', precision: str = 'tc_f16x3') -> "CodecConfig":
         """Parses the reference's string flags (nscm.py:33, :69; stride expansion cmrl.py:32, :168)."""
         bkd = tuple(int(v) for v in bottleneck_kernel_and_dilation.split())
         s = [int(v) for v in the_strides.split()]
         strides = (2, 2) if s[0] == 4 else (2,)
-        return CodecConfig(bkd, strides, resnet_type, num_bins)
+        return CodecConfig(bkd, strides, resnet_type, num_bins, precision)
 
     @property
     def code_length(self) -> int:
@@ -63,6 +67,9 @@ class CodecConfig:
             raise ValueError("resnet_type must be 'bottleneck' or 'gln'")
         s.resnet_type = 0 if self.resnet_type == 'bottleneck' else 1
         s.num_bins = self.num_bins
+        if self.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        s.precision = PRECISIONS[self.precision]
         return s
 
 

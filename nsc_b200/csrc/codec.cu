@@ -26,6 +26,7 @@ int validate_cfg(const nsc_codec_cfg* c) {
   NSC_CHECK_ARG(c->n_strides >= 1 && c->n_strides <= NSC_MAX_STRIDES, "codec cfg: n_strides=%d", c->n_strides);
   NSC_CHECK_ARG(c->resnet_type == 0 || c->resnet_type == 1, "codec cfg: resnet_type=%d", c->resnet_type);
   NSC_CHECK_ARG(c->num_bins >= 1 && c->num_bins <= 256, "codec cfg: num_bins=%d", c->num_bins);
+  NSC_CHECK_ARG(c->precision >= 0 && c->precision <= 2, "codec cfg: precision=%d", c->precision);
   int L = kFrameLen, C = c->wide;
   for (int i = 0; i < c->n_strides; ++i) {
     NSC_CHECK_ARG(c->strides[i] >= 1 && L % c->strides[i] == 0, "codec cfg: stride %d does not divide %d", c->strides[i], L);
@@ -56,6 +57,7 @@ struct Walker {
   int64_t off = 0;
   float* wide[3] = {nullptr, nullptr, nullptr};
   float* nar[3] = {nullptr, nullptr, nullptr};
+  void* wpack = nullptr;   // scratch for the tensor engine's packed weights
   int rc = NSC_OK;
 
   const LayerInfo* next_layer(int k, int cin, int cout, int separable) {
@@ -83,7 +85,8 @@ struct Walker {
     a.bias = a.w + (int64_t)K * Cin * Cout;
     a.res = res; a.res_mode = res_mode; a.post_act = post_act; a.shuffle = shuffle;
     a.B = B; a.Lin = Lin; a.Cin = Cin; a.Cout = Cout; a.K = K; a.dil = dil; a.stride = stride; a.act = act;
-    rc = launch_conv(a, st);
+    if (cfg.precision > 0 && wpack != nullptr && tc_conv_supported(a)) rc = launch_conv_tc(a, cfg.precision, wpack, st);
+    else rc = launch_conv(a, st);   // 1-channel stem / heads and odd shapes stay on the FFMA engine
   }
 
   // Keras SeparableConv1D: depthwise (k, cin, 1) -> pointwise (1, cin, cout) + bias + activation
@@ -205,8 +208,8 @@ int64_t codec_ws_floats_per_frame(const nsc_codec_cfg& c) {
 }
 
 int64_t codec_ws_bytes(const nsc_codec_cfg& c, int64_t Bc) {
-  // 8 carved buffers, each rounded up to 256 bytes
-  return codec_ws_floats_per_frame(c) * Bc * (int64_t)sizeof(float) + 8 * 256;
+  // 8 carved buffers, each rounded up to 256 bytes, plus the tensor engine's weight scratch
+  return codec_ws_floats_per_frame(c) * Bc * (int64_t)sizeof(float) + 9 * 256 + kTcWpackBytes;
 }
 
 struct CodecBuffers {
@@ -214,6 +217,7 @@ struct CodecBuffers {
   float* nar[3];
   float* fcode;
   float* code;
+  void* wpack;
 };
 
 CodecBuffers carve_codec(Carver& cv, const nsc_codec_cfg& c, int64_t Bc) {
@@ -222,6 +226,7 @@ CodecBuffers carve_codec(Carver& cv, const nsc_codec_cfg& c, int64_t Bc) {
   for (int i = 0; i < 3; ++i) b.nar[i] = cv.take(Bc * c.narrow * kFrameLen);
   b.fcode = cv.take(Bc * code_length(c));
   b.code = cv.take(Bc * code_length(c));
+  b.wpack = cv.take(kTcWpackBytes / (int64_t)sizeof(float));
   return b;
 }
 
@@ -238,6 +243,7 @@ int run_codec_chunk(const nsc_codec_cfg& cfg, const CodecLayout& lay, const floa
   w.st = st;
   w.layers = lay.layers;
   for (int i = 0; i < 3; ++i) { w.wide[i] = buf.wide[i]; w.nar[i] = buf.nar[i]; }
+  w.wpack = buf.wpack;
   float* fc = fcode ? fcode : buf.fcode;
   float* cd = code ? code : buf.code;
   if (which & 1) {

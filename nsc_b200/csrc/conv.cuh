@@ -27,6 +27,13 @@ struct ConvArgs {
 
 int launch_conv(const ConvArgs& a, cudaStream_t st);
 
+// Tensor-core engine (tc_conv.cu): same tensors and epilogue, tcgen05 implicit GEMM.
+//   precision 1 = fp16 hi/lo split, 3 MMAs, fp32-class results; 2 = fp16 inputs (reduced precision).
+bool tc_conv_supported(const ConvArgs& a);
+int64_t tc_wpack_bytes(int K, int Cin, int Cout);
+int launch_conv_tc(const ConvArgs& a, int precision, void* wpack, cudaStream_t st);
+constexpr int64_t kTcWpackBytes = 1 << 20;   // scratch for one layer's packed fp16 weights
+
 // depthwise part of SeparableConv1D: y[b,c,p] = sum_t x[b,c,p*s + t*d - padL] * dw[t,c]   (no bias)
 int launch_depthwise(const float* x, const float* dw, float* y, int64_t B, int Lin, int C, int K, int dil,
                      int stride, int x_cl, int y_cl, cudaStream_t st);
