@@ -298,7 +298,7 @@ int launch_conv_tc(const ConvArgs& a, int precision, void* wpack, cudaStream_t s
   p.tmem_cols = cols;
   p.wpack = reinterpret_cast<const uint4*>(wpack);
   const size_t smem = 1024 + (size_t)p.nbuf * p.slabs * p.rows * 128 + 2ull * p.slabs * p.n_pad * 128;
-  NSC_CHECK_ARG(smem <= 227 * 1024, "tensor conv: needs %zu bytes of shared memory", smem);
+  NSC_CHECK_ARG(smem + 256 <= 227 * 1024, "tensor conv: needs %zu bytes of shared memory", smem);
   {
     const int total = 2 * a.K * p.slabs * p.n_pad * 64;
     ProfScope prof(st, "tc_pack_weights", 0.0, 4.0 * a.K * a.Cin * a.Cout + 2.0 * total);
@@ -306,7 +306,7 @@ int launch_conv_tc(const ConvArgs& a, int precision, void* wpack, cudaStream_t s
         a.w, a.K, a.Cin, a.Cout, p.n_pad, p.slabs, reinterpret_cast<__half*>(wpack));
     NSC_LAUNCH_OK();
   }
-  NSC_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  NSC_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   char name[32];
   snprintf(name, sizeof(name), "tc%d_k%dd%ds%d_c%dto%d", precision, a.K, a.dil, a.stride, a.Cin, a.Cout);
   const double macs = (double)a.B * p.Lout * a.K * a.Cin * a.Cout;

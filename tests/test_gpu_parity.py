@@ -303,8 +303,13 @@ def test_codec_forward_vs_oracle(rt, st, the_share, precision):
     oc, gc = _make_pair(rt, st, seed=3, precision=precision)
     x = ar_frames(3, 512, seed=31, std=0.3)
     r_o, r_g = _check_codec(oc, gc, x, the_share)
-    if the_share:   # the soft path has no discontinuity: end-to-end output must agree directly
-        assert rel_err(r_g['out'].cpu().numpy(), r_o['out'].numpy()) < TOL
+    if the_share:
+        # The soft path has no discontinuity, so the END-TO-END output can be compared directly -- but the alpha=-300
+        # soft quantiser is steep (slope ~ alpha * bin spacing ~ 20), so fp32 rounding noise of the encoder is
+        # amplified: measure the fp32 oracle's own distance from float64 truth and allow 1e-4 on top of it.
+        r64 = oc.forward(torch.from_numpy(x).double()[:, :, None], the_share, 1.0)['out'].numpy()
+        floor = rel_err(r_o['out'].numpy(), r64)
+        assert rel_err(r_g['out'].cpu().numpy(), r64) < TOL + floor
 
 
 def test_codec_reduced_precision_fp16_is_stated_separately():
