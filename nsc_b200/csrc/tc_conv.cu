@@ -18,6 +18,7 @@
 //   (4 KB) is re-read from shared memory by every instruction, so narrow layers (N_pad = 32) are bound by
 //   shared-memory bandwidth, not by the tensor pipe.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "conv.cuh"
 
@@ -251,6 +252,246 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(p.tmem_cols) : "memory");
 }
 
+// ================================================================================================
+// Persistent, warp-specialised pipeline (the default).  Work unit = TILE output positions of one frame
+// (TILE = 256 = two M-tiles, or 128 when Lout = 128); CTAs loop over tiles round-robin.
+//
+//   warps 0-3   epilogue      wait acc_full[k]  -> TMEM -> bias/act/residual -> NCL fp32 stores -> arrive acc_empty[k]
+//   warp  4     MMA issuer    one elected thread: wait a_full / b_full, issue tcgen05.mma, tcgen05.commit -> b_empty,
+//                             a_empty, acc_full
+//   warp  5     B producer    one elected thread: cp.async.bulk of pre-packed weight stages (tap, slab) into a ring
+//   warps 6-13  A producers   NCL fp32 -> fp16 plane -> K-major SW128 rows of A buffer (job & 1); arrive a_full
+//
+// Two A buffers (hi / lo plane of a tile in split mode, consecutive tiles otherwise), kBStages weight stages and two
+// TMEM accumulator sets decouple the four roles: staging of tile i+1 and the epilogue of tile i-1 overlap the MMAs
+// of tile i.  All hand-offs are mbarriers; tensor-core completions arrive through tcgen05.commit.
+// ================================================================================================
+constexpr int kEpiWarps = 4, kAProdWarps = 8;
+constexpr int kPipeThreads = (kEpiWarps + 2 + kAProdWarps) * 32;   // 448
+constexpr int kBStages = 4;
+
+struct TcPipe {
+  ConvArgs a;
+  int Lout, padL;
+  int n_pad, ksteps, slabs;
+  int tile;          // output positions per work unit (128 or 256)
+  int mt;            // tile / 128
+  int tiles_per_frame;
+  int64_t n_tiles;
+  int rows;          // rows per (sub-buffer, slab), multiple of 8
+  int nsub;          // = stride
+  int passes;
+  int tmem_cols;
+  const uint4* wpack;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __grid_constant__ TcPipe p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t a_full[2], a_empty[2], b_full[kBStages], b_empty[kBStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const ConvArgs& a = p.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t slab_bytes = (uint32_t)p.rows * 128u;
+  const uint32_t sub_bytes = slab_bytes * (uint32_t)p.slabs;
+  const uint32_t abuf_bytes = sub_bytes * (uint32_t)p.nsub;
+  const uint32_t bstage_bytes = (uint32_t)p.n_pad * 128u;
+  uint8_t* sA = smem;                           // 2 A buffers
+  uint8_t* sB = smem + 2u * abuf_bytes;         // kBStages weight stages
+
+  for (uint32_t i = tid; i < 2u * abuf_bytes / 16; i += kPipeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], kAProdWarps);     // one arrival per producer warp
+      mbar_init(&a_empty[i], 1);              // tcgen05.commit
+      mbar_init(&acc_full[i], 1);             // tcgen05.commit
+      mbar_init(&acc_empty[i], kEpiWarps);    // one arrival per epilogue warp
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], 1);               // expect_tx arrival + bulk-copy bytes
+      mbar_init(&b_empty[i], 1);              // tcgen05.commit
+    }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int acc_cols = p.mt * p.n_pad;
+  const int jobs_per_tile = p.passes == 3 ? 2 : 1;          // A planes needed per tile
+  const int stages_per_pass = a.K * p.slabs;
+
+  if (warp < kEpiWarps) {
+    // =========================== epilogue ===========================
+    const int Cres = a.res_mode == RES_ADD_BCAST ? 1 : a.Cout;
+    const int r = a.shuffle;
+    const int Lout_y = p.Lout * r, Cout_y = a.Cout / r;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int64_t b = tile / p.tiles_per_frame;
+      const int q0 = (int)(tile - b * p.tiles_per_frame) * p.tile;
+      const uint32_t acc = it & 1u;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* yb = a.y + b * (int64_t)Lout_y * Cout_y;
+      const float* rb = a.res ? a.res + b * (int64_t)p.Lout * Cres : nullptr;
+      for (int mt = 0; mt < p.mt; ++mt) {
+        const int pos = q0 + mt * 128 + warp * 32 + lane;
+        for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_cols + mt * p.n_pad + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = c0 + j;
+            if (co >= a.Cout) break;
+            float o = apply_act(__uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + co) : 0.f), a.act);
+            if (a.res_mode != RES_NONE) {
+              const float rv = rb[(int64_t)(a.res_mode == RES_ADD_BCAST ? 0 : co) * p.Lout + pos];
+              o = a.res_mode == RES_MUL ? o * rv : o + rv;
+            }
+            o = apply_act(o, a.post_act);
+            if (r == 1) yb[(int64_t)co * Lout_y + pos] = o;
+            else yb[(int64_t)(co / r) * Lout_y + (int64_t)pos * r + (co % r)] = o;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(p.n_pad);
+      uint32_t it = 0, job = 0, bit = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait(&acc_empty[acc], ((it >> 1) & 1u) ^ 1u);
+        const uint32_t job_hi = job, job_lo = job + 1;     // job_lo only meaningful in split mode
+        for (int pass = 0; pass < p.passes; ++pass) {
+          const uint32_t jb = pass == 2 ? job_lo : job_hi;
+          if (pass == 0 || pass == 2) mbar_wait(&a_full[jb & 1u], (jb >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_buf = smem_u32(sA) + (jb & 1u) * abuf_bytes;
+          for (int t = 0; t < a.K; ++t) {
+            const int shift = t * a.dil;
+            const uint32_t sub = (uint32_t)(shift % p.nsub), rowoff = (uint32_t)(shift / p.nsub);
+            for (int sl = 0; sl < p.slabs; ++sl, ++bit) {
+              const uint32_t s = bit % kBStages;
+              mbar_wait(&b_full[s], (bit / kBStages) & 1u);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t b_base = smem_u32(sB) + s * bstage_bytes;
+              const int ks_n = min(4, p.ksteps - sl * 4);
+              for (int mt = 0; mt < p.mt; ++mt) {
+                const uint32_t d = tmem + (uint32_t)(acc * acc_cols + mt * p.n_pad);
+                const uint32_t a_row = a_buf + sub * sub_bytes + (uint32_t)sl * slab_bytes + ((uint32_t)(mt * 128) + rowoff) * 128u;
+                for (int ks = 0; ks < ks_n; ++ks)
+                  mma_f16_ss(d, make_desc_sw128(a_row + (uint32_t)ks * 32u), make_desc_sw128(b_base + (uint32_t)ks * 32u), idesc,
+                             (pass | t | sl | ks) != 0 ? 1u : 0u);
+              }
+              umma_commit(&b_empty[s]);            // weight stage reusable once these MMAs retire
+            }
+          }
+          // A buffers: hi is last read in pass 1 (split) or pass 0 (plain); lo in pass 2
+          if (p.passes == 1) umma_commit(&a_empty[job_hi & 1u]);
+          else if (pass == 1) umma_commit(&a_empty[job_hi & 1u]);
+          else if (pass == 2) umma_commit(&a_empty[job_lo & 1u]);
+        }
+        umma_commit(&acc_full[acc]);
+        job += (uint32_t)jobs_per_tile;
+      }
+    }
+  } else if (warp == 5) {
+    // =========================== B producer (bulk copies) ===========================
+    if (elect_one()) {
+      uint32_t bit = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int pass = 0; pass < p.passes; ++pass) {
+          const int b_plane = pass == 1 ? 1 : 0;
+          const uint4* src0 = p.wpack + (size_t)b_plane * stages_per_pass * (size_t)(p.n_pad * 8);
+          for (int st = 0; st < stages_per_pass; ++st, ++bit) {
+            const uint32_t s = bit % kBStages;
+            mbar_wait(&b_empty[s], ((bit / kBStages) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], bstage_bytes);
+            bulk_g2s(sB + s * bstage_bytes, src0 + (size_t)st * (size_t)(p.n_pad * 8), bstage_bytes, &b_full[s]);
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== A producers ===========================
+    const int ptid = tid - (kEpiWarps + 2) * 32, nprod = kAProdWarps * 32;
+    const int groups = (a.Cin + 7) >> 3;
+    const int span = p.rows * p.nsub;               // u-coordinates covered by one buffer
+    uint32_t job = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int64_t b = tile / p.tiles_per_frame;
+      const int q0 = (int)(tile - b * p.tiles_per_frame) * p.tile;
+      const float* xb = a.x + b * (int64_t)a.Cin * a.Lin;
+      const int u0 = q0 * p.nsub;                    // first u = pos + padL of this tile
+      for (int plane = 0; plane < jobs_per_tile; ++plane, ++job) {
+        const uint32_t buf = job & 1u;
+        mbar_wait(&a_empty[buf], ((job >> 1) & 1u) ^ 1u);
+        uint8_t* dstA = sA + buf * abuf_bytes;
+        for (int i = ptid; i < groups * span; i += nprod) {
+          const int g = i / span, j = i - g * span;
+          const int pos = u0 + j - p.padL;
+          const bool inside = pos >= 0 && pos < a.Lin;
+          const int c0 = g << 3;
+          __half h[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float v = (inside && c0 + jj < a.Cin) ? xb[(int64_t)(c0 + jj) * a.Lin + pos] : 0.f;
+            const __half hi = __float2half_rn(v);
+            h[jj] = plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
+          }
+          const int sub = j % p.nsub, row = j / p.nsub;
+          const int slab = g >> 3, chunk = g & 7;
+          uint8_t* dst = dstA + (uint32_t)sub * sub_bytes + (uint32_t)slab * slab_bytes + (uint32_t)row * 128u +
+                         (uint32_t)((chunk ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);
+      }
+    }
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 4) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 }  // namespace
 
 // bytes of packed weights the tensor engine needs for one layer
@@ -271,6 +512,39 @@ bool tc_conv_supported(const ConvArgs& a) {
   if (mt * n_pad > 512) return false;
   if (a.shuffle != 1 && a.Cout % a.shuffle != 0) return false;
   return true;
+}
+
+
+static int launch_conv_tc_pipe(const ConvArgs& a, int precision, void* wpack, cudaStream_t st) {
+  TcPipe p;
+  p.a = a;
+  same_padding(a.Lin, a.K, a.dil, a.stride, &p.Lout, &p.padL);
+  p.n_pad = (a.Cout + 15) & ~15;
+  p.ksteps = (a.Cin + 15) / 16;
+  p.slabs = (a.Cin + 63) / 64;
+  p.tile = p.Lout % 256 == 0 ? 256 : 128;
+  p.mt = p.tile / 128;
+  p.tiles_per_frame = p.Lout / p.tile;
+  p.n_tiles = a.B * p.tiles_per_frame;
+  p.nsub = a.stride;
+  p.rows = ((p.tile + ((a.K - 1) * a.dil) / a.stride + 1) + 7) & ~7;
+  p.passes = precision == 1 ? 3 : 1;
+  int cols = 32;
+  while (cols < 2 * p.mt * p.n_pad) cols *= 2;
+  p.tmem_cols = cols;
+  p.wpack = reinterpret_cast<const uint4*>(wpack);
+  const size_t smem = 1024 + 2ull * p.nsub * p.slabs * p.rows * 128 + (size_t)kBStages * p.n_pad * 128;
+  if (cols > 512 || smem + 512 > 227 * 1024) return 1;   // caller falls back to the simple kernel
+  NSC_CUDA_OK(cudaFuncSetAttribute(tc_conv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  char name[32];
+  snprintf(name, sizeof(name), "tc%d_k%dd%ds%d_c%dto%d", precision, a.K, a.dil, a.stride, a.Cin, a.Cout);
+  const double macs = (double)a.B * p.Lout * a.K * a.Cin * a.Cout;
+  const double bytes = 4.0 * ((double)a.B * ((double)a.Lin * a.Cin + (double)p.Lout * a.Cout) + (double)a.K * a.Cin * a.Cout);
+  ProfScope prof(st, name, 2.0 * macs, bytes);
+  const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  tc_conv_pipe_kernel<<<(unsigned)grid, kPipeThreads, smem, st>>>(p);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
 }
 
 // precision: 1 = fp16 hi/lo split (3 MMAs, fp32-class), 2 = fp16 inputs only.  wpack: tc_wpack_bytes() scratch.
@@ -305,6 +579,11 @@ int launch_conv_tc(const ConvArgs& a, int precision, void* wpack, cudaStream_t s
     tc_pack_weights_kernel<<<ceil_div(total, 256) < 592 ? ceil_div(total, 256) : 592, 256, 0, st>>>(
         a.w, a.K, a.Cin, a.Cout, p.n_pad, p.slabs, reinterpret_cast<__half*>(wpack));
     NSC_LAUNCH_OK();
+  }
+  static const bool force_simple = getenv("NSC_TC_SIMPLE") != nullptr;   // debugging aid: one-CTA-per-frame kernel
+  if (!force_simple) {
+    const int rc = launch_conv_tc_pipe(a, precision, wpack, st);
+    if (rc <= 0) return rc;
   }
   NSC_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   char name[32];
