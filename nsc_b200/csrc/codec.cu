@@ -3,6 +3,8 @@
 // kernel launches.  The topology is written ONCE (struct Walker): a dry walk enumerates the conv layers in the
 // order TensorFlow would create their variables -- which defines the flat parameter image -- and the live walk
 // issues the launches.  Frames are processed in chunks so the activation workspace stays bounded.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "conv.cuh"
@@ -12,7 +14,16 @@ namespace nsc {
 namespace {
 
 constexpr int kFrameLen = NSC_FRAME_LENGTH;
-constexpr int64_t kChunkFrames = 2048;   // frames per internal pass (bounds the activation workspace)
+// frames per internal pass (bounds the activation workspace); NSC_CHUNK_FRAMES overrides it for experiments
+static int64_t chunk_frames() {
+  static const int64_t v = [] {
+    const char* e = getenv("NSC_CHUNK_FRAMES");
+    const long long n = e ? atoll(e) : 0;
+    return (int64_t)(n >= 16 && n <= 65536 ? n : 2048);
+  }();
+  return v;
+}
+#define kChunkFrames (::nsc::chunk_frames())
 
 struct LayerInfo {
   int k, cin, cout, separable;
@@ -270,7 +281,6 @@ int run_codec_chunk(const nsc_codec_cfg& cfg, const CodecLayout& lay, const floa
 }  // namespace
 }  // namespace nsc
 
-using nsc::kChunkFrames;
 using nsc::kFrameLen;
 
 extern "C" {

@@ -256,19 +256,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 // Persistent, warp-specialised pipeline (the default).  Work unit = TILE output positions of one frame
 // (TILE = 256 = two M-tiles, or 128 when Lout = 128); CTAs loop over tiles round-robin.
 //
-//   warps 0-3   epilogue      wait acc_full[k]  -> TMEM -> bias/act/residual -> NCL fp32 stores -> arrive acc_empty[k]
-//   warp  4     MMA issuer    one elected thread: wait a_full / b_full, issue tcgen05.mma, tcgen05.commit -> b_empty,
+//   warps 0-7   epilogue      wait acc_full[k]  -> TMEM -> bias/act/residual -> NCL fp32 stores -> arrive acc_empty[k]
+//                             (two warps per TMEM lane quarter; 32 residual loads in flight per thread)
+//   warp  8     MMA issuer    one elected thread: wait a_full / b_full, issue tcgen05.mma, tcgen05.commit -> b_empty,
 //                             a_empty, acc_full
-//   warp  5     B producer    one elected thread: cp.async.bulk of pre-packed weight stages (tap, slab) into a ring
-//   warps 6-13  A producers   NCL fp32 -> fp16 plane -> K-major SW128 rows of A buffer (job & 1); arrive a_full
+//   warp  9     B producer    one elected thread: cp.async.bulk of pre-packed weight stages (tap, slab) into a ring
+//   warps 10-17 A producers   NCL fp32 -> fp16 plane -> K-major SW128 rows of A buffer (job & 1); arrive a_full
 //
-// Two A buffers (hi / lo plane of a tile in split mode, consecutive tiles otherwise), kBStages weight stages and two
+// Two A buffers (hi / lo plane of a tile in split mode, consecutive tiles otherwise), a ring of weight stages and two
 // TMEM accumulator sets decouple the four roles: staging of tile i+1 and the epilogue of tile i-1 overlap the MMAs
 // of tile i.  All hand-offs are mbarriers; tensor-core completions arrive through tcgen05.commit.
 // ================================================================================================
-constexpr int kEpiWarps = 4, kAProdWarps = 8;
-constexpr int kPipeThreads = (kEpiWarps + 2 + kAProdWarps) * 32;   // 448
-constexpr int kBStages = 4;
+constexpr int kEpiWarps = 8, kAProdWarps = 8;
+constexpr int kPipeThreads = (kEpiWarps + 2 + kAProdWarps) * 32;   // 576
+constexpr int kATasks = 4;        // A-producer tasks (8 loads each) in flight per thread
+constexpr int kMaxBStages = 32;   // weight ring depth is chosen per layer from the shared memory left over (TcPipe::bstages)
 
 struct TcPipe {
   ConvArgs a;
@@ -282,6 +284,9 @@ struct TcPipe {
   int nsub;          // = stride
   int passes;
   int tmem_cols;
+  int bstages;       // weight ring depth (2..kMaxBStages)
+  int group;         // (tap, slab) weight units per ring stage
+  int stages_per_pass;
   const uint4* wpack;
 };
 
@@ -304,7 +309,7 @@ __device__ __forceinline__ bool elect_one() {
 __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __grid_constant__ TcPipe p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t a_full[2], a_empty[2], b_full[kBStages], b_empty[kBStages], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full[2], a_empty[2], b_full[kMaxBStages], b_empty[kMaxBStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const ConvArgs& a = p.a;
@@ -312,9 +317,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
   const uint32_t slab_bytes = (uint32_t)p.rows * 128u;
   const uint32_t sub_bytes = slab_bytes * (uint32_t)p.slabs;
   const uint32_t abuf_bytes = sub_bytes * (uint32_t)p.nsub;
-  const uint32_t bstage_bytes = (uint32_t)p.n_pad * 128u;
+  const uint32_t unit_bytes = (uint32_t)p.n_pad * 128u;            // one (tap, slab) weight unit
+  const uint32_t bstage_bytes = unit_bytes * (uint32_t)p.group;    // one ring stage = `group` consecutive units
   uint8_t* sA = smem;                           // 2 A buffers
-  uint8_t* sB = smem + 2u * abuf_bytes;         // kBStages weight stages
+  uint8_t* sB = smem + 2u * abuf_bytes;         // p.bstages weight stages
 
   for (uint32_t i = tid; i < 2u * abuf_bytes / 16; i += kPipeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -324,13 +330,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
       mbar_init(&acc_full[i], 1);             // tcgen05.commit
       mbar_init(&acc_empty[i], kEpiWarps);    // one arrival per epilogue warp
     }
-    for (int i = 0; i < kBStages; ++i) {
+    for (int i = 0; i < p.bstages; ++i) {
       mbar_init(&b_full[i], 1);               // expect_tx arrival + bulk-copy bytes
       mbar_init(&b_empty[i], 1);              // tcgen05.commit
     }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -340,13 +346,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
   const uint32_t tmem = tmem_base_s;
   const int acc_cols = p.mt * p.n_pad;
   const int jobs_per_tile = p.passes == 3 ? 2 : 1;          // A planes needed per tile
-  const int stages_per_pass = a.K * p.slabs;
 
   if (warp < kEpiWarps) {
     // =========================== epilogue ===========================
     const int Cres = a.res_mode == RES_ADD_BCAST ? 1 : a.Cout;
     const int r = a.shuffle;
     const int Lout_y = p.Lout * r, Cout_y = a.Cout / r;
+    const int quarter = warp & 3, half = warp >> 2;        // TMEM lanes [32*quarter, +32); two warps share a quarter
+    const int nbatch = (a.Cout + 15) >> 4;                 // 16-column units per M-tile
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int64_t b = tile / p.tiles_per_frame;
@@ -354,70 +361,98 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
       const uint32_t acc = it & 1u;
       mbar_wait(&acc_full[acc], (it >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float* yb = a.y + b * (int64_t)Lout_y * Cout_y;
-      const float* rb = a.res ? a.res + b * (int64_t)p.Lout * Cres : nullptr;
-      for (int mt = 0; mt < p.mt; ++mt) {
-        const int pos = q0 + mt * 128 + warp * 32 + lane;
-        for (int c0 = 0; c0 < a.Cout; c0 += 16) {
-          uint32_t v[16];
-          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_cols + mt * p.n_pad + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* __restrict__ yb = a.y + b * (int64_t)Lout_y * Cout_y;
+      const float* __restrict__ rb = a.res ? a.res + b * (int64_t)p.Lout * Cres : nullptr;
+      const int n_units = p.mt * nbatch;
+      auto load_res = [&](int u, float (&rv)[16]) {
+        const int mt = u / nbatch, c0 = (u - mt * nbatch) << 4;
+        const int pos = q0 + mt * 128 + quarter * 32 + lane;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int co = c0 + j;
-            if (co >= a.Cout) break;
+        for (int j = 0; j < 16; ++j) {
+          const int co = c0 + j;
+          rv[j] = (a.res_mode != RES_NONE && u < n_units && co < a.Cout)
+                      ? __ldg(rb + (int64_t)(a.res_mode == RES_ADD_BCAST ? 0 : co) * p.Lout + pos) : 0.f;
+        }
+      };
+      float rv[16], rvn[16];
+      load_res(half, rv);
+      for (int u = half; u < n_units; u += 2) {
+        const int mt = u / nbatch, c0 = (u - mt * nbatch) << 4;
+        const int pos = q0 + mt * 128 + quarter * 32 + lane;
+        uint32_t v[16];
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + mt * p.n_pad + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        load_res(u + 2, rvn);        // residual of this warp's NEXT unit is in flight while this one is written
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = c0 + j;
+          if (co < a.Cout) {
             float o = apply_act(__uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + co) : 0.f), a.act);
-            if (a.res_mode != RES_NONE) {
-              const float rv = rb[(int64_t)(a.res_mode == RES_ADD_BCAST ? 0 : co) * p.Lout + pos];
-              o = a.res_mode == RES_MUL ? o * rv : o + rv;
-            }
+            if (a.res_mode == RES_MUL) o *= rv[j];
+            else if (a.res_mode != RES_NONE) o += rv[j];
             o = apply_act(o, a.post_act);
             if (r == 1) yb[(int64_t)co * Lout_y + pos] = o;
             else yb[(int64_t)(co / r) * Lout_y + (int64_t)pos * r + (co % r)] = o;
           }
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rv[j] = rvn[j];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kEpiWarps) {
     // =========================== MMA issuer ===========================
+    // One thread feeds the tensor core.  Descriptors are NOT rebuilt per instruction: the upper 32 bits (stride,
+    // version, swizzle mode) are constant and the lower word is (smem address >> 4) | LBO, so advancing along K or
+    // to the next position tile is an integer add (the first build spent ~140 cycles of address arithmetic per MMA,
+    // three times the 44-cycle cost of the instruction itself).
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(p.n_pad);
+      const uint32_t desc_hi = (uint32_t)(make_desc_sw128(0) >> 32);
+      auto mk = [desc_hi](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      auto lo_of = [](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | 0x10000u; };
+      const uint32_t mt_step = (128u * 128u) >> 4;           // next 128-position tile of the same buffer
       uint32_t it = 0, job = 0, bit = 0;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         mbar_wait(&acc_empty[acc], ((it >> 1) & 1u) ^ 1u);
+        const uint32_t d0 = tmem + acc * (uint32_t)acc_cols;
         const uint32_t job_hi = job, job_lo = job + 1;     // job_lo only meaningful in split mode
         for (int pass = 0; pass < p.passes; ++pass) {
           const uint32_t jb = pass == 2 ? job_lo : job_hi;
           if (pass == 0 || pass == 2) mbar_wait(&a_full[jb & 1u], (jb >> 1) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_buf = smem_u32(sA) + (jb & 1u) * abuf_bytes;
-          for (int t = 0; t < a.K; ++t) {
-            const int shift = t * a.dil;
-            const uint32_t sub = (uint32_t)(shift % p.nsub), rowoff = (uint32_t)(shift / p.nsub);
-            for (int sl = 0; sl < p.slabs; ++sl, ++bit) {
-              const uint32_t s = bit % kBStages;
-              mbar_wait(&b_full[s], (bit / kBStages) & 1u);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t b_base = smem_u32(sB) + s * bstage_bytes;
+          int t = 0, sl = 0;
+          for (int st = 0; st < p.stages_per_pass; ++st, ++bit) {
+            const uint32_t s = bit % (uint32_t)p.bstages;
+            mbar_wait(&b_full[s], (bit / (uint32_t)p.bstages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t b_lo = lo_of(smem_u32(sB) + s * bstage_bytes);
+            for (int g = 0; g < p.group; ++g) {               // (tap, slab) units of this stage
+              const int shift = t * a.dil;
+              const uint32_t sub = (uint32_t)(shift % p.nsub), rowoff = (uint32_t)(shift / p.nsub);
+              const uint32_t a_lo0 = lo_of(a_buf + sub * sub_bytes + (uint32_t)sl * slab_bytes + rowoff * 128u);
               const int ks_n = min(4, p.ksteps - sl * 4);
+              const uint32_t first = (uint32_t)(pass | t | sl);
               for (int mt = 0; mt < p.mt; ++mt) {
-                const uint32_t d = tmem + (uint32_t)(acc * acc_cols + mt * p.n_pad);
-                const uint32_t a_row = a_buf + sub * sub_bytes + (uint32_t)sl * slab_bytes + ((uint32_t)(mt * 128) + rowoff) * 128u;
+                const uint32_t d = d0 + (uint32_t)(mt * p.n_pad);
+                const uint32_t a_lo = a_lo0 + (uint32_t)mt * mt_step;
+#pragma unroll 4
                 for (int ks = 0; ks < ks_n; ++ks)
-                  mma_f16_ss(d, make_desc_sw128(a_row + (uint32_t)ks * 32u), make_desc_sw128(b_base + (uint32_t)ks * 32u), idesc,
-                             (pass | t | sl | ks) != 0 ? 1u : 0u);
+                  mma_f16_ss(d, mk(a_lo + 2u * (uint32_t)ks), mk(b_lo + 2u * (uint32_t)ks), idesc, (first | (uint32_t)ks) != 0 ? 1u : 0u);
               }
-              umma_commit(&b_empty[s]);            // weight stage reusable once these MMAs retire
+              b_lo += unit_bytes >> 4;
+              if (++sl == p.slabs) { sl = 0; ++t; }
             }
+            umma_commit(&b_empty[s]);            // weight stage reusable once these MMAs retire
           }
           // A buffers: hi is last read in pass 1 (split) or pass 0 (plain); lo in pass 2
           if (p.passes == 1) umma_commit(&a_empty[job_hi & 1u]);
@@ -428,19 +463,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
         job += (uint32_t)jobs_per_tile;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // =========================== B producer (bulk copies) ===========================
     if (elect_one()) {
       uint32_t bit = 0;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int pass = 0; pass < p.passes; ++pass) {
           const int b_plane = pass == 1 ? 1 : 0;
-          const uint4* src0 = p.wpack + (size_t)b_plane * stages_per_pass * (size_t)(p.n_pad * 8);
-          for (int st = 0; st < stages_per_pass; ++st, ++bit) {
-            const uint32_t s = bit % kBStages;
-            mbar_wait(&b_empty[s], ((bit / kBStages) & 1u) ^ 1u);
+          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)b_plane * p.stages_per_pass * (size_t)bstage_bytes;
+          for (int st = 0; st < p.stages_per_pass; ++st, ++bit) {
+            const uint32_t s = bit % (uint32_t)p.bstages;
+            mbar_wait(&b_empty[s], ((bit / (uint32_t)p.bstages) & 1u) ^ 1u);
             mbar_expect_tx(&b_full[s], bstage_bytes);
-            bulk_g2s(sB + s * bstage_bytes, src0 + (size_t)st * (size_t)(p.n_pad * 8), bstage_bytes, &b_full[s]);
+            bulk_g2s(sB + s * bstage_bytes, src0 + (size_t)st * bstage_bytes, bstage_bytes, &b_full[s]);
           }
         }
       }
@@ -460,23 +495,38 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
         const uint32_t buf = job & 1u;
         mbar_wait(&a_empty[buf], ((job >> 1) & 1u) ^ 1u);
         uint8_t* dstA = sA + buf * abuf_bytes;
-        for (int i = ptid; i < groups * span; i += nprod) {
-          const int g = i / span, j = i - g * span;
-          const int pos = u0 + j - p.padL;
-          const bool inside = pos >= 0 && pos < a.Lin;
-          const int c0 = g << 3;
-          __half h[8];
+        const int total = groups * span;
+        for (int i0 = ptid; i0 < total; i0 += kATasks * nprod) {
+          // kATasks tasks (= 8 * kATasks independent global loads) in flight per thread
+          float v[kATasks][8];
+          int gg[kATasks], jj_[kATasks];
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float v = (inside && c0 + jj < a.Cin) ? xb[(int64_t)(c0 + jj) * a.Lin + pos] : 0.f;
-            const __half hi = __float2half_rn(v);
-            h[jj] = plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
+          for (int q = 0; q < kATasks; ++q) {
+            const int i = i0 + q * nprod;
+            const int g = i < total ? i / span : 0, j = i < total ? i - g * span : 0;
+            gg[q] = g; jj_[q] = j;
+            const int pos = u0 + j - p.padL;
+            const bool inside = i < total && pos >= 0 && pos < a.Lin;
+            const int c0 = g << 3;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[q][c] = (inside && c0 + c < a.Cin) ? __ldg(xb + (int64_t)(c0 + c) * a.Lin + pos) : 0.f;
           }
-          const int sub = j % p.nsub, row = j / p.nsub;
-          const int slab = g >> 3, chunk = g & 7;
-          uint8_t* dst = dstA + (uint32_t)sub * sub_bytes + (uint32_t)slab * slab_bytes + (uint32_t)row * 128u +
-                         (uint32_t)((chunk ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+#pragma unroll
+          for (int q = 0; q < kATasks; ++q) {
+            if (i0 + q * nprod >= total) break;
+            __half h[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const __half hi = __float2half_rn(v[q][c]);
+              h[c] = plane == 0 ? hi : __float2half_rn(v[q][c] - __half2float(hi));
+            }
+            const int j = jj_[q], g = gg[q];
+            const int sub = j % p.nsub, row = j / p.nsub;
+            const int slab = g >> 3, chunk = g & 7;
+            uint8_t* dst = dstA + (uint32_t)sub * sub_bytes + (uint32_t)slab * slab_bytes + (uint32_t)row * 128u +
+                           (uint32_t)((chunk ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -486,7 +536,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(p.tmem_cols) : "memory");
   }
@@ -533,8 +583,25 @@ static int launch_conv_tc_pipe(const ConvArgs& a, int precision, void* wpack, cu
   while (cols < 2 * p.mt * p.n_pad) cols *= 2;
   p.tmem_cols = cols;
   p.wpack = reinterpret_cast<const uint4*>(wpack);
-  const size_t smem = 1024 + 2ull * p.nsub * p.slabs * p.rows * 128 + (size_t)kBStages * p.n_pad * 128;
-  if (cols > 512 || smem + 512 > 227 * 1024) return 1;   // caller falls back to the simple kernel
+  const size_t a_bytes = 2ull * p.nsub * p.slabs * p.rows * 128, unit_bytes = (size_t)p.n_pad * 128;
+  const size_t budget = 224 * 1024 - 1024;
+  if (cols > 512 || a_bytes + 2 * unit_bytes > budget) return 1;   // caller falls back to the simple kernel
+  // group several (tap, slab) units into one ring stage so that the issuing thread pays one barrier round trip per
+  // ~24 KB of weights, while keeping at least 3 stages in flight
+  const int units = a.K * p.slabs;
+  int group = 1;
+  for (int g = 1; g <= units; ++g)
+    if (units % g == 0 && (size_t)g * unit_bytes <= 24 * 1024 && a_bytes + 3 * (size_t)g * unit_bytes <= budget) group = g;
+  p.group = group;
+  p.stages_per_pass = units / group;
+  const size_t stage_bytes = (size_t)group * unit_bytes;
+  size_t nst = (budget - a_bytes) / stage_bytes;
+  const size_t per_tile = (size_t)p.passes * p.stages_per_pass;    // no point in a ring deeper than two tiles' worth
+  if (nst > 2 * per_tile) nst = 2 * per_tile;
+  if (nst < 2) nst = 2;
+  if (nst > (size_t)kMaxBStages) nst = kMaxBStages;
+  p.bstages = (int)nst;
+  const size_t smem = 1024 + a_bytes + nst * stage_bytes;
   NSC_CUDA_OK(cudaFuncSetAttribute(tc_conv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   char name[32];
   snprintf(name, sizeof(name), "tc%d_k%dd%ds%d_c%dto%d", precision, a.K, a.dil, a.stride, a.Cin, a.Cout);
