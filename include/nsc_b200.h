@@ -207,6 +207,35 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
                    float* const* qloss_ptrs_host, float* poly, float* res_x, float* decoded, float* synthesized,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step of the CQ cascade (loss assembly + optimiser of nscm.py:1033-1059 / cmrl.py:464-490; 'bottleneck'
+ * codecs).  Per-quantiser arrays have n_codecs + 1 entries: index 0 = LSF codebook, 1..n = codecs.
+ *   nsc_train_forward : soft path (the_share = True) with every activation kept in the workspace.  res_x is FED
+ *                       like in the reference's training loop (nscm.py:586-595).  Returns decoded (B,512),
+ *                       time_loss / freq_loss (B), quan_loss per quantiser (B each) and the LOCAL soft histograms
+ *                       (caller zeroes them; under data parallelism they are all-reduced before the backward call).
+ *   nsc_train_backward: gradients of  sum_b [c0*time_b + c1*freq_b + c2*sum_q quan_w[q]*quan_q,b] +
+ *                       global_B * tau * sum_q ent_w[q]*H_q(global hist)  w.r.t. every codec's flat parameter image
+ *                       (grad_ptrs, same layout as the parameters) and the LSF codebook {alpha, bins} (lsf_grad).
+ *                       Must be called with the same workspace right after nsc_train_forward.
+ *                       loss_coeff_host = {c0, c1, c2, tau}; trainable_host[q] = 0 skips that quantiser/codec.
+ *   nsc_adam_step     : TF1 AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps), t >= 1.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t nsc_train_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B);
+int nsc_train_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
+                      const float* lsf_params, int32_t n_lsf_bins, const float* res_x, const float* lsf, int64_t B,
+                      float res_scalar, float is_quan_on, const float* melw, float* decoded, float* time_loss,
+                      float* freq_loss, float* const* qloss_ptrs_host, float* const* hist_ptrs_host, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
+                       const float* lsf_params, int32_t n_lsf_bins, const float* res_x, const float* lsf, int64_t B,
+                       float res_scalar, float is_quan_on, const float* melw, const float* decoded,
+                       const float* loss_coeff_host, const float* quan_w_host, const float* ent_w_host, int64_t global_B,
+                       const float* const* hist_global_ptrs_host, const int32_t* trainable_host,
+                       float* const* grad_ptrs_host, float* lsf_grad, void* workspace, int64_t workspace_bytes, void* stream);
+int nsc_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, float lr, int64_t t, float beta1,
+                  float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

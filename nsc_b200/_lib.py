@@ -70,6 +70,11 @@ SIGNATURES = {
     "nsc_cq_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),
     "nsc_cq_forward": (_i32, [_cfgp, _i32, _ppv, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _i32, _vp, _vp, _vp, _ppv, _ppv, _ppv,
                               _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "nsc_train_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),
+    "nsc_train_forward": (_i32, [_cfgp, _i32, _ppv, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _ppv, _ppv, _vp, _i64, _vp]),
+    "nsc_train_backward": (_i32, [_cfgp, _i32, _ppv, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _vp, _vp, C.POINTER(_f32), C.POINTER(_f32),
+                                  C.POINTER(_f32), _i64, _ppv, C.POINTER(_i32), _ppv, _vp, _vp, _i64, _vp]),
+    "nsc_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _i64, _f32, _f32, _f32, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

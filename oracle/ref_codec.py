@@ -169,3 +169,23 @@ def tf1_adam_step(theta, grad, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
     theta = theta - lr_t * m / (np.sqrt(v) + eps)
     return theta, m, v
+
+
+def cq_training_objective(codecs, lsf_alpha, lsf_bins, res_x, lpc_x, is_quan_on, coeff, quan_w, ent_w, tau, res_scalar=1.0,
+                          global_batch=None):
+    """The scalar whose gradient `minimize` applies: sum over the batch of the per-frame loss vector,
+    with the scalar entropy term broadcast (counted once per frame).  res_x is FED (nscm.py:586-595); the LSF codebook only
+    enters through quan_loss / entropy of its own soft assignment.  All arguments may be torch tensors that require grad.
+    quan_w / ent_w: index 0 = LSF codebook, 1.. = codecs."""
+    B = res_x.shape[0]
+    soft_lpc, _ = ref_nn.scalar_softmax_quantization(lpc_x, lsf_alpha, lsf_bins, is_quan_on, True, LPC_ORDER, len(lsf_bins))
+    decoded, outs, per = cascade_forward(codecs, res_x, True, is_quan_on, res_scalar, lpc_variant=True)
+    time_loss = ref_loss.mse_loss(decoded, res_x[:, :, 0])
+    freq_loss = ref_loss.mfcc_loss(decoded, res_x[:, :, 0])
+    softs = [soft_lpc] + [p['soft'] for p in per]
+    quan = sum(w * ref_loss.quan_loss(s) for w, s in zip(quan_w, softs))
+    ent = sum(w * ref_loss.entropy_coding_loss(s) for w, s in zip(ent_w, softs))
+    vec = coeff[0] * time_loss + coeff[1] * freq_loss + coeff[2] * quan + tau * ent
+    gb = B if global_batch is None else global_batch
+    total = (coeff[0] * time_loss + coeff[1] * freq_loss + coeff[2] * quan).sum() + gb * tau * ent
+    return total, dict(vec=vec, time=time_loss, freq=freq_loss, quan=quan, ent=ent, decoded=decoded)
