@@ -128,6 +128,31 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def kernel_breakdown(lib, fn, cap=8192):
+    """Runs fn() once with per-launch CUDA-event recording on (nsc_profile_begin/end) and aggregates by kernel name:
+    name -> [ms, flops, bytes, launches]."""
+    lib.nsc_profile_begin(cap)
+    fn()
+    n = C.c_int32(0)
+    names = C.create_string_buffer(cap * 32)
+    ms = (C.c_float * cap)(); fl = (C.c_double * cap)(); by = (C.c_double * cap)()
+    lib.nsc_profile_end(C.byref(n), names, ms, fl, by, cap)
+    agg = {}
+    for i in range(n.value):
+        nm = names.raw[i * 32:(i + 1) * 32].split(b'\0')[0].decode()
+        a = agg.setdefault(nm, [0.0, 0.0, 0.0, 0])
+        a[0] += ms[i]; a[1] += fl[i]; a[2] += by[i]; a[3] += 1
+    return agg
+
+
+def breakdown_table(agg):
+    tot = sum(a[0] for a in agg.values()) or 1.0
+    return {k: {"ms": round(v[0], 3), "share": round(v[0] / tot, 4), "launches": v[3],
+                "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 2) if v[0] > 0 else None,
+                "gbs": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None}
+            for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -206,23 +231,9 @@ def run_ours(args):
     roof = None
     breakdown = None
     if rank == 0:
-        lib.nsc_profile_begin(4096)
-        step_device()
-        cap = 4096
-        n = C.c_int32(0)
-        names = C.create_string_buffer(cap * 32)
-        ms = (C.c_float * cap)(); fl = (C.c_double * cap)(); by = (C.c_double * cap)()
-        lib.nsc_profile_end(C.byref(n), names, ms, fl, by, cap)
-        agg = {}
-        for i in range(n.value):
-            nm = names.raw[i * 32:(i + 1) * 32].split(b'\0')[0].decode()
-            a = agg.setdefault(nm, [0.0, 0.0, 0.0, 0])
-            a[0] += ms[i]; a[1] += fl[i]; a[2] += by[i]; a[3] += 1
+        agg = kernel_breakdown(lib, step_device)
         tot = sum(a[0] for a in agg.values())
-        breakdown = {k: {"ms": round(v[0], 3), "share": round(v[0] / tot, 4), "launches": v[3],
-                         "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 2) if v[0] > 0 else None,
-                         "gbs": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None}
-                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        breakdown = breakdown_table(agg)
         conv = [(k, v) for k, v in agg.items() if k.startswith('conv_') or (k.startswith('tc') and k != 'tc_pack_weights')]
         top_name, top = max(conv, key=lambda kv: kv[1][0])
         hbm, bf16, bf16_sus, how = peaks()
@@ -280,6 +291,60 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Secondary workload (BASELINE.json configs[3]): full CQ training step -- forward keeping activations, backward of
+    every kernel, histogram + gradient all-reduce (NCCL), TF1 Adam -- `_finetuning_lpc`-shaped loss, 128 frames per GPU."""
+    import torch
+    import torch.distributed as dist
+    from nsc_b200 import _lib, codec, lpc_utilities as lu
+    from nsc_b200.sharding import max_over_ranks
+    from nsc_b200.training import CQTrainer
+    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    B = args.train_batch
+    cfg = codec.CodecConfig(precision=args.precision)
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
+    tr = CQTrainer.finetuning_lpc(cm, (60.0, 10.0, 10.0, 0.0), lr=2e-6)
+    x_np, win_np = synth_audio(B, seed=4321 + rank)
+    x = torch.from_numpy(x_np).to(dev) * 0.3
+    lsf = lu.lpc_analysis_windows(torch.from_numpy(win_np).to(dev), 16, dtype=torch.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        tr.step(x, lsf)
+    barrier()
+    l0 = lib.nsc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = tr.step(x, lsf)
+    e1.record()
+    barrier()
+    t = max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    if rank == 0:
+        fps = B * world * args.steps / t
+        print(json.dumps({"metric": "CQ training step throughput (frames/s; seconds of audio per second = x0.030)", "value": fps,
+                          "unit": "frames/s", "x_real_time": fps * SEC_PER_FRAME, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 backward; forward convs " + args.precision, "data": "synthetic",
+                          "config": {"workload": "train: 2-codec CQ cascade, finetuning_lpc loss (60/10/10), soft path, TF1 Adam, "
+                                                 "hist + flat-gradient all-reduce", "frames_per_gpu": B, "parallelism": f"dp{world}"},
+                          "gpu_launches": int(lib.nsc_launch_count() - l0), "loss_first_frame": float(out['loss_vector'][0]),
+                          "kernel_breakdown": breakdown_table(kernel_breakdown(lib, lambda: tr.step(x, lsf)))}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -290,6 +355,8 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=1024, help='bounded CPU-baseline sample (frames)')
     ap.add_argument('--ref-frames', type=int, default=512, help='frames per step of the reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='cq2', choices=['cq2', 'train'], help="cq2 = headline encode+decode; train = training step")
+    ap.add_argument('--train-batch', type=int, default=128, help='frames per GPU per training step')
     ap.add_argument('--precision', default='tc_f16x3', choices=['fp32', 'tc_f16x3', 'tc_f16'],
                     help="conv arithmetic: fp32 FFMA, tcgen05 fp16 hi/lo split (fp32-class, default), tcgen05 fp16 (reduced)")
     args = ap.parse_args()
@@ -297,6 +364,8 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train':
+        run_train(args)
     else:
         run_ours(args)
 

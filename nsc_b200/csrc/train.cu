@@ -16,6 +16,8 @@
 // weights; the weight gradient is an im2col-on-the-fly SGEMM reduced over (frame, position) with one atomic flush
 // per CTA; activation / residual / sub-pixel epilogues are undone by one elementwise kernel that reads the sign of
 // the stored OUTPUT (leaky-ReLU and tanh derivatives are functions of the output).
+#include <limits.h>
+
 #include "walker.cuh"
 
 namespace nsc {
@@ -85,78 +87,95 @@ __global__ void dgrad_strided_kernel(const float* __restrict__ g, const float* _
 // dW[(t,ci)][co] += sum_{b,p} x[b][ci][p*s + t*d - padL] * g[b][co][p] : a (K*Cin) x Cout x (B*Lout) GEMM whose A operand is
 // gathered on the fly.  CTA tile 64 x 64, 4 x 4 per thread, 32-position chunks staged in shared memory, batch split over
 // gridDim.z, one atomicAdd per output element per CTA.  gridDim.y == 0-th column CTAs also reduce the bias gradient.
-constexpr int kWgM = 64, kWgN = 64, kWgR = 32;
+constexpr int kWgM = 128, kWgR = 16;   // CTA tile: 128 rows (tap, cin) x (16 * NT) output channels, 16 positions per chunk
 
+template <int NT>   // output channels per thread (4 -> 64-wide tile, 2 -> 32-wide tile for the narrow layers)
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dw, float* __restrict__ db,
              int64_t B, int Lin, int Lout, int Cin, int Cout, int K, int dil, int stride, int padL, int frames_per_split) {
-  __shared__ float xs[kWgR][kWgM + 1];
-  __shared__ float gs[kWgR][kWgN + 1];
+  constexpr int TN = 16 * NT;
+  __shared__ __align__(16) float xs[kWgR][kWgM + 4];
+  __shared__ __align__(16) float gs[kWgR][TN + 4];
+  __shared__ int row_base[kWgM];    // ci * Lin + t * dil - padL of each tile row (fixed for the whole CTA), or INT_MIN
+  __shared__ int row_shift[kWgM];   // t * dil - padL (for the bounds test)
   const int M = K * Cin;
-  const int m0 = blockIdx.x * kWgM, n0 = blockIdx.y * kWgN;
+  const int m0 = blockIdx.x * kWgM, n0 = blockIdx.y * TN;
   const int64_t b_lo = (int64_t)blockIdx.z * frames_per_split;
   int64_t b_hi = b_lo + frames_per_split;
   if (b_hi > B) b_hi = B;
-  const int tid = threadIdx.x, tm = tid / 16, tn = tid % 16;   // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4];
+  const int tid = threadIdx.x, tm = tid >> 4, tn = tid & 15;   // 16 x 16 threads, 8 x NT outputs each
+  for (int mm = tid; mm < kWgM; mm += 256) {
+    const int m = m0 + mm;
+    if (m < M) {
+      const int t = m / Cin, ci = m - t * Cin;
+      row_shift[mm] = t * dil - padL;
+      row_base[mm] = ci * Lin;
+    } else {
+      row_shift[mm] = INT_MIN / 2;
+      row_base[mm] = 0;
+    }
+  }
+  __syncthreads();
+  float acc[8][NT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bacc = 0.f;   // bias partial: thread tid < 64 of the blockIdx.x == 0 CTAs owns column n0 + tid
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+  float bacc = 0.f;   // bias partial: thread tid < TN of the blockIdx.x == 0 CTAs owns column n0 + tid
 
   for (int64_t b = b_lo; b < b_hi; ++b) {
     const float* xb = x + b * (int64_t)Cin * Lin;
     const float* gb = g + b * (int64_t)Cout * Lout;
     for (int p0 = 0; p0 < Lout; p0 += kWgR) {
-      // stage: lanes walk positions (contiguous in NCL)
+      // stage: 16 consecutive positions per row; lanes walk positions (contiguous in NCL)
       for (int i = tid; i < kWgM * kWgR; i += 256) {
-        const int r = i % kWgR, mm = i / kWgR;
-        const int m = m0 + mm, p = p0 + r;
-        float v = 0.f;
-        if (m < M && p < Lout) {
-          const int t = m / Cin, ci = m - t * Cin;
-          const int u = p * stride + t * dil - padL;
-          if (u >= 0 && u < Lin) v = xb[(int64_t)ci * Lin + u];
-        }
-        xs[r][mm] = v;
+        const int r = i & (kWgR - 1), mm = i >> 4;
+        const int p = p0 + r;
+        const int u = p * stride + row_shift[mm];
+        xs[r][mm] = (p < Lout && u >= 0 && u < Lin) ? xb[row_base[mm] + u] : 0.f;
       }
-      for (int i = tid; i < kWgN * kWgR; i += 256) {
-        const int r = i % kWgR, nn = i / kWgR;
+      for (int i = tid; i < TN * kWgR; i += 256) {
+        const int r = i & (kWgR - 1), nn = i >> 4;
         const int n = n0 + nn, p = p0 + r;
         gs[r][nn] = (n < Cout && p < Lout) ? gb[(int64_t)n * Lout + p] : 0.f;
       }
       __syncthreads();
-#pragma unroll 8
+#pragma unroll
       for (int r = 0; r < kWgR; ++r) {
-        float a[4], c[4];
+        const float4 a0 = *reinterpret_cast<const float4*>(&xs[r][tm * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&xs[r][tm * 8 + 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float c[NT];
+        if (NT == 4) {
+          const float4 cv = *reinterpret_cast<const float4*>(&gs[r][tn * 4]);
+          c[0] = cv.x; c[1] = cv.y; c[NT > 2 ? 2 : 0] = cv.z; c[NT > 3 ? 3 : 0] = cv.w;
+        } else {
+          const float2 cv = *reinterpret_cast<const float2*>(&gs[r][tn * 2]);
+          c[0] = cv.x; c[1] = cv.y;
+        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = xs[r][tm * 4 + i];
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = gs[r][tn * 4 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
       }
-      if (db != nullptr && blockIdx.x == 0 && tid < kWgN) {
-#pragma unroll 8
+      if (db != nullptr && blockIdx.x == 0 && tid < TN) {
+#pragma unroll
         for (int r = 0; r < kWgR; ++r) bacc += gs[r][tid];
       }
       __syncthreads();
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + tm * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tm * 8 + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tn * 4 + j;
+    for (int j = 0; j < NT; ++j) {
+      const int n = n0 + tn * NT + j;
       if (n < Cout) atomicAdd(dw + (int64_t)m * Cout + n, acc[i][j]);
     }
   }
-  if (db != nullptr && blockIdx.x == 0 && tid < kWgN && n0 + tid < Cout) atomicAdd(db + n0 + tid, bacc);
+  if (db != nullptr && blockIdx.x == 0 && tid < TN && n0 + tid < Cout) atomicAdd(db + n0 + tid, bacc);
 }
 
 // ------------------------------------------------------------------------------------------------ quantiser backward
@@ -509,14 +528,16 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
   }
   {
     const int M = r.K * r.Cin;
-    const int gx = ceil_div(M, kWgM), gy = ceil_div(r.Cout, kWgN);
+    const int nt = r.Cout <= 32 ? 2 : 4;
+    const int gx = ceil_div(M, kWgM), gy = ceil_div(r.Cout, 16 * nt);
     int splits = ceil_div(2 * sm_count(), gx * gy);
     if (splits > B) splits = (int)B;
     if (splits < 1) splits = 1;
     const int fps = (int)ceil_div64(B, splits);
     splits = (int)ceil_div64(B, fps);
     ProfScope prof(st, "wgrad", 2.0 * B * Lout * (double)M * r.Cout, 4.0 * B * ((double)r.Lin * r.Cin + (double)Lout * r.Cout));
-    wgrad_kernel<<<dim3(gx, gy, splits), 256, 0, st>>>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, fps);
+    if (nt == 4) wgrad_kernel<4><<<dim3(gx, gy, splits), 256, 0, st>>>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, fps);
+    else wgrad_kernel<2><<<dim3(gx, gy, splits), 256, 0, st>>>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, fps);
     NSC_LAUNCH_OK();
   }
   if (!need_dx) return NSC_OK;
