@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 // ================================================================================================
 constexpr int kEpiWarps = 8, kAProdWarps = 8;
 constexpr int kPipeThreads = (kEpiWarps + 2 + kAProdWarps) * 32;   // 576
-constexpr int kATasks = 4;        // A-producer tasks (8 loads each) in flight per thread
+constexpr int kATasks = 2;        // A-producer tasks (8 x 128-bit loads each) in flight per thread
 constexpr int kMaxBStages = 32;   // weight ring depth is chosen per layer from the shared memory left over (TcPipe::bstages)
 
 struct TcPipe {
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
   for (uint32_t i = tid; i < 2u * abuf_bytes / 16; i += kPipeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], kAProdWarps);     // one arrival per producer warp
+      mbar_init(&a_full[i], kAProdWarps / 2); // one arrival per warp of the producer group that owns buffer i
       mbar_init(&a_empty[i], 1);              // tcgen05.commit
       mbar_init(&acc_full[i], 1);             // tcgen05.commit
       mbar_init(&acc_empty[i], kEpiWarps);    // one arrival per epilogue warp
@@ -482,7 +482,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
     }
   } else {
     // =========================== A producers ===========================
-    const int ptid = tid - (kEpiWarps + 2) * 32, nprod = kAProdWarps * 32;
+    // Two producer groups of kAProdWarps/2 warps: group g fills buffer g (jobs with job & 1 == g), so two staging
+    // jobs -- the hi and lo plane of a tile in split mode, consecutive tiles otherwise -- are in flight at once and a
+    // job's global-load latency no longer bounds the tile rate.
+    const int pgroup = (warp - (kEpiWarps + 2)) / (kAProdWarps / 2);
+    const int nprod = (kAProdWarps / 2) * 32;
+    const int ptid = tid - (kEpiWarps + 2) * 32 - pgroup * nprod;
     const int groups = (a.Cin + 7) >> 3;
     const int span = p.rows * p.nsub;               // u-coordinates covered by one buffer
     uint32_t job = 0;
@@ -493,39 +498,53 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
       const int u0 = q0 * p.nsub;                    // first u = pos + padL of this tile
       for (int plane = 0; plane < jobs_per_tile; ++plane, ++job) {
         const uint32_t buf = job & 1u;
+        if ((int)buf != pgroup) continue;             // the other group's job (the `continue` still advances job)
         mbar_wait(&a_empty[buf], ((job >> 1) & 1u) ^ 1u);
         uint8_t* dstA = sA + buf * abuf_bytes;
-        const int total = groups * span;
+        // A task = 8 channels x 4 consecutive positions: eight 128-bit loads (lanes walk position quads, so a warp
+        // request is 512 contiguous bytes), four 16-byte swizzled row stores.  kATasks tasks are in flight per thread
+        // (1 KB of loads): the staging rate is set by bytes in flight, not by instruction count.
+        const int pos_lo = u0 - p.padL;                       // position of buffer coordinate j = 0
+        const int pos_al = pos_lo & ~3;                       // floor to a multiple of 4 (two's complement: works for < 0)
+        const int quads = (pos_lo - pos_al + span + 3) >> 2;  // position quads covering [pos_lo, pos_lo + span)
+        const int total = groups * quads;
         for (int i0 = ptid; i0 < total; i0 += kATasks * nprod) {
-          // kATasks tasks (= 8 * kATasks independent global loads) in flight per thread
-          float v[kATasks][8];
-          int gg[kATasks], jj_[kATasks];
+          float4 v[kATasks][8];
+          int gg[kATasks], pp[kATasks];
 #pragma unroll
           for (int q = 0; q < kATasks; ++q) {
             const int i = i0 + q * nprod;
-            const int g = i < total ? i / span : 0, j = i < total ? i - g * span : 0;
-            gg[q] = g; jj_[q] = j;
-            const int pos = u0 + j - p.padL;
-            const bool inside = i < total && pos >= 0 && pos < a.Lin;
+            const int g = i < total ? i / quads : 0, k = i < total ? i - g * quads : 0;
+            const int pos = pos_al + 4 * k;
+            gg[q] = g; pp[q] = pos;
+            const bool inside = i < total && pos >= 0 && pos < a.Lin;    // Lin % 4 == 0: a quad is all in or all out
             const int c0 = g << 3;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[q][c] = (inside && c0 + c < a.Cin) ? __ldg(xb + (int64_t)(c0 + c) * a.Lin + pos) : 0.f;
+            for (int c = 0; c < 8; ++c)
+              v[q][c] = (inside && c0 + c < a.Cin) ? __ldg(reinterpret_cast<const float4*>(xb + (int64_t)(c0 + c) * a.Lin + pos))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int q = 0; q < kATasks; ++q) {
             if (i0 + q * nprod >= total) break;
-            __half h[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const __half hi = __float2half_rn(v[q][c]);
-              h[c] = plane == 0 ? hi : __float2half_rn(v[q][c] - __half2float(hi));
-            }
-            const int j = jj_[q], g = gg[q];
-            const int sub = j % p.nsub, row = j / p.nsub;
+            const int g = gg[q];
             const int slab = g >> 3, chunk = g & 7;
-            uint8_t* dst = dstA + (uint32_t)sub * sub_bytes + (uint32_t)slab * slab_bytes + (uint32_t)row * 128u +
-                           (uint32_t)((chunk ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = pp[q] + e - pos_lo;
+              if (j < 0 || j >= span) continue;
+              __half h[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float f = e == 0 ? v[q][c].x : e == 1 ? v[q][c].y : e == 2 ? v[q][c].z : v[q][c].w;
+                const __half hi = __float2half_rn(f);
+                h[c] = plane == 0 ? hi : __float2half_rn(f - __half2float(hi));
+              }
+              const int sub = j % p.nsub, row = j / p.nsub;
+              uint8_t* dst = dstA + (uint32_t)sub * sub_bytes + (uint32_t)slab * slab_bytes + (uint32_t)row * 128u +
+                             (uint32_t)((chunk ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -585,7 +604,8 @@ static int launch_conv_tc_pipe(const ConvArgs& a, int precision, void* wpack, cu
   p.wpack = reinterpret_cast<const uint4*>(wpack);
   const size_t a_bytes = 2ull * p.nsub * p.slabs * p.rows * 128, unit_bytes = (size_t)p.n_pad * 128;
   const size_t budget = 224 * 1024 - 1024;
-  if (cols > 512 || a_bytes + 2 * unit_bytes > budget) return 1;   // caller falls back to the simple kernel
+  if (cols > 512 || a_bytes + 2 * unit_bytes > budget || (a.Lin & 3) != 0 ||
+      (reinterpret_cast<uintptr_t>(a.x) & 15) != 0) return 1;   // caller falls back to the simple kernel
   // group several (tap, slab) units into one ring stage so that the issuing thread pays one barrier round trip per
   // ~24 KB of weights, while keeping at least 3 stages in flight
   const int units = a.K * p.slabs;
