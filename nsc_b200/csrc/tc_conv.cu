@@ -258,17 +258,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 //
 //   warps 0-7   epilogue      wait acc_full[k]  -> TMEM -> bias/act/residual -> NCL fp32 stores -> arrive acc_empty[k]
 //                             (two warps per TMEM lane quarter; 32 residual loads in flight per thread)
-//   warp  8     MMA issuer    one elected thread: wait a_full / b_full, issue tcgen05.mma, tcgen05.commit -> b_empty,
-//                             a_empty, acc_full
-//   warp  9     B producer    one elected thread: cp.async.bulk of pre-packed weight stages (tap, slab) into a ring
-//   warps 10-17 A producers   NCL fp32 -> fp16 plane -> K-major SW128 rows of A buffer (job & 1); arrive a_full
+//   warps 8-9   MMA issuers   one elected thread each, one per M-tile of the unit: wait a_full / b_full, issue tcgen05.mma,
+//                             tcgen05.commit -> b_empty, a_empty, acc_full (barrier counts = number of issuers)
+//   warp  10    B producer    one elected thread: cp.async.bulk of pre-packed weight stages (tap, slab) into a ring
+//   warps 11-18 A producers   NCL fp32 -> fp16 plane -> K-major SW128 rows of A buffer (job & 1); arrive a_full
 //
 // Two A buffers (hi / lo plane of a tile in split mode, consecutive tiles otherwise), a ring of weight stages and two
 // TMEM accumulator sets decouple the four roles: staging of tile i+1 and the epilogue of tile i-1 overlap the MMAs
 // of tile i.  All hand-offs are mbarriers; tensor-core completions arrive through tcgen05.commit.
 // ================================================================================================
 constexpr int kEpiWarps = 8, kAProdWarps = 8;
-constexpr int kPipeThreads = (kEpiWarps + 2 + kAProdWarps) * 32;   // 576
+constexpr int kMmaWarps = 2;       // one issuing thread per M-tile of the work unit (issue overhead, not the tensor pipe, bounds narrow layers)
+constexpr int kPipeThreads = (kEpiWarps + kMmaWarps + 1 + kAProdWarps) * 32;   // 608
 constexpr int kATasks = 2;        // A-producer tasks (8 x 128-bit loads each) in flight per thread
 constexpr int kMaxBStages = 32;   // weight ring depth is chosen per layer from the shared memory left over (TcPipe::bstages)
 
@@ -323,16 +324,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
   uint8_t* sB = smem + 2u * abuf_bytes;         // p.bstages weight stages
 
   for (uint32_t i = tid; i < 2u * abuf_bytes / 16; i += kPipeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  const uint32_t n_issuers = (uint32_t)(p.mt < kMmaWarps ? p.mt : kMmaWarps);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], kAProdWarps / 2); // one arrival per warp of the producer group that owns buffer i
-      mbar_init(&a_empty[i], 1);              // tcgen05.commit
-      mbar_init(&acc_full[i], 1);             // tcgen05.commit
+      mbar_init(&a_empty[i], n_issuers);      // tcgen05.commit of every issuing thread
+      mbar_init(&acc_full[i], n_issuers);     // tcgen05.commit of every issuing thread
       mbar_init(&acc_empty[i], kEpiWarps);    // one arrival per epilogue warp
     }
     for (int i = 0; i < p.bstages; ++i) {
       mbar_init(&b_full[i], 1);               // expect_tx arrival + bulk-copy bytes
-      mbar_init(&b_empty[i], 1);              // tcgen05.commit
+      mbar_init(&b_empty[i], n_issuers);      // tcgen05.commit of every issuing thread
     }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -407,13 +409,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-  } else if (warp == kEpiWarps) {
+  } else if (warp < kEpiWarps + kMmaWarps) {
     // =========================== MMA issuer ===========================
     // One thread feeds the tensor core.  Descriptors are NOT rebuilt per instruction: the upper 32 bits (stride,
     // version, swizzle mode) are constant and the lower word is (smem address >> 4) | LBO, so advancing along K or
     // to the next position tile is an integer add (the first build spent ~140 cycles of address arithmetic per MMA,
     // three times the 44-cycle cost of the instruction itself).
-    if (elect_one()) {
+    const int issuer = warp - kEpiWarps;                // issuer i owns M-tiles i, i + n_issuers, ...
+    if (issuer < (int)n_issuers && elect_one()) {
       const uint32_t idesc = make_idesc_f16(p.n_pad);
       const uint32_t desc_hi = (uint32_t)(make_desc_sw128(0) >> 32);
       auto mk = [desc_hi](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
               const uint32_t a_lo0 = lo_of(a_buf + sub * sub_bytes + (uint32_t)sl * slab_bytes + rowoff * 128u);
               const int ks_n = min(4, p.ksteps - sl * 4);
               const uint32_t first = (uint32_t)(pass | t | sl);
-              for (int mt = 0; mt < p.mt; ++mt) {
+              for (int mt = issuer; mt < p.mt; mt += (int)n_issuers) {
                 const uint32_t d = d0 + (uint32_t)(mt * p.n_pad);
                 const uint32_t a_lo = a_lo0 + (uint32_t)mt * mt_step;
 #pragma unroll 4
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
         job += (uint32_t)jobs_per_tile;
       }
     }
-  } else if (warp == kEpiWarps + 1) {
+  } else if (warp == kEpiWarps + kMmaWarps) {
     // =========================== B producer (bulk copies) ===========================
     if (elect_one()) {
       uint32_t bit = 0;
@@ -485,9 +488,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
     // Two producer groups of kAProdWarps/2 warps: group g fills buffer g (jobs with job & 1 == g), so two staging
     // jobs -- the hi and lo plane of a tile in split mode, consecutive tiles otherwise -- are in flight at once and a
     // job's global-load latency no longer bounds the tile rate.
-    const int pgroup = (warp - (kEpiWarps + 2)) / (kAProdWarps / 2);
+    const int pgroup = (warp - (kEpiWarps + kMmaWarps + 1)) / (kAProdWarps / 2);
     const int nprod = (kAProdWarps / 2) * 32;
-    const int ptid = tid - (kEpiWarps + 2) * 32 - pgroup * nprod;
+    const int ptid = tid - (kEpiWarps + kMmaWarps + 1) * 32 - pgroup * nprod;
     const int groups = (a.Cin + 7) >> 3;
     const int span = p.rows * p.nsub;               // u-coordinates covered by one buffer
     uint32_t job = 0;
@@ -533,12 +536,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_conv_pipe_kernel(const __g
             for (int e = 0; e < 4; ++e) {
               const int j = pp[q] + e - pos_lo;
               if (j < 0 || j >= span) continue;
-              __half h[8];
+              __half2 h[4];     // packed conversions: one F2FP per channel pair
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float f = e == 0 ? v[q][c].x : e == 1 ? v[q][c].y : e == 2 ? v[q][c].z : v[q][c].w;
-                const __half hi = __float2half_rn(f);
-                h[c] = plane == 0 ? hi : __float2half_rn(f - __half2float(hi));
+              for (int c = 0; c < 8; c += 2) {
+                const float fa = e == 0 ? v[q][c].x : e == 1 ? v[q][c].y : e == 2 ? v[q][c].z : v[q][c].w;
+                const float fb = e == 0 ? v[q][c + 1].x : e == 1 ? v[q][c + 1].y : e == 2 ? v[q][c + 1].z : v[q][c + 1].w;
+                const __half2 hi = __floats2half2_rn(fa, fb);
+                if (plane == 0) {
+                  h[c >> 1] = hi;
+                } else {
+                  const float2 back = __half22float2(hi);
+                  h[c >> 1] = __floats2half2_rn(fa - back.x, fb - back.y);
+                }
               }
               const int sub = j % p.nsub, row = j / p.nsub;
               uint8_t* dst = dstA + (uint32_t)sub * sub_bytes + (uint32_t)slab * slab_bytes + (uint32_t)row * 128u +
