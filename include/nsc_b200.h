@@ -59,6 +59,20 @@ enum { NSC_ACT_NONE = 0, NSC_ACT_TANH = 1, NSC_ACT_LRELU = 2 };
 int nsc_conv1d(const float* x, const float* w, const float* b, float* y, int64_t B, int32_t Lin, int32_t Cin,
                int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation, void* stream);
 
+/* conv1d on the tcgen05 tensor cores ("plane engine", the codec's conv path) with the fused epilogue of the codec's
+ * layers, channels-last fp32 tensors at the edge:
+ *   y = post_act( act(conv1d(x) + b) (+ res) ), optionally sub-pixel shuffled: y[b, shuffle*l + r, c] = t[b, l, shuffle*c + r]
+ *   (nscm.py:158-167).  res_mode 0 = none, 1 = res (B, Lout, Cout), 2 = res (B, Lout) broadcast over channels
+ *   (nn_core_operator.py:77).  precision 1 = fp16 hi/lo split, 3 MMAs, fp32-class; 2 = fp16 inputs (reduced).
+ *   Covers the codec's layer shapes (Lout a multiple of 128, stride 1 or 2, k <= 9 taps for multi-channel inputs, k55
+ *   1-channel stems / 1-channel heads); anything else returns NSC_E_INVALID -- there is no fallback. */
+int64_t nsc_conv1d_tc_workspace_bytes(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation,
+                                      int32_t stride, int32_t res_mode, int32_t shuffle, int32_t precision);
+int nsc_conv1d_tc(const float* x, const float* w, const float* b, const float* res, float* y, int64_t B, int32_t Lin,
+                  int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation,
+                  int32_t res_mode, int32_t post_activation, int32_t shuffle, int32_t precision, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
 /* conv1d_depth (nn_core_operator.py:17-21): Keras SeparableConv1D, depth multiplier 1.
  *   dw (k, Cin, 1), pw (1, Cin, Cout), b (Cout); tmp is a (B, Lout, Cin) scratch buffer. */
 int nsc_conv1d_depth(const float* x, const float* dw, const float* pw, const float* b, float* tmp, float* y,

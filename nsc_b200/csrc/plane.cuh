@@ -1,0 +1,91 @@
+// Plane engine interface (plane_conv.cu): the conv layers of the codec on tcgen05 with activations kept in HBM as
+// fp16 "plane images" -- the exact shared-memory image (K-major, SWIZZLE_128B rows of 64 channels) the tensor core
+// reads, so a layer's input tile is staged by ONE bulk copy per 64-channel slab and no thread ever converts or
+// transposes an activation on the way in.
+//
+//   image of one frame = slabs back to back; one slab = (rows + 16) x 128 bytes: 8 zero rows, `rows` positions,
+//   8 zero rows (SAME padding and tap halos come from the zero rows); 16-byte chunk c of row r sits at chunk
+//   position c ^ (r & 7) (r counted from the start of the slab).
+//   planes = 2: value = hi + lo, both fp16 (fp32-class products with 3 MMAs: hi*hi + hi*lo + lo*hi);  planes = 1: hi only.
+//   C <= 32 channels ("packed"): one slab, hi in bytes 0-63 and lo in bytes 64-127 of the same row.
+//   C  > 32: plane-major, ceil(C/64) slabs per plane.
+//   deint: two sub-images by position parity (position p -> sub-image p & 1, row p >> 1) -- the input layout of a
+//   stride-2 conv, for which every tap is again a pure row shift.
+#pragma once
+#include "conv.cuh"
+
+namespace nsc {
+
+struct PlaneTensor {
+  uint8_t* base = nullptr;   // image of frame 0
+  int64_t frame_bytes = 0;
+  int rows = 0;              // positions per (sub-)image
+  int spp = 1;               // slabs per plane
+  int planes = 1;
+  int packed = 0;
+  int deint = 0;
+};
+
+__host__ __device__ inline int pt_slab_bytes(const PlaneTensor& t) { return (t.rows + 16) * 128; }
+__host__ __device__ inline int pt_slab_index(const PlaneTensor& t, int sub, int plane, int s) {
+  return (sub * (t.packed ? 1 : t.planes) + plane) * t.spp + s;
+}
+__host__ __device__ inline int pt_n_slabs(const PlaneTensor& t) { return (t.deint ? 2 : 1) * (t.packed ? 1 : t.planes * t.spp); }
+
+inline PlaneTensor make_plane_tensor(void* base, int L, int C, int planes, int deint) {
+  PlaneTensor t;
+  const int cpad = (C + 15) & ~15;
+  t.base = static_cast<uint8_t*>(base);
+  t.rows = deint ? L / 2 : L;
+  t.packed = cpad <= 32 ? 1 : 0;
+  t.spp = t.packed ? 1 : (cpad + 63) / 64;
+  t.planes = planes;
+  t.deint = deint;
+  t.frame_bytes = (int64_t)pt_n_slabs(t) * pt_slab_bytes(t);
+  return t;
+}
+inline int64_t plane_tensor_frame_bytes(int L, int C, int planes, int deint) {
+  return make_plane_tensor(nullptr, L, C, planes, deint).frame_bytes;
+}
+
+enum PlaneKind { PK_T = 0, PK_X = 1, PK_GEN = 2 };
+
+// One conv layer of the plane engine.
+//   PK_T   "taps in N": P[row, (tap, co)] = sum_ci X[row, ci] W[tap, ci, co] is ONE MMA chain per tile (N = taps * Cout)
+//          and the tap sum y[row] = sum_t P[row + shift_t, t] is done across TMEM lanes with warp shuffles.  For the
+//          narrow-output layers (Cout = 20, k = 9) and the k55 heads (Cout = 1), where one MMA per tap would be bound by
+//          the ~44-cycle issue floor of an N = 32 instruction.
+//   PK_X   one MMA per (tap, 16-channel K step): tap = row shift of the A descriptor.  Wide-output layers.
+//   PK_GEN PK_X on the Toeplitz matrix of a 1-channel fp32 signal (stem k55 1->100, decoder k9 1->20), built in
+//          shared memory by producer warps; taps become the K dimension.
+struct PlaneConv {
+  int kind = PK_X;
+  int Lin = 0, Cin = 0, Cout = 0, K = 1, dil = 1, stride = 1;
+  int act = NSC_ACT_NONE, post_act = NSC_ACT_NONE;
+  int res_mode = RES_NONE;       // RES_ADD: `res` planes; RES_ADD_BCAST: `resvec` (B, Lout) fp32 broadcast over channels
+  int shuffle = 1;               // sub-pixel factor of the output (1 or 2)
+  int planes = 2;
+  PlaneTensor in;                // Cin > 1
+  const float* xvec = nullptr;   // Cin == 1: (B, Lin) fp32;  x' = xscale * (xvec - xsub)  (xsub may be null)
+  const float* xsub = nullptr;
+  float xscale = 1.f;
+  PlaneTensor out;               // Cout > 1
+  float* yvec = nullptr;         // Cout == 1: (B, Lout) fp32
+  PlaneTensor res;
+  const float* resvec = nullptr;
+  const float* w = nullptr;      // (K, Cin, Cout) fp32
+  const float* bias = nullptr;   // (Cout)
+  void* wpack = nullptr;         // plane_wpack_bytes() bytes, filled by plane_pack_weights()
+  int64_t B = 0;
+};
+
+bool plane_conv_supported(const PlaneConv& c);
+int64_t plane_wpack_bytes(const PlaneConv& c);
+int plane_pack_weights(const PlaneConv& c, cudaStream_t st);
+int plane_launch(const PlaneConv& c, cudaStream_t st);
+
+// fp32 <-> plane images (API edges and tests)
+int plane_from_f32(const float* x, int x_cl, int64_t B, int L, int C, const PlaneTensor& t, cudaStream_t st);
+int plane_to_f32(const PlaneTensor& t, float* y, int y_cl, int64_t B, int L, int C, cudaStream_t st);
+
+}  // namespace nsc

@@ -1,0 +1,1041 @@
+// Plane engine: the codec's conv layers on tcgen05 with fp16 plane-image activations (plane.cuh).
+//
+// Two kernels, both persistent and warp-specialised (bulk-copy loaders, ONE MMA-issuing thread, epilogue warps; all
+// hand-offs are mbarriers, tensor-core completions arrive through tcgen05.commit):
+//
+//   plane_t_kernel  PK_T  "taps in N".  A CTA walks whole frames, tile by tile (128 positions).  Per tile ONE MMA chain
+//                   computes P[row, (tap, co)] for all taps at once (N = 9 * 20 -> 192: 96 cycles per K step instead of
+//                   9 x 44 for nine N = 32 instructions) with the layer's packed weights RESIDENT in shared memory and
+//                   the input streamed slab by slab through a ring.  The tap sum y[row] = sum_t P[row + s_t, t] crosses
+//                   TMEM lanes: each epilogue warp owns 32 rows, pulls P[row + s_t] from lane (lane + s_t) mod 32 with a
+//                   shuffle, and the wrapped lanes accumulate the contribution that belongs to the SAME lane of the
+//                   neighbouring 32-row quarter ("up"/"down" spill).  Quarters are finished in row order: a quarter's
+//                   first rows take the previous quarter's up-spill, its last rows are parked in shared memory and
+//                   finished by the next quarter, which holds their down-spill.  No halo is ever loaded or recomputed.
+//   plane_x_kernel  PK_X  one MMA per (tap, K step): a tap is a row shift of the A descriptor inside the staged tile
+//                   (+8 halo rows each side, which are the zero rows of the image at frame borders).  Weights stay
+//                   resident when they fit, else stream through a ring; with hi/lo planes every W_hi unit is used for
+//                   both the A_hi and A_lo products while it is resident.  PK_GEN feeds the same pipeline from a
+//                   Toeplitz tile that producer warps build from a 1-channel fp32 signal.
+//
+// Epilogues write the next layer's plane image directly (bias, activation, residual add from the residual's planes,
+// hi/lo split, sub-pixel shuffle, stride-2 de-interleave are all index arithmetic on the way out).
+#include "plane.cuh"
+#include "tc_common.cuh"
+
+namespace nsc {
+
+using namespace tc;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// plane image addressing
+// ------------------------------------------------------------------------------------------------
+// channels [8g, 8g + 8) of position `pos` of the frame image `img`
+__device__ __forceinline__ void pt_store8(const PlaneTensor& t, uint8_t* img, int pos, int g, const float (&v)[8]) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  const int sub = t.deint ? (pos & 1) : 0;
+  const int row = (t.deint ? (pos >> 1) : pos) + 8;
+  const uint32_t sw = (uint32_t)row & 7u;
+  const int64_t sb = pt_slab_bytes(t);
+  if (t.packed) {
+    uint8_t* r = img + sub * sb + (int64_t)row * 128;
+    *reinterpret_cast<uint4*>(r + (((uint32_t)g ^ sw) << 4)) = hi;
+    if (t.planes == 2) *reinterpret_cast<uint4*>(r + (((uint32_t)(g + 4) ^ sw) << 4)) = lo;
+  } else {
+    uint8_t* r = img + (int64_t)pt_slab_index(t, sub, 0, g >> 3) * sb + (int64_t)row * 128 + ((((uint32_t)g & 7u) ^ sw) << 4);
+    *reinterpret_cast<uint4*>(r) = hi;
+    if (t.planes == 2) *reinterpret_cast<uint4*>(r + (int64_t)t.spp * sb) = lo;
+  }
+}
+
+__device__ __forceinline__ void pt_load8(const PlaneTensor& t, const uint8_t* img, int pos, int g, float (&v)[8]) {
+  const int sub = t.deint ? (pos & 1) : 0;
+  const int row = (t.deint ? (pos >> 1) : pos) + 8;
+  const uint32_t sw = (uint32_t)row & 7u;
+  const int64_t sb = pt_slab_bytes(t);
+  uint4 hi, lo = make_uint4(0, 0, 0, 0);
+  if (t.packed) {
+    const uint8_t* r = img + sub * sb + (int64_t)row * 128;
+    hi = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)g ^ sw) << 4)));
+    if (t.planes == 2) lo = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)(g + 4) ^ sw) << 4)));
+  } else {
+    const uint8_t* r = img + (int64_t)pt_slab_index(t, sub, 0, g >> 3) * sb + (int64_t)row * 128 + ((((uint32_t)g & 7u) ^ sw) << 4);
+    hi = __ldg(reinterpret_cast<const uint4*>(r));
+    if (t.planes == 2) lo = __ldg(reinterpret_cast<const uint4*>(r + (int64_t)t.spp * sb));
+  }
+  unpack8(hi, v);
+  if (t.planes == 2) {
+    float l[8];
+    unpack8(lo, l);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += l[i];
+  }
+}
+
+__host__ __device__ inline int pt_chunks_per_row(const PlaneTensor& t) { return t.packed ? 4 : t.spp * 8; }
+
+// ------------------------------------------------------------------------------------------------
+// fp32 <-> planes
+// ------------------------------------------------------------------------------------------------
+__global__ void plane_from_f32_kernel(const float* __restrict__ x, int x_cl, int64_t B, int L, int C, PlaneTensor t) {
+  const int nch = pt_chunks_per_row(t);
+  const int64_t total = B * (int64_t)nch * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pos = (int)(i % L);
+    const int g = (int)((i / L) % nch);
+    const int64_t b = i / ((int64_t)L * nch);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = 8 * g + e;
+      v[e] = c < C ? (x_cl ? x[(b * L + pos) * C + c] : x[(b * C + c) * L + pos]) : 0.f;
+    }
+    pt_store8(t, t.base + b * t.frame_bytes, pos, g, v);
+  }
+}
+
+__global__ void plane_to_f32_kernel(PlaneTensor t, float* __restrict__ y, int y_cl, int64_t B, int L, int C) {
+  const int nch = (C + 7) / 8;
+  const int64_t total = B * (int64_t)nch * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pos = (int)(i % L);
+    const int g = (int)((i / L) % nch);
+    const int64_t b = i / ((int64_t)L * nch);
+    float v[8];
+    pt_load8(t, t.base + b * t.frame_bytes, pos, g, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = 8 * g + e;
+      if (c < C) {
+        if (y_cl) y[(b * L + pos) * C + c] = v[e];
+        else y[(b * C + c) * L + pos] = v[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 (K, Cin, Cout) -> fp16 hi/lo operand slabs in the exact shared-memory image
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* w;
+  __half* out;
+  int kind, K, Cin, Cout, planes, in_packed, in_spp;
+  int rows;     // rows per unit (MMA N)
+  int C;        // PK_T: output channels per tap
+  int n_units;
+};
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int k) {
+  return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
+}
+
+__global__ void plane_pack_kernel(PackArgs a) {
+  const int64_t total = (int64_t)a.n_units * a.rows * 64;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i & 63);
+    const int n = (int)((i >> 6) % a.rows);
+    const int u = (int)(i / (64LL * a.rows));
+    int t = 0, ci = -1, co = -1, lo_plane = 0;
+    if (a.kind == PK_T) {
+      // units = weight slabs: unpacked input -> (plane, slab) ; packed input -> one slab [hi | lo]
+      t = n / a.C;
+      co = n - t * a.C;
+      if (t >= a.K) co = -1;
+      if (a.in_packed) { ci = k & 31; lo_plane = k >> 5; }
+      else { ci = (u % a.in_spp) * 64 + k; lo_plane = u / a.in_spp; }
+    } else if (a.kind == PK_X) {
+      co = n;
+      if (a.in_packed) { t = u; ci = k & 31; lo_plane = k >> 5; }
+      else {
+        // u = ((slab * K) + tap) * planes + plane
+        lo_plane = u % a.planes;
+        t = (u / a.planes) % a.K;
+        ci = (u / a.planes / a.K) * 64 + k;
+      }
+    } else {   // PK_GEN: taps are the K dimension, unit = plane
+      co = n; t = k; ci = 0; lo_plane = u;
+    }
+    float v = 0.f;
+    if (co >= 0 && co < a.Cout && ci >= 0 && ci < a.Cin && t < a.K && lo_plane < a.planes)
+      v = a.w[((int64_t)t * a.Cin + ci) * a.Cout + co];
+    const __half hi = __float2half_rn(v);
+    const __half val = lo_plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    *reinterpret_cast<__half*>(reinterpret_cast<char*>(a.out) + (size_t)u * a.rows * 128 + sw128_off(n, k)) = val;
+  }
+}
+
+// ================================================================================================
+// PK_T
+// ================================================================================================
+struct TParams {
+  PlaneTensor in, out;
+  const uint8_t* wpack;
+  const float* bias;
+  float* yvec;
+  int N, n_wslab, ksteps;
+  int L, dil, act, na;
+  int64_t B;
+};
+
+constexpr int kTThreads = 6 * 32;   // warps 0-3 epilogue (one per TMEM lane quarter), 4 MMA issuer, 5 loader
+constexpr int kTSlots = 12;         // spill slots: three tiles' worth of quarters
+constexpr int kAStage = 128 * 128;  // one input slab of one tile
+
+template <int C, int TAPS>
+struct TShape {
+  static constexpr int kMaxM = (C == 1) ? 32 : 8;   // largest row shift handled (lanes that can wrap)
+};
+
+// ---- phase 1: shifted sums of one 32-row quarter ---------------------------------------------------
+template <int C, int TAPS>
+__device__ __forceinline__ void t_phase1(uint32_t trow, int lane, int dil, float (&acc)[C], float (&up)[C], float (&down)[C]);
+
+template <>
+__device__ __forceinline__ void t_phase1<20, 9>(uint32_t trow, int lane, int dil, float (&acc)[20], float (&up)[20], float (&down)[20]) {
+#pragma unroll
+  for (int c = 0; c < 20; ++c) { acc[c] = 0.f; up[c] = 0.f; down[c] = 0.f; }
+  uint32_t r[2][20];
+  auto load_tap = [&](int t, uint32_t (&dst)[20]) {
+    uint32_t a[16], b[4];
+    tmem_ld16(trow + (uint32_t)(t * 20), a);
+    tmem_ld4(trow + (uint32_t)(t * 20 + 16), b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dst[i] = a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[16 + i] = b[i];
+  };
+  load_tap(0, r[0]);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    tmem_ld_wait();
+    if (t + 1 < 9) load_tap(t + 1, r[(t + 1) & 1]);   // next tap's load is in flight under this tap's shuffles
+    const int s = (t - 4) * dil;
+    const int src = (lane + s) & 31;
+    const bool inr = (unsigned)(lane + s) < 32u;
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+      const float v = __uint_as_float(r[t & 1][c]);
+      if (t == 4) {
+        acc[c] += v;
+      } else {
+        const float x = __shfl_sync(0xffffffffu, v, src);
+        if (inr) acc[c] += x;
+        else if (t > 4) down[c] += x;   // source row belongs to this quarter, target row to the previous one
+        else up[c] += x;                // ... to the next one
+      }
+    }
+  }
+}
+
+template <>
+__device__ __forceinline__ void t_phase1<1, 55>(uint32_t trow, int lane, int dil, float (&acc)[1], float (&up)[1], float (&down)[1]) {
+  (void)dil;
+  uint32_t r0[32], r1[32];
+  tmem_ld32(trow, r0);
+  tmem_ld32(trow + 32, r1);
+  tmem_ld_wait();
+  float a = 0.f, u = 0.f, d = 0.f;
+#pragma unroll
+  for (int t = 0; t < 55; ++t) {
+    const float v = __uint_as_float(t < 32 ? r0[t & 31] : r1[t & 31]);
+    const int s = t - 27;
+    if (s == 0) { a += v; continue; }
+    const float x = __shfl_sync(0xffffffffu, v, (lane + s) & 31);
+    const bool inr = (unsigned)(lane + s) < 32u;
+    if (inr) a += x;
+    else if (s > 0) d += x;
+    else u += x;
+  }
+  acc[0] = a; up[0] = u; down[0] = d;
+}
+
+template <int C>
+__device__ __forceinline__ void t_finalize(const TParams& p, int64_t f, int row, const float (&r)[C], const float (&bias)[C]) {
+  if constexpr (C == 1) {
+    p.yvec[f * p.L + row] = apply_act(r[0] + bias[0], p.act);
+  } else {
+    uint8_t* img = p.out.base + f * p.out.frame_bytes;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = 8 * g + e;
+        v[e] = c < C ? apply_act(r[c < C ? c : 0] + bias[c < C ? c : 0], p.act) : 0.f;
+      }
+      pt_store8(p.out, img, row, g, v);
+    }
+  }
+}
+
+template <int C, int TAPS>
+__global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
+  constexpr int kMaxM = TShape<C, TAPS>::kMaxM;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t w_full, a_full[8], a_empty[8], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t wslab_bytes = (uint32_t)p.N * 128u;
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + (uint32_t)p.n_wslab * wslab_bytes;
+  float* sU = reinterpret_cast<float*>(sA + (uint32_t)p.na * kAStage);     // [kTSlots][kMaxM][C]
+  float* sP = sU + kTSlots * kMaxM * C;                                     // [kTSlots][kMaxM][C]
+  const int T = p.L / 128;
+  const int nst = pt_n_slabs(p.in);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.N) tmem_cols *= 2;
+
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (warp == 4) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 4) {
+    // =========================== epilogue ===========================
+    const int q = warp;
+    float bias[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    const int m = ((TAPS - 1) / 2) * p.dil;
+    const int nq = 4 * T;
+    uint32_t it = 0;
+    for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
+      for (int j = 0; j < T; ++j, ++it) {
+        const uint32_t acc_i = it & 1u;
+        mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
+        tc_fence_after();
+        float acc[C], up[C], down[C];
+        t_phase1<C, TAPS>(tmem + ((uint32_t)(q * 32) << 16) + acc_i * (uint32_t)p.N, lane, p.dil, acc, up, down);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc_i]);   // TMEM slot free: the next tile's MMAs run under phase 2
+
+        const uint32_t gq = it * 4u + (uint32_t)q;
+        const int fqi = j * 4 + q;
+        const bool lastq = fqi == nq - 1;
+        const uint32_t slot = gq % kTSlots;
+        if (lane < m) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) sU[(slot * kMaxM + lane) * C + c] = up[c];
+        }
+        if (lane >= 32 - m && !lastq) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) sP[(slot * kMaxM + (lane - (32 - m))) * C + c] = acc[c];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t slot1 = (gq + kTSlots - 1) % kTSlots, slot2 = (gq + kTSlots - 2) % kTSlots;
+        if (lane < 32 - m || lastq) {          // this quarter's own rows that need nothing from the next quarter
+          float r[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) r[c] = acc[c];
+          if (lane < m && fqi >= 1) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) r[c] += sU[(slot1 * kMaxM + lane) * C + c];
+          }
+          t_finalize<C>(p, f, fqi * 32 + lane, r, bias);
+        }
+        if (lane >= 32 - m && fqi >= 1) {      // the previous quarter's parked rows: this thread holds their down-spill
+          float r[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) r[c] = sP[(slot1 * kMaxM + (lane - (32 - m))) * C + c] + down[c];
+          if (lane < m && fqi >= 2) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) r[c] += sU[(slot2 * kMaxM + lane) * C + c];
+          }
+          t_finalize<C>(p, f, (fqi - 1) * 32 + lane, r, bias);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      mbar_wait(&w_full, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_f16(p.N);
+      const uint32_t w_lo0 = desc_lo(smem_u32(sW));
+      const uint32_t wslab_lo = wslab_bytes >> 4;
+      uint32_t it = 0, ait = 0;
+      for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
+        for (int j = 0; j < T; ++j, ++it) {
+          const uint32_t acc_i = it & 1u;
+          mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d = tmem + acc_i * (uint32_t)p.N;
+          uint32_t accum = 0;
+          auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
+            for (int ks = 0; ks < nks; ++ks) {
+              mma_f16_ss(d, desc_from_lo(a_lo + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc, accum);
+              accum = 1;
+            }
+          };
+          for (int s = 0; s < nst; ++s, ++ait) {
+            const uint32_t slot = ait % (uint32_t)p.na;
+            mbar_wait(&a_full[slot], (ait / (uint32_t)p.na) & 1u);
+            tc_fence_after();
+            const uint32_t a_lo = desc_lo(smem_u32(sA + slot * kAStage));
+            if (p.in.packed) {
+              issue(a_lo, w_lo0, p.ksteps);                 // hi * W_hi
+              if (p.in.planes == 2) {
+                issue(a_lo, w_lo0 + 4u, p.ksteps);          // hi * W_lo   (lo halves start 64 bytes into the row)
+                issue(a_lo + 4u, w_lo0, p.ksteps);          // lo * W_hi
+              }
+            } else {
+              const int plane = s / p.in.spp, sl = s - plane * p.in.spp;
+              const int nks = min(4, p.ksteps - 4 * sl);
+              issue(a_lo, w_lo0 + (uint32_t)sl * wslab_lo, nks);                                      // (hi | lo) * W_hi
+              if (plane == 0 && p.in.planes == 2) issue(a_lo, w_lo0 + (uint32_t)(p.in.spp + sl) * wslab_lo, nks);   // hi * W_lo
+            }
+            umma_commit(&a_empty[slot]);
+          }
+          umma_commit(&acc_full[acc_i]);
+        }
+      }
+    }
+  } else {
+    // =========================== loader ===========================
+    if (elect_one()) {
+      mbar_expect_tx(&w_full, (uint32_t)p.n_wslab * wslab_bytes);
+      for (int i = 0; i < p.n_wslab; ++i) bulk_g2s(sW + (uint32_t)i * wslab_bytes, p.wpack + (size_t)i * wslab_bytes, wslab_bytes, &w_full);
+      const int64_t sb = pt_slab_bytes(p.in);
+      uint32_t ait = 0;
+      for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
+        const uint8_t* img = p.in.base + f * p.in.frame_bytes;
+        for (int j = 0; j < T; ++j) {
+          for (int s = 0; s < nst; ++s, ++ait) {
+            const uint32_t slot = ait % (uint32_t)p.na;
+            mbar_wait(&a_empty[slot], ((ait / (uint32_t)p.na) & 1u) ^ 1u);
+            mbar_expect_tx(&a_full[slot], kAStage);
+            bulk_g2s(sA + slot * kAStage, img + s * sb + (int64_t)(8 + 128 * j) * 128, kAStage, &a_full[slot]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ================================================================================================
+// PK_X / PK_GEN
+// ================================================================================================
+struct XParams {
+  int kind;
+  PlaneTensor in, out, res;
+  const float* xvec;
+  const float* xsub;
+  float xscale;
+  const float* resvec;
+  const uint8_t* wpack;
+  const float* bias;
+  int Lin, Lout, Cin, Cout, K, dil, stride, padL;
+  int act, post_act, res_mode, shuffle, planes;
+  int Npad, ksteps, mt, tile, tiles_per_frame;
+  int n_stage, kbuf, stage_bytes;
+  int n_units, unit_bytes, wslots, resident;
+  int tmem_cols;
+  int zero_from, zero_to;    // output chunks the epilogue must clear (K padding the consumer will read)
+  int64_t B, n_tiles;
+};
+
+constexpr int kXEpiWarps = 8, kXGenWarps = 4;
+constexpr int kXThreads = (kXEpiWarps + 3 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader
+constexpr int kXMaxStage = 16, kXMaxW = 40;
+
+__global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_constant__ XParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t a_full[kXMaxStage], a_empty[kXMaxStage], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbuf = p.n_stage * p.kbuf;
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
+  const int acc_cols = p.mt * p.Npad;
+
+  if (tid == 0) {
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], p.kind == PK_GEN ? kXGenWarps : 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kXEpiWarps); }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (warp == kXEpiWarps) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < kXEpiWarps) {
+    // =========================== epilogue ===========================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int nb = p.Npad >> 4;
+    const int n_e = p.mt * nb;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int64_t f = tile / p.tiles_per_frame;
+      const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+      const uint32_t acc_i = it & 1u;
+      uint8_t* oimg = p.out.base + f * p.out.frame_bytes;
+      const uint8_t* rimg = p.res_mode == RES_ADD ? p.res.base + f * p.res.frame_bytes : nullptr;
+      mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
+      tc_fence_after();
+      for (int u = half; u < n_e; u += 2) {
+        const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
+        const int pos = q0 + mt_i * 128 + quarter * 32 + lane;
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
+        float rs[16];
+        if (p.res_mode == RES_ADD) {
+          float ra[8], rb[8];
+          pt_load8(p.res, rimg, pos, c0 >> 3, ra);
+          pt_load8(p.res, rimg, pos, (c0 >> 3) + 1, rb);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { rs[e] = ra[e]; rs[8 + e] = rb[e]; }
+        } else if (p.res_mode == RES_ADD_BCAST) {
+          const float rv = __ldg(p.resvec + f * p.Lout + pos);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) rs[e] = (c0 + e < p.Cout) ? rv : 0.f;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) rs[e] = 0.f;
+        }
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int co = c0 + e;
+          const float b = (co < p.Cout && p.bias) ? __ldg(p.bias + co) : 0.f;
+          v[e] = apply_act(apply_act(__uint_as_float(r[e]) + b, p.act) + rs[e], p.post_act);
+        }
+        if (p.shuffle == 1) {
+          float a[8], b[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { a[e] = v[e]; b[e] = v[8 + e]; }
+          pt_store8(p.out, oimg, pos, c0 >> 3, a);
+          pt_store8(p.out, oimg, pos, (c0 >> 3) + 1, b);
+        } else {   // sub-pixel: out[2 pos + r, c] = y[pos, 2 c + r]   (nscm.py:158-167)
+          float a[8], b[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { a[e] = v[2 * e]; b[e] = v[2 * e + 1]; }
+          pt_store8(p.out, oimg, 2 * pos, c0 >> 4, a);
+          pt_store8(p.out, oimg, 2 * pos + 1, c0 >> 4, b);
+        }
+      }
+      if (half == 0 && p.zero_from < p.zero_to) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
+          const int pos = q0 + mt_i * 128 + quarter * 32 + lane;
+          for (int g = p.zero_from; g < p.zero_to; ++g) {
+            if (p.shuffle == 1) pt_store8(p.out, oimg, pos, g, z);
+            else { pt_store8(p.out, oimg, 2 * pos, g, z); pt_store8(p.out, oimg, 2 * pos + 1, g, z); }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc_i]);
+    }
+  } else if (warp == kXEpiWarps) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(p.Npad);
+      const uint32_t mt_step = (128u * 128u) >> 4;
+      uint32_t it = 0, wit = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc_i = it & 1u;
+        mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem + acc_i * (uint32_t)acc_cols;
+        const int kb = (int)(it % (uint32_t)p.kbuf) * p.n_stage;
+        const uint32_t a_phase = (it / (uint32_t)p.kbuf) & 1u;
+        uint32_t waited = 0, accum = 0;
+        int u = 0;
+        auto wait_stage = [&](int stage) {
+          if (!((waited >> stage) & 1u)) {
+            mbar_wait(&a_full[kb + stage], a_phase);
+            tc_fence_after();
+            waited |= 1u << stage;
+          }
+        };
+        auto wait_w = [&]() -> uint32_t {
+          const uint32_t ws = p.resident ? (uint32_t)u : wit % (uint32_t)p.wslots;
+          mbar_wait(&w_full[ws], p.resident ? 0u : (wit / (uint32_t)p.wslots) & 1u);
+          tc_fence_after();
+          return ws;
+        };
+        auto done_w = [&](uint32_t ws) {
+          if (!p.resident) { umma_commit(&w_empty[ws]); ++wit; }
+          ++u;
+        };
+        auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
+          for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
+            const uint32_t d = d0 + (uint32_t)(mt_i * p.Npad);
+            for (int ks = 0; ks < nks; ++ks)
+              mma_f16_ss(d, desc_from_lo(a_lo + (uint32_t)mt_i * mt_step + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc,
+                         accum | (uint32_t)(ks > 0));
+          }
+          accum = 1;
+        };
+        if (p.kind == PK_GEN) {
+          for (int wp = 0; wp < p.planes; ++wp) {
+            const uint32_t ws = wait_w();
+            const uint32_t b_lo = desc_lo(smem_u32(sW + ws * (uint32_t)p.unit_bytes));
+            for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
+              wait_stage(ap);
+              issue(desc_lo(smem_u32(sA + (uint32_t)(kb + ap) * (uint32_t)p.stage_bytes)), b_lo, p.ksteps);
+            }
+            done_w(ws);
+          }
+          for (int ap = 0; ap < p.planes; ++ap) umma_commit(&a_empty[kb + ap]);
+        } else if (p.in.packed) {
+          wait_stage(0);
+          for (int t = 0; t < p.K; ++t) {
+            const uint32_t ws = wait_w();
+            const uint32_t b_lo = desc_lo(smem_u32(sW + ws * (uint32_t)p.unit_bytes));
+            const uint32_t a_lo = desc_lo(smem_u32(sA + (uint32_t)kb * (uint32_t)p.stage_bytes) + (uint32_t)(8 + t * p.dil - p.padL) * 128u);
+            issue(a_lo, b_lo, p.ksteps);
+            if (p.planes == 2) {
+              issue(a_lo, b_lo + 4u, p.ksteps);
+              issue(a_lo + 4u, b_lo, p.ksteps);
+            }
+            done_w(ws);
+          }
+          umma_commit(&a_empty[kb]);
+        } else {
+          const int nsub = p.in.deint ? 2 : 1;
+          for (int s = 0; s < p.in.spp; ++s) {
+            const int nks = min(4, p.ksteps - 4 * s);
+            for (int t = 0; t < p.K; ++t) {
+              int sub = 0, rowoff;
+              if (p.stride == 1) rowoff = 8 + t * p.dil - p.padL;
+              else { const int tp = t - p.padL; sub = tp & 1; rowoff = 8 + (tp - sub) / 2; }
+              for (int wp = 0; wp < p.planes; ++wp) {
+                const uint32_t ws = wait_w();
+                const uint32_t b_lo = desc_lo(smem_u32(sW + ws * (uint32_t)p.unit_bytes));
+                for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
+                  const int stage = pt_slab_index(p.in, sub, ap, s);
+                  wait_stage(stage);
+                  issue(desc_lo(smem_u32(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes) + (uint32_t)rowoff * 128u), b_lo, nks);
+                }
+                done_w(ws);
+              }
+            }
+            for (int sub = 0; sub < nsub; ++sub)
+              for (int ap = 0; ap < p.planes; ++ap) umma_commit(&a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
+          }
+        }
+        umma_commit(&acc_full[acc_i]);
+      }
+    }
+  } else if (warp == kXEpiWarps + 1) {
+    // =========================== A loader (bulk copies of plane tiles) ===========================
+    if (p.kind != PK_GEN && elect_one()) {
+      const int64_t sb = pt_slab_bytes(p.in);
+      const int nsub = p.in.deint ? 2 : 1;
+      const int npl = p.in.packed ? 1 : p.in.planes;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int64_t f = tile / p.tiles_per_frame;
+        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+        const uint8_t* img = p.in.base + f * p.in.frame_bytes;
+        const int kb = (int)(it % (uint32_t)p.kbuf) * p.n_stage;
+        const uint32_t ph = ((it / (uint32_t)p.kbuf) & 1u) ^ 1u;
+        for (int s = 0; s < p.in.spp; ++s)          // consumption order of the issuer: slab-major
+          for (int sub = 0; sub < nsub; ++sub)
+            for (int ap = 0; ap < npl; ++ap) {
+              const int stage = pt_slab_index(p.in, sub, ap, s);
+              mbar_wait(&a_empty[kb + stage], ph);
+              mbar_expect_tx(&a_full[kb + stage], (uint32_t)p.stage_bytes);
+              bulk_g2s(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes, img + stage * sb + (int64_t)q0 * 128, (uint32_t)p.stage_bytes,
+                       &a_full[kb + stage]);
+            }
+      }
+    }
+  } else if (warp == kXEpiWarps + 2) {
+    // =========================== W loader ===========================
+    if (elect_one()) {
+      if (p.resident) {
+        for (int u = 0; u < p.n_units; ++u) {
+          mbar_expect_tx(&w_full[u], (uint32_t)p.unit_bytes);
+          bulk_g2s(sW + (uint32_t)u * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[u]);
+        }
+      } else {
+        uint32_t wit = 0;
+        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          for (int u = 0; u < p.n_units; ++u, ++wit) {
+            const uint32_t ws = wit % (uint32_t)p.wslots;
+            mbar_wait(&w_empty[ws], ((wit / (uint32_t)p.wslots) & 1u) ^ 1u);
+            mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
+            bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== Toeplitz producers (PK_GEN) ===========================
+    if (p.kind == PK_GEN) {
+      const int ptid = tid - (kXEpiWarps + 3) * 32;
+      const int nch = p.ksteps * 2;     // 16-byte chunks per row that the MMAs read
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int64_t f = tile / p.tiles_per_frame;
+        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+        const int kb = (int)(it % (uint32_t)p.kbuf) * p.n_stage;
+        const uint32_t ph = ((it / (uint32_t)p.kbuf) & 1u) ^ 1u;
+        for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
+        const float* xv = p.xvec + f * p.Lin;
+        const float* xs = p.xsub ? p.xsub + f * p.Lin : nullptr;
+        uint8_t* dhi = sA + (uint32_t)kb * (uint32_t)p.stage_bytes;
+        uint8_t* dlo = dhi + p.stage_bytes;
+        for (int item = ptid; item < p.tile * nch; item += kXGenWarps * 32) {
+          const int i = item / nch, g = item - i * nch;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = 8 * g + e;
+            const int pos = q0 + i - p.padL + k * p.dil;
+            float x = 0.f;
+            if (k < p.K && pos >= 0 && pos < p.Lin) x = p.xscale * (__ldg(xv + pos) - (xs ? __ldg(xs + pos) : 0.f));
+            v[e] = x;
+          }
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          const uint32_t off = (uint32_t)i * 128u + (((uint32_t)g ^ ((uint32_t)i & 7u)) << 4);
+          *reinterpret_cast<uint4*>(dhi + off) = hi;
+          if (p.planes == 2) *reinterpret_cast<uint4*>(dlo + off) = lo;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0)
+          for (int ap = 0; ap < p.planes; ++ap) mbar_arrive(&a_full[kb + ap]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == kXEpiWarps) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ourselves (alignment slack + static barriers)
+
+struct TPlan {
+  int N, n_wslab, ksteps, na;
+  size_t smem;
+};
+
+bool plan_t(const PlaneConv& c, TPlan* pl) {
+  const bool k9 = (c.Cout == 20 && c.K == 9 && c.dil >= 1 && c.dil <= 2);
+  const bool k55 = (c.Cout == 1 && c.K == 55 && c.dil == 1);
+  if (!k9 && !k55) return false;
+  if (c.stride != 1 || c.shuffle != 1 || c.res_mode != RES_NONE || c.post_act != NSC_ACT_NONE) return false;
+  if (c.Cin < 2 || c.in.deint || c.Lin % 128 != 0 || c.in.rows != c.Lin) return false;
+  if (k9 && (!c.out.packed || c.out.deint || c.out.rows != c.Lin)) return false;
+  pl->N = k9 ? 192 : 64;
+  pl->ksteps = (c.Cin + 15) / 16;
+  pl->n_wslab = c.in.packed ? 1 : c.in.planes * c.in.spp;
+  const int C = c.Cout, maxm = k9 ? 8 : 32;
+  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * kTSlots * maxm * C * sizeof(float);
+  if (fixed + 2ull * kAStage > kSmemBudget) return false;
+  size_t na = (kSmemBudget - fixed) / kAStage;
+  if (na > 8) na = 8;
+  pl->na = (int)na;
+  pl->smem = 1024 + fixed + na * kAStage;
+  return true;
+}
+
+bool plan_x(const PlaneConv& c, XParams* p) {
+  const bool gen = c.kind == PK_GEN;
+  int Lout, padL;
+  same_padding(c.Lin, c.K, c.dil, c.stride, &Lout, &padL);
+  if (Lout % 128 != 0) return false;
+  if (c.shuffle != 1 && c.shuffle != 2) return false;
+  if (c.Cout < 2 || c.Cout > 128 || c.Cout % c.shuffle != 0) return false;
+  if (gen) {
+    if (c.Cin != 1 || c.stride != 1 || c.K > 64 || c.xvec == nullptr) return false;
+  } else {
+    if (c.Cin < 2 || c.Cin > 128) return false;
+    if (c.stride == 1) { if (c.in.deint || c.in.rows != c.Lin) return false; }
+    else if (c.stride == 2) { if (!c.in.deint || c.in.packed || c.dil != 1 || c.Lin % 2 != 0 || c.in.rows != c.Lin / 2) return false; }
+    else return false;
+    const int span = (c.K - 1) * c.dil;           // rows touched beyond the tile: [8 - padL, 8 - padL + span] must stay in [0, 16]
+    if (c.stride == 1 && (padL > 8 || span - padL > 8)) return false;
+    if (c.stride == 2 && (padL > 16 || span - padL > 16)) return false;
+  }
+  if (c.res_mode == RES_ADD && (c.res.deint || c.res.rows != Lout)) return false;
+  if (c.res_mode == RES_ADD_BCAST && c.resvec == nullptr) return false;
+  if (c.res_mode == RES_MUL) return false;
+  if (c.out.rows != (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
+  p->kind = c.kind;
+  p->in = c.in; p->out = c.out; p->res = c.res;
+  p->xvec = c.xvec; p->xsub = c.xsub; p->xscale = c.xscale; p->resvec = c.resvec;
+  p->wpack = static_cast<const uint8_t*>(c.wpack); p->bias = c.bias;
+  p->Lin = c.Lin; p->Lout = Lout; p->Cin = c.Cin; p->Cout = c.Cout; p->K = c.K; p->dil = c.dil; p->stride = c.stride; p->padL = padL;
+  p->act = c.act; p->post_act = c.post_act; p->res_mode = c.res_mode; p->shuffle = c.shuffle; p->planes = c.planes;
+  p->Npad = (c.Cout + 15) & ~15;
+  p->ksteps = gen ? (c.K + 15) / 16 : (c.Cin + 15) / 16;
+  p->n_stage = gen ? c.planes : pt_n_slabs(c.in);
+  p->unit_bytes = p->Npad * 128;
+  p->n_units = gen ? c.planes : (c.in.packed ? c.K : c.in.spp * c.K * c.planes);
+  if (p->n_stage > kXMaxStage) return false;
+  // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
+  for (int mt = (Lout % 256 == 0 && c.stride == 1) ? 2 : 1; mt >= 1; --mt) {
+    p->mt = mt;
+    p->tile = 128 * mt;
+    p->stage_bytes = (p->tile + 16) * 128;
+    const size_t a1 = (size_t)p->n_stage * p->stage_bytes;
+    const size_t wall = (size_t)p->n_units * p->unit_bytes;
+    if (2 * mt * p->Npad > 512) continue;
+    if (p->n_units <= kXMaxW && 2 * a1 + wall <= kSmemBudget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
+    else if (p->n_units <= kXMaxW && a1 + wall <= kSmemBudget) { p->kbuf = 1; p->resident = 1; p->wslots = p->n_units; }
+    else if (2 * a1 + 4ull * p->unit_bytes <= kSmemBudget) { p->kbuf = 2; p->resident = 0; }
+    else if (a1 + 3ull * p->unit_bytes <= kSmemBudget) { p->kbuf = 1; p->resident = 0; }
+    else continue;
+    if (p->n_stage * p->kbuf > kXMaxStage) { if (p->kbuf == 2 && !p->resident && a1 + 3ull * p->unit_bytes <= kSmemBudget) p->kbuf = 1; else continue; }
+    if (!p->resident) {
+      size_t ws = (kSmemBudget - (size_t)p->kbuf * a1) / p->unit_bytes;
+      if (ws > (size_t)kXMaxW) ws = kXMaxW;
+      if (ws > (size_t)p->n_units) ws = p->n_units;
+      p->wslots = (int)ws;
+    }
+    p->tiles_per_frame = Lout / p->tile;
+    p->n_tiles = c.B * p->tiles_per_frame;
+    int cols = 32;
+    while (cols < 2 * mt * p->Npad) cols *= 2;
+    p->tmem_cols = cols;
+    p->B = c.B;
+    // chunks of the output row the consumer's K steps read but this layer does not write
+    const int out_c = c.Cout / c.shuffle;
+    const int written = c.shuffle == 1 ? p->Npad / 8 : p->Npad / 16;
+    int needed = ((out_c + 15) & ~15) / 8;
+    if (c.out.packed) needed = 4;
+    p->zero_from = written;
+    p->zero_to = needed > written ? needed : written;
+    return true;
+  }
+  return false;
+}
+
+size_t x_smem_bytes(const XParams& p) {
+  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.unit_bytes;
+}
+
+}  // namespace
+
+bool plane_conv_supported(const PlaneConv& c) {
+  if (c.planes != 1 && c.planes != 2) return false;
+  if (c.kind == PK_T) { TPlan pl; return plan_t(c, &pl); }
+  XParams p;
+  PlaneConv cc = c;
+  cc.B = 1;
+  return plan_x(cc, &p);
+}
+
+int64_t plane_wpack_bytes(const PlaneConv& c) {
+  if (c.kind == PK_T) {
+    TPlan pl;
+    if (!plan_t(c, &pl)) return -1;
+    return (int64_t)pl.n_wslab * pl.N * 128;
+  }
+  XParams p;
+  PlaneConv cc = c;
+  cc.B = 1;
+  if (!plan_x(cc, &p)) return -1;
+  return (int64_t)p.n_units * p.unit_bytes;
+}
+
+int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
+  NSC_CHECK_ARG(c.w != nullptr && c.wpack != nullptr, "plane engine: null weights");
+  PackArgs a;
+  a.w = c.w; a.out = static_cast<__half*>(c.wpack);
+  a.kind = c.kind; a.K = c.K; a.Cin = c.Cin; a.Cout = c.Cout; a.planes = c.planes;
+  a.in_packed = c.kind == PK_GEN ? 0 : c.in.packed;
+  a.in_spp = c.kind == PK_GEN ? 1 : c.in.spp;
+  a.C = c.Cout;
+  if (c.kind == PK_T) {
+    TPlan pl;
+    NSC_CHECK_ARG(plan_t(c, &pl), "plane engine: unsupported taps-in-N layer (k%d d%d %d->%d)", c.K, c.dil, c.Cin, c.Cout);
+    a.rows = pl.N; a.n_units = pl.n_wslab;
+  } else {
+    XParams p;
+    PlaneConv cc = c;
+    cc.B = 1;
+    NSC_CHECK_ARG(plan_x(cc, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
+    a.rows = p.Npad; a.n_units = p.n_units;
+  }
+  const int64_t total = (int64_t)a.n_units * a.rows * 64;
+  const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
+  ProfScope prof(st, "plane_pack_weights", 0.0, 4.0 * c.K * c.Cin * c.Cout + 2.0 * total);
+  plane_pack_kernel<<<blocks, 256, 0, st>>>(a);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+int plane_launch(const PlaneConv& c, cudaStream_t st) {
+  if (c.B == 0) return NSC_OK;
+  NSC_CHECK_ARG(c.wpack != nullptr, "plane engine: weights not packed");
+  int Lout, padL;
+  same_padding(c.Lin, c.K, c.dil, c.stride, &Lout, &padL);
+  const double macs = (double)c.B * Lout * c.K * c.Cin * c.Cout;
+  char name[32];
+  if (c.kind == PK_T) {
+    TPlan pl;
+    NSC_CHECK_ARG(plan_t(c, &pl), "plane engine: unsupported taps-in-N layer (k%d d%d %d->%d)", c.K, c.dil, c.Cin, c.Cout);
+    TParams p;
+    p.in = c.in; p.out = c.out;
+    p.wpack = static_cast<const uint8_t*>(c.wpack); p.bias = c.bias; p.yvec = c.yvec;
+    p.N = pl.N; p.n_wslab = pl.n_wslab; p.ksteps = pl.ksteps; p.L = c.Lin; p.dil = c.dil; p.act = c.act; p.na = pl.na; p.B = c.B;
+    NSC_CHECK_ARG(c.Cout > 1 || c.yvec != nullptr, "plane engine: head without an output vector");
+    snprintf(name, sizeof(name), "pT%d_k%dd%d_c%dto%d", c.planes, c.K, c.dil, c.Cin, c.Cout);
+    const double bytes = (double)c.B * (c.in.frame_bytes * (double)c.Lin / (c.Lin + 16) + (c.Cout > 1 ? 128.0 * c.Lin * (c.planes == 2 ? 1.0 : 0.5) : 4.0 * c.Lin));
+    ProfScope prof(st, name, 2.0 * macs, bytes);
+    const int64_t grid = c.B < sm_count() ? c.B : sm_count();
+    if (c.Cout == 20) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 9><<<(unsigned)grid, kTThreads, pl.smem, st>>>(p);
+    } else {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<1, 55><<<(unsigned)grid, kTThreads, pl.smem, st>>>(p);
+    }
+    NSC_LAUNCH_OK();
+    return NSC_OK;
+  }
+  XParams p;
+  NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
+  const size_t smem = x_smem_bytes(p);
+  NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
+  const double pl_bytes = c.planes == 2 ? 1.0 : 0.5;
+  double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : c.in.frame_bytes * 1.0);
+  bytes += (double)c.B * c.out.frame_bytes;
+  if (c.res_mode == RES_ADD) bytes += (double)c.B * c.res.frame_bytes;
+  (void)pl_bytes;
+  ProfScope prof(st, name, 2.0 * macs, bytes);
+  const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  plane_x_kernel<<<(unsigned)grid, kXThreads, smem, st>>>(p);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+int plane_from_f32(const float* x, int x_cl, int64_t B, int L, int C, const PlaneTensor& t, cudaStream_t st) {
+  if (B == 0) return NSC_OK;
+  const int64_t total = B * (int64_t)pt_chunks_per_row(t) * L;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  ProfScope prof(st, "plane_from_f32", 0.0, (double)B * (4.0 * L * C + t.frame_bytes));
+  plane_from_f32_kernel<<<blocks, 256, 0, st>>>(x, x_cl, B, L, C, t);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+int plane_to_f32(const PlaneTensor& t, float* y, int y_cl, int64_t B, int L, int C, cudaStream_t st) {
+  if (B == 0) return NSC_OK;
+  const int64_t total = B * (int64_t)((C + 7) / 8) * L;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  ProfScope prof(st, "plane_to_f32", 0.0, (double)B * (4.0 * L * C + t.frame_bytes));
+  plane_to_f32_kernel<<<blocks, 256, 0, st>>>(t, y, y_cl, B, L, C);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+}  // namespace nsc
+
+// ---- conv1d on the plane engine with channels-last fp32 tensors at the API edge -------------------------------
+namespace {
+
+struct TcConvPlan {
+  nsc::PlaneConv c;
+  int Lout, Ly, Cy;
+  int64_t in_bytes, out_bytes, res_bytes, w_bytes;
+};
+
+int make_tc_conv_plan(int64_t B, int Lin, int Cin, int Cout, int k, int dil, int stride, int act, int res_mode, int post_act,
+                      int shuffle, int precision, TcConvPlan* pl) {
+  using namespace nsc;
+  NSC_CHECK_ARG(precision == 1 || precision == 2, "nsc_conv1d_tc: precision must be 1 (fp16 hi/lo) or 2 (fp16)");
+  NSC_CHECK_ARG(Lin > 0 && Cin > 0 && Cout > 0 && k > 0 && dil > 0 && (stride == 1 || stride == 2) && shuffle >= 1, "nsc_conv1d_tc: bad shape");
+  PlaneConv& c = pl->c;
+  int padL;
+  same_padding(Lin, k, dil, stride, &pl->Lout, &padL);
+  c.kind = Cin == 1 ? PK_GEN : (((Cout == 20 && k == 9) || (Cout == 1 && k == 55)) && res_mode == RES_NONE && stride == 1 && shuffle == 1) ? PK_T : PK_X;
+  c.Lin = Lin; c.Cin = Cin; c.Cout = Cout; c.K = k; c.dil = dil; c.stride = stride;
+  c.act = act; c.post_act = post_act; c.res_mode = res_mode; c.shuffle = shuffle;
+  c.planes = precision == 1 ? 2 : 1;
+  c.B = B;
+  pl->Ly = pl->Lout * shuffle;
+  pl->Cy = Cout / shuffle;
+  if (Cin > 1) c.in = make_plane_tensor(nullptr, Lin, Cin, c.planes, stride == 2);
+  if (Cout > 1) c.out = make_plane_tensor(nullptr, pl->Ly, pl->Cy, c.planes, 0);
+  if (res_mode == RES_ADD) c.res = make_plane_tensor(nullptr, pl->Lout, Cout, c.planes, 0);
+  const float dummy = 0.f;
+  if (Cin == 1) c.xvec = &dummy;
+  if (res_mode == RES_ADD_BCAST) c.resvec = &dummy;
+  NSC_CHECK_ARG(plane_conv_supported(c), "nsc_conv1d_tc: shape not covered by the tensor engine (k%d d%d s%d %d->%d, L %d)", k, dil, stride, Cin, Cout, Lin);
+  pl->in_bytes = Cin > 1 ? align_up(B * c.in.frame_bytes, 1024) : 0;
+  pl->out_bytes = Cout > 1 ? align_up(B * c.out.frame_bytes, 1024) : 0;
+  pl->res_bytes = res_mode == RES_ADD ? align_up(B * c.res.frame_bytes, 1024) : 0;
+  pl->w_bytes = align_up(plane_wpack_bytes(c), 1024);
+  return NSC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t nsc_conv1d_tc_workspace_bytes(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation,
+                                      int32_t stride, int32_t res_mode, int32_t shuffle, int32_t precision) {
+  TcConvPlan pl;
+  if (make_tc_conv_plan(B < 1 ? 1 : B, Lin, Cin, Cout, k, dilation, stride, 0, res_mode, 0, shuffle, precision, &pl) != NSC_OK) return -1;
+  return 1024 + pl.in_bytes + pl.out_bytes + pl.res_bytes + pl.w_bytes;
+}
+
+int nsc_conv1d_tc(const float* x, const float* w, const float* b, const float* res, float* y, int64_t B, int32_t Lin,
+                  int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation,
+                  int32_t res_mode, int32_t post_activation, int32_t shuffle, int32_t precision, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  using namespace nsc;
+  if (B == 0) return NSC_OK;
+  NSC_CHECK_ARG(x && w && y && workspace, "nsc_conv1d_tc: null pointer");
+  NSC_CHECK_ARG(res_mode == RES_NONE || res != nullptr, "nsc_conv1d_tc: residual mode %d without a residual", res_mode);
+  TcConvPlan pl;
+  NSC_TRY(make_tc_conv_plan(B, Lin, Cin, Cout, k, dilation, stride, activation, res_mode, post_activation, shuffle, precision, &pl));
+  const int64_t need = 1024 + pl.in_bytes + pl.out_bytes + pl.res_bytes + pl.w_bytes;
+  if (workspace_bytes < need) {
+    set_error("nsc_conv1d_tc: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    return NSC_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  PlaneConv& c = pl.c;
+  NSC_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)(pl.in_bytes + pl.out_bytes + pl.res_bytes), st));   // the images' zero rows
+  c.in.base = p; p += pl.in_bytes;
+  c.out.base = p; p += pl.out_bytes;
+  c.res.base = p; p += pl.res_bytes;
+  c.wpack = p;
+  c.w = w; c.bias = b;
+  c.xvec = Cin == 1 ? x : nullptr;
+  c.resvec = res_mode == RES_ADD_BCAST ? res : nullptr;
+  c.yvec = Cout == 1 ? y : nullptr;
+  if (Cin > 1) NSC_TRY(plane_from_f32(x, 1, B, Lin, Cin, c.in, st));
+  if (res_mode == RES_ADD) NSC_TRY(plane_from_f32(res, 1, B, pl.Lout, Cout, c.res, st));
+  NSC_TRY(plane_pack_weights(c, st));
+  NSC_TRY(plane_launch(c, st));
+  if (Cout > 1) NSC_TRY(plane_to_f32(c.out, y, 1, B, pl.Ly, pl.Cy, st));
+  return NSC_OK;
+}
+
+}  // extern "C"

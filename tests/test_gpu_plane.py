@@ -1,0 +1,110 @@
+"""Plane engine (tcgen05 conv layers on fp16 plane images, nsc_b200/csrc/plane_conv.cu) against the CPU oracle, layer by
+layer and through the C ABI (nsc_conv1d_tc), on every layer shape the codec uses.
+
+precision 1 (fp16 hi/lo split, 3 MMAs) must meet the fp32 bar; precision 2 (plain fp16) is checked against a looser,
+stated bound."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_nn
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+ACTS = {None: 0, 'tanh': 1, 'lrelu': 2}
+
+
+def _oracle(x, w, b, dil, stride, act, res, res_mode, post_act, shuffle):
+    y = ref_nn.conv1d_explicit(torch.from_numpy(x), w, b, dil, stride, None)
+    y = y.numpy().astype(np.float64)
+    f = {None: lambda v: v, 'tanh': np.tanh, 'lrelu': lambda v: np.where(v > 0, v, 0.2 * v)}
+    y = f[act](y)
+    if res_mode == 1:
+        y = y + res
+    elif res_mode == 2:
+        y = y + res[:, :, None]
+    y = f[post_act](y)
+    if shuffle > 1:
+        B, L, C = y.shape
+        y = y.reshape(B, L, C // shuffle, shuffle).transpose(0, 1, 3, 2).reshape(B, L * shuffle, C // shuffle)
+    return y
+
+
+def _run(B, Lin, Cin, Cout, k, dil=1, stride=1, act=None, res_mode=0, post_act=None, shuffle=1, precision=1, seed=0):
+    from nsc_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(seed)
+    x = rng.randn(B, Lin, Cin).astype(np.float32)
+    lim = np.sqrt(6.0 / (k * Cin + k * Cout))
+    w = rng.uniform(-lim, lim, (k, Cin, Cout)).astype(np.float32)
+    b = (0.1 * rng.randn(Cout)).astype(np.float32)
+    Lout = (Lin + stride - 1) // stride
+    res = None
+    if res_mode == 1:
+        res = rng.randn(B, Lout, Cout).astype(np.float32)
+    elif res_mode == 2:
+        res = rng.randn(B, Lout).astype(np.float32)
+    want = _oracle(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), dil, stride, act,
+                   None if res is None else res.astype(np.float64), res_mode, post_act, shuffle)
+    xt, wt, bt = (torch.from_numpy(a).to(DEV) for a in (x, w, b))
+    rt = None if res is None else torch.from_numpy(res).to(DEV)
+    y = torch.full((B, Lout * shuffle, Cout // shuffle), float('nan'), device=DEV)
+    ws_bytes = lib.nsc_conv1d_tc_workspace_bytes(B, Lin, Cin, Cout, k, dil, stride, res_mode, shuffle, precision)
+    assert ws_bytes > 0, _lib.last_error()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    rc = lib.nsc_conv1d_tc(_lib.ptr(xt), _lib.ptr(wt), _lib.ptr(bt), _lib.ptr(rt), _lib.ptr(y), B, Lin, Cin, Cout, k, dil,
+                           stride, ACTS[act], res_mode, ACTS[post_act], shuffle, precision, _lib.ptr(ws), ws_bytes,
+                           _lib.stream_ptr())
+    _lib.check(rc, 'nsc_conv1d_tc')
+    torch.cuda.synchronize()
+    got = y.cpu().numpy()
+    assert np.isfinite(got).all()
+    return rel_err(got, want.reshape(got.shape))
+
+
+# every conv shape of the '9 9 100 20 1 2' / stride-2 bottleneck codec
+T_LAYERS = [
+    dict(Lin=512, Cin=100, Cout=20, k=9, act='lrelu'),             # block conv 1 @512
+    dict(Lin=256, Cin=100, Cout=20, k=9, act='lrelu'),             # block conv 1 @256
+    dict(Lin=512, Cin=50, Cout=20, k=9, act='lrelu'),              # decoder block conv 1 on 50 channels
+    dict(Lin=512, Cin=20, Cout=20, k=9, dil=1, act='lrelu'),       # block conv 2, dilation 1
+    dict(Lin=512, Cin=20, Cout=20, k=9, dil=2, act='lrelu'),       # block conv 2, dilation 2
+    dict(Lin=256, Cin=20, Cout=20, k=9, dil=2, act='lrelu'),
+    dict(Lin=256, Cin=100, Cout=1, k=55, act='tanh'),              # code head
+    dict(Lin=512, Cin=50, Cout=1, k=55, act=None),                 # output head
+]
+X_LAYERS = [
+    dict(Lin=512, Cin=20, Cout=100, k=9, res_mode=1, post_act='lrelu'),    # block conv 3 + residual + lrelu
+    dict(Lin=256, Cin=20, Cout=100, k=9, res_mode=1, post_act=None),       # last block of a stack: flat
+    dict(Lin=256, Cin=20, Cout=100, k=9, res_mode=2, post_act='lrelu'),    # decoder block 1: broadcast residual
+    dict(Lin=512, Cin=20, Cout=50, k=9, res_mode=1, post_act='lrelu'),
+    dict(Lin=512, Cin=100, Cout=100, k=9, stride=2, act='lrelu'),          # down-sampling conv
+    dict(Lin=256, Cin=100, Cout=100, k=9, act='lrelu', shuffle=2),         # up-sampling conv + sub-pixel shuffle
+    dict(Lin=512, Cin=1, Cout=100, k=55, act='lrelu'),                     # stem (Toeplitz)
+    dict(Lin=256, Cin=1, Cout=20, k=9, act='lrelu'),                       # decoder block 1 conv 1 (Toeplitz)
+]
+
+
+@pytest.mark.parametrize('layer', T_LAYERS, ids=lambda d: 'k%d_d%d_%dto%d_L%d' % (d['k'], d.get('dil', 1), d['Cin'], d['Cout'], d['Lin']))
+@pytest.mark.parametrize('precision', [1, 2])
+def test_taps_in_n_layers(layer, precision):
+    # 5 frames on 148 CTAs: one frame per CTA; 301 frames: CTAs walk several frames (spill slots recycle)
+    for B in (5, 301):
+        e = _run(B=B, precision=precision, seed=B, **layer)
+        assert e < (2e-5 if precision == 1 else 4e-3), (B, e)
+
+
+@pytest.mark.parametrize('layer', X_LAYERS, ids=lambda d: 'k%d_s%d_%dto%d_L%d_r%d_sh%d' % (d['k'], d.get('stride', 1), d['Cin'], d['Cout'], d['Lin'], d.get('res_mode', 0), d.get('shuffle', 1)))
+@pytest.mark.parametrize('precision', [1, 2])
+def test_tap_shift_layers(layer, precision):
+    for B in (3, 301):
+        e = _run(B=B, precision=precision, seed=B, **layer)
+        assert e < (2e-5 if precision == 1 else 4e-3), (B, e)
+
+
+def test_unsupported_shape_fails_loudly():
+    from nsc_b200 import _lib
+    lib = _lib.load()
+    assert lib.nsc_conv1d_tc_workspace_bytes(4, 500, 100, 20, 9, 1, 1, 0, 1, 1) < 0     # 500 is not a multiple of 128
+    assert 'tensor engine' in _lib.last_error()
