@@ -3,6 +3,7 @@
 // kernel launches.  The topology is written ONCE (struct Walker): a dry walk enumerates the conv layers in the
 // order TensorFlow would create their variables -- which defines the flat parameter image -- and the live walk
 // issues the launches.  Frames are processed in chunks so the activation workspace stays bounded.
+#include "plane_codec.cuh"
 #include "walker.cuh"
 
 namespace nsc {
@@ -74,10 +75,100 @@ int run_codec_chunk(const nsc_codec_cfg& cfg, const CodecLayout& lay, const floa
   return NSC_OK;
 }
 
+
+// ---- plane path (plane_codec.cuh): per-call state of a codec or a cascade of codecs -------------------------------
+struct PlaneCascade {
+  std::vector<PlaneCodecPlan> plans;
+  std::vector<int> region;      // activation region used by codec i (codecs with the same image geometry share one)
+  int n_regions = 0;
+  int64_t region_bytes = 0;     // bytes of one activation region
+  float* fcode = nullptr;       // (Bc, Lc) scratch, largest Lc
+  float* code = nullptr;
+
+  static bool supported(const nsc_codec_cfg* cfgs, int n) {
+    for (int i = 0; i < n; ++i)
+      if (!plane_codec_supported(cfgs[i])) return false;
+    return n >= 1;
+  }
+  static void layout(const nsc_codec_cfg* cfgs, int n, std::vector<int>* region, int* n_regions) {
+    region->assign(n, 0);
+    *n_regions = 0;
+    for (int i = 0; i < n; ++i) {
+      int r = -1;
+      for (int j = 0; j < i; ++j)
+        if (cfgs[j].wide == cfgs[i].wide && cfgs[j].precision == cfgs[i].precision) { r = (*region)[j]; break; }
+      (*region)[i] = r >= 0 ? r : (*n_regions)++;
+    }
+  }
+  static int64_t bytes(const nsc_codec_cfg* cfgs, int n, int64_t Bc) {
+    std::vector<int> region;
+    int nr = 0;
+    layout(cfgs, n, &region, &nr);
+    int64_t act = 0, w = 0;
+    for (int i = 0; i < n; ++i) {
+      const PlaneCodecPlan pl = make_plane_plan(cfgs[i]);
+      const int64_t a = plane_codec_act_bytes(pl, Bc);
+      if (a > act) act = a;
+      w += align_up(pl.wpack_bytes, 1024);
+    }
+    return act * nr + w + 2 * align_up(Bc * (kFrameLen / 2) * (int64_t)sizeof(float), 1024) + 2048;
+  }
+  // carves `ws`, clears the images' zero rows, binds every layer and packs all weights (once per call)
+  int setup(const nsc_codec_cfg* cfgs, const CodecLayout* lays, const float* const* params, int n, int64_t Bc, void* ws,
+            int64_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < bytes(cfgs, n, Bc)) {
+      set_error("codec (plane path): workspace %lld < %lld bytes", (long long)ws_bytes, (long long)bytes(cfgs, n, Bc));
+      return NSC_E_WORKSPACE;
+    }
+    layout(cfgs, n, &region, &n_regions);
+    plans.clear();
+    region_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+      plans.push_back(make_plane_plan(cfgs[i]));
+      if (plans[i].wpack_bytes < 0) { set_error("codec (plane path): a layer is not covered by the plane engine"); return NSC_E_INVALID; }
+      const int64_t a = plane_codec_act_bytes(plans[i], Bc);
+      if (a > region_bytes) region_bytes = a;
+    }
+    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+    uint8_t* act0 = p;
+    p += region_bytes * n_regions;
+    NSC_CUDA_OK(cudaMemsetAsync(act0, 0, (size_t)(region_bytes * n_regions), st));
+    for (int i = 0; i < n; ++i) {
+      plane_bind(plans[i], lays[i], params[i], act0 + region_bytes * region[i], Bc, p);
+      p += align_up(plans[i].wpack_bytes, 1024);
+      NSC_TRY(plane_codec_pack(plans[i], st));
+    }
+    fcode = reinterpret_cast<float*>(p);
+    p += align_up(Bc * (kFrameLen / 2) * (int64_t)sizeof(float), 1024);
+    code = reinterpret_cast<float*>(p);
+    return NSC_OK;
+  }
+};
+
+// plane-path twin of run_codec_chunk
+int run_codec_chunk_plane(PlaneCascade& pcs, int i, const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* params,
+                          const float* x, int64_t nb, float iq, int use_soft, float* fcode, uint8_t* idx, float* code,
+                          float* out, float* soft, float* hist, float* qloss, int which, cudaStream_t st) {
+  float* fc = fcode ? fcode : pcs.fcode;
+  float* cd = code ? code : pcs.code;
+  if (which & 1) {
+    NSC_TRY(plane_run_encoder(pcs.plans[i], x, nb, fc, st));
+    const float* alpha = params + lay.conv_floats;
+    NSC_TRY(launch_quantize(fc, nb, lay.code_len, alpha + 1, cfg.num_bins, alpha, iq, use_soft, cd, idx, soft, hist, qloss, st));
+  }
+  if (which & 2) NSC_TRY(plane_run_decoder(pcs.plans[i], cd, nb, out, st));
+  return NSC_OK;
+}
+
 }  // namespace
 }  // namespace nsc
 
 using nsc::kFrameLen;
+
+// frames per internal pass: the plane path wants a whole number of frames per SM
+static int64_t chunk_for(const nsc_codec_cfg* cfgs, int n) {
+  return nsc::PlaneCascade::supported(cfgs, n) ? nsc::plane_chunk_frames() : kChunkFrames;
+}
 
 extern "C" {
 
@@ -105,7 +196,9 @@ int32_t nsc_codec_layer_info(const nsc_codec_cfg* cfg, int32_t i, int32_t* k, in
 
 int64_t nsc_codec_workspace_bytes(const nsc_codec_cfg* cfg, int64_t B) {
   if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
-  const int64_t Bc = B < kChunkFrames ? (B < 1 ? 1 : B) : kChunkFrames;
+  const int64_t chunk = chunk_for(cfg, 1);
+  const int64_t Bc = B < chunk ? (B < 1 ? 1 : B) : chunk;
+  if (nsc::PlaneCascade::supported(cfg, 1)) return nsc::PlaneCascade::bytes(cfg, 1, Bc);
   return nsc::codec_ws_bytes(*cfg, Bc);
 }
 
@@ -116,14 +209,31 @@ static int codec_run(const nsc_codec_cfg* cfg, const float* params, const float*
   NSC_CHECK_ARG(params != nullptr && workspace != nullptr, "codec: null params/workspace");
   NSC_CHECK_ARG(B >= 0, "codec: negative batch");
   if (B == 0) return NSC_OK;
-  const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
+  const int64_t chunk = chunk_for(cfg, 1);
+  const int64_t Bc = B < chunk ? B : chunk;
+  const nsc::CodecLayout lay = nsc::make_layout(*cfg);
+  const int Lc = lay.code_len, n = cfg->num_bins;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nsc::PlaneCascade::supported(cfg, 1)) {
+    nsc::PlaneCascade pcs;
+    NSC_TRY(pcs.setup(cfg, &lay, &params, 1, Bc, workspace, workspace_bytes, st));
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+      const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
+      if (which == 2)
+        NSC_TRY(nsc::run_codec_chunk_plane(pcs, 0, *cfg, lay, params, nullptr, nb, iq, use_soft, nullptr, nullptr,
+                                           const_cast<float*>(code_in + b0 * Lc), out + b0 * kFrameLen, nullptr, nullptr, nullptr, 2, st));
+      else
+        NSC_TRY(nsc::run_codec_chunk_plane(pcs, 0, *cfg, lay, params, x + b0 * kFrameLen, nb, iq, use_soft,
+                                           fcode ? fcode + b0 * Lc : nullptr, idx ? idx + b0 * Lc : nullptr,
+                                           code ? code + b0 * Lc : nullptr, out ? out + b0 * kFrameLen : nullptr,
+                                           soft ? soft + b0 * Lc * n : nullptr, hist, qloss ? qloss + b0 : nullptr, which, st));
+    }
+    return NSC_OK;
+  }
   if (workspace_bytes < nsc::codec_ws_bytes(*cfg, Bc)) {
     nsc::set_error("codec: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)nsc::codec_ws_bytes(*cfg, Bc));
     return NSC_E_WORKSPACE;
   }
-  const nsc::CodecLayout lay = nsc::make_layout(*cfg);
-  const int Lc = lay.code_len, n = cfg->num_bins;
-  cudaStream_t st = (cudaStream_t)stream;
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
     nsc::Carver cv(workspace, workspace_bytes);
@@ -172,6 +282,8 @@ int nsc_codec_decode(const nsc_codec_cfg* cfg, const float* params, const float*
 
 // ---- cascade -------------------------------------------------------------------------------------
 static int64_t cascade_ws_bytes(const nsc_codec_cfg* cfgs, int32_t n, int64_t Bc) {
+  if (nsc::PlaneCascade::supported(cfgs, n))
+    return nsc::PlaneCascade::bytes(cfgs, n, Bc) + 2 * (Bc * kFrameLen * (int64_t)sizeof(float) + 256);
   int64_t worst = 0;
   for (int i = 0; i < n; ++i) {
     const int64_t b = nsc::codec_ws_bytes(cfgs[i], Bc);
@@ -185,7 +297,8 @@ int64_t nsc_cascade_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs,
   if (cfgs == nullptr || n_codecs < 1 || n_codecs > NSC_MAX_CODECS) return -1;
   for (int i = 0; i < n_codecs; ++i)
     if (nsc::validate_cfg(&cfgs[i]) != NSC_OK) return -1;
-  const int64_t Bc = B < kChunkFrames ? (B < 1 ? 1 : B) : kChunkFrames;
+  const int64_t chunk = chunk_for(cfgs, n_codecs);
+  const int64_t Bc = B < chunk ? (B < 1 ? 1 : B) : chunk;
   return cascade_ws_bytes(cfgs, n_codecs, Bc);
 }
 
@@ -194,13 +307,14 @@ static int cascade_chunk(const nsc_codec_cfg* cfgs, const nsc::CodecLayout* lays
                          const float* const* params, const float* x, int64_t b0, int64_t nb, int64_t Bc,
                          float res_scalar, int lpc_variant, float iq, int use_soft, uint8_t* const* idx,
                          float* const* hist, float* const* qloss, float* const* outs, float* decoded,
-                         void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                         void* workspace, int64_t workspace_bytes, cudaStream_t st, nsc::PlaneCascade* pcs = nullptr) {
   const int64_t nfl = nb * kFrameLen;
   for (int i = 0; i < n; ++i) {
     nsc::Carver cv(workspace, workspace_bytes);
     float* cin = cv.take(Bc * kFrameLen);
     float* cout = cv.take(Bc * kFrameLen);
-    nsc::CodecBuffers buf = nsc::carve_codec(cv, cfgs[i], Bc);
+    nsc::CodecBuffers buf{};
+    if (!pcs) buf = nsc::carve_codec(cv, cfgs[i], Bc);
     const float* xin = x;
     if (i == 0) {
       if (lpc_variant && res_scalar != 1.0f) {       // res_x * res_scalar, cmrl.py:810
@@ -212,9 +326,14 @@ static int cascade_chunk(const nsc_codec_cfg* cfgs, const nsc::CodecLayout* lays
       xin = cin;
     }
     const int Lc = lays[i].code_len;
-    NSC_TRY(nsc::run_codec_chunk(cfgs[i], lays[i], params[i], buf, xin, nb, iq, use_soft, nullptr,
-                                 (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, cout, nullptr,
-                                 (hist && hist[i]) ? hist[i] : nullptr, (qloss && qloss[i]) ? qloss[i] + b0 : nullptr, 3, st));
+    if (pcs)
+      NSC_TRY(nsc::run_codec_chunk_plane(*pcs, i, cfgs[i], lays[i], params[i], xin, nb, iq, use_soft, nullptr,
+                                         (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, cout, nullptr,
+                                         (hist && hist[i]) ? hist[i] : nullptr, (qloss && qloss[i]) ? qloss[i] + b0 : nullptr, 3, st));
+    else
+      NSC_TRY(nsc::run_codec_chunk(cfgs[i], lays[i], params[i], buf, xin, nb, iq, use_soft, nullptr,
+                                   (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, cout, nullptr,
+                                   (hist && hist[i]) ? hist[i] : nullptr, (qloss && qloss[i]) ? qloss[i] + b0 : nullptr, 3, st));
     const bool divide = (i > 0) || lpc_variant;       // codec 0 of the plain cascade is not divided (cmrl.py:522-528)
     const float d = divide ? res_scalar : 1.0f;
     if (outs && outs[i]) NSC_TRY(nsc::launch_div(outs[i] + b0 * kFrameLen, cout, d, nfl, st));
@@ -242,7 +361,8 @@ int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float
                         void* workspace, int64_t workspace_bytes, void* stream) {
   if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_TRY(check_cascade_args(cfgs, n_codecs, params_ptrs_host, x, decoded, workspace, res_scalar));
-  const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
+  const int64_t chunk = chunk_for(cfgs, n_codecs);
+  const int64_t Bc = B < chunk ? B : chunk;
   if (workspace_bytes < cascade_ws_bytes(cfgs, n_codecs, Bc)) {
     nsc::set_error("cascade: workspace %lld < %lld bytes", (long long)workspace_bytes,
                    (long long)cascade_ws_bytes(cfgs, n_codecs, Bc));
@@ -250,11 +370,19 @@ int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float
   }
   std::vector<nsc::CodecLayout> lays;
   for (int i = 0; i < n_codecs; ++i) lays.push_back(nsc::make_layout(cfgs[i]));
+  nsc::PlaneCascade pcs;
+  const bool plane = nsc::PlaneCascade::supported(cfgs, n_codecs);
+  if (plane) {
+    const int64_t head = 2 * nsc::align_up(Bc * kFrameLen * (int64_t)sizeof(float), 256);   // cascade_chunk's codec input / output
+    NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head,
+                      (cudaStream_t)stream));
+  }
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
     NSC_TRY(cascade_chunk(cfgs, lays.data(), n_codecs, params_ptrs_host, x + b0 * kFrameLen, b0, nb, Bc, res_scalar,
                           lpc_variant, is_quan_on, use_soft, idx_ptrs_host, hist_ptrs_host, qloss_ptrs_host,
-                          outs_ptrs_host, decoded + b0 * kFrameLen, workspace, workspace_bytes, (cudaStream_t)stream));
+                          outs_ptrs_host, decoded + b0 * kFrameLen, workspace, workspace_bytes, (cudaStream_t)stream,
+                          plane ? &pcs : nullptr));
   }
   return NSC_OK;
 }
@@ -268,7 +396,8 @@ static int64_t cq_extra_bytes(int64_t Bc) {
 int64_t nsc_cq_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B) {
   const int64_t c = nsc_cascade_workspace_bytes(cfgs, n_codecs, B);
   if (c < 0) return c;
-  const int64_t Bc = B < kChunkFrames ? (B < 1 ? 1 : B) : kChunkFrames;
+  const int64_t chunk = chunk_for(cfgs, n_codecs);
+  const int64_t Bc = B < chunk ? (B < 1 ? 1 : B) : chunk;
   return c + cq_extra_bytes(Bc);
 }
 
@@ -282,7 +411,8 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
   NSC_TRY(check_cascade_args(cfgs, n_codecs, params_ptrs_host, x, decoded, workspace, res_scalar));
   NSC_CHECK_ARG(lsf_params != nullptr && lsf != nullptr, "nsc_cq_forward: null LSF input");
   NSC_CHECK_ARG(n_lsf_bins >= 1 && n_lsf_bins <= 256, "nsc_cq_forward: n_lsf_bins=%d", n_lsf_bins);
-  const int64_t Bc = B < kChunkFrames ? B : kChunkFrames;
+  const int64_t chunk = chunk_for(cfgs, n_codecs);
+  const int64_t Bc = B < chunk ? B : chunk;
   const int64_t need = cascade_ws_bytes(cfgs, n_codecs, Bc) + cq_extra_bytes(Bc);
   if (workspace_bytes < need) {
     nsc::set_error("nsc_cq_forward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
@@ -292,6 +422,14 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
   std::vector<nsc::CodecLayout> lays;
   for (int i = 0; i < n_codecs; ++i) lays.push_back(nsc::make_layout(cfgs[i]));
   const int P = NSC_LPC_ORDER;
+  nsc::PlaneCascade pcs;
+  const bool plane = nsc::PlaneCascade::supported(cfgs, n_codecs);
+  if (plane) {
+    nsc::Carver cv(workspace, workspace_bytes);
+    cv.take(Bc * P); cv.take(Bc * (P + 1)); cv.take(Bc * kFrameLen);
+    const int64_t head = cv.used + 2 * nsc::align_up(Bc * kFrameLen * (int64_t)sizeof(float), 256);
+    NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head, st));
+  }
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
     nsc::Carver cv(workspace, workspace_bytes);
@@ -310,7 +448,7 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
     NSC_TRY(nsc_lpc_residual(x + b0 * kFrameLen, poly_c, nb, res_c, stream));               // cmrl.py:796
     NSC_TRY(cascade_chunk(cfgs, lays.data(), n_codecs, params_ptrs_host, res_c, b0, nb, Bc, res_scalar, 1, is_quan_on,
                           use_soft, idx_ptrs_host, hist_ptrs_host, qloss_ptrs_host, nullptr, decoded + b0 * kFrameLen,
-                          rest, rest_bytes, st));
+                          rest, rest_bytes, st, plane ? &pcs : nullptr));
     if (synthesized)                                                                         // cmrl.py:843
       NSC_TRY(nsc_lpc_synth(poly_c, decoded + b0 * kFrameLen, nb, synthesized + b0 * kFrameLen, stream));
   }

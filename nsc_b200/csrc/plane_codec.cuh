@@ -1,0 +1,212 @@
+// The codec topology (neural_speech_coding_module.py:152-260) as a program of plane-engine layers (plane.cuh): every
+// activation between the 1-channel input and the 1-channel code / output stays an fp16 plane image in HBM, written by
+// one layer's epilogue in exactly the form the next layer's bulk copies stage.  Host side only; included by codec.cu.
+//
+// Covered: resnet_type 'bottleneck', one stride-2 stage, narrow = 20, k = 9, dilations <= 2 (the BASELINE.json
+// configurations).  Anything else keeps the layer-by-layer engines (walker.cuh).
+#pragma once
+#include <stdlib.h>
+
+#include <vector>
+
+#include "plane.cuh"
+#include "walker.cuh"
+
+namespace nsc {
+namespace {
+
+bool plane_codec_supported(const nsc_codec_cfg& c) {
+  static const bool off = [] { const char* e = getenv("NSC_PLANE"); return e && e[0] == '0'; }();
+  if (off) return false;
+  if (c.precision != 1 && c.precision != 2) return false;
+  if (c.resnet_type != 0 || c.n_strides != 1 || c.strides[0] != 2) return false;
+  if (c.narrow != 20 || c.k_plain != 9 || c.k_dilated != 9) return false;
+  if (c.wide < 66 || c.wide > 128 || (c.wide & 1)) return false;   // wide and wide/2 both use unpacked (>32 channel) images
+  for (int i = 0; i < c.n_blocks; ++i)
+    if (c.dilations[i] < 1 || c.dilations[i] > 2) return false;
+  return true;
+}
+
+// frames per pass of the plane path: a whole number of frames per SM for every kernel
+int64_t plane_chunk_frames() {
+  static const int64_t v = [] {
+    const char* e = getenv("NSC_PLANE_CHUNK");
+    const long long n = e ? atoll(e) : 0;
+    return (int64_t)(n >= 1 && n <= 65536 ? n : 14LL * sm_count());
+  }();
+  return v;
+}
+
+enum PBuf { PB_W0 = 0, PB_W1, PB_WD, PB_H0, PB_H1, PB_N0, PB_N1, PB_M0, PB_M1, PB_C0, PB_C1, PB_COUNT };
+
+struct PlaneCodecPlan {
+  int planes = 2;
+  int Lc = 0;
+  PlaneTensor buf[PB_COUNT];             // bases relative to the activation region (filled by bind)
+  int64_t buf_off[PB_COUNT];
+  int64_t act_bytes_per_frame = 0;
+  std::vector<PlaneConv> enc, dec;
+  std::vector<int> enc_layer, dec_layer;  // index into the codec's layer table (parameter offsets)
+  std::vector<int64_t> w_off;             // packed-weight offset of every layer (enc then dec)
+  int64_t wpack_bytes = 0;
+};
+
+// Lays the codec out as plane layers.  Tensors carry offsets (base = nullptr + offset) until bound to a workspace.
+PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
+  PlaneCodecPlan pl;
+  pl.planes = c.precision == 1 ? 2 : 1;
+  const int P = pl.planes, L = kFrameLen, H = kFrameLen / 2, W = c.wide, Nn = c.narrow, Wd = c.wide / 2;
+  pl.Lc = H;
+  pl.buf[PB_W0] = make_plane_tensor(nullptr, L, W, P, 0);
+  pl.buf[PB_W1] = pl.buf[PB_W0];
+  pl.buf[PB_WD] = make_plane_tensor(nullptr, L, W, P, 1);
+  pl.buf[PB_H0] = make_plane_tensor(nullptr, H, W, P, 0);
+  pl.buf[PB_H1] = pl.buf[PB_H0];
+  pl.buf[PB_N0] = make_plane_tensor(nullptr, L, Nn, P, 0);
+  pl.buf[PB_N1] = pl.buf[PB_N0];
+  pl.buf[PB_M0] = make_plane_tensor(nullptr, H, Nn, P, 0);
+  pl.buf[PB_M1] = pl.buf[PB_M0];
+  pl.buf[PB_C0] = make_plane_tensor(nullptr, L, Wd, P, 0);
+  pl.buf[PB_C1] = pl.buf[PB_C0];
+  int64_t off = 0;
+  for (int i = 0; i < PB_COUNT; ++i) { pl.buf_off[i] = off; off += pl.buf[i].frame_bytes; }
+  pl.act_bytes_per_frame = off;
+
+  int layer = 0;   // creation-order layer index (same walk as Walker::encoder / decoder)
+  auto add = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int kind, int Lin, int Cin, int Cout, int K, int dil, int stride,
+                 int act, int in, int out, int res, int res_mode, int post, int shuffle) {
+    PlaneConv pc;
+    pc.kind = kind; pc.Lin = Lin; pc.Cin = Cin; pc.Cout = Cout; pc.K = K; pc.dil = dil; pc.stride = stride;
+    pc.act = act; pc.post_act = post; pc.res_mode = res_mode; pc.shuffle = shuffle; pc.planes = P;
+    if (in >= 0) pc.in = pl.buf[in];
+    if (out >= 0) pc.out = pl.buf[out];
+    if (res >= 0) pc.res = pl.buf[res];
+    // buffer ids ride in the (still null) base pointers until bind()
+    pc.in.base = reinterpret_cast<uint8_t*>((intptr_t)(in + 1));
+    pc.out.base = reinterpret_cast<uint8_t*>((intptr_t)(out + 1));
+    pc.res.base = reinterpret_cast<uint8_t*>((intptr_t)(res + 1));
+    v.push_back(pc);
+    vl.push_back(layer++);
+  };
+  // one stack of bottleneck blocks (nscm.py:183-217) on `cur`; returns the buffer that holds the result
+  auto stack = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int Ls, int Cw, int cur, int b0, int b1, int n0, int n1, int last_out,
+                   bool vec_in) {
+    for (int i = 0; i < c.n_blocks; ++i) {
+      const bool flat = i == c.n_blocks - 1;
+      int out = (cur == b0) ? b1 : b0;
+      if (flat && last_out >= 0) out = last_out;
+      const int post = flat ? NSC_ACT_NONE : NSC_ACT_LRELU;
+      if (vec_in && i == 0) {
+        add(v, vl, PK_GEN, Ls, 1, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, -1, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, PK_T, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, -1, RES_ADD_BCAST, post, 1);
+      } else {
+        add(v, vl, PK_T, Ls, Cw, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, cur, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, PK_T, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, cur, RES_ADD, post, 1);
+      }
+      cur = out;
+    }
+    return cur;
+  };
+  // encoder (nscm.py:219-237)
+  add(pl.enc, pl.enc_layer, PK_GEN, L, 1, W, 55, 1, 1, NSC_ACT_LRELU, -1, PB_W0, -1, RES_NONE, NSC_ACT_NONE, 1);
+  int cur = stack(pl.enc, pl.enc_layer, L, W, PB_W0, PB_W0, PB_W1, PB_N0, PB_N1, PB_WD, false);
+  add(pl.enc, pl.enc_layer, PK_X, L, W, W, 9, 1, 2, NSC_ACT_LRELU, cur, PB_H0, -1, RES_NONE, NSC_ACT_NONE, 1);
+  cur = stack(pl.enc, pl.enc_layer, H, W, PB_H0, PB_H0, PB_H1, PB_M0, PB_M1, -1, false);
+  add(pl.enc, pl.enc_layer, PK_T, H, W, 1, 55, 1, 1, NSC_ACT_TANH, cur, -1, -1, RES_NONE, NSC_ACT_NONE, 1);
+  // decoder (nscm.py:239-260)
+  cur = stack(pl.dec, pl.dec_layer, H, W, PB_H1, PB_H0, PB_H1, PB_M0, PB_M1, -1, true);   // first block writes the buffer that is not `cur`
+  add(pl.dec, pl.dec_layer, PK_X, H, W, W, 9, 1, 1, NSC_ACT_LRELU, cur, PB_C0, -1, RES_NONE, NSC_ACT_NONE, 2);
+  cur = stack(pl.dec, pl.dec_layer, L, Wd, PB_C0, PB_C0, PB_C1, PB_N0, PB_N1, -1, false);
+  add(pl.dec, pl.dec_layer, PK_T, L, Wd, 1, 55, 1, 1, NSC_ACT_NONE, cur, -1, -1, RES_NONE, NSC_ACT_NONE, 1);
+
+  int64_t woff = 0;
+  auto size_w = [&](std::vector<PlaneConv>& v) {
+    for (auto& pc : v) {
+      PlaneConv t = pc;
+      t.in.base = t.out.base = t.res.base = nullptr;
+      const float dummy = 0.f;
+      if (t.Cin == 1) t.xvec = &dummy;
+      if (t.res_mode == RES_ADD_BCAST) t.resvec = &dummy;
+      pl.w_off.push_back(woff);
+      const int64_t b = plane_wpack_bytes(t);
+      woff += align_up(b < 0 ? 0 : b, 1024);
+      if (b < 0) pl.wpack_bytes = -1;
+    }
+  };
+  size_w(pl.enc);
+  size_w(pl.dec);
+  if (pl.wpack_bytes == 0) pl.wpack_bytes = woff;
+  return pl;
+}
+
+int64_t plane_codec_act_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
+  int64_t total = 0;
+  for (int i = 0; i < PB_COUNT; ++i) total += align_up(pl.buf[i].frame_bytes * Bc, 1024);
+  return total + 1024;
+}
+
+// Resolves the buffer ids to addresses inside `act` (sized for Bc frames), attaches parameters and packed weights.
+void plane_bind(PlaneCodecPlan& pl, const CodecLayout& lay, const float* params, void* act, int64_t Bc, void* wpack) {
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(act) + 1023) & ~(uintptr_t)1023);
+  uint8_t* addr[PB_COUNT];
+  for (int i = 0; i < PB_COUNT; ++i) { addr[i] = base; base += align_up(pl.buf[i].frame_bytes * Bc, 1024); }
+  size_t li = 0;
+  auto fix = [&](std::vector<PlaneConv>& v, std::vector<int>& vl) {
+    for (size_t i = 0; i < v.size(); ++i, ++li) {
+      PlaneConv& pc = v[i];
+      auto resolve = [&](PlaneTensor& t) {
+        const intptr_t id = reinterpret_cast<intptr_t>(t.base);   // buffer id + 1, or an already bound address
+        if (id >= 1 && id <= PB_COUNT) t.base = addr[id - 1];
+        else if (id == 0) t.base = nullptr;
+      };
+      resolve(pc.in); resolve(pc.out); resolve(pc.res);
+      const LayerInfo& info = lay.layers[vl[i]];
+      pc.w = params + info.off;
+      pc.bias = pc.w + (int64_t)info.k * info.cin * info.cout;
+      pc.wpack = static_cast<uint8_t*>(wpack) + pl.w_off[li];
+    }
+  };
+  fix(pl.enc, pl.enc_layer);
+  fix(pl.dec, pl.dec_layer);
+}
+
+int plane_codec_pack(PlaneCodecPlan& pl, cudaStream_t st) {
+  for (auto* v : {&pl.enc, &pl.dec})
+    for (auto& pc : *v) {
+      PlaneConv t = pc;
+      const float dummy = 0.f;
+      if (t.Cin == 1) t.xvec = &dummy;
+      if (t.res_mode == RES_ADD_BCAST) t.resvec = &dummy;
+      NSC_TRY(plane_pack_weights(t, st));
+    }
+  return NSC_OK;
+}
+
+// encoder: x (nb, 512) -> fcode (nb, Lc);  decoder: code (nb, Lc) -> out (nb, 512)
+int plane_run_encoder(PlaneCodecPlan& pl, const float* x, int64_t nb, float* fcode, cudaStream_t st) {
+  for (auto& pc : pl.enc) {
+    PlaneConv t = pc;
+    t.B = nb;
+    if (t.Cin == 1) t.xvec = x;
+    if (t.Cout == 1) t.yvec = fcode;
+    NSC_TRY(plane_launch(t, st));
+  }
+  return NSC_OK;
+}
+
+int plane_run_decoder(PlaneCodecPlan& pl, const float* code, int64_t nb, float* out, cudaStream_t st) {
+  for (auto& pc : pl.dec) {
+    PlaneConv t = pc;
+    t.B = nb;
+    if (t.Cin == 1) t.xvec = code;
+    if (t.res_mode == RES_ADD_BCAST) t.resvec = code;
+    if (t.Cout == 1) t.yvec = out;
+    NSC_TRY(plane_launch(t, st));
+  }
+  return NSC_OK;
+}
+
+}  // namespace
+}  // namespace nsc

@@ -76,6 +76,7 @@ __device__ __forceinline__ void pt_load8(const PlaneTensor& t, const uint8_t* im
 }
 
 __host__ __device__ inline int pt_chunks_per_row(const PlaneTensor& t) { return t.packed ? 4 : t.spp * 8; }
+inline double pt_payload_bytes(const PlaneTensor& t) { return (double)pt_n_slabs(t) * t.rows * 128.0 * ((t.packed && t.planes == 1) ? 0.5 : 1.0); }
 
 // ------------------------------------------------------------------------------------------------
 // fp32 <-> planes
@@ -902,7 +903,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     p.N = pl.N; p.n_wslab = pl.n_wslab; p.ksteps = pl.ksteps; p.L = c.Lin; p.dil = c.dil; p.act = c.act; p.na = pl.na; p.B = c.B;
     NSC_CHECK_ARG(c.Cout > 1 || c.yvec != nullptr, "plane engine: head without an output vector");
     snprintf(name, sizeof(name), "pT%d_k%dd%d_c%dto%d", c.planes, c.K, c.dil, c.Cin, c.Cout);
-    const double bytes = (double)c.B * (c.in.frame_bytes * (double)c.Lin / (c.Lin + 16) + (c.Cout > 1 ? 128.0 * c.Lin * (c.planes == 2 ? 1.0 : 0.5) : 4.0 * c.Lin));
+    // algorithmic bytes: every input and output plane image moved exactly once (zero rows excluded)
+    const double bytes = (double)c.B * (pt_payload_bytes(c.in) + (c.Cout > 1 ? pt_payload_bytes(c.out) : 4.0 * c.Lin));
     ProfScope prof(st, name, 2.0 * macs, bytes);
     const int64_t grid = c.B < sm_count() ? c.B : sm_count();
     if (c.Cout == 20) {
@@ -920,11 +922,10 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   const size_t smem = x_smem_bytes(p);
   NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
-  const double pl_bytes = c.planes == 2 ? 1.0 : 0.5;
-  double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : c.in.frame_bytes * 1.0);
-  bytes += (double)c.B * c.out.frame_bytes;
-  if (c.res_mode == RES_ADD) bytes += (double)c.B * c.res.frame_bytes;
-  (void)pl_bytes;
+  double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_payload_bytes(c.in));
+  bytes += (double)c.B * pt_payload_bytes(c.out);
+  if (c.res_mode == RES_ADD) bytes += (double)c.B * pt_payload_bytes(c.res);
+  if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
   ProfScope prof(st, name, 2.0 * macs, bytes);
   const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   plane_x_kernel<<<(unsigned)grid, kXThreads, smem, st>>>(p);
