@@ -170,6 +170,30 @@ __global__ void plane_pack_kernel(PackArgs a) {
 }
 
 // ================================================================================================
+// shared pieces of the two kernels
+// ================================================================================================
+// activation as a slope: leaky_relu(v) = max(v, 0.2 v), identity = max(v, 1.0 v); tanh takes the slow uniform branch
+__device__ __forceinline__ float act_slope_of(int act) { return act == NSC_ACT_LRELU ? kLeakySlope : 1.0f; }
+__device__ __forceinline__ float act_fast(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, act); }
+
+// K steps of one (A tile, B unit) pair from the issuing thread; descriptors advance 32 bytes (2 units of 16 B) per step
+template <int NKS>
+__device__ __forceinline__ void issue_ks(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum0) {
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks)
+    mma_f16_ss(d, desc_from_lo(a_lo + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc, ks == 0 ? accum0 : 1u);
+}
+__device__ __forceinline__ void issue_n(int nks, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum0) {
+  switch (nks) {
+    case 4: issue_ks<4>(d, a_lo, b_lo, idesc, accum0); break;
+    case 3: issue_ks<3>(d, a_lo, b_lo, idesc, accum0); break;
+    case 2: issue_ks<2>(d, a_lo, b_lo, idesc, accum0); break;
+    default: issue_ks<1>(d, a_lo, b_lo, idesc, accum0); break;
+  }
+}
+
+// ================================================================================================
 // PK_T
 // ================================================================================================
 struct TParams {
@@ -182,32 +206,40 @@ struct TParams {
   int64_t B;
 };
 
-constexpr int kTThreads = 6 * 32;   // warps 0-3 epilogue (one per TMEM lane quarter), 4 MMA issuer, 5 loader
 constexpr int kTSlots = 12;         // spill slots: three tiles' worth of quarters
 constexpr int kAStage = 128 * 128;  // one input slab of one tile
 
+// Epilogue organisation: C = 20 -> three warps per TMEM lane quarter, one 8-channel chunk of the output row each
+// (channels 0-7, 8-15, 16-19 + zero padding); C = 1 (k55 head) -> one warp per quarter.
 template <int C, int TAPS>
 struct TShape {
-  static constexpr int kMaxM = (C == 1) ? 32 : 8;   // largest row shift handled (lanes that can wrap)
+  static constexpr int kGroups = (C == 1) ? 1 : 3;
+  static constexpr int kEpiWarps = 4 * kGroups;
+  static constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA issuer, loader
+  static constexpr int kMaxM = (C == 1) ? 32 : 8;         // largest row shift handled (lanes that can wrap)
+  static constexpr int kRowFloats = (C == 1) ? 1 : 24;    // floats per spilled row
 };
 
-// ---- phase 1: shifted sums of one 32-row quarter ---------------------------------------------------
-template <int C, int TAPS>
-__device__ __forceinline__ void t_phase1(uint32_t trow, int lane, int dil, float (&acc)[C], float (&up)[C], float (&down)[C]);
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
 
-template <>
-__device__ __forceinline__ void t_phase1<20, 9>(uint32_t trow, int lane, int dil, float (&acc)[20], float (&up)[20], float (&down)[20]) {
+// ---- phase 1: shifted sums of NCH channels of one 32-row quarter ------------------------------------
+// tcol: TMEM address of this warp's first column of tap 0; taps are `tap_stride` columns apart.
+template <int NCH>
+__device__ __forceinline__ void t_phase1_k9(uint32_t tcol, int lane, int dil, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
 #pragma unroll
-  for (int c = 0; c < 20; ++c) { acc[c] = 0.f; up[c] = 0.f; down[c] = 0.f; }
-  uint32_t r[2][20];
-  auto load_tap = [&](int t, uint32_t (&dst)[20]) {
-    uint32_t a[16], b[4];
-    tmem_ld16(trow + (uint32_t)(t * 20), a);
-    tmem_ld4(trow + (uint32_t)(t * 20 + 16), b);
+  for (int c = 0; c < NCH; ++c) { acc[c] = 0.f; up[c] = 0.f; down[c] = 0.f; }
+  uint32_t r[2][8];
+  auto load_tap = [&](int t, uint32_t (&dst)[8]) {
+    if constexpr (NCH == 8) tmem_ld8(tcol + (uint32_t)(t * 20), dst);
+    else {
+      uint32_t b[4];
+      tmem_ld4(tcol + (uint32_t)(t * 20), b);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dst[i] = a[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[16 + i] = b[i];
+      for (int i = 0; i < 4; ++i) dst[i] = b[i];
+    }
   };
   load_tap(0, r[0]);
 #pragma unroll
@@ -218,26 +250,24 @@ __device__ __forceinline__ void t_phase1<20, 9>(uint32_t trow, int lane, int dil
     const int src = (lane + s) & 31;
     const bool inr = (unsigned)(lane + s) < 32u;
 #pragma unroll
-    for (int c = 0; c < 20; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const float v = __uint_as_float(r[t & 1][c]);
       if (t == 4) {
         acc[c] += v;
       } else {
         const float x = __shfl_sync(0xffffffffu, v, src);
         if (inr) acc[c] += x;
-        else if (t > 4) down[c] += x;   // source row belongs to this quarter, target row to the previous one
-        else up[c] += x;                // ... to the next one
+        else if (t > 4) down[c] += x;   // source row is in this quarter, target row in the previous one
+        else up[c] += x;                // ... in the next one
       }
     }
   }
 }
 
-template <>
-__device__ __forceinline__ void t_phase1<1, 55>(uint32_t trow, int lane, int dil, float (&acc)[1], float (&up)[1], float (&down)[1]) {
-  (void)dil;
+__device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc, float& up, float& down) {
   uint32_t r0[32], r1[32];
-  tmem_ld32(trow, r0);
-  tmem_ld32(trow + 32, r1);
+  tmem_ld32(tcol, r0);
+  tmem_ld32(tcol + 32, r1);
   tmem_ld_wait();
   float a = 0.f, u = 0.f, d = 0.f;
 #pragma unroll
@@ -251,31 +281,14 @@ __device__ __forceinline__ void t_phase1<1, 55>(uint32_t trow, int lane, int dil
     else if (s > 0) d += x;
     else u += x;
   }
-  acc[0] = a; up[0] = u; down[0] = d;
-}
-
-template <int C>
-__device__ __forceinline__ void t_finalize(const TParams& p, int64_t f, int row, const float (&r)[C], const float (&bias)[C]) {
-  if constexpr (C == 1) {
-    p.yvec[f * p.L + row] = apply_act(r[0] + bias[0], p.act);
-  } else {
-    uint8_t* img = p.out.base + f * p.out.frame_bytes;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = 8 * g + e;
-        v[e] = c < C ? apply_act(r[c < C ? c : 0] + bias[c < C ? c : 0], p.act) : 0.f;
-      }
-      pt_store8(p.out, img, row, g, v);
-    }
-  }
+  acc = a; up = u; down = d;
 }
 
 template <int C, int TAPS>
-__global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
-  constexpr int kMaxM = TShape<C, TAPS>::kMaxM;
+__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
+  using S = TShape<C, TAPS>;
+  constexpr int kMaxM = S::kMaxM, kRF = S::kRowFloats, kEpi = S::kEpiWarps;
+  constexpr int NCHMAX = (C == 1) ? 1 : 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t w_full, a_full[8], a_empty[8], acc_full[2], acc_empty[2];
@@ -285,8 +298,8 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
   const uint32_t wslab_bytes = (uint32_t)p.N * 128u;
   uint8_t* sW = smem;
   uint8_t* sA = sW + (uint32_t)p.n_wslab * wslab_bytes;
-  float* sU = reinterpret_cast<float*>(sA + (uint32_t)p.na * kAStage);     // [kTSlots][kMaxM][C]
-  float* sP = sU + kTSlots * kMaxM * C;                                     // [kTSlots][kMaxM][C]
+  float* sU = reinterpret_cast<float*>(sA + (uint32_t)p.na * kAStage);     // [kTSlots][kMaxM][kRF]
+  float* sP = sU + kTSlots * kMaxM * kRF;                                   // [kTSlots][kMaxM][kRF]
   const int T = p.L / 128;
   const int nst = pt_n_slabs(p.in);
   uint32_t tmem_cols = 32;
@@ -295,21 +308,23 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
   if (tid == 0) {
     mbar_init(&w_full, 1);
     for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpi); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (warp == 4) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (warp == kEpi) tmem_alloc(&tmem_base_s, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp < kEpi) {
     // =========================== epilogue ===========================
-    const int q = warp;
-    float bias[C];
+    const int q = warp & 3, grp = warp >> 2;          // TMEM lane quarter; 8-channel chunk of the output row
+    const int nch = (C == 1) ? 1 : (grp == 2 ? 4 : 8);
+    float bias[NCHMAX];
 #pragma unroll
-    for (int c = 0; c < C; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    for (int c = 0; c < NCHMAX; ++c) bias[c] = (p.bias && c < nch) ? __ldg(p.bias + grp * 8 + c) : 0.f;
+    const float slope = act_slope_of(p.act);
     const int m = ((TAPS - 1) / 2) * p.dil;
     const int nq = 4 * T;
     uint32_t it = 0;
@@ -318,8 +333,20 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
         const uint32_t acc_i = it & 1u;
         mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
         tc_fence_after();
-        float acc[C], up[C], down[C];
-        t_phase1<C, TAPS>(tmem + ((uint32_t)(q * 32) << 16) + acc_i * (uint32_t)p.N, lane, p.dil, acc, up, down);
+        float acc[NCHMAX], up[NCHMAX], down[NCHMAX];
+        const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + acc_i * (uint32_t)p.N + (uint32_t)(grp * 8);
+        if constexpr (C == 1) {
+          t_phase1_k55(tcol, lane, acc[0], up[0], down[0]);
+        } else {
+          if (grp == 2) {
+            float a4[4], u4[4], d4[4];
+            t_phase1_k9<4>(tcol, lane, p.dil, a4, u4, d4);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { acc[c] = c < 4 ? a4[c & 3] : 0.f; up[c] = c < 4 ? u4[c & 3] : 0.f; down[c] = c < 4 ? d4[c & 3] : 0.f; }
+          } else {
+            t_phase1_k9<8>(tcol, lane, p.dil, acc, up, down);
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc_i]);   // TMEM slot free: the next tile's MMAs run under phase 2
@@ -328,47 +355,70 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
         const int fqi = j * 4 + q;
         const bool lastq = fqi == nq - 1;
         const uint32_t slot = gq % kTSlots;
+        const int coff = (C == 1) ? 0 : grp * 8;
         if (lane < m) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) sU[(slot * kMaxM + lane) * C + c] = up[c];
+          for (int c = 0; c < NCHMAX; ++c) sU[(slot * kMaxM + lane) * kRF + coff + c] = up[c];
         }
         if (lane >= 32 - m && !lastq) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) sP[(slot * kMaxM + (lane - (32 - m))) * C + c] = acc[c];
+          for (int c = 0; c < NCHMAX; ++c) sP[(slot * kMaxM + (lane - (32 - m))) * kRF + coff + c] = acc[c];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" :: "n"(kEpi * 32) : "memory");
         const uint32_t slot1 = (gq + kTSlots - 1) % kTSlots, slot2 = (gq + kTSlots - 2) % kTSlots;
-        if (lane < 32 - m || lastq) {          // this quarter's own rows that need nothing from the next quarter
-          float r[C];
+        // Every thread finishes ONE row: its own if nothing is missing from the next quarter, else the parked row of the
+        // previous quarter whose down-spill it holds.  The frame's last quarter also finishes its own parked rows (pass 1).
+        const bool high = lane >= 32 - m;
+        for (int pass = 0; pass < ((lastq && high) ? 2 : 1); ++pass) {
+          const bool own = !high || pass == 1;
+          if (!own && fqi < 1) continue;
+          float r[NCHMAX];
+          int row;
+          if (own) {
+            row = fqi * 32 + lane;
 #pragma unroll
-          for (int c = 0; c < C; ++c) r[c] = acc[c];
-          if (lane < m && fqi >= 1) {
+            for (int c = 0; c < NCHMAX; ++c) r[c] = acc[c];
+            if (lane < m && fqi >= 1) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) r[c] += sU[(slot1 * kMaxM + lane) * C + c];
+              for (int c = 0; c < NCHMAX; ++c) r[c] += sU[(slot1 * kMaxM + lane) * kRF + coff + c];
+            }
+          } else {
+            row = (fqi - 1) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < NCHMAX; ++c) r[c] = sP[(slot1 * kMaxM + (lane - (32 - m))) * kRF + coff + c] + down[c];
+            if (lane < m && fqi >= 2) {
+#pragma unroll
+              for (int c = 0; c < NCHMAX; ++c) r[c] += sU[(slot2 * kMaxM + lane) * kRF + coff + c];
+            }
           }
-          t_finalize<C>(p, f, fqi * 32 + lane, r, bias);
-        }
-        if (lane >= 32 - m && fqi >= 1) {      // the previous quarter's parked rows: this thread holds their down-spill
-          float r[C];
+          if constexpr (C == 1) {
+            p.yvec[f * p.L + row] = apply_act(r[0] + bias[0], p.act);
+          } else {
+            uint8_t* img = p.out.base + f * p.out.frame_bytes;
+            float v[8];
 #pragma unroll
-          for (int c = 0; c < C; ++c) r[c] = sP[(slot1 * kMaxM + (lane - (32 - m))) * C + c] + down[c];
-          if (lane < m && fqi >= 2) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) r[c] += sU[(slot2 * kMaxM + lane) * C + c];
+            for (int c = 0; c < 8; ++c) v[c] = c < nch ? act_fast(r[c] + bias[c], slope) : 0.f;
+            pt_store8(p.out, img, row, grp, v);
+            if (grp == 2) {
+              const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              pt_store8(p.out, img, row, 3, z);
+            }
           }
-          t_finalize<C>(p, f, (fqi - 1) * 32 + lane, r, bias);
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kEpi) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       mbar_wait(&w_full, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_f16(p.N);
       const uint32_t w_lo0 = desc_lo(smem_u32(sW));
+      const uint32_t a_lo0 = desc_lo(smem_u32(sA));
       const uint32_t wslab_lo = wslab_bytes >> 4;
-      uint32_t it = 0, ait = 0;
+      const int spp = p.in.spp, planes = p.in.planes;
+      const bool packed = p.in.packed != 0;
+      uint32_t it = 0, slot = 0, sph = 0;
       for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
         for (int j = 0; j < T; ++j, ++it) {
           const uint32_t acc_i = it & 1u;
@@ -376,30 +426,25 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
           tc_fence_after();
           const uint32_t d = tmem + acc_i * (uint32_t)p.N;
           uint32_t accum = 0;
-          auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
-            for (int ks = 0; ks < nks; ++ks) {
-              mma_f16_ss(d, desc_from_lo(a_lo + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc, accum);
-              accum = 1;
-            }
-          };
-          for (int s = 0; s < nst; ++s, ++ait) {
-            const uint32_t slot = ait % (uint32_t)p.na;
-            mbar_wait(&a_full[slot], (ait / (uint32_t)p.na) & 1u);
+          for (int s = 0; s < nst; ++s) {
+            mbar_wait(&a_full[slot], sph);
             tc_fence_after();
-            const uint32_t a_lo = desc_lo(smem_u32(sA + slot * kAStage));
-            if (p.in.packed) {
-              issue(a_lo, w_lo0, p.ksteps);                 // hi * W_hi
-              if (p.in.planes == 2) {
-                issue(a_lo, w_lo0 + 4u, p.ksteps);          // hi * W_lo   (lo halves start 64 bytes into the row)
-                issue(a_lo + 4u, w_lo0, p.ksteps);          // lo * W_hi
+            const uint32_t a_lo = a_lo0 + slot * (uint32_t)(kAStage >> 4);
+            if (packed) {
+              issue_n(p.ksteps, d, a_lo, w_lo0, idesc, accum);            // hi * W_hi
+              if (planes == 2) {
+                issue_n(p.ksteps, d, a_lo, w_lo0 + 4u, idesc, 1u);        // hi * W_lo   (lo halves start 64 bytes into the row)
+                issue_n(p.ksteps, d, a_lo + 4u, w_lo0, idesc, 1u);        // lo * W_hi
               }
             } else {
-              const int plane = s / p.in.spp, sl = s - plane * p.in.spp;
+              const int plane = s >= spp ? 1 : 0, sl = s - plane * spp;
               const int nks = min(4, p.ksteps - 4 * sl);
-              issue(a_lo, w_lo0 + (uint32_t)sl * wslab_lo, nks);                                      // (hi | lo) * W_hi
-              if (plane == 0 && p.in.planes == 2) issue(a_lo, w_lo0 + (uint32_t)(p.in.spp + sl) * wslab_lo, nks);   // hi * W_lo
+              issue_n(nks, d, a_lo, w_lo0 + (uint32_t)sl * wslab_lo, idesc, accum);                                   // (hi | lo) * W_hi
+              if (plane == 0 && planes == 2) issue_n(nks, d, a_lo, w_lo0 + (uint32_t)(spp + sl) * wslab_lo, idesc, 1u);   // hi * W_lo
             }
+            accum = 1;
             umma_commit(&a_empty[slot]);
+            if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
           }
           umma_commit(&acc_full[acc_i]);
         }
@@ -411,15 +456,15 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
       mbar_expect_tx(&w_full, (uint32_t)p.n_wslab * wslab_bytes);
       for (int i = 0; i < p.n_wslab; ++i) bulk_g2s(sW + (uint32_t)i * wslab_bytes, p.wpack + (size_t)i * wslab_bytes, wslab_bytes, &w_full);
       const int64_t sb = pt_slab_bytes(p.in);
-      uint32_t ait = 0;
+      uint32_t slot = 0, sph = 1;
       for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
         const uint8_t* img = p.in.base + f * p.in.frame_bytes;
         for (int j = 0; j < T; ++j) {
-          for (int s = 0; s < nst; ++s, ++ait) {
-            const uint32_t slot = ait % (uint32_t)p.na;
-            mbar_wait(&a_empty[slot], ((ait / (uint32_t)p.na) & 1u) ^ 1u);
+          for (int s = 0; s < nst; ++s) {
+            mbar_wait(&a_empty[slot], sph);
             mbar_expect_tx(&a_full[slot], kAStage);
             bulk_g2s(sA + slot * kAStage, img + s * sb + (int64_t)(8 + 128 * j) * 128, kAStage, &a_full[slot]);
+            if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
           }
         }
       }
@@ -428,7 +473,7 @@ __global__ void __launch_bounds__(kTThreads, 1) plane_t_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+  if (warp == kEpi) tmem_dealloc(tmem, tmem_cols);
 }
 
 // ================================================================================================
@@ -453,15 +498,28 @@ struct XParams {
   int64_t B, n_tiles;
 };
 
-constexpr int kXEpiWarps = 8, kXGenWarps = 4;
+constexpr int kXEpiGroups = 3;                   // epilogue warps per TMEM lane quarter (each takes every third 16-column batch)
+constexpr int kXEpiWarps = 4 * kXEpiGroups, kXGenWarps = 4;
 constexpr int kXThreads = (kXEpiWarps + 3 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader
 constexpr int kXMaxStage = 16, kXMaxW = 40;
+
+struct ResRaw { uint4 h0, h1, l0, l1; float s; };
+
+__device__ __forceinline__ void pt_load_raw(const PlaneTensor& t, const uint8_t* img, int pos, int g, uint4& hi, uint4& lo) {
+  const int row = pos + 8;                       // residual tensors are never de-interleaved or packed
+  const uint32_t sw = (uint32_t)row & 7u;
+  const int64_t sb = pt_slab_bytes(t);
+  const uint8_t* r = img + (int64_t)(g >> 3) * sb + (int64_t)row * 128 + ((((uint32_t)g & 7u) ^ sw) << 4);
+  hi = __ldg(reinterpret_cast<const uint4*>(r));
+  lo = t.planes == 2 ? __ldg(reinterpret_cast<const uint4*>(r + (int64_t)t.spp * sb)) : make_uint4(0, 0, 0, 0);
+}
 
 __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_constant__ XParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[kXMaxStage], a_empty[kXMaxStage], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nbuf = p.n_stage * p.kbuf;
@@ -469,6 +527,7 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
   uint8_t* sW = smem + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
   const int acc_cols = p.mt * p.Npad;
 
+  if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
     for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], p.kind == PK_GEN ? kXGenWarps : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -483,9 +542,11 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
 
   if (warp < kXEpiWarps) {
     // =========================== epilogue ===========================
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, grp = warp >> 2;
     const int nb = p.Npad >> 4;
     const int n_e = p.mt * nb;
+    const float slope = act_slope_of(p.act), pslope = act_slope_of(p.post_act);
+    const bool slow_act = p.act == NSC_ACT_TANH || p.post_act == NSC_ACT_TANH;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int64_t f = tile / p.tiles_per_frame;
@@ -493,35 +554,58 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
       const uint32_t acc_i = it & 1u;
       uint8_t* oimg = p.out.base + f * p.out.frame_bytes;
       const uint8_t* rimg = p.res_mode == RES_ADD ? p.res.base + f * p.res.frame_bytes : nullptr;
+      const float* rvec = p.res_mode == RES_ADD_BCAST ? p.resvec + f * p.Lout : nullptr;
+      const int row0 = q0 + quarter * 32 + lane;
+      auto load_res = [&](int u, ResRaw& rr) {
+        if (u >= n_e) return;
+        const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
+        const int pos = row0 + mt_i * 128;
+        if (rimg) {
+          pt_load_raw(p.res, rimg, pos, c0 >> 3, rr.h0, rr.l0);
+          pt_load_raw(p.res, rimg, pos, (c0 >> 3) + 1, rr.h1, rr.l1);
+        } else if (rvec) {
+          rr.s = __ldg(rvec + pos);
+        }
+      };
+      ResRaw rn;
+      rn.s = 0.f;
+      load_res(grp, rn);                 // the residual does not depend on the accumulator: fetch it before waiting
       mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
       tc_fence_after();
-      for (int u = half; u < n_e; u += 2) {
+      for (int u = grp; u < n_e; u += kXEpiGroups) {
         const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
-        const int pos = q0 + mt_i * 128 + quarter * 32 + lane;
+        const int pos = row0 + mt_i * 128;
         uint32_t r[16];
         tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
+        const ResRaw rc = rn;
+        load_res(u + kXEpiGroups, rn);   // next batch's residual is in flight while this one is finished
         float rs[16];
-        if (p.res_mode == RES_ADD) {
-          float ra[8], rb[8];
-          pt_load8(p.res, rimg, pos, c0 >> 3, ra);
-          pt_load8(p.res, rimg, pos, (c0 >> 3) + 1, rb);
+        if (rimg) {
+          float a[8], b[8];
+          unpack8(rc.h0, a); unpack8(rc.l0, b);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { rs[e] = ra[e]; rs[8 + e] = rb[e]; }
-        } else if (p.res_mode == RES_ADD_BCAST) {
-          const float rv = __ldg(p.resvec + f * p.Lout + pos);
+          for (int e = 0; e < 8; ++e) rs[e] = a[e] + b[e];
+          unpack8(rc.h1, a); unpack8(rc.l1, b);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) rs[e] = (c0 + e < p.Cout) ? rv : 0.f;
+          for (int e = 0; e < 8; ++e) rs[8 + e] = a[e] + b[e];
         } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) rs[e] = 0.f;
+          for (int e = 0; e < 16; ++e) rs[e] = (rvec && c0 + e < p.Cout) ? rc.s : 0.f;
+        }
+        float bs[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + e]);
+          bs[e] = b4.x; bs[e + 1] = b4.y; bs[e + 2] = b4.z; bs[e + 3] = b4.w;
         }
         tmem_ld_wait();
         float v[16];
+        if (!slow_act) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int co = c0 + e;
-          const float b = (co < p.Cout && p.bias) ? __ldg(p.bias + co) : 0.f;
-          v[e] = apply_act(apply_act(__uint_as_float(r[e]) + b, p.act) + rs[e], p.post_act);
+          for (int e = 0; e < 16; ++e) v[e] = act_fast(act_fast(__uint_as_float(r[e]) + bs[e], slope) + rs[e], pslope);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = act_slow(act_slow(__uint_as_float(r[e]) + bs[e], p.act) + rs[e], p.post_act);
         }
         if (p.shuffle == 1) {
           float a[8], b[8];
@@ -537,10 +621,10 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
           pt_store8(p.out, oimg, 2 * pos + 1, c0 >> 4, b);
         }
       }
-      if (half == 0 && p.zero_from < p.zero_to) {
+      if (grp == 0 && p.zero_from < p.zero_to) {
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
-          const int pos = q0 + mt_i * 128 + quarter * 32 + lane;
+          const int pos = row0 + mt_i * 128;
           for (int g = p.zero_from; g < p.zero_to; ++g) {
             if (p.shuffle == 1) pt_store8(p.out, oimg, pos, g, z);
             else { pt_store8(p.out, oimg, 2 * pos, g, z); pt_store8(p.out, oimg, 2 * pos + 1, g, z); }
@@ -556,16 +640,19 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(p.Npad);
       const uint32_t mt_step = (128u * 128u) >> 4;
-      uint32_t it = 0, wit = 0;
+      const uint32_t a_lo_base = desc_lo(smem_u32(sA)), w_lo_base = desc_lo(smem_u32(sW));
+      const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4, unit_lo = (uint32_t)p.unit_bytes >> 4;
+      const int planes = p.planes, mt = p.mt, spp = p.in.spp;
+      const bool resident = p.resident != 0;
+      uint32_t it = 0, ws = 0, wph = 0, kb = 0, a_phase = 0;
+      bool w_ready = false;               // resident weights: waited for once
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc_i = it & 1u;
         mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem + acc_i * (uint32_t)acc_cols;
-        const int kb = (int)(it % (uint32_t)p.kbuf) * p.n_stage;
-        const uint32_t a_phase = (it / (uint32_t)p.kbuf) & 1u;
         uint32_t waited = 0, accum = 0;
-        int u = 0;
+        uint32_t u = 0;
         auto wait_stage = [&](int stage) {
           if (!((waited >> stage) & 1u)) {
             mbar_wait(&a_full[kb + stage], a_phase);
@@ -573,74 +660,83 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
             waited |= 1u << stage;
           }
         };
-        auto wait_w = [&]() -> uint32_t {
-          const uint32_t ws = p.resident ? (uint32_t)u : wit % (uint32_t)p.wslots;
-          mbar_wait(&w_full[ws], p.resident ? 0u : (wit / (uint32_t)p.wslots) & 1u);
+        auto wait_w = [&]() -> uint32_t {      // descriptor (low word) of the next weight unit
+          if (resident) {
+            if (!w_ready) { mbar_wait(&w_full[u], 0u); tc_fence_after(); }
+            return w_lo_base + u * unit_lo;
+          }
+          mbar_wait(&w_full[ws], wph);
           tc_fence_after();
-          return ws;
+          return w_lo_base + ws * unit_lo;
         };
-        auto done_w = [&](uint32_t ws) {
-          if (!p.resident) { umma_commit(&w_empty[ws]); ++wit; }
+        auto done_w = [&]() {
+          if (!resident) {
+            umma_commit(&w_empty[ws]);
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
+          }
           ++u;
         };
         auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
-          for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
-            const uint32_t d = d0 + (uint32_t)(mt_i * p.Npad);
-            for (int ks = 0; ks < nks; ++ks)
-              mma_f16_ss(d, desc_from_lo(a_lo + (uint32_t)mt_i * mt_step + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc,
-                         accum | (uint32_t)(ks > 0));
-          }
+          issue_n(nks, d0, a_lo, b_lo, idesc, accum);
+          if (mt == 2) issue_n(nks, d0 + (uint32_t)p.Npad, a_lo + mt_step, b_lo, idesc, accum);
           accum = 1;
         };
         if (p.kind == PK_GEN) {
-          for (int wp = 0; wp < p.planes; ++wp) {
-            const uint32_t ws = wait_w();
-            const uint32_t b_lo = desc_lo(smem_u32(sW + ws * (uint32_t)p.unit_bytes));
-            for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
+          for (int wp = 0; wp < planes; ++wp) {
+            const uint32_t b_lo = wait_w();
+            for (int ap = 0; ap < (wp == 0 ? planes : 1); ++ap) {
               wait_stage(ap);
-              issue(desc_lo(smem_u32(sA + (uint32_t)(kb + ap) * (uint32_t)p.stage_bytes)), b_lo, p.ksteps);
+              issue(a_lo_base + (kb + (uint32_t)ap) * stage_lo, b_lo, p.ksteps);
             }
-            done_w(ws);
+            done_w();
           }
-          for (int ap = 0; ap < p.planes; ++ap) umma_commit(&a_empty[kb + ap]);
+          for (int ap = 0; ap < planes; ++ap) umma_commit(&a_empty[kb + ap]);
         } else if (p.in.packed) {
           wait_stage(0);
+          const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
           for (int t = 0; t < p.K; ++t) {
-            const uint32_t ws = wait_w();
-            const uint32_t b_lo = desc_lo(smem_u32(sW + ws * (uint32_t)p.unit_bytes));
-            const uint32_t a_lo = desc_lo(smem_u32(sA + (uint32_t)kb * (uint32_t)p.stage_bytes) + (uint32_t)(8 + t * p.dil - p.padL) * 128u);
+            const uint32_t b_lo = wait_w();
+            const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
             issue(a_lo, b_lo, p.ksteps);
-            if (p.planes == 2) {
+            if (planes == 2) {
               issue(a_lo, b_lo + 4u, p.ksteps);
               issue(a_lo + 4u, b_lo, p.ksteps);
             }
-            done_w(ws);
+            done_w();
           }
           umma_commit(&a_empty[kb]);
         } else {
           const int nsub = p.in.deint ? 2 : 1;
-          for (int s = 0; s < p.in.spp; ++s) {
+          for (int s = 0; s < spp; ++s) {
             const int nks = min(4, p.ksteps - 4 * s);
             for (int t = 0; t < p.K; ++t) {
               int sub = 0, rowoff;
               if (p.stride == 1) rowoff = 8 + t * p.dil - p.padL;
               else { const int tp = t - p.padL; sub = tp & 1; rowoff = 8 + (tp - sub) / 2; }
-              for (int wp = 0; wp < p.planes; ++wp) {
-                const uint32_t ws = wait_w();
-                const uint32_t b_lo = desc_lo(smem_u32(sW + ws * (uint32_t)p.unit_bytes));
-                for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
-                  const int stage = pt_slab_index(p.in, sub, ap, s);
-                  wait_stage(stage);
-                  issue(desc_lo(smem_u32(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes) + (uint32_t)rowoff * 128u), b_lo, nks);
-                }
-                done_w(ws);
+              const int st_hi = pt_slab_index(p.in, sub, 0, s);
+              const uint32_t a_hi = a_lo_base + (kb + (uint32_t)st_hi) * stage_lo + (uint32_t)rowoff * 8u;
+              const uint32_t a_lo_pl = a_hi + (uint32_t)spp * stage_lo;     // the lo plane's stage is spp slabs further
+              {   // W_hi unit: hi * W_hi and lo * W_hi while it is resident
+                const uint32_t b_lo = wait_w();
+                wait_stage(st_hi);
+                issue(a_hi, b_lo, nks);
+                if (planes == 2) { wait_stage(st_hi + spp); issue(a_lo_pl, b_lo, nks); }
+                done_w();
+              }
+              if (planes == 2) {   // W_lo unit: hi * W_lo
+                const uint32_t b_lo = wait_w();
+                issue(a_hi, b_lo, nks);
+                done_w();
               }
             }
             for (int sub = 0; sub < nsub; ++sub)
-              for (int ap = 0; ap < p.planes; ++ap) umma_commit(&a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
+              for (int ap = 0; ap < planes; ++ap) umma_commit(&a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
           }
         }
         umma_commit(&acc_full[acc_i]);
+        w_ready = true;
+        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) a_phase ^= 1u; }
+        else a_phase ^= 1u;
       }
     }
   } else if (warp == kXEpiWarps + 1) {
@@ -649,13 +745,11 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
       const int64_t sb = pt_slab_bytes(p.in);
       const int nsub = p.in.deint ? 2 : 1;
       const int npl = p.in.packed ? 1 : p.in.planes;
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      uint32_t kb = 0, ph = 1;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         const uint8_t* img = p.in.base + f * p.in.frame_bytes;
-        const int kb = (int)(it % (uint32_t)p.kbuf) * p.n_stage;
-        const uint32_t ph = ((it / (uint32_t)p.kbuf) & 1u) ^ 1u;
         for (int s = 0; s < p.in.spp; ++s)          // consumption order of the issuer: slab-major
           for (int sub = 0; sub < nsub; ++sub)
             for (int ap = 0; ap < npl; ++ap) {
@@ -665,6 +759,8 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
               bulk_g2s(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes, img + stage * sb + (int64_t)q0 * 128, (uint32_t)p.stage_bytes,
                        &a_full[kb + stage]);
             }
+        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
+        else ph ^= 1u;
       }
     }
   } else if (warp == kXEpiWarps + 2) {
@@ -676,13 +772,13 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
           bulk_g2s(sW + (uint32_t)u * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[u]);
         }
       } else {
-        uint32_t wit = 0;
+        uint32_t ws = 0, wph = 1;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-          for (int u = 0; u < p.n_units; ++u, ++wit) {
-            const uint32_t ws = wit % (uint32_t)p.wslots;
-            mbar_wait(&w_empty[ws], ((wit / (uint32_t)p.wslots) & 1u) ^ 1u);
+          for (int u = 0; u < p.n_units; ++u) {
+            mbar_wait(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
             bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
           }
         }
       }
@@ -692,16 +788,14 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
     if (p.kind == PK_GEN) {
       const int ptid = tid - (kXEpiWarps + 3) * 32;
       const int nch = p.ksteps * 2;     // 16-byte chunks per row that the MMAs read
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      uint32_t kb = 0, ph = 1;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
-        const int kb = (int)(it % (uint32_t)p.kbuf) * p.n_stage;
-        const uint32_t ph = ((it / (uint32_t)p.kbuf) & 1u) ^ 1u;
         for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
         const float* xv = p.xvec + f * p.Lin;
         const float* xs = p.xsub ? p.xsub + f * p.Lin : nullptr;
-        uint8_t* dhi = sA + (uint32_t)kb * (uint32_t)p.stage_bytes;
+        uint8_t* dhi = sA + kb * (uint32_t)p.stage_bytes;
         uint8_t* dlo = dhi + p.stage_bytes;
         for (int item = ptid; item < p.tile * nch; item += kXGenWarps * 32) {
           const int i = item / nch, g = item - i * nch;
@@ -724,6 +818,8 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0)
           for (int ap = 0; ap < p.planes; ++ap) mbar_arrive(&a_full[kb + ap]);
+        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
+        else ph ^= 1u;
       }
     }
   }
@@ -750,8 +846,8 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   pl->N = k9 ? 192 : 64;
   pl->ksteps = (c.Cin + 15) / 16;
   pl->n_wslab = c.in.packed ? 1 : c.in.planes * c.in.spp;
-  const int C = c.Cout, maxm = k9 ? 8 : 32;
-  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * kTSlots * maxm * C * sizeof(float);
+  const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
+  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * kTSlots * maxm * rowf * sizeof(float);
   if (fixed + 2ull * kAStage > kSmemBudget) return false;
   size_t na = (kSmemBudget - fixed) / kAStage;
   if (na > 8) na = 8;
@@ -909,10 +1005,10 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     const int64_t grid = c.B < sm_count() ? c.B : sm_count();
     if (c.Cout == 20) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 9><<<(unsigned)grid, kTThreads, pl.smem, st>>>(p);
+      plane_t_kernel<20, 9><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
     } else {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<1, 55><<<(unsigned)grid, kTThreads, pl.smem, st>>>(p);
+      plane_t_kernel<1, 55><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
     }
     NSC_LAUNCH_OK();
     return NSC_OK;
