@@ -229,37 +229,33 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 // tcol: TMEM address of this warp's first column of tap 0; taps are `tap_stride` columns apart.
 template <int NCH>
 __device__ __forceinline__ void t_phase1_k9(uint32_t tcol, int lane, int dil, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
+  // all nine taps are fetched before the single wait: 9 * NCH independent shuffles then pipeline back to back
+  uint32_t r[9][8];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) { acc[c] = 0.f; up[c] = 0.f; down[c] = 0.f; }
-  uint32_t r[2][8];
-  auto load_tap = [&](int t, uint32_t (&dst)[8]) {
-    if constexpr (NCH == 8) tmem_ld8(tcol + (uint32_t)(t * 20), dst);
+  for (int t = 0; t < 9; ++t) {
+    if constexpr (NCH == 8) tmem_ld8(tcol + (uint32_t)(t * 20), r[t]);
     else {
       uint32_t b[4];
       tmem_ld4(tcol + (uint32_t)(t * 20), b);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = b[i];
+      for (int i = 0; i < 4; ++i) r[t][i] = b[i];
     }
-  };
-  load_tap(0, r[0]);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { acc[c] = __uint_as_float(r[4][c]); up[c] = 0.f; down[c] = 0.f; }
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    tmem_ld_wait();
-    if (t + 1 < 9) load_tap(t + 1, r[(t + 1) & 1]);   // next tap's load is in flight under this tap's shuffles
+    if (t == 4) continue;
     const int s = (t - 4) * dil;
     const int src = (lane + s) & 31;
     const bool inr = (unsigned)(lane + s) < 32u;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const float v = __uint_as_float(r[t & 1][c]);
-      if (t == 4) {
-        acc[c] += v;
-      } else {
-        const float x = __shfl_sync(0xffffffffu, v, src);
-        if (inr) acc[c] += x;
-        else if (t > 4) down[c] += x;   // source row is in this quarter, target row in the previous one
-        else up[c] += x;                // ... in the next one
-      }
+      const float x = __shfl_sync(0xffffffffu, __uint_as_float(r[t][c]), src);
+      if (inr) acc[c] += x;
+      else if (t > 4) down[c] += x;   // source row is in this quarter, target row in the previous one
+      else up[c] += x;                // ... in the next one
     }
   }
 }
@@ -500,7 +496,9 @@ struct XParams {
 
 constexpr int kXEpiGroups = 3;                   // epilogue warps per TMEM lane quarter (each takes every third 16-column batch)
 constexpr int kXEpiWarps = 4 * kXEpiGroups, kXGenWarps = 4;
-constexpr int kXThreads = (kXEpiWarps + 3 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader
+constexpr int kXThreadsX = (kXEpiWarps + 3) * 32;                 // + MMA issuer, A loader, W loader
+constexpr int kXThreadsGen = (kXEpiWarps + 3 + kXGenWarps) * 32;   // + Toeplitz producers
+constexpr int kGenSeg = 336;                                       // staged input samples per tile: 256 + 63 taps, rounded up
 constexpr int kXMaxStage = 16, kXMaxW = 40;
 
 struct ResRaw { uint4 h0, h1, l0, l1; float s; };
@@ -514,12 +512,14 @@ __device__ __forceinline__ void pt_load_raw(const PlaneTensor& t, const uint8_t*
   lo = t.planes == 2 ? __ldg(reinterpret_cast<const uint4*>(r + (int64_t)t.spp * sb)) : make_uint4(0, 0, 0, 0);
 }
 
-__global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_constant__ XParams p) {
+template <bool kGen>
+__global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_kernel(const __grid_constant__ XParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[kXMaxStage], a_empty[kXMaxStage], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128];
+  __shared__ __align__(16) __half s_xh[kGen ? kGenSeg : 8], s_xl[kGen ? kGenSeg : 8];   // hi / lo halves of the tile's input samples
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nbuf = p.n_stage * p.kbuf;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
 
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], p.kind == PK_GEN ? kXGenWarps : 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kXEpiWarps); }
   }
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
       const float* rvec = p.res_mode == RES_ADD_BCAST ? p.resvec + f * p.Lout : nullptr;
       const int row0 = q0 + quarter * 32 + lane;
       auto load_res = [&](int u, ResRaw& rr) {
-        if (u >= n_e) return;
+        if (kGen || u >= n_e) return;      // 1-channel-input layers carry no residual
         const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
         const int pos = row0 + mt_i * 128;
         if (rimg) {
@@ -567,9 +567,10 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
           rr.s = __ldg(rvec + pos);
         }
       };
-      ResRaw rn;
-      rn.s = 0.f;
-      load_res(grp, rn);                 // the residual does not depend on the accumulator: fetch it before waiting
+      ResRaw rn, rn2;
+      rn.s = 0.f; rn2.s = 0.f;
+      load_res(grp, rn);                 // the residual does not depend on the accumulator: two batches are fetched
+      load_res(grp + kXEpiGroups, rn2);  // before waiting for it, and the pipeline stays two batches deep
       mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
       tc_fence_after();
       for (int u = grp; u < n_e; u += kXEpiGroups) {
@@ -578,7 +579,8 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
         uint32_t r[16];
         tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
         const ResRaw rc = rn;
-        load_res(u + kXEpiGroups, rn);   // next batch's residual is in flight while this one is finished
+        rn = rn2;
+        load_res(u + 2 * kXEpiGroups, rn2);
         float rs[16];
         if (rimg) {
           float a[8], b[8];
@@ -681,7 +683,7 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
           if (mt == 2) issue_n(nks, d0 + (uint32_t)p.Npad, a_lo + mt_step, b_lo, idesc, accum);
           accum = 1;
         };
-        if (p.kind == PK_GEN) {
+        if (kGen) {
           for (int wp = 0; wp < planes; ++wp) {
             const uint32_t b_lo = wait_w();
             for (int ap = 0; ap < (wp == 0 ? planes : 1); ++ap) {
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
     }
   } else if (warp == kXEpiWarps + 1) {
     // =========================== A loader (bulk copies of plane tiles) ===========================
-    if (p.kind != PK_GEN && elect_one()) {
+    if (!kGen && elect_one()) {
       const int64_t sb = pt_slab_bytes(p.in);
       const int nsub = p.in.deint ? 2 : 1;
       const int npl = p.in.packed ? 1 : p.in.planes;
@@ -785,39 +787,55 @@ __global__ void __launch_bounds__(kXThreads, 1) plane_x_kernel(const __grid_cons
     }
   } else {
     // =========================== Toeplitz producers (PK_GEN) ===========================
-    if (p.kind == PK_GEN) {
+    // The tile's input samples are split into hi / lo halves ONCE into a small staging array; row i of the Toeplitz
+    // tile is then the 2 * ksteps * 8 consecutive halves starting at sample i, i.e. per 16-byte chunk five 32-bit
+    // shared loads and (for odd i) four funnel shifts.  Entries past the K taps meet zero weights.
+    if constexpr (kGen) {
       const int ptid = tid - (kXEpiWarps + 3) * 32;
       const int nch = p.ksteps * 2;     // 16-byte chunks per row that the MMAs read
+      const int nch_sh = nch == 8 ? 3 : (nch == 4 ? 2 : (nch == 2 ? 1 : 0));
+      const uint32_t* wh = reinterpret_cast<const uint32_t*>(s_xh);
+      const uint32_t* wl = reinterpret_cast<const uint32_t*>(s_xl);
       uint32_t kb = 0, ph = 1;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
-        for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
         const float* xv = p.xvec + f * p.Lin;
         const float* xs = p.xsub ? p.xsub + f * p.Lin : nullptr;
+        for (int j = ptid; j < kGenSeg; j += kXGenWarps * 32) {
+          const int pos = q0 - p.padL + j;
+          float x = 0.f;
+          if (pos >= 0 && pos < p.Lin) x = p.xscale * (__ldg(xv + pos) - (xs ? __ldg(xs + pos) : 0.f));
+          const __half h = __float2half_rn(x);
+          s_xh[j] = h;
+          s_xl[j] = __float2half_rn(x - __half2float(h));
+        }
+        for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
+        asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");
         uint8_t* dhi = sA + kb * (uint32_t)p.stage_bytes;
         uint8_t* dlo = dhi + p.stage_bytes;
-        for (int item = ptid; item < p.tile * nch; item += kXGenWarps * 32) {
-          const int i = item / nch, g = item - i * nch;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = 8 * g + e;
-            const int pos = q0 + i - p.padL + k * p.dil;
-            float x = 0.f;
-            if (k < p.K && pos >= 0 && pos < p.Lin) x = p.xscale * (__ldg(xv + pos) - (xs ? __ldg(xs + pos) : 0.f));
-            v[e] = x;
-          }
-          uint4 hi, lo;
-          split8(v, hi, lo);
+        for (int item = ptid; item < (p.tile << nch_sh); item += kXGenWarps * 32) {
+          const int i = item >> nch_sh, g = item & (nch - 1);
+          const int j0 = i + 8 * g;
+          const int w = j0 >> 1;
           const uint32_t off = (uint32_t)i * 128u + (((uint32_t)g ^ ((uint32_t)i & 7u)) << 4);
-          *reinterpret_cast<uint4*>(dhi + off) = hi;
-          if (p.planes == 2) *reinterpret_cast<uint4*>(dlo + off) = lo;
+          uint32_t a0 = wh[w], a1 = wh[w + 1], a2 = wh[w + 2], a3 = wh[w + 3], a4 = wh[w + 4];
+          uint4 o;
+          if (j0 & 1) o = make_uint4(__funnelshift_r(a0, a1, 16), __funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), __funnelshift_r(a3, a4, 16));
+          else o = make_uint4(a0, a1, a2, a3);
+          *reinterpret_cast<uint4*>(dhi + off) = o;
+          if (p.planes == 2) {
+            a0 = wl[w]; a1 = wl[w + 1]; a2 = wl[w + 2]; a3 = wl[w + 3]; a4 = wl[w + 4];
+            if (j0 & 1) o = make_uint4(__funnelshift_r(a0, a1, 16), __funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), __funnelshift_r(a3, a4, 16));
+            else o = make_uint4(a0, a1, a2, a3);
+            *reinterpret_cast<uint4*>(dlo + off) = o;
+          }
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0)
           for (int ap = 0; ap < p.planes; ++ap) mbar_arrive(&a_full[kb + ap]);
+        asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");   // staging array is reused by the next tile
         if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
         else ph ^= 1u;
       }
@@ -864,7 +882,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   if (c.shuffle != 1 && c.shuffle != 2) return false;
   if (c.Cout < 2 || c.Cout > 128 || c.Cout % c.shuffle != 0) return false;
   if (gen) {
-    if (c.Cin != 1 || c.stride != 1 || c.K > 64 || c.xvec == nullptr) return false;
+    if (c.Cin != 1 || c.stride != 1 || c.dil != 1 || c.K > 64 || c.xvec == nullptr) return false;
   } else {
     if (c.Cin < 2 || c.Cin > 128) return false;
     if (c.stride == 1) { if (c.in.deint || c.in.rows != c.Lin) return false; }
@@ -876,7 +894,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   }
   if (c.res_mode == RES_ADD && (c.res.deint || c.res.rows != Lout)) return false;
   if (c.res_mode == RES_ADD_BCAST && c.resvec == nullptr) return false;
-  if (c.res_mode == RES_MUL) return false;
+  if (c.res_mode == RES_MUL || (gen && c.res_mode != RES_NONE)) return false;
   if (c.out.rows != (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
   p->kind = c.kind;
   p->in = c.in; p->out = c.out; p->res = c.res;
@@ -1016,7 +1034,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   XParams p;
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
   const size_t smem = x_smem_bytes(p);
-  NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
   double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_payload_bytes(c.in));
   bytes += (double)c.B * pt_payload_bytes(c.out);
@@ -1024,7 +1043,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
   ProfScope prof(st, name, 2.0 * macs, bytes);
   const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  plane_x_kernel<<<(unsigned)grid, kXThreads, smem, st>>>(p);
+  if (c.kind == PK_GEN) plane_x_kernel<true><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
+  else plane_x_kernel<false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
