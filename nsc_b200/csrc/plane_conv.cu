@@ -20,6 +20,8 @@
 //
 // Epilogues write the next layer's plane image directly (bias, activation, residual add from the residual's planes,
 // hi/lo split, sub-pixel shuffle, stride-2 de-interleave are all index arithmetic on the way out).
+#include <stdlib.h>
+
 #include "plane.cuh"
 #include "tc_common.cuh"
 
@@ -491,6 +493,7 @@ struct XParams {
   int n_units, unit_bytes, wslots, resident;
   int tmem_cols;
   int zero_from, zero_to;    // output chunks the epilogue must clear (K padding the consumer will read)
+  int staged;                // plane_xs_kernel: epilogue through shared-memory units and bulk copies
   int64_t B, n_tiles;
 };
 
@@ -847,6 +850,292 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   if (warp == kXEpiWarps) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
+// ================================================================================================
+// PK_X with a staged epilogue (narrow-input layers: 20 -> 100 / 20 -> 50 + residual, the HBM-bound third conv of a block)
+//
+// A thread owns one ROW of the accumulator, so direct global loads / stores of its 16-byte chunks touch 32 different
+// 128-byte lines per warp instruction -- the load/store unit then moves one line per cycle and caps the kernel far below
+// the HBM rate.  Here the residual tile arrives by bulk copy into a shared-memory unit laid out exactly like the image
+// (128 rows x 128 B per plane), the epilogue adds it and writes the result over it IN PLACE (16-byte shared accesses,
+// conflict-free thanks to the swizzle), and a dedicated thread sends the finished unit back with one bulk store per
+// plane.  No thread touches global memory; latency hiding is the copy engine's job.
+//   unit = (M tile, 64-channel output slab) x planes; ring of kSUnits units:  residual loader -> epilogue -> storer.
+// ================================================================================================
+constexpr int kSEpiGroups = 4, kSEpiWarps = 4 * kSEpiGroups;
+constexpr int kSThreads = (kSEpiWarps + 5) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer
+constexpr int kSUnits = 3;
+constexpr int kSPlane = 128 * 128;                 // one plane of one unit
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_constant__ XParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t a_full[4], a_empty[4], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
+  __shared__ uint64_t st_full[kSUnits], st_done[kSUnits], st_empty[kSUnits];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbuf = p.n_stage * p.kbuf;                 // n_stage == 1 (packed input)
+  const uint32_t stg_bytes = (uint32_t)p.planes * kSPlane;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
+  uint8_t* sS = sW + (uint32_t)p.wslots * (uint32_t)p.unit_bytes;
+  const int acc_cols = p.mt * p.Npad;
+  const int ospp = p.out.spp;
+  const int nb = p.Npad >> 4;
+
+  if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kSEpiWarps); }
+    for (int i = 0; i < kSUnits; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_done[i], kSEpiWarps); mbar_init(&st_empty[i], 1); }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (warp == kSEpiWarps) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < kSEpiWarps) {
+    // =========================== epilogue ===========================
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int lr = quarter * 32 + lane;                  // row inside the M tile
+    const float slope = act_slope_of(p.act), pslope = act_slope_of(p.post_act);
+    const bool has_res = p.res_mode == RES_ADD;
+    const bool barrier_rw = has_res && p.out.deint;      // residual and output use different unit layouts: read all, then write all
+    // shared-memory offsets of this thread's two chunks inside a unit plane (layout of the OUTPUT image)
+    const int srow_o = p.out.deint ? (lr >> 1) : lr;
+    const uint32_t obase = (p.out.deint ? (uint32_t)(lr & 1) * (kSPlane / 2) : 0u) + (uint32_t)srow_o * 128u;
+    const uint32_t osw = (uint32_t)srow_o & 7u;
+    const uint32_t rbase = (uint32_t)lr * 128u, rsw = (uint32_t)lr & 7u;   // residual units are never de-interleaved
+    uint32_t it = 0, slot = 0, sph = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int64_t f = tile / p.tiles_per_frame;
+      const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+      const uint32_t acc_i = it & 1u;
+      const float* rvec = p.res_mode == RES_ADD_BCAST ? p.resvec + f * p.Lout : nullptr;
+      mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
+      tc_fence_after();
+      for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
+        const float rv = rvec ? __ldg(rvec + q0 + mt_i * 128 + lr) : 0.f;
+        for (int s = 0; s < ospp; ++s) {
+          const int nbs = min(4, nb - 4 * s);
+          mbar_wait(&st_full[slot], sph);
+          uint8_t* unit = sS + slot * stg_bytes;
+          const bool mine = grp < nbs;
+          const int c0 = 64 * s + 16 * grp;              // first column / channel of this warp's batch
+          const uint32_t cg = 2u * (uint32_t)grp;        // first 16-byte chunk inside the slab
+          float v[16];
+          if (mine) {
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
+            float rs[16];
+            if (has_res) {
+              const uint4 h0 = *reinterpret_cast<const uint4*>(unit + rbase + ((cg ^ rsw) << 4));
+              const uint4 h1 = *reinterpret_cast<const uint4*>(unit + rbase + (((cg + 1u) ^ rsw) << 4));
+              float a[8], b[8];
+              unpack8(h0, a); unpack8(h1, b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { rs[e] = a[e]; rs[8 + e] = b[e]; }
+              if (p.planes == 2) {
+                const uint4 l0 = *reinterpret_cast<const uint4*>(unit + kSPlane + rbase + ((cg ^ rsw) << 4));
+                const uint4 l1 = *reinterpret_cast<const uint4*>(unit + kSPlane + rbase + (((cg + 1u) ^ rsw) << 4));
+                unpack8(l0, a); unpack8(l1, b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { rs[e] += a[e]; rs[8 + e] += b[e]; }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) rs[e] = (rvec && c0 + e < p.Cout) ? rv : 0.f;
+            }
+            float bs[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + e]);
+              bs[e] = b4.x; bs[e + 1] = b4.y; bs[e + 2] = b4.z; bs[e + 3] = b4.w;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = act_fast(act_fast(__uint_as_float(r[e]) + bs[e], slope) + rs[e], pslope);
+          }
+          if (barrier_rw) asm volatile("bar.sync 3, %0;" :: "n"(kSEpiWarps * 32) : "memory");
+          if (mine) {
+            float a[8], b[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] = v[e]; b[e] = v[8 + e]; }
+            uint4 hi, lo;
+            split8(a, hi, lo);
+            *reinterpret_cast<uint4*>(unit + obase + ((cg ^ osw) << 4)) = hi;
+            if (p.planes == 2) *reinterpret_cast<uint4*>(unit + kSPlane + obase + ((cg ^ osw) << 4)) = lo;
+            split8(b, hi, lo);
+            *reinterpret_cast<uint4*>(unit + obase + (((cg + 1u) ^ osw) << 4)) = hi;
+            if (p.planes == 2) *reinterpret_cast<uint4*>(unit + kSPlane + obase + (((cg + 1u) ^ osw) << 4)) = lo;
+          }
+          fence_async_smem();                            // generic-proxy writes -> visible to the bulk store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_done[slot]);
+          if (++slot == kSUnits) { slot = 0; sph ^= 1u; }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc_i]);
+    }
+  } else if (warp == kSEpiWarps) {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(p.Npad);
+      const uint32_t mt_step = (128u * 128u) >> 4;
+      const uint32_t a_lo_base = desc_lo(smem_u32(sA)), w_lo_base = desc_lo(smem_u32(sW));
+      const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4, unit_lo = (uint32_t)p.unit_bytes >> 4;
+      const int planes = p.planes, mt = p.mt;
+      const bool resident = p.resident != 0;
+      uint32_t it = 0, ws = 0, wph = 0, kb = 0, a_phase = 0;
+      bool w_ready = false;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc_i = it & 1u;
+        mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem + acc_i * (uint32_t)acc_cols;
+        uint32_t accum = 0;
+        auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
+          issue_n(nks, d0, a_lo, b_lo, idesc, accum);
+          if (mt == 2) issue_n(nks, d0 + (uint32_t)p.Npad, a_lo + mt_step, b_lo, idesc, accum);
+          accum = 1;
+        };
+        mbar_wait(&a_full[kb], a_phase);
+        tc_fence_after();
+        const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
+        for (int t = 0; t < p.K; ++t) {
+          uint32_t b_lo;
+          if (resident) {
+            if (!w_ready) { mbar_wait(&w_full[t], 0u); tc_fence_after(); }
+            b_lo = w_lo_base + (uint32_t)t * unit_lo;
+          } else {
+            mbar_wait(&w_full[ws], wph);
+            tc_fence_after();
+            b_lo = w_lo_base + ws * unit_lo;
+          }
+          const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
+          issue(a_lo, b_lo, p.ksteps);
+          if (planes == 2) {
+            issue(a_lo, b_lo + 4u, p.ksteps);
+            issue(a_lo + 4u, b_lo, p.ksteps);
+          }
+          if (!resident) {
+            umma_commit(&w_empty[ws]);
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
+          }
+        }
+        umma_commit(&a_empty[kb]);
+        umma_commit(&acc_full[acc_i]);
+        w_ready = true;
+        if (p.kbuf == 2) { kb ^= 1u; if (kb == 0) a_phase ^= 1u; }
+        else a_phase ^= 1u;
+      }
+    }
+  } else if (warp == kSEpiWarps + 1) {
+    // =========================== A loader ===========================
+    if (elect_one()) {
+      uint32_t kb = 0, ph = 1;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t f = tile / p.tiles_per_frame;
+        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+        mbar_wait(&a_empty[kb], ph);
+        mbar_expect_tx(&a_full[kb], (uint32_t)p.stage_bytes);
+        bulk_g2s(sA + kb * (uint32_t)p.stage_bytes, p.in.base + f * p.in.frame_bytes + (int64_t)q0 * 128, (uint32_t)p.stage_bytes, &a_full[kb]);
+        if (p.kbuf == 2) { kb ^= 1u; if (kb == 0) ph ^= 1u; }
+        else ph ^= 1u;
+      }
+    }
+  } else if (warp == kSEpiWarps + 2) {
+    // =========================== W loader ===========================
+    if (elect_one()) {
+      if (p.resident) {
+        for (int u = 0; u < p.n_units; ++u) {
+          mbar_expect_tx(&w_full[u], (uint32_t)p.unit_bytes);
+          bulk_g2s(sW + (uint32_t)u * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[u]);
+        }
+      } else {
+        uint32_t ws = 0, wph = 1;
+        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          for (int u = 0; u < p.n_units; ++u) {
+            mbar_wait(&w_empty[ws], wph);
+            mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
+            bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == kSEpiWarps + 3) {
+    // =========================== residual loader ===========================
+    if (elect_one()) {
+      const bool has_res = p.res_mode == RES_ADD;
+      const int64_t rsb = pt_slab_bytes(p.res);
+      uint32_t slot = 0, ph = 1;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t f = tile / p.tiles_per_frame;
+        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+        for (int mt_i = 0; mt_i < p.mt; ++mt_i)
+          for (int s = 0; s < ospp; ++s) {
+            mbar_wait(&st_empty[slot], ph);
+            if (has_res) {
+              mbar_expect_tx(&st_full[slot], stg_bytes);
+              for (int pl = 0; pl < p.planes; ++pl)
+                bulk_g2s(sS + slot * stg_bytes + (uint32_t)pl * kSPlane,
+                         p.res.base + f * p.res.frame_bytes + (int64_t)(pl * p.res.spp + s) * rsb + (int64_t)(8 + q0 + mt_i * 128) * 128, kSPlane,
+                         &st_full[slot]);
+            } else {
+              mbar_arrive(&st_full[slot]);
+            }
+            if (++slot == kSUnits) { slot = 0; ph ^= 1u; }
+          }
+      }
+    }
+  } else {
+    // =========================== storer ===========================
+    if (elect_one()) {
+      const int64_t osb = pt_slab_bytes(p.out);
+      uint32_t slot = 0, ph = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t f = tile / p.tiles_per_frame;
+        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+        uint8_t* oimg = p.out.base + f * p.out.frame_bytes;
+        for (int mt_i = 0; mt_i < p.mt; ++mt_i)
+          for (int s = 0; s < ospp; ++s) {
+            mbar_wait(&st_done[slot], ph);
+            const int p0 = q0 + mt_i * 128;
+            for (int pl = 0; pl < p.planes; ++pl) {
+              const uint8_t* src = sS + slot * stg_bytes + (uint32_t)pl * kSPlane;
+              if (!p.out.deint) {
+                bulk_s2g(oimg + (int64_t)pt_slab_index(p.out, 0, pl, s) * osb + (int64_t)(8 + p0) * 128, src, kSPlane);
+              } else {
+                for (int sub = 0; sub < 2; ++sub)
+                  bulk_s2g(oimg + (int64_t)pt_slab_index(p.out, sub, pl, s) * osb + (int64_t)(8 + p0 / 2) * 128, src + sub * (kSPlane / 2), kSPlane / 2);
+              }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the unit may be refilled once the copy engine has read it
+            mbar_arrive(&st_empty[slot]);
+            if (++slot == kSUnits) { slot = 0; ph ^= 1u; }
+          }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             // all stores complete before the CTA retires
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == kSEpiWarps) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ourselves (alignment slack + static barriers)
 
 struct TPlan {
@@ -908,6 +1197,11 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   p->unit_bytes = p->Npad * 128;
   p->n_units = gen ? c.planes : (c.in.packed ? c.K : c.in.spp * c.K * c.planes);
   if (p->n_stage > kXMaxStage) return false;
+  // narrow-input, wide-output layers (the HBM-bound third conv of a block) take the staged epilogue
+  static const bool no_stage = getenv("NSC_PLANE_NOSTAGE") != nullptr;
+  p->staged = (!gen && c.in.packed && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage) ? 1 : 0;
+  const size_t stg_total = p->staged ? (size_t)kSUnits * c.planes * kSPlane : 0;
+  const size_t budget = kSmemBudget - stg_total;
   // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
   for (int mt = (Lout % 256 == 0 && c.stride == 1) ? 2 : 1; mt >= 1; --mt) {
     p->mt = mt;
@@ -916,14 +1210,14 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     const size_t a1 = (size_t)p->n_stage * p->stage_bytes;
     const size_t wall = (size_t)p->n_units * p->unit_bytes;
     if (2 * mt * p->Npad > 512) continue;
-    if (p->n_units <= kXMaxW && 2 * a1 + wall <= kSmemBudget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
-    else if (p->n_units <= kXMaxW && a1 + wall <= kSmemBudget) { p->kbuf = 1; p->resident = 1; p->wslots = p->n_units; }
-    else if (2 * a1 + 4ull * p->unit_bytes <= kSmemBudget) { p->kbuf = 2; p->resident = 0; }
-    else if (a1 + 3ull * p->unit_bytes <= kSmemBudget) { p->kbuf = 1; p->resident = 0; }
+    if (p->n_units <= kXMaxW && 2 * a1 + wall <= budget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
+    else if (2 * a1 + 4ull * p->unit_bytes <= budget) { p->kbuf = 2; p->resident = 0; }
+    else if (p->n_units <= kXMaxW && a1 + wall <= budget) { p->kbuf = 1; p->resident = 1; p->wslots = p->n_units; }
+    else if (a1 + 3ull * p->unit_bytes <= budget) { p->kbuf = 1; p->resident = 0; }
     else continue;
-    if (p->n_stage * p->kbuf > kXMaxStage) { if (p->kbuf == 2 && !p->resident && a1 + 3ull * p->unit_bytes <= kSmemBudget) p->kbuf = 1; else continue; }
+    if (p->n_stage * p->kbuf > kXMaxStage) { if (p->kbuf == 2 && !p->resident && a1 + 3ull * p->unit_bytes <= budget) p->kbuf = 1; else continue; }
     if (!p->resident) {
-      size_t ws = (kSmemBudget - (size_t)p->kbuf * a1) / p->unit_bytes;
+      size_t ws = (budget - (size_t)p->kbuf * a1) / p->unit_bytes;
       if (ws > (size_t)kXMaxW) ws = kXMaxW;
       if (ws > (size_t)p->n_units) ws = p->n_units;
       p->wslots = (int)ws;
@@ -941,13 +1235,14 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     if (c.out.packed) needed = 4;
     p->zero_from = written;
     p->zero_to = needed > written ? needed : written;
+    if (p->staged && (p->zero_from != p->zero_to || p->n_stage != 1)) p->staged = 0;   // (never for the codec's shapes)
     return true;
   }
   return false;
 }
 
 size_t x_smem_bytes(const XParams& p) {
-  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.unit_bytes;
+  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.unit_bytes + (p.staged ? (size_t)kSUnits * p.planes * kSPlane : 0);
 }
 
 }  // namespace
@@ -1035,6 +1330,7 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
   const size_t smem = x_smem_bytes(p);
   if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
   double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_payload_bytes(c.in));
@@ -1044,6 +1340,7 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   ProfScope prof(st, name, 2.0 * macs, bytes);
   const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   if (c.kind == PK_GEN) plane_x_kernel<true><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
+  else if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
   else plane_x_kernel<false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;
