@@ -72,6 +72,9 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   for (int i = 0; i < PB_COUNT; ++i) { pl.buf_off[i] = off; off += pl.buf[i].frame_bytes; }
   pl.act_bytes_per_frame = off;
 
+  // narrow -> narrow convs (20 -> 20): taps-in-N by default; the tap-shift kernel is within 5 % here (measured 5.6 vs 5.3 ms per
+  // step: nine N = 32 MMAs per K step issue-bound vs the tap-sum epilogue) and can be selected for experiments
+  static const int kNarrowKind = getenv("NSC_PLANE_NARROW_X") ? PK_X : PK_T;
   int layer = 0;   // creation-order layer index (same walk as Walker::encoder / decoder)
   auto add = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int kind, int Lin, int Cin, int Cout, int K, int dil, int stride,
                  int act, int in, int out, int res, int res_mode, int post, int shuffle) {
@@ -98,11 +101,11 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
       const int post = flat ? NSC_ACT_NONE : NSC_ACT_LRELU;
       if (vec_in && i == 0) {
         add(v, vl, PK_GEN, Ls, 1, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, -1, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
-        add(v, vl, PK_T, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
         add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, -1, RES_ADD_BCAST, post, 1);
       } else {
         add(v, vl, PK_T, Ls, Cw, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, cur, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
-        add(v, vl, PK_T, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
         add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, cur, RES_ADD, post, 1);
       }
       cur = out;

@@ -494,13 +494,14 @@ struct XParams {
   int tmem_cols;
   int zero_from, zero_to;    // output chunks the epilogue must clear (K padding the consumer will read)
   int staged;                // plane_xs_kernel: epilogue through shared-memory units and bulk copies
+  int n_iss;                 // MMA-issuing threads (1, or one per M tile)
   int64_t B, n_tiles;
 };
 
 constexpr int kXEpiGroups = 3;                   // epilogue warps per TMEM lane quarter (each takes every third 16-column batch)
 constexpr int kXEpiWarps = 4 * kXEpiGroups, kXGenWarps = 4;
-constexpr int kXThreadsX = (kXEpiWarps + 3) * 32;                 // + MMA issuer, A loader, W loader
-constexpr int kXThreadsGen = (kXEpiWarps + 3 + kXGenWarps) * 32;   // + Toeplitz producers
+constexpr int kXThreadsX = (kXEpiWarps + 4) * 32;                 // + MMA issuer, A loader, W loader, second MMA issuer
+constexpr int kXThreadsGen = (kXEpiWarps + 4 + kXGenWarps) * 32;   // + Toeplitz producers (the second issuer is the last warp)
 constexpr int kGenSeg = 336;                                       // staged input samples per tile: 256 + 63 taps, rounded up
 constexpr int kXMaxStage = 16, kXMaxW = 40;
 
@@ -513,6 +514,171 @@ __device__ __forceinline__ void pt_load_raw(const PlaneTensor& t, const uint8_t*
   const uint8_t* r = img + (int64_t)(g >> 3) * sb + (int64_t)row * 128 + ((((uint32_t)g & 7u) ^ sw) << 4);
   hi = __ldg(reinterpret_cast<const uint4*>(r));
   lo = t.planes == 2 ? __ldg(reinterpret_cast<const uint4*>(r + (int64_t)t.spp * sb)) : make_uint4(0, 0, 0, 0);
+}
+
+
+// ---- MMA issue (shared by plane_x_kernel and plane_xs_kernel) ------------------------------------------------------
+// One elected thread per issuing warp.  With two M tiles per work unit there are TWO issuing threads, one per M tile
+// (independent accumulators): descriptor arithmetic and the tcgen05.mma issue itself cost ~50-90 cycles per instruction
+// from a single thread, more than the 44-60 cycles the narrow MMAs of this codec take on the tensor pipe.
+struct XBars {
+  uint64_t *a_full, *a_empty, *w_full, *w_empty, *acc_full, *acc_empty;
+};
+
+struct XIssue {
+  uint32_t d, idesc;                // this issuer's first accumulator
+  int nmt;                          // M tiles this thread issues for (accumulators Npad columns apart, A rows 128 apart)
+  uint32_t npad;
+  uint32_t w_lo_base, unit_lo;
+  uint32_t ws, wph, u;              // weight ring slot / phase, unit counter inside the tile
+  bool resident, w_ready;
+  int wslots;
+  const XBars* b;
+  __device__ __forceinline__ uint32_t wait_w() {
+    if (resident) {
+      if (!w_ready) { mbar_wait(&b->w_full[u], 0u); tc_fence_after(); }
+      return w_lo_base + u * unit_lo;
+    }
+    mbar_wait(&b->w_full[ws], wph);
+    tc_fence_after();
+    return w_lo_base + ws * unit_lo;
+  }
+  __device__ __forceinline__ void done_w() {
+    if (!resident) {
+      umma_commit(&b->w_empty[ws]);
+      if (++ws == (uint32_t)wslots) { ws = 0; wph ^= 1u; }
+    }
+    ++u;
+  }
+};
+
+template <int NKS>
+__device__ __forceinline__ void x_issue_mt(const XIssue& x, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
+  issue_ks<NKS>(x.d, a_lo, b_lo, x.idesc, accum);
+  if (x.nmt == 2) issue_ks<NKS>(x.d + x.npad, a_lo + ((128u * 128u) >> 4), b_lo, x.idesc, accum);
+}
+
+// narrow (packed [hi | lo]) input: per tap hi*W_hi, hi*W_lo, lo*W_hi
+template <int NKS>
+__device__ __forceinline__ void x_issue_packed(XIssue& x, const XParams& p, uint32_t a_lo0) {
+  uint32_t accum = 0;
+  for (int t = 0; t < p.K; ++t) {
+    const uint32_t b_lo = x.wait_w();
+    const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
+    x_issue_mt<NKS>(x, a_lo, b_lo, accum);
+    if (p.planes == 2) {
+      x_issue_mt<NKS>(x, a_lo, b_lo + 4u, 1u);
+      x_issue_mt<NKS>(x, a_lo + 4u, b_lo, 1u);
+    }
+    accum = 1;
+    x.done_w();
+  }
+}
+
+// one 64-channel slab of a wide input: per tap the W_hi unit meets the hi and the lo plane, the W_lo unit the hi plane
+template <int NKS>
+__device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s, uint32_t a_stage0, uint32_t stage_lo, uint32_t kb,
+                                             uint32_t a_phase, uint32_t& waited, uint32_t& accum) {
+  const int spp = p.in.spp;
+  auto wait_stage = [&](int stage) {
+    if (!((waited >> stage) & 1u)) {
+      mbar_wait(&x.b->a_full[kb + stage], a_phase);
+      tc_fence_after();
+      waited |= 1u << stage;
+    }
+  };
+  for (int t = 0; t < p.K; ++t) {
+    int sub = 0, rowoff;
+    if (p.stride == 1) rowoff = 8 + t * p.dil - p.padL;
+    else { const int tp = t - p.padL; sub = tp & 1; rowoff = 8 + (tp - sub) / 2; }
+    const int st_hi = pt_slab_index(p.in, sub, 0, s);
+    const uint32_t a_hi = a_stage0 + (uint32_t)st_hi * stage_lo + (uint32_t)rowoff * 8u;
+    const uint32_t a_lo_pl = a_hi + (uint32_t)spp * stage_lo;     // the lo plane's stage is spp slabs further
+    {
+      const uint32_t b_lo = x.wait_w();
+      wait_stage(st_hi);
+      x_issue_mt<NKS>(x, a_hi, b_lo, accum);
+      accum = 1;
+      if (p.planes == 2) { wait_stage(st_hi + spp); x_issue_mt<NKS>(x, a_lo_pl, b_lo, 1u); }
+      x.done_w();
+    }
+    if (p.planes == 2) {
+      const uint32_t b_lo = x.wait_w();
+      x_issue_mt<NKS>(x, a_hi, b_lo, 1u);
+      x.done_w();
+    }
+  }
+}
+
+__device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer, uint8_t* sA, uint8_t* sW, uint32_t tmem, const XBars& bars) {
+  const uint32_t mt_step = (128u * 128u) >> 4;
+  const int m0 = p.n_iss == 2 ? issuer : 0;                       // first M tile of this thread
+  const uint32_t a_lo_base = desc_lo(smem_u32(sA)) + (uint32_t)m0 * mt_step;
+  const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4;
+  const int acc_cols = p.mt * p.Npad;
+  XIssue x;
+  x.idesc = make_idesc_f16(p.Npad);
+  x.w_lo_base = desc_lo(smem_u32(sW));
+  x.unit_lo = (uint32_t)p.unit_bytes >> 4;
+  x.ws = 0; x.wph = 0; x.u = 0;
+  x.resident = p.resident != 0;
+  x.w_ready = false;
+  x.wslots = p.wslots;
+  x.b = &bars;
+  x.nmt = p.n_iss == 2 ? 1 : p.mt;
+  x.npad = (uint32_t)p.Npad;
+  uint32_t it = 0, kb = 0, a_phase = 0;
+  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const uint32_t acc_i = it & 1u;
+    mbar_wait(&bars.acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+    tc_fence_after();
+    x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)(m0 * p.Npad);
+    x.u = 0;
+    if (gen) {
+      uint32_t accum = 0;
+      for (int wp = 0; wp < p.planes; ++wp) {
+        const uint32_t b_lo = x.wait_w();
+        for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
+          if (wp == 0) { mbar_wait(&bars.a_full[kb + ap], a_phase); tc_fence_after(); }
+          for (int m = 0; m < x.nmt; ++m)
+            issue_n(p.ksteps, x.d + (uint32_t)m * x.npad, a_lo_base + (kb + (uint32_t)ap) * stage_lo + (uint32_t)m * mt_step, b_lo, x.idesc, accum);
+          accum = 1;
+        }
+        x.done_w();
+      }
+      for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + ap]);
+    } else if (p.in.packed) {
+      mbar_wait(&bars.a_full[kb], a_phase);
+      tc_fence_after();
+      const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
+      switch (p.ksteps) {
+        case 2: x_issue_packed<2>(x, p, a_lo0); break;
+        case 1: x_issue_packed<1>(x, p, a_lo0); break;
+        case 3: x_issue_packed<3>(x, p, a_lo0); break;
+        default: x_issue_packed<4>(x, p, a_lo0); break;
+      }
+      umma_commit(&bars.a_empty[kb]);
+    } else {
+      const int nsub = p.in.deint ? 2 : 1;
+      uint32_t waited = 0, accum = 0;
+      for (int s = 0; s < p.in.spp; ++s) {
+        const int nks = min(4, p.ksteps - 4 * s);
+        const uint32_t a0 = a_lo_base + kb * stage_lo;
+        switch (nks) {
+          case 4: x_issue_slab<4>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          case 3: x_issue_slab<3>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          case 2: x_issue_slab<2>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          default: x_issue_slab<1>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+        }
+        for (int sub = 0; sub < nsub; ++sub)
+          for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
+      }
+    }
+    umma_commit(&bars.acc_full[acc_i]);
+    x.w_ready = true;
+    if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) a_phase ^= 1u; }
+    else a_phase ^= 1u;
+  }
 }
 
 template <bool kGen>
@@ -529,12 +695,14 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   uint8_t* sA = smem;
   uint8_t* sW = smem + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
   const int acc_cols = p.mt * p.Npad;
+  const int n_iss = p.n_iss;           // issuing threads: one, or one per M tile
+  constexpr int kIssuer1 = kGen ? kXEpiWarps + 3 + kXGenWarps : kXEpiWarps + 3;
 
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kXEpiWarps); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], n_iss); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_iss); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], kXEpiWarps); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   if (warp == kXEpiWarps) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
@@ -640,109 +808,12 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc_i]);
     }
-  } else if (warp == kXEpiWarps) {
-    // =========================== MMA issuer ===========================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(p.Npad);
-      const uint32_t mt_step = (128u * 128u) >> 4;
-      const uint32_t a_lo_base = desc_lo(smem_u32(sA)), w_lo_base = desc_lo(smem_u32(sW));
-      const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4, unit_lo = (uint32_t)p.unit_bytes >> 4;
-      const int planes = p.planes, mt = p.mt, spp = p.in.spp;
-      const bool resident = p.resident != 0;
-      uint32_t it = 0, ws = 0, wph = 0, kb = 0, a_phase = 0;
-      bool w_ready = false;               // resident weights: waited for once
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc_i = it & 1u;
-        mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem + acc_i * (uint32_t)acc_cols;
-        uint32_t waited = 0, accum = 0;
-        uint32_t u = 0;
-        auto wait_stage = [&](int stage) {
-          if (!((waited >> stage) & 1u)) {
-            mbar_wait(&a_full[kb + stage], a_phase);
-            tc_fence_after();
-            waited |= 1u << stage;
-          }
-        };
-        auto wait_w = [&]() -> uint32_t {      // descriptor (low word) of the next weight unit
-          if (resident) {
-            if (!w_ready) { mbar_wait(&w_full[u], 0u); tc_fence_after(); }
-            return w_lo_base + u * unit_lo;
-          }
-          mbar_wait(&w_full[ws], wph);
-          tc_fence_after();
-          return w_lo_base + ws * unit_lo;
-        };
-        auto done_w = [&]() {
-          if (!resident) {
-            umma_commit(&w_empty[ws]);
-            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
-          }
-          ++u;
-        };
-        auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
-          issue_n(nks, d0, a_lo, b_lo, idesc, accum);
-          if (mt == 2) issue_n(nks, d0 + (uint32_t)p.Npad, a_lo + mt_step, b_lo, idesc, accum);
-          accum = 1;
-        };
-        if (kGen) {
-          for (int wp = 0; wp < planes; ++wp) {
-            const uint32_t b_lo = wait_w();
-            for (int ap = 0; ap < (wp == 0 ? planes : 1); ++ap) {
-              wait_stage(ap);
-              issue(a_lo_base + (kb + (uint32_t)ap) * stage_lo, b_lo, p.ksteps);
-            }
-            done_w();
-          }
-          for (int ap = 0; ap < planes; ++ap) umma_commit(&a_empty[kb + ap]);
-        } else if (p.in.packed) {
-          wait_stage(0);
-          const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
-          for (int t = 0; t < p.K; ++t) {
-            const uint32_t b_lo = wait_w();
-            const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
-            issue(a_lo, b_lo, p.ksteps);
-            if (planes == 2) {
-              issue(a_lo, b_lo + 4u, p.ksteps);
-              issue(a_lo + 4u, b_lo, p.ksteps);
-            }
-            done_w();
-          }
-          umma_commit(&a_empty[kb]);
-        } else {
-          const int nsub = p.in.deint ? 2 : 1;
-          for (int s = 0; s < spp; ++s) {
-            const int nks = min(4, p.ksteps - 4 * s);
-            for (int t = 0; t < p.K; ++t) {
-              int sub = 0, rowoff;
-              if (p.stride == 1) rowoff = 8 + t * p.dil - p.padL;
-              else { const int tp = t - p.padL; sub = tp & 1; rowoff = 8 + (tp - sub) / 2; }
-              const int st_hi = pt_slab_index(p.in, sub, 0, s);
-              const uint32_t a_hi = a_lo_base + (kb + (uint32_t)st_hi) * stage_lo + (uint32_t)rowoff * 8u;
-              const uint32_t a_lo_pl = a_hi + (uint32_t)spp * stage_lo;     // the lo plane's stage is spp slabs further
-              {   // W_hi unit: hi * W_hi and lo * W_hi while it is resident
-                const uint32_t b_lo = wait_w();
-                wait_stage(st_hi);
-                issue(a_hi, b_lo, nks);
-                if (planes == 2) { wait_stage(st_hi + spp); issue(a_lo_pl, b_lo, nks); }
-                done_w();
-              }
-              if (planes == 2) {   // W_lo unit: hi * W_lo
-                const uint32_t b_lo = wait_w();
-                issue(a_hi, b_lo, nks);
-                done_w();
-              }
-            }
-            for (int sub = 0; sub < nsub; ++sub)
-              for (int ap = 0; ap < planes; ++ap) umma_commit(&a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
-          }
-        }
-        umma_commit(&acc_full[acc_i]);
-        w_ready = true;
-        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) a_phase ^= 1u; }
-        else a_phase ^= 1u;
-      }
+  } else if (warp == kXEpiWarps || warp == kIssuer1) {
+    // =========================== MMA issuers ===========================
+    const int issuer = warp == kXEpiWarps ? 0 : 1;
+    if (issuer < n_iss && elect_one()) {
+      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty};
+      x_issuer(p, kGen, issuer, sA, sW, tmem, bars);
     }
   } else if (warp == kXEpiWarps + 1) {
     // =========================== A loader (bulk copies of plane tiles) ===========================
@@ -862,7 +933,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
 //   unit = (M tile, 64-channel output slab) x planes; ring of kSUnits units:  residual loader -> epilogue -> storer.
 // ================================================================================================
 constexpr int kSEpiGroups = 4, kSEpiWarps = 4 * kSEpiGroups;
-constexpr int kSThreads = (kSEpiWarps + 5) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer
+constexpr int kSThreads = (kSEpiWarps + 6) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer, second MMA issuer
 constexpr int kSUnits = 3;
 constexpr int kSPlane = 128 * 128;                 // one plane of one unit
 
@@ -890,9 +961,9 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
 
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kSEpiWarps); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], p.n_iss); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], p.n_iss); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], p.n_iss); mbar_init(&acc_empty[i], kSEpiWarps); }
     for (int i = 0; i < kSUnits; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_done[i], kSEpiWarps); mbar_init(&st_empty[i], 1); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -987,58 +1058,12 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc_i]);
     }
-  } else if (warp == kSEpiWarps) {
-    // =========================== MMA issuer ===========================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(p.Npad);
-      const uint32_t mt_step = (128u * 128u) >> 4;
-      const uint32_t a_lo_base = desc_lo(smem_u32(sA)), w_lo_base = desc_lo(smem_u32(sW));
-      const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4, unit_lo = (uint32_t)p.unit_bytes >> 4;
-      const int planes = p.planes, mt = p.mt;
-      const bool resident = p.resident != 0;
-      uint32_t it = 0, ws = 0, wph = 0, kb = 0, a_phase = 0;
-      bool w_ready = false;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc_i = it & 1u;
-        mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem + acc_i * (uint32_t)acc_cols;
-        uint32_t accum = 0;
-        auto issue = [&](uint32_t a_lo, uint32_t b_lo, int nks) {
-          issue_n(nks, d0, a_lo, b_lo, idesc, accum);
-          if (mt == 2) issue_n(nks, d0 + (uint32_t)p.Npad, a_lo + mt_step, b_lo, idesc, accum);
-          accum = 1;
-        };
-        mbar_wait(&a_full[kb], a_phase);
-        tc_fence_after();
-        const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
-        for (int t = 0; t < p.K; ++t) {
-          uint32_t b_lo;
-          if (resident) {
-            if (!w_ready) { mbar_wait(&w_full[t], 0u); tc_fence_after(); }
-            b_lo = w_lo_base + (uint32_t)t * unit_lo;
-          } else {
-            mbar_wait(&w_full[ws], wph);
-            tc_fence_after();
-            b_lo = w_lo_base + ws * unit_lo;
-          }
-          const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
-          issue(a_lo, b_lo, p.ksteps);
-          if (planes == 2) {
-            issue(a_lo, b_lo + 4u, p.ksteps);
-            issue(a_lo + 4u, b_lo, p.ksteps);
-          }
-          if (!resident) {
-            umma_commit(&w_empty[ws]);
-            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
-          }
-        }
-        umma_commit(&a_empty[kb]);
-        umma_commit(&acc_full[acc_i]);
-        w_ready = true;
-        if (p.kbuf == 2) { kb ^= 1u; if (kb == 0) a_phase ^= 1u; }
-        else a_phase ^= 1u;
-      }
+  } else if (warp == kSEpiWarps || warp == kSEpiWarps + 5) {
+    // =========================== MMA issuers (one per M tile) ===========================
+    const int issuer = warp == kSEpiWarps ? 0 : 1;
+    if (issuer < p.n_iss && elect_one()) {
+      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty};
+      x_issuer(p, false, issuer, sA, sW, tmem, bars);
     }
   } else if (warp == kSEpiWarps + 1) {
     // =========================== A loader ===========================
@@ -1099,7 +1124,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
           }
       }
     }
-  } else {
+  } else if (warp == kSEpiWarps + 4) {
     // =========================== storer ===========================
     if (elect_one()) {
       const int64_t osb = pt_slab_bytes(p.out);
@@ -1236,6 +1261,13 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     p->zero_from = written;
     p->zero_to = needed > written ? needed : written;
     if (p->staged && (p->zero_from != p->zero_to || p->n_stage != 1)) p->staged = 0;   // (never for the codec's shapes)
+    {
+      // one issuing thread per M tile where the issue rate, not HBM, bounds the layer (measured); the staged layers are HBM-bound
+      static const int knob = [] { const char* e = getenv("NSC_PLANE_ISSUERS"); return e ? atoi(e) : 0; }();
+      p->n_iss = (p->mt == 2 && !p->staged) ? 2 : 1;
+      if (knob == 1) p->n_iss = 1;
+      if (knob == 2 && p->mt == 2) p->n_iss = 2;
+    }
     return true;
   }
   return false;
