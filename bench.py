@@ -378,7 +378,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--frames', type=int, default=32768, help='frames per GPU per step')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--cpu-frames', type=int, default=1024, help='bounded CPU-baseline sample (frames)')
+    ap.add_argument('--cpu-frames', type=int, default=8192, help='bounded CPU-baseline sample (frames)')
     ap.add_argument('--ref-frames', type=int, default=512, help='frames per step of the reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='cq2', choices=['cq2', 'train'], help="cq2 = headline encode+decode; train = training step")

@@ -250,6 +250,38 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
 int nsc_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, float lr, int64_t t, float beta1,
                   float beta2, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Either side of the codec pass: framing, overlap-add, utterance-level filters, code packing
+ * ---------------------------------------------------------------------------------------------- */
+/* utterance_to_segment (utilities.py:25-39): frames of 512 at hop 480 starting at `offset` (cmrl.py:695 uses 256 on the
+ *   LPC path); count = len(range(0, T - offset - 512, 480)) = nsc_segment_count(T - offset).  post_window = 1 copies,
+ *   0 multiplies by the trapezoid-Hann `the_window`.  segments (N, 512). */
+int64_t nsc_segment_count(int64_t T);
+int nsc_utterance_to_segment(const float* utterance, int64_t T, int64_t offset, int32_t post_window, float* segments,
+                             void* stream);
+/* The 1024-sample analysis windows lpc_analysis_at_test cuts at hop 512 out of the FLATTENED (N, 512) hop-480 frame
+ *   matrix (lpc_utilities.py:98-104; the 32 repeated samples per frame boundary are reproduced).  windows (Nw, 1024),
+ *   Nw = nsc_lpc_window_count(nsc_segment_count(T)); feed them to nsc_lpc_analyze. */
+int64_t nsc_lpc_window_count(int64_t n_segments);
+int nsc_lpc_windows(const float* utterance, int64_t T, float* windows, void* stream);
+/* hann_process + overlap-add (utilities.py:7-22; cmrl.py:595-597, :710-716): out[480 j : 480 j + 512] += w_j * frames[j]
+ *   for j < n_used, w_j = first / last / middle window chosen by (j, seg_amount) exactly like hann_process(seg, j, seg_amount)
+ *   (the LPC path passes seg_amount = N but only runs j < N - 2, so its last window is never used).  out (out_len). */
+int nsc_overlap_add(const float* frames, int64_t n_used, int64_t seg_amount, float* out, int64_t out_len, void* stream);
+/* Zero-state second-order recursive filter over n_signals signals of length T (audiolazy ZFilter call semantics), float64
+ *   arithmetic as a chunked parallel scan: y[n] = b0 x[n] + b1 x[n-1] + b2 x[n-2] - a1 y[n-1] - a2 y[n-2]; a[0] must be 1.
+ *   highpass_filter / empha_filter / 1/empha_filter (lpc_utilities.py:8-11, cmrl.py:671, :735) are instances.
+ *   y_f32 and/or y_f64 receive the result. */
+int64_t nsc_iir_workspace_bytes(int64_t T, int64_t n_signals);
+int nsc_iir_biquad(const float* x, int64_t T, int64_t n_signals, const double* b_host, const double* a_host, float* y_f32,
+                   double* y_f64, void* workspace, int64_t workspace_bytes, void* stream);
+/* Fixed-width packing of hard codes: rows of L indices (< 2^bits) -> rows of nsc_packed_row_bytes(L, bits) bytes,
+ *   little-endian bit order.  (The reference has no bitstream; it estimates bitrate from entropy,
+ *   loss_terms_and_measures.py:63-67.) */
+int32_t nsc_packed_row_bytes(int32_t L, int32_t bits);
+int nsc_pack_codes(const uint8_t* idx, int64_t rows, int32_t L, int32_t bits, uint8_t* packed, void* stream);
+int nsc_unpack_codes(const uint8_t* packed, int64_t rows, int32_t L, int32_t bits, uint8_t* idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

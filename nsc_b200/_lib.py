@@ -76,6 +76,16 @@ SIGNATURES = {
     "nsc_train_forward": (_i32, [_cfgp, _i32, _ppv, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _ppv, _ppv, _vp, _i64, _vp]),
     "nsc_train_backward": (_i32, [_cfgp, _i32, _ppv, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _vp, _vp, C.POINTER(_f32), C.POINTER(_f32),
                                   C.POINTER(_f32), _i64, _ppv, C.POINTER(_i32), _ppv, _vp, _vp, _i64, _vp]),
+    "nsc_segment_count": (_i64, [_i64]),
+    "nsc_utterance_to_segment": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
+    "nsc_lpc_window_count": (_i64, [_i64]),
+    "nsc_lpc_windows": (_i32, [_vp, _i64, _vp, _vp]),
+    "nsc_overlap_add": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp]),
+    "nsc_iir_workspace_bytes": (_i64, [_i64, _i64]),
+    "nsc_iir_biquad": (_i32, [_vp, _i64, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _vp, _i64, _vp]),
+    "nsc_packed_row_bytes": (_i32, [_i32, _i32]),
+    "nsc_pack_codes": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "nsc_unpack_codes": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "nsc_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _i64, _f32, _f32, _f32, _vp]),
 }
 

@@ -218,3 +218,32 @@ def test_fp32_vs_fp64_oracle_noise_floor():
     oc.ps._cursor = 0
     f64 = oc.encoder(x.double())
     assert rel_err(f32.numpy(), f64.numpy()) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- framing
+def test_framing_oracle_counts_windows_and_filters():
+    from oracle import ref_framing as rf
+    # frame count of utilities.py:26: len(range(0, T - 512, 480))
+    for T, n in ((512, 0), (513, 1), (992, 1), (993, 2), (48000, 99)):
+        assert rf.utterance_to_segment(np.zeros(T), True).shape == (n, 512)
+    the_w, first_w, last_w = rf.windows()
+    assert the_w.shape == first_w.shape == last_w.shape == (512,)
+    assert the_w[0] == 0.0 and the_w[31] == 1.0 and the_w[480] == 1.0 and the_w[511] == 0.0     # hanning(63) halves
+    assert np.all(first_w[:480] == 1) and np.all(last_w[32:] == 1)
+    # overlap-add of the middle windows: hanning(63)[k] + hanning(63)[31 + k] = 1 only at the ends -> seam error < 6 %
+    seam = the_w[480:] + the_w[:32]
+    assert abs(seam - 1).max() < 0.06
+    # the flatten quirk of lpc_analysis_at_test: window 1 starts at frame 1 sample 0 = utterance sample 480
+    x = np.arange(5000, dtype=np.float64)
+    w = rf.lpc_windows_at_test(rf.utterance_to_segment(x, True))
+    assert w.shape == (len(range(0, 5000 - 512, 480)) - 2, 1024)
+    assert w[1, 0] == 480 and w[0, 512] == 480 and w[0, 511] == 511
+    # filters: the asymmetric numerator taps (0.989502 vs 0.989592, lpc_utilities.py:10) leave a DC gain of
+    # 9e-5 / 2.44e-4 = 0.3689 instead of 0 -- a reference quirk that is reproduced, not repaired
+    hp = rf.highpass_filter(np.ones(20000))
+    assert abs(hp[-1] - 9e-5 / 2.44e-4) < 1e-6
+    y = rf.de_empha_filter(rf.empha_filter(x))
+    assert np.allclose(y, x)
+    idx = np.array([[1, 2, 3, 31, 0, 17, 8, 9]], dtype=np.uint8)
+    pk = rf.pack_bits(idx, 5)
+    assert pk.shape == (1, 5) and pk[0, 0] == (1 | (2 << 5)) & 0xFF
