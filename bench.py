@@ -317,6 +317,81 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_corpus(args):
+    """Secondary workload (BASELINE.json configs[4]): an hour-scale synthetic corpus, wav -> hard codes (packed records) -> wav,
+    through nsc_b200.pipeline (cmrl.py:666-737 batched): host signals in, packed records + synthesized signals out, every step
+    (normalisation, filters, framing, LPC analysis, CQ pass, overlap-add, de-emphasis, bit packing, H2D/D2H) inside the timed
+    region.  Utterances are sharded across ranks."""
+    import torch
+    import torch.distributed as dist
+    from nsc_b200 import _lib, codec, pipeline
+    from nsc_b200.sharding import max_over_ranks
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    cfg = codec.CodecConfig(precision=args.precision)
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
+    n_utt, T = args.utterances, int(args.utt_seconds * 16000)
+    x_np, _ = synth_audio(64, seed=4321 + rank)
+    base = np.tile(x_np.reshape(-1), -(-T * 8 // x_np.size))        # a few distinct utterances, tiled
+    host = [torch.from_numpy(np.ascontiguousarray(base[(i % 8) * 4000:(i % 8) * 4000 + T])).pin_memory() for i in range(n_utt)]
+    out_host = {}
+
+    def step():
+        sigs = [h.to(dev, non_blocking=True) for h in host]
+        res = pipeline.code_utterances(cm, sigs, the_share=False, pack=True)
+        rec = torch.cat([r['records'] for r in res])
+        syn = torch.cat([r['synthesized'] for r in res])
+        for k, t in (('rec', rec), ('syn', syn)):
+            if k not in out_host:
+                out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            out_host[k].copy_(t, non_blocking=True)
+        return sum(r['n_frames'] for r in res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        frames = step()
+    barrier()
+    l0 = lib.nsc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t = max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    launches = lib.nsc_launch_count() - l0
+    if rank == 0:
+        audio_s = n_utt * world * args.utt_seconds
+        v = audio_s * args.steps / t
+        print(json.dumps({
+            "metric": "seconds of 16 kHz audio coded per second (x real-time), corpus wav -> packed hard codes -> wav, end to end",
+            "value": v, "unit": "x real-time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32-equivalent convs (fp16 hi/lo on tensor cores); filters / LPC f64", "data": "synthetic",
+            "config": {"workload": f"corpus: {n_utt} utterances x {args.utt_seconds:g} s per GPU ({audio_s / 3600:.2f} h in total), "
+                                   "cq2 codec, hard codes packed to 336-byte frame records, utterance filters + framing + overlap-add on the GPU",
+                       "frames_per_gpu_per_step": int(frames), "conv_precision": args.precision,
+                       "l2_policy": "inputs larger than L2", "parallelism": f"dp{world} (utterances sharded by rank, no collective)"},
+            "e2e": {"value": v, "unit": "x real-time", "h2d_bytes_per_step": int(n_utt * T * 4 * world),
+                    "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in out_host.values()) * world)},
+            "gpu_launches": int(launches), "record_kbps": 336 * 8 * 16000 / 480 / 1000.0}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_train(args):
     """Secondary workload (BASELINE.json configs[3]): full CQ training step -- forward keeping activations, backward of
     every kernel, histogram + gradient all-reduce (NCCL), TF1 Adam -- `_finetuning_lpc`-shaped loss, 128 frames per GPU."""
@@ -381,7 +456,10 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=8192, help='bounded CPU-baseline sample (frames)')
     ap.add_argument('--ref-frames', type=int, default=512, help='frames per step of the reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='cq2', choices=['cq2', 'train'], help="cq2 = headline encode+decode; train = training step")
+    ap.add_argument('--workload', default='cq2', choices=['cq2', 'train', 'corpus'],
+                    help="cq2 = headline encode+decode; train = training step; corpus = wav -> packed codes -> wav")
+    ap.add_argument('--utterances', type=int, default=360, help='corpus workload: utterances per GPU')
+    ap.add_argument('--utt-seconds', type=float, default=10.0, help='corpus workload: seconds per utterance')
     ap.add_argument('--train-batch', type=int, default=128, help='frames per GPU per training step')
     ap.add_argument('--precision', default='tc_f16x3', choices=['fp32', 'tc_f16x3', 'tc_f16'],
                     help="conv arithmetic: fp32 FFMA, tcgen05 fp16 hi/lo split (fp32-class, default), tcgen05 fp16 (reduced)")
@@ -392,6 +470,8 @@ def main():
         run_reference(args)
     elif args.workload == 'train':
         run_train(args)
+    elif args.workload == 'corpus':
+        run_corpus(args)
     else:
         run_ours(args)
 

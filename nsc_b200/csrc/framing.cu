@@ -95,21 +95,26 @@ __global__ void iir_pass1_kernel(const float* __restrict__ x, int64_t T, int64_t
   }
 }
 
-// carry[c] = state entering chunk c (c >= 1):  carry[c] = A^Lc carry[c-1] + z[c-1]   (A^Lc applied by Lc homogeneous steps)
+// carry[c] = state entering chunk c:  carry[c + 1] = M carry[c] + z[c]  with  M = A^Lc  (2 x 2, built once per thread by running the
+// homogeneous recursion on the two basis vectors), so the sequential part is 4 FMAs per chunk, not Lc steps
 __global__ void iir_pass2_kernel(int64_t T, int64_t n_sig, Biquad f, double* __restrict__ state, int64_t n_chunks) {
   const int64_t sig = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (sig >= n_sig) return;
+  (void)T;
+  double m11 = 1.0, m21 = 0.0, m12 = 0.0, m22 = 1.0;      // columns = images of (1,0) and (0,1)
+  for (int n = 0; n < kScanChunk; ++n) {
+    const double h = -f.a1 * m11 - f.a2 * m21; m21 = m11; m11 = h;
+    const double g = -f.a1 * m12 - f.a2 * m22; m22 = m12; m12 = g;
+  }
   double* st = state + sig * n_chunks * 2;
   double c1 = 0.0, c2 = 0.0;      // state entering the current chunk
   for (int64_t c = 0; c < n_chunks; ++c) {
     const double z1 = st[2 * c], z2 = st[2 * c + 1];
     st[2 * c] = c1;
     st[2 * c + 1] = c2;
-    const int64_t len = (c + 1) * kScanChunk <= T ? kScanChunk : T - c * kScanChunk;
-    double h1 = c1, h2 = c2;
-    for (int64_t n = 0; n < len; ++n) { const double h = -f.a1 * h1 - f.a2 * h2; h2 = h1; h1 = h; }
-    c1 = h1 + z1;
-    c2 = h2 + z2;
+    const double n1 = m11 * c1 + m12 * c2 + z1, n2 = m21 * c1 + m22 * c2 + z2;   // (only full chunks are ever carried out of)
+    c1 = n1;
+    c2 = n2;
   }
 }
 

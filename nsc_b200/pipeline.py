@@ -1,0 +1,72 @@
+"""Utterance-level collaborative-quantisation coding: the loop of CMRL.cmrl_eval_lpc (cmrl.py:666-737) with every step on
+the GPU and the per-frame ``sess.run`` replaced by ONE batched pass over the frames of all utterances.
+
+    per utterance:  s / std(s)                                  _load_sig_lpc           nscm.py:98-113
+                    high-pass -> pre-emphasis                   cmrl.py:671
+                    1024-sample LPC windows -> 16 LSFs          lpc_analysis_at_test    cmrl.py:693
+                    frames of sig[256:] (hop 480)               cmrl.py:695
+    all frames:     LSF codebook -> residual -> CMRL cascade -> synthesis   (CMRL.feedforward_lpc)
+    per utterance:  trapezoid-Hann overlap-add of the first N2 - 2 frames   cmrl.py:698-716
+                    de-emphasis, * std                          cmrl.py:735-737
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import torch
+
+from . import bitstream, lpc_utilities as lu, utilities as ut
+from .constants import frame_length
+
+HOP = ut.hop_size
+
+
+def analysis(sig: torch.Tensor) -> Dict[str, object]:
+    """One utterance (T,) float32 on the GPU -> filtered signal, frames to code, their LSFs and the bookkeeping counts."""
+    s, std = ut.load_sig_lpc(sig)
+    f = ut.empha_filter(ut.highpass_filter(s))
+    T = f.numel()
+    n_seg = ut.segment_count(T)                     # frames of the whole signal (sizes the output arrays, cmrl.py:674-676)
+    n_seg2 = ut.segment_count(T - 256)              # frames of sig[256:]                                 (cmrl.py:695)
+    n_used = max(n_seg2 - 2, 0)                     # the loop runs range(N2 - 2)                           (cmrl.py:698)
+    frames = ut.utterance_to_segment(f, True, offset=256)[:n_used]
+    lsf = lu.lpc_analysis_windows(ut.lpc_windows_at_test(f), dtype=torch.float32)[:n_used]
+    return {'std': std, 'filtered': f, 'frames': frames, 'lsf': lsf, 'n_seg': n_seg, 'n_seg2': n_seg2, 'n_used': n_used}
+
+
+def synthesis(frames: torch.Tensor, n_seg: int, n_seg2: int, std, de_emphasis: bool = True) -> torch.Tensor:
+    """Overlap-add the coded frames of one utterance back into a signal (cmrl.py:710-716, :735-737)."""
+    out_len = frame_length + HOP * (n_seg - 2)
+    y = ut.overlap_add(frames, seg_amount=n_seg2, n_used=frames.shape[0], out_len=max(out_len, 0))
+    if de_emphasis:
+        y = ut.de_empha_filter(y)
+    return y * std
+
+
+def code_utterances(cm, signals: Sequence[torch.Tensor], the_share: bool = False, pack: bool = False) -> List[Dict[str, object]]:
+    """Encode + decode a list of utterances with ``cm`` (a codec.CMRL).  Returns per utterance:
+    'synthesized' (time domain, de-emphasised, rescaled), 'decoded' (overlap-added residual-domain signal), 'lsf_idx',
+    'idx' (per codec) and, with ``pack``, the fixed-width 'records' of bitstream.pack_frames."""
+    ana = [analysis(s) for s in signals]
+    counts = [a['n_used'] for a in ana]
+    if sum(counts) == 0:
+        return [{'synthesized': torch.zeros(0, device=s.device), 'decoded': torch.zeros(0, device=s.device)} for s in signals]
+    frames = torch.cat([a['frames'] for a in ana])
+    lsf = torch.cat([a['lsf'] for a in ana])
+    r = cm.feedforward_lpc(frames, lsf, the_share, 1.0)
+    records = None
+    if pack:
+        records = bitstream.pack_frames(r['lsf_idx'], r['idx'], [c.cfg.num_bins for c in cm.codecs], cm.n_lsf_bins)
+    out, o = [], 0
+    for a, n in zip(ana, counts):
+        sl = slice(o, o + n)
+        d = {
+            'synthesized': synthesis(r['synthesized'][sl], a['n_seg'], a['n_seg2'], a['std']),
+            'decoded': synthesis(r['decoded'][sl], a['n_seg'], a['n_seg2'], 1.0, de_emphasis=False),
+            'lsf_idx': r['lsf_idx'][sl], 'idx': [i[sl] for i in r['idx']], 'n_frames': n,
+        }
+        if records is not None:
+            d['records'] = records[sl]
+        out.append(d)
+        o += n
+    return out

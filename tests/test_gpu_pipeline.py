@@ -1,0 +1,69 @@
+"""wav -> codes -> wav through nsc_b200.pipeline against the oracle's composition of the same reference steps
+(cmrl.py:666-737): std normalisation, high-pass, pre-emphasis, LPC windows, frames of sig[256:], CQ pass, overlap-add,
+de-emphasis."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_codec, ref_framing as rf, ref_lpc, ref_nn
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _utterance(T, seed):
+    from scipy.signal import lfilter
+    rng = np.random.RandomState(seed)
+    x = lfilter([1.0], [1.0, -1.6, 0.8], rng.randn(T + 200))[200:]
+    return (0.05 * x).astype(np.float32)
+
+
+def _oracle_pipeline(x, ocs, bins, the_share):
+    std = np.std(x)
+    s = x / std
+    f = rf.empha_filter(rf.highpass_filter(s))
+    seg = rf.utterance_to_segment(f, True)
+    lsf_all = ref_lpc.lpc_analysis_at_test(seg, 16)
+    seg2 = rf.utterance_to_segment(f[256:], True)
+    n_used = seg2.shape[0] - 2
+    fr = torch.from_numpy(seg2[:n_used].astype(np.float32))[:, :, None]
+    lsf = torch.from_numpy(lsf_all[:n_used].astype(np.float32))[:, :, None]
+    o = ref_codec.cq_feedforward(ocs, -300.0, bins, fr, lsf, the_share, 1.0)
+    out_len = 512 + 480 * (seg.shape[0] - 2)
+    syn = rf.overlap_add(np.asarray(o['synthesized'], dtype=np.float64), seg2.shape[0], n_used, out_len)
+    return rf.de_empha_filter(syn) * std, n_used
+
+
+def test_code_utterances_matches_oracle_composition():
+    from nsc_b200 import codec, pipeline
+    ocfg = ref_codec.OracleCodecCfg()
+    cfg = codec.CodecConfig()
+    ocs = [ref_codec.OracleCodec(ocfg, seed=5), ref_codec.OracleCodec(ocfg, seed=6)]
+    gcs = [codec.NeuralCodec(cfg, torch.from_numpy(codec.pack_params_numpy(cfg, o.conv_params, o.alpha, o.bins)).to(DEV)) for o in ocs]
+    cm = codec.CMRL(gcs, res_scalar=1.0)
+    bins = np.load(os.path.join(GOLD, 'lsf_bins_f64.npy')).astype(np.float32)
+    sigs = [_utterance(6000, 1), _utterance(9137, 2)]
+    got = pipeline.code_utterances(cm, [torch.from_numpy(s).to(DEV) for s in sigs], the_share=True)
+    for s, g in zip(sigs, got):
+        want, n_used = _oracle_pipeline(s, ocs, bins, True)
+        assert g['n_frames'] == n_used
+        assert g['synthesized'].shape[0] == want.shape[0]
+        assert rel_err(g['synthesized'].cpu().numpy(), want) < 2e-4    # soft path end to end (1e-4 per stage: analysis LSFs, codec, filters)
+
+
+def test_hard_codes_pack_and_survive_the_round_trip():
+    from nsc_b200 import bitstream, codec, pipeline
+    cfg = codec.CodecConfig()
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=5), codec.NeuralCodec(cfg, device=DEV, seed=6)], res_scalar=1.0)
+    sigs = [torch.from_numpy(_utterance(16000, 3)).to(DEV)]
+    out = pipeline.code_utterances(cm, sigs, the_share=False, pack=True)[0]
+    n = out['n_frames']
+    assert out['records'].shape == (n, 16 + 160 + 160)
+    lsf_idx, codes = bitstream.unpack_frames(out['records'], [256, 256], [32, 32])
+    assert torch.equal(lsf_idx, out['lsf_idx']) and all(torch.equal(a, b) for a, b in zip(codes, out['idx']))
+    assert torch.isfinite(out['synthesized']).all()
+    assert out['synthesized'].shape[0] == 512 + 480 * (pipeline.ut.segment_count(16000) - 2)
