@@ -449,9 +449,11 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
     NSC_TRY(cascade_chunk(cfgs, lays.data(), n_codecs, params_ptrs_host, res_c, b0, nb, Bc, res_scalar, 1, is_quan_on,
                           use_soft, idx_ptrs_host, hist_ptrs_host, qloss_ptrs_host, nullptr, decoded + b0 * kFrameLen,
                           rest, rest_bytes, st, plane ? &pcs : nullptr));
-    if (synthesized)                                                                         // cmrl.py:843
+    if (synthesized && poly == nullptr)                                                      // cmrl.py:843 (per chunk: poly lives in the workspace)
       NSC_TRY(nsc_lpc_synth(poly_c, decoded + b0 * kFrameLen, nb, synthesized + b0 * kFrameLen, stream));
   }
+  // one thread per frame, 512 dependent steps: latency-bound, so it runs ONCE over the whole batch when the caller keeps poly
+  if (synthesized && poly != nullptr) NSC_TRY(nsc_lpc_synth(poly, decoded, B, synthesized, stream));
   return NSC_OK;
 }
 

@@ -230,7 +230,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 // ---- phase 1: shifted sums of NCH channels of one 32-row quarter ------------------------------------
 // tcol: TMEM address of this warp's first column of tap 0; taps are `tap_stride` columns apart.
 template <int NCH>
-__device__ __forceinline__ void t_phase1_k9(uint32_t tcol, int lane, int dil, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
+__device__ __forceinline__ void t_phase1_k9(uint32_t tcol, const int (&srcl)[9], uint32_t inrm, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
   // all nine taps are fetched before the single wait: 9 * NCH independent shuffles then pipeline back to back
   uint32_t r[9][8];
 #pragma unroll
@@ -249,9 +249,8 @@ __device__ __forceinline__ void t_phase1_k9(uint32_t tcol, int lane, int dil, fl
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     if (t == 4) continue;
-    const int s = (t - 4) * dil;
-    const int src = (lane + s) & 31;
-    const bool inr = (unsigned)(lane + s) < 32u;
+    const int src = srcl[t];
+    const bool inr = (inrm >> t) & 1u;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const float x = __shfl_sync(0xffffffffu, __uint_as_float(r[t][c]), src);
@@ -325,8 +324,45 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
     const float slope = act_slope_of(p.act);
     const int m = ((TAPS - 1) / 2) * p.dil;
     const int nq = 4 * T;
-    uint32_t it = 0;
+    const bool low = lane < m, high = lane >= 32 - m;
+    // everything that depends only on the lane is computed once: shuffle sources and the in-range mask of the nine taps,
+    // this thread's rows inside a spill slot, its swizzle phase
+    int srcl[9];
+    uint32_t inrm = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int s = (t - 4) * p.dil;
+      srcl[t] = (lane + s) & 31;
+      if ((unsigned)(lane + s) < 32u) inrm |= 1u << t;
+    }
+    constexpr int kSlotF = kMaxM * kRF;
+    const int coff = (C == 1) ? 0 : grp * 8;
+    float* const sU_l = sU + lane * kRF + coff;
+    float* const sP_l = sP + (lane - (32 - m)) * kRF + coff;
+    const int out_planes = p.out.planes;
+    uint32_t it = 0, tb = 0, tbp = 8;                 // tb: first spill slot of this tile's quarters (0, 4, 8 in turn)
     for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
+      uint8_t* const orow = (C == 1) ? nullptr : p.out.base + f * p.out.frame_bytes + 8 * 128;   // position 0 of the packed image
+      float* const yrow = (C == 1) ? p.yvec + f * p.L : nullptr;
+      auto store_row = [&](int row, const float (&r)[NCHMAX]) {
+        if constexpr (C == 1) {
+          yrow[row] = apply_act(r[0] + bias[0], p.act);
+        } else {
+          float v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = c < nch ? act_fast(r[c] + bias[c], slope) : 0.f;
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          uint8_t* rp = orow + row * 128;
+          const uint32_t sw = (uint32_t)row & 7u;       // (row + 8) & 7
+          *reinterpret_cast<uint4*>(rp + (((uint32_t)grp ^ sw) << 4)) = hi;
+          if (out_planes == 2) *reinterpret_cast<uint4*>(rp + (((uint32_t)(grp + 4) ^ sw) << 4)) = lo;
+          if (grp == 2) {                               // channels 24-31 of both halves: K padding the consumer reads
+            *reinterpret_cast<uint4*>(rp + ((3u ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+            if (out_planes == 2) *reinterpret_cast<uint4*>(rp + ((7u ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      };
       for (int j = 0; j < T; ++j, ++it) {
         const uint32_t acc_i = it & 1u;
         mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
@@ -338,71 +374,62 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         } else {
           if (grp == 2) {
             float a4[4], u4[4], d4[4];
-            t_phase1_k9<4>(tcol, lane, p.dil, a4, u4, d4);
+            t_phase1_k9<4>(tcol, srcl, inrm, a4, u4, d4);
 #pragma unroll
             for (int c = 0; c < 8; ++c) { acc[c] = c < 4 ? a4[c & 3] : 0.f; up[c] = c < 4 ? u4[c & 3] : 0.f; down[c] = c < 4 ? d4[c & 3] : 0.f; }
           } else {
-            t_phase1_k9<8>(tcol, lane, p.dil, acc, up, down);
+            t_phase1_k9<8>(tcol, srcl, inrm, acc, up, down);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc_i]);   // TMEM slot free: the next tile's MMAs run under phase 2
 
-        const uint32_t gq = it * 4u + (uint32_t)q;
         const int fqi = j * 4 + q;
         const bool lastq = fqi == nq - 1;
-        const uint32_t slot = gq % kTSlots;
-        const int coff = (C == 1) ? 0 : grp * 8;
-        if (lane < m) {
+        const uint32_t slot = tb + (uint32_t)q;
+        const uint32_t slot1 = q ? slot - 1u : tbp + 3u;                       // previous quarter (possibly of the previous tile)
+        const uint32_t slot2 = q >= 2 ? slot - 2u : tbp + 2u + (uint32_t)q;    // the one before it
+        if (low) {
 #pragma unroll
-          for (int c = 0; c < NCHMAX; ++c) sU[(slot * kMaxM + lane) * kRF + coff + c] = up[c];
+          for (int c = 0; c < NCHMAX; ++c) sU_l[slot * kSlotF + c] = up[c];
         }
-        if (lane >= 32 - m && !lastq) {
+        if (high && !lastq) {
 #pragma unroll
-          for (int c = 0; c < NCHMAX; ++c) sP[(slot * kMaxM + (lane - (32 - m))) * kRF + coff + c] = acc[c];
+          for (int c = 0; c < NCHMAX; ++c) sP_l[slot * kSlotF + c] = acc[c];
         }
         asm volatile("bar.sync 1, %0;" :: "n"(kEpi * 32) : "memory");
-        const uint32_t slot1 = (gq + kTSlots - 1) % kTSlots, slot2 = (gq + kTSlots - 2) % kTSlots;
         // Every thread finishes ONE row: its own if nothing is missing from the next quarter, else the parked row of the
-        // previous quarter whose down-spill it holds.  The frame's last quarter also finishes its own parked rows (pass 1).
-        const bool high = lane >= 32 - m;
-        for (int pass = 0; pass < ((lastq && high) ? 2 : 1); ++pass) {
-          const bool own = !high || pass == 1;
-          if (!own && fqi < 1) continue;
-          float r[NCHMAX];
-          int row;
-          if (own) {
-            row = fqi * 32 + lane;
+        // previous quarter whose down-spill it holds.  The frame's last quarter also finishes its own parked rows.
+        float r[NCHMAX];
+        if (!high) {
 #pragma unroll
-            for (int c = 0; c < NCHMAX; ++c) r[c] = acc[c];
-            if (lane < m && fqi >= 1) {
+          for (int c = 0; c < NCHMAX; ++c) r[c] = acc[c];
+          if (low && fqi >= 1) {
 #pragma unroll
-              for (int c = 0; c < NCHMAX; ++c) r[c] += sU[(slot1 * kMaxM + lane) * kRF + coff + c];
-            }
-          } else {
-            row = (fqi - 1) * 32 + lane;
-#pragma unroll
-            for (int c = 0; c < NCHMAX; ++c) r[c] = sP[(slot1 * kMaxM + (lane - (32 - m))) * kRF + coff + c] + down[c];
-            if (lane < m && fqi >= 2) {
-#pragma unroll
-              for (int c = 0; c < NCHMAX; ++c) r[c] += sU[(slot2 * kMaxM + lane) * kRF + coff + c];
-            }
+            for (int c = 0; c < NCHMAX; ++c) r[c] += sU_l[slot1 * kSlotF + c];
           }
-          if constexpr (C == 1) {
-            p.yvec[f * p.L + row] = apply_act(r[0] + bias[0], p.act);
-          } else {
-            uint8_t* img = p.out.base + f * p.out.frame_bytes;
-            float v[8];
+          store_row(fqi * 32 + lane, r);
+        } else if (fqi >= 1) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = c < nch ? act_fast(r[c] + bias[c], slope) : 0.f;
-            pt_store8(p.out, img, row, grp, v);
-            if (grp == 2) {
-              const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              pt_store8(p.out, img, row, 3, z);
-            }
+          for (int c = 0; c < NCHMAX; ++c) r[c] = sP_l[slot1 * kSlotF + c] + down[c];
+          if (C == 1 && low && fqi >= 2) {             // shifts beyond 16 rows (k55): the parked row also took an up-spill
+#pragma unroll
+            for (int c = 0; c < NCHMAX; ++c) r[c] += sU_l[slot2 * kSlotF + c];
           }
+          store_row(fqi * 32 + lane - 32, r);
         }
+        if (lastq && high) {
+#pragma unroll
+          for (int c = 0; c < NCHMAX; ++c) r[c] = acc[c];
+          if (C == 1 && low && fqi >= 1) {
+#pragma unroll
+            for (int c = 0; c < NCHMAX; ++c) r[c] += sU_l[slot1 * kSlotF + c];
+          }
+          store_row(fqi * 32 + lane, r);
+        }
+        tbp = tb;
+        tb = tb == 8u ? 0u : tb + 4u;
       }
     }
   } else if (warp == kEpi) {
@@ -516,6 +543,58 @@ __device__ __forceinline__ void pt_load_raw(const PlaneTensor& t, const uint8_t*
   lo = t.planes == 2 ? __ldg(reinterpret_cast<const uint4*>(r + (int64_t)t.spp * sb)) : make_uint4(0, 0, 0, 0);
 }
 
+
+// ---- Toeplitz producers (PK_GEN), shared by plane_x_kernel<true> and plane_xs_kernel ---------------------------------
+__device__ __forceinline__ void gen_producer(const XParams& p, int ptid, int lane, uint8_t* sA, uint64_t* a_full, uint64_t* a_empty,
+                                             __half* s_xh, __half* s_xl) {
+      const int nch = p.ksteps * 2;     // 16-byte chunks per row that the MMAs read
+      const int nch_sh = nch == 8 ? 3 : (nch == 4 ? 2 : (nch == 2 ? 1 : 0));
+      const uint32_t* wh = reinterpret_cast<const uint32_t*>(s_xh);
+      const uint32_t* wl = reinterpret_cast<const uint32_t*>(s_xl);
+      uint32_t kb = 0, ph = 1;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t f = tile / p.tiles_per_frame;
+        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
+        const float* xv = p.xvec + f * p.Lin;
+        const float* xs = p.xsub ? p.xsub + f * p.Lin : nullptr;
+        for (int j = ptid; j < kGenSeg; j += kXGenWarps * 32) {
+          const int pos = q0 - p.padL + j;
+          float x = 0.f;
+          if (pos >= 0 && pos < p.Lin) x = p.xscale * (__ldg(xv + pos) - (xs ? __ldg(xs + pos) : 0.f));
+          const __half h = __float2half_rn(x);
+          s_xh[j] = h;
+          s_xl[j] = __float2half_rn(x - __half2float(h));
+        }
+        for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
+        asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");
+        uint8_t* dhi = sA + kb * (uint32_t)p.stage_bytes;
+        uint8_t* dlo = dhi + p.stage_bytes;
+        for (int item = ptid; item < (p.tile << nch_sh); item += kXGenWarps * 32) {
+          const int i = item >> nch_sh, g = item & (nch - 1);
+          const int j0 = i + 8 * g;
+          const int w = j0 >> 1;
+          const uint32_t off = (uint32_t)i * 128u + (((uint32_t)g ^ ((uint32_t)i & 7u)) << 4);
+          uint32_t a0 = wh[w], a1 = wh[w + 1], a2 = wh[w + 2], a3 = wh[w + 3], a4 = wh[w + 4];
+          uint4 o;
+          if (j0 & 1) o = make_uint4(__funnelshift_r(a0, a1, 16), __funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), __funnelshift_r(a3, a4, 16));
+          else o = make_uint4(a0, a1, a2, a3);
+          *reinterpret_cast<uint4*>(dhi + off) = o;
+          if (p.planes == 2) {
+            a0 = wl[w]; a1 = wl[w + 1]; a2 = wl[w + 2]; a3 = wl[w + 3]; a4 = wl[w + 4];
+            if (j0 & 1) o = make_uint4(__funnelshift_r(a0, a1, 16), __funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), __funnelshift_r(a3, a4, 16));
+            else o = make_uint4(a0, a1, a2, a3);
+            *reinterpret_cast<uint4*>(dlo + off) = o;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0)
+          for (int ap = 0; ap < p.planes; ++ap) mbar_arrive(&a_full[kb + ap]);
+        asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");   // staging array is reused by the next tile
+        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
+        else ph ^= 1u;
+      }
+}
 
 // ---- MMA issue (shared by plane_x_kernel and plane_xs_kernel) ------------------------------------------------------
 // One elected thread per issuing warp.  With two M tiles per work unit there are TWO issuing threads, one per M tile
@@ -864,56 +943,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
     // The tile's input samples are split into hi / lo halves ONCE into a small staging array; row i of the Toeplitz
     // tile is then the 2 * ksteps * 8 consecutive halves starting at sample i, i.e. per 16-byte chunk five 32-bit
     // shared loads and (for odd i) four funnel shifts.  Entries past the K taps meet zero weights.
-    if constexpr (kGen) {
-      const int ptid = tid - (kXEpiWarps + 3) * 32;
-      const int nch = p.ksteps * 2;     // 16-byte chunks per row that the MMAs read
-      const int nch_sh = nch == 8 ? 3 : (nch == 4 ? 2 : (nch == 2 ? 1 : 0));
-      const uint32_t* wh = reinterpret_cast<const uint32_t*>(s_xh);
-      const uint32_t* wl = reinterpret_cast<const uint32_t*>(s_xl);
-      uint32_t kb = 0, ph = 1;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int64_t f = tile / p.tiles_per_frame;
-        const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
-        const float* xv = p.xvec + f * p.Lin;
-        const float* xs = p.xsub ? p.xsub + f * p.Lin : nullptr;
-        for (int j = ptid; j < kGenSeg; j += kXGenWarps * 32) {
-          const int pos = q0 - p.padL + j;
-          float x = 0.f;
-          if (pos >= 0 && pos < p.Lin) x = p.xscale * (__ldg(xv + pos) - (xs ? __ldg(xs + pos) : 0.f));
-          const __half h = __float2half_rn(x);
-          s_xh[j] = h;
-          s_xl[j] = __float2half_rn(x - __half2float(h));
-        }
-        for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
-        asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");
-        uint8_t* dhi = sA + kb * (uint32_t)p.stage_bytes;
-        uint8_t* dlo = dhi + p.stage_bytes;
-        for (int item = ptid; item < (p.tile << nch_sh); item += kXGenWarps * 32) {
-          const int i = item >> nch_sh, g = item & (nch - 1);
-          const int j0 = i + 8 * g;
-          const int w = j0 >> 1;
-          const uint32_t off = (uint32_t)i * 128u + (((uint32_t)g ^ ((uint32_t)i & 7u)) << 4);
-          uint32_t a0 = wh[w], a1 = wh[w + 1], a2 = wh[w + 2], a3 = wh[w + 3], a4 = wh[w + 4];
-          uint4 o;
-          if (j0 & 1) o = make_uint4(__funnelshift_r(a0, a1, 16), __funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), __funnelshift_r(a3, a4, 16));
-          else o = make_uint4(a0, a1, a2, a3);
-          *reinterpret_cast<uint4*>(dhi + off) = o;
-          if (p.planes == 2) {
-            a0 = wl[w]; a1 = wl[w + 1]; a2 = wl[w + 2]; a3 = wl[w + 3]; a4 = wl[w + 4];
-            if (j0 & 1) o = make_uint4(__funnelshift_r(a0, a1, 16), __funnelshift_r(a1, a2, 16), __funnelshift_r(a2, a3, 16), __funnelshift_r(a3, a4, 16));
-            else o = make_uint4(a0, a1, a2, a3);
-            *reinterpret_cast<uint4*>(dlo + off) = o;
-          }
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0)
-          for (int ap = 0; ap < p.planes; ++ap) mbar_arrive(&a_full[kb + ap]);
-        asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");   // staging array is reused by the next tile
-        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
-        else ph ^= 1u;
-      }
-    }
+    if constexpr (kGen) gen_producer(p, tid - (kXEpiWarps + 3) * 32, lane, sA, a_full, a_empty, s_xh, s_xl);
   }
   tc_fence_before();
   __syncthreads();
@@ -933,7 +963,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
 //   unit = (M tile, 64-channel output slab) x planes; ring of kSUnits units:  residual loader -> epilogue -> storer.
 // ================================================================================================
 constexpr int kSEpiGroups = 4, kSEpiWarps = 4 * kSEpiGroups;
-constexpr int kSThreads = (kSEpiWarps + 6) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer, second MMA issuer
+constexpr int kSThreads = (kSEpiWarps + 6 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer, second MMA issuer, Toeplitz producers
 constexpr int kSUnits = 3;
 constexpr int kSPlane = 128 * 128;                 // one plane of one unit
 
@@ -948,6 +978,8 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
   __shared__ uint64_t st_full[kSUnits], st_done[kSUnits], st_empty[kSUnits];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128];
+  __shared__ __align__(16) __half s_xh[kGenSeg], s_xl[kGenSeg];   // PK_GEN: hi / lo halves of the tile's input samples
+  const bool gen = p.kind == PK_GEN;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nbuf = p.n_stage * p.kbuf;                 // n_stage == 1 (packed input)
@@ -961,7 +993,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
 
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], p.n_iss); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], gen ? kXGenWarps : 1); mbar_init(&a_empty[i], p.n_iss); }
     for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], p.n_iss); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], p.n_iss); mbar_init(&acc_empty[i], kSEpiWarps); }
     for (int i = 0; i < kSUnits; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_done[i], kSEpiWarps); mbar_init(&st_empty[i], 1); }
@@ -1063,11 +1095,11 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
     const int issuer = warp == kSEpiWarps ? 0 : 1;
     if (issuer < p.n_iss && elect_one()) {
       const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty};
-      x_issuer(p, false, issuer, sA, sW, tmem, bars);
+      x_issuer(p, gen, issuer, sA, sW, tmem, bars);
     }
   } else if (warp == kSEpiWarps + 1) {
     // =========================== A loader ===========================
-    if (elect_one()) {
+    if (!gen && elect_one()) {
       uint32_t kb = 0, ph = 1;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t f = tile / p.tiles_per_frame;
@@ -1154,6 +1186,9 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             // all stores complete before the CTA retires
     }
+  } else if (warp >= kSEpiWarps + 6) {
+    // =========================== Toeplitz producers (PK_GEN) ===========================
+    if (gen) gen_producer(p, tid - (kSEpiWarps + 6) * 32, lane, sA, a_full, a_empty, s_xh, s_xl);
   }
   tc_fence_before();
   __syncthreads();
@@ -1224,7 +1259,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   if (p->n_stage > kXMaxStage) return false;
   // narrow-input, wide-output layers (the HBM-bound third conv of a block) take the staged epilogue
   static const bool no_stage = getenv("NSC_PLANE_NOSTAGE") != nullptr;
-  p->staged = (!gen && c.in.packed && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage) ? 1 : 0;
+  p->staged = ((gen || c.in.packed) && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage) ? 1 : 0;
   const size_t stg_total = p->staged ? (size_t)kSUnits * c.planes * kSPlane : 0;
   const size_t budget = kSmemBudget - stg_total;
   // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
@@ -1260,7 +1295,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     if (c.out.packed) needed = 4;
     p->zero_from = written;
     p->zero_to = needed > written ? needed : written;
-    if (p->staged && (p->zero_from != p->zero_to || p->n_stage != 1)) p->staged = 0;   // (never for the codec's shapes)
+    if (p->staged && (p->zero_from != p->zero_to || p->n_stage * p->kbuf > 4)) p->staged = 0;   // (never for the codec's shapes)
     {
       // one issuing thread per M tile where the issue rate, not HBM, bounds the layer (measured); the staged layers are HBM-bound
       static const int knob = [] { const char* e = getenv("NSC_PLANE_ISSUERS"); return e ? atoi(e) : 0; }();
@@ -1361,8 +1396,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   XParams p;
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
   const size_t smem = x_smem_bytes(p);
-  if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
   double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_payload_bytes(c.in));
@@ -1371,8 +1406,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
   ProfScope prof(st, name, 2.0 * macs, bytes);
   const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  if (c.kind == PK_GEN) plane_x_kernel<true><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
-  else if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
+  if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
+  else if (c.kind == PK_GEN) plane_x_kernel<true><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
   else plane_x_kernel<false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;

@@ -187,6 +187,31 @@ soft_hist_kernel(const float* __restrict__ soft, int64_t rows, int n, int rows_p
   for (int k = threadIdx.x; k < n; k += 256) atomicAdd(hist + k, h[k]);
 }
 
+
+// Hard path only (no soft tensor, histogram or quantisation loss wanted): one THREAD per code, bins in shared memory.
+// Same arithmetic as quantize_kernel -- fp32 distance, separate fp32 multiply by alpha, first maximum wins -- so the
+// indices are bit-identical; it just does not spend a warp and five shuffle rounds per code.
+__global__ void __launch_bounds__(256) quantize_hard_kernel(const float* __restrict__ x, int64_t rows, const float* __restrict__ bins,
+                                                            int n, const float* __restrict__ alpha_p, float iq,
+                                                            float* __restrict__ out, uint8_t* __restrict__ idx) {
+  __shared__ float bins_s[256];
+  for (int k = threadIdx.x; k < n; k += blockDim.x) bins_s[k] = bins[k];
+  __syncthreads();
+  const float alpha = *alpha_p;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[r];
+    float best = 0.f;
+    int besti = -1;
+    for (int k = 0; k < n; ++k) {
+      const float lg = __fmul_rn(alpha, fabsf(__fsub_rn(xv, bins_s[k])));
+      if (besti < 0 || lg > best) { best = lg; besti = k; }   // strictly greater keeps the lowest index; NaN never wins
+    }
+    if (besti < 0) besti = 0;
+    if (out) out[r] = __fadd_rn(__fmul_rn(1.f - iq, xv), __fmul_rn(iq, bins_s[besti]));
+    if (idx) idx[r] = (uint8_t)besti;
+  }
+}
+
 int launch_quantize(const float* x, int64_t B, int L, const float* bins, int n, const float* alpha, float iq,
                     int use_soft, float* out, uint8_t* idx, float* soft, float* hist, float* qloss,
                     cudaStream_t st) {
@@ -195,6 +220,17 @@ int launch_quantize(const float* x, int64_t B, int L, const float* bins, int n, 
   NSC_CHECK_ARG(L >= 1 && L <= 4096, "nsc_quantize_scalar: code length %d not in [1,4096]", L);
   NSC_CHECK_ARG(x && bins && alpha, "nsc_quantize_scalar: null input");
   if (B == 0) return NSC_OK;
+  if (!use_soft && soft == nullptr && hist == nullptr && qloss == nullptr) {
+    char hname[32];
+    snprintf(hname, sizeof(hname), "quantize_hard_n%d_L%d", n, L);
+    ProfScope hprof(st, hname, (double)B * L * n * 4.0, (double)B * L * 9.0);
+    const int64_t rows = B * (int64_t)L;
+    int64_t g = ceil_div64(rows, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    quantize_hard_kernel<<<(unsigned)g, 256, 0, st>>>(x, rows, bins, n, alpha, iq, out, idx);
+    NSC_LAUNCH_OK();
+    return NSC_OK;
+  }
   const int frames_per_cta = L >= 256 ? 1 : 256 / L;
   const int64_t grid = ceil_div64(B, frames_per_cta);
   const int npl = n <= 32 ? 1 : n <= 64 ? 2 : n <= 128 ? 4 : 8;
