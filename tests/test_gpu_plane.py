@@ -108,3 +108,70 @@ def test_unsupported_shape_fails_loudly():
     lib = _lib.load()
     assert lib.nsc_conv1d_tc_workspace_bytes(4, 500, 100, 20, 9, 1, 1, 0, 1, 1) < 0     # 500 is not a multiple of 128
     assert 'tensor engine' in _lib.last_error()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def _cq2(seed0=5, seed1=6, precision='tc_f16x3'):
+    from nsc_b200 import codec
+    cfg = codec.CodecConfig(precision=precision)
+    return codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=seed0), codec.NeuralCodec(cfg, device=DEV, seed=seed1)], res_scalar=1.0)
+
+
+def test_full_size_batch_independence_across_chunk_boundaries():
+    """BASELINE-size batch (4,500 frames: three 2,072-frame chunks, the last one ragged): every frame's codes and waveform are
+    bit-identical to coding it in a 7-frame batch -- no dependence on the chunk it fell in, the CTA that took it, or its
+    neighbours (frames are independent units)."""
+    from util import ar_frames
+    from nsc_b200 import lpc_utilities as lu
+    cm = _cq2()
+    win = torch.from_numpy(ar_frames(4500, 1024, seed=77)).to(DEV)
+    x = win[:, 256:768].contiguous()
+    lsf = lu.lpc_analysis_windows(win, 16, dtype=torch.float32)
+    big = cm.feedforward_lpc(x, lsf, False, 1.0)
+    for lo in (0, 2068, 2072, 4140, 4493):      # around the 2,072 / 4,144 chunk boundaries and the ragged tail
+        small = cm.feedforward_lpc(x[lo:lo + 7].contiguous(), lsf[lo:lo + 7].contiguous(), False, 1.0)
+        for k in range(2):
+            assert torch.equal(small['idx'][k], big['idx'][k][lo:lo + 7])
+        assert torch.equal(small['lsf_idx'], big['lsf_idx'][lo:lo + 7])
+        assert torch.equal(small['synthesized'], big['synthesized'][lo:lo + 7])
+    assert torch.isfinite(big['synthesized']).all()
+
+
+def test_full_size_cascade_algebra_and_hard_round_trip():
+    """decoded = sum of the codecs' outputs; decoding the hard indices reproduces the forward pass output bit for bit."""
+    from util import ar_frames
+    cm = _cq2(7, 8)
+    x = torch.from_numpy(ar_frames(2500, 512, seed=78, std=0.3)).to(DEV)
+    r = cm.all_modules_feedforward(x, False, 1.0, want_outs=True)
+    total = r['outs'][0] + r['outs'][1]
+    assert rel_err(r['decoded'].cpu().numpy(), total.cpu().numpy()) < 1e-6
+    # codec 0 sees x itself: its decoder applied to the transmitted indices gives outs[0] exactly
+    dec0 = cm.codecs[0].decode_indices(r['idx'][0])
+    assert torch.equal(dec0, r['outs'][0])
+    # codec 1 codes the residual x - outs[0]
+    enc1 = cm.codecs[1].encode((x - r['outs'][0]).contiguous(), False, 1.0)
+    assert torch.equal(enc1['idx'], r['idx'][1])
+
+
+def test_plane_path_matches_layer_by_layer_engine_at_full_size(monkeypatch):
+    """Plane engine vs the first tensor engine (same hi/lo arithmetic, fp32 activations between layers) on 1,000 frames."""
+    import subprocess, sys, os, json
+    from util import ar_frames
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from util import ar_frames\n"
+        "from nsc_b200 import codec\n"
+        "cfg = codec.CodecConfig(); gc = codec.NeuralCodec(cfg, device='cuda', seed=9)\n"
+        "x = torch.from_numpy(ar_frames(1000, 512, seed=79, std=0.3)).cuda()\n"
+        "r = gc.computational_graph_end2end_quan_on(x, True, 1.0)\n"
+        "np.save(sys.argv[1], np.concatenate([r['floating_code'].cpu().numpy().ravel(), r['out'].cpu().numpy().ravel()]))\n"
+    ) % (root, os.path.join(root, 'tests'))
+    outs = []
+    for tag, env in (('plane', {}), ('layered', {'NSC_PLANE': '0'})):
+        path = '/tmp/nsc_plane_vs_layered_%s.npy' % tag
+        e = dict(os.environ); e.update(env)
+        subprocess.run([sys.executable, '-c', code, path], check=True, env=e, timeout=300)
+        outs.append(np.load(path))
+    assert rel_err(outs[0], outs[1]) < 1e-4
