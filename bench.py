@@ -173,8 +173,8 @@ def run_ours(args):
     lib = _lib.load()
 
     B = args.frames                      # frames per GPU per step (weak scaling)
-    cfg = codec.CodecConfig(precision=args.precision)
-    gcs = [codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)]
+    cfg = codec.CodecConfig(precision=args.precision, num_bins=args.bins)
+    gcs = [codec.NeuralCodec(cfg, device=dev, seed=5 + i) for i in range(args.codecs)]
     cm = codec.CMRL(gcs, res_scalar=1.0)
     x_np, win_np = synth_audio(min(B, 4096), seed=1234 + rank)
     reps = -(-B // x_np.shape[0])
@@ -193,7 +193,7 @@ def run_ours(args):
         wd = win_host.to(dev, non_blocking=True)
         lsf = lu.lpc_analysis_windows(wd, 16, dtype=torch.float32)
         r = cm.feedforward_lpc(xd, lsf, False, 1.0)
-        for k, t in (('lsf_idx', r['lsf_idx']), ('idx0', r['idx'][0]), ('idx1', r['idx'][1]), ('syn', r['synthesized'])):
+        for k, t in [('lsf_idx', r['lsf_idx']), ('syn', r['synthesized'])] + [('idx%d' % i, t) for i, t in enumerate(r['idx'])]:
             if k not in out_host:
                 out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             out_host[k].copy_(t, non_blocking=True)
@@ -296,8 +296,8 @@ def run_ours(args):
             "dtype": {"fp32": "f32", "tc_f16x3": "f32-equivalent (fp16 hi/lo split on tensor cores, fp32 accumulate)",
                       "tc_f16": "f16 inputs / f32 accumulate (REDUCED precision)"}[args.precision] +
                      "; LPC analysis/residual/synthesis f64", "data": "synthetic",
-            "config": {"workload": "cq2: LPC analysis + 256-bin LSF codebook + 2 cascaded bottleneck codecs "
-                                   "('9 9 100 20 1 2', stride 2, 32 bins, hard codes) + LPC synthesis",
+            "config": {"workload": f"cq{args.codecs}: LPC analysis + 256-bin LSF codebook + {args.codecs} cascaded bottleneck codecs "
+                                   f"('9 9 100 20 1 2', stride 2, {args.bins} bins, hard codes) + LPC synthesis",
                        "frames_per_gpu_per_step": B, "frames_per_step": frames_total, "conv_precision": args.precision,
                        "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of frames+windows per GPU per step, plus a "
                                     "multi-GB activation workspace cycled per ~2k-frame chunk (L2 is 126 MB); no explicit flush",
@@ -310,7 +310,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "kernel_breakdown": breakdown,
-            "compute_tflops_whole_step": frames_total * args.steps * 2 * FLOP_PER_FRAME_CODEC / t_dev / 1e12,
+            "compute_tflops_whole_step": frames_total * args.steps * args.codecs * FLOP_PER_FRAME_CODEC / t_dev / 1e12,
         }
         print(json.dumps(line))
     if world > 1:
@@ -458,6 +458,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='cq2', choices=['cq2', 'train', 'corpus'],
                     help="cq2 = headline encode+decode; train = training step; corpus = wav -> packed codes -> wav")
+    ap.add_argument('--codecs', type=int, default=2, help='cascaded codecs (BASELINE.json configs[2] scales this and --bins)')
+    ap.add_argument('--bins', type=int, default=32, help='code bins per codec')
     ap.add_argument('--utterances', type=int, default=360, help='corpus workload: utterances per GPU')
     ap.add_argument('--utt-seconds', type=float, default=10.0, help='corpus workload: seconds per utterance')
     ap.add_argument('--train-batch', type=int, default=128, help='frames per GPU per training step')
