@@ -205,11 +205,13 @@ struct TParams {
   float* yvec;
   int N, n_wslab, ksteps;
   int L, dil, act, na;
+  int nacc;                  // TMEM accumulator slots (2, or 1 when two CTAs share an SM)
   int64_t B;
 };
 
 constexpr int kTSlots = 12;         // spill slots: three tiles' worth of quarters
 constexpr int kAStage = 128 * 128;  // one input slab of one tile
+constexpr int kORing = 256;         // rows of the output staging ring (two tiles)
 
 // Epilogue organisation: C = 20 -> three warps per TMEM lane quarter, one 8-channel chunk of the output row each
 // (channels 0-7, 8-15, 16-19 + zero padding); C = 1 (k55 head) -> one warp per quarter.
@@ -244,19 +246,70 @@ __device__ __forceinline__ void t_phase1_k9(uint32_t tcol, const int (&srcl)[9],
     }
   }
   tmem_ld_wait();
+  // packed fp32x2 adds (sm_100 FADD2): the epilogue is bound by ALU issue (3-register fp32 ops issue every other cycle), and two
+  // channels per instruction halve the add count
+  float2 a2[NCH / 2], u2[NCH / 2], d2[NCH / 2];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) { acc[c] = __uint_as_float(r[4][c]); up[c] = 0.f; down[c] = 0.f; }
+  for (int c = 0; c < NCH / 2; ++c) {
+    a2[c] = make_float2(__uint_as_float(r[4][2 * c]), __uint_as_float(r[4][2 * c + 1]));
+    u2[c] = make_float2(0.f, 0.f);
+    d2[c] = make_float2(0.f, 0.f);
+  }
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     if (t == 4) continue;
     const int src = srcl[t];
     const bool inr = (inrm >> t) & 1u;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const float x = __shfl_sync(0xffffffffu, __uint_as_float(r[t][c]), src);
-      if (inr) acc[c] += x;
-      else if (t > 4) down[c] += x;   // source row is in this quarter, target row in the previous one
-      else up[c] += x;                // ... in the next one
+    for (int c = 0; c < NCH / 2; ++c) {
+      float2 x;
+      x.x = __shfl_sync(0xffffffffu, __uint_as_float(r[t][2 * c]), src);
+      x.y = __shfl_sync(0xffffffffu, __uint_as_float(r[t][2 * c + 1]), src);
+      if (inr) a2[c] = __fadd2_rn(a2[c], x);
+      else if (t > 4) d2[c] = __fadd2_rn(d2[c], x);   // source row is in this quarter, target row in the previous one
+      else u2[c] = __fadd2_rn(u2[c], x);              // ... in the next one
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH / 2; ++c) {
+    acc[2 * c] = a2[c].x; acc[2 * c + 1] = a2[c].y;
+    up[2 * c] = u2[c].x; up[2 * c + 1] = u2[c].y;
+    down[2 * c] = d2[c].x; down[2 * c + 1] = d2[c].y;
+  }
+}
+
+// Low-register variant (two CTAs per SM): taps are fetched one ahead instead of all at once.
+template <int NCH>
+__device__ __forceinline__ void t_phase1_k9_roll(uint32_t tcol, const int (&srcl)[9], uint32_t inrm, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { acc[c] = 0.f; up[c] = 0.f; down[c] = 0.f; }
+  uint32_t r[2][8];
+  auto load_tap = [&](int t, uint32_t (&dst)[8]) {
+    if constexpr (NCH == 8) tmem_ld8(tcol + (uint32_t)(t * 20), dst);
+    else {
+      uint32_t b[4];
+      tmem_ld4(tcol + (uint32_t)(t * 20), b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = b[i];
+    }
+  };
+  load_tap(0, r[0]);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    tmem_ld_wait();
+    if (t + 1 < 9) load_tap(t + 1, r[(t + 1) & 1]);
+    const int src = srcl[t];
+    const bool inr = (inrm >> t) & 1u;
+#pragma unroll
+    for (int c = 0; c < NCH; c += 2) {
+      float2 x = make_float2(__uint_as_float(r[t & 1][c]), __uint_as_float(r[t & 1][c + 1]));
+      if (t != 4) {
+        x.x = __shfl_sync(0xffffffffu, x.x, src);
+        x.y = __shfl_sync(0xffffffffu, x.y, src);
+      }
+      if (t == 4 || inr) { const float2 y = __fadd2_rn(make_float2(acc[c], acc[c + 1]), x); acc[c] = y.x; acc[c + 1] = y.y; }
+      else if (t > 4) { const float2 y = __fadd2_rn(make_float2(down[c], down[c + 1]), x); down[c] = y.x; down[c + 1] = y.y; }
+      else { const float2 y = __fadd2_rn(make_float2(up[c], up[c + 1]), x); up[c] = y.x; up[c + 1] = y.y; }
     }
   }
 }
@@ -281,8 +334,8 @@ __device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc
   acc = a; up = u; down = d;
 }
 
-template <int C, int TAPS>
-__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
+template <int C, int TAPS, int OCC>
+__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel(const __grid_constant__ TParams p) {
   using S = TShape<C, TAPS>;
   constexpr int kMaxM = S::kMaxM, kRF = S::kRowFloats, kEpi = S::kEpiWarps;
   constexpr int NCHMAX = (C == 1) ? 1 : 8;
@@ -297,10 +350,13 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
   uint8_t* sA = sW + (uint32_t)p.n_wslab * wslab_bytes;
   float* sU = reinterpret_cast<float*>(sA + (uint32_t)p.na * kAStage);     // [kTSlots][kMaxM][kRF]
   float* sP = sU + kTSlots * kMaxM * kRF;                                   // [kTSlots][kMaxM][kRF]
+  // output staging ring (C = 20): kORing image rows of 128 B, same swizzle as the global image, bulk-stored one window per tile
+  uint8_t* sO = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sP + kTSlots * kMaxM * kRF) + 1023) & ~(uintptr_t)1023);
   const int T = p.L / 128;
   const int nst = pt_n_slabs(p.in);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)p.N) tmem_cols *= 2;
+  while (tmem_cols < (uint32_t)p.nacc * (uint32_t)p.N) tmem_cols *= 2;
+  const bool two_acc = p.nacc == 2;
 
   if (tid == 0) {
     mbar_init(&w_full, 1);
@@ -343,6 +399,8 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
     uint32_t it = 0, tb = 0, tbp = 8;                 // tb: first spill slot of this tile's quarters (0, 4, 8 in turn)
     for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
       uint8_t* const orow = (C == 1) ? nullptr : p.out.base + f * p.out.frame_bytes + 8 * 128;   // position 0 of the packed image
+      const int ring0 = (int)((it * 128u) & (kORing - 1));      // ring row of this frame's position 0 (frames are whole tiles)
+      int done_rows = 0;                                        // positions of this frame already handed to the copy engine
       float* const yrow = (C == 1) ? p.yvec + f * p.L : nullptr;
       auto store_row = [&](int row, const float (&r)[NCHMAX]) {
         if constexpr (C == 1) {
@@ -353,7 +411,10 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
           for (int c = 0; c < 8; ++c) v[c] = c < nch ? act_fast(r[c] + bias[c], slope) : 0.f;
           uint4 hi, lo;
           split8(v, hi, lo);
-          uint8_t* rp = orow + row * 128;
+          // A thread owns a ROW, so direct global stores would touch 32 different 128-byte lines per warp instruction (measured:
+          // 1,600 of the 2,900 cycles of a tile).  The row goes into a shared-memory ring that mirrors the image; one thread
+          // bulk-stores a whole window of finished rows per tile.
+          uint8_t* rp = sO + (uint32_t)((ring0 + row) & (kORing - 1)) * 128u;
           const uint32_t sw = (uint32_t)row & 7u;       // (row + 8) & 7
           *reinterpret_cast<uint4*>(rp + (((uint32_t)grp ^ sw) << 4)) = hi;
           if (out_planes == 2) *reinterpret_cast<uint4*>(rp + (((uint32_t)(grp + 4) ^ sw) << 4)) = lo;
@@ -364,8 +425,8 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         }
       };
       for (int j = 0; j < T; ++j, ++it) {
-        const uint32_t acc_i = it & 1u;
-        mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
+        const uint32_t acc_i = two_acc ? (it & 1u) : 0u;
+        mbar_wait(&acc_full[acc_i], two_acc ? (it >> 1) & 1u : it & 1u);
         tc_fence_after();
         float acc[NCHMAX], up[NCHMAX], down[NCHMAX];
         const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + acc_i * (uint32_t)p.N + (uint32_t)(grp * 8);
@@ -374,11 +435,13 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         } else {
           if (grp == 2) {
             float a4[4], u4[4], d4[4];
-            t_phase1_k9<4>(tcol, srcl, inrm, a4, u4, d4);
+            if constexpr (OCC == 2) t_phase1_k9_roll<4>(tcol, srcl, inrm, a4, u4, d4);
+            else t_phase1_k9<4>(tcol, srcl, inrm, a4, u4, d4);
 #pragma unroll
             for (int c = 0; c < 8; ++c) { acc[c] = c < 4 ? a4[c & 3] : 0.f; up[c] = c < 4 ? u4[c & 3] : 0.f; down[c] = c < 4 ? d4[c & 3] : 0.f; }
           } else {
-            t_phase1_k9<8>(tcol, srcl, inrm, acc, up, down);
+            if constexpr (OCC == 2) t_phase1_k9_roll<8>(tcol, srcl, inrm, acc, up, down);
+            else t_phase1_k9<8>(tcol, srcl, inrm, acc, up, down);
           }
         }
         tc_fence_before();
@@ -401,23 +464,18 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         asm volatile("bar.sync 1, %0;" :: "n"(kEpi * 32) : "memory");
         // Every thread finishes ONE row: its own if nothing is missing from the next quarter, else the parked row of the
         // previous quarter whose down-spill it holds.  The frame's last quarter also finishes its own parked rows.
+        // (one code path for both kinds of lane: the row's own part comes from registers, the neighbour's part from shared memory)
         float r[NCHMAX];
-        if (!high) {
+        {
+          const bool take = high ? (fqi >= 1) : (low && fqi >= 1);
+          const float* src = (high ? sP_l : sU_l) + slot1 * kSlotF;
 #pragma unroll
-          for (int c = 0; c < NCHMAX; ++c) r[c] = acc[c];
-          if (low && fqi >= 1) {
-#pragma unroll
-            for (int c = 0; c < NCHMAX; ++c) r[c] += sU_l[slot1 * kSlotF + c];
-          }
-          store_row(fqi * 32 + lane, r);
-        } else if (fqi >= 1) {
-#pragma unroll
-          for (int c = 0; c < NCHMAX; ++c) r[c] = sP_l[slot1 * kSlotF + c] + down[c];
-          if (C == 1 && low && fqi >= 2) {             // shifts beyond 16 rows (k55): the parked row also took an up-spill
+          for (int c = 0; c < NCHMAX; ++c) r[c] = (high ? down[c] : acc[c]) + (take ? src[c] : 0.f);
+          if (C == 1 && high && low && fqi >= 2) {     // shifts beyond 16 rows (k55): the parked row also took an up-spill
 #pragma unroll
             for (int c = 0; c < NCHMAX; ++c) r[c] += sU_l[slot2 * kSlotF + c];
           }
-          store_row(fqi * 32 + lane - 32, r);
+          if (!high || fqi >= 1) store_row(fqi * 32 + lane - (high ? 32 : 0), r);
         }
         if (lastq && high) {
 #pragma unroll
@@ -428,9 +486,31 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
           }
           store_row(fqi * 32 + lane, r);
         }
+        if constexpr (C != 1) {
+          fence_async_smem();                                      // generic-proxy row writes -> visible to the bulk store
+          asm volatile("bar.sync 2, %0;" :: "n"(kEpi * 32) : "memory");
+          if (warp == 0 && lane == 0) {
+            // rows final after this tile: everything up to 8 rows before its end (those wait for the next tile's down-spill)
+            const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
+            int r0 = done_rows;
+            while (r0 < upto) {                                    // at most two pieces (ring wrap)
+              const int ring_r = (ring0 + r0) & (kORing - 1);
+              int n = upto - r0;
+              if (ring_r + n > kORing) n = kORing - ring_r;
+              bulk_s2g(orow + (int64_t)r0 * 128, sO + (uint32_t)ring_r * 128u, (uint32_t)n * 128u);
+              r0 += n;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the window before this one has left shared memory
+          }
+          done_rows = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
+        }
         tbp = tb;
         tb = tb == 8u ? 0u : tb + 4u;
       }
+    }
+    if constexpr (C != 1) {
+      if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp == kEpi) {
     // =========================== MMA issuer ===========================
@@ -446,8 +526,8 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
       uint32_t it = 0, slot = 0, sph = 0;
       for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
         for (int j = 0; j < T; ++j, ++it) {
-          const uint32_t acc_i = it & 1u;
-          mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+          const uint32_t acc_i = two_acc ? (it & 1u) : 0u;
+          mbar_wait(&acc_empty[acc_i], (two_acc ? (it >> 1) & 1u : it & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d = tmem + acc_i * (uint32_t)p.N;
           uint32_t accum = 0;
@@ -967,9 +1047,6 @@ constexpr int kSThreads = (kSEpiWarps + 6 + kXGenWarps) * 32;   // + MMA issuer,
 constexpr int kSUnits = 3;
 constexpr int kSPlane = 128 * 128;                 // one plane of one unit
 
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
 
 __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_constant__ XParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1199,7 +1276,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ourselves (alignment slack + static barriers)
 
 struct TPlan {
-  int N, n_wslab, ksteps, na;
+  int N, n_wslab, ksteps, na, occ;
   size_t smem;
 };
 
@@ -1214,9 +1291,15 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   pl->ksteps = (c.Cin + 15) / 16;
   pl->n_wslab = c.in.packed ? 1 : c.in.planes * c.in.spp;
   const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
-  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * kTSlots * maxm * rowf * sizeof(float);
+  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * kTSlots * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
   if (fixed + 2ull * kAStage > kSmemBudget) return false;
-  size_t na = (kSmemBudget - fixed) / kAStage;
+  // Optional: two CTAs per SM for the narrow-input layers (half the shared memory, ONE accumulator slot each, <= 72 registers).
+  // Measured neutral (4.8 vs 4.8 ms per step on 20 -> 20) once the output rows are staged, so it is off unless asked for.
+  static const bool occ2_on = getenv("NSC_PLANE_T_OCC2") != nullptr;
+  const size_t half = (227 * 1024) / 2 - 2048;
+  pl->occ = (k9 && c.in.packed && occ2_on && fixed + 2ull * kAStage + 1024 <= half) ? 2 : 1;
+  const size_t budget = pl->occ == 2 ? half - 1024 : kSmemBudget;
+  size_t na = (budget - fixed) / kAStage;
   if (na > 8) na = 8;
   pl->na = (int)na;
   pl->smem = 1024 + fixed + na * kAStage;
@@ -1382,13 +1465,18 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     // algorithmic bytes: every input and output plane image moved exactly once (zero rows excluded)
     const double bytes = (double)c.B * (pt_payload_bytes(c.in) + (c.Cout > 1 ? pt_payload_bytes(c.out) : 4.0 * c.Lin));
     ProfScope prof(st, name, 2.0 * macs, bytes);
-    const int64_t grid = c.B < sm_count() ? c.B : sm_count();
-    if (c.Cout == 20) {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 9><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
+    const int64_t slots = (int64_t)sm_count() * pl.occ;
+    const int64_t grid = c.B < slots ? c.B : slots;
+    p.nacc = pl.occ == 2 ? 1 : 2;
+    if (c.Cout == 20 && pl.occ == 2) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 9, 2><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
+    } else if (c.Cout == 20) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 9, 1><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
     } else {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<1, 55><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<1, 55, 1><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
     }
     NSC_LAUNCH_OK();
     return NSC_OK;
