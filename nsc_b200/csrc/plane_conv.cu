@@ -602,6 +602,7 @@ struct XParams {
   int zero_from, zero_to;    // output chunks the epilogue must clear (K padding the consumer will read)
   int staged;                // plane_xs_kernel: epilogue through shared-memory units and bulk copies
   int n_iss;                 // MMA-issuing threads (1, or one per M tile)
+  int mcast;                 // 2-CTA clusters: CTA 0's loader multicasts every weight unit to both CTAs (halves the L2 weight stream)
   int64_t B, n_tiles;
 };
 
@@ -845,6 +846,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[kXMaxStage], a_empty[kXMaxStage], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
+  __shared__ uint64_t w_ready[kXMaxW];     // multicast: both CTAs of the pair have freed and re-armed a ring slot (lives in CTA 0)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(16) __half s_xh[kGen ? kGenSeg : 8], s_xl[kGen ? kGenSeg : 8];   // hi / lo halves of the tile's input samples
@@ -860,7 +862,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
     for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], n_iss); }
-    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_iss); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_iss); mbar_init(&w_ready[i], 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], kXEpiWarps); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -868,6 +870,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.mcast) cluster_sync_all();          // the peer's barriers exist before anything is multicast or arrived remotely
   const uint32_t tmem = tmem_base_s;
 
   if (warp < kXEpiWarps) {
@@ -1006,7 +1009,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
           mbar_expect_tx(&w_full[u], (uint32_t)p.unit_bytes);
           bulk_g2s(sW + (uint32_t)u * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[u]);
         }
-      } else {
+      } else if (!p.mcast) {
         uint32_t ws = 0, wph = 1;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           for (int u = 0; u < p.n_units; ++u) {
@@ -1014,6 +1017,23 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
             mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
             bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
             if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
+          }
+        }
+      } else {
+        // Both CTAs of the pair walk the same unit sequence (same layer, same number of tiles).  Each frees and re-arms its own
+        // slot, then reports to CTA 0, whose loader issues ONE copy that lands in both shared memories.
+        const uint32_t rank = cluster_ctarank();
+        uint32_t ws = 0, wph = 1, rph = 0;
+        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          for (int u = 0; u < p.n_units; ++u) {
+            mbar_wait(&w_empty[ws], wph);
+            mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
+            mbar_arrive_remote(&w_ready[ws], 0u);
+            if (rank == 0) {
+              mbar_wait_cluster(&w_ready[ws], rph);
+              bulk_g2s_mcast(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws], (uint16_t)3);
+            }
+            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; rph ^= 1u; }
           }
         }
       }
@@ -1029,6 +1049,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   __syncthreads();
   tc_fence_after();
   if (warp == kXEpiWarps) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  if (p.mcast) cluster_sync_all();          // neither CTA retires while its peer can still multicast into it or arrive on its barriers
 }
 
 // ================================================================================================
@@ -1383,6 +1404,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
       // one issuing thread per M tile where the issue rate, not HBM, bounds the layer (measured); the staged layers are HBM-bound
       static const int knob = [] { const char* e = getenv("NSC_PLANE_ISSUERS"); return e ? atoi(e) : 0; }();
       p->n_iss = (p->mt == 2 && !p->staged) ? 2 : 1;
+      p->mcast = 0;
       if (knob == 1) p->n_iss = 1;
       if (knob == 2 && p->mt == 2) p->n_iss = 2;
     }
@@ -1494,9 +1516,29 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
   ProfScope prof(st, name, 2.0 * macs, bytes);
   const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  // Weight multicast across CTA pairs is implemented and correct, but measured 2x SLOWER on the 100 -> 100 convs (12.5 vs 5.7 ms,
+  // 7.7 vs 4.4 ms per step): the per-unit hand-shake (both CTAs free + re-arm a slot, remote arrive, cluster-scope wait) costs more
+  // than the 5-6 slot ring can hide.  Opt-in for experiments only.
+  static const bool mcast_off = getenv("NSC_PLANE_MCAST") == nullptr;
   if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
   else if (c.kind == PK_GEN) plane_x_kernel<true><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
-  else plane_x_kernel<false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
+  else if (!p.resident && !mcast_off && grid % 2 == 0 && p.n_tiles % grid == 0) {
+    // ring-streamed weights (the 100 -> 100 convs): CTA pairs share every weight unit through one multicast copy
+    p.mcast = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kXThreadsX);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NSC_CUDA_OK(cudaLaunchKernelEx(&cfg, plane_x_kernel<false>, p));
+  } else plane_x_kernel<false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }

@@ -103,6 +103,23 @@ def test_tap_shift_layers(layer, precision):
         assert e < (2e-5 if precision == 1 else 4e-3), (B, e)
 
 
+@pytest.mark.parametrize('layer', [X_LAYERS[4], X_LAYERS[5]], ids=['down_s2', 'up_shuffle'])
+def test_weight_multicast_pairs(layer, monkeypatch):
+    """296 frames = a whole number of tiles per CTA: with NSC_PLANE_MCAST set the 100 -> 100 convs run as 2-CTA clusters whose weight
+    units arrive by ONE multicast copy per pair (plane_x_kernel, ring mode; opt-in because it measured slower); results must not
+    change.  The switch is read once per process, so the multicast run happens in a child process."""
+    import os, subprocess, sys
+    e = _run(B=296, precision=1, seed=11, **layer)
+    assert e < 2e-5, e
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_gpu_plane as t\n"
+            "e = t._run(B=296, precision=1, seed=11, **%r)\n"
+            "assert e < 2e-5, e\n") % (root, os.path.join(root, 'tests'), layer)
+    env = dict(os.environ, NSC_PLANE_MCAST='1')
+    subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=300)
+
+
 def test_unsupported_shape_fails_loudly():
     from nsc_b200 import _lib
     lib = _lib.load()
