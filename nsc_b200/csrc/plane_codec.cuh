@@ -47,11 +47,13 @@ struct PlaneCodecPlan {
   int64_t act_bytes_per_frame = 0;
   std::vector<PlaneConv> enc, dec;
   std::vector<int> enc_layer, dec_layer;  // index into the codec's layer table (parameter offsets)
+  struct Io { int in, out, res; };        // activation buffers of a layer (PBuf ids, -1 = the 1-channel vector at the edge)
+  std::vector<Io> enc_io, dec_io;
   std::vector<int64_t> w_off;             // packed-weight offset of every layer (enc then dec)
   int64_t wpack_bytes = 0;
 };
 
-// Lays the codec out as plane layers.  Tensors carry offsets (base = nullptr + offset) until bound to a workspace.
+// Lays the codec out as plane layers.  Tensors carry geometry only (base = nullptr) until plane_bind() attaches a workspace.
 PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   PlaneCodecPlan pl;
   pl.planes = c.precision == 1 ? 2 : 1;
@@ -78,16 +80,13 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   int layer = 0;   // creation-order layer index (same walk as Walker::encoder / decoder)
   auto add = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int kind, int Lin, int Cin, int Cout, int K, int dil, int stride,
                  int act, int in, int out, int res, int res_mode, int post, int shuffle) {
+    (&v == &pl.enc ? pl.enc_io : pl.dec_io).push_back(PlaneCodecPlan::Io{in, out, res});
     PlaneConv pc;
     pc.kind = kind; pc.Lin = Lin; pc.Cin = Cin; pc.Cout = Cout; pc.K = K; pc.dil = dil; pc.stride = stride;
     pc.act = act; pc.post_act = post; pc.res_mode = res_mode; pc.shuffle = shuffle; pc.planes = P;
     if (in >= 0) pc.in = pl.buf[in];
     if (out >= 0) pc.out = pl.buf[out];
     if (res >= 0) pc.res = pl.buf[res];
-    // buffer ids ride in the (still null) base pointers until bind()
-    pc.in.base = reinterpret_cast<uint8_t*>((intptr_t)(in + 1));
-    pc.out.base = reinterpret_cast<uint8_t*>((intptr_t)(out + 1));
-    pc.res.base = reinterpret_cast<uint8_t*>((intptr_t)(res + 1));
     v.push_back(pc);
     vl.push_back(layer++);
   };
@@ -128,7 +127,6 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   auto size_w = [&](std::vector<PlaneConv>& v) {
     for (auto& pc : v) {
       PlaneConv t = pc;
-      t.in.base = t.out.base = t.res.base = nullptr;
       const float dummy = 0.f;
       if (t.Cin == 1) t.xvec = &dummy;
       if (t.res_mode == RES_ADD_BCAST) t.resvec = &dummy;
@@ -156,23 +154,20 @@ void plane_bind(PlaneCodecPlan& pl, const CodecLayout& lay, const float* params,
   uint8_t* addr[PB_COUNT];
   for (int i = 0; i < PB_COUNT; ++i) { addr[i] = base; base += align_up(pl.buf[i].frame_bytes * Bc, 1024); }
   size_t li = 0;
-  auto fix = [&](std::vector<PlaneConv>& v, std::vector<int>& vl) {
+  auto fix = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, const std::vector<PlaneCodecPlan::Io>& io) {
     for (size_t i = 0; i < v.size(); ++i, ++li) {
       PlaneConv& pc = v[i];
-      auto resolve = [&](PlaneTensor& t) {
-        const intptr_t id = reinterpret_cast<intptr_t>(t.base);   // buffer id + 1, or an already bound address
-        if (id >= 1 && id <= PB_COUNT) t.base = addr[id - 1];
-        else if (id == 0) t.base = nullptr;
-      };
-      resolve(pc.in); resolve(pc.out); resolve(pc.res);
+      pc.in.base = io[i].in >= 0 ? addr[io[i].in] : nullptr;
+      pc.out.base = io[i].out >= 0 ? addr[io[i].out] : nullptr;
+      pc.res.base = io[i].res >= 0 ? addr[io[i].res] : nullptr;
       const LayerInfo& info = lay.layers[vl[i]];
       pc.w = params + info.off;
       pc.bias = pc.w + (int64_t)info.k * info.cin * info.cout;
       pc.wpack = static_cast<uint8_t*>(wpack) + pl.w_off[li];
     }
   };
-  fix(pl.enc, pl.enc_layer);
-  fix(pl.dec, pl.dec_layer);
+  fix(pl.enc, pl.enc_layer, pl.enc_io);
+  fix(pl.dec, pl.dec_layer, pl.dec_io);
 }
 
 int plane_codec_pack(PlaneCodecPlan& pl, cudaStream_t st) {

@@ -1,0 +1,63 @@
+"""Host-side logic of the plane engine, no GPU needed: which layer shapes the tensor engine plans (and which it refuses, loudly),
+workspace sizes of the codec entry points on the plane path, bit-packing sizes, frame counts."""
+import numpy as np
+import pytest
+
+from nsc_b200 import _lib, codec
+
+
+def _ws(B, Lin, Cin, Cout, k, dil=1, stride=1, res_mode=0, shuffle=1, precision=1):
+    return _lib.load().nsc_conv1d_tc_workspace_bytes(B, Lin, Cin, Cout, k, dil, stride, res_mode, shuffle, precision)
+
+
+def test_codec_layer_shapes_are_planned():
+    # every conv shape of the '9 9 100 20 1 2' / stride-2 codec, both precisions
+    shapes = [
+        (512, 1, 100, 55, 1, 1, 0, 1), (512, 100, 20, 9, 1, 1, 0, 1), (512, 20, 20, 9, 2, 1, 0, 1), (512, 20, 100, 9, 1, 1, 1, 1),
+        (512, 100, 100, 9, 1, 2, 0, 1), (256, 100, 1, 55, 1, 1, 0, 1), (256, 1, 20, 9, 1, 1, 0, 1), (256, 20, 100, 9, 1, 1, 2, 1),
+        (256, 100, 100, 9, 1, 1, 0, 2), (512, 50, 20, 9, 1, 1, 0, 1), (512, 20, 50, 9, 1, 1, 1, 1), (512, 50, 1, 55, 1, 1, 0, 1),
+    ]
+    for prec in (1, 2):
+        for (L, cin, cout, k, dil, stride, res, sh) in shapes:
+            n = _ws(64, L, cin, cout, k, dil, stride, res, sh, prec)
+            assert n > 0, ((L, cin, cout, k, dil, stride, res, sh, prec), _lib.last_error())
+    # hi/lo planes need more workspace than fp16 planes
+    assert _ws(64, 512, 100, 20, 9, precision=1) > _ws(64, 512, 100, 20, 9, precision=2)
+
+
+@pytest.mark.parametrize('bad', [
+    dict(Lin=500, Cin=100, Cout=20, k=9),                 # length not a multiple of 128
+    dict(Lin=512, Cin=100, Cout=100, k=15, dil=2),        # 14-row halo does not fit the 8 zero rows of an image
+    dict(Lin=512, Cin=100, Cout=100, k=9, stride=3),      # stride
+    dict(Lin=512, Cin=200, Cout=100, k=9),                # more than 128 input channels
+    dict(Lin=512, Cin=100, Cout=100, k=9, precision=0),   # fp32 is not a tensor-engine mode
+])
+def test_unsupported_shapes_are_refused(bad):
+    assert _ws(8, **bad) < 0
+    assert _lib.last_error() != ''
+
+
+def test_codec_workspace_sizes_on_the_plane_path():
+    lib = _lib.load()
+    cfg = codec.CodecConfig(precision='tc_f16x3').to_struct()
+    cfg32 = codec.CodecConfig(precision='fp32').to_struct()
+    import ctypes as C
+    one = lib.nsc_codec_workspace_bytes(C.byref(cfg), 1)
+    big = lib.nsc_codec_workspace_bytes(C.byref(cfg), 100000)
+    chunk = lib.nsc_codec_workspace_bytes(C.byref(cfg), 2072)
+    assert 0 < one < chunk == big                           # capped at one chunk of 14 x 148 frames
+    per_frame = (chunk - one) / 2071
+    assert 1.5e6 < per_frame < 1.7e6                        # 11 plane buffers: 1.57 MB per frame
+    assert lib.nsc_codec_workspace_bytes(C.byref(cfg32), 2048) < chunk   # fp32 NCL buffers are smaller
+    # configurations outside the plane path keep the layer-by-layer workspace
+    gln = codec.CodecConfig(resnet_type='gln', precision='tc_f16x3').to_struct()
+    assert lib.nsc_codec_workspace_bytes(C.byref(gln), 2048) < chunk
+
+
+def test_framing_and_packing_sizes():
+    lib = _lib.load()
+    for T in (0, 512, 513, 992, 993, 48000):
+        assert lib.nsc_segment_count(T) == len(range(0, T - 512, 480))
+    assert lib.nsc_lpc_window_count(99) == 97 and lib.nsc_lpc_window_count(2) == 0
+    assert lib.nsc_packed_row_bytes(256, 5) == 160 and lib.nsc_packed_row_bytes(16, 8) == 16 and lib.nsc_packed_row_bytes(7, 3) == 3
+    assert lib.nsc_iir_workspace_bytes(1000, 2) >= 2 * 1000 * 8
