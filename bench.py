@@ -187,16 +187,42 @@ def run_ours(args):
         return cm.feedforward_lpc(x_dev, lsf, False, 1.0)
 
     out_host = {}
+    # End-to-end step through the public API with HOST buffers: the batch goes through in sub-batches so that the pinned-memory
+    # H2D copy of sub-batch k+1 and the D2H copy of sub-batch k-1 (copy stream) run under the compute of sub-batch k.
+    n_sub = max(1, min(4, B // 4144))
+    bounds = [(i * B // n_sub, (i + 1) * B // n_sub) for i in range(n_sub)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [None] * n_sub
 
     def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        wd = win_host.to(dev, non_blocking=True)
-        lsf = lu.lpc_analysis_windows(wd, 16, dtype=torch.float32)
-        r = cm.feedforward_lpc(xd, lsf, False, 1.0)
-        for k, t in [('lsf_idx', r['lsf_idx']), ('syn', r['synthesized'])] + [('idx%d' % i, t) for i, t in enumerate(r['idx'])]:
-            if k not in out_host:
-                out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            out_host[k].copy_(t, non_blocking=True)
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)
+        h2d_done = []
+        for i, (lo, hi) in enumerate(bounds):
+            with torch.cuda.stream(copy_stream):
+                dev_in[i] = (x_host[lo:hi].to(dev, non_blocking=True), win_host[lo:hi].to(dev, non_blocking=True))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                h2d_done.append(ev)
+        r = None
+        for i, (lo, hi) in enumerate(bounds):
+            main.wait_event(h2d_done[i])
+            xd, wd = dev_in[i]
+            lsf = lu.lpc_analysis_windows(wd, 16, dtype=torch.float32)
+            r = cm.feedforward_lpc(xd, lsf, False, 1.0)
+            done = torch.cuda.Event()
+            done.record(main)
+            outs = [('lsf_idx', r['lsf_idx']), ('syn', r['synthesized'])] + [('idx%d' % k, t) for k, t in enumerate(r['idx'])]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                for k, t in outs:
+                    if k not in out_host:
+                        out_host[k] = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                    out_host[k][lo:hi].copy_(t, non_blocking=True)
+                    t.record_stream(copy_stream)
+            xd.record_stream(main)
+            wd.record_stream(main)
+        main.wait_stream(copy_stream)
         return r
 
     def barrier():
