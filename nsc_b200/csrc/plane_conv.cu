@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
       };
       for (int j = 0; j < T; ++j, ++it) {
         const uint32_t acc_i = two_acc ? (it & 1u) : 0u;
-        mbar_wait(&acc_full[acc_i], two_acc ? (it >> 1) & 1u : it & 1u);
+        mbar_wait_relaxed(&acc_full[acc_i], two_acc ? (it >> 1) & 1u : it & 1u);
         tc_fence_after();
         float acc[NCHMAX], up[NCHMAX], down[NCHMAX];
         const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + acc_i * (uint32_t)p.N + (uint32_t)(grp * 8);
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
         const uint8_t* img = p.in.base + f * p.in.frame_bytes;
         for (int j = 0; j < T; ++j) {
           for (int s = 0; s < nst; ++s) {
-            mbar_wait(&a_empty[slot], sph);
+            mbar_wait_relaxed(&a_empty[slot], sph);
             mbar_expect_tx(&a_full[slot], kAStage);
             bulk_g2s(sA + slot * kAStage, img + s * sb + (int64_t)(8 + 128 * j) * 128, kAStage, &a_full[slot]);
             if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
@@ -646,7 +646,7 @@ __device__ __forceinline__ void gen_producer(const XParams& p, int ptid, int lan
           s_xh[j] = h;
           s_xl[j] = __float2half_rn(x - __half2float(h));
         }
-        for (int ap = 0; ap < p.planes; ++ap) mbar_wait(&a_empty[kb + ap], ph);
+        for (int ap = 0; ap < p.planes; ++ap) mbar_wait_relaxed(&a_empty[kb + ap], ph);
         asm volatile("bar.sync 2, %0;" :: "n"(kXGenWarps * 32) : "memory");
         uint8_t* dhi = sA + kb * (uint32_t)p.stage_bytes;
         uint8_t* dlo = dhi + p.stage_bytes;
@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       rn.s = 0.f; rn2.s = 0.f;
       load_res(grp, rn);                 // the residual does not depend on the accumulator: two batches are fetched
       load_res(grp + kXEpiGroups, rn2);  // before waiting for it, and the pipeline stays two batches deep
-      mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
+      mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
       tc_fence_after();
       for (int u = grp; u < n_e; u += kXEpiGroups) {
         const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
@@ -992,7 +992,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
           for (int sub = 0; sub < nsub; ++sub)
             for (int ap = 0; ap < npl; ++ap) {
               const int stage = pt_slab_index(p.in, sub, ap, s);
-              mbar_wait(&a_empty[kb + stage], ph);
+              mbar_wait_relaxed(&a_empty[kb + stage], ph);
               mbar_expect_tx(&a_full[kb + stage], (uint32_t)p.stage_bytes);
               bulk_g2s(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes, img + stage * sb + (int64_t)q0 * 128, (uint32_t)p.stage_bytes,
                        &a_full[kb + stage]);
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         uint32_t ws = 0, wph = 1;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           for (int u = 0; u < p.n_units; ++u) {
-            mbar_wait(&w_empty[ws], wph);
+            mbar_wait_relaxed(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
             bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
             if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         uint32_t ws = 0, wph = 1, rph = 0;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           for (int u = 0; u < p.n_units; ++u) {
-            mbar_wait(&w_empty[ws], wph);
+            mbar_wait_relaxed(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
             mbar_arrive_remote(&w_ready[ws], 0u);
             if (rank == 0) {
@@ -1121,13 +1121,13 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
       const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
       const uint32_t acc_i = it & 1u;
       const float* rvec = p.res_mode == RES_ADD_BCAST ? p.resvec + f * p.Lout : nullptr;
-      mbar_wait(&acc_full[acc_i], (it >> 1) & 1u);
+      mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
       tc_fence_after();
       for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
         const float rv = rvec ? __ldg(rvec + q0 + mt_i * 128 + lr) : 0.f;
         for (int s = 0; s < ospp; ++s) {
           const int nbs = min(4, nb - 4 * s);
-          mbar_wait(&st_full[slot], sph);
+          mbar_wait_relaxed(&st_full[slot], sph);
           uint8_t* unit = sS + slot * stg_bytes;
           const bool mine = grp < nbs;
           const int c0 = 64 * s + 16 * grp;              // first column / channel of this warp's batch
@@ -1202,7 +1202,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
-        mbar_wait(&a_empty[kb], ph);
+        mbar_wait_relaxed(&a_empty[kb], ph);
         mbar_expect_tx(&a_full[kb], (uint32_t)p.stage_bytes);
         bulk_g2s(sA + kb * (uint32_t)p.stage_bytes, p.in.base + f * p.in.frame_bytes + (int64_t)q0 * 128, (uint32_t)p.stage_bytes, &a_full[kb]);
         if (p.kbuf == 2) { kb ^= 1u; if (kb == 0) ph ^= 1u; }
@@ -1221,7 +1221,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
         uint32_t ws = 0, wph = 1;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           for (int u = 0; u < p.n_units; ++u) {
-            mbar_wait(&w_empty[ws], wph);
+            mbar_wait_relaxed(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
             bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
             if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
@@ -1240,7 +1240,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         for (int mt_i = 0; mt_i < p.mt; ++mt_i)
           for (int s = 0; s < ospp; ++s) {
-            mbar_wait(&st_empty[slot], ph);
+            mbar_wait_relaxed(&st_empty[slot], ph);
             if (has_res) {
               mbar_expect_tx(&st_full[slot], stg_bytes);
               for (int pl = 0; pl < p.planes; ++pl)
@@ -1265,7 +1265,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
         uint8_t* oimg = p.out.base + f * p.out.frame_bytes;
         for (int mt_i = 0; mt_i < p.mt; ++mt_i)
           for (int s = 0; s < ospp; ++s) {
-            mbar_wait(&st_done[slot], ph);
+            mbar_wait_relaxed(&st_done[slot], ph);
             const int p0 = q0 + mt_i * 128;
             for (int pl = 0; pl < p.planes; ++pl) {
               const uint8_t* src = sS + slot * stg_bytes + (uint32_t)pl * kSPlane;
