@@ -1,22 +1,28 @@
 // Plane engine: the codec's conv layers on tcgen05 with fp16 plane-image activations (plane.cuh).
 //
-// Two kernels, both persistent and warp-specialised (bulk-copy loaders, ONE MMA-issuing thread, epilogue warps; all
-// hand-offs are mbarriers, tensor-core completions arrive through tcgen05.commit):
+// Three kernels, all persistent (one CTA per SM) and warp-specialised -- bulk-copy loader threads, one or two MMA-issuing
+// threads, epilogue warps; every hand-off is an mbarrier and tensor-core completions arrive through tcgen05.commit:
 //
-//   plane_t_kernel  PK_T  "taps in N".  A CTA walks whole frames, tile by tile (128 positions).  Per tile ONE MMA chain
-//                   computes P[row, (tap, co)] for all taps at once (N = 9 * 20 -> 192: 96 cycles per K step instead of
-//                   9 x 44 for nine N = 32 instructions) with the layer's packed weights RESIDENT in shared memory and
-//                   the input streamed slab by slab through a ring.  The tap sum y[row] = sum_t P[row + s_t, t] crosses
-//                   TMEM lanes: each epilogue warp owns 32 rows, pulls P[row + s_t] from lane (lane + s_t) mod 32 with a
-//                   shuffle, and the wrapped lanes accumulate the contribution that belongs to the SAME lane of the
-//                   neighbouring 32-row quarter ("up"/"down" spill).  Quarters are finished in row order: a quarter's
-//                   first rows take the previous quarter's up-spill, its last rows are parked in shared memory and
-//                   finished by the next quarter, which holds their down-spill.  No halo is ever loaded or recomputed.
-//   plane_x_kernel  PK_X  one MMA per (tap, K step): a tap is a row shift of the A descriptor inside the staged tile
-//                   (+8 halo rows each side, which are the zero rows of the image at frame borders).  Weights stay
-//                   resident when they fit, else stream through a ring; with hi/lo planes every W_hi unit is used for
-//                   both the A_hi and A_lo products while it is resident.  PK_GEN feeds the same pipeline from a
-//                   Toeplitz tile that producer warps build from a 1-channel fp32 signal.
+//   plane_t_kernel   PK_T  "taps in N".  A CTA walks whole frames, tile by tile (128 positions).  Per tile ONE MMA chain
+//                    computes P[row, (tap, co)] for all taps at once (N = 9 * 20 -> 192: 96 cycles per K step instead of
+//                    9 x 44 for nine N = 32 instructions) with the layer's packed weights RESIDENT in shared memory and
+//                    the input streamed slab by slab through a ring.  The tap sum y[row] = sum_t P[row + s_t, t] crosses
+//                    TMEM lanes: each epilogue warp owns 32 rows (12 warps: 4 lane quarters x three 8-channel chunks), pulls
+//                    P[row + s_t] from lane (lane + s_t) mod 32 with a shuffle, and the wrapped lanes accumulate the
+//                    contribution that belongs to the SAME lane of the neighbouring quarter ("up"/"down" spill).  Quarters
+//                    are finished in row order: a quarter's first rows take the previous quarter's up-spill, its last rows
+//                    are parked in shared memory and finished by the next quarter, which holds their down-spill.  No halo
+//                    is ever loaded or recomputed.  Finished rows go to a shared-memory ring that mirrors the output image
+//                    and leave by one bulk store per tile.
+//   plane_x_kernel   PK_X  one MMA per (tap, K step): a tap is a row shift of the A descriptor inside the staged tile
+//                    (+8 halo rows each side, which are the zero rows of the image at frame borders).  Weights stay
+//                    resident when they fit, else stream through a ring; with hi/lo planes every W_hi unit is used for
+//                    both the A_hi and A_lo products while it is resident.  The 100 -> 100 convs (stride 2 / sub-pixel).
+//                    <true>: PK_GEN, the same pipeline fed from a Toeplitz tile that producer warps build from a 1-channel
+//                    fp32 signal (decoder's k9 1 -> 20).
+//   plane_xs_kernel  PK_X / PK_GEN with a STAGED epilogue (narrow-input 20 -> 100 / 20 -> 50 + residual, and the k55 stem): the
+//                    residual tile comes in and the result goes out by bulk copies through shared-memory units; no thread
+//                    touches global memory.
 //
 // Epilogues write the next layer's plane image directly (bias, activation, residual add from the residual's planes,
 // hi/lo split, sub-pixel shuffle, stride-2 de-interleave are all index arithmetic on the way out).
