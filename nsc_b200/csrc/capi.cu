@@ -1,4 +1,5 @@
 // Library-wide pieces of the C ABI: version, thread-local error message, device attribute cache.
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -25,6 +26,10 @@ int sm_count() {
   if (cached[dev] == 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (const char* e = getenv("NSC_SMS")) {   // experiments: persistent grids of fewer CTAs (two streams side by side)
+      const int cap = atoi(e);
+      if (cap >= 1 && cap < n) n = cap;
+    }
     cached[dev] = n;   // immutable once written; a benign race writes the same value
   }
   return cached[dev];

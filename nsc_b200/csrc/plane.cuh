@@ -79,6 +79,8 @@ struct PlaneConv {
   int64_t B = 0;
 };
 
+// kernel family of the narrow -> narrow convs (20 -> 20): NSC_PLANE_NARROW=T|X overrides the default
+int plane_narrow_kind();
 bool plane_conv_supported(const PlaneConv& c);
 int64_t plane_wpack_bytes(const PlaneConv& c);
 int plane_pack_weights(const PlaneConv& c, cudaStream_t st);

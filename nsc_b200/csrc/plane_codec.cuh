@@ -76,7 +76,7 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
 
   // narrow -> narrow convs (20 -> 20): taps-in-N by default; the tap-shift kernel is within 5 % here (measured 5.6 vs 5.3 ms per
   // step: nine N = 32 MMAs per K step issue-bound vs the tap-sum epilogue) and can be selected for experiments
-  static const int kNarrowKind = getenv("NSC_PLANE_NARROW_X") ? PK_X : PK_T;
+  const int kNarrowKind = plane_narrow_kind();
   int layer = 0;   // creation-order layer index (same walk as Walker::encoder / decoder)
   auto add = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int kind, int Lin, int Cin, int Cout, int K, int dil, int stride,
                  int act, int in, int out, int res, int res_mode, int post, int shuffle) {

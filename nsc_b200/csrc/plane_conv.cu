@@ -186,11 +186,23 @@ __device__ __forceinline__ float act_fast(float v, float slope) { return fmaxf(v
 __device__ __noinline__ float act_slow(float v, int act) { return apply_act(v, act); }
 
 // K steps of one (A tile, B unit) pair from the issuing thread; descriptors advance 32 bytes (2 units of 16 B) per step
-template <int NKS>
+// MODE: 0 = one CTA; 1 = leader of a CTA pair (cta_group::2 instructions, M = 256); 2 = the leader's peer, which issues nothing
+// (its issuing thread only forwards "operand landed" to the leader, see XIssue)
+template <int NKS, int MODE = 0>
 __device__ __forceinline__ void issue_ks(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum0) {
+  if constexpr (MODE == 2) return;
 #pragma unroll
-  for (int ks = 0; ks < NKS; ++ks)
-    mma_f16_ss(d, desc_from_lo(a_lo + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc, ks == 0 ? accum0 : 1u);
+  for (int ks = 0; ks < NKS; ++ks) {
+    if constexpr (MODE == 1)
+      mma_f16_ss_cg2(d, desc_from_lo(a_lo + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc, ks == 0 ? accum0 : 1u);
+    else
+      mma_f16_ss(d, desc_from_lo(a_lo + 2u * (uint32_t)ks), desc_from_lo(b_lo + 2u * (uint32_t)ks), idesc, ks == 0 ? accum0 : 1u);
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void commit_mode(uint64_t* bar) {
+  if constexpr (MODE == 0) umma_commit(bar);
+  else if constexpr (MODE == 1) umma_commit_cg2(bar);
 }
 __device__ __forceinline__ void issue_n(int nks, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum0) {
   switch (nks) {
@@ -608,7 +620,9 @@ struct XParams {
   int zero_from, zero_to;    // output chunks the epilogue must clear (K padding the consumer will read)
   int staged;                // plane_xs_kernel: epilogue through shared-memory units and bulk copies
   int n_iss;                 // MMA-issuing threads (1, or one per M tile)
-  int mcast;                 // 2-CTA clusters: CTA 0's loader multicasts every weight unit to both CTAs (halves the L2 weight stream)
+  int pair;                  // CTA pairs (cta_group::2): each CTA stages its own tile and HALF of every weight unit; the leader's
+                             // M = 256 instructions cover both tiles (half the weight stream, half the instructions per tile)
+  int slot_bytes;            // shared-memory bytes of one weight unit in this CTA (unit_bytes, or half of it in a pair)
   int64_t B, n_tiles;
 };
 
@@ -689,7 +703,18 @@ __device__ __forceinline__ void gen_producer(const XParams& p, int ptid, int lan
 // from a single thread, more than the 44-60 cycles the narrow MMAs of this codec take on the tensor pipe.
 struct XBars {
   uint64_t *a_full, *a_empty, *w_full, *w_empty, *acc_full, *acc_empty;
+  uint64_t *a_full2, *w_full2;      // CTA pairs: the peer's "landed" reports, in the leader's shared memory
 };
+
+// "operand landed" of a CTA pair: every CTA's copies complete on its own barrier; the peer's issuing thread forwards each
+// completion to the leader's twin barrier, the leader waits for both.
+template <int MODE>
+__device__ __forceinline__ void wait_full(uint64_t* mine, uint64_t* twin, uint32_t parity) {
+  mbar_wait(mine, parity);
+  if constexpr (MODE == 1) mbar_wait(twin, parity);
+  if constexpr (MODE == 2) mbar_arrive_remote(twin, 0u);
+  tc_fence_after();
+}
 
 struct XIssue {
   uint32_t d, idesc;                // this issuer's first accumulator
@@ -700,56 +725,56 @@ struct XIssue {
   bool resident, w_ready;
   int wslots;
   const XBars* b;
+  template <int MODE>
   __device__ __forceinline__ uint32_t wait_w() {
     if (resident) {
-      if (!w_ready) { mbar_wait(&b->w_full[u], 0u); tc_fence_after(); }
+      if (!w_ready) wait_full<MODE>(&b->w_full[u], &b->w_full2[u], 0u);
       return w_lo_base + u * unit_lo;
     }
-    mbar_wait(&b->w_full[ws], wph);
-    tc_fence_after();
+    wait_full<MODE>(&b->w_full[ws], &b->w_full2[ws], wph);
     return w_lo_base + ws * unit_lo;
   }
+  template <int MODE>
   __device__ __forceinline__ void done_w() {
     if (!resident) {
-      umma_commit(&b->w_empty[ws]);
+      commit_mode<MODE>(&b->w_empty[ws]);
       if (++ws == (uint32_t)wslots) { ws = 0; wph ^= 1u; }
     }
     ++u;
   }
 };
 
-template <int NKS>
+template <int NKS, int MODE>
 __device__ __forceinline__ void x_issue_mt(const XIssue& x, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
-  issue_ks<NKS>(x.d, a_lo, b_lo, x.idesc, accum);
-  if (x.nmt == 2) issue_ks<NKS>(x.d + x.npad, a_lo + ((128u * 128u) >> 4), b_lo, x.idesc, accum);
+  issue_ks<NKS, MODE>(x.d, a_lo, b_lo, x.idesc, accum);
+  if (x.nmt == 2) issue_ks<NKS, MODE>(x.d + x.npad, a_lo + ((128u * 128u) >> 4), b_lo, x.idesc, accum);
 }
 
 // narrow (packed [hi | lo]) input: per tap hi*W_hi, hi*W_lo, lo*W_hi
-template <int NKS>
+template <int NKS, int MODE>
 __device__ __forceinline__ void x_issue_packed(XIssue& x, const XParams& p, uint32_t a_lo0) {
   uint32_t accum = 0;
   for (int t = 0; t < p.K; ++t) {
-    const uint32_t b_lo = x.wait_w();
+    const uint32_t b_lo = x.wait_w<MODE>();
     const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
-    x_issue_mt<NKS>(x, a_lo, b_lo, accum);
+    x_issue_mt<NKS, MODE>(x, a_lo, b_lo, accum);
     if (p.planes == 2) {
-      x_issue_mt<NKS>(x, a_lo, b_lo + 4u, 1u);
-      x_issue_mt<NKS>(x, a_lo + 4u, b_lo, 1u);
+      x_issue_mt<NKS, MODE>(x, a_lo, b_lo + 4u, 1u);
+      x_issue_mt<NKS, MODE>(x, a_lo + 4u, b_lo, 1u);
     }
     accum = 1;
-    x.done_w();
+    x.done_w<MODE>();
   }
 }
 
 // one 64-channel slab of a wide input: per tap the W_hi unit meets the hi and the lo plane, the W_lo unit the hi plane
-template <int NKS>
+template <int NKS, int MODE>
 __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s, uint32_t a_stage0, uint32_t stage_lo, uint32_t kb,
                                              uint32_t a_phase, uint32_t& waited, uint32_t& accum) {
   const int spp = p.in.spp;
   auto wait_stage = [&](int stage) {
     if (!((waited >> stage) & 1u)) {
-      mbar_wait(&x.b->a_full[kb + stage], a_phase);
-      tc_fence_after();
+      wait_full<MODE>(&x.b->a_full[kb + stage], &x.b->a_full2[kb + stage], a_phase);
       waited |= 1u << stage;
     }
   };
@@ -761,21 +786,22 @@ __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s,
     const uint32_t a_hi = a_stage0 + (uint32_t)st_hi * stage_lo + (uint32_t)rowoff * 8u;
     const uint32_t a_lo_pl = a_hi + (uint32_t)spp * stage_lo;     // the lo plane's stage is spp slabs further
     {
-      const uint32_t b_lo = x.wait_w();
+      const uint32_t b_lo = x.wait_w<MODE>();
       wait_stage(st_hi);
-      x_issue_mt<NKS>(x, a_hi, b_lo, accum);
+      x_issue_mt<NKS, MODE>(x, a_hi, b_lo, accum);
       accum = 1;
-      if (p.planes == 2) { wait_stage(st_hi + spp); x_issue_mt<NKS>(x, a_lo_pl, b_lo, 1u); }
-      x.done_w();
+      if (p.planes == 2) { wait_stage(st_hi + spp); x_issue_mt<NKS, MODE>(x, a_lo_pl, b_lo, 1u); }
+      x.done_w<MODE>();
     }
     if (p.planes == 2) {
-      const uint32_t b_lo = x.wait_w();
-      x_issue_mt<NKS>(x, a_hi, b_lo, 1u);
-      x.done_w();
+      const uint32_t b_lo = x.wait_w<MODE>();
+      x_issue_mt<NKS, MODE>(x, a_hi, b_lo, 1u);
+      x.done_w<MODE>();
     }
   }
 }
 
+template <int MODE>
 __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer, uint8_t* sA, uint8_t* sW, uint32_t tmem, const XBars& bars) {
   const uint32_t mt_step = (128u * 128u) >> 4;
   const int m0 = p.n_iss == 2 ? issuer : 0;                       // first M tile of this thread
@@ -783,9 +809,9 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4;
   const int acc_cols = p.mt * p.Npad;
   XIssue x;
-  x.idesc = make_idesc_f16(p.Npad);
+  x.idesc = make_idesc_f16(p.Npad, MODE == 0 ? 128 : 256);
   x.w_lo_base = desc_lo(smem_u32(sW));
-  x.unit_lo = (uint32_t)p.unit_bytes >> 4;
+  x.unit_lo = (uint32_t)p.slot_bytes >> 4;
   x.ws = 0; x.wph = 0; x.u = 0;
   x.resident = p.resident != 0;
   x.w_ready = false;
@@ -796,34 +822,35 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   uint32_t it = 0, kb = 0, a_phase = 0;
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
     const uint32_t acc_i = it & 1u;
-    mbar_wait(&bars.acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+    if constexpr (MODE != 2) mbar_wait(&bars.acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);   // (pair: both CTAs' epilogues arrive on the leader's)
     tc_fence_after();
     x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)(m0 * p.Npad);
     x.u = 0;
     if (gen) {
-      uint32_t accum = 0;
-      for (int wp = 0; wp < p.planes; ++wp) {
-        const uint32_t b_lo = x.wait_w();
-        for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
-          if (wp == 0) { mbar_wait(&bars.a_full[kb + ap], a_phase); tc_fence_after(); }
-          for (int m = 0; m < x.nmt; ++m)
-            issue_n(p.ksteps, x.d + (uint32_t)m * x.npad, a_lo_base + (kb + (uint32_t)ap) * stage_lo + (uint32_t)m * mt_step, b_lo, x.idesc, accum);
-          accum = 1;
+      if constexpr (MODE == 0) {
+        uint32_t accum = 0;
+        for (int wp = 0; wp < p.planes; ++wp) {
+          const uint32_t b_lo = x.wait_w<0>();
+          for (int ap = 0; ap < (wp == 0 ? p.planes : 1); ++ap) {
+            if (wp == 0) { mbar_wait(&bars.a_full[kb + ap], a_phase); tc_fence_after(); }
+            for (int m = 0; m < x.nmt; ++m)
+              issue_n(p.ksteps, x.d + (uint32_t)m * x.npad, a_lo_base + (kb + (uint32_t)ap) * stage_lo + (uint32_t)m * mt_step, b_lo, x.idesc, accum);
+            accum = 1;
+          }
+          x.done_w<0>();
         }
-        x.done_w();
+        for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + ap]);
       }
-      for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + ap]);
     } else if (p.in.packed) {
-      mbar_wait(&bars.a_full[kb], a_phase);
-      tc_fence_after();
+      wait_full<MODE>(&bars.a_full[kb], &bars.a_full2[kb], a_phase);
       const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
       switch (p.ksteps) {
-        case 2: x_issue_packed<2>(x, p, a_lo0); break;
-        case 1: x_issue_packed<1>(x, p, a_lo0); break;
-        case 3: x_issue_packed<3>(x, p, a_lo0); break;
-        default: x_issue_packed<4>(x, p, a_lo0); break;
+        case 2: x_issue_packed<2, MODE>(x, p, a_lo0); break;
+        case 1: x_issue_packed<1, MODE>(x, p, a_lo0); break;
+        case 3: x_issue_packed<3, MODE>(x, p, a_lo0); break;
+        default: x_issue_packed<4, MODE>(x, p, a_lo0); break;
       }
-      umma_commit(&bars.a_empty[kb]);
+      commit_mode<MODE>(&bars.a_empty[kb]);
     } else {
       const int nsub = p.in.deint ? 2 : 1;
       uint32_t waited = 0, accum = 0;
@@ -831,28 +858,29 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
         const int nks = min(4, p.ksteps - 4 * s);
         const uint32_t a0 = a_lo_base + kb * stage_lo;
         switch (nks) {
-          case 4: x_issue_slab<4>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
-          case 3: x_issue_slab<3>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
-          case 2: x_issue_slab<2>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
-          default: x_issue_slab<1>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          case 4: x_issue_slab<4, MODE>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          case 3: x_issue_slab<3, MODE>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          case 2: x_issue_slab<2, MODE>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+          default: x_issue_slab<1, MODE>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
         }
         for (int sub = 0; sub < nsub; ++sub)
-          for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
+          for (int ap = 0; ap < p.planes; ++ap) commit_mode<MODE>(&bars.a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
       }
     }
-    umma_commit(&bars.acc_full[acc_i]);
+    commit_mode<MODE>(&bars.acc_full[acc_i]);
     x.w_ready = true;
     if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) a_phase ^= 1u; }
     else a_phase ^= 1u;
   }
 }
 
-template <bool kGen>
+template <bool kGen, bool kPair>
 __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_kernel(const __grid_constant__ XParams p) {
+  static_assert(!(kGen && kPair), "Toeplitz layers do not run as CTA pairs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[kXMaxStage], a_empty[kXMaxStage], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
-  __shared__ uint64_t w_ready[kXMaxW];     // multicast: both CTAs of the pair have freed and re-armed a ring slot (lives in CTA 0)
+  __shared__ uint64_t a_full2[kXMaxStage], w_full2[kXMaxW];   // CTA pairs: the peer's operands have landed (live in the leader)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(16) __half s_xh[kGen ? kGenSeg : 8], s_xl[kGen ? kGenSeg : 8];   // hi / lo halves of the tile's input samples
@@ -866,17 +894,22 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   constexpr int kIssuer1 = kGen ? kXEpiWarps + 3 + kXGenWarps : kXEpiWarps + 3;
 
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
+  constexpr bool pair = kPair;          // (a kernel that contains cta_group::2 instructions can only be launched as a cluster)
+  const uint32_t crank = pair ? cluster_ctarank() : 0u;
   if (tid == 0) {
-    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], n_iss); }
-    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_iss); mbar_init(&w_ready[i], 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], kXEpiWarps); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], n_iss); mbar_init(&a_full2[i], 1); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_iss); mbar_init(&w_full2[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], pair ? 2 * kXEpiWarps : kXEpiWarps); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (warp == kXEpiWarps) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == kXEpiWarps) {
+    if constexpr (pair) tmem_alloc_cg2(&tmem_base_s, (uint32_t)p.tmem_cols);
+    else tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // the peer's barriers (and TMEM) exist before anything arrives remotely
   tc_fence_after();
-  if (p.mcast) cluster_sync_all();          // the peer's barriers exist before anything is multicast or arrived remotely
   const uint32_t tmem = tmem_base_s;
 
   if (warp < kXEpiWarps) {
@@ -974,14 +1007,24 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc_i]);
+      if (lane == 0) {
+        if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);   // the leader's barrier counts both CTAs' epilogue warps
+        else mbar_arrive(&acc_empty[acc_i]);
+      }
     }
   } else if (warp == kXEpiWarps || warp == kIssuer1) {
     // =========================== MMA issuers ===========================
     const int issuer = warp == kXEpiWarps ? 0 : 1;
     if (issuer < n_iss && elect_one()) {
-      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty};
-      x_issuer(p, kGen, issuer, sA, sW, tmem, bars);
+      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty, a_full2, w_full2};
+      if constexpr (kGen) x_issuer<0>(p, true, issuer, sA, sW, tmem, bars);
+      else {
+        if constexpr (!pair) x_issuer<0>(p, false, issuer, sA, sW, tmem, bars);
+        else {
+          if (crank == 0) x_issuer<1>(p, false, issuer, sA, sW, tmem, bars);
+          else if (issuer == 0) x_issuer<2>(p, false, issuer, sA, sW, tmem, bars);   // the peer only reports what has landed
+        }
+      }
     }
   } else if (warp == kXEpiWarps + 1) {
     // =========================== A loader (bulk copies of plane tiles) ===========================
@@ -1010,36 +1053,22 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   } else if (warp == kXEpiWarps + 2) {
     // =========================== W loader ===========================
     if (elect_one()) {
+      // a CTA of a pair stages its half of every unit (output columns [rank Npad/2, (rank + 1) Npad/2))
+      const uint8_t* wsrc = p.wpack + (pair ? (size_t)crank * (size_t)p.slot_bytes : 0);
+      const uint32_t sbytes = (uint32_t)p.slot_bytes;
       if (p.resident) {
         for (int u = 0; u < p.n_units; ++u) {
-          mbar_expect_tx(&w_full[u], (uint32_t)p.unit_bytes);
-          bulk_g2s(sW + (uint32_t)u * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[u]);
+          mbar_expect_tx(&w_full[u], sbytes);
+          bulk_g2s(sW + (uint32_t)u * sbytes, wsrc + (size_t)u * p.unit_bytes, sbytes, &w_full[u]);
         }
-      } else if (!p.mcast) {
+      } else {
         uint32_t ws = 0, wph = 1;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           for (int u = 0; u < p.n_units; ++u) {
             mbar_wait_relaxed(&w_empty[ws], wph);
-            mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
-            bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
+            mbar_expect_tx(&w_full[ws], sbytes);
+            bulk_g2s(sW + ws * sbytes, wsrc + (size_t)u * p.unit_bytes, sbytes, &w_full[ws]);
             if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
-          }
-        }
-      } else {
-        // Both CTAs of the pair walk the same unit sequence (same layer, same number of tiles).  Each frees and re-arms its own
-        // slot, then reports to CTA 0, whose loader issues ONE copy that lands in both shared memories.
-        const uint32_t rank = cluster_ctarank();
-        uint32_t ws = 0, wph = 1, rph = 0;
-        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-          for (int u = 0; u < p.n_units; ++u) {
-            mbar_wait_relaxed(&w_empty[ws], wph);
-            mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
-            mbar_arrive_remote(&w_ready[ws], 0u);
-            if (rank == 0) {
-              mbar_wait_cluster(&w_ready[ws], rph);
-              bulk_g2s_mcast(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws], (uint16_t)3);
-            }
-            if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; rph ^= 1u; }
           }
         }
       }
@@ -1053,9 +1082,12 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // nobody frees TMEM (or retires) while the leader's instruction stream can still touch it
   tc_fence_after();
-  if (warp == kXEpiWarps) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
-  if (p.mcast) cluster_sync_all();          // neither CTA retires while its peer can still multicast into it or arrive on its barriers
+  if (warp == kXEpiWarps) {
+    if constexpr (pair) tmem_dealloc_cg2(tmem, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  }
 }
 
 // ================================================================================================
@@ -1198,8 +1230,8 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
     // =========================== MMA issuers (one per M tile) ===========================
     const int issuer = warp == kSEpiWarps ? 0 : 1;
     if (issuer < p.n_iss && elect_one()) {
-      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty};
-      x_issuer(p, gen, issuer, sA, sW, tmem, bars);
+      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty, nullptr, nullptr};
+      x_issuer<0>(p, gen, issuer, sA, sW, tmem, bars);
     }
   } else if (warp == kSEpiWarps + 1) {
     // =========================== A loader ===========================
@@ -1373,12 +1405,25 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   const size_t stg_total = p->staged ? (size_t)kSUnits * c.planes * kSPlane : 0;
   const size_t budget = kSmemBudget - stg_total;
   // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
+  // CTA pairs (cta_group::2) for the layers with a plain epilogue: each CTA of a pair keeps its own tile and half of every
+  // weight unit (half the weight stream into each shared memory, half the instructions).  Needs an even number of work units,
+  // otherwise the one-CTA kernel runs.  Measured (profiles/r01_pair_probe.log, cycles per tile): up-sampling conv (two M tiles,
+  // two issuing threads) 25.5 k -> 23.0 k; stride-2 conv (one M tile) 19.1 k -> 20.5 k, its 11-slot half-unit ring runs dry more
+  // often than the 5-slot ring did; 20 -> 20 is unchanged (an M = 256 instruction occupies BOTH tensor pipes for as long as an
+  // M = 128 one occupies one, so the ~44-cycle floor of narrow instructions is not halved).  Default: pairs where two M tiles
+  // share a weight pass; NSC_PLANE_PAIR=0 never, =2 wherever possible.
+  static const int pair_knob = [] { const char* e = getenv("NSC_PLANE_PAIR"); return e ? atoi(e) : 1; }();
   for (int mt = (Lout % 256 == 0 && c.stride == 1) ? 2 : 1; mt >= 1; --mt) {
     p->mt = mt;
     p->tile = 128 * mt;
     p->stage_bytes = (p->tile + 16) * 128;
+    p->tiles_per_frame = Lout / p->tile;
+    p->n_tiles = c.B * p->tiles_per_frame;
+    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && !p->staged && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
+    p->slot_bytes = p->pair ? p->unit_bytes / 2 : p->unit_bytes;
+    const size_t slot = (size_t)p->slot_bytes;
     const size_t a1 = (size_t)p->n_stage * p->stage_bytes;
-    const size_t wall = (size_t)p->n_units * p->unit_bytes;
+    const size_t wall = (size_t)p->n_units * slot;
     if (2 * mt * p->Npad > 512) continue;
     if (p->n_units <= kXMaxW && 2 * a1 + wall <= budget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
     else if (2 * a1 + 4ull * p->unit_bytes <= budget) { p->kbuf = 2; p->resident = 0; }
@@ -1387,13 +1432,11 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     else continue;
     if (p->n_stage * p->kbuf > kXMaxStage) { if (p->kbuf == 2 && !p->resident && a1 + 3ull * p->unit_bytes <= budget) p->kbuf = 1; else continue; }
     if (!p->resident) {
-      size_t ws = (budget - (size_t)p->kbuf * a1) / p->unit_bytes;
+      size_t ws = (budget - (size_t)p->kbuf * a1) / slot;
       if (ws > (size_t)kXMaxW) ws = kXMaxW;
       if (ws > (size_t)p->n_units) ws = p->n_units;
       p->wslots = (int)ws;
     }
-    p->tiles_per_frame = Lout / p->tile;
-    p->n_tiles = c.B * p->tiles_per_frame;
     int cols = 32;
     while (cols < 2 * mt * p->Npad) cols *= 2;
     p->tmem_cols = cols;
@@ -1406,11 +1449,11 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     p->zero_from = written;
     p->zero_to = needed > written ? needed : written;
     if (p->staged && (p->zero_from != p->zero_to || p->n_stage * p->kbuf > 4)) p->staged = 0;   // (never for the codec's shapes)
+    if (p->staged) { p->pair = 0; p->slot_bytes = p->unit_bytes; }
     {
       // one issuing thread per M tile where the issue rate, not HBM, bounds the layer (measured); the staged layers are HBM-bound
       static const int knob = [] { const char* e = getenv("NSC_PLANE_ISSUERS"); return e ? atoi(e) : 0; }();
       p->n_iss = (p->mt == 2 && !p->staged) ? 2 : 1;
-      p->mcast = 0;
       if (knob == 1) p->n_iss = 1;
       if (knob == 2 && p->mt == 2) p->n_iss = 2;
     }
@@ -1420,10 +1463,20 @@ bool plan_x(const PlaneConv& c, XParams* p) {
 }
 
 size_t x_smem_bytes(const XParams& p) {
-  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.unit_bytes + (p.staged ? (size_t)kSUnits * p.planes * kSPlane : 0);
+  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.slot_bytes + (p.staged ? (size_t)kSUnits * p.planes * kSPlane : 0);
 }
 
 }  // namespace
+
+int plane_narrow_kind() {
+  static const int kind = [] {
+    const char* e = getenv("NSC_PLANE_NARROW");
+    if (e && (e[0] == 'X' || e[0] == 'x')) return (int)PK_X;
+    if (e && (e[0] == 'T' || e[0] == 't')) return (int)PK_T;
+    return (int)PK_T;
+  }();
+  return kind;
+}
 
 bool plane_conv_supported(const PlaneConv& c) {
   if (c.planes != 1 && c.planes != 2) return false;
@@ -1513,24 +1566,18 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
   const size_t smem = x_smem_bytes(p);
   if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
   double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_payload_bytes(c.in));
   bytes += (double)c.B * pt_payload_bytes(c.out);
   if (c.res_mode == RES_ADD) bytes += (double)c.B * pt_payload_bytes(c.res);
   if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
   ProfScope prof(st, name, 2.0 * macs, bytes);
-  const int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  // Weight multicast across CTA pairs is implemented and correct, but measured 2x SLOWER on the 100 -> 100 convs (12.5 vs 5.7 ms,
-  // 7.7 vs 4.4 ms per step): the per-unit hand-shake (both CTAs free + re-arm a slot, remote arrive, cluster-scope wait) costs more
-  // than the 5-6 slot ring can hide.  Opt-in for experiments only.
-  static const bool mcast_off = getenv("NSC_PLANE_MCAST") == nullptr;
-  if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
-  else if (c.kind == PK_GEN) plane_x_kernel<true><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
-  else if (!p.resident && !mcast_off && grid % 2 == 0 && p.n_tiles % grid == 0) {
-    // ring-streamed weights (the 100 -> 100 convs): CTA pairs share every weight unit through one multicast copy
-    p.mcast = 1;
+  int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  if (p.pair) grid &= ~(int64_t)1;
+  auto launch_pairs = [&]() {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kXThreadsX);
@@ -1543,8 +1590,12 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NSC_CUDA_OK(cudaLaunchKernelEx(&cfg, plane_x_kernel<false>, p));
-  } else plane_x_kernel<false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
+    return cudaLaunchKernelEx(&cfg, plane_x_kernel<false, true>, p);
+  };
+  if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
+  else if (c.kind == PK_GEN) plane_x_kernel<true, false><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
+  else if (p.pair) NSC_CUDA_OK(launch_pairs());
+  else plane_x_kernel<false, false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
@@ -1589,6 +1640,7 @@ int make_tc_conv_plan(int64_t B, int Lin, int Cin, int Cout, int k, int dil, int
   int padL;
   same_padding(Lin, k, dil, stride, &pl->Lout, &padL);
   c.kind = Cin == 1 ? PK_GEN : (((Cout == 20 && k == 9) || (Cout == 1 && k == 55)) && res_mode == RES_NONE && stride == 1 && shuffle == 1) ? PK_T : PK_X;
+  if (c.kind == PK_T && Cin <= 32 && Cout == 20 && plane_narrow_kind() == PK_X) c.kind = PK_X;   // same choice as the codec program
   c.Lin = Lin; c.Cin = Cin; c.Cout = Cout; c.K = k; c.dil = dil; c.stride = stride;
   c.act = act; c.post_act = post_act; c.res_mode = res_mode; c.shuffle = shuffle;
   c.planes = precision == 1 ? 2 : 1;

@@ -24,8 +24,8 @@ __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
 }
 
 // kind::f16 instruction descriptor: fp16 A and B (both K-major), fp32 accumulator, M = 128
-__host__ __device__ inline uint32_t make_idesc_f16(int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ inline uint32_t make_idesc_f16(int N, int M = 128) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -36,6 +36,19 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// ---- CTA pairs (cta_group::2): ONE instruction of the leader CTA multiplies 256 rows of A (128 from each CTA's shared memory, same
+// offsets) with N rows of B (N/2 from each CTA); rows [128 r, 128 r + 128) of D land in CTA r's TMEM (tools/cg2_probe.cu).
+__device__ __forceinline__ void mma_f16_ss_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
@@ -75,7 +88,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// ---- thread-block cluster pieces (weight multicast) ----------------------------------------------------------------------
+// ---- thread-block cluster pieces (CTA pairs) ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -85,26 +98,13 @@ __device__ __forceinline__ void cluster_sync_all() {   // every thread of every 
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `target` of the cluster (release at cluster scope)
+// arrive on the mbarrier at the same shared-memory offset in CTA `target` of the cluster.  Default semantics (release at CTA scope),
+// as CUTLASS's ClusterBarrier does: a cluster-scope release costs the arriving thread ~900 cycles per arrive (measured,
+// profiles/r01_pair_probe_release_cluster.log), which serialises any per-unit hand-shake between the CTAs of a pair.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(raddr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  }
-}
-// global -> the same shared-memory offset of every CTA in `cta_mask`; completes `bytes` on each CTA's own mbarrier
-__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(raddr) : "memory");
 }
 // shared -> global bulk store, tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -126,6 +126,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t cols
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
+}
+// CTA-pair flavour: one warp of EACH CTA of the pair calls it
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* slot_in_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot_in_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
 }
 
 // TMEM -> registers, thread = lane (row), consecutive columns.  No wait inside: callers batch loads and then wait.

@@ -103,21 +103,34 @@ def test_tap_shift_layers(layer, precision):
         assert e < (2e-5 if precision == 1 else 4e-3), (B, e)
 
 
-@pytest.mark.parametrize('layer', [X_LAYERS[4], X_LAYERS[5]], ids=['down_s2', 'up_shuffle'])
-def test_weight_multicast_pairs(layer, monkeypatch):
-    """296 frames = a whole number of tiles per CTA: with NSC_PLANE_MCAST set the 100 -> 100 convs run as 2-CTA clusters whose weight
-    units arrive by ONE multicast copy per pair (plane_x_kernel, ring mode; opt-in because it measured slower); results must not
-    change.  The switch is read once per process, so the multicast run happens in a child process."""
+def _child(env_extra, body):
+    """Engine switches are read once per process: runs `body` (python source using test_gpu_plane as t) in a child process."""
     import os, subprocess, sys
-    e = _run(B=296, precision=1, seed=11, **layer)
-    assert e < 2e-5, e
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-            "import test_gpu_plane as t\n"
-            "e = t._run(B=296, precision=1, seed=11, **%r)\n"
-            "assert e < 2e-5, e\n") % (root, os.path.join(root, 'tests'), layer)
-    env = dict(os.environ, NSC_PLANE_MCAST='1')
-    subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=300)
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\nimport test_gpu_plane as t\n" % (root, os.path.join(root, 'tests'))) + body
+    subprocess.run([sys.executable, '-c', code], check=True, env=dict(os.environ, **env_extra), timeout=600)
+
+
+@pytest.mark.parametrize('precision', [1, 2])
+def test_cta_pair_up_conv(precision):
+    """An even number of work units runs the up-sampling 100 -> 100 conv as CTA pairs (cta_group::2: M = 256 instructions issued by
+    the leader, each CTA stages its own tile and half of every weight unit).  2 frames = one pair; 302 = every pair busy, ragged;
+    1184 frames = several units per CTA so ring slots, accumulator slots and the peer's landed-reports all wrap."""
+    for B in (2, 302, 1184):
+        e = _run(B=B, precision=precision, seed=B, **X_LAYERS[5])
+        assert e < (2e-5 if precision == 1 else 4e-3), (B, e)
+
+
+@pytest.mark.parametrize('pair', ['0', '2'])
+def test_cta_pair_knob(pair):
+    """NSC_PLANE_PAIR=0: the one-CTA kernel on even batches; =2: pairs wherever the shape allows (stride-2 conv, and 20 -> 20 on
+    the tap-shift kernel via NSC_PLANE_NARROW=X).  Results must not depend on the choice."""
+    _child({'NSC_PLANE_PAIR': pair, 'NSC_PLANE_NARROW': 'X'},
+           "for layer in (t.X_LAYERS[4], t.X_LAYERS[5], t.T_LAYERS[3], t.T_LAYERS[5]):\n"
+           "    for prec in (1, 2):\n"
+           "        for B in (2, 302, 1184):\n"
+           "            e = t._run(B=B, precision=prec, seed=B, **layer)\n"
+           "            assert e < (2e-5 if prec == 1 else 4e-3), (layer, prec, B, e)\n")
 
 
 def test_unsupported_shape_fails_loudly():
