@@ -386,6 +386,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t st) {
   NSC_CONV_CASE(15, 1, 1)
   NSC_CONV_CASE(15, 2, 1)
   NSC_CONV_CASE(1, 1, 1)
+  NSC_CONV_CASE(5, 1, 1)    // data gradient of the stride-2 k9 conv as a sub-pixel conv (train.cu)
 #undef NSC_CONV_CASE
   if (CT == 8) return launch_one(conv_tile_generic_kernel<8, 8>, p, threads, smem, st);
   if (CT == 4) return launch_one(conv_tile_generic_kernel<8, 4>, p, threads, smem, st);

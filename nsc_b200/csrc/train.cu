@@ -83,87 +83,133 @@ __global__ void dgrad_strided_kernel(const float* __restrict__ g, const float* _
   }
 }
 
+// The data gradient of the stride-2 k9 conv (padL = 3) as a SUB-PIXEL conv on the forward engine: input position u = 2 v + par takes
+// g[co][v + q] W[par + padL - 2 q][ci][co] for q in [-2, 2], i.e. a stride-1 k5 conv from Cout to 2 Cin channels (c' = 2 ci + par)
+// whose output is pixel-shuffled by 2.  Wt[j][co][2 ci + par] = W[par + padL - 2 (j - 2)][ci][co], zero outside the kernel.
+__global__ void subpixel_dgrad_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int Cin, int Cout, int padL) {
+  const int total = 5 * Cout * 2 * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c2 = i % (2 * Cin), co = (i / (2 * Cin)) % Cout, j = i / (2 * Cin * Cout);
+    const int ci = c2 >> 1, par = c2 & 1;
+    const int t = par + padL - 2 * (j - 2);
+    wt[i] = (t >= 0 && t < K) ? w[((int64_t)t * Cin + ci) * Cout + co] : 0.f;
+  }
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[(t,ci)][co] += sum_{b,p} x[b][ci][p*s + t*d - padL] * g[b][co][p] : a (K*Cin) x Cout x (B*Lout) GEMM whose A operand is
-// gathered on the fly.  CTA tile 64 x 64, 4 x 4 per thread, 32-position chunks staged in shared memory, batch split over
-// gridDim.z, one atomicAdd per output element per CTA.  gridDim.y == 0-th column CTAs also reduce the bias gradient.
+// gathered on the fly.  CTA tile 128 x (16 NT), 8 x NT per thread, 16-position chunks; batch split over gridDim.z, one atomicAdd
+// per output element per CTA (measured: the flush is < 1 % of the kernel).  The reduction runs as a software pipeline: the NEXT
+// chunk's operands are fetched from global memory into registers before the current chunk is multiplied out of shared memory,
+// then stored into the other shared-memory buffer -- one barrier per chunk and the global latency hidden behind the FMAs (the
+// first version staged, synchronised and multiplied in turn and sat at 6 TFLOP/s, bound by exposed load latency).
+// blockIdx.x == 0 CTAs also reduce the bias gradient.
 constexpr int kWgM = 128, kWgR = 16;   // CTA tile: 128 rows (tap, cin) x (16 * NT) output channels, 16 positions per chunk
 
 template <int NT>   // output channels per thread (4 -> 64-wide tile, 2 -> 32-wide tile for the narrow layers)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dw, float* __restrict__ db,
              int64_t B, int Lin, int Lout, int Cin, int Cout, int K, int dil, int stride, int padL, int frames_per_split) {
   constexpr int TN = 16 * NT;
-  __shared__ __align__(16) float xs[kWgR][kWgM + 4];
-  __shared__ __align__(16) float gs[kWgR][TN + 4];
-  __shared__ int row_base[kWgM];    // ci * Lin + t * dil - padL of each tile row (fixed for the whole CTA), or INT_MIN
-  __shared__ int row_shift[kWgM];   // t * dil - padL (for the bounds test)
+  __shared__ __align__(16) float xs[2][kWgR][kWgM + 4];
+  __shared__ __align__(16) float gs[2][kWgR][TN + 4];
   const int M = K * Cin;
   const int m0 = blockIdx.x * kWgM, n0 = blockIdx.y * TN;
   const int64_t b_lo = (int64_t)blockIdx.z * frames_per_split;
   int64_t b_hi = b_lo + frames_per_split;
   if (b_hi > B) b_hi = B;
   const int tid = threadIdx.x, tm = tid >> 4, tn = tid & 15;   // 16 x 16 threads, 8 x NT outputs each
-  for (int mm = tid; mm < kWgM; mm += 256) {
-    const int m = m0 + mm;
+  // staging map, fixed for the whole CTA: this thread fetches position (tid & 15) of rows (tid >> 4) + 16 k of the A tile and of
+  // columns (tid >> 4) + 16 j of the gradient tile; lanes walk positions (contiguous in NCL)
+  const int sr = tid & 15, sm = tid >> 4;
+  int xoff[8], xshift[8];      // ci * Lin + shift, shift = t * dil - padL (INT_MIN / 2: row beyond M)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int m = m0 + sm + 16 * k;
     if (m < M) {
       const int t = m / Cin, ci = m - t * Cin;
-      row_shift[mm] = t * dil - padL;
-      row_base[mm] = ci * Lin;
+      xshift[k] = t * dil - padL;
+      xoff[k] = ci * Lin + xshift[k];
     } else {
-      row_shift[mm] = INT_MIN / 2;
-      row_base[mm] = 0;
+      xshift[k] = INT_MIN / 2;
+      xoff[k] = 0;
     }
   }
-  __syncthreads();
+  const int cpf = (Lout + kWgR - 1) / kWgR;                     // chunks per frame
+  const int64_t n_chunks = (b_hi - b_lo) * cpf;
+  float xr[8], gr[NT];
+  auto fetch = [&](int64_t c) {
+    const int64_t b = b_lo + c / cpf;
+    const int p = (int)(c % cpf) * kWgR + sr;
+    const float* xb = x + b * (int64_t)Cin * Lin;
+    const float* gb = g + b * (int64_t)Cout * Lout;
+    const int ps = p * stride;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int u = ps + xshift[k];
+      xr[k] = (p < Lout && u >= 0 && u < Lin) ? __ldg(xb + xoff[k] + ps) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int n = n0 + sm + 16 * j;
+      gr[j] = (n < Cout && p < Lout) ? __ldg(gb + (int64_t)n * Lout + p) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xs[buf][sr][sm + 16 * k] = xr[k];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) gs[buf][sr][sm + 16 * j] = gr[j];
+  };
   float acc[8][NT];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
   float bacc = 0.f;   // bias partial: thread tid < TN of the blockIdx.x == 0 CTAs owns column n0 + tid
+  const bool do_bias = db != nullptr && blockIdx.x == 0 && tid < TN;
 
-  for (int64_t b = b_lo; b < b_hi; ++b) {
-    const float* xb = x + b * (int64_t)Cin * Lin;
-    const float* gb = g + b * (int64_t)Cout * Lout;
-    for (int p0 = 0; p0 < Lout; p0 += kWgR) {
-      // stage: 16 consecutive positions per row; lanes walk positions (contiguous in NCL)
-      for (int i = tid; i < kWgM * kWgR; i += 256) {
-        const int r = i & (kWgR - 1), mm = i >> 4;
-        const int p = p0 + r;
-        const int u = p * stride + row_shift[mm];
-        xs[r][mm] = (p < Lout && u >= 0 && u < Lin) ? xb[row_base[mm] + u] : 0.f;
-      }
-      for (int i = tid; i < TN * kWgR; i += 256) {
-        const int r = i & (kWgR - 1), nn = i >> 4;
-        const int n = n0 + nn, p = p0 + r;
-        gs[r][nn] = (n < Cout && p < Lout) ? gb[(int64_t)n * Lout + p] : 0.f;
-      }
-      __syncthreads();
+  if (n_chunks > 0) {
+    fetch(0);
+    stash(0);
+  }
+  __syncthreads();
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int buf = (int)(c & 1);
+    if (c + 1 < n_chunks) fetch(c + 1);            // in flight while this chunk is multiplied
 #pragma unroll
-      for (int r = 0; r < kWgR; ++r) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&xs[r][tm * 8]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&xs[r][tm * 8 + 4]);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float c[NT];
-        if (NT == 4) {
-          const float4 cv = *reinterpret_cast<const float4*>(&gs[r][tn * 4]);
-          c[0] = cv.x; c[1] = cv.y; c[NT > 2 ? 2 : 0] = cv.z; c[NT > 3 ? 3 : 0] = cv.w;
-        } else {
-          const float2 cv = *reinterpret_cast<const float2*>(&gs[r][tn * 2]);
-          c[0] = cv.x; c[1] = cv.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+    for (int r = 0; r < kWgR; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&xs[buf][r][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&xs[buf][r][tm * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float cc[NT];
+      if (NT == 4) {
+        const float4 cv = *reinterpret_cast<const float4*>(&gs[buf][r][tn * 4]);
+        cc[0] = cv.x; cc[1] = cv.y; cc[NT > 2 ? 2 : 0] = cv.z; cc[NT > 3 ? 3 : 0] = cv.w;
+      } else {
+        const float2 cv = *reinterpret_cast<const float2*>(&gs[buf][r][tn * 2]);
+        cc[0] = cv.x; cc[1] = cv.y;
       }
-      if (db != nullptr && blockIdx.x == 0 && tid < TN) {
 #pragma unroll
-        for (int r = 0; r < kWgR; ++r) bacc += gs[r][tid];
-      }
-      __syncthreads();
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(a[i], cc[j], acc[i][j]);
     }
+    if (do_bias) {
+#pragma unroll
+      for (int r = 0; r < kWgR; ++r) bacc += gs[buf][r][tid];
+    }
+    if (c + 1 < n_chunks) stash(buf ^ 1);          // the other buffer was last read before the previous barrier
+    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -175,7 +221,7 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __
       if (n < Cout) atomicAdd(dw + (int64_t)m * Cout + n, acc[i][j]);
     }
   }
-  if (db != nullptr && blockIdx.x == 0 && tid < TN && n0 + tid < Cout) atomicAdd(db + n0 + tid, bacc);
+  if (do_bias && n0 + tid < Cout) atomicAdd(db + n0 + tid, bacc);
 }
 
 // ------------------------------------------------------------------------------------------------ quantiser backward
@@ -512,7 +558,7 @@ int walk_codec(const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* pa
 
 // backward through one conv record.  G(ptr) maps an activation pointer to its gradient twin.
 int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params, float* grads, char* act_base, char* grad_base,
-                  int64_t B, float* gpre, float* wflip, bool need_dx, cudaStream_t st) {
+                  int64_t B, float* gpre, float* wflip, float* gtmp, bool need_dx, cudaStream_t st) {
   auto G = [&](const float* p) { return reinterpret_cast<float*>(grad_base + (reinterpret_cast<const char*>(p) - act_base)); };
   int Lout, padL;
   same_padding(r.Lin, r.K, r.dil, r.stride, &Lout, &padL);
@@ -530,7 +576,8 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     const int M = r.K * r.Cin;
     const int nt = r.Cout <= 32 ? 2 : 4;
     const int gx = ceil_div(M, kWgM), gy = ceil_div(r.Cout, 16 * nt);
-    int splits = ceil_div(2 * sm_count(), gx * gy);
+    static const int split_mul = getenv("NSC_WGRAD_SPLITMUL") ? atoi(getenv("NSC_WGRAD_SPLITMUL")) : 4;   // CTAs per SM aimed at
+    int splits = ceil_div(split_mul * sm_count(), gx * gy);
     if (splits > B) splits = (int)B;
     if (splits < 1) splits = 1;
     const int fps = (int)ceil_div64(B, splits);
@@ -549,6 +596,17 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     a.x = gpre; a.w = wflip; a.bias = nullptr; a.y = G(r.x); a.res = G(r.x); a.res_mode = RES_ADD;
     a.B = B; a.Lin = Lout; a.Cin = r.Cout; a.Cout = r.Cin; a.K = r.K; a.dil = r.dil; a.stride = 1;
     NSC_TRY(launch_conv(a, st));
+  } else if (r.stride == 2 && r.dil == 1 && r.K == 9 && padL == 3 && r.Lin == 2 * Lout && (r.Lin & 3) == 0 &&
+             (int64_t)5 * r.Cout * 2 * r.Cin <= kWflipFloats) {
+    subpixel_dgrad_weights_kernel<<<ew_grid((int64_t)5 * r.Cout * 2 * r.Cin), 256, 0, st>>>(w, wflip, r.K, r.Cin, r.Cout, padL);
+    NSC_LAUNCH_OK();
+    ConvArgs a;   // gtmp = shuffle2(conv_k5(gpre, Wt)), then gx += gtmp (the residual operand of a shuffled conv has the pre-shuffle shape)
+    a.x = gpre; a.w = wflip; a.bias = nullptr; a.y = gtmp; a.res_mode = RES_NONE; a.shuffle = 2;
+    a.B = B; a.Lin = Lout; a.Cin = r.Cout; a.Cout = 2 * r.Cin; a.K = 5; a.dil = 1; a.stride = 1;
+    NSC_TRY(launch_conv(a, st));
+    const int64_t n4 = B * (int64_t)r.Cin * r.Lin / 4;
+    add_inplace_kernel<<<ew_grid(n4), 256, 0, st>>>(G(r.x), gtmp, n4);
+    NSC_LAUNCH_OK();
   } else {
     ProfScope prof(st, "dgrad_strided", 2.0 * B * Lout * (double)r.K * r.Cin * r.Cout, 4.0 * B * ((double)r.Lin * r.Cin + (double)Lout * r.Cout));
     dgrad_strided_kernel<<<ew_grid(B * (int64_t)r.Cin * r.Lin), 256, 0, st>>>(gpre, w, G(r.x), B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil,
@@ -561,7 +619,7 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
 struct TrainLayout {
   std::vector<int64_t> arena;   // activation arena bytes per codec
   int64_t act_off[NSC_MAX_CODECS], grad_off[NSC_MAX_CODECS];
-  int64_t gpre_off, wflip_off, gdec_off, acc_off, ge_off, wpack_off, total;
+  int64_t gpre_off, gtmp_off, wflip_off, gdec_off, acc_off, ge_off, wpack_off, total;
 };
 
 TrainLayout train_layout(const nsc_codec_cfg* cfgs, int n, int64_t B) {
@@ -575,6 +633,7 @@ TrainLayout train_layout(const nsc_codec_cfg* cfgs, int n, int64_t B) {
     if (cfgs[i].wide > max_wide) max_wide = cfgs[i].wide;
   }
   t.gpre_off = off; off += align_up(B * (int64_t)max_wide * kFrameLen * 4, 256);
+  t.gtmp_off = off; off += align_up(B * (int64_t)max_wide * kFrameLen * 4, 256);   // data gradient of the strided conv before it is added
   t.wflip_off = off; off += kWflipFloats * 4;
   t.gdec_off = off; off += align_up(B * (int64_t)kFrameLen * 4, 256);
   t.acc_off = off; off += align_up(B * (int64_t)kFrameLen * 4, 256);
@@ -656,6 +715,7 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
   const float c0 = loss_coeff_host[0], c1 = loss_coeff_host[1], c2 = loss_coeff_host[2], tau = loss_coeff_host[3];
   const int64_t nfl = B * nsc::kFrameLen;
   float* gpre = reinterpret_cast<float*>(ws + tl.gpre_off);
+  float* gtmp = reinterpret_cast<float*>(ws + tl.gtmp_off);
   float* wflip = reinterpret_cast<float*>(ws + tl.wflip_off);
   float* gdec = reinterpret_cast<float*>(ws + tl.gdec_off);
   float* acc = reinterpret_cast<float*>(ws + tl.acc_off);     // sum over later codecs of -rs * d/d(codec input)
@@ -697,7 +757,7 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
     // seed: d/d(raw decoder output) = (gdec + acc) / rs
     NSC_TRY(nsc::launch_axpby(G(tb.out), gdec, 1.0f / res_scalar, acc, 1.0f, nfl, st));   // (gdec - acc) / rs, acc = sum_{m>i} rs * d/d in_m
     for (int k = (int)tb.dec_tape.size() - 1; k >= 0; --k)
-      NSC_TRY(nsc::conv_backward(tb.dec_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, true, st));
+      NSC_TRY(nsc::conv_backward(tb.dec_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, true, st));
     // quantiser (soft path)
     const float* alpha = params_ptrs_host[i] + lay.conv_floats;
     nsc::entropy_grad_kernel<<<1, 32, 0, st>>>(hist_global_ptrs_host[i + 1], cfgs[i].num_bins, tau * ent_w_host[i + 1] * (float)global_B, ge);
@@ -708,7 +768,7 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
     bool earlier = false;
     for (int j = 0; j < i; ++j) earlier = earlier || trainable_host[j + 1];
     for (int k = (int)tb.enc_tape.size() - 1; k >= 0; --k)
-      NSC_TRY(nsc::conv_backward(tb.enc_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, k > 0 || earlier, st));
+      NSC_TRY(nsc::conv_backward(tb.enc_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, k > 0 || earlier, st));
     if (earlier) {
       // acc += rs * d/d in_i   (applied with a minus sign in the seed of every earlier codec)
       NSC_TRY(nsc::launch_axpby(acc, G(tb.cin), res_scalar, acc, -1.0f / res_scalar, nfl, st));
