@@ -558,7 +558,7 @@ int walk_codec(const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* pa
 
 // backward through one conv record.  G(ptr) maps an activation pointer to its gradient twin.
 int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params, float* grads, char* act_base, char* grad_base,
-                  int64_t B, float* gpre, float* wflip, float* gtmp, bool need_dx, cudaStream_t st) {
+                  int64_t B, float* gpre, float* wflip, float* gtmp, int precision, void* wpack, bool need_dx, cudaStream_t st) {
   auto G = [&](const float* p) { return reinterpret_cast<float*>(grad_base + (reinterpret_cast<const char*>(p) - act_base)); };
   int Lout, padL;
   same_padding(r.Lin, r.K, r.dil, r.stride, &Lout, &padL);
@@ -595,7 +595,9 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     ConvArgs a;   // gx += conv(gpre, Wflip): forward engine, Cout -> Cin channels, accumulate through the residual input
     a.x = gpre; a.w = wflip; a.bias = nullptr; a.y = G(r.x); a.res = G(r.x); a.res_mode = RES_ADD;
     a.B = B; a.Lin = Lout; a.Cin = r.Cout; a.Cout = r.Cin; a.K = r.K; a.dil = r.dil; a.stride = 1;
-    NSC_TRY(launch_conv(a, st));
+    // same engine choice as the forward walk (walker.cuh): tensor cores (fp16 hi/lo split) when the codec asks for them
+    if (precision > 0 && wpack != nullptr && tc_conv_supported(a)) NSC_TRY(launch_conv_tc(a, precision, wpack, st));
+    else NSC_TRY(launch_conv(a, st));
   } else if (r.stride == 2 && r.dil == 1 && r.K == 9 && padL == 3 && r.Lin == 2 * Lout && (r.Lin & 3) == 0 &&
              (int64_t)5 * r.Cout * 2 * r.Cin <= kWflipFloats) {
     subpixel_dgrad_weights_kernel<<<ew_grid((int64_t)5 * r.Cout * 2 * r.Cin), 256, 0, st>>>(w, wflip, r.K, r.Cin, r.Cout, padL);
@@ -757,7 +759,7 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
     // seed: d/d(raw decoder output) = (gdec + acc) / rs
     NSC_TRY(nsc::launch_axpby(G(tb.out), gdec, 1.0f / res_scalar, acc, 1.0f, nfl, st));   // (gdec - acc) / rs, acc = sum_{m>i} rs * d/d in_m
     for (int k = (int)tb.dec_tape.size() - 1; k >= 0; --k)
-      NSC_TRY(nsc::conv_backward(tb.dec_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, true, st));
+      NSC_TRY(nsc::conv_backward(tb.dec_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, cfgs[i].precision, ws + tl.wpack_off, true, st));
     // quantiser (soft path)
     const float* alpha = params_ptrs_host[i] + lay.conv_floats;
     nsc::entropy_grad_kernel<<<1, 32, 0, st>>>(hist_global_ptrs_host[i + 1], cfgs[i].num_bins, tau * ent_w_host[i + 1] * (float)global_B, ge);
@@ -768,7 +770,7 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
     bool earlier = false;
     for (int j = 0; j < i; ++j) earlier = earlier || trainable_host[j + 1];
     for (int k = (int)tb.enc_tape.size() - 1; k >= 0; --k)
-      NSC_TRY(nsc::conv_backward(tb.enc_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, k > 0 || earlier, st));
+      NSC_TRY(nsc::conv_backward(tb.enc_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, cfgs[i].precision, ws + tl.wpack_off, k > 0 || earlier, st));
     if (earlier) {
       // acc += rs * d/d in_i   (applied with a minus sign in the seed of every earlier codec)
       NSC_TRY(nsc::launch_axpby(acc, G(tb.cin), res_scalar, acc, -1.0f / res_scalar, nfl, st));

@@ -96,10 +96,13 @@ def inputs(B, seed=91):
     return res_x, lsf
 
 
-@pytest.mark.parametrize('alpha,is_quan_on', [(-20.0, 1.0), (-300.0, 1.0), (-20.0, 0.0)])
-def test_backward_matches_autograd_two_codecs(alpha, is_quan_on):
+@pytest.mark.parametrize('alpha,is_quan_on,precision', [(-20.0, 1.0, 'fp32'), (-300.0, 1.0, 'fp32'), (-20.0, 0.0, 'fp32'),
+                                                        (-20.0, 1.0, 'tc_f16x3')])
+def test_backward_matches_autograd_two_codecs(alpha, is_quan_on, precision):
+    """fp32: every conv (forward, data gradient) on the FFMA engine; tc_f16x3: forward and data-gradient convs on the tensor
+    cores with the fp16 hi/lo split -- both must meet the same gradient bound against float64 autograd."""
     from nsc_b200.training import CQTrainer
-    ocs, cm, cfg = make_models(2, alpha)
+    ocs, cm, cfg = make_models(2, alpha, precision=precision)
     res_x, lsf = inputs(5)
     coeff, quan_w, ent_w, tau = (60.0, 10.0, 10.0), [0.06, 0.5, 0.44], [0.06, 0.5, 0.44], 0.7
     tr = CQTrainer(cm, coeff + (tau,), quan_w=quan_w, ent_w=ent_w)
