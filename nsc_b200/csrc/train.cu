@@ -224,6 +224,51 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __
   if (do_bias && n0 + tid < Cout) atomicAdd(db + n0 + tid, bacc);
 }
 
+// Weight gradient of the 1-channel heads (k55, Cout = 1): dW[t][ci] = sum_{b,p} x[b][ci][p + t - padL] g[b][p] is a correlation,
+// not a GEMM -- on the tiled kernel its single output column pads to 32 and the two heads cost a quarter of all weight-gradient
+// time.  One CTA per (input channel, batch split): the channel's row (with its zero halo) and the gradient row sit in shared
+// memory, thread t owns tap t.
+constexpr int kWhThreads = 64, kWhMaxL = 1024;
+
+__global__ void __launch_bounds__(kWhThreads)
+wgrad_head_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dw, float* __restrict__ db,
+                  int64_t B, int L, int Cin, int K, int padL, int frames_per_split) {
+  __shared__ float xs[kWhMaxL + kWhThreads];
+  __shared__ float gs[kWhMaxL];
+  const int ci = blockIdx.x, t = threadIdx.x;
+  const int64_t b_lo = (int64_t)blockIdx.y * frames_per_split;
+  int64_t b_hi = b_lo + frames_per_split;
+  if (b_hi > B) b_hi = B;
+  float acc = 0.f, bacc = 0.f;
+  for (int64_t b = b_lo; b < b_hi; ++b) {
+    const float* xr = x + (b * Cin + ci) * (int64_t)L;
+    const float* gr = g + b * (int64_t)L;
+    for (int i = t; i < L + K - 1; i += kWhThreads) {
+      const int u = i - padL;
+      xs[i] = (u >= 0 && u < L) ? __ldg(xr + u) : 0.f;
+    }
+    for (int i = t; i < L; i += kWhThreads) {
+      const float v = __ldg(gr + i);
+      gs[i] = v;
+      bacc += v;
+    }
+    __syncthreads();
+    if (t < K) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;     // four chains: the loop is latency-, not throughput-bound per thread
+      for (int p = 0; p < L; p += 4) {
+        a0 = fmaf(xs[p + t], gs[p], a0);
+        a1 = fmaf(xs[p + 1 + t], gs[p + 1], a1);
+        a2 = fmaf(xs[p + 2 + t], gs[p + 2], a2);
+        a3 = fmaf(xs[p + 3 + t], gs[p + 3], a3);
+      }
+      acc += (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+  }
+  if (t < K) atomicAdd(dw + (int64_t)t * Cin + ci, acc);
+  if (db != nullptr && ci == 0) atomicAdd(db, bacc);
+}
+
 // ------------------------------------------------------------------------------------------------ quantiser backward
 // dH/dh_k of entropy_coding_loss (loss_terms_and_measures.py:262-267), times coef (= tau * w_e * global batch)
 __global__ void entropy_grad_kernel(const float* __restrict__ hist, int n, float coef, float* __restrict__ ge) {
@@ -572,7 +617,16 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
                                                                       r.act, r.res_mode, r.post_act, r.shuffle);
     NSC_LAUNCH_OK();
   }
-  {
+  if (r.Cout == 1 && r.stride == 1 && r.dil == 1 && r.K <= kWhThreads && r.Lin == Lout && Lout <= kWhMaxL && (Lout & 3) == 0) {
+    int splits = ceil_div(16 * sm_count(), r.Cin);      // small CTAs (64 threads, 5 KB): many per SM
+    if (splits > B) splits = (int)B;
+    if (splits < 1) splits = 1;
+    const int fps = (int)ceil_div64(B, splits);
+    splits = (int)ceil_div64(B, fps);
+    ProfScope prof(st, "wgrad_head", 2.0 * B * Lout * (double)r.K * r.Cin, 4.0 * B * ((double)r.Lin * r.Cin + (double)Lout));
+    wgrad_head_kernel<<<dim3(r.Cin, splits), kWhThreads, 0, st>>>(r.x, gpre, dw, db, B, Lout, r.Cin, r.K, padL, fps);
+    NSC_LAUNCH_OK();
+  } else {
     const int M = r.K * r.Cin;
     const int nt = r.Cout <= 32 ? 2 : 4;
     const int gx = ceil_div(M, kWgM), gy = ceil_div(r.Cout, 16 * nt);

@@ -5,7 +5,7 @@ L=gpurun_out/wgrad_try.log
 : > $L
 timeout 900 python -m pytest tests/test_gpu_training.py -x -q >> $L 2>&1
 echo "pytest rc=$?" >> $L
-for cfg in "X=1" "NSC_WGRAD_SPLITMUL=2" "NSC_WGRAD_SPLITMUL=8"; do
+for cfg in "X=1"; do
   echo "== $cfg" >> $L
   env $cfg timeout 300 python bench.py --workload train --steps 5 --warmup 3 >> $L 2>&1
 done
