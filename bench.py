@@ -276,15 +276,15 @@ def run_ours(args):
         conv_ms = sum(v[0] for _, v in conv)
         conv_fl = sum(v[1] for _, v in conv)
         conv_by = sum(v[2] for _, v in conv)
-        traffic = None
+        traffic = traffic_detail = None
         tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
         if os.path.exists(tpath):
             t = json.load(open(tpath)).get(top_name)
             if t:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
-                traffic = {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "frames_per_launch": t["frames_per_launch"],
-                           "algorithmic_bytes_of_that_launch": 589824 * t["frames_per_launch"],
-                           "source": t["source"]}
-        common = {"kernel": top_name, "launch_ms": top[0] / top[3], "share_of_step": top[0] / tot, "traffic": traffic,
+                traffic = t["dram_bytes_per_launch"]
+                traffic_detail = {"frames_of_that_launch": t["frames_per_launch"],
+                                  "algorithmic_bytes_of_that_launch": 589824 * t["frames_per_launch"], "source": t["source"]}
+        common = {"kernel": top_name, "launch_ms": top[0] / top[3], "share_of_step": top[0] / tot, "traffic": traffic, "traffic_detail": traffic_detail,
                   "pipe": ("fp32 FFMA (CUDA cores)" if not tensor_path else
                            "tcgen05 kind::f16, fp32 accumulate in TMEM" + (" -- 3 MMAs per product (fp16 hi/lo split): "
                            "issued tensor flops are 3x the algorithmic flops" if mma_per_product == 3 else "")),

@@ -227,7 +227,10 @@ struct TParams {
   int64_t B;
 };
 
-constexpr int kTSlots = 12;         // spill slots: three tiles' worth of quarters
+// spill slots: the quarters of the current and the previous tile; the k55 head has no per-tile barrier after its reads (no staged
+// output), so it keeps a third tile's worth.  (Eight slots instead of twelve give the 100 -> 20 layer a fifth input stage: the
+// layer is bound by bytes in flight -- 4 x 16 KB per SM against ~2 us of loaded HBM latency is 32 GB/s per SM, 73 % of peak.)
+constexpr int t_slots(int C) { return C == 1 ? 12 : 8; }
 constexpr int kAStage = 128 * 128;  // one input slab of one tile
 constexpr int kORing = 256;         // rows of the output staging ring (two tiles)
 
@@ -240,6 +243,7 @@ struct TShape {
   static constexpr int kThreads = (kEpiWarps + 2) * 32;   // + MMA issuer, loader
   static constexpr int kMaxM = (C == 1) ? 32 : 8;         // largest row shift handled (lanes that can wrap)
   static constexpr int kRowFloats = (C == 1) ? 1 : 24;    // floats per spilled row
+  static constexpr int kSlots = t_slots(C);
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
   const uint32_t wslab_bytes = (uint32_t)p.N * 128u;
   uint8_t* sW = smem;
   uint8_t* sA = sW + (uint32_t)p.n_wslab * wslab_bytes;
+  constexpr int kTSlots = S::kSlots;
   float* sU = reinterpret_cast<float*>(sA + (uint32_t)p.na * kAStage);     // [kTSlots][kMaxM][kRF]
   float* sP = sU + kTSlots * kMaxM * kRF;                                   // [kTSlots][kMaxM][kRF]
   // output staging ring (C = 20): kORing image rows of 128 B, same swizzle as the global image, bulk-stored one window per tile
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
     float* const sU_l = sU + lane * kRF + coff;
     float* const sP_l = sP + (lane - (32 - m)) * kRF + coff;
     const int out_planes = p.out.planes;
-    uint32_t it = 0, tb = 0, tbp = 8;                 // tb: first spill slot of this tile's quarters (0, 4, 8 in turn)
+    uint32_t it = 0, tb = 0, tbp = kTSlots - 4;       // tb: first spill slot of this tile's quarters (0, 4[, 8] in turn)
     for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
       uint8_t* const orow = (C == 1) ? nullptr : p.out.base + f * p.out.frame_bytes + 8 * 128;   // position 0 of the packed image
       const int ring0 = (int)((it * 128u) & (kORing - 1));      // ring row of this frame's position 0 (frames are whole tiles)
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
           done_rows = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
         }
         tbp = tb;
-        tb = tb == 8u ? 0u : tb + 4u;
+        tb = tb == (uint32_t)(kTSlots - 4) ? 0u : tb + 4u;
       }
     }
     if constexpr (C != 1) {
@@ -1350,7 +1355,7 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   pl->ksteps = (c.Cin + 15) / 16;
   pl->n_wslab = c.in.packed ? 1 : c.in.planes * c.in.spp;
   const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
-  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * kTSlots * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
+  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * t_slots(k9 ? 20 : 1) * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
   if (fixed + 2ull * kAStage > kSmemBudget) return false;
   // Optional: two CTAs per SM for the narrow-input layers (half the shared memory, ONE accumulator slot each, <= 72 registers).
   // Measured neutral (4.8 vs 4.8 ms per step on 20 -> 20) once the output rows are staged, so it is off unless asked for.
