@@ -223,7 +223,6 @@ struct TParams {
   float* yvec;
   int N, n_wslab, ksteps;
   int L, dil, act, na;
-  int nacc;                  // TMEM accumulator slots (2, or 1 when two CTAs share an SM)
   int64_t B;
 };
 
@@ -300,42 +299,6 @@ __device__ __forceinline__ void t_phase1_k9(uint32_t tcol, const int (&srcl)[9],
   }
 }
 
-// Low-register variant (two CTAs per SM): taps are fetched one ahead instead of all at once.
-template <int NCH>
-__device__ __forceinline__ void t_phase1_k9_roll(uint32_t tcol, const int (&srcl)[9], uint32_t inrm, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) { acc[c] = 0.f; up[c] = 0.f; down[c] = 0.f; }
-  uint32_t r[2][8];
-  auto load_tap = [&](int t, uint32_t (&dst)[8]) {
-    if constexpr (NCH == 8) tmem_ld8(tcol + (uint32_t)(t * 20), dst);
-    else {
-      uint32_t b[4];
-      tmem_ld4(tcol + (uint32_t)(t * 20), b);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = b[i];
-    }
-  };
-  load_tap(0, r[0]);
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    tmem_ld_wait();
-    if (t + 1 < 9) load_tap(t + 1, r[(t + 1) & 1]);
-    const int src = srcl[t];
-    const bool inr = (inrm >> t) & 1u;
-#pragma unroll
-    for (int c = 0; c < NCH; c += 2) {
-      float2 x = make_float2(__uint_as_float(r[t & 1][c]), __uint_as_float(r[t & 1][c + 1]));
-      if (t != 4) {
-        x.x = __shfl_sync(0xffffffffu, x.x, src);
-        x.y = __shfl_sync(0xffffffffu, x.y, src);
-      }
-      if (t == 4 || inr) { const float2 y = __fadd2_rn(make_float2(acc[c], acc[c + 1]), x); acc[c] = y.x; acc[c + 1] = y.y; }
-      else if (t > 4) { const float2 y = __fadd2_rn(make_float2(down[c], down[c + 1]), x); down[c] = y.x; down[c + 1] = y.y; }
-      else { const float2 y = __fadd2_rn(make_float2(up[c], up[c + 1]), x); up[c] = y.x; up[c + 1] = y.y; }
-    }
-  }
-}
-
 __device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc, float& up, float& down) {
   uint32_t r0[32], r1[32];
   tmem_ld32(tcol, r0);
@@ -356,8 +319,8 @@ __device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc
   acc = a; up = u; down = d;
 }
 
-template <int C, int TAPS, int OCC>
-__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel(const __grid_constant__ TParams p) {
+template <int C, int TAPS>
+__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
   using S = TShape<C, TAPS>;
   constexpr int kMaxM = S::kMaxM, kRF = S::kRowFloats, kEpi = S::kEpiWarps;
   constexpr int NCHMAX = (C == 1) ? 1 : 8;
@@ -378,8 +341,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
   const int T = p.L / 128;
   const int nst = pt_n_slabs(p.in);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.nacc * (uint32_t)p.N) tmem_cols *= 2;
-  const bool two_acc = p.nacc == 2;
+  while (tmem_cols < 2u * (uint32_t)p.N) tmem_cols *= 2;      // two accumulator slots: the next tile's MMAs run under this tile's epilogue
 
   if (tid == 0) {
     mbar_init(&w_full, 1);
@@ -448,8 +410,8 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
         }
       };
       for (int j = 0; j < T; ++j, ++it) {
-        const uint32_t acc_i = two_acc ? (it & 1u) : 0u;
-        mbar_wait_relaxed(&acc_full[acc_i], two_acc ? (it >> 1) & 1u : it & 1u);
+        const uint32_t acc_i = it & 1u;
+        mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
         tc_fence_after();
         float acc[NCHMAX], up[NCHMAX], down[NCHMAX];
         const uint32_t tcol = tmem + ((uint32_t)(q * 32) << 16) + acc_i * (uint32_t)p.N + (uint32_t)(grp * 8);
@@ -458,13 +420,11 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
         } else {
           if (grp == 2) {
             float a4[4], u4[4], d4[4];
-            if constexpr (OCC == 2) t_phase1_k9_roll<4>(tcol, srcl, inrm, a4, u4, d4);
-            else t_phase1_k9<4>(tcol, srcl, inrm, a4, u4, d4);
+            t_phase1_k9<4>(tcol, srcl, inrm, a4, u4, d4);
 #pragma unroll
             for (int c = 0; c < 8; ++c) { acc[c] = c < 4 ? a4[c & 3] : 0.f; up[c] = c < 4 ? u4[c & 3] : 0.f; down[c] = c < 4 ? d4[c & 3] : 0.f; }
           } else {
-            if constexpr (OCC == 2) t_phase1_k9_roll<8>(tcol, srcl, inrm, acc, up, down);
-            else t_phase1_k9<8>(tcol, srcl, inrm, acc, up, down);
+            t_phase1_k9<8>(tcol, srcl, inrm, acc, up, down);
           }
         }
         tc_fence_before();
@@ -549,8 +509,8 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, OCC) plane_t_kernel
       uint32_t it = 0, slot = 0, sph = 0;
       for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
         for (int j = 0; j < T; ++j, ++it) {
-          const uint32_t acc_i = two_acc ? (it & 1u) : 0u;
-          mbar_wait(&acc_empty[acc_i], (two_acc ? (it >> 1) & 1u : it & 1u) ^ 1u);
+          const uint32_t acc_i = it & 1u;
+          mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d = tmem + acc_i * (uint32_t)p.N;
           uint32_t accum = 0;
@@ -1340,7 +1300,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ourselves (alignment slack + static barriers)
 
 struct TPlan {
-  int N, n_wslab, ksteps, na, occ;
+  int N, n_wslab, ksteps, na;
   size_t smem;
 };
 
@@ -1357,12 +1317,8 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
   const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * t_slots(k9 ? 20 : 1) * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
   if (fixed + 2ull * kAStage > kSmemBudget) return false;
-  // Optional: two CTAs per SM for the narrow-input layers (half the shared memory, ONE accumulator slot each, <= 72 registers).
-  // Measured neutral (4.8 vs 4.8 ms per step on 20 -> 20) once the output rows are staged, so it is off unless asked for.
-  static const bool occ2_on = getenv("NSC_PLANE_T_OCC2") != nullptr;
-  const size_t half = (227 * 1024) / 2 - 2048;
-  pl->occ = (k9 && c.in.packed && occ2_on && fixed + 2ull * kAStage + 1024 <= half) ? 2 : 1;
-  const size_t budget = pl->occ == 2 ? half - 1024 : kSmemBudget;
+  // (Two CTAs per SM for the narrow-input layers measured neutral -- 4.8 vs 4.8 ms per step on 20 -> 20 -- and were removed.)
+  const size_t budget = kSmemBudget;
   size_t na = (budget - fixed) / kAStage;
   if (na > 8) na = 8;
   pl->na = (int)na;
@@ -1551,18 +1507,13 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     // algorithmic bytes: every input and output plane image moved exactly once (zero rows excluded)
     const double bytes = (double)c.B * (pt_payload_bytes(c.in) + (c.Cout > 1 ? pt_payload_bytes(c.out) : 4.0 * c.Lin));
     ProfScope prof(st, name, 2.0 * macs, bytes);
-    const int64_t slots = (int64_t)sm_count() * pl.occ;
-    const int64_t grid = c.B < slots ? c.B : slots;
-    p.nacc = pl.occ == 2 ? 1 : 2;
-    if (c.Cout == 20 && pl.occ == 2) {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 9, 2><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
-    } else if (c.Cout == 20) {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 9, 1><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
+    const int64_t grid = c.B < sm_count() ? c.B : sm_count();
+    if (c.Cout == 20) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 9><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
     } else {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<1, 55, 1><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<1, 55><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
     }
     NSC_LAUNCH_OK();
     return NSC_OK;

@@ -630,8 +630,7 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     const int M = r.K * r.Cin;
     const int nt = r.Cout <= 32 ? 2 : 4;
     const int gx = ceil_div(M, kWgM), gy = ceil_div(r.Cout, 16 * nt);
-    static const int split_mul = getenv("NSC_WGRAD_SPLITMUL") ? atoi(getenv("NSC_WGRAD_SPLITMUL")) : 4;   // CTAs per SM aimed at
-    int splits = ceil_div(split_mul * sm_count(), gx * gy);
+    int splits = ceil_div(4 * sm_count(), gx * gy);   // two resident CTAs per SM, two waves (measured: 2 -> 4 CTAs per SM of grid 7.6 -> 7.4 ms)
     if (splits > B) splits = (int)B;
     if (splits < 1) splits = 1;
     const int fps = (int)ceil_div64(B, splits);
