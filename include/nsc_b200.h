@@ -68,6 +68,12 @@ int nsc_conv1d(const float* x, const float* w, const float* b, float* y, int64_t
  *   1-channel stems / 1-channel heads); anything else returns NSC_E_INVALID -- there is no fallback. */
 int64_t nsc_conv1d_tc_workspace_bytes(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation,
                                       int32_t stride, int32_t res_mode, int32_t shuffle, int32_t precision);
+/* How nsc_conv1d_tc would launch this layer (host logic only, no device work) -- for tests and tuning.  out[0..11] =
+ *   kernel family (0 taps-in-N, 1 tap-shift, 2 Toeplitz), staged epilogue, CTA pair (cta_group::2), M tiles per work unit,
+ *   MMA-issuing threads, weights resident, weight-ring slots, input stages in flight, dynamic shared memory bytes,
+ *   TMEM columns, grid size, work units (tiles, or frames for taps-in-N).  Returns NSC_OK or NSC_E_INVALID. */
+int nsc_conv1d_tc_plan_info(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride,
+                            int32_t res_mode, int32_t shuffle, int32_t precision, int64_t* out12);
 int nsc_conv1d_tc(const float* x, const float* w, const float* b, const float* res, float* y, int64_t B, int32_t Lin,
                   int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation,
                   int32_t res_mode, int32_t post_activation, int32_t shuffle, int32_t precision, void* workspace,

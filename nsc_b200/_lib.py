@@ -45,6 +45,7 @@ SIGNATURES = {
     "nsc_profile_end": (_i32, [C.POINTER(_i32), C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "nsc_conv1d": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nsc_conv1d_tc_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "nsc_conv1d_tc_plan_info": (_i32, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_int64)]),
     "nsc_conv1d_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "nsc_conv1d_depth": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nsc_block_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),

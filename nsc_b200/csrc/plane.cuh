@@ -85,6 +85,8 @@ bool plane_conv_supported(const PlaneConv& c);
 int64_t plane_wpack_bytes(const PlaneConv& c);
 int plane_pack_weights(const PlaneConv& c, cudaStream_t st);
 int plane_launch(const PlaneConv& c, cudaStream_t st);
+// launch plan of a layer (what plane_launch would do), see nsc_conv1d_tc_plan_info
+bool plane_plan_info(const PlaneConv& c, int64_t* out12);
 
 // fp32 <-> plane images (API edges and tests)
 int plane_from_f32(const float* x, int x_cl, int64_t B, int L, int C, const PlaneTensor& t, cudaStream_t st);

@@ -1461,6 +1461,29 @@ int64_t plane_wpack_bytes(const PlaneConv& c) {
   return (int64_t)p.n_units * p.unit_bytes;
 }
 
+bool plane_plan_info(const PlaneConv& c, int64_t* o) {
+  for (int i = 0; i < 12; ++i) o[i] = 0;
+  o[0] = c.kind;
+  if (c.kind == PK_T) {
+    TPlan pl;
+    if (!plan_t(c, &pl)) return false;
+    o[3] = 1; o[4] = 1; o[5] = 1; o[6] = pl.n_wslab; o[7] = pl.na; o[8] = (int64_t)pl.smem;
+    int cols = 32;
+    while (cols < 2 * pl.N) cols *= 2;
+    o[9] = cols;
+    o[10] = c.B < sm_count() ? c.B : sm_count();
+    o[11] = c.B;
+    return true;
+  }
+  XParams p;
+  if (!plan_x(c, &p)) return false;
+  int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  if (p.pair) grid &= ~(int64_t)1;
+  o[1] = p.staged; o[2] = p.pair; o[3] = p.mt; o[4] = p.n_iss; o[5] = p.resident; o[6] = p.wslots; o[7] = (int64_t)p.n_stage * p.kbuf;
+  o[8] = (int64_t)x_smem_bytes(p); o[9] = p.tmem_cols; o[10] = grid; o[11] = p.n_tiles;
+  return true;
+}
+
 int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
   NSC_CHECK_ARG(c.w != nullptr && c.wpack != nullptr, "plane engine: null weights");
   PackArgs a;
@@ -1626,6 +1649,15 @@ int64_t nsc_conv1d_tc_workspace_bytes(int64_t B, int32_t Lin, int32_t Cin, int32
   TcConvPlan pl;
   if (make_tc_conv_plan(B < 1 ? 1 : B, Lin, Cin, Cout, k, dilation, stride, 0, res_mode, 0, shuffle, precision, &pl) != NSC_OK) return -1;
   return 1024 + pl.in_bytes + pl.out_bytes + pl.res_bytes + pl.w_bytes;
+}
+
+int nsc_conv1d_tc_plan_info(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride,
+                            int32_t res_mode, int32_t shuffle, int32_t precision, int64_t* out12) {
+  NSC_CHECK_ARG(out12 != nullptr, "nsc_conv1d_tc_plan_info: null output");
+  TcConvPlan pl;
+  NSC_TRY(make_tc_conv_plan(B < 1 ? 1 : B, Lin, Cin, Cout, k, dilation, stride, 0, res_mode, 0, shuffle, precision, &pl));
+  NSC_CHECK_ARG(nsc::plane_plan_info(pl.c, out12), "nsc_conv1d_tc_plan_info: layer not planned");
+  return NSC_OK;
 }
 
 int nsc_conv1d_tc(const float* x, const float* w, const float* b, const float* res, float* y, int64_t B, int32_t Lin,

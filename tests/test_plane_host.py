@@ -37,6 +37,53 @@ def test_unsupported_shapes_are_refused(bad):
     assert _lib.last_error() != ''
 
 
+PLAN_KEYS = ('kind', 'staged', 'pair', 'mt', 'n_iss', 'resident', 'wslots', 'stages', 'smem', 'tmem_cols', 'grid', 'units')
+
+
+def _plan(B, Lin, Cin, Cout, k, dil=1, stride=1, res_mode=0, shuffle=1, precision=1):
+    import ctypes as C
+    out = (C.c_int64 * 12)()
+    rc = _lib.load().nsc_conv1d_tc_plan_info(B, Lin, Cin, Cout, k, dil, stride, res_mode, shuffle, precision, out)
+    assert rc == 0, _lib.last_error()
+    return dict(zip(PLAN_KEYS, list(out)))
+
+
+def test_launch_plans_of_the_codec_layers():
+    """What the plane engine would launch for every layer shape of the codec (148 SMs assumed without a device): kernel family,
+    shared memory within one SM, TMEM within 512 columns, the rings the DESIGN.md kernel table describes."""
+    smem_max = 227 * 1024
+    t1 = _plan(2072, 512, 100, 20, 9)
+    assert t1['kind'] == 0 and t1['stages'] == 5 and t1['wslots'] == 4 and t1['tmem_cols'] == 512      # 4 weight slabs resident, 5 input stages
+    t2 = _plan(2072, 512, 20, 20, 9, dil=2)
+    assert t2['kind'] == 0 and t2['stages'] == 8 and t2['wslots'] == 1
+    head = _plan(2072, 256, 100, 1, 55)
+    assert head['kind'] == 0 and head['tmem_cols'] == 128
+    x3 = _plan(2072, 512, 20, 100, 9, res_mode=1)
+    assert x3['kind'] == 1 and x3['staged'] == 1 and x3['pair'] == 0 and x3['mt'] == 2 and x3['resident'] == 0 and x3['wslots'] >= 4
+    stem = _plan(2072, 512, 1, 100, 55)
+    assert stem['kind'] == 2 and stem['staged'] == 1
+    down = _plan(2072, 512, 100, 100, 9, stride=2)
+    assert down['kind'] == 1 and down['mt'] == 1 and down['pair'] == 0 and down['resident'] == 0 and down['units'] == 2 * 2072
+    up = _plan(2072, 256, 100, 100, 9, shuffle=2)
+    assert up['kind'] == 1 and up['mt'] == 2 and up['n_iss'] == 2 and up['pair'] == 1 and up['grid'] == 148 and up['units'] == 2072
+    for p in (t1, t2, head, x3, stem, down, up):
+        assert 0 < p['smem'] <= smem_max and p['tmem_cols'] <= 512, p
+
+
+def test_cta_pairs_need_an_even_number_of_work_units():
+    """The up-sampling conv runs as CTA pairs only when every CTA of a pair gets the same number of tiles; an odd batch falls back
+    to the one-CTA kernel (same weights image, same result).  A pair's ring holds half-size units, so it has more slots."""
+    even = _plan(302, 256, 100, 100, 9, shuffle=2)
+    odd = _plan(301, 256, 100, 100, 9, shuffle=2)
+    assert even['pair'] == 1 and even['grid'] % 2 == 0 and even['grid'] == 148
+    assert odd['pair'] == 0 and odd['grid'] == 148
+    assert even['wslots'] > odd['wslots'] and even['smem'] <= 227 * 1024
+    tiny = _plan(2, 256, 100, 100, 9, shuffle=2)
+    assert tiny['pair'] == 1 and tiny['grid'] == 2
+    one = _plan(1, 256, 100, 100, 9, shuffle=2)
+    assert one['pair'] == 0 and one['grid'] == 1
+
+
 def test_codec_workspace_sizes_on_the_plane_path():
     lib = _lib.load()
     cfg = codec.CodecConfig(precision='tc_f16x3').to_struct()
