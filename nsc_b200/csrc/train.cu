@@ -107,35 +107,54 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[(t,ci)][co] += sum_{b,p} x[b][ci][p*s + t*d - padL] * g[b][co][p] : a (K*Cin) x Cout x (B*Lout) GEMM whose A operand is
-// gathered on the fly.  CTA tile 128 x (16 NT), 8 x NT per thread, 16-position chunks; batch split over gridDim.z, one atomicAdd
-// per output element per CTA (measured: the flush is < 1 % of the kernel).  The reduction runs as a software pipeline: the NEXT
-// chunk's operands are fetched from global memory into registers before the current chunk is multiplied out of shared memory,
-// then stored into the other shared-memory buffer -- one barrier per chunk and the global latency hidden behind the FMAs (the
-// first version staged, synchronised and multiplied in turn and sat at 6 TFLOP/s, bound by exposed load latency).
+// gathered on the fly.  A CTA owns a (8 TMW) x (NT TNW) tile of dW, thread (tm, tn) an 8 x NT block of it, and walks a range of
+// 16-position chunks of the (frame, position) reduction; one atomicAdd per output element per CTA at the end (measured: the
+// flush is < 1 % of the kernel).
+//   * Software pipeline: the NEXT chunk's operands are fetched from global memory into registers before the current chunk is
+//     multiplied out of shared memory, then stored into the other shared-memory buffer -- one barrier per chunk and the global
+//     latency hidden behind the FMAs (the first version staged, synchronised and multiplied in turn: 6 TFLOP/s, bound by exposed
+//     load latency).
+//   * Tile shapes follow the codec's layers instead of powers of two: the weight matrices are 180 / 450 / 900 rows by 20 / 50 /
+//     100 columns, which a 128 x 32 / 128 x 64 tile fills to 44-69 %.  25 x 10 threads (200 rows; 20 or 50 columns) and 12 x 20
+//     threads (96 rows; 100 columns) fill 75-94 %.
+//   * COLS_STRIDED: thread tn owns columns tn + TNW j (scalar shared loads, conflict-free) when NT is not 2 or 4.
 // blockIdx.x == 0 CTAs also reduce the bias gradient.
-constexpr int kWgM = 128, kWgR = 16;   // CTA tile: 128 rows (tap, cin) x (16 * NT) output channels, 16 positions per chunk
+constexpr int kWgR = 16;   // positions per chunk
 
-template <int NT>   // output channels per thread (4 -> 64-wide tile, 2 -> 32-wide tile for the narrow layers)
+template <int TMW, int TNW, int NT>
+struct WgShape {
+  static constexpr int kRows = 8 * TMW, kCols = NT * TNW, kActive = TMW * TNW;
+  static constexpr int kXK = (kRows * kWgR + 255) / 256;     // A-tile elements a thread stages per chunk
+  static constexpr int kGJ = (kCols * kWgR + 255) / 256;     // gradient-tile elements
+  static constexpr bool kStrided = !(NT == 2 || NT == 4);
+  static_assert(kActive <= 256, "wgrad tile: more owners than threads");
+};
+
+template <int TMW, int TNW, int NT>
 __global__ void __launch_bounds__(256, 2)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dw, float* __restrict__ db,
-             int64_t B, int Lin, int Lout, int Cin, int Cout, int K, int dil, int stride, int padL, int frames_per_split) {
-  constexpr int TN = 16 * NT;
-  __shared__ __align__(16) float xs[2][kWgR][kWgM + 4];
+             int64_t B, int Lin, int Lout, int Cin, int Cout, int K, int dil, int stride, int padL, int64_t chunks_per_split) {
+  using S = WgShape<TMW, TNW, NT>;
+  constexpr int kRows = S::kRows, TN = S::kCols, XK = S::kXK, GJ = S::kGJ;
+  __shared__ __align__(16) float xs[2][kWgR][kRows + 4];
   __shared__ __align__(16) float gs[2][kWgR][TN + 4];
   const int M = K * Cin;
-  const int m0 = blockIdx.x * kWgM, n0 = blockIdx.y * TN;
-  const int64_t b_lo = (int64_t)blockIdx.z * frames_per_split;
-  int64_t b_hi = b_lo + frames_per_split;
-  if (b_hi > B) b_hi = B;
-  const int tid = threadIdx.x, tm = tid >> 4, tn = tid & 15;   // 16 x 16 threads, 8 x NT outputs each
+  const int m0 = blockIdx.x * kRows, n0 = blockIdx.y * TN;
+  const int cpf = (Lout + kWgR - 1) / kWgR;                     // chunks per frame
+  const int64_t c_lo = (int64_t)blockIdx.z * chunks_per_split;
+  int64_t c_hi = c_lo + chunks_per_split;
+  if (c_hi > B * cpf) c_hi = B * cpf;
+  const int tid = threadIdx.x;
+  const bool owner = tid < S::kActive;
+  const int tm = owner ? tid / TNW : 0, tn = owner ? tid % TNW : 0;
   // staging map, fixed for the whole CTA: this thread fetches position (tid & 15) of rows (tid >> 4) + 16 k of the A tile and of
   // columns (tid >> 4) + 16 j of the gradient tile; lanes walk positions (contiguous in NCL)
   const int sr = tid & 15, sm = tid >> 4;
-  int xoff[8], xshift[8];      // ci * Lin + shift, shift = t * dil - padL (INT_MIN / 2: row beyond M)
+  int xoff[XK], xshift[XK];      // ci * Lin + shift, shift = t * dil - padL (INT_MIN / 2: row beyond the tile or M)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int m = m0 + sm + 16 * k;
-    if (m < M) {
+  for (int k = 0; k < XK; ++k) {
+    const int mm = sm + 16 * k, m = m0 + mm;
+    if (mm < kRows && m < M) {
       const int t = m / Cin, ci = m - t * Cin;
       xshift[k] = t * dil - padL;
       xoff[k] = ci * Lin + xshift[k];
@@ -144,31 +163,31 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __
       xoff[k] = 0;
     }
   }
-  const int cpf = (Lout + kWgR - 1) / kWgR;                     // chunks per frame
-  const int64_t n_chunks = (b_hi - b_lo) * cpf;
-  float xr[8], gr[NT];
+  float xr[XK], gr[GJ];
   auto fetch = [&](int64_t c) {
-    const int64_t b = b_lo + c / cpf;
-    const int p = (int)(c % cpf) * kWgR + sr;
+    const int64_t b = c / cpf;
+    const int p = (int)(c - b * cpf) * kWgR + sr;
     const float* xb = x + b * (int64_t)Cin * Lin;
     const float* gb = g + b * (int64_t)Cout * Lout;
     const int ps = p * stride;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < XK; ++k) {
       const int u = ps + xshift[k];
       xr[k] = (p < Lout && u >= 0 && u < Lin) ? __ldg(xb + xoff[k] + ps) : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int n = n0 + sm + 16 * j;
-      gr[j] = (n < Cout && p < Lout) ? __ldg(gb + (int64_t)n * Lout + p) : 0.f;
+    for (int j = 0; j < GJ; ++j) {
+      const int nn = sm + 16 * j, n = n0 + nn;
+      gr[j] = (nn < TN && n < Cout && p < Lout) ? __ldg(gb + (int64_t)n * Lout + p) : 0.f;
     }
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) xs[buf][sr][sm + 16 * k] = xr[k];
+    for (int k = 0; k < XK; ++k)
+      if (sm + 16 * k < kRows) xs[buf][sr][sm + 16 * k] = xr[k];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) gs[buf][sr][sm + 16 * j] = gr[j];
+    for (int j = 0; j < GJ; ++j)
+      if (sm + 16 * j < TN) gs[buf][sr][sm + 16 * j] = gr[j];
   };
   float acc[8][NT];
 #pragma unroll
@@ -178,50 +197,72 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __
   float bacc = 0.f;   // bias partial: thread tid < TN of the blockIdx.x == 0 CTAs owns column n0 + tid
   const bool do_bias = db != nullptr && blockIdx.x == 0 && tid < TN;
 
-  if (n_chunks > 0) {
-    fetch(0);
+  if (c_lo < c_hi) {
+    fetch(c_lo);
     stash(0);
   }
   __syncthreads();
-  for (int64_t c = 0; c < n_chunks; ++c) {
-    const int buf = (int)(c & 1);
-    if (c + 1 < n_chunks) fetch(c + 1);            // in flight while this chunk is multiplied
+  for (int64_t c = c_lo; c < c_hi; ++c) {
+    const int buf = (int)((c - c_lo) & 1);
+    if (c + 1 < c_hi) fetch(c + 1);                // in flight while this chunk is multiplied
+    if (owner) {
 #pragma unroll
-    for (int r = 0; r < kWgR; ++r) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&xs[buf][r][tm * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&xs[buf][r][tm * 8 + 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float cc[NT];
-      if (NT == 4) {
-        const float4 cv = *reinterpret_cast<const float4*>(&gs[buf][r][tn * 4]);
-        cc[0] = cv.x; cc[1] = cv.y; cc[NT > 2 ? 2 : 0] = cv.z; cc[NT > 3 ? 3 : 0] = cv.w;
-      } else {
-        const float2 cv = *reinterpret_cast<const float2*>(&gs[buf][r][tn * 2]);
-        cc[0] = cv.x; cc[1] = cv.y;
+      for (int r = 0; r < kWgR; ++r) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&xs[buf][r][tm * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&xs[buf][r][tm * 8 + 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float cc[NT];
+        if constexpr (NT == 4) {
+          const float4 cv = *reinterpret_cast<const float4*>(&gs[buf][r][tn * 4]);
+          cc[0] = cv.x; cc[1] = cv.y; cc[2] = cv.z; cc[3] = cv.w;
+        } else if constexpr (NT == 2) {
+          const float2 cv = *reinterpret_cast<const float2*>(&gs[buf][r][tn * 2]);
+          cc[0] = cv.x; cc[1] = cv.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < NT; ++j) cc[j] = gs[buf][r][tn + TNW * j];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(a[i], cc[j], acc[i][j]);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(a[i], cc[j], acc[i][j]);
     }
     if (do_bias) {
 #pragma unroll
       for (int r = 0; r < kWgR; ++r) bacc += gs[buf][r][tid];
     }
-    if (c + 1 < n_chunks) stash(buf ^ 1);          // the other buffer was last read before the previous barrier
+    if (c + 1 < c_hi) stash(buf ^ 1);              // the other buffer was last read before the previous barrier
     __syncthreads();
   }
+  if (owner) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + tm * 8 + i;
-    if (m >= M) continue;
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + tm * 8 + i;
+      if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int n = n0 + tn * NT + j;
-      if (n < Cout) atomicAdd(dw + (int64_t)m * Cout + n, acc[i][j]);
+      for (int j = 0; j < NT; ++j) {
+        const int n = n0 + (S::kStrided ? tn + TNW * j : tn * NT + j);
+        if (n < Cout) atomicAdd(dw + (int64_t)m * Cout + n, acc[i][j]);
+      }
     }
   }
   if (do_bias && n0 + tid < Cout) atomicAdd(db + n0 + tid, bacc);
+}
+
+template <int TMW, int TNW, int NT>
+void launch_wgrad(const float* x, const float* g, float* dw, float* db, int64_t B, int Lin, int Lout, int Cin, int Cout, int K,
+                  int dil, int stride, int padL, cudaStream_t st) {
+  using S = WgShape<TMW, TNW, NT>;
+  const int gx = ceil_div(K * Cin, S::kRows), gy = ceil_div(Cout, S::kCols);
+  const int64_t total = B * (int64_t)ceil_div(Lout, kWgR);
+  int64_t splits = ceil_div(4 * sm_count(), gx * gy);   // two resident CTAs per SM, two waves (2 -> 4 CTAs per SM of grid: 7.6 -> 7.4 ms)
+  if (splits > total) splits = total;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  const int64_t cps = ceil_div64(total, splits);
+  splits = ceil_div64(total, cps);
+  wgrad_kernel<TMW, TNW, NT><<<dim3(gx, gy, (unsigned)splits), 256, 0, st>>>(x, g, dw, db, B, Lin, Lout, Cin, Cout, K, dil, stride, padL, cps);
 }
 
 // Weight gradient of the 1-channel heads (k55, Cout = 1): dW[t][ci] = sum_{b,p} x[b][ci][p + t - padL] g[b][p] is a correlation,
@@ -628,16 +669,13 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     NSC_LAUNCH_OK();
   } else {
     const int M = r.K * r.Cin;
-    const int nt = r.Cout <= 32 ? 2 : 4;
-    const int gx = ceil_div(M, kWgM), gy = ceil_div(r.Cout, 16 * nt);
-    int splits = ceil_div(4 * sm_count(), gx * gy);   // two resident CTAs per SM, two waves (measured: 2 -> 4 CTAs per SM of grid 7.6 -> 7.4 ms)
-    if (splits > B) splits = (int)B;
-    if (splits < 1) splits = 1;
-    const int fps = (int)ceil_div64(B, splits);
-    splits = (int)ceil_div64(B, fps);
     ProfScope prof(st, "wgrad", 2.0 * B * Lout * (double)M * r.Cout, 4.0 * B * ((double)r.Lin * r.Cin + (double)Lout * r.Cout));
-    if (nt == 4) wgrad_kernel<4><<<dim3(gx, gy, splits), 256, 0, st>>>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, fps);
-    else wgrad_kernel<2><<<dim3(gx, gy, splits), 256, 0, st>>>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, fps);
+    // tile shape by output width: 20 -> 200 x 20, 50 -> 200 x 50, 100 -> 96 x 100; anything else the power-of-two tiles
+    if (r.Cout <= 20) launch_wgrad<25, 10, 2>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, st);
+    else if (r.Cout > 32 && r.Cout <= 50) launch_wgrad<25, 10, 5>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, st);
+    else if (r.Cout > 64 && r.Cout <= 100) launch_wgrad<12, 20, 5>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, st);
+    else if (r.Cout <= 32) launch_wgrad<16, 16, 2>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, st);
+    else launch_wgrad<16, 16, 4>(r.x, gpre, dw, db, B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL, st);
     NSC_LAUNCH_OK();
   }
   if (!need_dx) return NSC_OK;
