@@ -9,7 +9,7 @@ import sys, os
 root = os.environ.get('GRAFT_REPO_ROOT', '/root/repo')
 sys.path.insert(0, root); sys.path.insert(0, root + '/tests')
 import test_gpu_plane as t
-for layer, Bs in ((t.X_LAYERS[5], (2, 150)), (t.X_LAYERS[4], (3,)), (t.T_LAYERS[0], (5, 150)), (t.T_LAYERS[4], (5, 150)), (t.X_LAYERS[0], (3,))):
+for layer, Bs in ((t.X_LAYERS[5], (2, 150)), (t.X_LAYERS[4], (3,)), (t.T_LAYERS[0], (5, 149)), (t.T_LAYERS[4], (5, 149)), (t.X_LAYERS[0], (3,))):
     for B in Bs:
         e = t._run(B=B, precision=1, seed=B, **layer)
         print(layer, B, e)
@@ -18,6 +18,6 @@ import test_gpu_training as tt
 tt.test_backward_matches_autograd_two_codecs(-20.0, 1.0, 'tc_f16x3')
 print('training backward ok')
 PY
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/san_child.py > gpurun_out/sanitizer_memcheck_r01w.log 2>&1
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/san_child.py > gpurun_out/sanitizer_memcheck_r01w.log 2>&1
 echo "memcheck rc=$?" >> gpurun_out/sanitizer_memcheck_r01w.log
 tail -5 gpurun_out/sanitizer_memcheck_r01w.log
