@@ -103,6 +103,12 @@ def cpu_reference_throughput(n_frames, chunk=128, threads=None):
     return n_frames * SEC_PER_FRAME / dt, dt, threads
 
 
+def workload_name(codecs, bins):
+    """config.workload of both arms (ours and --impl reference)"""
+    return (f"cq{codecs}: LPC analysis + 256-bin LSF codebook + {codecs} cascaded bottleneck codecs "
+            f"('9 9 100 20 1 2', stride 2, {bins} bins, hard codes) + LPC synthesis")
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -120,8 +126,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "x real-time", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (LPC parts f64)", "data": "synthetic",
-        "config": {"workload": "cq2: LPC analysis + 256-bin LSF codebook + 2 cascaded bottleneck codecs + synthesis",
-                   "frames_per_step": n},
+        "config": {"workload": workload_name(2, 32), "frames_per_step": n,
+                   "sample_of": "the headline arm's workload, bounded to what the host cores finish in seconds per step"},
         "cpu_baseline": {"value": v, "unit": "x real-time", "cores": thr, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "TensorFlow/audiolazy/spectrum are not installable here; this is the CPU restatement, not TensorFlow",
@@ -323,8 +329,7 @@ def run_ours(args):
             "dtype": {"fp32": "f32", "tc_f16x3": "f32-equivalent (fp16 hi/lo split on tensor cores, fp32 accumulate)",
                       "tc_f16": "f16 inputs / f32 accumulate (REDUCED precision)"}[args.precision] +
                      "; LPC analysis/residual/synthesis f64", "data": "synthetic",
-            "config": {"workload": f"cq{args.codecs}: LPC analysis + 256-bin LSF codebook + {args.codecs} cascaded bottleneck codecs "
-                                   f"('9 9 100 20 1 2', stride 2, {args.bins} bins, hard codes) + LPC synthesis",
+            "config": {"workload": workload_name(args.codecs, args.bins),
                        "frames_per_gpu_per_step": B, "frames_per_step": frames_total, "conv_precision": args.precision,
                        "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of frames+windows per GPU per step, plus a "
                                     "multi-GB activation workspace cycled per ~2k-frame chunk (L2 is 126 MB); no explicit flush",
