@@ -588,6 +588,7 @@ struct XParams {
   int pair;                  // CTA pairs (cta_group::2): each CTA stages its own tile and HALF of every weight unit; the leader's
                              // M = 256 instructions cover both tiles (half the weight stream, half the instructions per tile)
   int slot_bytes;            // shared-memory bytes of one weight unit in this CTA (unit_bytes, or half of it in a pair)
+  int s_units;               // staged epilogue: residual / output units in the ring (3, or 4 in a pair)
   int64_t B, n_tiles;
 };
 
@@ -1068,41 +1069,50 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
 // ================================================================================================
 constexpr int kSEpiGroups = 4, kSEpiWarps = 4 * kSEpiGroups;
 constexpr int kSThreads = (kSEpiWarps + 6 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer, second MMA issuer, Toeplitz producers
-constexpr int kSUnits = 3;
+constexpr int kSUnits = 3, kSMaxUnits = 4;
 constexpr int kSPlane = 128 * 128;                 // one plane of one unit
 
 
+template <bool kPair>
 __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_constant__ XParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[4], a_empty[4], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
-  __shared__ uint64_t st_full[kSUnits], st_done[kSUnits], st_empty[kSUnits];
+  __shared__ uint64_t a_full2[4], w_full2[kXMaxW];     // CTA pairs: the peer's operands have landed (live in the leader)
+  __shared__ uint64_t st_full[kSMaxUnits], st_done[kSMaxUnits], st_empty[kSMaxUnits];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[128];
-  __shared__ __align__(16) __half s_xh[kGenSeg], s_xl[kGenSeg];   // PK_GEN: hi / lo halves of the tile's input samples
-  const bool gen = p.kind == PK_GEN;
+  __shared__ __align__(16) __half s_xh[kPair ? 8 : kGenSeg], s_xl[kPair ? 8 : kGenSeg];   // PK_GEN: hi / lo halves of the tile's input samples
+  const bool gen = !kPair && p.kind == PK_GEN;
+  constexpr bool pair = kPair;
+  const uint32_t crank = pair ? cluster_ctarank() : 0u;
+  const uint32_t n_su = (uint32_t)p.s_units;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nbuf = p.n_stage * p.kbuf;                 // n_stage == 1 (packed input)
   const uint32_t stg_bytes = (uint32_t)p.planes * kSPlane;
   uint8_t* sA = smem;
   uint8_t* sW = sA + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
-  uint8_t* sS = sW + (uint32_t)p.wslots * (uint32_t)p.unit_bytes;
+  uint8_t* sS = sW + (uint32_t)p.wslots * (uint32_t)p.slot_bytes;
   const int acc_cols = p.mt * p.Npad;
   const int ospp = p.out.spp;
   const int nb = p.Npad >> 4;
 
   if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], gen ? kXGenWarps : 1); mbar_init(&a_empty[i], p.n_iss); }
-    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], p.n_iss); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], p.n_iss); mbar_init(&acc_empty[i], kSEpiWarps); }
-    for (int i = 0; i < kSUnits; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_done[i], kSEpiWarps); mbar_init(&st_empty[i], 1); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], gen ? kXGenWarps : 1); mbar_init(&a_empty[i], p.n_iss); mbar_init(&a_full2[i], 1); }
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], p.n_iss); mbar_init(&w_full2[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], p.n_iss); mbar_init(&acc_empty[i], pair ? 2 * kSEpiWarps : kSEpiWarps); }
+    for (int i = 0; i < kSMaxUnits; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_done[i], kSEpiWarps); mbar_init(&st_empty[i], 1); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (warp == kSEpiWarps) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  if (warp == kSEpiWarps) {
+    if constexpr (pair) tmem_alloc_cg2(&tmem_base_s, (uint32_t)p.tmem_cols);
+    else tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // the peer's barriers (and TMEM) exist before anything arrives remotely
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -1184,19 +1194,26 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
           fence_async_smem();                            // generic-proxy writes -> visible to the bulk store
           __syncwarp();
           if (lane == 0) mbar_arrive(&st_done[slot]);
-          if (++slot == kSUnits) { slot = 0; sph ^= 1u; }
+          if (++slot == n_su) { slot = 0; sph ^= 1u; }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc_i]);
+      if (lane == 0) {
+        if constexpr (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);   // the leader's barrier counts both CTAs' epilogue warps
+        else mbar_arrive(&acc_empty[acc_i]);
+      }
     }
   } else if (warp == kSEpiWarps || warp == kSEpiWarps + 5) {
     // =========================== MMA issuers (one per M tile) ===========================
     const int issuer = warp == kSEpiWarps ? 0 : 1;
     if (issuer < p.n_iss && elect_one()) {
-      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty, nullptr, nullptr};
-      x_issuer<0>(p, gen, issuer, sA, sW, tmem, bars);
+      const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty, a_full2, w_full2};
+      if constexpr (!pair) x_issuer<0>(p, gen, issuer, sA, sW, tmem, bars);
+      else {
+        if (crank == 0) x_issuer<1>(p, false, issuer, sA, sW, tmem, bars);
+        else if (issuer == 0) x_issuer<2>(p, false, issuer, sA, sW, tmem, bars);   // the peer only reports what has landed
+      }
     }
   } else if (warp == kSEpiWarps + 1) {
     // =========================== A loader ===========================
@@ -1215,18 +1232,21 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
   } else if (warp == kSEpiWarps + 2) {
     // =========================== W loader ===========================
     if (elect_one()) {
+      // a CTA of a pair stages its half of every unit (output columns [rank Npad/2, (rank + 1) Npad/2))
+      const uint8_t* wsrc = p.wpack + (pair ? (size_t)crank * (size_t)p.slot_bytes : 0);
+      const uint32_t sbytes = (uint32_t)p.slot_bytes;
       if (p.resident) {
         for (int u = 0; u < p.n_units; ++u) {
-          mbar_expect_tx(&w_full[u], (uint32_t)p.unit_bytes);
-          bulk_g2s(sW + (uint32_t)u * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[u]);
+          mbar_expect_tx(&w_full[u], sbytes);
+          bulk_g2s(sW + (uint32_t)u * sbytes, wsrc + (size_t)u * p.unit_bytes, sbytes, &w_full[u]);
         }
       } else {
         uint32_t ws = 0, wph = 1;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
           for (int u = 0; u < p.n_units; ++u) {
             mbar_wait_relaxed(&w_empty[ws], wph);
-            mbar_expect_tx(&w_full[ws], (uint32_t)p.unit_bytes);
-            bulk_g2s(sW + ws * (uint32_t)p.unit_bytes, p.wpack + (size_t)u * p.unit_bytes, (uint32_t)p.unit_bytes, &w_full[ws]);
+            mbar_expect_tx(&w_full[ws], sbytes);
+            bulk_g2s(sW + ws * sbytes, wsrc + (size_t)u * p.unit_bytes, sbytes, &w_full[ws]);
             if (++ws == (uint32_t)p.wslots) { ws = 0; wph ^= 1u; }
           }
         }
@@ -1253,7 +1273,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
             } else {
               mbar_arrive(&st_full[slot]);
             }
-            if (++slot == kSUnits) { slot = 0; ph ^= 1u; }
+            if (++slot == n_su) { slot = 0; ph ^= 1u; }
           }
       }
     }
@@ -1282,7 +1302,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the unit may be refilled once the copy engine has read it
             mbar_arrive(&st_empty[slot]);
-            if (++slot == kSUnits) { slot = 0; ph ^= 1u; }
+            if (++slot == n_su) { slot = 0; ph ^= 1u; }
           }
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             // all stores complete before the CTA retires
@@ -1293,8 +1313,12 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // nobody frees TMEM (or retires) while the leader's instruction stream can still touch it
   tc_fence_after();
-  if (warp == kSEpiWarps) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  if (warp == kSEpiWarps) {
+    if constexpr (pair) tmem_dealloc_cg2(tmem, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  }
 }
 
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ourselves (alignment slack + static barriers)
@@ -1363,8 +1387,6 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   // narrow-input, wide-output layers (the HBM-bound third conv of a block) take the staged epilogue
   static const bool no_stage = getenv("NSC_PLANE_NOSTAGE") != nullptr;
   p->staged = ((gen || c.in.packed) && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage) ? 1 : 0;
-  const size_t stg_total = p->staged ? (size_t)kSUnits * c.planes * kSPlane : 0;
-  const size_t budget = kSmemBudget - stg_total;
   // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
   // CTA pairs (cta_group::2) for the layers with a plain epilogue: each CTA of a pair keeps its own tile and half of every
   // weight unit (half the weight stream into each shared memory, half the instructions).  Needs an even number of work units,
@@ -1380,14 +1402,18 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     p->stage_bytes = (p->tile + 16) * 128;
     p->tiles_per_frame = Lout / p->tile;
     p->n_tiles = c.B * p->tiles_per_frame;
-    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && !p->staged && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
+    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
     p->slot_bytes = p->pair ? p->unit_bytes / 2 : p->unit_bytes;
     const size_t slot = (size_t)p->slot_bytes;
     const size_t a1 = (size_t)p->n_stage * p->stage_bytes;
     const size_t wall = (size_t)p->n_units * slot;
     if (2 * mt * p->Npad > 512) continue;
+    // staged epilogue: ring of residual / output units.  A pair's half-size weight slots leave room for a fourth unit -- more
+    // bytes in flight per SM, which is what bounds the HBM-bound layers
+    p->s_units = p->staged ? ((p->pair && 2 * a1 + 3 * slot + (size_t)(kSUnits + 1) * c.planes * kSPlane <= kSmemBudget) ? kSUnits + 1 : kSUnits) : 0;
+    const size_t budget = kSmemBudget - (size_t)p->s_units * c.planes * kSPlane;
     if (p->n_units <= kXMaxW && 2 * a1 + wall <= budget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
-    else if (2 * a1 + 4ull * p->unit_bytes <= budget) { p->kbuf = 2; p->resident = 0; }
+    else if (2 * a1 + (p->pair ? 3 * slot : 4ull * p->unit_bytes) <= budget) { p->kbuf = 2; p->resident = 0; }
     else if (p->n_units <= kXMaxW && a1 + wall <= budget) { p->kbuf = 1; p->resident = 1; p->wslots = p->n_units; }
     else if (a1 + 3ull * p->unit_bytes <= budget) { p->kbuf = 1; p->resident = 0; }
     else continue;
@@ -1410,7 +1436,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     p->zero_from = written;
     p->zero_to = needed > written ? needed : written;
     if (p->staged && (p->zero_from != p->zero_to || p->n_stage * p->kbuf > 4)) p->staged = 0;   // (never for the codec's shapes)
-    if (p->staged) { p->pair = 0; p->slot_bytes = p->unit_bytes; }
+    if (!p->staged) p->s_units = 0;
     {
       // one issuing thread per M tile where the issue rate, not HBM, bounds the layer (measured); the staged layers are HBM-bound
       static const int knob = [] { const char* e = getenv("NSC_PLANE_ISSUERS"); return e ? atoi(e) : 0; }();
@@ -1424,7 +1450,7 @@ bool plan_x(const PlaneConv& c, XParams* p) {
 }
 
 size_t x_smem_bytes(const XParams& p) {
-  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.slot_bytes + (p.staged ? (size_t)kSUnits * p.planes * kSPlane : 0);
+  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.slot_bytes + (size_t)p.s_units * p.planes * kSPlane;
 }
 
 }  // namespace
@@ -1544,7 +1570,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   XParams p;
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
   const size_t smem = x_smem_bytes(p);
-  if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.staged && p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1559,7 +1586,7 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   auto launch_pairs = [&]() {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kXThreadsX);
+    cfg.blockDim = dim3(p.staged ? kSThreads : kXThreadsX);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1569,11 +1596,11 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, plane_x_kernel<false, true>, p);
+    return p.staged ? cudaLaunchKernelEx(&cfg, plane_xs_kernel<true>, p) : cudaLaunchKernelEx(&cfg, plane_x_kernel<false, true>, p);
   };
-  if (p.staged) plane_xs_kernel<<<(unsigned)grid, kSThreads, smem, st>>>(p);
+  if (p.pair) NSC_CUDA_OK(launch_pairs());
+  else if (p.staged) plane_xs_kernel<false><<<(unsigned)grid, kSThreads, smem, st>>>(p);
   else if (c.kind == PK_GEN) plane_x_kernel<true, false><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
-  else if (p.pair) NSC_CUDA_OK(launch_pairs());
   else plane_x_kernel<false, false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
   NSC_LAUNCH_OK();
   return NSC_OK;

@@ -111,13 +111,18 @@ def _child(env_extra, body):
     subprocess.run([sys.executable, '-c', code], check=True, env=dict(os.environ, **env_extra), timeout=600)
 
 
+PAIR_LAYERS = [X_LAYERS[5], X_LAYERS[0], X_LAYERS[1], X_LAYERS[2], X_LAYERS[3]]
+
+
+@pytest.mark.parametrize('layer', PAIR_LAYERS, ids=['up_shuffle', '20to100_L512', '20to100_L256_flat', '20to100_L256_bcast', '20to50_L512'])
 @pytest.mark.parametrize('precision', [1, 2])
-def test_cta_pair_up_conv(precision):
-    """An even number of work units runs the up-sampling 100 -> 100 conv as CTA pairs (cta_group::2: M = 256 instructions issued by
-    the leader, each CTA stages its own tile and half of every weight unit).  2 frames = one pair; 302 = every pair busy, ragged;
-    1184 frames = several units per CTA so ring slots, accumulator slots and the peer's landed-reports all wrap."""
+def test_cta_pair_layers(layer, precision):
+    """An even number of work units runs the up-sampling 100 -> 100 conv and the staged narrow-input layers as CTA pairs
+    (cta_group::2: M = 256 instructions issued by the leader, each CTA stages its own tile and half of every weight unit; the staged
+    kernel uses the freed shared memory for a fourth residual / output unit).  2 frames = one or two pairs; 302 = every pair busy,
+    ragged; 1184 frames = several units per CTA so ring slots, accumulator slots, staging units and the peer's landed-reports wrap."""
     for B in (2, 302, 1184):
-        e = _run(B=B, precision=precision, seed=B, **X_LAYERS[5])
+        e = _run(B=B, precision=precision, seed=B, **layer)
         assert e < (2e-5 if precision == 1 else 4e-3), (B, e)
 
 
@@ -126,7 +131,7 @@ def test_cta_pair_knob(pair):
     """NSC_PLANE_PAIR=0: the one-CTA kernel on even batches; =2: pairs wherever the shape allows (stride-2 conv, and 20 -> 20 on
     the tap-shift kernel via NSC_PLANE_NARROW=X).  Results must not depend on the choice."""
     _child({'NSC_PLANE_PAIR': pair, 'NSC_PLANE_NARROW': 'X'},
-           "for layer in (t.X_LAYERS[4], t.X_LAYERS[5], t.T_LAYERS[3], t.T_LAYERS[5]):\n"
+           "for layer in (t.X_LAYERS[4], t.X_LAYERS[5], t.X_LAYERS[0], t.X_LAYERS[3], t.T_LAYERS[3], t.T_LAYERS[5]):\n"
            "    for prec in (1, 2):\n"
            "        for B in (2, 302, 1184):\n"
            "            e = t._run(B=B, precision=prec, seed=B, **layer)\n"

@@ -59,7 +59,9 @@ def test_launch_plans_of_the_codec_layers():
     head = _plan(2072, 256, 100, 1, 55)
     assert head['kind'] == 0 and head['tmem_cols'] == 128
     x3 = _plan(2072, 512, 20, 100, 9, res_mode=1)
-    assert x3['kind'] == 1 and x3['staged'] == 1 and x3['pair'] == 0 and x3['mt'] == 2 and x3['resident'] == 0 and x3['wslots'] >= 4
+    assert x3['kind'] == 1 and x3['staged'] == 1 and x3['pair'] == 1 and x3['mt'] == 2 and x3['resident'] == 0 and x3['wslots'] >= 4
+    x3_odd = _plan(2071, 256, 20, 100, 9, res_mode=1)        # odd number of work units: one-CTA kernel, full-size weight slots
+    assert x3_odd['pair'] == 0 and x3_odd['staged'] == 1 and x3_odd['smem'] < x3['smem']
     stem = _plan(2072, 512, 1, 100, 55)
     assert stem['kind'] == 2 and stem['staged'] == 1
     down = _plan(2072, 512, 100, 100, 9, stride=2)
