@@ -14,6 +14,11 @@
 //                    are parked in shared memory and finished by the next quarter, which holds their down-spill.  No halo
 //                    is ever loaded or recomputed.  Finished rows go to a shared-memory ring that mirrors the output image
 //                    and leave by one bulk store per tile.
+//                    Narrow inputs (20 -> 20) use the GROUPED form: the nine taps are three groups of three, a group is a row shift
+//                    of the A descriptor (-2d, 0, +2d) and only the shifts INSIDE a group cross TMEM lanes -- five tap slots
+//                    (shifts -2d .. +2d) instead of nine, i.e. half the lane-crossing volume that bounds this layer.  The outer
+//                    groups shift one way only ({-2d,-d,0} and {0,+d,+2d}), which keeps frame borders exact: a row that would
+//                    take a contribution from outside the frame only ever needed zeros from there.
 //   plane_x_kernel   PK_X  one MMA per (tap, K step): a tap is a row shift of the A descriptor inside the staged tile
 //                    (+8 halo rows each side, which are the zero rows of the image at frame borders).  Weights stay
 //                    resident when they fit, else stream through a ring; with hi/lo planes every W_hi unit is used for
@@ -129,6 +134,20 @@ __global__ void plane_to_f32_kernel(PlaneTensor t, float* __restrict__ y, int y_
 // ------------------------------------------------------------------------------------------------
 // weight packing: fp32 (K, Cin, Cout) -> fp16 hi/lo operand slabs in the exact shared-memory image
 // ------------------------------------------------------------------------------------------------
+// Grouped taps-in-N (narrow inputs, k = 9): tap groups are row shifts of the A descriptor, the shifts inside a group cross TMEM lanes
+// as "tap slots".  Outer groups shift one way only, which keeps frame borders exact (see the file header).
+//   3 groups x 3 taps, 5 slots (-2d .. +2d):  shifts {-2d, 0, +2d};            group g, slot s in [g, g + 2]  -> tap s + 2 g
+//   5 groups {0,1} {2,3} {4} {5,6} {7,8}, 3 slots (-d, 0, +d):  shifts {-3d, -d, 0, +d, +3d}
+__host__ __device__ constexpr int tgroup_shift(int groups, int g) {      // in units of the dilation
+  return groups == 3 ? 2 * (g - 1) : (g == 0 ? -3 : g == 1 ? -1 : g == 2 ? 0 : g == 3 ? 1 : 3);
+}
+__host__ __device__ constexpr int tgroup_tap(int groups, int g, int slot) {   // -1: the slot is unused by this group
+  if (groups == 3) return (slot >= g && slot <= g + 2) ? slot + 2 * g : -1;
+  if (g < 2) return slot <= 1 ? 2 * g + slot : -1;
+  if (g == 2) return slot == 1 ? 4 : -1;
+  return slot >= 1 ? 2 * g - 2 + slot : -1;      // g = 3: slots 1, 2 -> taps 5, 6;  g = 4: -> taps 7, 8
+}
+
 struct PackArgs {
   const float* w;
   __half* out;
@@ -136,6 +155,7 @@ struct PackArgs {
   int rows;     // rows per unit (MMA N)
   int C;        // PK_T: output channels per tap
   int n_units;
+  int groups;   // PK_T grouped form (3 or 5 groups): unit = tap group g, row = (slot, co)
 };
 
 __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
@@ -153,6 +173,10 @@ __global__ void plane_pack_kernel(PackArgs a) {
       // units = weight slabs: unpacked input -> (plane, slab) ; packed input -> one slab [hi | lo]
       t = n / a.C;
       co = n - t * a.C;
+      if (a.groups > 1) {                        // n = (slot, co); unit = group
+        const int tt = t < (a.groups == 3 ? 5 : 3) ? tgroup_tap(a.groups, u, t) : -1;
+        t = tt < 0 ? a.K : tt;
+      }
       if (t >= a.K) co = -1;
       if (a.in_packed) { ci = k & 31; lo_plane = k >> 5; }
       else { ci = (u % a.in_spp) * 64 + k; lo_plane = u / a.in_spp; }
@@ -222,6 +246,7 @@ struct TParams {
   const float* bias;
   float* yvec;
   int N, n_wslab, ksteps;
+  int stage_bytes;           // one input slab of one tile: 128 rows, + 8 halo rows each side in the grouped form
   int L, dil, act, na;
   int64_t B;
 };
@@ -230,11 +255,11 @@ struct TParams {
 // output), so it keeps a third tile's worth.  (Eight slots instead of twelve give the 100 -> 20 layer a fifth input stage: the
 // layer is bound by bytes in flight -- 4 x 16 KB per SM against ~2 us of loaded HBM latency is 32 GB/s per SM, 73 % of peak.)
 constexpr int t_slots(int C) { return C == 1 ? 12 : 8; }
-constexpr int kAStage = 128 * 128;  // one input slab of one tile
 constexpr int kORing = 256;         // rows of the output staging ring (two tiles)
 
 // Epilogue organisation: C = 20 -> three warps per TMEM lane quarter, one 8-channel chunk of the output row each
 // (channels 0-7, 8-15, 16-19 + zero padding); C = 1 (k55 head) -> one warp per quarter.
+// TAPS = tap slots the epilogue sums across lanes (9; 5 in the grouped form; 55 for the head), GROUPS = MMA groups by row shift
 template <int C, int TAPS>
 struct TShape {
   static constexpr int kGroups = (C == 1) ? 1 : 3;
@@ -252,12 +277,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 // ---- phase 1: shifted sums of NCH channels of one 32-row quarter ------------------------------------
 // tcol: TMEM address of this warp's first column of tap 0; taps are `tap_stride` columns apart.
-template <int NCH>
-__device__ __forceinline__ void t_phase1_k9(uint32_t tcol, const int (&srcl)[9], uint32_t inrm, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
-  // all nine taps are fetched before the single wait: 9 * NCH independent shuffles then pipeline back to back
-  uint32_t r[9][8];
+template <int NCH, int TAPS>
+__device__ __forceinline__ void t_phase1(uint32_t tcol, const int (&srcl)[TAPS], uint32_t inrm, float (&acc)[NCH], float (&up)[NCH], float (&down)[NCH]) {
+  constexpr int kMid = TAPS / 2;
+  // all tap slots are fetched before the single wait: the independent shuffles then pipeline back to back
+  uint32_t r[TAPS][8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
+  for (int t = 0; t < TAPS; ++t) {
     if constexpr (NCH == 8) tmem_ld8(tcol + (uint32_t)(t * 20), r[t]);
     else {
       uint32_t b[4];
@@ -272,13 +298,13 @@ __device__ __forceinline__ void t_phase1_k9(uint32_t tcol, const int (&srcl)[9],
   float2 a2[NCH / 2], u2[NCH / 2], d2[NCH / 2];
 #pragma unroll
   for (int c = 0; c < NCH / 2; ++c) {
-    a2[c] = make_float2(__uint_as_float(r[4][2 * c]), __uint_as_float(r[4][2 * c + 1]));
+    a2[c] = make_float2(__uint_as_float(r[kMid][2 * c]), __uint_as_float(r[kMid][2 * c + 1]));
     u2[c] = make_float2(0.f, 0.f);
     d2[c] = make_float2(0.f, 0.f);
   }
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    if (t == 4) continue;
+  for (int t = 0; t < TAPS; ++t) {
+    if (t == kMid) continue;
     const int src = srcl[t];
     const bool inr = (inrm >> t) & 1u;
 #pragma unroll
@@ -287,8 +313,8 @@ __device__ __forceinline__ void t_phase1_k9(uint32_t tcol, const int (&srcl)[9],
       x.x = __shfl_sync(0xffffffffu, __uint_as_float(r[t][2 * c]), src);
       x.y = __shfl_sync(0xffffffffu, __uint_as_float(r[t][2 * c + 1]), src);
       if (inr) a2[c] = __fadd2_rn(a2[c], x);
-      else if (t > 4) d2[c] = __fadd2_rn(d2[c], x);   // source row is in this quarter, target row in the previous one
-      else u2[c] = __fadd2_rn(u2[c], x);              // ... in the next one
+      else if (t > kMid) d2[c] = __fadd2_rn(d2[c], x);   // source row is in this quarter, target row in the previous one
+      else u2[c] = __fadd2_rn(u2[c], x);                 // ... in the next one
     }
   }
 #pragma unroll
@@ -319,9 +345,11 @@ __device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc
   acc = a; up = u; down = d;
 }
 
-template <int C, int TAPS>
+template <int C, int TAPS, int GROUPS>
 __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
   using S = TShape<C, TAPS>;
+  constexpr int kTE = (C == 1) ? 1 : TAPS;              // tap slots of the shuffle tap sum (the head has its own phase 1)
+  const uint32_t kAStage = (uint32_t)p.stage_bytes;
   constexpr int kMaxM = S::kMaxM, kRF = S::kRowFloats, kEpi = S::kEpiWarps;
   constexpr int NCHMAX = (C == 1) ? 1 : 8;
   extern __shared__ uint8_t smem_raw[];
@@ -368,11 +396,11 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
     const bool low = lane < m, high = lane >= 32 - m;
     // everything that depends only on the lane is computed once: shuffle sources and the in-range mask of the nine taps,
     // this thread's rows inside a spill slot, its swizzle phase
-    int srcl[9];
+    int srcl[kTE];
     uint32_t inrm = 0;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int s = (t - 4) * p.dil;
+    for (int t = 0; t < kTE; ++t) {
+      const int s = (t - kTE / 2) * p.dil;
       srcl[t] = (lane + s) & 31;
       if ((unsigned)(lane + s) < 32u) inrm |= 1u << t;
     }
@@ -420,11 +448,11 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         } else {
           if (grp == 2) {
             float a4[4], u4[4], d4[4];
-            t_phase1_k9<4>(tcol, srcl, inrm, a4, u4, d4);
+            t_phase1<4, kTE>(tcol, srcl, inrm, a4, u4, d4);
 #pragma unroll
             for (int c = 0; c < 8; ++c) { acc[c] = c < 4 ? a4[c & 3] : 0.f; up[c] = c < 4 ? u4[c & 3] : 0.f; down[c] = c < 4 ? d4[c & 3] : 0.f; }
           } else {
-            t_phase1_k9<8>(tcol, srcl, inrm, acc, up, down);
+            t_phase1<8, kTE>(tcol, srcl, inrm, acc, up, down);
           }
         }
         tc_fence_before();
@@ -518,7 +546,19 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
             mbar_wait(&a_full[slot], sph);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + slot * (uint32_t)(kAStage >> 4);
-            if (packed) {
+            if constexpr (GROUPS > 1) {
+              // tap groups = row shifts of the staged tile (8 halo rows above)
+#pragma unroll
+              for (int g = 0; g < GROUPS; ++g) {
+                const uint32_t ag = a_lo + (uint32_t)(8 + tgroup_shift(GROUPS, g) * p.dil) * 8u;   // one row = 128 bytes = 8 descriptor units
+                const uint32_t bg = w_lo0 + (uint32_t)g * wslab_lo;
+                issue_n(p.ksteps, d, ag, bg, idesc, g == 0 ? accum : 1u);                 // hi * W_hi
+                if (planes == 2) {
+                  issue_n(p.ksteps, d, ag, bg + 4u, idesc, 1u);                           // hi * W_lo
+                  issue_n(p.ksteps, d, ag + 4u, bg, idesc, 1u);                           // lo * W_hi
+                }
+              }
+            } else if (packed) {
               issue_n(p.ksteps, d, a_lo, w_lo0, idesc, accum);            // hi * W_hi
               if (planes == 2) {
                 issue_n(p.ksteps, d, a_lo, w_lo0 + 4u, idesc, 1u);        // hi * W_lo   (lo halves start 64 bytes into the row)
@@ -551,7 +591,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
           for (int s = 0; s < nst; ++s) {
             mbar_wait_relaxed(&a_empty[slot], sph);
             mbar_expect_tx(&a_full[slot], kAStage);
-            bulk_g2s(sA + slot * kAStage, img + s * sb + (int64_t)(8 + 128 * j) * 128, kAStage, &a_full[slot]);
+            bulk_g2s(sA + slot * kAStage, img + s * sb + (int64_t)((GROUPS > 1 ? 0 : 8) + 128 * j) * 128, kAStage, &a_full[slot]);
             if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
           }
         }
@@ -1325,6 +1365,8 @@ constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ou
 
 struct TPlan {
   int N, n_wslab, ksteps, na;
+  int groups;        // 3: grouped form (narrow input), 1: all taps in N
+  int stage_bytes;
   size_t smem;
 };
 
@@ -1335,9 +1377,17 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   if (c.stride != 1 || c.shuffle != 1 || c.res_mode != RES_NONE || c.post_act != NSC_ACT_NONE) return false;
   if (c.Cin < 2 || c.in.deint || c.Lin % 128 != 0 || c.in.rows != c.Lin) return false;
   if (k9 && (!c.out.packed || c.out.deint || c.out.rows != c.Lin)) return false;
-  pl->N = k9 ? 192 : 64;
+  // narrow -> narrow: tap groups by row shift, 5 (or 3) tap slots across lanes instead of 9 -- the lane-crossing volume bounds the layer.
+  // Measured per 33k frames (both dilations): nine taps in N 21.1 ms, 3 groups / 5 slots 18.4 ms, 5 groups / 3 slots 21.0 ms on a box
+  // where 3 groups took 19.3 (30 MMAs per tile from ONE issuing thread cost more than the lanes save).
+  // NSC_PLANE_TGROUPS=3 (default) / 5 / 0 (all nine taps in N).  Wide inputs stay ungrouped: three times the MMAs would exceed their HBM time.
+  static const int groups_knob = [] { const char* e = getenv("NSC_PLANE_TGROUPS"); const int v = e ? atoi(e) : 3; return (v == 3 || v == 5) ? v : 1; }();
+  pl->groups = (k9 && c.in.packed) ? groups_knob : 1;
+  pl->stage_bytes = pl->groups > 1 ? (128 + 16) * 128 : 128 * 128;
+  const size_t kAStage = (size_t)pl->stage_bytes;
+  pl->N = k9 ? (pl->groups == 5 ? 64 : pl->groups == 3 ? 112 : 192) : 64;
   pl->ksteps = (c.Cin + 15) / 16;
-  pl->n_wslab = c.in.packed ? 1 : c.in.planes * c.in.spp;
+  pl->n_wslab = pl->groups > 1 ? pl->groups : (c.in.packed ? 1 : c.in.planes * c.in.spp);
   const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
   const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * t_slots(k9 ? 20 : 1) * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
   if (fixed + 2ull * kAStage > kSmemBudget) return false;
@@ -1493,6 +1543,7 @@ bool plane_plan_info(const PlaneConv& c, int64_t* o) {
   if (c.kind == PK_T) {
     TPlan pl;
     if (!plan_t(c, &pl)) return false;
+    o[1] = pl.groups > 1 ? pl.groups : 0;    // (taps-in-N: the "staged" field reports the tap groups of the grouped form)
     o[3] = 1; o[4] = 1; o[5] = 1; o[6] = pl.n_wslab; o[7] = pl.na; o[8] = (int64_t)pl.smem;
     int cols = 32;
     while (cols < 2 * pl.N) cols *= 2;
@@ -1518,10 +1569,11 @@ int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
   a.in_packed = c.kind == PK_GEN ? 0 : c.in.packed;
   a.in_spp = c.kind == PK_GEN ? 1 : c.in.spp;
   a.C = c.Cout;
+  a.groups = 1;
   if (c.kind == PK_T) {
     TPlan pl;
     NSC_CHECK_ARG(plan_t(c, &pl), "plane engine: unsupported taps-in-N layer (k%d d%d %d->%d)", c.K, c.dil, c.Cin, c.Cout);
-    a.rows = pl.N; a.n_units = pl.n_wslab;
+    a.rows = pl.N; a.n_units = pl.n_wslab; a.groups = pl.groups;
   } else {
     XParams p;
     PlaneConv cc = c;
@@ -1550,19 +1602,25 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     TParams p;
     p.in = c.in; p.out = c.out;
     p.wpack = static_cast<const uint8_t*>(c.wpack); p.bias = c.bias; p.yvec = c.yvec;
-    p.N = pl.N; p.n_wslab = pl.n_wslab; p.ksteps = pl.ksteps; p.L = c.Lin; p.dil = c.dil; p.act = c.act; p.na = pl.na; p.B = c.B;
+    p.N = pl.N; p.n_wslab = pl.n_wslab; p.ksteps = pl.ksteps; p.stage_bytes = pl.stage_bytes; p.L = c.Lin; p.dil = c.dil; p.act = c.act; p.na = pl.na; p.B = c.B;
     NSC_CHECK_ARG(c.Cout > 1 || c.yvec != nullptr, "plane engine: head without an output vector");
     snprintf(name, sizeof(name), "pT%d_k%dd%d_c%dto%d", c.planes, c.K, c.dil, c.Cin, c.Cout);
     // algorithmic bytes: every input and output plane image moved exactly once (zero rows excluded)
     const double bytes = (double)c.B * (pt_payload_bytes(c.in) + (c.Cout > 1 ? pt_payload_bytes(c.out) : 4.0 * c.Lin));
     ProfScope prof(st, name, 2.0 * macs, bytes);
     const int64_t grid = c.B < sm_count() ? c.B : sm_count();
-    if (c.Cout == 20) {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 9><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
+    if (c.Cout == 20 && pl.groups == 5) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 3, 5><<<(unsigned)grid, TShape<20, 3>::kThreads, pl.smem, st>>>(p);
+    } else if (c.Cout == 20 && pl.groups == 3) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 5, 3><<<(unsigned)grid, TShape<20, 5>::kThreads, pl.smem, st>>>(p);
+    } else if (c.Cout == 20) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<20, 9, 1><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
     } else {
-      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<1, 55><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      plane_t_kernel<1, 55, 1><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
     }
     NSC_LAUNCH_OK();
     return NSC_OK;

@@ -138,6 +138,19 @@ def test_cta_pair_knob(pair):
            "            assert e < (2e-5 if prec == 1 else 4e-3), (layer, prec, B, e)\n")
 
 
+@pytest.mark.parametrize('groups', ['0', '5'])
+def test_narrow_layers_with_other_tap_groupings(groups):
+    """20 -> 20 (k9, dilation 1 / 2): the default is three tap groups by descriptor row shift with five tap slots across TMEM lanes;
+    NSC_PLANE_TGROUPS=0 keeps all nine taps in N, =5 uses five groups with three slots.  Same results, frame borders included
+    (5 frames: every tile touches a border; 301: CTAs walk several frames)."""
+    _child({'NSC_PLANE_TGROUPS': groups},
+           "for layer in (t.T_LAYERS[3], t.T_LAYERS[4], t.T_LAYERS[5]):\n"
+           "    for prec in (1, 2):\n"
+           "        for B in (5, 301):\n"
+           "            e = t._run(B=B, precision=prec, seed=B, **layer)\n"
+           "            assert e < (2e-5 if prec == 1 else 4e-3), (layer, prec, B, e)\n")
+
+
 def test_unsupported_shape_fails_loudly():
     from nsc_b200 import _lib
     lib = _lib.load()

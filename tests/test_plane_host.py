@@ -55,7 +55,7 @@ def test_launch_plans_of_the_codec_layers():
     t1 = _plan(2072, 512, 100, 20, 9)
     assert t1['kind'] == 0 and t1['stages'] == 5 and t1['wslots'] == 4 and t1['tmem_cols'] == 512      # 4 weight slabs resident, 5 input stages
     t2 = _plan(2072, 512, 20, 20, 9, dil=2)
-    assert t2['kind'] == 0 and t2['stages'] == 8 and t2['wslots'] == 1
+    assert t2['kind'] == 0 and t2['staged'] == 3 and t2['stages'] == 7 and t2['wslots'] == 3 and t2['tmem_cols'] == 256   # grouped form: 3 tap groups, 5 tap slots
     head = _plan(2072, 256, 100, 1, 55)
     assert head['kind'] == 0 and head['tmem_cols'] == 128
     x3 = _plan(2072, 512, 20, 100, 9, res_mode=1)
