@@ -23,11 +23,19 @@
 //                    (+8 halo rows each side, which are the zero rows of the image at frame borders).  Weights stay
 //                    resident when they fit, else stream through a ring; with hi/lo planes every W_hi unit is used for
 //                    both the A_hi and A_lo products while it is resident.  The 100 -> 100 convs (stride 2 / sub-pixel).
-//                    <true>: PK_GEN, the same pipeline fed from a Toeplitz tile that producer warps build from a 1-channel
+//                    <true, .>: PK_GEN, the same pipeline fed from a Toeplitz tile that producer warps build from a 1-channel
 //                    fp32 signal (decoder's k9 1 -> 20).
 //   plane_xs_kernel  PK_X / PK_GEN with a STAGED epilogue (narrow-input 20 -> 100 / 20 -> 50 + residual, and the k55 stem): the
 //                    residual tile comes in and the result goes out by bulk copies through shared-memory units; no thread
 //                    touches global memory.
+//
+// CTA PAIRS (plane_x_kernel<false, true>, plane_xs_kernel<true>; cta_group::2): with an even number of work units two CTAs on one
+// TPC run as a pair.  Each keeps its own tile(s), loaders, epilogue and TMEM half, but only HALF of every weight unit (output columns
+// [rank N/2, (rank + 1) N/2)); the leader's issuing thread multiplies both tiles with one M = 256 instruction per K step.  The peer's
+// issuing thread forwards "my operand landed" to twin barriers in the leader (plain remote mbarrier.arrive -- a cluster-scope
+// release costs ~900 cycles per arrive), tcgen05.commit multicasts "slot free" / "accumulator full" back to both CTAs, and both
+// CTAs' epilogue warps arrive on the leader's "accumulator empty".  What it buys: half the weight stream into and half the B-operand
+// reads out of each shared memory, and room for a fourth staging unit in plane_xs_kernel.
 //
 // Epilogues write the next layer's plane image directly (bias, activation, residual add from the residual's planes,
 // hi/lo split, sub-pixel shuffle, stride-2 de-interleave are all index arithmetic on the way out).
