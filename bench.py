@@ -196,14 +196,19 @@ def run_ours(args):
     out_host = {}
     # End-to-end step through the public API with HOST buffers: the batch goes through in sub-batches so that the pinned-memory
     # H2D copy of sub-batch k+1 and the D2H copy of sub-batch k-1 (copy stream) run under the compute of sub-batch k.
-    n_sub = max(1, min(4, B // 4144))
-    bounds = [(i * B // n_sub, (i + 1) * B // n_sub) for i in range(n_sub)]
+    # Sub-batches are whole passes of the engine (2 x 2,072 frames) so no pass is split; the exposed part of the copies is the
+    # first sub-batch's H2D and the last one's D2H.  H2D and D2H use separate streams (both copy engines).
+    sub = 4144
+    n_sub = max(1, min(8, -(-B // sub)))
+    bounds = [(i * sub, (i + 1) * sub if i + 1 < n_sub else B) for i in range(n_sub)]
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
     dev_in = [None] * n_sub
 
     def step_e2e():
         main = torch.cuda.current_stream()
         copy_stream.wait_stream(main)
+        d2h_stream.wait_stream(main)
         h2d_done = []
         for i, (lo, hi) in enumerate(bounds):
             with torch.cuda.stream(copy_stream):
@@ -220,16 +225,17 @@ def run_ours(args):
             done = torch.cuda.Event()
             done.record(main)
             outs = [('lsf_idx', r['lsf_idx']), ('syn', r['synthesized'])] + [('idx%d' % k, t) for k, t in enumerate(r['idx'])]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
                 for k, t in outs:
                     if k not in out_host:
                         out_host[k] = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
                     out_host[k][lo:hi].copy_(t, non_blocking=True)
-                    t.record_stream(copy_stream)
+                    t.record_stream(d2h_stream)
             xd.record_stream(main)
             wd.record_stream(main)
         main.wait_stream(copy_stream)
+        main.wait_stream(d2h_stream)
         return r
 
     def barrier():
