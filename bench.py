@@ -46,6 +46,68 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, 'fallback'
 
 
+
+ALG_BYTES_PER_FRAME = {"cq": 4624, "cq_with_lpc_window": 8720, "codec1": 4352}   # compulsory HBM bytes per frame
+
+
+def ncu_facts():
+    """Numbers that only a profiler gives, from the committed ncu summary of THIS round (profiles/r02_ncu_facts.json, written by
+    tools/ncu_facts.py from `ncu --set full` / `--metrics dram__bytes...` captures of the same bench command): per kernel
+    dram bytes per launch and sm__pipe_tensor_cycles_active, and the whole step's DRAM bytes per frame."""
+    p = os.path.join(ROOT, 'profiles', 'r02_ncu_facts.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def roofline_record(agg, tot_ms, args, frames):
+    """the conv kernels are dense contractions (1.3e5 FLOP per compulsory byte), so the roof that binds them is the
+    TENSOR PIPE: frac = algorithmic FLOP/s (2 x real-channel MACs, no padding, ONE product per MAC) / measured sustained bf16
+    rate.  The fp32-class mode issues 3 MMAs per product (fp16 hi/lo split), so `issued_frac` = 3 x frac is what the pipe
+    executes; ncu's own sm__pipe_tensor_cycles_active sits beside it.  HBM stays in the record as `traffic` (measured DRAM bytes
+    of one launch) against the kernel's algorithmic bytes, and for the whole step against SURVEY's compulsory bytes per frame."""
+    hbm, bf16, bf16_sus, how = peaks()
+    is_conv = lambda k: (k.startswith(('conv_', 'pT', 'pX', 'pG', 'pB')) or (k.startswith('tc') and k != 'tc_pack_weights'))
+    conv = [(k, v) for k, v in agg.items() if is_conv(k)]
+    top_name, top = max(conv, key=lambda kv: kv[1][0])
+    tensor_path = not top_name.startswith('conv_')
+    mma_per_product = 3 if (args.precision == 'tc_f16x3' and tensor_path) else 1
+    secs = top[0] * 1e-3
+    ach_tf = top[1] / secs / 1e12
+    ach_gbs = top[2] / secs / 1e9
+    conv_ms = sum(v[0] for _, v in conv)
+    conv_fl = sum(v[1] for _, v in conv)
+    all_fl = sum(v[1] for v in agg.values())
+    facts = ncu_facts()
+    kf = facts.get('kernels', {}).get(top_name, {})
+    traffic = kf.get('dram_bytes_per_launch')
+    alg_bytes_launch = top[2] / top[3]
+    step = facts.get('whole_step', {})
+    dram_pf = step.get('dram_bytes_per_frame')
+    peak = bf16_sus if tensor_path else None
+    rec = {
+        "bound": "tensor", "achieved": ach_tf, "peak": bf16_sus, "unit": "TFLOP/s", "frac": ach_tf / bf16_sus,
+        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how}); the kernel is timed inside a long step",
+        "kernel": top_name, "launch_ms": top[0] / top[3], "launches_per_step": top[3], "share_of_step": top[0] / tot_ms,
+        "pipe": ("fp32 FFMA (CUDA cores)" if not tensor_path else "tcgen05 kind::f16, fp32 accumulate in TMEM"),
+        "mma_per_product": mma_per_product,
+        "issued_frac": ach_tf * mma_per_product / bf16_sus,
+        "tensor_pipe_active_ncu": kf.get('sm__pipe_tensor_cycles_active_pct'),
+        "traffic": traffic,
+        "traffic_detail": ({"algorithmic_bytes_of_that_launch": kf.get('algorithmic_bytes_per_launch'),
+                            "traffic_vs_algorithmic": (traffic / kf['algorithmic_bytes_per_launch']) if traffic and kf.get('algorithmic_bytes_per_launch') else None,
+                            "frames_of_that_launch": kf.get('frames_per_launch'), "source": kf.get('source')} if kf else None),
+        "hbm": {"achieved_gbs_algorithmic": ach_gbs, "frac_of_measured": ach_gbs / hbm, "peak_gbs": hbm,
+                "algorithmic_bytes_per_launch": alg_bytes_launch,
+                "note": "real channels only (2 B per channel and fp16 plane), input + output (+ residual) moved once"},
+        "all_conv": {"tflops_algorithmic": conv_fl / (conv_ms * 1e-3) / 1e12, "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / bf16_sus,
+                     "issued_frac": conv_fl * mma_per_product / (conv_ms * 1e-3) / 1e12 / bf16_sus, "share_of_step": conv_ms / tot_ms},
+        "whole_step": {"tflops_algorithmic": all_fl / (tot_ms * 1e-3) / 1e12, "frac": all_fl / (tot_ms * 1e-3) / 1e12 / bf16_sus,
+                       "dram_bytes_per_frame": dram_pf, "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME["cq"] if args.codecs == 2 else None,
+                       "traffic_vs_algorithmic": (dram_pf / ALG_BYTES_PER_FRAME["cq"]) if (dram_pf and args.codecs == 2) else None,
+                       "source": step.get('source')},
+    }
+    return rec
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -166,21 +228,11 @@ def run_ours(args):
     from nsc_b200 import _lib, codec, lpc_utilities as lu
     from nsc_b200.sharding import max_over_ranks
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        # the contract is ONE JSON line on stdout: keep NCCL's banner ("NCCL version ...") off it
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+    world, rank, local, dev = init_dist()
     lib = _lib.load()
 
     B = args.frames                      # frames per GPU per step (weak scaling)
-    cfg = codec.CodecConfig(precision=args.precision, num_bins=args.bins)
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=args.precision, num_bins=args.bins)
     gcs = [codec.NeuralCodec(cfg, device=dev, seed=5 + i) for i in range(args.codecs)]
     cm = codec.CMRL(gcs, res_scalar=1.0)
     x_np, win_np = synth_audio(min(B, 4096), seed=1234 + rank)
@@ -273,47 +325,27 @@ def run_ours(args):
         agg = kernel_breakdown(lib, step_device)
         tot = sum(a[0] for a in agg.values())
         breakdown = breakdown_table(agg)
-        is_conv = lambda k: (k.startswith(('conv_', 'pT', 'pX', 'pG')) or (k.startswith('tc') and k != 'tc_pack_weights'))
-        conv = [(k, v) for k, v in agg.items() if is_conv(k)]
-        top_name, top = max(conv, key=lambda kv: kv[1][0])
-        hbm, bf16, bf16_sus, how = peaks()
-        tensor_path = not top_name.startswith('conv_')
-        mma_per_product = 3 if (args.precision == 'tc_f16x3' and tensor_path) else 1
-        secs = top[0] * 1e-3
-        ach_tf = top[1] / secs / 1e12
-        ach_gbs = top[2] / secs / 1e9
-        # which roof binds this kernel: time its algorithmic bytes need at the measured HBM rate vs the time its ISSUED
-        # tensor flops need at the measured bf16 rate
-        t_hbm = top[2] / (hbm * 1e9)
-        t_tc = top[1] * mma_per_product / (bf16_sus * 1e12)
-        conv_ms = sum(v[0] for _, v in conv)
-        conv_fl = sum(v[1] for _, v in conv)
-        conv_by = sum(v[2] for _, v in conv)
-        traffic = traffic_detail = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-        if os.path.exists(tpath):
-            t = json.load(open(tpath)).get(top_name)
-            if t:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
-                traffic = t["dram_bytes_per_launch"]
-                traffic_detail = {"frames_of_that_launch": t["frames_per_launch"],
-                                  "algorithmic_bytes_of_that_launch": 589824 * t["frames_per_launch"], "source": t["source"]}
-        common = {"kernel": top_name, "launch_ms": top[0] / top[3], "share_of_step": top[0] / tot, "traffic": traffic, "traffic_detail": traffic_detail,
-                  "pipe": ("fp32 FFMA (CUDA cores)" if not tensor_path else
-                           "tcgen05 kind::f16, fp32 accumulate in TMEM" + (" -- 3 MMAs per product (fp16 hi/lo split): "
-                           "issued tensor flops are 3x the algorithmic flops" if mma_per_product == 3 else "")),
-                  "achieved_tflops_algorithmic": ach_tf, "issued_tflops": ach_tf * mma_per_product,
-                  "tensor_frac_of_measured_bf16_sustained": ach_tf * mma_per_product / bf16_sus,
-                  "achieved_gbs_algorithmic": ach_gbs, "hbm_frac_of_measured": ach_gbs / hbm,
-                  "all_conv": {"tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "gbs": conv_by / (conv_ms * 1e-3) / 1e9,
-                               "hbm_frac_of_measured": conv_by / (conv_ms * 1e-3) / 1e9 / hbm,
-                               "share_of_step": conv_ms / tot}}
-        if t_hbm >= t_tc:
-            roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
-                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how}); algorithmic bytes = the layer's input, residual and "
-                                   "output plane images, each moved once", **common}
-        else:
-            roof = {"bound": "tensor", "achieved": ach_tf, "peak": bf16_sus, "unit": "TFLOP/s", "frac": ach_tf / bf16_sus,
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how}); kernel timed inside a long step", **common}
+        roof = roofline_record(agg, tot, args, B)
+
+    # ---- the other BASELINE.json configurations as bounded sub-records of the same run (every rank takes part: the training
+    # step contains the gradient all-reduce, the corpus and the sweeps shard by rank)
+    subrec = None
+    if args.sub_records:
+        del x_dev, win_dev
+        torch.cuda.empty_cache()
+        subrec = {}
+        for name, fn in (("codec1_b128", lambda: measure_codec1(args, world, rank, dev, lib, cpu=not args.no_cpu_baseline)),
+                         ("cq_scaled", lambda: measure_cq_sweep(args, world, rank, dev, lib)),
+                         ("train", lambda: measure_train(args, world, rank, dev, lib, 20, 5, breakdown=True)),
+                         ("corpus_1h_per_gpu", lambda: measure_corpus(args, world, rank, dev, lib, 2, 1, n_utt=360))):
+            try:
+                subrec[name] = fn()
+            except Exception as e:      # a sub-record must never cost the headline line
+                subrec[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise
+        if world > 1 and isinstance(subrec.get("train"), dict):
+            subrec["train"].pop("kernel_breakdown", None)
 
     if rank == 0:
         frames_total = B * world
@@ -348,6 +380,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "kernel_breakdown": breakdown,
+            "sub_records": subrec,
             "compute_tflops_whole_step": frames_total * args.steps * args.codecs * FLOP_PER_FRAME_CODEC / t_dev / 1e12,
         }
         print(json.dumps(line))
@@ -355,33 +388,61 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_corpus(args):
-    """Secondary workload (BASELINE.json configs[4]): an hour-scale synthetic corpus, wav -> hard codes (packed records) -> wav,
-    through nsc_b200.pipeline (cmrl.py:666-737 batched): host signals in, packed records + synthesized signals out, every step
-    (normalisation, filters, framing, LPC analysis, CQ pass, overlap-add, de-emphasis, bit packing, H2D/D2H) inside the timed
-    region.  Utterances are sharded across ranks."""
+def init_dist():
     import torch
     import torch.distributed as dist
-    from nsc_b200 import _lib, codec, pipeline
-    from nsc_b200.sharding import max_over_ranks
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
+        # the contract is ONE JSON line on stdout: keep NCCL's banner ("NCCL version ...") off it
         if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
             os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
-    lib = _lib.load()
-    cfg = codec.CodecConfig(precision=args.precision)
+    return world, rank, local, dev
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _timed(fn, steps, world, dev):
+    """steps calls of fn between a barrier + synchronize on both sides, CUDA events, max over ranks -> seconds"""
+    import torch
+    from nsc_b200.sharding import max_over_ranks
+    _barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    _barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+
+
+def measure_corpus(args, world, rank, dev, lib, steps, warmup, n_utt=None):
+    """BASELINE.json configs[4]: an hour-scale synthetic corpus, wav -> hard codes (packed records) -> wav, through
+    nsc_b200.pipeline (cmrl.py:666-737 batched): host signals in, packed records + synthesized signals out, every step
+    (normalisation, filters, framing, LPC analysis, CQ pass, overlap-add, de-emphasis, bit packing, H2D/D2H) inside the timed
+    region.  Utterances are sharded across ranks (weak scaling: n_utt per GPU)."""
+    import torch
+    from nsc_b200 import codec, pipeline
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=args.precision)
     cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
-    n_utt, T = args.utterances, int(args.utt_seconds * 16000)
+    n_utt = n_utt or args.utterances
+    T = int(args.utt_seconds * 16000)
     x_np, _ = synth_audio(64, seed=4321 + rank)
     base = np.tile(x_np.reshape(-1), -(-T * 8 // x_np.size))        # a few distinct utterances, tiled
     host = [torch.from_numpy(np.ascontiguousarray(base[(i % 8) * 4000:(i % 8) * 4000 + T])).pin_memory() for i in range(n_utt)]
     out_host = {}
+    frames = [0]
 
     def step():
         sigs = [h.to(dev, non_blocking=True) for h in host]
@@ -392,100 +453,190 @@ def run_corpus(args):
             if k not in out_host:
                 out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             out_host[k].copy_(t, non_blocking=True)
-        return sum(r['n_frames'] for r in res)
+        frames[0] = sum(r['n_frames'] for r in res)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        frames = step()
-    barrier()
-    l0 = lib.nsc_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    for _ in range(warmup):
         step()
-    e1.record()
-    barrier()
-    t = max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    l0 = lib.nsc_launch_count()
+    t = _timed(step, steps, world, dev)
     launches = lib.nsc_launch_count() - l0
+    audio_s = n_utt * world * args.utt_seconds
+    v = audio_s * steps / t
+    return {
+        "metric": "seconds of 16 kHz audio coded per second (x real-time), corpus wav -> packed hard codes -> wav, end to end",
+        "value": v, "unit": "x real-time", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32-equivalent convs (fp16 hi/lo on tensor cores); filters / LPC f64", "data": "synthetic",
+        "config": {"workload": f"corpus: {n_utt} utterances x {args.utt_seconds:g} s per GPU ({audio_s / 3600:.2f} h in total), "
+                               "cq2 codec, hard codes packed to 336-byte frame records, utterance filters + framing + overlap-add on the GPU",
+                   "frames_per_gpu_per_step": int(frames[0]), "conv_precision": args.precision,
+                   "l2_policy": "inputs larger than L2", "parallelism": f"dp{world} (utterances sharded by rank, no collective)"},
+        "e2e": {"value": v, "unit": "x real-time", "h2d_bytes_per_step": int(n_utt * T * 4 * world),
+                "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in out_host.values()) * world)},
+        "gpu_launches": int(launches), "record_kbps": 336 * 8 * 16000 / 480 / 1000.0}
+
+
+def run_corpus(args):
+    import torch.distributed as dist
+    from nsc_b200 import _lib
+    world, rank, local, dev = init_dist()
+    rec = measure_corpus(args, world, rank, dev, _lib.load(), args.steps, args.warmup)
     if rank == 0:
-        audio_s = n_utt * world * args.utt_seconds
-        v = audio_s * args.steps / t
-        print(json.dumps({
-            "metric": "seconds of 16 kHz audio coded per second (x real-time), corpus wav -> packed hard codes -> wav, end to end",
-            "value": v, "unit": "x real-time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32-equivalent convs (fp16 hi/lo on tensor cores); filters / LPC f64", "data": "synthetic",
-            "config": {"workload": f"corpus: {n_utt} utterances x {args.utt_seconds:g} s per GPU ({audio_s / 3600:.2f} h in total), "
-                                   "cq2 codec, hard codes packed to 336-byte frame records, utterance filters + framing + overlap-add on the GPU",
-                       "frames_per_gpu_per_step": int(frames), "conv_precision": args.precision,
-                       "l2_policy": "inputs larger than L2", "parallelism": f"dp{world} (utterances sharded by rank, no collective)"},
-            "e2e": {"value": v, "unit": "x real-time", "h2d_bytes_per_step": int(n_utt * T * 4 * world),
-                    "d2h_bytes_per_step": int(sum(o.numel() * o.element_size() for o in out_host.values()) * world)},
-            "gpu_launches": int(launches), "record_kbps": 336 * 8 * 16000 / 480 / 1000.0}))
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_train(args):
-    """Secondary workload (BASELINE.json configs[3]): full CQ training step -- forward keeping activations, backward of
-    every kernel, histogram + gradient all-reduce (NCCL), TF1 Adam -- `_finetuning_lpc`-shaped loss, 128 frames per GPU."""
+def measure_train(args, world, rank, dev, lib, steps, warmup, breakdown=True):
+    """BASELINE.json configs[3]: full CQ training step -- forward keeping activations, backward of every kernel, ONE flat
+    all-reduce (NCCL) of gradients + soft histograms, TF1 Adam -- `_finetuning_lpc`-shaped loss, train_batch frames per GPU."""
     import torch
-    import torch.distributed as dist
-    from nsc_b200 import _lib, codec, lpc_utilities as lu
-    from nsc_b200.sharding import max_over_ranks
+    from nsc_b200 import codec, lpc_utilities as lu
     from nsc_b200.training import CQTrainer
-    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
-    lib = _lib.load()
     B = args.train_batch
-    cfg = codec.CodecConfig(precision=args.precision)
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=args.precision)
     cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
     tr = CQTrainer.finetuning_lpc(cm, (60.0, 10.0, 10.0, 0.0), lr=2e-6)
     x_np, win_np = synth_audio(B, seed=4321 + rank)
     x = torch.from_numpy(x_np).to(dev) * 0.3
     lsf = lu.lpc_analysis_windows(torch.from_numpy(win_np).to(dev), 16, dtype=torch.float32)
+    out = {}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        tr.step(x, lsf)
-    barrier()
+    def step():
+        out['r'] = tr.step(x, lsf)
+
+    for _ in range(warmup):
+        step()
     l0 = lib.nsc_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = tr.step(x, lsf)
-    e1.record()
-    barrier()
-    t = max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
-    # the per-kernel breakdown is one more step: EVERY rank runs it (it contains the all-reduces), rank 0 reports
-    agg = kernel_breakdown(lib, lambda: tr.step(x, lsf))
-    barrier()
+    t = _timed(step, steps, world, dev)
+    launches = lib.nsc_launch_count() - l0
+    # the per-kernel breakdown is one more step: EVERY rank runs it (it contains the all-reduce), rank 0 reports
+    agg = kernel_breakdown(lib, step) if breakdown else None
+    _barrier(world)
+    fps = B * world * steps / t
+    rec = {"metric": "CQ training step throughput (frames/s; seconds of audio per second = x0.030)", "value": fps,
+           "unit": "frames/s", "x_real_time": fps * SEC_PER_FRAME, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": t / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32 weight gradients, epilogues and Adam; forward and data-gradient convs " + args.precision,
+           "data": "synthetic",
+           "config": {"workload": "train: 2-codec CQ cascade, finetuning_lpc loss (60/10/10), soft path, TF1 Adam, "
+                                  "one flat all-reduce of gradients + soft histograms", "frames_per_gpu": B, "parallelism": f"dp{world}"},
+           "gpu_launches": int(launches), "launches_per_step": int(launches) // max(1, steps),
+           "collectives_per_step": getattr(tr, 'collectives_per_step', None),
+           "loss_first_frame": float(out['r']['loss_vector'][0])}
+    if agg is not None:
+        bt = breakdown_table(agg)
+        rec["kernel_breakdown"] = bt
+        ar = [v for k, v in bt.items() if 'allreduce' in k or 'all_reduce' in k]
+        rec["allreduce_share"] = round(sum(v['share'] for v in ar), 4) if ar else (0.0 if world == 1 else None)
+    return rec
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from nsc_b200 import _lib
+    world, rank, local, dev = init_dist()
+    rec = measure_train(args, world, rank, dev, _lib.load(), args.steps, args.warmup)
     if rank == 0:
-        fps = B * world * args.steps / t
-        print(json.dumps({"metric": "CQ training step throughput (frames/s; seconds of audio per second = x0.030)", "value": fps,
-                          "unit": "frames/s", "x_real_time": fps * SEC_PER_FRAME, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32 weight gradients, epilogues and Adam; forward and data-gradient convs " + args.precision,
-                          "data": "synthetic",
-                          "config": {"workload": "train: 2-codec CQ cascade, finetuning_lpc loss (60/10/10), soft path, TF1 Adam, "
-                                                 "hist + flat-gradient all-reduce", "frames_per_gpu": B, "parallelism": f"dp{world}"},
-                          "gpu_launches": int(lib.nsc_launch_count() - l0), "loss_first_frame": float(out['loss_vector'][0]),
-                          "kernel_breakdown": breakdown_table(agg)}))
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_codec1(args, world, rank, dev, lib, cpu=True):
+    """BASELINE.json configs[0]: ONE neural codec (num_resnets = 1), no LPC, eval forward (hard codes) on synthetic 512-sample
+    frames, batch 128 -- the shape of the reference's only timing probe (cmrl.py:513-543, :584-611).  Device-resident and
+    end-to-end (pinned host frames in, codes + decoded audio back) x real-time, plus the oracle on the host cores."""
+    import torch
+    from nsc_b200 import codec
+    B = 128
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=args.precision)
+    gc = codec.NeuralCodec(cfg, device=dev, seed=5)
+    x_np, _ = synth_audio(B, seed=99 + rank)
+    x_np = (x_np / 33.461480140686035).astype(np.float32)          # pure-time-domain normalisation (constants.py:16)
+    xh = torch.from_numpy(x_np).pin_memory()
+    xd = xh.to(dev)
+    outs = {}
+
+    def step_dev():
+        outs['r'] = gc.computational_graph_end2end_quan_on(xd, False, 1.0)
+
+    def step_e2e():
+        r = gc.computational_graph_end2end_quan_on(xh.to(dev, non_blocking=True), False, 1.0)
+        for k in ('idx', 'out'):
+            if k not in outs:
+                outs[k] = torch.empty(r[k].shape, dtype=r[k].dtype).pin_memory()
+            outs[k].copy_(r[k], non_blocking=True)
+
+    n = 50
+    for _ in range(5):
+        step_dev(); step_e2e()
+    l0 = lib.nsc_launch_count()
+    t_dev = _timed(step_dev, n, world, dev)
+    launches = (lib.nsc_launch_count() - l0) // n
+    t_e2e = _timed(step_e2e, n, world, dev)
+    rec = {"workload": "codec1: one bottleneck codec ('9 9 100 20 1 2', stride 2, 32 bins), no LPC, hard codes, batch 128 per GPU "
+                       "(BASELINE.json configs[0])",
+           "value": B * world * n * SEC_PER_FRAME / t_dev, "unit": "x real-time", "ms_per_call": t_dev / n * 1e3,
+           "e2e": {"value": B * world * n * SEC_PER_FRAME / t_e2e, "unit": "x real-time", "ms_per_call": t_e2e / n * 1e3,
+                   "h2d_bytes_per_step": B * 512 * 4 * world, "d2h_bytes_per_step": (B * 256 + B * 512 * 4) * world},
+           "launches_per_call": int(launches), "steps": n}
+    if cpu and rank == 0 and world == 1:
+        from oracle import ref_codec
+        torch.set_num_threads(os.cpu_count())
+        oc = ref_codec.OracleCodec(ref_codec.OracleCodecCfg(), seed=5)
+        xt = torch.from_numpy(x_np)[:, :, None]
+        with torch.no_grad():
+            oc.forward(xt, False, 1.0)
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                oc.forward(xt, False, 1.0)
+            dt = (time.perf_counter() - t0) / reps
+        rec["cpu_baseline"] = {"value": B * SEC_PER_FRAME / dt, "unit": "x real-time", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"the same 128-frame batch, {reps} calls of the restated reference (torch-CPU oracle), {dt * 1e3:.0f} ms per call"}
+    return rec
+
+
+def measure_cq_sweep(args, world, rank, dev, lib):
+    """BASELINE.json configs[2]: CQ scaled towards 24 kbps -- more cascaded codecs and bins -- batch-size sweep, encode+decode,
+    device-resident and end-to-end."""
+    import torch
+    from nsc_b200 import codec, lpc_utilities as lu
+    rows = []
+    for n_codecs, bins in ((3, 32), (4, 64)):
+        cfg = codec.CodecConfig(resnet_type='bottleneck', precision=args.precision, num_bins=bins)
+        cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5 + i) for i in range(n_codecs)], res_scalar=1.0)
+        for B in (128, 2072, 8288):
+            x_np, win_np = synth_audio(min(B, 2072), seed=77 + rank)
+            reps = -(-B // x_np.shape[0])
+            xh = torch.from_numpy(np.tile(x_np, (reps, 1))[:B]).pin_memory()
+            wh = torch.from_numpy(np.tile(win_np, (reps, 1))[:B]).pin_memory()
+            xd, wd = xh.to(dev), wh.to(dev)
+            keep = {}
+
+            def step_dev():
+                keep['r'] = cm.feedforward_lpc(xd, lu.lpc_analysis_windows(wd, 16, dtype=torch.float32), False, 1.0)
+
+            def step_e2e():
+                a, b = xh.to(dev, non_blocking=True), wh.to(dev, non_blocking=True)
+                r = cm.feedforward_lpc(a, lu.lpc_analysis_windows(b, 16, dtype=torch.float32), False, 1.0)
+                outs = [('lsf_idx', r['lsf_idx']), ('syn', r['synthesized'])] + [('idx%d' % k, t) for k, t in enumerate(r['idx'])]
+                for k, t in outs:
+                    kk = (k, B)
+                    if kk not in keep:
+                        keep[kk] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                    keep[kk].copy_(t, non_blocking=True)
+
+            n = 20 if B <= 2072 else 5
+            for _ in range(3):
+                step_dev(); step_e2e()
+            t_dev = _timed(step_dev, n, world, dev)
+            t_e2e = _timed(step_e2e, n, world, dev)
+            rows.append({"codecs": n_codecs, "bins": bins, "frames_per_gpu": B, "value": B * world * n * SEC_PER_FRAME / t_dev,
+                         "e2e": B * world * n * SEC_PER_FRAME / t_e2e, "unit": "x real-time", "ms_per_call": t_dev / n * 1e3})
+    return {"workload": "cq3 (3 codecs x 32 bins) and cq4x64 (4 codecs x 64 bins): LPC + LSF codebook + cascade + synthesis, hard codes, "
+                        "batch sweep (BASELINE.json configs[2])", "rows": rows}
 
 
 def main():
@@ -505,6 +656,8 @@ def main():
     ap.add_argument('--utterances', type=int, default=360, help='corpus workload: utterances per GPU')
     ap.add_argument('--utt-seconds', type=float, default=10.0, help='corpus workload: seconds per utterance')
     ap.add_argument('--train-batch', type=int, default=128, help='frames per GPU per training step')
+    ap.add_argument('--no-sub-records', dest='sub_records', action='store_false',
+                    help="skip the bounded sub-records (codec1 batch 128, scaled CQ sweep, training step, 1-hour corpus) of the default run")
     ap.add_argument('--precision', default='tc_f16x3', choices=['fp32', 'tc_f16x3', 'tc_f16'],
                     help="conv arithmetic: fp32 FFMA, tcgen05 fp16 hi/lo split (fp32-class, default), tcgen05 fp16 (reduced)")
     args = ap.parse_args()

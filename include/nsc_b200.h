@@ -59,6 +59,14 @@ enum { NSC_ACT_NONE = 0, NSC_ACT_TANH = 1, NSC_ACT_LRELU = 2 };
 int nsc_conv1d(const float* x, const float* w, const float* b, float* y, int64_t B, int32_t Lin, int32_t Cin,
                int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation, void* stream);
 
+/* PRECISION MODES of the tensor-core conv path (nsc_codec_cfg.precision, `precision` arguments):
+ *   1  fp16 hi/lo split: every activation and weight is x = hi + lo (two fp16 values, 22 mantissa bits), products hi*wh + lo*wh +
+ *      hi*wl accumulate in fp32 in TMEM.  fp32-CLASS: measured per-frame error of the whole encoder 3-5e-6 of the frame's code peak
+ *      for input levels 1e-4 ... 1 (the same as a float32 evaluation) and within the 1e-4 parity bar for |x| <= 64 -- the SUPPORTED
+ *      INPUT DOMAIN (the reference feeds unit-variance or 1/33.46-scaled frames, constants.py:16).  Beyond it (|x| ~ 1e3) sums that
+ *      cancel over three decades expose the 22-bit mantissa: ~4x the float32 error (tests/test_gpu_parity_depth.py).
+ *   2  plain fp16 inputs: REDUCED precision (~1e-3), stated separately, never the headline.
+ *   0  fp32 FFMA on the CUDA cores. */
 /* conv1d on the tcgen05 tensor cores ("plane engine", the codec's conv path) with the fused epilogue of the codec's
  * layers, channels-last fp32 tensors at the edge:
  *   y = post_act( act(conv1d(x) + b) (+ res) ), optionally sub-pixel shuffled: y[b, shuffle*l + r, c] = t[b, l, shuffle*c + r]
@@ -95,6 +103,22 @@ int nsc_bottleneck_block(const float* x, const float* params, float* y, int64_t 
                          int32_t wide, int32_t narrow, int32_t k_plain, int32_t k_dilated, int32_t dilation,
                          int32_t is_last_flat, int32_t gated, void* workspace, int64_t workspace_bytes,
                          void* stream);
+
+/* the_bottleneck on the tcgen05 tensor cores (the codec's path): the block's three convs run as ONE persistent launch whose CTAs take
+ * three roles (conv 1 / conv 2 / conv 3 + residual) and pass frames through L2-resident rings, so the 20-channel intermediates never
+ * reach HBM (nn_core_operator.py:57-79).  x (B, L, wide) channels-last -> y (B, L, wide); params as nsc_bottleneck_block.
+ *   Covers narrow = 20, k = 9, dilation 1 or 2, 32 < wide <= 128, L a multiple of 128; precision as nsc_conv1d_tc.
+ *   *fused (may be NULL) reports whether the fused kernel ran (it needs an even number of 128/256-position tiles; otherwise the same
+ *   three tensor-core kernels run one launch each; *fused == -1 on entry forces that form -- the two are bit-identical). */
+int64_t nsc_bottleneck_block_tc_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t narrow, int32_t precision);
+int nsc_bottleneck_block_tc(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t wide, int32_t narrow,
+                            int32_t k_plain, int32_t k_dilated, int32_t dilation, int32_t is_last_flat, int32_t precision,
+                            int32_t* fused, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Tuning aid: per-CTA counters of the most recent fused block launch, recorded when the process runs with NSC_BLOCK_STATS=1
+ * (8 words per CTA: role, epilogue-loop cycles, cycles waited for a free ring slot, cycles waited for a ready frame, work units,
+ * cycles the storer waited for its own stores, 2 spare).  Synchronises the device.  Returns the number of CTAs copied. */
+int nsc_debug_block_stats(unsigned long long* out_host, int32_t max_ctas);
 
 /* ------------------------------------------------------------------------------------------------
  * scalar_softmax_quantization (nn_core_operator.py:140-164) + quan_loss (loss_terms_and_measures.py:257-259)

@@ -4,7 +4,8 @@ It is DATA the hot path is parameterised by: 16 
 of 16 values each -- NOT monotone over the whole table.  Stored as the little-endian float32 image
 (base64) of the reference's decimal literals so the values are bit-identical to what
 ``tf.Variable(lpc_coeff_lsf_bins, dtype=tf.float32)`` holds (cmrl.py:781, nscm.py:997).
-tests/test_constants.py re-derives it from /root/reference when that tree is present.
+tests/test_oracle_pins.py (test_lsf_codebook_matches_reference_constants) re-derives it from /root/reference/constants.py when
+that tree is present.
 """
 import base64
 

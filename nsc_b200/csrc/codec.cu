@@ -109,7 +109,7 @@ struct PlaneCascade {
       const PlaneCodecPlan pl = make_plane_plan(cfgs[i]);
       const int64_t a = plane_codec_act_bytes(pl, Bc);
       if (a > act) act = a;
-      w += align_up(pl.wpack_bytes, 1024);
+      w += align_up(pl.wpack_bytes, 1024) + plane_codec_flag_bytes(pl, Bc);
     }
     return act * nr + w + 2 * align_up(Bc * (kFrameLen / 2) * (int64_t)sizeof(float), 1024) + 2048;
   }
@@ -136,6 +136,9 @@ struct PlaneCascade {
     for (int i = 0; i < n; ++i) {
       plane_bind(plans[i], lays[i], params[i], act0 + region_bytes * region[i], Bc, p);
       p += align_up(plans[i].wpack_bytes, 1024);
+      plans[i].flags = reinterpret_cast<uint32_t*>(p);
+      plans[i].flag_frames = Bc;
+      p += plane_codec_flag_bytes(plans[i], Bc);
       NSC_TRY(plane_codec_pack(plans[i], st));
     }
     fcode = reinterpret_cast<float*>(p);

@@ -299,8 +299,8 @@ __global__ void depthwise_kernel(const float* __restrict__ x, const float* __res
 }
 
 // y = a * (x - b*z)  (cascade input, cmrl.py:529-531 / :822-823), or a * x when z is null
-__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, const float* __restrict__ z,
-                             float b, int64_t n) {
+// y and z may be the SAME buffer (train.cu accumulates in place): neither is declared __restrict__
+__global__ void axpby_kernel(float* y, const float* __restrict__ x, float a, const float* z, float b, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = z ? a * (x[i] - z[i] * b) : a * x[i];
 }

@@ -7,8 +7,13 @@
 //   8 zero rows (SAME padding and tap halos come from the zero rows); 16-byte chunk c of row r sits at chunk
 //   position c ^ (r & 7) (r counted from the start of the slab).
 //   planes = 2: value = hi + lo, both fp16 (fp32-class products with 3 MMAs: hi*hi + hi*lo + lo*hi);  planes = 1: hi only.
-//   C <= 32 channels ("packed"): one slab, hi in bytes 0-63 and lo in bytes 64-127 of the same row.
-//   C  > 32: plane-major, ceil(C/64) slabs per plane.
+//   "packed" (narrow tensors): one slab, one 128-byte row per position.
+//     planes = 2, C <= 20: the row's 64 halves form ONE K axis on which x * w = hi*wh + lo*wh + hi*wl is a single MMA chain of 4 K
+//       steps (instead of three products of 2 K steps each): 16-byte chunks
+//         0,1: hi[0:16]   2,3: lo[0:16]   4,5: hi[0:16]   6: hi[16:20] | lo[16:20]   7: hi[16:20] | 0
+//       against weight rows   wh[0:16]   wh[0:16]   wl[0:16]   wh[16:20] | wh[16:20]   wl[16:20] | 0   (plane_pack_kernel).
+//     planes = 1, C <= 32: hi in bytes 0-63.
+//   otherwise: plane-major, ceil(C/64) slabs per plane.
 //   deint: two sub-images by position parity (position p -> sub-image p & 1, row p >> 1) -- the input layout of a
 //   stride-2 conv, for which every tap is again a pure row shift.
 #pragma once
@@ -24,7 +29,13 @@ struct PlaneTensor {
   int planes = 1;
   int packed = 0;
   int deint = 0;
+  int ring = 0;              // > 0 (a power of two): the tensor is a ring of `ring` frame slots, frame f lives in slot f & (ring - 1)
 };
+
+// byte offset of frame f's image
+__host__ __device__ inline int64_t pt_frame_off(const PlaneTensor& t, int64_t f) {
+  return (t.ring > 0 ? (f & (int64_t)(t.ring - 1)) : f) * t.frame_bytes;
+}
 
 __host__ __device__ inline int pt_slab_bytes(const PlaneTensor& t) { return (t.rows + 16) * 128; }
 __host__ __device__ inline int pt_slab_index(const PlaneTensor& t, int sub, int plane, int s) {
@@ -37,7 +48,7 @@ inline PlaneTensor make_plane_tensor(void* base, int L, int C, int planes, int d
   const int cpad = (C + 15) & ~15;
   t.base = static_cast<uint8_t*>(base);
   t.rows = deint ? L / 2 : L;
-  t.packed = cpad <= 32 ? 1 : 0;
+  t.packed = (planes == 2 ? C <= 20 : cpad <= 32) ? 1 : 0;
   t.spp = t.packed ? 1 : (cpad + 63) / 64;
   t.planes = planes;
   t.deint = deint;
@@ -87,6 +98,20 @@ int plane_pack_weights(const PlaneConv& c, cudaStream_t st);
 int plane_launch(const PlaneConv& c, cudaStream_t st);
 // launch plan of a layer (what plane_launch would do), see nsc_conv1d_tc_plan_info
 bool plane_plan_info(const PlaneConv& c, int64_t* out12);
+
+// ---- fused bottleneck block (nn_core_operator.py:57-79): ONE persistent launch runs the block's three convs as three CTA roles
+// that stream frames to each other through ring buffers of a few dozen frames (L2-resident: the 20-channel intermediates never
+// reach HBM, the block's input is read from HBM once -- the residual read of the third conv hits L2 -- and its output written once).
+struct PlaneBlock {
+  PlaneConv c1, c2, c3;          // wide -> narrow (PK_T), narrow -> narrow (PK_T grouped), narrow -> wide + residual (PK_X staged, CTA pairs)
+  uint32_t* flags = nullptr;     // plane_block_flag_words(B) words, zeroed before the launch
+  int ring = 0;                  // frame slots of the two rings (c1.out / c2.in and c2.out / c3.in carry ring = this)
+};
+bool plane_block_supported(const PlaneBlock& b);
+bool plane_block_default_on();   // NSC_BLOCK_FUSED=1: the codec program launches its blocks fused (default: one launch per conv)
+int64_t plane_block_flag_words(int64_t B);
+int plane_block_ring_frames();
+int plane_block_launch(const PlaneBlock& b, cudaStream_t st);
 
 // fp32 <-> plane images (API edges and tests)
 int plane_from_f32(const float* x, int x_cl, int64_t B, int L, int C, const PlaneTensor& t, cudaStream_t st);

@@ -51,6 +51,10 @@ struct PlaneCodecPlan {
   std::vector<Io> enc_io, dec_io;
   std::vector<int64_t> w_off;             // packed-weight offset of every layer (enc then dec)
   int64_t wpack_bytes = 0;
+  std::vector<int> enc_block, dec_block;  // per layer: 1 = first conv of a bottleneck block whose three convs can run as ONE fused launch
+  uint32_t* flags = nullptr;              // frame flags of the fused blocks (plane_block_flag_words(flag_frames) words per fused block)
+  int64_t flag_frames = 0;                // frames per pass the flag words were sized for
+  int n_fused = 0;
 };
 
 // Lays the codec out as plane layers.  Tensors carry geometry only (base = nullptr) until plane_bind() attaches a workspace.
@@ -103,6 +107,9 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
         add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
         add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, -1, RES_ADD_BCAST, post, 1);
       } else {
+        (&v == &pl.enc ? pl.enc_block : pl.dec_block).resize(v.size() + 1, 0);
+        (&v == &pl.enc ? pl.enc_block : pl.dec_block)[v.size()] = 1;
+        ++pl.n_fused;
         add(v, vl, PK_T, Ls, Cw, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, cur, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
         add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
         add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, cur, RES_ADD, post, 1);
@@ -139,7 +146,14 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   size_w(pl.enc);
   size_w(pl.dec);
   if (pl.wpack_bytes == 0) pl.wpack_bytes = woff;
+  pl.enc_block.resize(pl.enc.size(), 0);
+  pl.dec_block.resize(pl.dec.size(), 0);
   return pl;
+}
+
+// frame flags of the fused blocks of one codec pass
+int64_t plane_codec_flag_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
+  return align_up((int64_t)pl.n_fused * plane_block_flag_words(Bc) * (int64_t)sizeof(uint32_t), 1024);
 }
 
 int64_t plane_codec_act_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
@@ -182,10 +196,38 @@ int plane_codec_pack(PlaneCodecPlan& pl, cudaStream_t st) {
   return NSC_OK;
 }
 
+// Runs layers [i, i + 3) as one fused block launch when the fused kernel covers them; `*fused_no` counts the codec's fused blocks
+// (each has its own flag words, cleared once per pass by plane_clear_flags).
+bool plane_try_block(PlaneCodecPlan& pl, std::vector<PlaneConv>& v, const std::vector<int>& is_block, size_t i, int64_t nb, int* fused_no,
+                     cudaStream_t st, int* rc) {
+  if (!plane_block_default_on() || !is_block[i] || i + 2 >= v.size() || pl.flags == nullptr) return false;
+  const int no = (*fused_no)++;
+  PlaneBlock b;
+  b.c1 = v[i]; b.c2 = v[i + 1]; b.c3 = v[i + 2];
+  b.c1.B = b.c2.B = b.c3.B = nb;
+  int ring = plane_block_ring_frames();
+  while (ring > 2 && ring > nb) ring /= 2;
+  b.ring = ring;
+  b.flags = pl.flags + (int64_t)no * plane_block_flag_words(pl.flag_frames);
+  if (!plane_block_supported(b)) return false;
+  *rc = plane_block_launch(b, st);
+  return true;
+}
+
+int plane_clear_flags(PlaneCodecPlan& pl, cudaStream_t st) {
+  if (!plane_block_default_on() || pl.flags == nullptr || pl.n_fused == 0) return NSC_OK;
+  NSC_CUDA_OK(cudaMemsetAsync(pl.flags, 0, (size_t)pl.n_fused * plane_block_flag_words(pl.flag_frames) * sizeof(uint32_t), st));
+  return NSC_OK;
+}
+
 // encoder: x (nb, 512) -> fcode (nb, Lc);  decoder: code (nb, Lc) -> out (nb, 512)
 int plane_run_encoder(PlaneCodecPlan& pl, const float* x, int64_t nb, float* fcode, cudaStream_t st) {
-  for (auto& pc : pl.enc) {
-    PlaneConv t = pc;
+  NSC_TRY(plane_clear_flags(pl, st));
+  int fused_no = 0;
+  for (size_t i = 0; i < pl.enc.size(); ++i) {
+    int rc = NSC_OK;
+    if (plane_try_block(pl, pl.enc, pl.enc_block, i, nb, &fused_no, st, &rc)) { NSC_TRY(rc); i += 2; continue; }
+    PlaneConv t = pl.enc[i];
     t.B = nb;
     if (t.Cin == 1) t.xvec = x;
     if (t.Cout == 1) t.yvec = fcode;
@@ -195,8 +237,12 @@ int plane_run_encoder(PlaneCodecPlan& pl, const float* x, int64_t nb, float* fco
 }
 
 int plane_run_decoder(PlaneCodecPlan& pl, const float* code, int64_t nb, float* out, cudaStream_t st) {
-  for (auto& pc : pl.dec) {
-    PlaneConv t = pc;
+  NSC_TRY(plane_clear_flags(pl, st));
+  int fused_no = 0;
+  for (size_t i = 0; i < pl.dec.size(); ++i) {
+    int rc = NSC_OK;
+    if (plane_try_block(pl, pl.dec, pl.dec_block, i, nb, &fused_no, st, &rc)) { NSC_TRY(rc); i += 2; continue; }
+    PlaneConv t = pl.dec[i];
     t.B = nb;
     if (t.Cin == 1) t.xvec = code;
     if (t.res_mode == RES_ADD_BCAST) t.resvec = code;

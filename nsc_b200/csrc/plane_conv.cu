@@ -63,8 +63,18 @@ __device__ __forceinline__ void pt_store8(const PlaneTensor& t, uint8_t* img, in
   const int64_t sb = pt_slab_bytes(t);
   if (t.packed) {
     uint8_t* r = img + sub * sb + (int64_t)row * 128;
-    *reinterpret_cast<uint4*>(r + (((uint32_t)g ^ sw) << 4)) = hi;
-    if (t.planes == 2) *reinterpret_cast<uint4*>(r + (((uint32_t)(g + 4) ^ sw) << 4)) = lo;
+    if (t.planes == 2) {   // K-concatenated row (plane.cuh)
+      if (g < 2) {
+        *reinterpret_cast<uint4*>(r + (((uint32_t)g ^ sw) << 4)) = hi;
+        *reinterpret_cast<uint4*>(r + (((uint32_t)(g + 2) ^ sw) << 4)) = lo;
+        *reinterpret_cast<uint4*>(r + (((uint32_t)(g + 4) ^ sw) << 4)) = hi;
+      } else if (g == 2) {
+        *reinterpret_cast<uint4*>(r + ((6u ^ sw) << 4)) = make_uint4(hi.x, hi.y, lo.x, lo.y);
+        *reinterpret_cast<uint4*>(r + ((7u ^ sw) << 4)) = make_uint4(hi.x, hi.y, 0u, 0u);
+      }                    // g == 3: channels 24-31 are not represented (C <= 20)
+    } else {
+      *reinterpret_cast<uint4*>(r + (((uint32_t)g ^ sw) << 4)) = hi;
+    }
   } else {
     uint8_t* r = img + (int64_t)pt_slab_index(t, sub, 0, g >> 3) * sb + (int64_t)row * 128 + ((((uint32_t)g & 7u) ^ sw) << 4);
     *reinterpret_cast<uint4*>(r) = hi;
@@ -80,8 +90,20 @@ __device__ __forceinline__ void pt_load8(const PlaneTensor& t, const uint8_t* im
   uint4 hi, lo = make_uint4(0, 0, 0, 0);
   if (t.packed) {
     const uint8_t* r = img + sub * sb + (int64_t)row * 128;
-    hi = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)g ^ sw) << 4)));
-    if (t.planes == 2) lo = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)(g + 4) ^ sw) << 4)));
+    if (t.planes == 2) {
+      if (g < 2) {
+        hi = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)g ^ sw) << 4)));
+        lo = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)(g + 2) ^ sw) << 4)));
+      } else if (g == 2) {
+        const uint4 c6 = __ldg(reinterpret_cast<const uint4*>(r + ((6u ^ sw) << 4)));
+        hi = make_uint4(c6.x, c6.y, 0u, 0u);
+        lo = make_uint4(c6.z, c6.w, 0u, 0u);
+      } else {
+        hi = make_uint4(0, 0, 0, 0);
+      }
+    } else {
+      hi = __ldg(reinterpret_cast<const uint4*>(r + (((uint32_t)g ^ sw) << 4)));
+    }
   } else {
     const uint8_t* r = img + (int64_t)pt_slab_index(t, sub, 0, g >> 3) * sb + (int64_t)row * 128 + ((((uint32_t)g & 7u) ^ sw) << 4);
     hi = __ldg(reinterpret_cast<const uint4*>(r));
@@ -97,7 +119,9 @@ __device__ __forceinline__ void pt_load8(const PlaneTensor& t, const uint8_t* im
 }
 
 __host__ __device__ inline int pt_chunks_per_row(const PlaneTensor& t) { return t.packed ? 4 : t.spp * 8; }
-inline double pt_payload_bytes(const PlaneTensor& t) { return (double)pt_n_slabs(t) * t.rows * 128.0 * ((t.packed && t.planes == 1) ? 0.5 : 1.0); }
+// ALGORITHMIC bytes of an activation tensor of C real channels over `positions` positions: 2 bytes per channel and plane (the
+// padding channels and zero rows of the image are not payload)
+inline double pt_real_bytes(int positions, int C, int planes) { return (double)positions * C * 2.0 * planes; }
 
 // ------------------------------------------------------------------------------------------------
 // fp32 <-> planes
@@ -170,6 +194,16 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
   return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
 }
 
+// K slot k (0..63) of a weight row that meets a packed input row: which input channel and which weight plane it holds
+// (planes = 2: the K-concatenated layout of plane.cuh; planes = 1: channels 0..31 of the hi plane)
+__device__ __forceinline__ void kcat_slot(int planes, int k, int* ci, int* lo_plane) {
+  if (planes != 2) { *ci = k & 31; *lo_plane = k >> 5; return; }
+  const int c = k >> 3, e = k & 7;
+  if (c < 6) { *ci = (c & 1) * 8 + e; *lo_plane = c >= 4 ? 1 : 0; }
+  else if (c == 6) { *ci = 16 + (e & 3); *lo_plane = 0; }
+  else { *ci = e < 4 ? 16 + e : -1; *lo_plane = 1; }
+}
+
 __global__ void plane_pack_kernel(PackArgs a) {
   const int64_t total = (int64_t)a.n_units * a.rows * 64;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -186,11 +220,11 @@ __global__ void plane_pack_kernel(PackArgs a) {
         t = tt < 0 ? a.K : tt;
       }
       if (t >= a.K) co = -1;
-      if (a.in_packed) { ci = k & 31; lo_plane = k >> 5; }
+      if (a.in_packed) kcat_slot(a.planes, k, &ci, &lo_plane);
       else { ci = (u % a.in_spp) * 64 + k; lo_plane = u / a.in_spp; }
     } else if (a.kind == PK_X) {
       co = n;
-      if (a.in_packed) { t = u; ci = k & 31; lo_plane = k >> 5; }
+      if (a.in_packed) { t = u; kcat_slot(a.planes, k, &ci, &lo_plane); }
       else {
         // u = ((slab * K) + tap) * planes + plane
         lo_plane = u % a.planes;
@@ -245,6 +279,48 @@ __device__ __forceinline__ void issue_n(int nks, uint32_t d, uint32_t a_lo, uint
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// frame flags of the fused block kernel: CTAs of different roles hand frames to each other through global-memory rings.
+// A producer's bulk stores are complete (cp.async.bulk.wait_group) before it publishes; a consumer orders its bulk loads after
+// the acquire with a proxy fence.  A flag that stays unset for seconds means a broken launch: trap instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long flag_wait(const uint32_t* p, uint32_t target) {
+  long long waited = 0;
+  if (ld_acquire_gpu(p) < target) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(p) < target) {
+      __nanosleep(64);
+      if (clock64() - t0 > (1ll << 33)) __trap();
+    }
+    waited = clock64() - t0;
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  return waited;
+}
+// optional per-CTA counters of the fused block kernel (NSC_BLOCK_STATS=1, nsc_debug_block_stats): 8 words per CTA --
+// role, epilogue loop cycles, cycles the storer waited for a free ring slot, cycles the loader waited for a ready frame,
+// work units, cycles the storer waited for its own stores, cycles the MMA issuer waited for its input stage, ... for a free accumulator
+constexpr int kStatWords = 8, kStatCtas = 160;
+__device__ unsigned long long g_block_stats[kStatCtas * kStatWords];
+__device__ __forceinline__ void stat_add(unsigned long long* stats, int word, long long v) {
+  if (stats != nullptr && blockIdx.x < kStatCtas) atomicAdd(stats + blockIdx.x * kStatWords + word, (unsigned long long)v);
+}
+__device__ __forceinline__ void flag_signal(uint32_t* p) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+}
+// "I have read my part of the frame out of the ring": nothing of this thread's has to become visible, the bump only has to stay
+// behind the mbarrier wait (an acquire) that observed the bulk loads' completion -- no fence on the issuing thread's path
+__device__ __forceinline__ void flag_bump(uint32_t* p) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+}
+
 // ================================================================================================
 // PK_T
 // ================================================================================================
@@ -257,6 +333,11 @@ struct TParams {
   int stage_bytes;           // one input slab of one tile: 128 rows, + 8 halo rows each side in the grouped form
   int L, dil, act, na;
   int64_t B;
+  // role-relative CTA numbering (a plain launch: cta0 = 0, ncta = gridDim.x) and the frame flags of ring tensors (fused block)
+  int cta0, ncta;
+  uint32_t *in_ready, *in_free, *out_ready, *out_free;
+  int out_free_target;       // arrivals that free a frame slot of `out`: its consumer's CTAs per frame
+  unsigned long long* stats; // optional counters (fused block kernel)
 };
 
 // spill slots: the quarters of the current and the previous tile; the k55 head has no per-tile barrier after its reads (no staged
@@ -354,8 +435,9 @@ __device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc
 }
 
 template <int C, int TAPS, int GROUPS>
-__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
+__device__ __forceinline__ void t_body(const TParams& p) {
   using S = TShape<C, TAPS>;
+  const int rank = (int)blockIdx.x - p.cta0, nranks = p.ncta;
   constexpr int kTE = (C == 1) ? 1 : TAPS;              // tap slots of the shuffle tap sum (the head has its own phase 1)
   const uint32_t kAStage = (uint32_t)p.stage_bytes;
   constexpr int kMaxM = S::kMaxM, kRF = S::kRowFloats, kEpi = S::kEpiWarps;
@@ -363,9 +445,11 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t w_full, a_full[8], a_empty[8], acc_full[2], acc_empty[2];
+  __shared__ uint64_t so_ready[2], so_free[2];      // ring mode: output windows handed to / returned by the storer warp (by tile parity)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool ring_out = (C != 1) && p.out_ready != nullptr;   // fused block: a dedicated warp stores and publishes (the CTA has spare warps)
   const uint32_t wslab_bytes = (uint32_t)p.N * 128u;
   uint8_t* sW = smem;
   uint8_t* sA = sW + (uint32_t)p.n_wslab * wslab_bytes;
@@ -383,6 +467,7 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
     mbar_init(&w_full, 1);
     for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpi); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&so_ready[i], kEpi); mbar_init(&so_free[i], 1); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   if (warp == kEpi) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -418,8 +503,9 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
     float* const sP_l = sP + (lane - (32 - m)) * kRF + coff;
     const int out_planes = p.out.planes;
     uint32_t it = 0, tb = 0, tbp = kTSlots - 4;       // tb: first spill slot of this tile's quarters (0, 4[, 8] in turn)
-    for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
-      uint8_t* const orow = (C == 1) ? nullptr : p.out.base + f * p.out.frame_bytes + 8 * 128;   // position 0 of the packed image
+    const long long t_begin = clock64();
+    for (int64_t f = rank; f < p.B; f += nranks) {
+      uint8_t* const orow = (C == 1) ? nullptr : p.out.base + pt_frame_off(p.out, f) + 8 * 128;   // position 0 of the packed image
       const int ring0 = (int)((it * 128u) & (kORing - 1));      // ring row of this frame's position 0 (frames are whole tiles)
       int done_rows = 0;                                        // positions of this frame already handed to the copy engine
       float* const yrow = (C == 1) ? p.yvec + f * p.L : nullptr;
@@ -437,11 +523,18 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
           // bulk-stores a whole window of finished rows per tile.
           uint8_t* rp = sO + (uint32_t)((ring0 + row) & (kORing - 1)) * 128u;
           const uint32_t sw = (uint32_t)row & 7u;       // (row + 8) & 7
-          *reinterpret_cast<uint4*>(rp + (((uint32_t)grp ^ sw) << 4)) = hi;
-          if (out_planes == 2) *reinterpret_cast<uint4*>(rp + (((uint32_t)(grp + 4) ^ sw) << 4)) = lo;
-          if (grp == 2) {                               // channels 24-31 of both halves: K padding the consumer reads
-            *reinterpret_cast<uint4*>(rp + ((3u ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
-            if (out_planes == 2) *reinterpret_cast<uint4*>(rp + ((7u ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+          if (out_planes == 2) {                        // K-concatenated row (plane.cuh)
+            if (grp < 2) {
+              *reinterpret_cast<uint4*>(rp + (((uint32_t)grp ^ sw) << 4)) = hi;
+              *reinterpret_cast<uint4*>(rp + (((uint32_t)(grp + 2) ^ sw) << 4)) = lo;
+              *reinterpret_cast<uint4*>(rp + (((uint32_t)(grp + 4) ^ sw) << 4)) = hi;
+            } else {
+              *reinterpret_cast<uint4*>(rp + ((6u ^ sw) << 4)) = make_uint4(hi.x, hi.y, lo.x, lo.y);
+              *reinterpret_cast<uint4*>(rp + ((7u ^ sw) << 4)) = make_uint4(hi.x, hi.y, 0u, 0u);
+            }
+          } else {
+            *reinterpret_cast<uint4*>(rp + (((uint32_t)grp ^ sw) << 4)) = hi;
+            if (grp == 2) *reinterpret_cast<uint4*>(rp + ((3u ^ sw) << 4)) = make_uint4(0, 0, 0, 0);   // channels 24-31: K padding the consumer reads
           }
         }
       };
@@ -466,6 +559,8 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc_i]);   // TMEM slot free: the next tile's MMAs run under phase 2
+        // ring mode: this tile's rows overwrite the staging window of two tiles ago -- the storer warp has seen it leave shared memory
+        if (ring_out) mbar_wait_relaxed(&so_free[it & 1u], ((it >> 1) & 1u) ^ 1u);
 
         const int fqi = j * 4 + q;
         const bool lastq = fqi == nq - 1;
@@ -507,29 +602,39 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
         }
         if constexpr (C != 1) {
           fence_async_smem();                                      // generic-proxy row writes -> visible to the bulk store
-          asm volatile("bar.sync 2, %0;" :: "n"(kEpi * 32) : "memory");
-          if (warp == 0 && lane == 0) {
-            // rows final after this tile: everything up to 8 rows before its end (those wait for the next tile's down-spill)
-            const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
-            int r0 = done_rows;
-            while (r0 < upto) {                                    // at most two pieces (ring wrap)
-              const int ring_r = (ring0 + r0) & (kORing - 1);
-              int n = upto - r0;
-              if (ring_r + n > kORing) n = kORing - ring_r;
-              bulk_s2g(orow + (int64_t)r0 * 128, sO + (uint32_t)ring_r * 128u, (uint32_t)n * 128u);
-              r0 += n;
+          if (ring_out) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&so_ready[it & 1u]);         // the storer warp takes it from here
+          } else {
+            asm volatile("bar.sync 2, %0;" :: "n"(kEpi * 32) : "memory");
+            if (warp == 0 && lane == 0) {
+              // rows final after this tile: everything up to 8 rows before its end (those wait for the next tile's down-spill)
+              const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
+              int r0 = done_rows;
+              while (r0 < upto) {                                    // at most two pieces (ring wrap)
+                const int ring_r = (ring0 + r0) & (kORing - 1);
+                int n = upto - r0;
+                if (ring_r + n > kORing) n = kORing - ring_r;
+                bulk_s2g(orow + (int64_t)r0 * 128, sO + (uint32_t)ring_r * 128u, (uint32_t)n * 128u);
+                r0 += n;
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the window before this one has left shared memory
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the window before this one has left shared memory
+            done_rows = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
           }
-          done_rows = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
         }
         tbp = tb;
         tb = tb == (uint32_t)(kTSlots - 4) ? 0u : tb + 4u;
       }
     }
     if constexpr (C != 1) {
-      if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (warp == 0 && lane == 0 && !ring_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0 && p.stats != nullptr) {
+      stat_add(p.stats, 0, p.in_ready != nullptr ? 2 : 1);
+      stat_add(p.stats, 1, clock64() - t_begin);
+      stat_add(p.stats, 4, (long long)it);
     }
   } else if (warp == kEpi) {
     // =========================== MMA issuer ===========================
@@ -543,15 +648,19 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
       const int spp = p.in.spp, planes = p.in.planes;
       const bool packed = p.in.packed != 0;
       uint32_t it = 0, slot = 0, sph = 0;
-      for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
+      for (int64_t f = rank; f < p.B; f += nranks) {
         for (int j = 0; j < T; ++j, ++it) {
           const uint32_t acc_i = it & 1u;
+          long long tw = p.stats != nullptr ? clock64() : 0;
           mbar_wait(&acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);
+          if (p.stats != nullptr) stat_add(p.stats, 7, clock64() - tw);
           tc_fence_after();
           const uint32_t d = tmem + acc_i * (uint32_t)p.N;
           uint32_t accum = 0;
           for (int s = 0; s < nst; ++s) {
+            tw = p.stats != nullptr ? clock64() : 0;
             mbar_wait(&a_full[slot], sph);
+            if (p.stats != nullptr) stat_add(p.stats, 6, clock64() - tw);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + slot * (uint32_t)(kAStage >> 4);
             if constexpr (GROUPS > 1) {
@@ -560,18 +669,10 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
               for (int g = 0; g < GROUPS; ++g) {
                 const uint32_t ag = a_lo + (uint32_t)(8 + tgroup_shift(GROUPS, g) * p.dil) * 8u;   // one row = 128 bytes = 8 descriptor units
                 const uint32_t bg = w_lo0 + (uint32_t)g * wslab_lo;
-                issue_n(p.ksteps, d, ag, bg, idesc, g == 0 ? accum : 1u);                 // hi * W_hi
-                if (planes == 2) {
-                  issue_n(p.ksteps, d, ag, bg + 4u, idesc, 1u);                           // hi * W_lo
-                  issue_n(p.ksteps, d, ag + 4u, bg, idesc, 1u);                           // lo * W_hi
-                }
+                issue_n(p.ksteps, d, ag, bg, idesc, g == 0 ? accum : 1u);   // planes = 2: hi*wh + lo*wh + hi*wl along ONE K axis (4 K steps)
               }
             } else if (packed) {
-              issue_n(p.ksteps, d, a_lo, w_lo0, idesc, accum);            // hi * W_hi
-              if (planes == 2) {
-                issue_n(p.ksteps, d, a_lo, w_lo0 + 4u, idesc, 1u);        // hi * W_lo   (lo halves start 64 bytes into the row)
-                issue_n(p.ksteps, d, a_lo + 4u, w_lo0, idesc, 1u);        // lo * W_hi
-              }
+              issue_n(p.ksteps, d, a_lo, w_lo0, idesc, accum);            // planes = 2: the K-concatenated row, 4 K steps
             } else {
               const int plane = s >= spp ? 1 : 0, sl = s - plane * spp;
               const int nks = min(4, p.ksteps - 4 * sl);
@@ -582,19 +683,21 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
             umma_commit(&a_empty[slot]);
             if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
           }
+          if (j == T - 1 && p.in_free != nullptr) flag_bump(p.in_free + f);   // every stage of the frame has been read out of the ring
           umma_commit(&acc_full[acc_i]);
         }
       }
     }
-  } else {
-    // =========================== loader ===========================
+  } else if (warp == kEpi + 1) {
+    // =========================== loader ===========================   (the fused block kernel has more warps than this role uses)
     if (elect_one()) {
       mbar_expect_tx(&w_full, (uint32_t)p.n_wslab * wslab_bytes);
       for (int i = 0; i < p.n_wslab; ++i) bulk_g2s(sW + (uint32_t)i * wslab_bytes, p.wpack + (size_t)i * wslab_bytes, wslab_bytes, &w_full);
       const int64_t sb = pt_slab_bytes(p.in);
       uint32_t slot = 0, sph = 1;
-      for (int64_t f = blockIdx.x; f < p.B; f += gridDim.x) {
-        const uint8_t* img = p.in.base + f * p.in.frame_bytes;
+      for (int64_t f = rank; f < p.B; f += nranks) {
+        const uint8_t* img = p.in.base + pt_frame_off(p.in, f);
+        if (p.in_ready != nullptr) stat_add(p.stats, 3, flag_wait(p.in_ready + f, 1u));
         for (int j = 0; j < T; ++j) {
           for (int s = 0; s < nst; ++s) {
             mbar_wait_relaxed(&a_empty[slot], sph);
@@ -606,10 +709,56 @@ __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(c
       }
     }
   }
+  else if (warp == kEpi + 2) {
+    // =========================== storer (ring mode: the fused block kernel) ===========================
+    // One thread sends every finished window to the ring in global memory, waits for a frame's stores to COMPLETE and publishes the
+    // frame at once -- a CTA never holds an unpublished frame while it waits for a free slot (that wait would close a cycle through
+    // the other roles), and the epilogue warps never wait for a store.
+    if constexpr (C != 1) {
+      if (ring_out && elect_one()) {
+        uint32_t it = 0;
+        for (int64_t f = rank; f < p.B; f += nranks) {
+          uint8_t* const orow = p.out.base + pt_frame_off(p.out, f) + 8 * 128;
+          const int ring0 = (int)((it * 128u) & (kORing - 1));
+          int done_rows = 0;
+          // the slot's previous frame has been consumed before this frame's first rows go out
+          if (p.out_free != nullptr && f >= p.out.ring) stat_add(p.stats, 2, flag_wait(p.out_free + (f - p.out.ring), (uint32_t)p.out_free_target));
+          for (int j = 0; j < T; ++j, ++it) {
+            mbar_wait_relaxed(&so_ready[it & 1u], (it >> 1) & 1u);
+            const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
+            int r0 = done_rows;
+            while (r0 < upto) {                                    // at most two pieces (ring wrap)
+              const int ring_r = (ring0 + r0) & (kORing - 1);
+              int n = upto - r0;
+              if (ring_r + n > kORing) n = kORing - ring_r;
+              bulk_s2g(orow + (int64_t)r0 * 128, sO + (uint32_t)ring_r * 128u, (uint32_t)n * 128u);
+              r0 += n;
+            }
+            done_rows = upto;
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            const long long t0 = p.stats != nullptr ? clock64() : 0;
+            if (j == T - 1) {
+              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");         // the frame is complete in global memory
+              flag_signal(p.out_ready + f);
+            } else {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the window has left shared memory
+            }
+            if (p.stats != nullptr) stat_add(p.stats, 5, clock64() - t0);
+            mbar_arrive(&so_free[it & 1u]);
+          }
+        }
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == kEpi) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <int C, int TAPS, int GROUPS>
+__global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
+  t_body<C, TAPS, GROUPS>(p);
 }
 
 // ================================================================================================
@@ -638,6 +787,10 @@ struct XParams {
   int slot_bytes;            // shared-memory bytes of one weight unit in this CTA (unit_bytes, or half of it in a pair)
   int s_units;               // staged epilogue: residual / output units in the ring (3, or 4 in a pair)
   int64_t B, n_tiles;
+  // role-relative CTA numbering (a plain launch: cta0 = 0, ncta = gridDim.x) and the frame flags of a ring input (fused block)
+  int cta0, ncta;
+  uint32_t *in_ready, *in_free;
+  unsigned long long* stats; // optional counters (fused block kernel)
 };
 
 constexpr int kXEpiGroups = 3;                   // epilogue warps per TMEM lane quarter (each takes every third 16-column batch)
@@ -667,7 +820,7 @@ __device__ __forceinline__ void gen_producer(const XParams& p, int ptid, int lan
       const uint32_t* wh = reinterpret_cast<const uint32_t*>(s_xh);
       const uint32_t* wl = reinterpret_cast<const uint32_t*>(s_xl);
       uint32_t kb = 0, ph = 1;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         const float* xv = p.xvec + f * p.Lin;
@@ -764,7 +917,7 @@ __device__ __forceinline__ void x_issue_mt(const XIssue& x, uint32_t a_lo, uint3
   if (x.nmt == 2) issue_ks<NKS, MODE>(x.d + x.npad, a_lo + ((128u * 128u) >> 4), b_lo, x.idesc, accum);
 }
 
-// narrow (packed [hi | lo]) input: per tap hi*W_hi, hi*W_lo, lo*W_hi
+// narrow (packed) input: per tap ONE chain over the row's K axis (planes = 2: K-concatenated hi*wh + lo*wh + hi*wl, 4 K steps)
 template <int NKS, int MODE>
 __device__ __forceinline__ void x_issue_packed(XIssue& x, const XParams& p, uint32_t a_lo0) {
   uint32_t accum = 0;
@@ -772,10 +925,6 @@ __device__ __forceinline__ void x_issue_packed(XIssue& x, const XParams& p, uint
     const uint32_t b_lo = x.wait_w<MODE>();
     const uint32_t a_lo = a_lo0 + (uint32_t)(t * p.dil) * 8u;      // one row = 128 bytes = 8 descriptor units
     x_issue_mt<NKS, MODE>(x, a_lo, b_lo, accum);
-    if (p.planes == 2) {
-      x_issue_mt<NKS, MODE>(x, a_lo, b_lo + 4u, 1u);
-      x_issue_mt<NKS, MODE>(x, a_lo + 4u, b_lo, 1u);
-    }
     accum = 1;
     x.done_w<MODE>();
   }
@@ -834,9 +983,11 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   x.nmt = p.n_iss == 2 ? 1 : p.mt;
   x.npad = (uint32_t)p.Npad;
   uint32_t it = 0, kb = 0, a_phase = 0;
-  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+  for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta, ++it) {
     const uint32_t acc_i = it & 1u;
+    long long tw = p.stats != nullptr ? clock64() : 0;
     if constexpr (MODE != 2) mbar_wait(&bars.acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);   // (pair: both CTAs' epilogues arrive on the leader's)
+    if (p.stats != nullptr) stat_add(p.stats, 7, clock64() - tw);
     tc_fence_after();
     x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)(m0 * p.Npad);
     x.u = 0;
@@ -856,7 +1007,10 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
         for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + ap]);
       }
     } else if (p.in.packed) {
+      tw = p.stats != nullptr ? clock64() : 0;
       wait_full<MODE>(&bars.a_full[kb], &bars.a_full2[kb], a_phase);
+      if (p.stats != nullptr) stat_add(p.stats, 6, clock64() - tw);
+      if (p.in_free != nullptr && issuer == 0) flag_bump(p.in_free + tile / p.tiles_per_frame);   // this CTA's tile has been read out of the ring
       const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
       switch (p.ksteps) {
         case 2: x_issue_packed<2, MODE>(x, p, a_lo0); break;
@@ -934,7 +1088,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
     const float slope = act_slope_of(p.act), pslope = act_slope_of(p.post_act);
     const bool slow_act = p.act == NSC_ACT_TANH || p.post_act == NSC_ACT_TANH;
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta, ++it) {
       const int64_t f = tile / p.tiles_per_frame;
       const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
       const uint32_t acc_i = it & 1u;
@@ -1047,7 +1201,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       const int nsub = p.in.deint ? 2 : 1;
       const int npl = p.in.packed ? 1 : p.in.planes;
       uint32_t kb = 0, ph = 1;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         const uint8_t* img = p.in.base + f * p.in.frame_bytes;
@@ -1077,7 +1231,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         }
       } else {
         uint32_t ws = 0, wph = 1;
-        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
           for (int u = 0; u < p.n_units; ++u) {
             mbar_wait_relaxed(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], sbytes);
@@ -1115,14 +1269,17 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
 // plane.  No thread touches global memory; latency hiding is the copy engine's job.
 //   unit = (M tile, 64-channel output slab) x planes; ring of kSUnits units:  residual loader -> epilogue -> storer.
 // ================================================================================================
-constexpr int kSEpiGroups = 4, kSEpiWarps = 4 * kSEpiGroups;
-constexpr int kSThreads = (kSEpiWarps + 6 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer, second MMA issuer, Toeplitz producers
+constexpr int kSEpiGroups = 4;                     // epilogue warps per TMEM lane quarter of the stand-alone kernel (one 16-column batch each)
+constexpr int kSThreads = (4 * kSEpiGroups + 6 + kXGenWarps) * 32;   // + MMA issuer, A loader, W loader, residual loader, storer, second MMA issuer, Toeplitz producers
 constexpr int kSUnits = 3, kSMaxUnits = 4;
 constexpr int kSPlane = 128 * 128;                 // one plane of one unit
 
-
-template <bool kPair>
-__global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_constant__ XParams p) {
+// kEG: epilogue warps per lane quarter.  4 = one 16-column batch of a 64-channel unit per warp; the fused block kernel runs 3 (the
+// register budget of its taps-in-N roles caps the CTA at 18 warps), where the first group takes two batches of a full unit.
+template <bool kPair, int kEG>
+__device__ __forceinline__ void xs_body(const XParams& p) {
+  constexpr int kSEpiWarps = 4 * kEG;
+  constexpr int kNB = (4 + kEG - 1) / kEG;          // batches a warp may own in one unit
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[4], a_empty[4], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
@@ -1177,7 +1334,8 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
     const uint32_t osw = (uint32_t)srow_o & 7u;
     const uint32_t rbase = (uint32_t)lr * 128u, rsw = (uint32_t)lr & 7u;   // residual units are never de-interleaved
     uint32_t it = 0, slot = 0, sph = 0;
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const long long t_begin = clock64();
+    for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta, ++it) {
       const int64_t f = tile / p.tiles_per_frame;
       const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
       const uint32_t acc_i = it & 1u;
@@ -1190,54 +1348,62 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
           const int nbs = min(4, nb - 4 * s);
           mbar_wait_relaxed(&st_full[slot], sph);
           uint8_t* unit = sS + slot * stg_bytes;
-          const bool mine = grp < nbs;
-          const int c0 = 64 * s + 16 * grp;              // first column / channel of this warp's batch
-          const uint32_t cg = 2u * (uint32_t)grp;        // first 16-byte chunk inside the slab
-          float v[16];
-          if (mine) {
-            uint32_t r[16];
-            tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
-            float rs[16];
-            if (has_res) {
-              const uint4 h0 = *reinterpret_cast<const uint4*>(unit + rbase + ((cg ^ rsw) << 4));
-              const uint4 h1 = *reinterpret_cast<const uint4*>(unit + rbase + (((cg + 1u) ^ rsw) << 4));
-              float a[8], b[8];
-              unpack8(h0, a); unpack8(h1, b);
+          float v[kNB][16];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { rs[e] = a[e]; rs[8 + e] = b[e]; }
-              if (p.planes == 2) {
-                const uint4 l0 = *reinterpret_cast<const uint4*>(unit + kSPlane + rbase + ((cg ^ rsw) << 4));
-                const uint4 l1 = *reinterpret_cast<const uint4*>(unit + kSPlane + rbase + (((cg + 1u) ^ rsw) << 4));
-                unpack8(l0, a); unpack8(l1, b);
+          for (int bi = 0; bi < kNB; ++bi) {
+            const int bt = grp + bi * kEG;                 // 16-column batch of this unit
+            if (bt < nbs) {
+              const int c0 = 64 * s + 16 * bt;             // first column / channel of the batch
+              const uint32_t cg = 2u * (uint32_t)bt;       // first 16-byte chunk inside the slab
+              uint32_t r[16];
+              tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
+              float rs[16];
+              if (has_res) {
+                const uint4 h0 = *reinterpret_cast<const uint4*>(unit + rbase + ((cg ^ rsw) << 4));
+                const uint4 h1 = *reinterpret_cast<const uint4*>(unit + rbase + (((cg + 1u) ^ rsw) << 4));
+                float a[8], b[8];
+                unpack8(h0, a); unpack8(h1, b);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { rs[e] += a[e]; rs[8 + e] += b[e]; }
+                for (int e = 0; e < 8; ++e) { rs[e] = a[e]; rs[8 + e] = b[e]; }
+                if (p.planes == 2) {
+                  const uint4 l0 = *reinterpret_cast<const uint4*>(unit + kSPlane + rbase + ((cg ^ rsw) << 4));
+                  const uint4 l1 = *reinterpret_cast<const uint4*>(unit + kSPlane + rbase + (((cg + 1u) ^ rsw) << 4));
+                  unpack8(l0, a); unpack8(l1, b);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { rs[e] += a[e]; rs[8 + e] += b[e]; }
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) rs[e] = (rvec && c0 + e < p.Cout) ? rv : 0.f;
               }
-            } else {
+              float bs[16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) rs[e] = (rvec && c0 + e < p.Cout) ? rv : 0.f;
+              for (int e = 0; e < 16; e += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + e]);
+                bs[e] = b4.x; bs[e + 1] = b4.y; bs[e + 2] = b4.z; bs[e + 3] = b4.w;
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[bi][e] = act_fast(act_fast(__uint_as_float(r[e]) + bs[e], slope) + rs[e], pslope);
             }
-            float bs[16];
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + e]);
-              bs[e] = b4.x; bs[e + 1] = b4.y; bs[e + 2] = b4.z; bs[e + 3] = b4.w;
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = act_fast(act_fast(__uint_as_float(r[e]) + bs[e], slope) + rs[e], pslope);
           }
           if (barrier_rw) asm volatile("bar.sync 3, %0;" :: "n"(kSEpiWarps * 32) : "memory");
-          if (mine) {
-            float a[8], b[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { a[e] = v[e]; b[e] = v[8 + e]; }
-            uint4 hi, lo;
-            split8(a, hi, lo);
-            *reinterpret_cast<uint4*>(unit + obase + ((cg ^ osw) << 4)) = hi;
-            if (p.planes == 2) *reinterpret_cast<uint4*>(unit + kSPlane + obase + ((cg ^ osw) << 4)) = lo;
-            split8(b, hi, lo);
-            *reinterpret_cast<uint4*>(unit + obase + (((cg + 1u) ^ osw) << 4)) = hi;
-            if (p.planes == 2) *reinterpret_cast<uint4*>(unit + kSPlane + obase + (((cg + 1u) ^ osw) << 4)) = lo;
+          for (int bi = 0; bi < kNB; ++bi) {
+            const int bt = grp + bi * kEG;
+            if (bt < nbs) {
+              const uint32_t cg = 2u * (uint32_t)bt;
+              float a[8], b[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { a[e] = v[bi][e]; b[e] = v[bi][8 + e]; }
+              uint4 hi, lo;
+              split8(a, hi, lo);
+              *reinterpret_cast<uint4*>(unit + obase + ((cg ^ osw) << 4)) = hi;
+              if (p.planes == 2) *reinterpret_cast<uint4*>(unit + kSPlane + obase + ((cg ^ osw) << 4)) = lo;
+              split8(b, hi, lo);
+              *reinterpret_cast<uint4*>(unit + obase + (((cg + 1u) ^ osw) << 4)) = hi;
+              if (p.planes == 2) *reinterpret_cast<uint4*>(unit + kSPlane + obase + (((cg + 1u) ^ osw) << 4)) = lo;
+            }
           }
           fence_async_smem();                            // generic-proxy writes -> visible to the bulk store
           __syncwarp();
@@ -1251,6 +1417,11 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
         if constexpr (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);   // the leader's barrier counts both CTAs' epilogue warps
         else mbar_arrive(&acc_empty[acc_i]);
       }
+    }
+    if (warp == 0 && lane == 0 && p.stats != nullptr) {
+      stat_add(p.stats, 0, 3);
+      stat_add(p.stats, 1, clock64() - t_begin);
+      stat_add(p.stats, 4, (long long)it);
     }
   } else if (warp == kSEpiWarps || warp == kSEpiWarps + 5) {
     // =========================== MMA issuers (one per M tile) ===========================
@@ -1267,12 +1438,13 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
     // =========================== A loader ===========================
     if (!gen && elect_one()) {
       uint32_t kb = 0, ph = 1;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         mbar_wait_relaxed(&a_empty[kb], ph);
+        if (p.in_ready != nullptr) stat_add(p.stats, 3, flag_wait(p.in_ready + f, 1u));
         mbar_expect_tx(&a_full[kb], (uint32_t)p.stage_bytes);
-        bulk_g2s(sA + kb * (uint32_t)p.stage_bytes, p.in.base + f * p.in.frame_bytes + (int64_t)q0 * 128, (uint32_t)p.stage_bytes, &a_full[kb]);
+        bulk_g2s(sA + kb * (uint32_t)p.stage_bytes, p.in.base + pt_frame_off(p.in, f) + (int64_t)q0 * 128, (uint32_t)p.stage_bytes, &a_full[kb]);
         if (p.kbuf == 2) { kb ^= 1u; if (kb == 0) ph ^= 1u; }
         else ph ^= 1u;
       }
@@ -1290,7 +1462,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
         }
       } else {
         uint32_t ws = 0, wph = 1;
-        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
           for (int u = 0; u < p.n_units; ++u) {
             mbar_wait_relaxed(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], sbytes);
@@ -1306,7 +1478,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
       const bool has_res = p.res_mode == RES_ADD;
       const int64_t rsb = pt_slab_bytes(p.res);
       uint32_t slot = 0, ph = 1;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         for (int mt_i = 0; mt_i < p.mt; ++mt_i)
@@ -1330,7 +1502,7 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
     if (elect_one()) {
       const int64_t osb = pt_slab_bytes(p.out);
       uint32_t slot = 0, ph = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         uint8_t* oimg = p.out.base + f * p.out.frame_bytes;
@@ -1369,6 +1541,37 @@ __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_con
   }
 }
 
+template <bool kPair>
+__global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_constant__ XParams p) {
+  xs_body<kPair, kSEpiGroups>(p);
+}
+
+// ================================================================================================
+// Fused bottleneck block (nn_core_operator.py:57-79): ONE persistent launch, three CTA roles.
+//   role 1  conv 1 (wide -> narrow, taps-in-N)        t_body<20, 9, 1>       reads the block's input x from HBM, writes h1 into ring 1
+//   role 2  conv 2 (narrow -> narrow, grouped)        t_body<20, 5, 3>       ring 1 -> ring 2
+//   role 3  conv 3 (narrow -> wide) + residual + act  xs_body<pair, 3>       ring 2 + x (second read: L2) -> the block's output y
+// The rings hold a few dozen frames (plane_block_ring_frames(); a few MB, far below the 126 MB L2), so h1 and h2 are produced and
+// consumed out of L2 and never written back before they are overwritten; frame hand-off is one flag per frame and direction
+// (flag_wait / flag_signal / flag_bump above).  All CTAs of the launch are co-resident (grid <= SM count, one CTA per SM), roles are
+// contiguous CTA ranges of even size so that the CTA pairs of role 3 stay pairs.  Why not shared memory: in the fp16 hi/lo
+// representation the three convs' packed weights alone are 270 KB.
+// ================================================================================================
+constexpr int kBlockThreads = (12 + 6) * 32;      // 12 epilogue warps in every role + the 6 service warps of role 3
+
+struct BlockParams {
+  TParams p1, p2;
+  XParams p3;
+};
+
+template <int TAPS2, int GROUPS2>
+__global__ void __launch_bounds__(kBlockThreads, 1) plane_block_kernel(const __grid_constant__ BlockParams bp) {
+  const int b = (int)blockIdx.x;
+  if (b < bp.p2.cta0) t_body<20, 9, 1>(bp.p1);
+  else if (b < bp.p3.cta0) t_body<20, TAPS2, GROUPS2>(bp.p2);
+  else xs_body<true, 3>(bp.p3);
+}
+
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ourselves (alignment slack + static barriers)
 
 struct TPlan {
@@ -1383,6 +1586,7 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   const bool k55 = (c.Cout == 1 && c.K == 55 && c.dil == 1);
   if (!k9 && !k55) return false;
   if (c.stride != 1 || c.shuffle != 1 || c.res_mode != RES_NONE || c.post_act != NSC_ACT_NONE) return false;
+  if (k9 && c.act == NSC_ACT_TANH) return false;      // the 20-channel epilogue applies slope-form activations only
   if (c.Cin < 2 || c.in.deint || c.Lin % 128 != 0 || c.in.rows != c.Lin) return false;
   if (k9 && (!c.out.packed || c.out.deint || c.out.rows != c.Lin)) return false;
   // narrow -> narrow: tap groups by row shift, 5 (or 3) tap slots across lanes instead of 9 -- the lane-crossing volume bounds the layer.
@@ -1394,7 +1598,7 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   pl->stage_bytes = pl->groups > 1 ? (128 + 16) * 128 : 128 * 128;
   const size_t kAStage = (size_t)pl->stage_bytes;
   pl->N = k9 ? (pl->groups == 5 ? 64 : pl->groups == 3 ? 112 : 192) : 64;
-  pl->ksteps = (c.Cin + 15) / 16;
+  pl->ksteps = (c.in.packed && c.planes == 2) ? 4 : (c.Cin + 15) / 16;   // packed hi/lo rows: one K axis of 64 halves
   pl->n_wslab = pl->groups > 1 ? pl->groups : (c.in.packed ? 1 : c.in.planes * c.in.spp);
   const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
   const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * t_slots(k9 ? 20 : 1) * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
@@ -1408,7 +1612,19 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   return true;
 }
 
-bool plan_x(const PlaneConv& c, XParams* p) {
+TParams make_tparams(const PlaneConv& c, const TPlan& pl, int cta0, int ncta) {
+  TParams p;
+  p.in = c.in; p.out = c.out;
+  p.wpack = static_cast<const uint8_t*>(c.wpack); p.bias = c.bias; p.yvec = c.yvec;
+  p.N = pl.N; p.n_wslab = pl.n_wslab; p.ksteps = pl.ksteps; p.stage_bytes = pl.stage_bytes; p.L = c.Lin; p.dil = c.dil; p.act = c.act; p.na = pl.na; p.B = c.B;
+  p.cta0 = cta0; p.ncta = ncta;
+  p.in_ready = p.in_free = p.out_ready = p.out_free = nullptr;
+  p.out_free_target = 1;
+  p.stats = nullptr;
+  return p;
+}
+
+bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   const bool gen = c.kind == PK_GEN;
   int Lout, padL;
   same_padding(c.Lin, c.K, c.dil, c.stride, &Lout, &padL);
@@ -1431,20 +1647,22 @@ bool plan_x(const PlaneConv& c, XParams* p) {
   if (c.res_mode == RES_MUL || (gen && c.res_mode != RES_NONE)) return false;
   if (c.out.rows != (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
   p->kind = c.kind;
+  p->cta0 = 0; p->ncta = 1; p->in_ready = nullptr; p->in_free = nullptr; p->stats = nullptr;
   p->in = c.in; p->out = c.out; p->res = c.res;
   p->xvec = c.xvec; p->xsub = c.xsub; p->xscale = c.xscale; p->resvec = c.resvec;
   p->wpack = static_cast<const uint8_t*>(c.wpack); p->bias = c.bias;
   p->Lin = c.Lin; p->Lout = Lout; p->Cin = c.Cin; p->Cout = c.Cout; p->K = c.K; p->dil = c.dil; p->stride = c.stride; p->padL = padL;
   p->act = c.act; p->post_act = c.post_act; p->res_mode = c.res_mode; p->shuffle = c.shuffle; p->planes = c.planes;
   p->Npad = (c.Cout + 15) & ~15;
-  p->ksteps = gen ? (c.K + 15) / 16 : (c.Cin + 15) / 16;
+  p->ksteps = gen ? (c.K + 15) / 16 : ((c.in.packed && c.planes == 2) ? 4 : (c.Cin + 15) / 16);   // packed hi/lo rows: one K axis of 64 halves
   p->n_stage = gen ? c.planes : pt_n_slabs(c.in);
   p->unit_bytes = p->Npad * 128;
   p->n_units = gen ? c.planes : (c.in.packed ? c.K : c.in.spp * c.K * c.planes);
   if (p->n_stage > kXMaxStage) return false;
   // narrow-input, wide-output layers (the HBM-bound third conv of a block) take the staged epilogue
   static const bool no_stage = getenv("NSC_PLANE_NOSTAGE") != nullptr;
-  p->staged = ((gen || c.in.packed) && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage) ? 1 : 0;
+  p->staged = ((gen || c.in.packed) && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage && c.act != NSC_ACT_TANH &&
+               c.post_act != NSC_ACT_TANH) ? 1 : 0;   // (the staged epilogue applies slope-form activations only)
   // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
   // CTA pairs (cta_group::2) for the layers with a plain epilogue: each CTA of a pair keeps its own tile and half of every
   // weight unit (half the weight stream into each shared memory, half the instructions).  Needs an even number of work units,
@@ -1468,8 +1686,8 @@ bool plan_x(const PlaneConv& c, XParams* p) {
     if (2 * mt * p->Npad > 512) continue;
     // staged epilogue: ring of residual / output units.  A pair's half-size weight slots leave room for a fourth unit -- more
     // bytes in flight per SM, which is what bounds the HBM-bound layers
-    p->s_units = p->staged ? ((p->pair && 2 * a1 + 3 * slot + (size_t)(kSUnits + 1) * c.planes * kSPlane <= kSmemBudget) ? kSUnits + 1 : kSUnits) : 0;
-    const size_t budget = kSmemBudget - (size_t)p->s_units * c.planes * kSPlane;
+    p->s_units = p->staged ? ((p->pair && 2 * a1 + 3 * slot + (size_t)(kSUnits + 1) * c.planes * kSPlane <= smem_budget) ? kSUnits + 1 : kSUnits) : 0;
+    const size_t budget = smem_budget - (size_t)p->s_units * c.planes * kSPlane;
     if (p->n_units <= kXMaxW && 2 * a1 + wall <= budget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
     else if (2 * a1 + (p->pair ? 3 * slot : 4ull * p->unit_bytes) <= budget) { p->kbuf = 2; p->resident = 0; }
     else if (p->n_units <= kXMaxW && a1 + wall <= budget) { p->kbuf = 1; p->resident = 1; p->wslots = p->n_units; }
@@ -1607,16 +1825,13 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.kind == PK_T) {
     TPlan pl;
     NSC_CHECK_ARG(plan_t(c, &pl), "plane engine: unsupported taps-in-N layer (k%d d%d %d->%d)", c.K, c.dil, c.Cin, c.Cout);
-    TParams p;
-    p.in = c.in; p.out = c.out;
-    p.wpack = static_cast<const uint8_t*>(c.wpack); p.bias = c.bias; p.yvec = c.yvec;
-    p.N = pl.N; p.n_wslab = pl.n_wslab; p.ksteps = pl.ksteps; p.stage_bytes = pl.stage_bytes; p.L = c.Lin; p.dil = c.dil; p.act = c.act; p.na = pl.na; p.B = c.B;
     NSC_CHECK_ARG(c.Cout > 1 || c.yvec != nullptr, "plane engine: head without an output vector");
+    const int64_t grid = c.B < sm_count() ? c.B : sm_count();
+    const TParams p = make_tparams(c, pl, 0, (int)grid);
     snprintf(name, sizeof(name), "pT%d_k%dd%d_c%dto%d", c.planes, c.K, c.dil, c.Cin, c.Cout);
     // algorithmic bytes: every input and output plane image moved exactly once (zero rows excluded)
-    const double bytes = (double)c.B * (pt_payload_bytes(c.in) + (c.Cout > 1 ? pt_payload_bytes(c.out) : 4.0 * c.Lin));
+    const double bytes = (double)c.B * (pt_real_bytes(c.Lin, c.Cin, c.planes) + (c.Cout > 1 ? pt_real_bytes(c.Lin, c.Cout, c.planes) : 4.0 * c.Lin));
     ProfScope prof(st, name, 2.0 * macs, bytes);
-    const int64_t grid = c.B < sm_count() ? c.B : sm_count();
     if (c.Cout == 20 && pl.groups == 5) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
       plane_t_kernel<20, 3, 5><<<(unsigned)grid, TShape<20, 3>::kThreads, pl.smem, st>>>(p);
@@ -1636,15 +1851,20 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   XParams p;
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
   const size_t smem = x_smem_bytes(p);
+  {
+    int64_t g = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    if (p.pair) g &= ~(int64_t)1;
+    p.ncta = (int)g;
+  }
   if (p.staged && p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
-  double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_payload_bytes(c.in));
-  bytes += (double)c.B * pt_payload_bytes(c.out);
-  if (c.res_mode == RES_ADD) bytes += (double)c.B * pt_payload_bytes(c.res);
+  double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_real_bytes(c.Lin, c.Cin, c.planes));
+  bytes += (double)c.B * pt_real_bytes(Lout, c.Cout, c.planes);
+  if (c.res_mode == RES_ADD) bytes += (double)c.B * pt_real_bytes(Lout, c.Cout, c.planes);
   if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
   ProfScope prof(st, name, 2.0 * macs, bytes);
   int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
@@ -1668,6 +1888,141 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   else if (p.staged) plane_xs_kernel<false><<<(unsigned)grid, kSThreads, smem, st>>>(p);
   else if (c.kind == PK_GEN) plane_x_kernel<true, false><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
   else plane_x_kernel<false, false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+// ---- fused bottleneck block ---------------------------------------------------------------------------------------------
+int plane_block_ring_frames() {
+  static const int v = [] {
+    const char* e = getenv("NSC_BLOCK_RING");
+    int n = e ? atoi(e) : 128;
+    if (n < 2) n = 2;
+    int r = 2;
+    while (r * 2 <= n && r < 4096) r *= 2;
+    return r;
+  }();
+  return v;
+}
+
+int64_t plane_block_flag_words(int64_t B) { return 4 * align_up(B < 1 ? 1 : B, 32); }
+
+namespace {
+
+// CTAs per role.  Defaults are measured (tools/block_stats.py, profiles/r02_block_stats*.log): per 128-position tile role 1 costs
+// ~3.6 k cycles (shared-memory bandwidth of its N = 192 instructions), role 2 ~2.6 k (tap-sum epilogue), role 3 ~4.4 k (staging
+// traffic of the residual / output units) for a 100-channel block; a 50-channel block is cheaper on role 3.
+// NSC_BLOCK_SPLIT="n1,n2" overrides (even numbers; role 3 takes the rest).
+void block_split(const PlaneBlock& b, int* n1, int* n2, int* n3) {
+  const int sms = sm_count() & ~1;
+  static const char* knob = getenv("NSC_BLOCK_SPLIT");
+  int a = 0, c = 0;
+  if (knob && sscanf(knob, "%d,%d", &a, &c) == 2 && a >= 2 && c >= 2 && a + c + 2 <= sms) { a &= ~1; c &= ~1; }
+  else if (b.c1.Cin >= 64) { a = (int)(sms * 50 / 148) & ~1; c = (int)(sms * 36 / 148) & ~1; }
+  else { a = (int)(sms * 52 / 148) & ~1; c = (int)(sms * 44 / 148) & ~1; }
+  if (a < 2) a = 2;
+  if (c < 2) c = 2;
+  *n1 = a; *n2 = c; *n3 = sms - a - c;
+}
+
+struct BlockPlan {
+  TPlan t1, t2;
+  XParams x3;
+  size_t smem;
+};
+
+bool plan_block(const PlaneBlock& b, BlockPlan* bp) {
+  const PlaneConv &c1 = b.c1, &c2 = b.c2, &c3 = b.c3;
+  if (c1.kind != PK_T || c2.kind != PK_T || c3.kind != PK_X) return false;
+  if (c1.Cout != 20 || c2.Cin != 20 || c2.Cout != 20 || c3.Cin != 20 || c1.Cin != c3.Cout) return false;
+  if (c3.res_mode != RES_ADD || c1.planes != c2.planes || c1.planes != c3.planes) return false;
+  if (c1.B != c2.B || c1.B != c3.B || c1.B < 1) return false;
+  if (b.ring < 2 || (b.ring & (b.ring - 1))) return false;
+  if (sm_count() < 8) return false;
+  if (!plan_t(c1, &bp->t1) || !plan_t(c2, &bp->t2) || bp->t2.groups != 3) return false;
+  if (!plan_x(c3, &bp->x3, kSmemBudget - 2048) || !bp->x3.staged || !bp->x3.pair) return false;   // (the fused kernel's static shared memory is the sum of its roles')   // (pairs need an even number of tiles)
+  bp->smem = bp->t1.smem;
+  if (bp->t2.smem > bp->smem) bp->smem = bp->t2.smem;
+  if (x_smem_bytes(bp->x3) > bp->smem) bp->smem = x_smem_bytes(bp->x3);
+  return true;
+}
+
+}  // namespace
+
+bool plane_block_supported(const PlaneBlock& b) {
+  BlockPlan bp;
+  return plan_block(b, &bp);
+}
+
+// Whether the codec program launches its bottleneck blocks fused.  Measured on the headline workload (profiles/r02_block_*.log,
+// DESIGN.md section 4): the fused launch keeps the intermediates out of HBM and is bit-identical, but its three roles are bound by
+// shared-memory bandwidth / the tap-sum epilogue rather than by HBM, and under the 1 kW power cap the step is 8 % SLOWER with it
+// (124 vs 113 ms) -- so it is opt-in (NSC_BLOCK_FUSED=1); the operator surface (nsc_bottleneck_block_tc) uses it.
+bool plane_block_default_on() {
+  static const bool on = [] { const char* e = getenv("NSC_BLOCK_FUSED"); return e && e[0] == '1'; }();
+  return on;
+}
+
+int plane_block_launch(const PlaneBlock& b, cudaStream_t st) {
+  BlockPlan pl;
+  NSC_CHECK_ARG(plan_block(b, &pl), "plane engine: block not covered by the fused kernel");
+  NSC_CHECK_ARG(b.flags != nullptr && b.c1.wpack && b.c2.wpack && b.c3.wpack, "plane engine: fused block without flags / packed weights");
+  const int64_t B = b.c1.B;
+  const int64_t fw = align_up(B, 32);
+  uint32_t* h1_ready = b.flags;
+  uint32_t* h1_free = b.flags + fw;
+  uint32_t* h2_ready = b.flags + 2 * fw;
+  uint32_t* h2_free = b.flags + 3 * fw;
+  int n1, n2, n3;
+  block_split(b, &n1, &n2, &n3);
+  BlockParams bp;
+  PlaneConv c1 = b.c1, c2 = b.c2, c3 = b.c3;
+  c1.out.ring = b.ring; c2.in.ring = b.ring; c2.out.ring = b.ring; c3.in.ring = b.ring;
+  bp.p1 = make_tparams(c1, pl.t1, 0, n1);
+  bp.p1.out_ready = h1_ready; bp.p1.out_free = h1_free; bp.p1.out_free_target = 1;
+  bp.p2 = make_tparams(c2, pl.t2, n1, n2);
+  bp.p2.in_ready = h1_ready; bp.p2.in_free = h1_free;
+  bp.p2.out_ready = h2_ready; bp.p2.out_free = h2_free; bp.p2.out_free_target = pl.x3.tiles_per_frame;
+  bp.p3 = pl.x3;
+  bp.p3.in = c3.in;
+  bp.p3.cta0 = n1 + n2; bp.p3.ncta = n3;
+  bp.p3.in_ready = h2_ready; bp.p3.in_free = h2_free;
+  static const bool want_stats = getenv("NSC_BLOCK_STATS") != nullptr;
+  if (want_stats) {
+    void* sp = nullptr;
+    NSC_CUDA_OK(cudaGetSymbolAddress(&sp, g_block_stats));
+    NSC_CUDA_OK(cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * kStatCtas * kStatWords, st));
+    bp.p1.stats = bp.p2.stats = bp.p3.stats = static_cast<unsigned long long*>(sp);
+  }
+  auto kern = plane_block_kernel<5, 3>;
+  static size_t static_smem = 0;
+  if (static_smem == 0) {
+    cudaFuncAttributes fa;
+    NSC_CUDA_OK(cudaFuncGetAttributes(&fa, kern));
+    static_smem = fa.sharedSizeBytes;
+  }
+  NSC_CHECK_ARG(pl.smem + static_smem <= 227 * 1024, "plane engine: fused block needs %zu + %zu bytes of shared memory", pl.smem, static_smem);
+  NSC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int Lout, padL;
+  same_padding(c1.Lin, c1.K, 1, 1, &Lout, &padL);
+  const double macs = (double)B * Lout * ((double)c1.K * c1.Cin * c1.Cout + (double)c2.K * c2.Cin * c2.Cout + (double)c3.K * c3.Cin * c3.Cout);
+  char name[32];
+  snprintf(name, sizeof(name), "pB%d_d%d_c%d_L%d", c1.planes, c2.dil, c1.Cin, c1.Lin);
+  // algorithmic bytes: the block's input and output images, each moved once (the residual read and both intermediates stay in L2)
+  ProfScope prof(st, name, 2.0 * macs, (double)B * (pt_real_bytes(c1.Lin, c1.Cin, c1.planes) + pt_real_bytes(Lout, c3.Cout, c3.planes)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n1 + n2 + n3));
+  cfg.blockDim = dim3(kBlockThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NSC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bp));
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
@@ -1786,6 +2141,115 @@ int nsc_conv1d_tc(const float* x, const float* w, const float* b, const float* r
   NSC_TRY(plane_launch(c, st));
   if (Cout > 1) NSC_TRY(plane_to_f32(c.out, y, 1, B, pl.Ly, pl.Cy, st));
   return NSC_OK;
+}
+
+// ---- the_bottleneck (nn_core_operator.py:57-79) on the plane engine, channels-last fp32 tensors at the edge -----------------
+namespace {
+
+struct TcBlockPlan {
+  nsc::PlaneBlock b;
+  int64_t x_bytes, y_bytes, n_bytes, w1, w2, w3, flag_bytes;
+};
+
+int make_tc_block_plan(int64_t B, int L, int wide, int narrow, int k_plain, int k_dilated, int dilation, int is_last_flat, int precision,
+                       TcBlockPlan* pl) {
+  using namespace nsc;
+  NSC_CHECK_ARG(precision == 1 || precision == 2, "nsc_bottleneck_block_tc: precision must be 1 (fp16 hi/lo) or 2 (fp16)");
+  NSC_CHECK_ARG(B >= 1 && L > 0 && L % 128 == 0 && wide > 32 && wide <= 128 && narrow == 20 && k_plain == 9 && k_dilated == 9 &&
+                    dilation >= 1 && dilation <= 2,
+                "nsc_bottleneck_block_tc: shape not covered by the tensor engine (L %d, %d/%d, k %d/%d, dilation %d)", L, wide, narrow, k_plain,
+                k_dilated, dilation);
+  const int P = precision == 1 ? 2 : 1;
+  PlaneBlock& b = pl->b;
+  auto conv = [&](PlaneConv& c, int kind, int cin, int cout, int K, int dil, int act, int res_mode, int post) {
+    c.kind = kind; c.Lin = L; c.Cin = cin; c.Cout = cout; c.K = K; c.dil = dil; c.stride = 1;
+    c.act = act; c.post_act = post; c.res_mode = res_mode; c.shuffle = 1; c.planes = P; c.B = B;
+  };
+  conv(b.c1, PK_T, wide, narrow, k_plain, 1, NSC_ACT_LRELU, RES_NONE, NSC_ACT_NONE);
+  conv(b.c2, PK_T, narrow, narrow, k_dilated, dilation, NSC_ACT_LRELU, RES_NONE, NSC_ACT_NONE);
+  conv(b.c3, PK_X, narrow, wide, k_plain, 1, NSC_ACT_NONE, RES_ADD, is_last_flat ? NSC_ACT_NONE : NSC_ACT_LRELU);
+  const PlaneTensor tx = make_plane_tensor(nullptr, L, wide, P, 0), tn = make_plane_tensor(nullptr, L, narrow, P, 0);
+  b.c1.in = tx; b.c1.out = tn; b.c2.in = tn; b.c2.out = tn; b.c3.in = tn; b.c3.out = tx; b.c3.res = tx;
+  int ring = plane_block_ring_frames();
+  while (ring > 2 && ring > B) ring /= 2;
+  b.ring = ring;
+  NSC_CHECK_ARG(plane_conv_supported(b.c1) && plane_conv_supported(b.c2) && plane_conv_supported(b.c3),
+                "nsc_bottleneck_block_tc: a conv of the block is not covered by the tensor engine");
+  pl->x_bytes = align_up(B * tx.frame_bytes, 1024);
+  pl->y_bytes = pl->x_bytes;
+  pl->n_bytes = align_up(B * tn.frame_bytes, 1024);
+  pl->w1 = align_up(plane_wpack_bytes(b.c1), 1024);
+  pl->w2 = align_up(plane_wpack_bytes(b.c2), 1024);
+  pl->w3 = align_up(plane_wpack_bytes(b.c3), 1024);
+  pl->flag_bytes = align_up(plane_block_flag_words(B) * (int64_t)sizeof(uint32_t), 1024);
+  return NSC_OK;
+}
+
+}  // namespace
+
+int64_t nsc_bottleneck_block_tc_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t narrow, int32_t precision) {
+  TcBlockPlan pl;
+  if (make_tc_block_plan(B < 1 ? 1 : B, L, wide, narrow, 9, 9, 1, 0, precision, &pl) != NSC_OK) return -1;
+  return 2048 + pl.x_bytes + pl.y_bytes + 2 * pl.n_bytes + pl.w1 + pl.w2 + pl.w3 + pl.flag_bytes;
+}
+
+int nsc_bottleneck_block_tc(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t wide, int32_t narrow,
+                            int32_t k_plain, int32_t k_dilated, int32_t dilation, int32_t is_last_flat, int32_t precision,
+                            int32_t* fused_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace nsc;
+  const bool force_unfused = fused_out && *fused_out == -1;      // tests: the same three kernels, one launch each
+  if (fused_out) *fused_out = 0;
+  if (B == 0) return NSC_OK;
+  NSC_CHECK_ARG(x && params && y && workspace, "nsc_bottleneck_block_tc: null pointer");
+  TcBlockPlan pl;
+  NSC_TRY(make_tc_block_plan(B, L, wide, narrow, k_plain, k_dilated, dilation, is_last_flat, precision, &pl));
+  const int64_t need = 2048 + pl.x_bytes + pl.y_bytes + 2 * pl.n_bytes + pl.w1 + pl.w2 + pl.w3 + pl.flag_bytes;
+  if (workspace_bytes < need) {
+    set_error("nsc_bottleneck_block_tc: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    return NSC_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // the images sit 1 KB into the workspace: the first slab's halo reads stay inside it
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023) + 1024;
+  NSC_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)(pl.x_bytes + pl.y_bytes + 2 * pl.n_bytes), st));   // the images' zero rows
+  PlaneBlock& b = pl.b;
+  b.c1.in.base = p; b.c3.res.base = p; p += pl.x_bytes;
+  b.c3.out.base = p; p += pl.y_bytes;
+  b.c1.out.base = p; b.c2.in.base = p; p += pl.n_bytes;
+  b.c2.out.base = p; b.c3.in.base = p; p += pl.n_bytes;
+  b.c1.wpack = p; p += pl.w1;
+  b.c2.wpack = p; p += pl.w2;
+  b.c3.wpack = p; p += pl.w3;
+  b.flags = reinterpret_cast<uint32_t*>(p);
+  // parameters in creation order: each kernel (k, cin, cout) then its bias (nn_core_operator.py:61-75)
+  const float* w = params;
+  b.c1.w = w; b.c1.bias = w + (int64_t)k_plain * wide * narrow; w = b.c1.bias + narrow;
+  b.c2.w = w; b.c2.bias = w + (int64_t)k_dilated * narrow * narrow; w = b.c2.bias + narrow;
+  b.c3.w = w; b.c3.bias = w + (int64_t)k_plain * narrow * wide;
+  NSC_TRY(plane_from_f32(x, 1, B, L, wide, b.c1.in, st));
+  NSC_TRY(plane_pack_weights(b.c1, st));
+  NSC_TRY(plane_pack_weights(b.c2, st));
+  NSC_TRY(plane_pack_weights(b.c3, st));
+  if (!force_unfused && plane_block_supported(b)) {
+    NSC_CUDA_OK(cudaMemsetAsync(b.flags, 0, (size_t)pl.flag_bytes, st));
+    NSC_TRY(plane_block_launch(b, st));
+    if (fused_out) *fused_out = 1;
+  } else {   // an odd number of tiles (CTA pairs need an even one): the same three kernels, one launch each
+    NSC_TRY(plane_launch(b.c1, st));
+    NSC_TRY(plane_launch(b.c2, st));
+    NSC_TRY(plane_launch(b.c3, st));
+  }
+  NSC_TRY(plane_to_f32(b.c3.out, y, 1, B, L, wide, st));
+  return NSC_OK;
+}
+
+/* per-CTA counters of the most recent fused block launch (NSC_BLOCK_STATS=1): 8 words per CTA, see plane_conv.cu */
+int nsc_debug_block_stats(unsigned long long* out_host, int32_t max_ctas) {
+  NSC_CHECK_ARG(out_host != nullptr && max_ctas >= 1, "nsc_debug_block_stats: bad arguments");
+  const int n = max_ctas < nsc::kStatCtas ? max_ctas : nsc::kStatCtas;
+  NSC_CUDA_OK(cudaDeviceSynchronize());
+  NSC_CUDA_OK(cudaMemcpyFromSymbol(out_host, nsc::g_block_stats, sizeof(unsigned long long) * n * nsc::kStatWords));
+  return n;
 }
 
 }  // extern "C"

@@ -21,6 +21,24 @@ from . import constants as _c
 
 _lib.load()   # fail loudly at import time if the CUDA library is missing
 
+# Conv arithmetic of the surface functions, same modes as CodecConfig.precision:
+#   'tc_f16x3' (default)  tcgen05 tensor cores, fp16 hi/lo split, fp32 accumulate: fp32-class results (<= 1e-4, tests/test_gpu_plane.py)
+#   'tc_f16'              tcgen05, plain fp16 inputs: REDUCED precision, stated separately
+#   'fp32'                CUDA-core FFMA
+# Shapes the tensor engine does not cover (anything but the codec's layer shapes) run on the FFMA engine in every mode.
+_ENGINE = 'tc_f16x3'
+_PRECISION_CODE = {'tc_f16x3': 1, 'tc_f16': 2}
+last_engine = None      # 'tc' / 'tc_fused' / 'ffma': which engine the most recent conv-bearing call ran on (for tests)
+
+
+def set_engine(name: str) -> str:
+    """Selects the conv arithmetic of conv1d / change_channel / the_bottleneck; returns the previous setting."""
+    global _ENGINE
+    if name not in ('tc_f16x3', 'tc_f16', 'fp32'):
+        raise ValueError(f"unknown engine {name!r}")
+    prev, _ENGINE = _ENGINE, name
+    return prev
+
 
 def _act_code(activation) -> int:
     if activation is None:
@@ -53,11 +71,26 @@ def conv1d(inputs, num_filters, filter_size, padding='SAME', dilation_rate=1, st
     if tuple(w.shape) != (filter_size, cin, num_filters) or tuple(b.shape) != (num_filters,):
         raise ValueError(f"conv1d params {tuple(w.shape)}/{tuple(b.shape)} do not match "
                          f"({filter_size},{cin},{num_filters})")
+    global last_engine
     y = torch.empty((B, _same_out(L, strides), num_filters), dtype=torch.float32, device=x.device)
-    rc = _lib.load().nsc_conv1d(_lib.ptr(x), _lib.ptr(_lib.require_f32(w, 'kernel')), _lib.ptr(_lib.require_f32(b, 'bias')),
-                                _lib.ptr(y), B, L, cin, num_filters, filter_size, dilation_rate, strides,
-                                _act_code(activation), _lib.stream_ptr())
+    lib = _lib.load()
+    w, b = _lib.require_f32(w, 'kernel'), _lib.require_f32(b, 'bias')
+    prec = _PRECISION_CODE.get(_ENGINE)
+    if prec is not None and B > 0 and (num_filters == 1 or _act_code(activation) != _lib.ACT_TANH):
+        # the codec's layer shapes run on the tensor engine (the same kernels the whole-codec entry points launch)
+        ws_bytes = lib.nsc_conv1d_tc_workspace_bytes(B, L, cin, num_filters, filter_size, dilation_rate, strides, 0, 1, prec)
+        if ws_bytes > 0:
+            ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
+            rc = lib.nsc_conv1d_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), None, _lib.ptr(y), B, L, cin, num_filters, filter_size,
+                                   dilation_rate, strides, _act_code(activation), 0, _lib.ACT_NONE, 1, prec, _lib.ptr(ws), ws_bytes,
+                                   _lib.stream_ptr())
+            _lib.check(rc, 'conv1d')
+            last_engine = 'tc'
+            return y
+    rc = lib.nsc_conv1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), B, L, cin, num_filters, filter_size, dilation_rate,
+                        strides, _act_code(activation), _lib.stream_ptr())
     _lib.check(rc, 'conv1d')
+    last_engine = 'ffma'
     return y
 
 
@@ -108,12 +141,28 @@ def _flatten_params(params, n_expected: int) -> torch.Tensor:
     return torch.cat([_lib.require_f32(t, 'param').reshape(-1) for t in flat])
 
 
-def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rate, is_last_flat, gated, params):
+def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rate, is_last_flat, gated, params, fused=True):
     x = _check_cl(the_input, 'the_input')
     B, L, cin = x.shape
     flat = _flatten_params(params, 8 if gated else 6)
+    global last_engine
     y = torch.empty((B, L, wide_layer), dtype=torch.float32, device=x.device)
     lib = _lib.load()
+    prec = _PRECISION_CODE.get(_ENGINE)
+    if prec is not None and not gated and B > 0 and cin == wide_layer:
+        # the fused block kernel of the codec path (one launch: three CTA roles, intermediates through L2-resident rings)
+        ws_bytes = lib.nsc_bottleneck_block_tc_workspace_bytes(B, L, wide_layer, narrow_layer, prec)
+        if ws_bytes > 0 and k_plain == 9 and k_dilated == 9 and dilation_rate in (1, 2):
+            import ctypes as C
+            ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
+            fused = C.c_int32(0 if fused else -1)
+            rc = lib.nsc_bottleneck_block_tc(_lib.ptr(x), _lib.ptr(flat), _lib.ptr(y), B, L, wide_layer, narrow_layer, k_plain, k_dilated,
+                                             dilation_rate, int(bool(is_last_flat)), prec, C.byref(fused), _lib.ptr(ws), ws_bytes,
+                                             _lib.stream_ptr())
+            _lib.check(rc, 'the_bottleneck')
+            last_engine = 'tc_fused' if fused.value else 'tc'
+            return y
+    last_engine = 'ffma'
     ws_bytes = lib.nsc_block_workspace_bytes(B, L, wide_layer, narrow_layer)
     ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)
     rc = lib.nsc_bottleneck_block(_lib.ptr(x), _lib.ptr(flat), _lib.ptr(y), B, L, cin, wide_layer, narrow_layer, k_plain,
@@ -124,10 +173,11 @@ def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rat
 
 
 def the_bottleneck(the_input, wide_layer=30, narrow_layer=10, non_dilated_neck_kernel_size=9,
-                   dilated_neck_kernel_size=9, dilation_rate=1, is_last_flat=False, *, params):
-    """nn_core_operator.py:57-79.  params = [(w1,b1), (w2,b2), (w3,b3)]."""
+                   dilated_neck_kernel_size=9, dilation_rate=1, is_last_flat=False, *, params, fused=True):
+    """nn_core_operator.py:57-79.  params = [(w1,b1), (w2,b2), (w3,b3)].
+    On the tensor engine the block is ONE fused launch (`fused=False`: the same three kernels, one launch each -- tests)."""
     return _block(the_input, wide_layer, narrow_layer, non_dilated_neck_kernel_size, dilated_neck_kernel_size,
-                  dilation_rate, is_last_flat, False, params)
+                  dilation_rate, is_last_flat, False, params, fused)
 
 
 def gated_bottleneck(the_input, wide_layer=30, narrow_layer=10, non_dilated_neck_kernel_size=9,

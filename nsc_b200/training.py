@@ -6,9 +6,12 @@ Mirrors the loss assembly and optimiser of the reference graphs -- not their epo
 Facts reproduced: soft value path; per-frame loss VECTORS whose SUM is differentiated; the scalar entropy term counted
 once per frame of the (global) batch; no gradient through lsf2poly / residual / synthesis; res_x is fed; TF1 Adam.
 
-Multi-GPU: one process per GPU, frames sharded by rank.  Two collectives per step, both SUM all-reduces over
-torch.distributed (NCCL on B200): the soft histograms (a few hundred floats, BEFORE the backward pass so the batch-global
-entropy is exact) and the flat gradient buffers (<1 M floats per codec).
+Multi-GPU: one process per GPU, frames sharded by rank (equal shard sizes).  Every codec's gradient, the LSF codebook's gradient
+and the soft histograms live in ONE flat fp32 buffer (< 1 M floats) that is SUM all-reduced ONCE per step over torch.distributed
+(NCCL on B200) -- `collectives_per_step == 1`.  Only when an entropy weight is non-zero (one_ae_lpc; `_finetuning_lpc` drops the
+term, cmrl.py:485) does the backward pass need the batch-GLOBAL histograms before it starts (the entropy is a function of the global
+histogram); then the few hundred histogram floats are all-reduced ahead of it (`collectives_per_step == 2`).
+Nothing in the step synchronises the host: the global batch is world_size x the per-rank batch.
 """
 from __future__ import annotations
 
@@ -44,12 +47,32 @@ class CQTrainer:
         self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
         self.t = 0
         dev = cmrl.lsf_params.device
-        self.grads = [torch.zeros_like(c.params) for c in cmrl.codecs]
-        self.lsf_grad = torch.zeros_like(cmrl.lsf_params)
+        # ONE flat buffer: [codec 0 grads | codec 1 grads | ... | LSF codebook grads | LSF histogram | codec histograms]
+        sizes = [c.params.numel() for c in cmrl.codecs] + [cmrl.lsf_params.numel()]
+        hsizes = [cmrl.n_lsf_bins] + [c.cfg.num_bins for c in cmrl.codecs]
+        # (every segment starts on a 256-byte boundary, like the separately allocated tensors it replaces; the padding stays zero)
+        al = lambda v: (v + 63) // 64 * 64
+        self._n_grad = sum(al(sz) for sz in sizes)
+        self.flat = torch.zeros(self._n_grad + sum(al(sz) for sz in hsizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for sz in sizes + hsizes:
+            views.append(self.flat[off:off + sz]); off += al(sz)
+        self.grads = views[:n]
+        self.lsf_grad = views[n]
+        self.hists = views[n + 1:]
         self.m = [torch.zeros_like(c.params) for c in cmrl.codecs] + [torch.zeros_like(cmrl.lsf_params)]
         self.v = [torch.zeros_like(c.params) for c in cmrl.codecs] + [torch.zeros_like(cmrl.lsf_params)]
         self._ws: Optional[torch.Tensor] = None
         self._dev = dev
+
+    @property
+    def needs_global_hist(self) -> bool:
+        """The backward pass differentiates tau * entropy(global histogram) only when an entropy weight is non-zero."""
+        return any(w != 0.0 for w in self.ent_w)
+
+    @property
+    def collectives_per_step(self) -> int:
+        return 0 if not _dist_on() else (2 if self.needs_global_hist else 1)
 
     @staticmethod
     def one_ae_lpc(cmrl: CMRL, coeff_term=(60.0, 10.0, 10.0, 0.0), is_cq: bool = True, **kw) -> "CQTrainer":
@@ -88,22 +111,19 @@ class CQTrainer:
         time_l = torch.empty(B, dtype=torch.float32, device=dev)
         freq_l = torch.empty(B, dtype=torch.float32, device=dev)
         qloss = [torch.empty(B, dtype=torch.float32, device=dev) for _ in range(n + 1)]
-        hists = [torch.zeros(cm.n_lsf_bins, dtype=torch.float32, device=dev)] + \
-                [torch.zeros(c.cfg.num_bins, dtype=torch.float32, device=dev) for c in cm.codecs]
+        hists = self.hists
+        self.flat[self._n_grad:].zero_()
         params = _lib.ptr_array([c.params for c in cm.codecs])
         rc = lib.nsc_train_forward(cm._cfgs, n, params, _lib.ptr(cm.lsf_params), cm.n_lsf_bins, _lib.ptr(x), _lib.ptr(lsf), B,
                                    cm.res_scalar, float(is_quan_on), _lib.ptr(melw), _lib.ptr(decoded), _lib.ptr(time_l),
                                    _lib.ptr(freq_l), _lib.ptr_array(qloss), _lib.ptr_array(hists), _lib.ptr(ws), ws.numel(),
                                    _lib.stream_ptr())
         _lib.check(rc, 'nsc_train_forward')
-        global_B = B
-        if _dist_on():
-            flat = torch.cat(hists + [torch.tensor([float(B)], device=dev)])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)            # batch-global soft histograms (exact entropy under DP)
-            off = 0
-            for h in hists:
-                h.copy_(flat[off:off + h.numel()]); off += h.numel()
-            global_B = int(round(float(flat[-1])))
+        # equal shards: the global batch needs no collective and no host synchronisation
+        global_B = B * (dist.get_world_size() if _dist_on() else 1)
+        hists_early = _dist_on() and self.needs_global_hist
+        if hists_early:
+            dist.all_reduce(self.flat[self._n_grad:], op=dist.ReduceOp.SUM)   # batch-global soft histograms BEFORE the backward pass
         coeff = (C.c_float * 4)(self.c[0], self.c[1], self.c[2], tau)
         qw = (C.c_float * (n + 1))(*self.quan_w)
         ew = (C.c_float * (n + 1))(*self.ent_w)
@@ -114,13 +134,13 @@ class CQTrainer:
                                     ws.numel(), _lib.stream_ptr())
         _lib.check(rc, 'nsc_train_backward')
         if _dist_on():
-            for g in self.grads + [self.lsf_grad]:
-                dist.all_reduce(g, op=dist.ReduceOp.SUM)           # the single gradient all-reduce of the step (SUM, not mean)
+            # THE all-reduce of the step (SUM, not mean): all gradients -- and the histograms when the backward did not need them
+            dist.all_reduce(self.flat[:self._n_grad] if hists_early else self.flat, op=dist.ReduceOp.SUM)
         ent = [entropy_from_hist(h) for h in hists]
         quan = sum(w * q for w, q in zip(self.quan_w, qloss))
         ent_term = sum(w * e for w, e in zip(self.ent_w, ent))
         return {'decoded': decoded, 'time_loss': time_l, 'freq_loss': freq_l, 'quan_loss': quan, 'ent_loss': ent_term,
-                'entropies': ent, 'hists': hists, 'global_batch': global_B,
+                'entropies': ent, 'hists': [h.clone() for h in hists], 'global_batch': global_B,
                 'loss_vector': self.c[0] * time_l + self.c[1] * freq_l + self.c[2] * quan + tau * ent_term}
 
     def apply_adam(self, lr: Optional[float] = None) -> None:

@@ -51,7 +51,7 @@ def test_layer_table_matches_oracle_creation_order(rt, st):
 
 
 def test_pack_params_roundtrip():
-    cfg = codec.CodecConfig()
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
     oc = ref_codec.OracleCodec(ref_codec.OracleCodecCfg(), seed=3)
     flat = codec.pack_params_numpy(cfg, oc.conv_params, oc.alpha, oc.bins)
     tab = codec.layer_table(cfg)
@@ -69,11 +69,11 @@ def test_from_args_matches_readme_flags():
 
 def test_invalid_config_is_reported_not_crashed():
     lib = _lib.load()
-    st = codec.CodecConfig().to_struct()
+    st = codec.CodecConfig(resnet_type='bottleneck').to_struct()
     st.num_bins = 1000
     assert lib.nsc_codec_param_count(C.byref(st)) == -1
     assert 'num_bins' in _lib.last_error()
-    st = codec.CodecConfig().to_struct()
+    st = codec.CodecConfig(resnet_type='bottleneck').to_struct()
     st.wide = 101          # decoder channels not divisible by the stride (nscm.py:187 assert)
     assert lib.nsc_codec_workspace_bytes(C.byref(st), 4) == -1
     with pytest.raises(ValueError):

@@ -32,7 +32,7 @@ def test_import_matches_oracle_parameter_stream(rt, st):
 
 
 def test_import_errors():
-    cfg = codec.CodecConfig()
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
     with pytest.raises(KeyError):
         ck.params_from_tf_variables(cfg, 'scope_1', {})
     oc = ref_codec.OracleCodec(ref_codec.OracleCodecCfg(), seed=1)

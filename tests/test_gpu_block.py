@@ -1,0 +1,131 @@
+"""The fused bottleneck block (ONE launch, three CTA roles, intermediates through L2-resident rings; plane_conv.cu) against the
+oracle's the_bottleneck (nn_core_operator.py:57-79), against the same three kernels launched one by one (bit-identical), at batch
+sizes below, at and far above the ring size (slot reuse and back-pressure), through the operator surface and the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_nn
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _params(wide, dil, seed):
+    ps = ref_nn.ParamStream(seed=seed)
+    x1 = torch.zeros(1, 128, wide)
+    ref_nn.the_bottleneck(x1, wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, ps=ps)
+    return ps
+
+
+@pytest.mark.parametrize('B,L,wide,dil,flat', [(2, 512, 100, 1, False), (2, 512, 100, 2, True), (4, 256, 100, 2, False),
+                                               (2, 512, 50, 1, False), (6, 512, 50, 2, True), (3, 512, 100, 1, False)])
+def test_fused_block_vs_oracle(B, L, wide, dil, flat):
+    from nsc_b200 import nn_core_operator as nn
+    ps = ref_nn.ParamStream(seed=wide + dil)
+    x = np.random.RandomState(8).randn(B, L, wide).astype(np.float32)
+    ref = ref_nn.the_bottleneck(torch.from_numpy(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=flat, ps=ps).numpy()
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    got = nn.the_bottleneck(cu(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=flat, params=params)
+    torch.cuda.synchronize()
+    assert nn.last_engine == 'tc_fused'          # every case has an even number of tiles
+    assert rel_err(got.cpu().numpy(), ref) < 5e-5
+    # per-frame error (a quiet frame must not hide behind a loud one)
+    g, r = got.cpu().numpy(), ref
+    per = np.abs(g - r).reshape(B, -1).max(1) / np.abs(r).reshape(B, -1).max(1)
+    assert per.max() < 5e-5
+
+
+@pytest.mark.parametrize('B,L,wide,dil', [(127, 512, 100, 2), (128, 256, 100, 1), (700, 512, 100, 1), (1000, 256, 100, 2), (518, 512, 50, 2)])
+def test_fused_block_equals_three_launches(B, L, wide, dil):
+    """Ring wrap-around and back-pressure: far more frames than ring slots; the fused launch and the three separate launches run
+    the same kernels on the same data, so every bit must agree."""
+    from nsc_b200 import nn_core_operator as nn
+    ps = _params(wide, dil, seed=3)
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    x = cu(np.random.RandomState(B).randn(B, L, wide).astype(np.float32))
+    a = nn.the_bottleneck(x, wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, params=params)
+    assert nn.last_engine == 'tc_fused'
+    b = nn.the_bottleneck(x, wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, params=params, fused=False)
+    assert nn.last_engine == 'tc'
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # and both are the oracle's block (spot check on a few frames spread over the batch)
+    sel = [0, B // 3, B - 1]
+    ps2 = ref_nn.ParamStream(seed=3)
+    ref = ref_nn.the_bottleneck(x[sel].cpu(), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, ps=ps2).numpy()
+    assert rel_err(a[sel].cpu().numpy(), ref) < 5e-5
+
+
+def test_fused_block_repeated_launches_are_deterministic():
+    from nsc_b200 import nn_core_operator as nn
+    ps = _params(100, 2, seed=5)
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    x = cu(np.random.RandomState(1).randn(300, 512, 100).astype(np.float32))
+    outs = [nn.the_bottleneck(x, wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=True, params=params) for _ in range(4)]
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def test_odd_tile_count_takes_the_three_launch_form():
+    from nsc_b200 import nn_core_operator as nn
+    ps = _params(100, 1, seed=6)
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    x = np.random.RandomState(2).randn(3, 256, 100).astype(np.float32)     # 3 tiles of 256 positions
+    got = nn.the_bottleneck(cu(x), wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=False, params=params)
+    assert nn.last_engine == 'tc'
+    ps2 = ref_nn.ParamStream(seed=6)
+    ref = ref_nn.the_bottleneck(torch.from_numpy(x), wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=False, ps=ps2).numpy()
+    assert rel_err(got.cpu().numpy(), ref) < 5e-5
+
+
+def test_surface_engine_switch():
+    """set_engine('fp32') keeps the CUDA-core path reachable; both engines meet the fp32 bar."""
+    from nsc_b200 import nn_core_operator as nn
+    ps = _params(100, 1, seed=7)
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    x = cu(np.random.RandomState(3).randn(2, 512, 100).astype(np.float32))
+    a = nn.the_bottleneck(x, wide_layer=100, narrow_layer=20, params=params)
+    prev = nn.set_engine('fp32')
+    try:
+        b = nn.the_bottleneck(x, wide_layer=100, narrow_layer=20, params=params)
+        assert nn.last_engine == 'ffma'
+    finally:
+        nn.set_engine(prev)
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5
+
+
+def test_codec_program_with_fused_blocks_is_bit_identical():
+    """NSC_BLOCK_FUSED=1 (read once per process, hence the subprocess): the whole codec with every bottleneck block as ONE fused launch
+    gives the same bits as the default program (one launch per conv) -- codes and decoder output, more frames than ring slots."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+            "from nsc_b200 import codec, _lib\n"
+            "from util import ar_frames\n"
+            "cfg = codec.CodecConfig(resnet_type='bottleneck'); gc = codec.NeuralCodec(cfg, device='cuda', seed=9)\n"
+            "x = torch.from_numpy(ar_frames(300, 512, seed=4, std=0.3)).cuda()\n"
+            "l0 = _lib.load().nsc_launch_count()\n"
+            "r = gc.computational_graph_end2end_quan_on(x, False, 1.0)\n"
+            "torch.cuda.synchronize()\n"
+            "np.savez(sys.argv[1], idx=r['idx'].cpu().numpy(), out=r['out'].cpu().numpy(), launches=_lib.load().nsc_launch_count() - l0)\n")
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for mode in ('0', '1'):
+            path = os.path.join(td, f'o{mode}.npz')
+            env = dict(os.environ, NSC_BLOCK_FUSED=mode)
+            subprocess.run([sys.executable, '-c', code, path], check=True, env=env, timeout=300)
+            res[mode] = dict(np.load(path))
+    assert np.array_equal(res['0']['idx'], res['1']['idx'])
+    assert np.array_equal(res['0']['out'], res['1']['out'])
+    assert int(res['1']['launches']) == int(res['0']['launches']) - 2 * 7      # 7 blocks: three launches -> one

@@ -345,9 +345,11 @@ def test_codec_golden_fixture():
         oc, gc = _make_pair(rt, st, seed=3)
         r = gc.computational_graph_end2end_quan_on(cu(g[name + '_x']), False, 1.0)
         assert rel_err(r['floating_code'].cpu().numpy(), g[name + '_floating']) < TOL
+        # the fixture's inputs sit away from quantiser boundaries (tests/golden/make_golden.py), so every hard code must agree --
+        # a flipped code fails here instead of silently skipping the decoder check
         same = r['code'].cpu().numpy() == g[name + '_code']
-        if same.all():
-            assert rel_err(r['out'].cpu().numpy(), g[name + '_out']) < TOL
+        assert same.all(), f"{name}: {int((~same).sum())} of {same.size} hard codes differ from the golden fixture"
+        assert rel_err(r['out'].cpu().numpy(), g[name + '_out']) < TOL
 
 
 def test_codec_encode_decode_split_equals_fused_and_chunking():

@@ -41,7 +41,7 @@ def _oracle_pipeline(x, ocs, bins, the_share):
 def test_code_utterances_matches_oracle_composition():
     from nsc_b200 import codec, pipeline
     ocfg = ref_codec.OracleCodecCfg()
-    cfg = codec.CodecConfig()
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
     ocs = [ref_codec.OracleCodec(ocfg, seed=5), ref_codec.OracleCodec(ocfg, seed=6)]
     gcs = [codec.NeuralCodec(cfg, torch.from_numpy(codec.pack_params_numpy(cfg, o.conv_params, o.alpha, o.bins)).to(DEV)) for o in ocs]
     cm = codec.CMRL(gcs, res_scalar=1.0)
@@ -57,7 +57,7 @@ def test_code_utterances_matches_oracle_composition():
 
 def test_hard_codes_pack_and_survive_the_round_trip():
     from nsc_b200 import bitstream, codec, pipeline
-    cfg = codec.CodecConfig()
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
     cm = codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=5), codec.NeuralCodec(cfg, device=DEV, seed=6)], res_scalar=1.0)
     sigs = [torch.from_numpy(_utterance(16000, 3)).to(DEV)]
     out = pipeline.code_utterances(cm, sigs, the_share=False, pack=True)[0]

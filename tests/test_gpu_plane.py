@@ -161,7 +161,7 @@ def test_unsupported_shape_fails_loudly():
 # ------------------------------------------------------------------------------------------------ full-size properties
 def _cq2(seed0=5, seed1=6, precision='tc_f16x3'):
     from nsc_b200 import codec
-    cfg = codec.CodecConfig(precision=precision)
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=precision)
     return codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=seed0), codec.NeuralCodec(cfg, device=DEV, seed=seed1)], res_scalar=1.0)
 
 
@@ -211,7 +211,7 @@ def test_plane_path_matches_layer_by_layer_engine_at_full_size(monkeypatch):
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "from util import ar_frames\n"
         "from nsc_b200 import codec\n"
-        "cfg = codec.CodecConfig(); gc = codec.NeuralCodec(cfg, device='cuda', seed=9)\n"
+        "cfg = codec.CodecConfig(resnet_type='bottleneck'); gc = codec.NeuralCodec(cfg, device='cuda', seed=9)\n"
         "x = torch.from_numpy(ar_frames(1000, 512, seed=79, std=0.3)).cuda()\n"
         "r = gc.computational_graph_end2end_quan_on(x, True, 1.0)\n"
         "np.save(sys.argv[1], np.concatenate([r['floating_code'].cpu().numpy().ravel(), r['out'].cpu().numpy().ravel()]))\n"

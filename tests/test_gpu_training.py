@@ -26,7 +26,7 @@ def lsf_bins():
 def make_models(n_codecs, alpha, precision='fp32', seeds=(5, 6, 7)):
     from nsc_b200 import codec
     ocfg = ref_codec.OracleCodecCfg()
-    cfg = codec.CodecConfig(precision=precision)
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=precision)
     ocs, gcs = [], []
     for i in range(n_codecs):
         oc = ref_codec.OracleCodec(ocfg, seed=seeds[i], alpha=alpha)

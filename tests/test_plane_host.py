@@ -88,8 +88,8 @@ def test_cta_pairs_need_an_even_number_of_work_units():
 
 def test_codec_workspace_sizes_on_the_plane_path():
     lib = _lib.load()
-    cfg = codec.CodecConfig(precision='tc_f16x3').to_struct()
-    cfg32 = codec.CodecConfig(precision='fp32').to_struct()
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision='tc_f16x3').to_struct()
+    cfg32 = codec.CodecConfig(resnet_type='bottleneck', precision='fp32').to_struct()
     import ctypes as C
     one = lib.nsc_codec_workspace_bytes(C.byref(cfg), 1)
     big = lib.nsc_codec_workspace_bytes(C.byref(cfg), 100000)

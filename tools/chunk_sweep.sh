@@ -1,17 +1,19 @@
 #!/bin/bash
-# Frames-per-pass sweep of the plane path (NSC_PLANE_CHUNK): per-launch fill/drain overhead vs workspace size.
-#   tools/chunk_sweep.sh  ->  gpurun_out/chunk_sweep.log  (one bench line per chunk size)
-set -u
-mkdir -p gpurun_out
-: > gpurun_out/chunk_sweep.log
-for c in 2072 4144 8288 16576; do
-  echo "== NSC_PLANE_CHUNK=$c" >> gpurun_out/chunk_sweep.log
-  NSC_PLANE_CHUNK=$c timeout 300 python bench.py --frames 33152 --steps 3 --warmup 3 --no-cpu-baseline >> gpurun_out/chunk_sweep.log 2>&1
-done
-python - <<'PY'
-import json
-for line in open('gpurun_out/chunk_sweep.log'):
-    if line.startswith('=='): print(line.strip()); continue
-    if line.startswith('{'):
-        d = json.loads(line); print(round(d['value']), d['ms_per_step'], d['e2e']['value'])
-PY
+out=gpurun_out/r02_chunk_sweep.log
+: > $out
+run() {
+  echo "=== $*" >> $out
+  env "$@" timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-sub-records 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+kb=d['kernel_breakdown']
+print('ms/step', round(d['ms_per_step'],2), 'xRT', round(d['value']), 'e2e', round(d['e2e']['value']), 'sm_mhz', d['clocks']['sm_mhz'], 'launches', d['gpu_launches'])
+print('   blocks', round(sum(v['ms'] for k,v in kb.items() if k.startswith('pB')),2), 'unfused convs of blocks', round(sum(v['ms'] for k,v in kb.items() if k.startswith(('pT2_k9','pX2_k9d1s1_c20'))),2))
+" >> $out 2>&1
+}
+run NSC_BLOCK_FUSED=0
+run NSC_BLOCK_FUSED=1
+run NSC_BLOCK_FUSED=1 NSC_PLANE_CHUNK=4144
+run NSC_BLOCK_FUSED=1 NSC_PLANE_CHUNK=8288
+run NSC_BLOCK_FUSED=0 NSC_PLANE_CHUNK=4144
+cat $out

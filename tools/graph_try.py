@@ -3,7 +3,7 @@ sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 from util import ar_frames
 from nsc_b200 import codec, lpc_utilities as lu
 dev='cuda'
-cfg=codec.CodecConfig()
+cfg=codec.CodecConfig(resnet_type='bottleneck')
 cm=codec.CMRL([codec.NeuralCodec(cfg,device=dev,seed=5),codec.NeuralCodec(cfg,device=dev,seed=6)],res_scalar=1.0)
 for B in (1,128,1024):
     win=torch.from_numpy(ar_frames(B,1024,seed=1)).to(dev); x=win[:,256:768].contiguous()

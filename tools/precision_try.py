@@ -5,7 +5,7 @@ from oracle import ref_codec
 from util import ar_frames, rel_err
 from nsc_b200 import codec
 import test_gpu_parity as tp
-ocfg=ref_codec.OracleCodecCfg(); cfg=codec.CodecConfig(precision=sys.argv[1] if len(sys.argv)>1 else 'tc_f16x3')
+ocfg=ref_codec.OracleCodecCfg(); cfg=codec.CodecConfig(resnet_type='bottleneck', precision=sys.argv[1] if len(sys.argv)>1 else 'tc_f16x3')
 for seed in (3,4,7):
     oc=ref_codec.OracleCodec(ocfg, seed=seed)
     gc=codec.NeuralCodec(cfg, torch.from_numpy(codec.pack_params_numpy(cfg, oc.conv_params, oc.alpha, oc.bins)).cuda())

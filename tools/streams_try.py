@@ -3,7 +3,7 @@ sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 from util import ar_frames
 from nsc_b200 import codec, lpc_utilities as lu
 dev='cuda'
-cfg=codec.CodecConfig()
+cfg=codec.CodecConfig(resnet_type='bottleneck')
 gcs=[codec.NeuralCodec(cfg,device=dev,seed=5),codec.NeuralCodec(cfg,device=dev,seed=6)]
 cmA=codec.CMRL(gcs,res_scalar=1.0); cmB=codec.CMRL(gcs,res_scalar=1.0)
 B=16576
