@@ -307,6 +307,23 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_device()
+    if args.profile_one_step:
+        # for `ncu --profile-from-start off`: exactly ONE device-resident step inside the profiler range, with the launch names in
+        # order (nsc_profile records) written beside it so that tools/ncu_facts.py can attribute ncu's rows to layers
+        torch.cuda.synchronize()
+        agg_names = []
+        lib.nsc_profile_begin(8192)
+        torch.cuda.cudart().cudaProfilerStart()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        n = C.c_int32(0)
+        names = C.create_string_buffer(8192 * 32)
+        ms = (C.c_float * 8192)(); fl = (C.c_double * 8192)(); by = (C.c_double * 8192)()
+        lib.nsc_profile_end(C.byref(n), names, ms, fl, by, 8192)
+        recs = [{"name": names.raw[i * 32:(i + 1) * 32].split(b'\0')[0].decode(), "ms": ms[i], "flops": fl[i], "bytes": by[i]} for i in range(n.value)]
+        json.dump({"frames": B, "records": recs}, open(args.profile_one_step, 'w'))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -336,6 +353,8 @@ def run_ours(args):
         subrec = {}
         for name, fn in (("codec1_b128", lambda: measure_codec1(args, world, rank, dev, lib, cpu=not args.no_cpu_baseline)),
                          ("cq_scaled", lambda: measure_cq_sweep(args, world, rank, dev, lib)),
+                         ("cq2_gln", lambda: measure_variant(args, world, rank, dev, lib, 'gln', (2,))),
+                         ("cq2_stride4", lambda: measure_variant(args, world, rank, dev, lib, 'bottleneck', (2, 2))),
                          ("train", lambda: measure_train(args, world, rank, dev, lib, 20, 5, breakdown=True)),
                          ("corpus_1h_per_gpu", lambda: measure_corpus(args, world, rank, dev, lib, 2, 1, n_utt=360))):
             try:
@@ -598,6 +617,38 @@ def measure_codec1(args, world, rank, dev, lib, cpu=True):
     return rec
 
 
+def measure_variant(args, world, rank, dev, lib, resnet_type, strides, frames=4144):
+    """The reference's SHIPPED switches (constants.py:14 resnet_type = 'gln'; the_strides '4' -> [2, 2], cmrl.py:804) on the same
+    CQ 2-codec workload.  These topologies run on the layer-by-layer engines (first tensor engine: fp16 hi/lo split, fp32 activations
+    between layers; the k55 stem / heads and the separable up-conv on CUDA cores), not on the plane engine."""
+    import torch
+    from nsc_b200 import codec, lpc_utilities as lu
+    cfg = codec.CodecConfig(resnet_type=resnet_type, the_strides=strides, precision=args.precision)
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5 + i) for i in range(2)], res_scalar=1.0)
+    B = frames
+    x_np, win_np = synth_audio(min(B, 2072), seed=55 + rank)
+    reps = -(-B // x_np.shape[0])
+    xd = torch.from_numpy(np.tile(x_np, (reps, 1))[:B]).to(dev)
+    wd = torch.from_numpy(np.tile(win_np, (reps, 1))[:B]).to(dev)
+
+    def step():
+        cm.feedforward_lpc(xd, lu.lpc_analysis_windows(wd, 16, dtype=torch.float32), False, 1.0)
+
+    for _ in range(3):
+        step()
+    n = 5
+    t = _timed(step, n, world, dev)
+    agg = kernel_breakdown(lib, step)
+    fl = sum(v[1] for v in agg.values())
+    ms = sum(v[0] for v in agg.values())
+    hbm, bf16, bf16_sus, how = peaks()
+    return {"workload": f"cq2 with resnet_type '{resnet_type}', strides {list(strides)}: LPC + LSF codebook + 2 codecs + synthesis, hard codes, "
+                        f"{B} frames per GPU", "value": B * world * n * SEC_PER_FRAME / t, "unit": "x real-time", "ms_per_call": t / n * 1e3,
+            "engine": "layer-by-layer (first tensor engine tcgen05 fp16 hi/lo + CUDA-core stem/heads/depthwise)",
+            "tflops_algorithmic": fl / (ms * 1e-3) / 1e12, "tensor_frac_of_measured_bf16_sustained": fl / (ms * 1e-3) / 1e12 / bf16_sus,
+            "top_kernels": {k: {"ms": round(v[0], 3), "launches": v[3]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:6]}}
+
+
 def measure_cq_sweep(args, world, rank, dev, lib):
     """BASELINE.json configs[2]: CQ scaled towards 24 kbps -- more cascaded codecs and bins -- batch-size sweep, encode+decode,
     device-resident and end-to-end."""
@@ -656,6 +707,8 @@ def main():
     ap.add_argument('--utterances', type=int, default=360, help='corpus workload: utterances per GPU')
     ap.add_argument('--utt-seconds', type=float, default=10.0, help='corpus workload: seconds per utterance')
     ap.add_argument('--train-batch', type=int, default=128, help='frames per GPU per training step')
+    ap.add_argument('--profile-one-step', default=None, metavar='JSON',
+                    help="profiling aid: warm up, run ONE step inside cudaProfilerStart/Stop, write the launch names to JSON, exit")
     ap.add_argument('--no-sub-records', dest='sub_records', action='store_false',
                     help="skip the bounded sub-records (codec1 batch 128, scaled CQ sweep, training step, 1-hour corpus) of the default run")
     ap.add_argument('--precision', default='tc_f16x3', choices=['fp32', 'tc_f16x3', 'tc_f16'],

@@ -8,9 +8,15 @@ maintainer dumps on a TensorFlow machine with
     np.savez('nsc_vars.npz', **{n: r.get_tensor(n) for n in r.get_variable_to_shape_map()})
 
 [LIB] variable names of `tf.compat.v1.layers.conv1d` inside `variable_scope(scope)`: the i-th conv created in the scope is
-``<scope>/conv1d/{kernel,bias}`` for i = 0 and ``<scope>/conv1d_<i>/{kernel,bias}`` after that; Keras SeparableConv1D:
-``<scope>/separable_conv1d[_<j>]/{depthwise_kernel,pointwise_kernel,bias}``; quantiser variables ``<scope>/alpha``,
-``<scope>/bins`` (nscm.py:267-269, :305-308); the LSF codebook lives in scope ``lpc_quan`` (nscm.py:994-997).
+``<scope>/conv1d/{kernel,bias}`` for i = 0 and ``<scope>/conv1d_<i>/{kernel,bias}`` after that (names are uniquified per enclosing
+variable scope).  Keras `SeparableConv1D` (the 'gln' up-conv, nscm.py:175-177) is different: Keras layer names are uniquified per
+GRAPH, not per variable scope, so in a multi-codec graph (cmrl.py all_modules_feedforward[_lpc], follower training) the j-th
+separable conv created ANYWHERE in the graph is ``<scope>/separable_conv1d[_<j>]/{depthwise_kernel,pointwise_kernel,bias}`` --
+codec 2's up-conv is ``scope_2/separable_conv1d_1`` (and further suffixes with the_strides = '4').  `sep_start` carries that
+running count; `params_from_tf_variables` additionally resolves the layer by pattern inside the scope when the exact name is absent.
+UNVERIFIED against a real TensorFlow 2.0 dump (TensorFlow is not installable here): derived from TF's naming rules.
+Quantiser variables ``<scope>/alpha``, ``<scope>/bins`` (nscm.py:267-269, :305-308); the LSF codebook lives in scope
+``lpc_quan`` (nscm.py:994-997).
 Adam slot variables (``.../Adam``, ``.../Adam_1``) are ignored, like the reference's stage-to-stage restores (cmrl.py:116-119).
 
 The schedule shell reproduces the entropy controller of the training loops (nscm.py:630-639, :494-518) and the
@@ -25,9 +31,16 @@ import numpy as np
 from .codec import CodecConfig, layer_table, pack_params_numpy
 
 
-def tf_variable_names(cfg: CodecConfig, scope: str) -> List[Tuple[str, ...]]:
-    """Names of one codec's conv variables in creation order: (kernel, bias) or (depthwise, pointwise, bias) per layer."""
-    names, n_conv, n_sep = [], 0, 0
+def separable_count(cfg: CodecConfig) -> int:
+    """Separable convs one codec creates (one per up-sampling stage of a 'gln' codec) -- the increment of `sep_start` per codec."""
+    return sum(1 for spec in layer_table(cfg) if spec.separable)
+
+
+def tf_variable_names(cfg: CodecConfig, scope: str, sep_start: int = 0) -> List[Tuple[str, ...]]:
+    """Names of one codec's conv variables in creation order: (kernel, bias) or (depthwise, pointwise, bias) per layer.
+    sep_start: separable convs created EARLIER IN THE SAME GRAPH (Keras names are per graph): 0 for the first codec built,
+    separable_count(cfg_1) for the second, ..."""
+    names, n_conv, n_sep = [], 0, int(sep_start)
     for spec in layer_table(cfg):
         if spec.separable:
             base = f"{scope}/separable_conv1d" + (f"_{n_sep}" if n_sep else "")
@@ -47,10 +60,27 @@ def _get(variables: Mapping[str, np.ndarray], name: str) -> np.ndarray:
     raise KeyError(f"variable {name!r} is not in the checkpoint dump")
 
 
-def params_from_tf_variables(cfg: CodecConfig, scope: str, variables: Mapping[str, np.ndarray]) -> np.ndarray:
-    """Flat float32 parameter image (the layout of nsc_codec_layer_info) of the codec that lives in ``scope`` ('scope_1', ...)."""
+def _resolve_separable(variables: Mapping[str, np.ndarray], scope: str, nth: int) -> str:
+    """Base name of the nth (0-based, ascending suffix) separable conv that exists inside ``scope`` in the dump."""
+    import re
+    pat = re.compile(re.escape(scope) + r"/separable_conv1d(?:_(\d+))?/depthwise_kernel(?::0)?$")
+    found = sorted((int(m.group(1) or 0) for m in (pat.match(k) for k in variables) if m))
+    if nth >= len(found):
+        raise KeyError(f"separable conv #{nth} of scope {scope!r} is not in the checkpoint dump (found suffixes {found})")
+    return f"{scope}/separable_conv1d" + (f"_{found[nth]}" if found[nth] else "")
+
+
+def params_from_tf_variables(cfg: CodecConfig, scope: str, variables: Mapping[str, np.ndarray], sep_start: int = 0) -> np.ndarray:
+    """Flat float32 parameter image (the layout of nsc_codec_layer_info) of the codec that lives in ``scope`` ('scope_1', ...).
+    Separable layers are looked up under the name `sep_start` predicts and, failing that, by ascending suffix inside the scope."""
     conv = []
-    for spec, names in zip(layer_table(cfg), tf_variable_names(cfg, scope)):
+    nth_sep = 0
+    for spec, names in zip(layer_table(cfg), tf_variable_names(cfg, scope, sep_start)):
+        if spec.separable:
+            if not any(k in variables for k in (names[0], names[0] + ":0")):
+                base = _resolve_separable(variables, scope, nth_sep)
+                names = (base + "/depthwise_kernel", base + "/pointwise_kernel", base + "/bias")
+            nth_sep += 1
         arrs = [_get(variables, n).astype(np.float32) for n in names]
         want = ([(spec.k, spec.cin, 1), (1, spec.cin, spec.cout), (spec.cout,)] if spec.separable
                 else [(spec.k, spec.cin, spec.cout), (spec.cout,)])
@@ -73,10 +103,10 @@ def lsf_params_from_tf_variables(variables: Mapping[str, np.ndarray], scope: str
     return np.concatenate([[np.float32(alpha)], bins]).astype(np.float32)
 
 
-def tf_variables_from_params(cfg: CodecConfig, scope: str, params: np.ndarray) -> Dict[str, np.ndarray]:
+def tf_variables_from_params(cfg: CodecConfig, scope: str, params: np.ndarray, sep_start: int = 0) -> Dict[str, np.ndarray]:
     """Inverse of params_from_tf_variables (export towards a TensorFlow `assign`)."""
     out, p = {}, np.asarray(params, dtype=np.float32)
-    for spec, names in zip(layer_table(cfg), tf_variable_names(cfg, scope)):
+    for spec, names in zip(layer_table(cfg), tf_variable_names(cfg, scope, sep_start)):
         o = spec.offset
         shapes = ([(spec.k, spec.cin, 1), (1, spec.cin, spec.cout), (spec.cout,)] if spec.separable
                   else [(spec.k, spec.cin, spec.cout), (spec.cout,)])
@@ -114,13 +144,16 @@ class EntropyController:
         return self.tau
 
 
-def schedule(epoch: int, pretrain_step: int, update_every: int = 30) -> Dict[str, object]:
-    """What one epoch of model_training_lpc does (nscm.py:560-584): the first ``pretrain_step`` epochs minimise the loss
-    without the quantisation terms with is_quan_on = 0; CQ runs recompute all LPC residuals with the current (sorted)
-    LSF codebook every 30 epochs."""
+def schedule(epoch: int, pretrain_step: int, epochs: int = 0, is_cq: bool = True, update_every: int = 30) -> Dict[str, object]:
+    """What epoch ``epoch`` of model_training_lpc does (nscm.py:560-598).
+      * the first ``pretrain_step`` epochs run the op that minimises loss_no_quan = c0 time + c1 freq with is_quan_on = 0, the rest
+        the op that minimises loss_quan (:560-568) -- two AdamOptimizer instances with SEPARATE slots (nscm.py:1055-1059);
+      * a CQ run recomputes all LPC residuals with the current (sorted) LSF codebook when ``i % 30 == 0 and i != 0`` or
+        ``i == epoch - 3`` -- regardless of the pre-training phase -- and that epoch SKIPS its training pass (:578-584)."""
     pre = epoch < pretrain_step
-    return {'loss': 'loss_no_quan' if pre else 'loss_quan', 'is_quan_on': 0.0 if pre else 1.0,
-            'update_lpc_residual': (not pre) and epoch > 0 and epoch % update_every == 0}
+    update = bool(is_cq) and ((epoch % update_every == 0 and epoch != 0) or (epochs > 0 and epoch == epochs - 3))
+    return {'loss': 'loss_no_quan' if pre else 'loss_quan', 'is_quan_on': 0.0 if pre else 1.0, 'optimizer': 'no_quan' if pre else 'quan',
+            'update_lpc_residual': update, 'skip_training': update}
 
 
 def sorted_lsf_bins(lsf_params: np.ndarray) -> np.ndarray:

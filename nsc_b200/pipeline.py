@@ -21,8 +21,12 @@ from .constants import frame_length
 HOP = ut.hop_size
 
 
-def analysis(sig: torch.Tensor) -> Dict[str, object]:
-    """One utterance (T,) float32 on the GPU -> filtered signal, frames to code, their LSFs and the bookkeeping counts."""
+def analysis(sig: torch.Tensor, strict: bool = False) -> Dict[str, object]:
+    """One utterance (T,) float32 on the GPU -> filtered signal, frames to code, their LSFs and the bookkeeping counts.
+    A silent (all-zero) LPC window has no LPC solution: the reference raises inside poly2lsf there.  strict=True raises like the
+    reference; otherwise such frames take the previous frame's LSFs (the first one: the uniform LSF grid of A(z) = 1) -- with a
+    silent residual the choice is inaudible -- and their count is returned as 'n_failed', so that a NaN never reaches the
+    de-emphasis IIR (which would spread it over the rest of the utterance)."""
     s, std = ut.load_sig_lpc(sig)
     f = ut.empha_filter(ut.highpass_filter(s))
     T = f.numel()
@@ -31,7 +35,19 @@ def analysis(sig: torch.Tensor) -> Dict[str, object]:
     n_used = max(n_seg2 - 2, 0)                     # the loop runs range(N2 - 2)                           (cmrl.py:698)
     frames = ut.utterance_to_segment(f, True, offset=256)[:n_used]
     lsf = lu.lpc_analysis_windows(ut.lpc_windows_at_test(f), dtype=torch.float32)[:n_used]
-    return {'std': std, 'filtered': f, 'frames': frames, 'lsf': lsf, 'n_seg': n_seg, 'n_seg2': n_seg2, 'n_used': n_used}
+    bad = ~torch.isfinite(lsf).all(dim=1)
+    n_failed = bad.sum()                               # stays on the device: no host synchronisation per utterance
+    if strict and lsf.numel() and int(n_failed):
+        raise ValueError(f"LPC analysis failed on {int(n_failed)} silent frame(s) (the reference raises in poly2lsf)")
+    if lsf.numel():
+        # forward-fill: index of the last good frame at or before each frame (-1 -> the neutral grid); a no-op without failures
+        idx = torch.arange(lsf.shape[0], device=lsf.device)
+        last = torch.cummax(torch.where(bad, torch.full_like(idx, -1), idx), dim=0).values
+        neutral = (torch.arange(1, lsf.shape[1] + 1, device=lsf.device, dtype=lsf.dtype) * (torch.pi / (lsf.shape[1] + 1)))
+        filled = torch.where((last >= 0)[:, None], torch.nan_to_num(lsf[last.clamp(min=0)]), neutral[None, :].expand_as(lsf))
+        lsf = torch.where(bad[:, None], filled, lsf)
+    return {'std': std, 'filtered': f, 'frames': frames, 'lsf': lsf, 'n_seg': n_seg, 'n_seg2': n_seg2, 'n_used': n_used,
+            'n_failed': n_failed}
 
 
 def synthesis(frames: torch.Tensor, n_seg: int, n_seg2: int, std, de_emphasis: bool = True) -> torch.Tensor:
@@ -43,11 +59,12 @@ def synthesis(frames: torch.Tensor, n_seg: int, n_seg2: int, std, de_emphasis: b
     return y * std
 
 
-def code_utterances(cm, signals: Sequence[torch.Tensor], the_share: bool = False, pack: bool = False) -> List[Dict[str, object]]:
+def code_utterances(cm, signals: Sequence[torch.Tensor], the_share: bool = False, pack: bool = False,
+                    strict: bool = False) -> List[Dict[str, object]]:
     """Encode + decode a list of utterances with ``cm`` (a codec.CMRL).  Returns per utterance:
     'synthesized' (time domain, de-emphasised, rescaled), 'decoded' (overlap-added residual-domain signal), 'lsf_idx',
     'idx' (per codec) and, with ``pack``, the fixed-width 'records' of bitstream.pack_frames."""
-    ana = [analysis(s) for s in signals]
+    ana = [analysis(s, strict) for s in signals]
     counts = [a['n_used'] for a in ana]
     if sum(counts) == 0:
         return [{'synthesized': torch.zeros(0, device=s.device), 'decoded': torch.zeros(0, device=s.device)} for s in signals]
@@ -63,7 +80,7 @@ def code_utterances(cm, signals: Sequence[torch.Tensor], the_share: bool = False
         d = {
             'synthesized': synthesis(r['synthesized'][sl], a['n_seg'], a['n_seg2'], a['std']),
             'decoded': synthesis(r['decoded'][sl], a['n_seg'], a['n_seg2'], 1.0, de_emphasis=False),
-            'lsf_idx': r['lsf_idx'][sl], 'idx': [i[sl] for i in r['idx']], 'n_frames': n,
+            'lsf_idx': r['lsf_idx'][sl], 'idx': [i[sl] for i in r['idx']], 'n_frames': n, 'n_failed_lpc_frames': a['n_failed'],
         }
         if records is not None:
             d['records'] = records[sl]

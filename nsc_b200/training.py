@@ -60,8 +60,12 @@ class CQTrainer:
         self.grads = views[:n]
         self.lsf_grad = views[n]
         self.hists = views[n + 1:]
-        self.m = [torch.zeros_like(c.params) for c in cmrl.codecs] + [torch.zeros_like(cmrl.lsf_params)]
-        self.v = [torch.zeros_like(c.params) for c in cmrl.codecs] + [torch.zeros_like(cmrl.lsf_params)]
+        # two optimizers with separate slots, like the reference's two AdamOptimizer(...).minimize ops (nscm.py:1055-1059):
+        # 'quan' minimises loss_quan, 'no_quan' (pre-training epochs) minimises c0 time + c1 freq only
+        self._slots = {name: {'m': [torch.zeros_like(c.params) for c in cmrl.codecs] + [torch.zeros_like(cmrl.lsf_params)],
+                              'v': [torch.zeros_like(c.params) for c in cmrl.codecs] + [torch.zeros_like(cmrl.lsf_params)], 't': 0}
+                       for name in ('quan', 'no_quan')}
+        self.m, self.v = self._slots['quan']['m'], self._slots['quan']['v']
         self._ws: Optional[torch.Tensor] = None
         self._dev = dev
 
@@ -96,15 +100,19 @@ class CQTrainer:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self._dev)
         return self._ws
 
-    def loss_and_grads(self, res_x, lpc_x, tau: Optional[float] = None, is_quan_on: float = 1.0) -> Dict[str, object]:
+    def loss_and_grads(self, res_x, lpc_x, tau: Optional[float] = None, is_quan_on: float = 1.0, quan_terms: bool = True) -> Dict[str, object]:
         """One forward + backward on this rank's shard.  Gradients (of the batch-SUM objective over the GLOBAL batch)
-        land in self.grads / self.lsf_grad, already all-reduced when torch.distributed is initialised."""
+        land in self.grads / self.lsf_grad, already all-reduced when torch.distributed is initialised.
+        quan_terms=False differentiates loss_no_quan = c0 time + c1 freq (the pre-training op, nscm.py:1049): c2 and tau are zero."""
         lib = _lib.load()
         cm, n = self.cm, len(self.cm.codecs)
         x = _lib.require_f32(res_x, 'res_x').reshape(-1, FRAME)
         lsf = _lib.require_f32(lpc_x, 'lpc_x').reshape(-1, _lib.LPC_ORDER)
         B, dev = x.shape[0], x.device
         tau = self.c[3] if tau is None else float(tau)
+        c2 = self.c[2]
+        if not quan_terms:
+            c2, tau = 0.0, 0.0
         ws = self._workspace(B)
         melw = mel_filterbank(dev)
         decoded = torch.empty((B, FRAME), dtype=torch.float32, device=dev)
@@ -124,7 +132,7 @@ class CQTrainer:
         hists_early = _dist_on() and self.needs_global_hist
         if hists_early:
             dist.all_reduce(self.flat[self._n_grad:], op=dist.ReduceOp.SUM)   # batch-global soft histograms BEFORE the backward pass
-        coeff = (C.c_float * 4)(self.c[0], self.c[1], self.c[2], tau)
+        coeff = (C.c_float * 4)(self.c[0], self.c[1], c2, tau)
         qw = (C.c_float * (n + 1))(*self.quan_w)
         ew = (C.c_float * (n + 1))(*self.ent_w)
         tr = (C.c_int32 * (n + 1))(*[int(v) for v in self.trainable])
@@ -141,22 +149,28 @@ class CQTrainer:
         ent_term = sum(w * e for w, e in zip(self.ent_w, ent))
         return {'decoded': decoded, 'time_loss': time_l, 'freq_loss': freq_l, 'quan_loss': quan, 'ent_loss': ent_term,
                 'entropies': ent, 'hists': [h.clone() for h in hists], 'global_batch': global_B,
-                'loss_vector': self.c[0] * time_l + self.c[1] * freq_l + self.c[2] * quan + tau * ent_term}
+                'loss_vector': self.c[0] * time_l + self.c[1] * freq_l + c2 * quan + tau * ent_term}
 
-    def apply_adam(self, lr: Optional[float] = None) -> None:
-        """TF1 AdamOptimizer update of every trainable scope (separate slots per scope, like tf's per-variable slots)."""
+    def apply_adam(self, lr: Optional[float] = None, optimizer: str = 'quan') -> None:
+        """TF1 AdamOptimizer update of every trainable scope (separate slots per scope, like tf's per-variable slots; one set of
+        slots and one step counter per optimizer, 'quan' or 'no_quan')."""
         lib = _lib.load()
-        self.t += 1
+        sl = self._slots[optimizer]
+        sl['t'] += 1
+        self.t = self._slots['quan']['t']
         lr = self.lr if lr is None else lr
         items = [(c.params, g) for c, g in zip(self.cm.codecs, self.grads)] + [(self.cm.lsf_params, self.lsf_grad)]
         flags = self.trainable[1:] + [self.trainable[0]]
-        for (p, g), m, v, on in zip(items, self.m, self.v, flags):
+        for (p, g), m, v, on in zip(items, sl['m'], sl['v'], flags):
             if not on:
                 continue
-            _lib.check(lib.nsc_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), float(lr), self.t,
+            _lib.check(lib.nsc_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), p.numel(), float(lr), sl['t'],
                                          self.b1, self.b2, self.eps, _lib.stream_ptr()), 'nsc_adam_step')
 
-    def step(self, res_x, lpc_x, tau: Optional[float] = None, is_quan_on: float = 1.0, lr: Optional[float] = None):
-        out = self.loss_and_grads(res_x, lpc_x, tau, is_quan_on)
-        self.apply_adam(lr)
+    def step(self, res_x, lpc_x, tau: Optional[float] = None, is_quan_on: float = 1.0, lr: Optional[float] = None,
+             optimizer: str = 'quan'):
+        """One training step.  optimizer='no_quan' is the pre-training op of the reference (loss_no_quan, fed is_quan_on = 0,
+        checkpoint.schedule(...)['optimizer'])."""
+        out = self.loss_and_grads(res_x, lpc_x, tau, is_quan_on, quan_terms=(optimizer == 'quan'))
+        self.apply_adam(lr, optimizer)
         return out

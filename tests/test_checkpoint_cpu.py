@@ -58,6 +58,36 @@ def test_lsf_codebook_and_schedule():
     assert abs(c.update(1.9) - 0.07) < 1e-12             # below target: three steps down
     assert abs(c.update(5.0, is_quan_on=0.0) - 0.07) < 1e-12
     assert abs(c.update_finetune(2.5) - 0.085) < 1e-12
-    s = ck.schedule(3, pretrain_step=5)
-    assert s == {'loss': 'loss_no_quan', 'is_quan_on': 0.0, 'update_lpc_residual': False}
-    assert ck.schedule(30, 5)['update_lpc_residual'] and not ck.schedule(31, 5)['update_lpc_residual']
+    s = ck.schedule(3, pretrain_step=5, epochs=100)
+    assert s == {'loss': 'loss_no_quan', 'is_quan_on': 0.0, 'optimizer': 'no_quan', 'update_lpc_residual': False, 'skip_training': False}
+    assert ck.schedule(30, 5, 100)['update_lpc_residual'] and not ck.schedule(31, 5, 100)['update_lpc_residual']
+    # nscm.py:578-584: `is_cq and (i % 30 == 0 and i != 0 or i == epoch - 3)` -- also DURING pre-training, and that epoch skips training
+    pre = ck.schedule(30, pretrain_step=50, epochs=100)
+    assert pre['loss'] == 'loss_no_quan' and pre['update_lpc_residual'] and pre['skip_training']
+    assert ck.schedule(97, 5, epochs=100)['update_lpc_residual'] and not ck.schedule(96, 5, epochs=100)['update_lpc_residual']
+    assert not ck.schedule(30, 5, 100, is_cq=False)['update_lpc_residual'] and not ck.schedule(0, 5, 100)['update_lpc_residual']
+
+
+def test_separable_names_are_per_graph_in_multi_codec_graphs():
+    """Keras layer names are uniquified per graph: the second 'gln' codec's up-conv is scope_2/separable_conv1d_1 [LIB, unverified].
+    The importer finds it by the predicted name (sep_start) and, failing that, by ascending suffix inside the scope."""
+    cfg = codec.CodecConfig(resnet_type='gln', the_strides=(2,))
+    assert ck.separable_count(cfg) == 1
+    assert ck.separable_count(codec.CodecConfig(resnet_type='gln', the_strides=(2, 2))) == 2
+    ocs = [ref_codec.OracleCodec(ref_codec.OracleCodecCfg(resnet_type='gln', strides=(2,)), seed=s) for s in (1, 2)]
+    variables, start = {}, 0
+    for i, oc in enumerate(ocs):
+        scope = f'scope_{i + 1}'
+        names = ck.tf_variable_names(cfg, scope, sep_start=start)
+        for ns, arrs in zip(names, oc.conv_params):
+            for n, a in zip(ns, arrs):
+                variables[n] = a
+        variables[f'{scope}/alpha'] = np.float32(oc.alpha)
+        variables[f'{scope}/bins'] = np.asarray(oc.bins, dtype=np.float32)
+        start += ck.separable_count(cfg)
+    assert 'scope_1/separable_conv1d/depthwise_kernel' in variables and 'scope_2/separable_conv1d_1/depthwise_kernel' in variables
+    for i, oc in enumerate(ocs):
+        want = codec.pack_params_numpy(cfg, oc.conv_params, oc.alpha, oc.bins)
+        assert np.array_equal(ck.params_from_tf_variables(cfg, f'scope_{i + 1}', variables, sep_start=i), want)
+        # without the hint (sep_start = 0) the per-scope pattern search still finds the layer
+        assert np.array_equal(ck.params_from_tf_variables(cfg, f'scope_{i + 1}', variables), want)

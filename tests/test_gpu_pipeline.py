@@ -67,3 +67,22 @@ def test_hard_codes_pack_and_survive_the_round_trip():
     assert torch.equal(lsf_idx, out['lsf_idx']) and all(torch.equal(a, b) for a, b in zip(codes, out['idx']))
     assert torch.isfinite(out['synthesized']).all()
     assert out['synthesized'].shape[0] == 512 + 480 * (pipeline.ut.segment_count(16000) - 2)
+
+
+def test_digital_silence_does_not_poison_the_utterance():
+    """A silent stretch has no LPC solution (the reference raises in poly2lsf).  strict=True raises like the reference; the default
+    substitutes the previous frame's LSFs, counts the frames, and every output sample stays finite -- before the fix a single NaN
+    frame went through the de-emphasis IIR into the whole rest of the utterance."""
+    from nsc_b200 import codec, pipeline
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=5), codec.NeuralCodec(cfg, device=DEV, seed=6)], res_scalar=1.0)
+    x = _utterance(24000, 7)
+    x[:6000] = 0.0                     # leading digital silence: the zero-state filters keep it exactly zero
+    sig = torch.from_numpy(x).to(DEV)
+    out = pipeline.code_utterances(cm, [sig], the_share=False, pack=True)[0]
+    assert int(out['n_failed_lpc_frames']) > 0
+    assert torch.isfinite(out['synthesized']).all() and torch.isfinite(out['decoded']).all()
+    with pytest.raises(ValueError):
+        pipeline.code_utterances(cm, [sig], strict=True)
+    clean = pipeline.code_utterances(cm, [torch.from_numpy(_utterance(24000, 7)).to(DEV)])[0]
+    assert int(clean['n_failed_lpc_frames']) == 0

@@ -215,3 +215,79 @@ def test_data_parallel_gradients_equal_big_batch():
         for i in range(2):
             assert rel_l2(grads[i], tr.grads[i].cpu().numpy()) < 1e-4
         assert rel_l2(lsf_grad, tr.lsf_grad.cpu().numpy()) < 1e-4
+
+
+def _dp_worker_one_collective(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from nsc_b200.sharding import frame_shard
+    from nsc_b200.training import CQTrainer
+    torch.cuda.set_device(0)
+    _, cm, _ = make_models(2, -20.0)
+    res_x, lsf = inputs(6, seed=99)
+    a, b = frame_shard(6, rank, world)
+    tr = CQTrainer.finetuning_lpc(cm, (60.0, 10.0, 10.0, 0.0))
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, *a_, **k: (calls.append(t.numel()), real(t, *a_, **k))[1]
+    out = tr.loss_and_grads(torch.from_numpy(res_x[a:b]).to(DEV), torch.from_numpy(lsf[a:b]).to(DEV))
+    dist.all_reduce = real
+    q.put((rank, [g.cpu().numpy() for g in tr.grads], tr.lsf_grad.cpu().numpy(), [h.cpu().numpy() for h in out['hists']],
+           tr.collectives_per_step, calls, tr.flat.numel()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_is_one_flat_allreduce_without_entropy_term():
+    """`_finetuning_lpc` drops the entropy term (cmrl.py:485): the backward pass does not need the global histograms, so gradients
+    of every codec, of the LSF codebook AND the histograms travel in ONE SUM all-reduce of one flat buffer; no host sync (the
+    global batch is world x per-rank batch)."""
+    import torch.multiprocessing as mp
+    from nsc_b200.training import CQTrainer
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker_one_collective, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    _, cm, cfg = make_models(2, -20.0)
+    res_x, lsf = inputs(6, seed=99)
+    tr = CQTrainer.finetuning_lpc(cm, (60.0, 10.0, 10.0, 0.0))
+    big = tr.loss_and_grads(torch.from_numpy(res_x).to(DEV), torch.from_numpy(lsf).to(DEV))
+    assert tr.collectives_per_step == 0            # single process
+    for rank, grads, lsf_grad, hists, n_coll, calls, flat_n in res:
+        assert n_coll == 1 and calls == [flat_n]   # exactly one all-reduce, of the whole flat buffer
+        for i in range(2):
+            assert rel_l2(grads[i], tr.grads[i].cpu().numpy()) < 1e-4
+        assert rel_l2(lsf_grad, tr.lsf_grad.cpu().numpy()) < 1e-4
+        for h, hb in zip(hists, big['hists']):
+            assert rel_l2(h, hb.cpu().numpy()) < 1e-5      # the all-reduced histograms are the global ones
+
+
+def test_pretraining_op_has_its_own_adam_slots_and_no_quantisation_terms():
+    """nscm.py:1049-1059: loss_no_quan = c0 time + c1 freq is minimised by its OWN AdamOptimizer (separate slots); the quantisation
+    and entropy terms contribute no gradient there."""
+    from nsc_b200.training import CQTrainer
+    _, cm, _ = make_models(1, -20.0)
+    res_x, lsf = inputs(8, seed=5)
+    x, l = torch.from_numpy(res_x).to(DEV), torch.from_numpy(lsf).to(DEV)
+    w = [16.0 / 272.0, 256.0 / 272.0]
+    tr = CQTrainer(cm, (60.0, 10.0, 10.0, 0.5), quan_w=w, ent_w=w)
+    tr.loss_and_grads(x, l, tau=0.5, is_quan_on=0.0, quan_terms=False)
+    g_noq = [g.clone() for g in tr.grads] + [tr.lsf_grad.clone()]
+    tr0 = CQTrainer(cm, (60.0, 10.0, 0.0, 0.0), quan_w=w, ent_w=w)          # the same objective spelled with zero coefficients
+    tr0.loss_and_grads(x, l, tau=0.0, is_quan_on=0.0)
+    for a, b in zip(g_noq, [g for g in tr0.grads] + [tr0.lsf_grad]):
+        assert torch.equal(a, b)
+    assert float(g_noq[-1].abs().max()) == 0.0                              # the LSF codebook only sees quan / entropy terms
+    tr.step(x, l, tau=0.5, is_quan_on=0.0, optimizer='no_quan')
+    assert tr._slots['no_quan']['t'] == 1 and tr._slots['quan']['t'] == 0
+    assert float(tr._slots['quan']['m'][0].abs().max()) == 0.0 and float(tr._slots['no_quan']['m'][0].abs().max()) > 0.0
+    tr.step(x, l, tau=0.5)
+    assert tr._slots['quan']['t'] == 1 and float(tr._slots['quan']['m'][0].abs().max()) > 0.0
