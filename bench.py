@@ -619,8 +619,9 @@ def measure_codec1(args, world, rank, dev, lib, cpu=True):
 
 def measure_variant(args, world, rank, dev, lib, resnet_type, strides, frames=4144):
     """The reference's SHIPPED switches (constants.py:14 resnet_type = 'gln'; the_strides '4' -> [2, 2], cmrl.py:804) on the same
-    CQ 2-codec workload.  These topologies run on the layer-by-layer engines (first tensor engine: fp16 hi/lo split, fp32 activations
-    between layers; the k55 stem / heads and the separable up-conv on CUDA cores), not on the plane engine."""
+    CQ 2-codec workload.  'gln' with one stride-2 stage runs on the plane engine (fused k15 gate pair, depthwise + pointwise up-conv);
+    two stride-2 stages keep the layer-by-layer engines (first tensor engine: fp16 hi/lo split, fp32 activations between layers; the
+    k55 stem / heads on CUDA cores).  `engine` says which."""
     import torch
     from nsc_b200 import codec, lpc_utilities as lu
     cfg = codec.CodecConfig(resnet_type=resnet_type, the_strides=strides, precision=args.precision)
@@ -644,7 +645,8 @@ def measure_variant(args, world, rank, dev, lib, resnet_type, strides, frames=41
     hbm, bf16, bf16_sus, how = peaks()
     return {"workload": f"cq2 with resnet_type '{resnet_type}', strides {list(strides)}: LPC + LSF codebook + 2 codecs + synthesis, hard codes, "
                         f"{B} frames per GPU", "value": B * world * n * SEC_PER_FRAME / t, "unit": "x real-time", "ms_per_call": t / n * 1e3,
-            "engine": "layer-by-layer (first tensor engine tcgen05 fp16 hi/lo + CUDA-core stem/heads/depthwise)",
+            "engine": ("plane engine (tcgen05, fp16 hi/lo plane images between layers)" if lib.nsc_codec_on_plane_engine(C.byref(cfg.to_struct())) == 1
+                       else "layer-by-layer (first tensor engine tcgen05 fp16 hi/lo + CUDA-core stem/heads/depthwise)"),
             "tflops_algorithmic": fl / (ms * 1e-3) / 1e12, "tensor_frac_of_measured_bf16_sustained": fl / (ms * 1e-3) / 1e12 / bf16_sus,
             "top_kernels": {k: {"ms": round(v[0], 3), "launches": v[3]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:6]}}
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "nsc_codec_param_count": (_i64, [_cfgp]),
     "nsc_codec_layer_info": (_i32, [_cfgp, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
     "nsc_codec_workspace_bytes": (_i64, [_cfgp, _i64]),
+    "nsc_codec_on_plane_engine": (_i32, [_cfgp]),
     "nsc_codec_forward": (_i32, [_cfgp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "nsc_codec_encode": (_i32, [_cfgp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "nsc_codec_decode": (_i32, [_cfgp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),

@@ -197,6 +197,12 @@ int32_t nsc_codec_layer_info(const nsc_codec_cfg* cfg, int32_t i, int32_t* k, in
   return (int32_t)l.layers.size();
 }
 
+int32_t nsc_codec_on_plane_engine(const nsc_codec_cfg* cfg) {
+  if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
+  if (!nsc::PlaneCascade::supported(cfg, 1)) return 0;
+  return nsc::make_plane_plan(*cfg).wpack_bytes >= 0 ? 1 : 0;     // every layer has a launch plan
+}
+
 int64_t nsc_codec_workspace_bytes(const nsc_codec_cfg* cfg, int64_t B) {
   if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
   const int64_t chunk = chunk_for(cfg, 1);

@@ -59,7 +59,7 @@ inline int64_t plane_tensor_frame_bytes(int L, int C, int planes, int deint) {
   return make_plane_tensor(nullptr, L, C, planes, deint).frame_bytes;
 }
 
-enum PlaneKind { PK_T = 0, PK_X = 1, PK_GEN = 2 };
+enum PlaneKind { PK_T = 0, PK_X = 1, PK_GEN = 2, PK_DW = 3 };
 
 // One conv layer of the plane engine.
 //   PK_T   "taps in N": P[row, (tap, co)] = sum_ci X[row, ci] W[tap, ci, co] is ONE MMA chain per tile (N = taps * Cout)
@@ -69,6 +69,16 @@ enum PlaneKind { PK_T = 0, PK_X = 1, PK_GEN = 2 };
 //   PK_X   one MMA per (tap, 16-channel K step): tap = row shift of the A descriptor.  Wide-output layers.
 //   PK_GEN PK_X on the Toeplitz matrix of a 1-channel fp32 signal (stem k55 1->100, decoder k9 1->20), built in
 //          shared memory by producer warps; taps become the K dimension.
+//   PK_DW  depthwise FIR over the rows of a wide image on CUDA cores (the depthwise half of the 'gln' separable up-conv,
+//          nscm.py:175-177): w = (K, C) fp32, no bias, no activation; the pointwise half is a PK_X layer with K = 1.
+//
+// Gated linear unit (gated_bottleneck, nn_core_operator.py:82-112): the two k15 gate convs of a block share their input, so they run
+// as ONE PK_X layer with Cout = 40 -- columns [0, 20) the linear gate (w, bias), [20, 40) the tanh gate (w2, bias2) -- whose epilogue
+// writes (a + b_a) * tanh(g + b_g) as the 20-channel packed image (`glu`).  A dilation-2 gate conv needs 14-row halos, more than the
+// 8 zero rows of an image; it runs instead on the DE-INTERLEAVED image of its input (written that way by the k1 conv in front of it):
+// the two sub-images by position parity are independent "frames" of half the length on which the conv has dilation 1 (`bmul` = 2
+// frames per codec frame), and the epilogue interleaves the result back (`ileave`: frame f', row r -> frame f' >> 1, position
+// 2 r + (f' & 1)).
 struct PlaneConv {
   int kind = PK_X;
   int Lin = 0, Cin = 0, Cout = 0, K = 1, dil = 1, stride = 1;
@@ -88,6 +98,11 @@ struct PlaneConv {
   const float* bias = nullptr;   // (Cout)
   void* wpack = nullptr;         // plane_wpack_bytes() bytes, filled by plane_pack_weights()
   int64_t B = 0;
+  int glu = 0;                   // PK_X: gated linear unit, Cout = 40 = [linear | tanh] gate, 20-channel packed output
+  const float* w2 = nullptr;     // glu: the tanh gate's (K, Cin, 20) kernel and bias
+  const float* bias2 = nullptr;
+  int ileave = 0;                // the output image interleaves pairs of input frames (see above)
+  int bmul = 1;                  // frames of this layer per codec frame (2 for a layer on de-interleaved sub-images)
 };
 
 // kernel family of the narrow -> narrow convs (20 -> 20): NSC_PLANE_NARROW=T|X overrides the default

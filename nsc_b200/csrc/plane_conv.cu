@@ -164,6 +164,38 @@ __global__ void plane_to_f32_kernel(PlaneTensor t, float* __restrict__ y, int y_
 }
 
 // ------------------------------------------------------------------------------------------------
+// depthwise FIR over the rows of a wide image (Keras SeparableConv1D's depthwise half, nscm.py:175-177): one thread per
+// (frame, position, 8-channel chunk); the K row reads of neighbouring positions overlap in L1.  SAME padding comes from the
+// image's zero rows (K <= 17).  fp32 arithmetic on hi + lo, result split back into planes.
+// ------------------------------------------------------------------------------------------------
+__global__ void plane_depthwise_kernel(PlaneTensor in, PlaneTensor out, const float* __restrict__ w, int K, int C, int L, int64_t B) {
+  __shared__ float s_w[17 * 128];
+  const int nch = in.spp * 8;
+  for (int i = threadIdx.x; i < K * nch * 8; i += blockDim.x) {
+    const int t = i / (nch * 8), c = i - t * (nch * 8);
+    s_w[i] = c < C ? __ldg(w + (int64_t)t * C + c) : 0.f;
+  }
+  __syncthreads();
+  const int padL = (K - 1) / 2;
+  const int64_t total = B * (int64_t)L * nch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % nch);
+    const int pos = (int)((i / nch) % L);
+    const int64_t b = i / ((int64_t)nch * L);
+    const uint8_t* img = in.base + b * in.frame_bytes;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < K; ++t) {
+      float v[8];
+      pt_load8(in, img, pos + t - padL, g, v);        // rows -8 .. L + 7 exist (zero rows)
+      const float* wt = s_w + (t * nch + g) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], wt[e], acc[e]);
+    }
+    pt_store8(out, out.base + b * out.frame_bytes, pos, g, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: fp32 (K, Cin, Cout) -> fp16 hi/lo operand slabs in the exact shared-memory image
 // ------------------------------------------------------------------------------------------------
 // Grouped taps-in-N (narrow inputs, k = 9): tap groups are row shifts of the A descriptor, the shifts inside a group cross TMEM lanes
@@ -188,6 +220,8 @@ struct PackArgs {
   int C;        // PK_T: output channels per tap
   int n_units;
   int groups;   // PK_T grouped form (3 or 5 groups): unit = tap group g, row = (slot, co)
+  const float* w2;   // gated linear unit: output columns [csplit, Cout) come from this second (K, Cin, Cout - csplit) kernel
+  int csplit;
 };
 
 __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
@@ -235,8 +269,11 @@ __global__ void plane_pack_kernel(PackArgs a) {
       co = n; t = k; ci = 0; lo_plane = u;
     }
     float v = 0.f;
-    if (co >= 0 && co < a.Cout && ci >= 0 && ci < a.Cin && t < a.K && lo_plane < a.planes)
-      v = a.w[((int64_t)t * a.Cin + ci) * a.Cout + co];
+    if (co >= 0 && co < a.Cout && ci >= 0 && ci < a.Cin && t < a.K && lo_plane < a.planes) {
+      if (a.w2 == nullptr) v = a.w[((int64_t)t * a.Cin + ci) * a.Cout + co];
+      else if (co < a.csplit) v = a.w[((int64_t)t * a.Cin + ci) * a.csplit + co];
+      else v = a.w2[((int64_t)t * a.Cin + ci) * (a.Cout - a.csplit) + (co - a.csplit)];
+    }
     const __half hi = __float2half_rn(v);
     const __half val = lo_plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
     *reinterpret_cast<__half*>(reinterpret_cast<char*>(a.out) + (size_t)u * a.rows * 128 + sw128_off(n, k)) = val;
@@ -711,18 +748,30 @@ __device__ __forceinline__ void t_body(const TParams& p) {
   }
   else if (warp == kEpi + 2) {
     // =========================== storer (ring mode: the fused block kernel) ===========================
-    // One thread sends every finished window to the ring in global memory, waits for a frame's stores to COMPLETE and publishes the
-    // frame at once -- a CTA never holds an unpublished frame while it waits for a free slot (that wait would close a cycle through
-    // the other roles), and the epilogue warps never wait for a store.
+    // One thread sends every finished window to the ring in global memory and publishes a frame once its stores have COMPLETED.
+    // The completion wait is deferred by one frame: frame f - 1 is published after the last window of frame f has been handed to the
+    // copy engine (cp.async.bulk.wait_group T leaves this frame's T groups in flight), so the write latency to L2 (~2-4 us under
+    // load, half of this role's loop time when it was waited for in line -- profiles/r02_block_stats3.log) hides behind a whole
+    // frame of work.  A CTA never holds an unpublished frame while it BLOCKS on a free slot (that wait would close a cycle through
+    // the other roles): the pending frame is published first.  The epilogue warps never wait for a store.
     if constexpr (C != 1) {
       if (ring_out && elect_one()) {
         uint32_t it = 0;
+        int64_t pending = -1;                                      // frame whose stores are issued but not yet known complete
         for (int64_t f = rank; f < p.B; f += nranks) {
           uint8_t* const orow = p.out.base + pt_frame_off(p.out, f) + 8 * 128;
           const int ring0 = (int)((it * 128u) & (kORing - 1));
           int done_rows = 0;
           // the slot's previous frame has been consumed before this frame's first rows go out
-          if (p.out_free != nullptr && f >= p.out.ring) stat_add(p.stats, 2, flag_wait(p.out_free + (f - p.out.ring), (uint32_t)p.out_free_target));
+          if (p.out_free != nullptr && f >= p.out.ring) {
+            const uint32_t* fr = p.out_free + (f - p.out.ring);
+            if (pending >= 0 && ld_acquire_gpu(fr) < (uint32_t)p.out_free_target) {
+              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+              flag_signal(p.out_ready + pending);
+              pending = -1;
+            }
+            stat_add(p.stats, 2, flag_wait(fr, (uint32_t)p.out_free_target));
+          }
           for (int j = 0; j < T; ++j, ++it) {
             mbar_wait_relaxed(&so_ready[it & 1u], (it >> 1) & 1u);
             const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
@@ -737,15 +786,25 @@ __device__ __forceinline__ void t_body(const TParams& p) {
             done_rows = upto;
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             const long long t0 = p.stats != nullptr ? clock64() : 0;
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the window has left shared memory
+            mbar_arrive(&so_free[it & 1u]);
             if (j == T - 1) {
-              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");         // the frame is complete in global memory
-              flag_signal(p.out_ready + f);
-            } else {
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the window has left shared memory
+              if (pending >= 0) {
+                // everything but this frame's T groups is complete in global memory -> the previous frame can be published
+                if (T == 4) asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+                else if (T == 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+                else if (T == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                flag_signal(p.out_ready + pending);
+              }
+              pending = f;
             }
             if (p.stats != nullptr) stat_add(p.stats, 5, clock64() - t0);
-            mbar_arrive(&so_free[it & 1u]);
           }
+        }
+        if (pending >= 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          flag_signal(p.out_ready + pending);
         }
       }
     }
@@ -773,6 +832,8 @@ struct XParams {
   const float* resvec;
   const uint8_t* wpack;
   const float* bias;
+  const float* bias2;        // gated linear unit: bias of the tanh gate (columns [20, 40))
+  int glu, ileave;           // see PlaneConv
   int Lin, Lout, Cin, Cout, K, dil, stride, padL;
   int act, post_act, res_mode, shuffle, planes;
   int Npad, ksteps, mt, tile, tiles_per_frame;
@@ -1061,7 +1122,10 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   const int n_iss = p.n_iss;           // issuing threads: one, or one per M tile
   constexpr int kIssuer1 = kGen ? kXEpiWarps + 3 + kXGenWarps : kXEpiWarps + 3;
 
-  if (tid < 128) s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
+  if (tid < 128) {
+    if (p.glu) s_bias[tid] = tid < 20 ? (p.bias ? __ldg(p.bias + tid) : 0.f) : (tid < 40 && p.bias2) ? __ldg(p.bias2 + tid - 20) : 0.f;
+    else s_bias[tid] = (p.bias && tid < p.Cout) ? __ldg(p.bias + tid) : 0.f;
+  }
   constexpr bool pair = kPair;          // (a kernel that contains cta_group::2 instructions can only be launched as a cluster)
   const uint32_t crank = pair ? cluster_ctarank() : 0u;
   if (tid == 0) {
@@ -1092,10 +1156,53 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       const int64_t f = tile / p.tiles_per_frame;
       const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
       const uint32_t acc_i = it & 1u;
-      uint8_t* oimg = p.out.base + f * p.out.frame_bytes;
+      // `ileave`: this layer's frames are the two position-parity sub-images of the output's frames
+      uint8_t* oimg = p.out.base + (p.ileave ? (f >> 1) : f) * p.out.frame_bytes;
+      const int opar = p.ileave ? (int)(f & 1) : 0, omul = p.ileave ? 2 : 1;
       const uint8_t* rimg = p.res_mode == RES_ADD ? p.res.base + f * p.res.frame_bytes : nullptr;
       const float* rvec = p.res_mode == RES_ADD_BCAST ? p.resvec + f * p.Lout : nullptr;
       const int row0 = q0 + quarter * 32 + lane;
+      if (p.glu) {
+        // gated linear unit: columns [0, 20) linear gate, [20, 40) tanh gate -> 20-channel packed row (nn_core_operator.py:91-102)
+        mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
+        tc_fence_after();
+        for (int mt_i = grp; mt_i < p.mt; mt_i += kXEpiGroups) {
+          const int pos = row0 + mt_i * 128;
+          uint32_t r0[16], r1[16], r2[16];
+          const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad);
+          tmem_ld16(tb, r0);
+          tmem_ld16(tb + 16u, r1);
+          tmem_ld16(tb + 32u, r2);
+          tmem_ld_wait();
+          float v[24];
+#pragma unroll
+          for (int c = 0; c < 20; ++c) {
+            const float a = __uint_as_float(c < 16 ? r0[c & 15] : r1[c & 3]) + s_bias[c];
+            const float g = __uint_as_float(c < 12 ? r1[(4 + c) & 15] : r2[(c - 12) & 15]) + s_bias[20 + c];
+            v[c] = a * tanhf(g);
+          }
+          v[20] = v[21] = v[22] = v[23] = 0.f;
+          float a8[8];
+#pragma unroll
+          for (int g3 = 0; g3 < 3; ++g3) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a8[e] = v[8 * g3 + e];
+            pt_store8(p.out, oimg, omul * pos + opar, g3, a8);
+          }
+          if (p.out.planes == 1) {   // channels 24-31: K padding the consumer reads
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a8[e] = 0.f;
+            pt_store8(p.out, oimg, omul * pos + opar, 3, a8);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);
+          else mbar_arrive(&acc_empty[acc_i]);
+        }
+        continue;
+      }
       auto load_res = [&](int u, ResRaw& rr) {
         if (kGen || u >= n_e) return;      // 1-channel-input layers carry no residual
         const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
@@ -1153,8 +1260,8 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
           float a[8], b[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) { a[e] = v[e]; b[e] = v[8 + e]; }
-          pt_store8(p.out, oimg, pos, c0 >> 3, a);
-          pt_store8(p.out, oimg, pos, (c0 >> 3) + 1, b);
+          pt_store8(p.out, oimg, omul * pos + opar, c0 >> 3, a);
+          pt_store8(p.out, oimg, omul * pos + opar, (c0 >> 3) + 1, b);
         } else {   // sub-pixel: out[2 pos + r, c] = y[pos, 2 c + r]   (nscm.py:158-167)
           float a[8], b[8];
 #pragma unroll
@@ -1168,7 +1275,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         for (int mt_i = 0; mt_i < p.mt; ++mt_i) {
           const int pos = row0 + mt_i * 128;
           for (int g = p.zero_from; g < p.zero_to; ++g) {
-            if (p.shuffle == 1) pt_store8(p.out, oimg, pos, g, z);
+            if (p.shuffle == 1) pt_store8(p.out, oimg, omul * pos + opar, g, z);
             else { pt_store8(p.out, oimg, 2 * pos, g, z); pt_store8(p.out, oimg, 2 * pos + 1, g, z); }
           }
         }
@@ -1645,8 +1752,11 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   if (c.res_mode == RES_ADD && (c.res.deint || c.res.rows != Lout)) return false;
   if (c.res_mode == RES_ADD_BCAST && c.resvec == nullptr) return false;
   if (c.res_mode == RES_MUL || (gen && c.res_mode != RES_NONE)) return false;
-  if (c.out.rows != (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
+  if (c.glu && (gen || !c.in.packed || !c.out.packed || c.Cout != 40 || c.shuffle != 1 || c.res_mode != RES_NONE || c.stride != 1)) return false;
+  if (c.ileave && (c.out.deint || c.shuffle != 1 || c.out.rows != 2 * Lout)) return false;
+  if (!c.ileave && c.out.rows != (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
   p->kind = c.kind;
+  p->glu = c.glu; p->ileave = c.ileave; p->bias2 = c.bias2;
   p->cta0 = 0; p->ncta = 1; p->in_ready = nullptr; p->in_free = nullptr; p->stats = nullptr;
   p->in = c.in; p->out = c.out; p->res = c.res;
   p->xvec = c.xvec; p->xsub = c.xsub; p->xscale = c.xscale; p->resvec = c.resvec;
@@ -1678,7 +1788,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
     p->stage_bytes = (p->tile + 16) * 128;
     p->tiles_per_frame = Lout / p->tile;
     p->n_tiles = c.B * p->tiles_per_frame;
-    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
+    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && !c.glu && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
     p->slot_bytes = p->pair ? p->unit_bytes / 2 : p->unit_bytes;
     const size_t slot = (size_t)p->slot_bytes;
     const size_t a1 = (size_t)p->n_stage * p->stage_bytes;
@@ -1711,6 +1821,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
     if (c.out.packed) needed = 4;
     p->zero_from = written;
     p->zero_to = needed > written ? needed : written;
+    if (c.glu) p->zero_from = p->zero_to = 0;          // the gate epilogue writes the whole packed row itself
     if (p->staged && (p->zero_from != p->zero_to || p->n_stage * p->kbuf > 4)) p->staged = 0;   // (never for the codec's shapes)
     if (!p->staged) p->s_units = 0;
     {
@@ -1743,6 +1854,9 @@ int plane_narrow_kind() {
 
 bool plane_conv_supported(const PlaneConv& c) {
   if (c.planes != 1 && c.planes != 2) return false;
+  if (c.kind == PK_DW)
+    return c.Cin == c.Cout && c.Cin > 32 && c.Cin <= 128 && c.K >= 1 && c.K <= 17 && c.dil == 1 && c.stride == 1 && c.shuffle == 1 &&
+           c.res_mode == RES_NONE && !c.in.packed && !c.in.deint && !c.out.packed && !c.out.deint && c.in.rows == c.Lin && c.out.rows == c.Lin;
   if (c.kind == PK_T) { TPlan pl; return plan_t(c, &pl); }
   XParams p;
   PlaneConv cc = c;
@@ -1751,6 +1865,7 @@ bool plane_conv_supported(const PlaneConv& c) {
 }
 
 int64_t plane_wpack_bytes(const PlaneConv& c) {
+  if (c.kind == PK_DW) return plane_conv_supported(c) ? 0 : -1;
   if (c.kind == PK_T) {
     TPlan pl;
     if (!plan_t(c, &pl)) return -1;
@@ -1766,6 +1881,7 @@ int64_t plane_wpack_bytes(const PlaneConv& c) {
 bool plane_plan_info(const PlaneConv& c, int64_t* o) {
   for (int i = 0; i < 12; ++i) o[i] = 0;
   o[0] = c.kind;
+  if (c.kind == PK_DW) return plane_conv_supported(c);
   if (c.kind == PK_T) {
     TPlan pl;
     if (!plan_t(c, &pl)) return false;
@@ -1788,9 +1904,12 @@ bool plane_plan_info(const PlaneConv& c, int64_t* o) {
 }
 
 int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
+  if (c.kind == PK_DW) return NSC_OK;      // the depthwise FIR reads its fp32 taps directly
   NSC_CHECK_ARG(c.w != nullptr && c.wpack != nullptr, "plane engine: null weights");
+  NSC_CHECK_ARG(!c.glu || c.w2 != nullptr, "plane engine: gated layer without its second kernel");
   PackArgs a;
   a.w = c.w; a.out = static_cast<__half*>(c.wpack);
+  a.w2 = c.glu ? c.w2 : nullptr; a.csplit = 20;
   a.kind = c.kind; a.K = c.K; a.Cin = c.Cin; a.Cout = c.Cout; a.planes = c.planes;
   a.in_packed = c.kind == PK_GEN ? 0 : c.in.packed;
   a.in_spp = c.kind == PK_GEN ? 1 : c.in.spp;
@@ -1817,6 +1936,17 @@ int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
 
 int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.B == 0) return NSC_OK;
+  if (c.kind == PK_DW) {
+    NSC_CHECK_ARG(plane_conv_supported(c) && c.w != nullptr, "plane engine: unsupported depthwise layer (k%d %d channels)", c.K, c.Cin);
+    char dname[32];
+    snprintf(dname, sizeof(dname), "pD%d_k%d_c%d", c.planes, c.K, c.Cin);
+    ProfScope prof(st, dname, 2.0 * (double)c.B * c.Lin * c.K * c.Cin, 2.0 * (double)c.B * pt_real_bytes(c.Lin, c.Cin, c.planes));
+    const int64_t total = c.B * (int64_t)c.Lin * (c.in.spp * 8);
+    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
+    plane_depthwise_kernel<<<blocks, 256, 0, st>>>(c.in, c.out, c.w, c.K, c.Cin, c.Lin, c.B);
+    NSC_LAUNCH_OK();
+    return NSC_OK;
+  }
   NSC_CHECK_ARG(c.wpack != nullptr, "plane engine: weights not packed");
   int Lout, padL;
   same_padding(c.Lin, c.K, c.dil, c.stride, &Lout, &padL);
@@ -1861,7 +1991,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : "X", c.planes, c.K, c.dil, c.stride, c.Cin, c.Cout);
+  snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : (c.glu ? (c.ileave ? "U2x" : "U") : "X"), c.planes, c.K, c.dil, c.stride,
+           c.Cin, c.Cout);
   double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_real_bytes(c.Lin, c.Cin, c.planes));
   bytes += (double)c.B * pt_real_bytes(Lout, c.Cout, c.planes);
   if (c.res_mode == RES_ADD) bytes += (double)c.B * pt_real_bytes(Lout, c.Cout, c.planes);

@@ -163,3 +163,34 @@ def test_gated_bottleneck_decoder_vs_oracle():
         got = nn.gated_bottleneck_decoder(cu(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=flat, params=params)
         assert got.shape == ref.shape
         assert rel_err(got.cpu().numpy(), ref) < 5e-5
+
+
+@pytest.mark.parametrize('B', [5, 32])
+def test_gln_codec_on_the_plane_engine_per_frame_vs_oracle(B):
+    """The reference's SHIPPED block type (constants.py:14 resnet_type = 'gln'; gated_bottleneck, nn_core_operator.py:82-112; separable
+    up-conv, nscm.py:175-177) on the plane engine: fused k15 gate pair with the gate product in the epilogue, the dilation-2 gates on
+    de-interleaved sub-images, depthwise + pointwise up-conv.  Per-frame error of the encoder's floating code vs float64 truth (the
+    float32 oracle's own distance is the yardstick) and of the decoder on identical codes vs the float32 oracle; odd and even batches
+    (CTA pairs need an even number of tiles)."""
+    from nsc_b200 import _lib
+    oc, gc = _pair(seed=11, rt='gln')
+    x = ar_frames(B, 512, seed=B, std=0.3)
+    x[1] *= 1e-2                                                      # a quiet frame must not hide behind the loud ones
+    oc.ps._cursor = 0
+    truth = oc.encoder(torch.from_numpy(x).double()[:, :, None])[:, :, 0].numpy()
+    oc.ps._cursor = 0
+    ref32 = oc.encoder(torch.from_numpy(x)[:, :, None])[:, :, 0].numpy()
+    n_enc = oc.ps._cursor
+    enc = gc.encode(cu(x))
+    got = enc['floating_code'].cpu().numpy()
+    e_gpu, e_ref = _frame_err(got, truth), _frame_err(ref32, truth)
+    assert (e_gpu <= e_ref + 1e-4).all() and (e_gpu < 5e-5).all(), (e_gpu, e_ref)
+    code = enc['code'].cpu().numpy()
+    oc.ps._cursor = n_enc
+    out_o = oc.decoder(torch.from_numpy(code)[:, :, None])[:, :, 0].numpy()
+    out_g = gc.decode_indices(enc['idx']).cpu().numpy()
+    assert _frame_err(out_g, out_o).max() < 1e-4
+    lib = _lib.load()
+    cfg = gc.cfg.to_struct()
+    import ctypes as C
+    assert lib.nsc_codec_on_plane_engine(C.byref(cfg)) == 1           # the tcgen05 plane path, not the layer-by-layer engines

@@ -201,8 +201,10 @@ def test_full_size_cascade_algebra_and_hard_round_trip():
     assert torch.equal(enc1['idx'], r['idx'][1])
 
 
-def test_plane_path_matches_layer_by_layer_engine_at_full_size(monkeypatch):
-    """Plane engine vs the first tensor engine (same hi/lo arithmetic, fp32 activations between layers) on 1,000 frames."""
+@pytest.mark.parametrize('resnet_type', ['bottleneck', 'gln'])
+def test_plane_path_matches_layer_by_layer_engine_at_full_size(monkeypatch, resnet_type):
+    """Plane engine vs the first tensor engine (same hi/lo arithmetic, fp32 activations between layers) on 1,000 frames --
+    both block types: the_bottleneck and the reference's shipped default gated_bottleneck (constants.py:14)."""
     import subprocess, sys, os, json
     from util import ar_frames
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -211,11 +213,11 @@ def test_plane_path_matches_layer_by_layer_engine_at_full_size(monkeypatch):
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "from util import ar_frames\n"
         "from nsc_b200 import codec\n"
-        "cfg = codec.CodecConfig(resnet_type='bottleneck'); gc = codec.NeuralCodec(cfg, device='cuda', seed=9)\n"
+        "cfg = codec.CodecConfig(resnet_type=%r); gc = codec.NeuralCodec(cfg, device='cuda', seed=9)\n"
         "x = torch.from_numpy(ar_frames(1000, 512, seed=79, std=0.3)).cuda()\n"
         "r = gc.computational_graph_end2end_quan_on(x, True, 1.0)\n"
         "np.save(sys.argv[1], np.concatenate([r['floating_code'].cpu().numpy().ravel(), r['out'].cpu().numpy().ravel()]))\n"
-    ) % (root, os.path.join(root, 'tests'))
+    ) % (root, os.path.join(root, 'tests'), resnet_type)
     outs = []
     for tag, env in (('plane', {}), ('layered', {'NSC_PLANE': '0'})):
         path = '/tmp/nsc_plane_vs_layered_%s.npy' % tag

@@ -284,7 +284,8 @@ def test_pretraining_op_has_its_own_adam_slots_and_no_quantisation_terms():
     tr0 = CQTrainer(cm, (60.0, 10.0, 0.0, 0.0), quan_w=w, ent_w=w)          # the same objective spelled with zero coefficients
     tr0.loss_and_grads(x, l, tau=0.0, is_quan_on=0.0)
     for a, b in zip(g_noq, [g for g in tr0.grads] + [tr0.lsf_grad]):
-        assert torch.equal(a, b)
+        # (the weight-gradient kernels reduce with atomics: two runs agree to rounding, not to the bit)
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm())
     assert float(g_noq[-1].abs().max()) == 0.0                              # the LSF codebook only sees quan / entropy terms
     tr.step(x, l, tau=0.5, is_quan_on=0.0, optimizer='no_quan')
     assert tr._slots['no_quan']['t'] == 1 and tr._slots['quan']['t'] == 0

@@ -98,9 +98,14 @@ def test_codec_workspace_sizes_on_the_plane_path():
     per_frame = (chunk - one) / 2071
     assert 1.5e6 < per_frame < 1.7e6                        # 11 plane buffers: 1.57 MB per frame
     assert lib.nsc_codec_workspace_bytes(C.byref(cfg32), 2048) < chunk   # fp32 NCL buffers are smaller
-    # configurations outside the plane path keep the layer-by-layer workspace
+    # the reference's shipped 'gln' blocks run on the plane path too: three more buffers (two de-interleaved narrow twins for the
+    # dilation-2 gate convs, a third half-length wide image for the depthwise half of the separable up-conv)
     gln = codec.CodecConfig(resnet_type='gln', precision='tc_f16x3').to_struct()
-    assert lib.nsc_codec_workspace_bytes(C.byref(gln), 2048) < chunk
+    gchunk = lib.nsc_codec_workspace_bytes(C.byref(gln), 2072)
+    assert chunk < gchunk < 1.2 * chunk and gchunk == lib.nsc_codec_workspace_bytes(C.byref(gln), 100000)
+    # configurations outside the plane path keep the layer-by-layer workspace
+    s4 = codec.CodecConfig(resnet_type='bottleneck', the_strides=(2, 2), precision='tc_f16x3').to_struct()
+    assert lib.nsc_codec_workspace_bytes(C.byref(s4), 2048) < chunk
 
 
 def test_framing_and_packing_sizes():
