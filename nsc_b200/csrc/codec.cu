@@ -85,9 +85,11 @@ struct PlaneCascade {
   float* fcode = nullptr;       // (Bc, Lc) scratch, largest Lc
   float* code = nullptr;
 
+  // every codec's topology is covered AND every one of its layers has a launch plan (e.g. 'gln' with two stride-2 stages is not: its
+  // dilation-2 gate conv at 128 positions would run on 64-row sub-images, below the 128-row MMA tile)
   static bool supported(const nsc_codec_cfg* cfgs, int n) {
     for (int i = 0; i < n; ++i)
-      if (!plane_codec_supported(cfgs[i])) return false;
+      if (!plane_codec_supported(cfgs[i]) || make_plane_plan(cfgs[i]).wpack_bytes < 0) return false;
     return n >= 1;
   }
   static void layout(const nsc_codec_cfg* cfgs, int n, std::vector<int>* region, int* n_regions) {
@@ -96,7 +98,8 @@ struct PlaneCascade {
     for (int i = 0; i < n; ++i) {
       int r = -1;
       for (int j = 0; j < i; ++j)
-        if (cfgs[j].wide == cfgs[i].wide && cfgs[j].precision == cfgs[i].precision) { r = (*region)[j]; break; }
+        if (cfgs[j].wide == cfgs[i].wide && cfgs[j].precision == cfgs[i].precision && cfgs[j].resnet_type == cfgs[i].resnet_type &&
+            cfgs[j].n_strides == cfgs[i].n_strides) { r = (*region)[j]; break; }   // same image geometry: the zero rows stay zero
       (*region)[i] = r >= 0 ? r : (*n_regions)++;
     }
   }
@@ -148,18 +151,43 @@ struct PlaneCascade {
   }
 };
 
+// Cascade arithmetic around one codec of the plane path, folded into its first and last kernels (cmrl.py:522-531, :810-830):
+// the stem reads in = in_scale * (x - in_sub) directly, the output head adds out / out_div to `acc` (and writes the quotient).
+struct CascadeFold {
+  const float* in_sub = nullptr;
+  float in_scale = 1.f;
+  float* acc = nullptr;
+  float* quot = nullptr;
+  float out_div = 1.f;
+  int acc_first = 0;
+};
+
+static bool plane_fold_on() {
+  static const bool on = [] { const char* e = getenv("NSC_PLANE_FOLD"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // plane-path twin of run_codec_chunk
 int run_codec_chunk_plane(PlaneCascade& pcs, int i, const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* params,
                           const float* x, int64_t nb, float iq, int use_soft, float* fcode, uint8_t* idx, float* code,
-                          float* out, float* soft, float* hist, float* qloss, int which, cudaStream_t st) {
+                          float* out, float* soft, float* hist, float* qloss, int which, cudaStream_t st,
+                          const CascadeFold* cf = nullptr) {
   float* fc = fcode ? fcode : pcs.fcode;
   float* cd = code ? code : pcs.code;
   if (which & 1) {
-    NSC_TRY(plane_run_encoder(pcs.plans[i], x, nb, fc, st));
     const float* alpha = params + lay.conv_floats;
-    NSC_TRY(launch_quantize(fc, nb, lay.code_len, alpha + 1, cfg.num_bins, alpha, iq, use_soft, cd, idx, soft, hist, qloss, st));
+    // hard codes and no statistics asked for: the quantiser runs in the code head's epilogue (NSC_PLANE_FOLD=0: stand-alone kernel)
+    const bool qfold = plane_fold_on() && !use_soft && soft == nullptr && hist == nullptr && qloss == nullptr;
+    HeadFold hf;
+    if (qfold) { hf.q_bins = alpha + 1; hf.q_alpha = alpha; hf.q_n = cfg.num_bins; hf.q_iq = iq; hf.q_idx = idx; hf.q_code = cd; }
+    NSC_TRY(plane_run_encoder(pcs.plans[i], x, cf ? cf->in_sub : nullptr, cf ? cf->in_scale : 1.f, nb, (qfold && !fcode) ? nullptr : fc, hf, st));
+    if (!qfold) NSC_TRY(launch_quantize(fc, nb, lay.code_len, alpha + 1, cfg.num_bins, alpha, iq, use_soft, cd, idx, soft, hist, qloss, st));
   }
-  if (which & 2) NSC_TRY(plane_run_decoder(pcs.plans[i], cd, nb, out, st));
+  if (which & 2) {
+    HeadFold hf;
+    if (cf && cf->acc) { hf.acc = cf->acc; hf.quot = cf->quot; hf.div = cf->out_div; hf.acc_first = cf->acc_first; }
+    NSC_TRY(plane_run_decoder(pcs.plans[i], cd, nb, out, hf, st));
+  }
   return NSC_OK;
 }
 
@@ -199,8 +227,7 @@ int32_t nsc_codec_layer_info(const nsc_codec_cfg* cfg, int32_t i, int32_t* k, in
 
 int32_t nsc_codec_on_plane_engine(const nsc_codec_cfg* cfg) {
   if (nsc::validate_cfg(cfg) != NSC_OK) return -1;
-  if (!nsc::PlaneCascade::supported(cfg, 1)) return 0;
-  return nsc::make_plane_plan(*cfg).wpack_bytes >= 0 ? 1 : 0;     // every layer has a launch plan
+  return nsc::PlaneCascade::supported(cfg, 1) ? 1 : 0;
 }
 
 int64_t nsc_codec_workspace_bytes(const nsc_codec_cfg* cfg, int64_t B) {
@@ -325,6 +352,22 @@ static int cascade_chunk(const nsc_codec_cfg* cfgs, const nsc::CodecLayout* lays
     nsc::CodecBuffers buf{};
     if (!pcs) buf = nsc::carve_codec(cv, cfgs[i], Bc);
     const float* xin = x;
+    const int Lc = lays[i].code_len;
+    const bool divide = (i > 0) || lpc_variant;       // codec 0 of the plain cascade is not divided (cmrl.py:522-528)
+    const float d = divide ? res_scalar : 1.0f;
+    if (pcs && nsc::plane_fold_on()) {
+      // plane path: the stem applies the input arithmetic, the output head accumulates -- no stand-alone cascade kernels, and the
+      // codec's input / raw output never exist as tensors in HBM
+      nsc::CascadeFold cf;
+      if (i == 0) { cf.in_scale = lpc_variant ? res_scalar : 1.0f; }          // res_x * res_scalar, cmrl.py:810
+      else { cf.in_sub = decoded; cf.in_scale = res_scalar; }                  // res_scalar * (x - sum_{j<i} out_j), cmrl.py:529-531 / :822-823
+      cf.acc = decoded; cf.acc_first = i == 0 ? 1 : 0; cf.out_div = d;
+      cf.quot = (outs && outs[i]) ? outs[i] + b0 * kFrameLen : nullptr;
+      NSC_TRY(nsc::run_codec_chunk_plane(*pcs, i, cfgs[i], lays[i], params[i], x, nb, iq, use_soft, nullptr,
+                                         (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, nullptr, nullptr,
+                                         (hist && hist[i]) ? hist[i] : nullptr, (qloss && qloss[i]) ? qloss[i] + b0 : nullptr, 3, st, &cf));
+      continue;
+    }
     if (i == 0) {
       if (lpc_variant && res_scalar != 1.0f) {       // res_x * res_scalar, cmrl.py:810
         NSC_TRY(nsc::launch_axpby(cin, x, res_scalar, nullptr, 0.f, nfl, st));
@@ -334,7 +377,6 @@ static int cascade_chunk(const nsc_codec_cfg* cfgs, const nsc::CodecLayout* lays
       NSC_TRY(nsc::launch_axpby(cin, x, res_scalar, decoded, 1.0f, nfl, st));
       xin = cin;
     }
-    const int Lc = lays[i].code_len;
     if (pcs)
       NSC_TRY(nsc::run_codec_chunk_plane(*pcs, i, cfgs[i], lays[i], params[i], xin, nb, iq, use_soft, nullptr,
                                          (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, cout, nullptr,
@@ -343,8 +385,6 @@ static int cascade_chunk(const nsc_codec_cfg* cfgs, const nsc::CodecLayout* lays
       NSC_TRY(nsc::run_codec_chunk(cfgs[i], lays[i], params[i], buf, xin, nb, iq, use_soft, nullptr,
                                    (idx && idx[i]) ? idx[i] + b0 * Lc : nullptr, nullptr, cout, nullptr,
                                    (hist && hist[i]) ? hist[i] : nullptr, (qloss && qloss[i]) ? qloss[i] + b0 : nullptr, 3, st));
-    const bool divide = (i > 0) || lpc_variant;       // codec 0 of the plain cascade is not divided (cmrl.py:522-528)
-    const float d = divide ? res_scalar : 1.0f;
     if (outs && outs[i]) NSC_TRY(nsc::launch_div(outs[i] + b0 * kFrameLen, cout, d, nfl, st));
     NSC_TRY(nsc::launch_accum_div(decoded, cout, d, i == 0 ? 1 : 0, nfl, st));
   }

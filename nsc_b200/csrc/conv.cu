@@ -312,6 +312,10 @@ __global__ void accum_div_kernel(float* __restrict__ acc, const float* __restric
   }
 }
 
+__global__ void mul_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = a[i] * b[i];
+}
+
 __global__ void div_kernel(float* __restrict__ y, const float* __restrict__ x, float d, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = x[i] / d;
@@ -409,6 +413,14 @@ int launch_axpby(float* y, const float* x, float a, const float* z, float b, int
   if (n == 0) return NSC_OK;
   ProfScope prof(st, "cascade_input", 2.0 * (double)n, (z ? 12.0 : 8.0) * (double)n);
   axpby_kernel<<<ew_grid(n), 256, 0, st>>>(y, x, a, z, b, n);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+int launch_mul(float* y, const float* a, const float* b, int64_t n, cudaStream_t st) {
+  if (n == 0) return NSC_OK;
+  ProfScope prof(st, "gate_product", (double)n, 12.0 * (double)n);
+  mul_kernel<<<ew_grid(n), 256, 0, st>>>(y, a, b, n);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }

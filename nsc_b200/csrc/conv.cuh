@@ -42,6 +42,8 @@ int launch_depthwise(const float* x, const float* dw, float* y, int64_t B, int L
 int launch_axpby(float* y, const float* x, float a, const float* z, float b, int64_t n, cudaStream_t st);
 // y = x / d
 int launch_div(float* y, const float* x, float d, int64_t n, cudaStream_t st);
+// y = a * b elementwise (the gate product of a gated block on the training tape)
+int launch_mul(float* y, const float* a, const float* b, int64_t n, cudaStream_t st);
 // acc (+)= x / d ; first = 1 overwrites
 int launch_accum_div(float* acc, const float* x, float d, int first, int64_t n, cudaStream_t st);
 

@@ -61,6 +61,24 @@ inline int64_t plane_tensor_frame_bytes(int L, int C, int planes, int deint) {
 
 enum PlaneKind { PK_T = 0, PK_X = 1, PK_GEN = 2, PK_DW = 3 };
 
+// Work folded into the epilogue of a 1-channel k55 head (PK_T, Cout = 1), bit-identical to the stand-alone kernels it replaces:
+//   code head:   the HARD scalar quantiser (nn_core_operator.py:140-164; quantize_kernel's arithmetic): index and blended code
+//                straight from the tanh output -- the floating code only goes to HBM if the caller asks for it;
+//   output head: the cascade's accumulation decoded (+)= out / res_scalar (cmrl.py:522-531, :822-830; accum_div_kernel) and the
+//                per-codec quotient.
+struct HeadFold {
+  const float* q_bins = nullptr;   // n bins (device); null = no quantiser fold
+  const float* q_alpha = nullptr;  // device scalar
+  int q_n = 0;
+  float q_iq = 1.f;                // is_quan_on
+  uint8_t* q_idx = nullptr;        // (B, L) indices, may be null
+  float* q_code = nullptr;         // (B, L) code = (1 - iq) x + iq bins[idx], may be null
+  float* acc = nullptr;            // (B, L) running sum; null = no accumulation fold
+  float* quot = nullptr;           // (B, L) out / div, may be null
+  float div = 1.f;
+  int acc_first = 0;               // 1: overwrite acc instead of adding
+};
+
 // One conv layer of the plane engine.
 //   PK_T   "taps in N": P[row, (tap, co)] = sum_ci X[row, ci] W[tap, ci, co] is ONE MMA chain per tile (N = taps * Cout)
 //          and the tap sum y[row] = sum_t P[row + shift_t, t] is done across TMEM lanes with warp shuffles.  For the
@@ -103,6 +121,7 @@ struct PlaneConv {
   const float* bias2 = nullptr;
   int ileave = 0;                // the output image interleaves pairs of input frames (see above)
   int bmul = 1;                  // frames of this layer per codec frame (2 for a layer on de-interleaved sub-images)
+  HeadFold fold;                 // PK_T heads (Cout = 1)
 };
 
 // kernel family of the narrow -> narrow convs (20 -> 20): NSC_PLANE_NARROW=T|X overrides the default

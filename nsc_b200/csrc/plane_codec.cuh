@@ -3,9 +3,10 @@
 // one layer's epilogue in exactly the form the next layer's bulk copies stage.  Host side only; included by codec.cu.
 //
 // Covered: resnet_type 'bottleneck' AND 'gln' (the reference's shipped default, constants.py:14: gated blocks with k15 gates and the
-// separable up-conv), one stride-2 stage, narrow = 20, k = 9, dilations <= 2.  Anything else keeps the layer-by-layer engines
-// (walker.cuh).
+// separable up-conv), one or two stride-2 stages (the_strides '2' / '4', cmrl.py:804), narrow = 20, k = 9, dilations <= 2.  Anything
+// else keeps the layer-by-layer engines (walker.cuh).
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -20,9 +21,14 @@ bool plane_codec_supported(const nsc_codec_cfg& c) {
   static const bool off = [] { const char* e = getenv("NSC_PLANE"); return e && e[0] == '0'; }();
   if (off) return false;
   if (c.precision != 1 && c.precision != 2) return false;
-  if ((c.resnet_type != 0 && c.resnet_type != 1) || c.n_strides != 1 || c.strides[0] != 2) return false;
+  if ((c.resnet_type != 0 && c.resnet_type != 1) || c.n_strides < 1 || c.n_strides > 2) return false;
+  for (int i = 0; i < c.n_strides; ++i)
+    if (c.strides[i] != 2) return false;
   if (c.narrow != 20 || c.k_plain != 9 || c.k_dilated != 9) return false;
   if (c.wide < 66 || c.wide > 128 || (c.wide & 1)) return false;   // wide and wide/2 both use unpacked (>32 channel) images
+  // two stages (the_strides = '4', cmrl.py:804): the decoder's last level has wide/4 channels, which must still be an unpacked image
+  // (more than 20 channels with hi/lo planes; the one-plane mode would pack it)
+  if (c.n_strides == 2 && (c.precision != 1 || (c.wide & 3) || c.wide / 4 <= 20)) return false;
   for (int i = 0; i < c.n_blocks; ++i)
     if (c.dilations[i] < 1 || c.dilations[i] > 2) return false;
   return true;
@@ -38,20 +44,14 @@ int64_t plane_chunk_frames() {
   return v;
 }
 
-// PB_N0D / PB_M0D: de-interleaved twins of PB_N0 / PB_M0 ('gln': input of a dilation-2 gate conv); PB_H2: third half-length wide
-// buffer ('gln': the depthwise half of the separable up-conv)
-enum PBuf { PB_W0 = 0, PB_W1, PB_WD, PB_H0, PB_H1, PB_N0, PB_N1, PB_M0, PB_M1, PB_C0, PB_C1, PB_N0D, PB_M0D, PB_H2, PB_COUNT };
-
 struct PlaneCodecPlan {
   int planes = 2;
   int Lc = 0;
-  PlaneTensor buf[PB_COUNT];             // bases relative to the activation region (filled by bind)
-  int64_t buf_off[PB_COUNT];
-  int64_t act_bytes_per_frame = 0;
+  std::vector<PlaneTensor> buf;          // activation images; bases relative to the activation region (filled by bind)
   std::vector<PlaneConv> enc, dec;
   std::vector<int> enc_layer, dec_layer;  // index into the codec's layer table (parameter offsets; a gated layer also owns the next entry)
   std::vector<int> enc_sep, dec_sep;      // 0 plain conv; 1 / 2: depthwise / pointwise half of a separable layer (one table entry)
-  struct Io { int in, out, res; };        // activation buffers of a layer (PBuf ids, -1 = the 1-channel vector at the edge)
+  struct Io { int in, out, res; };        // activation buffers of a layer (ids into buf, -1 = the 1-channel vector at the edge)
   std::vector<Io> enc_io, dec_io;
   std::vector<int64_t> w_off;             // packed-weight offset of every layer (enc then dec)
   int64_t wpack_bytes = 0;
@@ -62,32 +62,34 @@ struct PlaneCodecPlan {
 };
 
 // Lays the codec out as plane layers.  Tensors carry geometry only (base = nullptr) until plane_bind() attaches a workspace.
+// Resolution levels: level l has 512 >> l positions; the encoder walks down the levels with 100-channel images, the decoder walks
+// back up halving the channels at every sub-pixel stage (nscm.py:152-181, :219-260).  Every level owns two wide images (ping-pong
+// of the blocks), a de-interleaved one (input of the stride-2 conv below it), two narrow images -- plus, for 'gln', the de-interleaved
+// twin of the first narrow image (input of a dilation-2 gate conv) and a third wide image (depthwise half of the separable up-conv) --
+// and the decoder's own pair of wide images where its channel count differs from the encoder's.
 PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   PlaneCodecPlan pl;
   pl.planes = c.precision == 1 ? 2 : 1;
-  const int P = pl.planes, L = kFrameLen, H = kFrameLen / 2, W = c.wide, Nn = c.narrow, Wd = c.wide / 2;
-  pl.Lc = H;
-  pl.buf[PB_W0] = make_plane_tensor(nullptr, L, W, P, 0);
-  pl.buf[PB_W1] = pl.buf[PB_W0];
-  pl.buf[PB_WD] = make_plane_tensor(nullptr, L, W, P, 1);
-  pl.buf[PB_H0] = make_plane_tensor(nullptr, H, W, P, 0);
-  pl.buf[PB_H1] = pl.buf[PB_H0];
-  pl.buf[PB_N0] = make_plane_tensor(nullptr, L, Nn, P, 0);
-  pl.buf[PB_N1] = pl.buf[PB_N0];
-  pl.buf[PB_M0] = make_plane_tensor(nullptr, H, Nn, P, 0);
-  pl.buf[PB_M1] = pl.buf[PB_M0];
-  pl.buf[PB_C0] = make_plane_tensor(nullptr, L, Wd, P, 0);
-  pl.buf[PB_C1] = pl.buf[PB_C0];
+  const int P = pl.planes, W = c.wide, Nn = c.narrow, NS = c.n_strides;
   const bool gln = c.resnet_type == 1;
-  // (buffers only the gated topology uses stay empty for 'bottleneck')
-  if (gln) {
-    pl.buf[PB_N0D] = make_plane_tensor(nullptr, L, Nn, P, 1);
-    pl.buf[PB_M0D] = make_plane_tensor(nullptr, H, Nn, P, 1);
-    pl.buf[PB_H2] = pl.buf[PB_H0];
+  pl.Lc = kFrameLen >> NS;
+  auto newbuf = [&](int L, int C, int deint) { pl.buf.push_back(make_plane_tensor(nullptr, L, C, P, deint)); return (int)pl.buf.size() - 1; };
+  struct Level { int L, w0, w1, wd, n0, n1, n0d, w2, c0, c1, Cdec; };
+  std::vector<Level> lv(NS + 1);
+  for (int l = 0; l <= NS; ++l) {
+    Level& v = lv[l];
+    v.L = kFrameLen >> l;
+    v.Cdec = W >> (NS - l);                       // decoder channels at this level
+    v.w0 = newbuf(v.L, W, 0);
+    v.w1 = newbuf(v.L, W, 0);
+    v.wd = l < NS ? newbuf(v.L, W, 1) : -1;
+    v.n0 = newbuf(v.L, Nn, 0);
+    v.n1 = newbuf(v.L, Nn, 0);
+    v.n0d = gln ? newbuf(v.L, Nn, 1) : -1;
+    v.c0 = v.c1 = v.w2 = -1;
+    if (l < NS) { v.c0 = newbuf(v.L, v.Cdec, 0); v.c1 = newbuf(v.L, v.Cdec, 0); }
+    if (l > 0 && gln) v.w2 = newbuf(v.L, W >> (NS - l), 0);     // depthwise result of the up-conv that leaves this level
   }
-  int64_t off = 0;
-  for (int i = 0; i < PB_COUNT; ++i) { pl.buf_off[i] = off; off += pl.buf[i].frame_bytes; }
-  pl.act_bytes_per_frame = off;
 
   // narrow -> narrow convs (20 -> 20): taps-in-N by default; the tap-shift kernel is within 5 % here (measured 5.6 vs 5.3 ms per
   // step: nine N = 32 MMAs per K step issue-bound vs the tap-sum epilogue) and can be selected for experiments
@@ -122,9 +124,10 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
     }
     ++layer;   // the tanh gate's entry
   };
-  // one stack of bottleneck blocks (nscm.py:183-217) on `cur`; returns the buffer that holds the result
-  auto stack = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int Ls, int Cw, int cur, int b0, int b1, int n0, int n1, int last_out,
-                   bool vec_in) {
+  // one stack of bottleneck blocks (nscm.py:183-217) on `cur` at level `lvl` with ping-pong images b0 / b1; returns the buffer that
+  // holds the result
+  auto stack = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, const Level& lvl, int Cw, int cur, int b0, int b1, int last_out, bool vec_in) {
+    const int Ls = lvl.L, n0 = lvl.n0, n1 = lvl.n1, n0d = lvl.n0d;
     for (int i = 0; i < c.n_blocks; ++i) {
       const bool flat = i == c.n_blocks - 1;
       int out = (cur == b0) ? b1 : b0;
@@ -132,7 +135,6 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
       const int post = flat ? NSC_ACT_NONE : NSC_ACT_LRELU;
       if (gln) {   // gated_bottleneck (nn_core_operator.py:82-112): k1 -> [k15 gate * tanh(k15 gate)] -> k9 + residual
         const int d = c.dilations[i];
-        const int n0d = n0 == PB_N0 ? PB_N0D : PB_M0D;
         const int k1_out = d == 2 ? n0d : n0;
         const bool vec = vec_in && i == 0;
         add(v, vl, vec ? PK_GEN : PK_X, Ls, vec ? 1 : Cw, Nn, 1, 1, 1, NSC_ACT_LRELU, vec ? -1 : cur, k1_out, -1, RES_NONE, NSC_ACT_NONE, 1);
@@ -157,22 +159,31 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
     }
     return cur;
   };
-  // encoder (nscm.py:219-237)
-  add(pl.enc, pl.enc_layer, PK_GEN, L, 1, W, 55, 1, 1, NSC_ACT_LRELU, -1, PB_W0, -1, RES_NONE, NSC_ACT_NONE, 1);
-  int cur = stack(pl.enc, pl.enc_layer, L, W, PB_W0, PB_W0, PB_W1, PB_N0, PB_N1, PB_WD, false);
-  add(pl.enc, pl.enc_layer, PK_X, L, W, W, 9, 1, 2, NSC_ACT_LRELU, cur, PB_H0, -1, RES_NONE, NSC_ACT_NONE, 1);
-  cur = stack(pl.enc, pl.enc_layer, H, W, PB_H0, PB_H0, PB_H1, PB_M0, PB_M1, -1, false);
-  add(pl.enc, pl.enc_layer, PK_T, H, W, 1, 55, 1, 1, NSC_ACT_TANH, cur, -1, -1, RES_NONE, NSC_ACT_NONE, 1);
-  // decoder (nscm.py:239-260)
-  cur = stack(pl.dec, pl.dec_layer, H, W, PB_H1, PB_H0, PB_H1, PB_M0, PB_M1, -1, true);   // first block writes the buffer that is not `cur`
-  if (gln) {   // separable up-conv (nscm.py:175-177): depthwise k9 -> pointwise + bias + leaky ReLU -> sub-pixel shuffle
-    add(pl.dec, pl.dec_layer, PK_DW, H, W, W, 9, 1, 1, NSC_ACT_NONE, cur, PB_H2, -1, RES_NONE, NSC_ACT_NONE, 1, 1);
-    add(pl.dec, pl.dec_layer, PK_X, H, W, W, 1, 1, 1, NSC_ACT_LRELU, PB_H2, PB_C0, -1, RES_NONE, NSC_ACT_NONE, 2, 2);
-  } else {
-    add(pl.dec, pl.dec_layer, PK_X, H, W, W, 9, 1, 1, NSC_ACT_LRELU, cur, PB_C0, -1, RES_NONE, NSC_ACT_NONE, 2);
+  // encoder (nscm.py:219-237): stem, then per stage [blocks, stride-2 conv], blocks, code head
+  add(pl.enc, pl.enc_layer, PK_GEN, kFrameLen, 1, W, 55, 1, 1, NSC_ACT_LRELU, -1, lv[0].w0, -1, RES_NONE, NSC_ACT_NONE, 1);
+  int cur = lv[0].w0;
+  for (int s = 0; s < NS; ++s) {
+    cur = stack(pl.enc, pl.enc_layer, lv[s], W, cur, lv[s].w0, lv[s].w1, lv[s].wd, false);     // last block writes the de-interleaved image
+    add(pl.enc, pl.enc_layer, PK_X, lv[s].L, W, W, 9, 1, 2, NSC_ACT_LRELU, cur, lv[s + 1].w0, -1, RES_NONE, NSC_ACT_NONE, 1);
+    cur = lv[s + 1].w0;
   }
-  cur = stack(pl.dec, pl.dec_layer, L, Wd, PB_C0, PB_C0, PB_C1, PB_N0, PB_N1, -1, false);
-  add(pl.dec, pl.dec_layer, PK_T, L, Wd, 1, 55, 1, 1, NSC_ACT_NONE, cur, -1, -1, RES_NONE, NSC_ACT_NONE, 1);
+  cur = stack(pl.enc, pl.enc_layer, lv[NS], W, cur, lv[NS].w0, lv[NS].w1, -1, false);
+  add(pl.enc, pl.enc_layer, PK_T, lv[NS].L, W, 1, 55, 1, 1, NSC_ACT_TANH, cur, -1, -1, RES_NONE, NSC_ACT_NONE, 1);
+  // decoder (nscm.py:239-260): per stage [blocks, up-conv + sub-pixel shuffle], blocks, output head
+  cur = stack(pl.dec, pl.dec_layer, lv[NS], W, lv[NS].w1, lv[NS].w0, lv[NS].w1, -1, true);   // first block writes the buffer that is not `cur`
+  int C = W;
+  for (int l = NS; l > 0; --l) {
+    const int Ll = lv[l].L;
+    if (gln) {   // separable up-conv (nscm.py:175-177): depthwise k9 -> pointwise + bias + leaky ReLU -> sub-pixel shuffle
+      add(pl.dec, pl.dec_layer, PK_DW, Ll, C, C, 9, 1, 1, NSC_ACT_NONE, cur, lv[l].w2, -1, RES_NONE, NSC_ACT_NONE, 1, 1);
+      add(pl.dec, pl.dec_layer, PK_X, Ll, C, C, 1, 1, 1, NSC_ACT_LRELU, lv[l].w2, lv[l - 1].c0, -1, RES_NONE, NSC_ACT_NONE, 2, 2);
+    } else {
+      add(pl.dec, pl.dec_layer, PK_X, Ll, C, C, 9, 1, 1, NSC_ACT_LRELU, cur, lv[l - 1].c0, -1, RES_NONE, NSC_ACT_NONE, 2);
+    }
+    C /= 2;
+    cur = stack(pl.dec, pl.dec_layer, lv[l - 1], C, lv[l - 1].c0, lv[l - 1].c0, lv[l - 1].c1, -1, false);
+  }
+  add(pl.dec, pl.dec_layer, PK_T, kFrameLen, C, 1, 55, 1, 1, NSC_ACT_NONE, cur, -1, -1, RES_NONE, NSC_ACT_NONE, 1);
 
   int64_t woff = 0;
   auto size_w = [&](std::vector<PlaneConv>& v) {
@@ -184,7 +195,10 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
       pl.w_off.push_back(woff);
       const int64_t b = plane_wpack_bytes(t);
       woff += align_up(b < 0 ? 0 : b, 1024);
-      if (b < 0) pl.wpack_bytes = -1;
+      if (b < 0) {
+        pl.wpack_bytes = -1;
+        if (getenv("NSC_PLANE_DEBUG")) fprintf(stderr, "plane plan: no launch plan for kind %d k%d d%d s%d %d->%d L%d shuffle %d glu %d\n", pc.kind, pc.K, pc.dil, pc.stride, pc.Cin, pc.Cout, pc.Lin, pc.shuffle, pc.glu);
+      }
     }
   };
   size_w(pl.enc);
@@ -202,15 +216,15 @@ int64_t plane_codec_flag_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
 
 int64_t plane_codec_act_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
   int64_t total = 0;
-  for (int i = 0; i < PB_COUNT; ++i) total += align_up(pl.buf[i].frame_bytes * Bc, 1024);
+  for (const PlaneTensor& t : pl.buf) total += align_up(t.frame_bytes * Bc, 1024);
   return total + 1024;
 }
 
 // Resolves the buffer ids to addresses inside `act` (sized for Bc frames), attaches parameters and packed weights.
 void plane_bind(PlaneCodecPlan& pl, const CodecLayout& lay, const float* params, void* act, int64_t Bc, void* wpack) {
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(act) + 1023) & ~(uintptr_t)1023);
-  uint8_t* addr[PB_COUNT];
-  for (int i = 0; i < PB_COUNT; ++i) { addr[i] = base; base += align_up(pl.buf[i].frame_bytes * Bc, 1024); }
+  std::vector<uint8_t*> addr(pl.buf.size());
+  for (size_t i = 0; i < pl.buf.size(); ++i) { addr[i] = base; base += align_up(pl.buf[i].frame_bytes * Bc, 1024); }
   size_t li = 0;
   auto fix = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, const std::vector<PlaneCodecPlan::Io>& io, const std::vector<int>& sep) {
     for (size_t i = 0; i < v.size(); ++i, ++li) {
@@ -274,8 +288,10 @@ int plane_clear_flags(PlaneCodecPlan& pl, cudaStream_t st) {
   return NSC_OK;
 }
 
-// encoder: x (nb, 512) -> fcode (nb, Lc);  decoder: code (nb, Lc) -> out (nb, 512)
-int plane_run_encoder(PlaneCodecPlan& pl, const float* x, int64_t nb, float* fcode, cudaStream_t st) {
+// encoder: x' = xscale * (x - xsub) (nb, 512) -> fcode (nb, Lc) [may be null when the quantiser is folded into the head];
+// decoder: code (nb, Lc) -> out (nb, 512) [may be null when the cascade accumulation is folded into the head]
+int plane_run_encoder(PlaneCodecPlan& pl, const float* x, const float* xsub, float xscale, int64_t nb, float* fcode, const HeadFold& fold,
+                      cudaStream_t st) {
   NSC_TRY(plane_clear_flags(pl, st));
   int fused_no = 0;
   for (size_t i = 0; i < pl.enc.size(); ++i) {
@@ -283,14 +299,14 @@ int plane_run_encoder(PlaneCodecPlan& pl, const float* x, int64_t nb, float* fco
     if (plane_try_block(pl, pl.enc, pl.enc_block, i, nb, &fused_no, st, &rc)) { NSC_TRY(rc); i += 2; continue; }
     PlaneConv t = pl.enc[i];
     t.B = nb * t.bmul;
-    if (t.Cin == 1) t.xvec = x;
-    if (t.Cout == 1) t.yvec = fcode;
+    if (t.Cin == 1) { t.xvec = x; t.xsub = xsub; t.xscale = xscale; }     // the stem applies the cascade's input arithmetic
+    if (t.Cout == 1) { t.yvec = fcode; t.fold = fold; }
     NSC_TRY(plane_launch(t, st));
   }
   return NSC_OK;
 }
 
-int plane_run_decoder(PlaneCodecPlan& pl, const float* code, int64_t nb, float* out, cudaStream_t st) {
+int plane_run_decoder(PlaneCodecPlan& pl, const float* code, int64_t nb, float* out, const HeadFold& fold, cudaStream_t st) {
   NSC_TRY(plane_clear_flags(pl, st));
   int fused_no = 0;
   for (size_t i = 0; i < pl.dec.size(); ++i) {
@@ -300,7 +316,7 @@ int plane_run_decoder(PlaneCodecPlan& pl, const float* code, int64_t nb, float* 
     t.B = nb * t.bmul;
     if (t.Cin == 1) t.xvec = code;
     if (t.res_mode == RES_ADD_BCAST) t.resvec = code;
-    if (t.Cout == 1) t.yvec = out;
+    if (t.Cout == 1) { t.yvec = out; t.fold = fold; }
     NSC_TRY(plane_launch(t, st));
   }
   return NSC_OK;

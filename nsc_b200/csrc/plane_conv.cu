@@ -165,10 +165,10 @@ __global__ void plane_to_f32_kernel(PlaneTensor t, float* __restrict__ y, int y_
 
 // ------------------------------------------------------------------------------------------------
 // depthwise FIR over the rows of a wide image (Keras SeparableConv1D's depthwise half, nscm.py:175-177): one thread per
-// (frame, position, 8-channel chunk); the K row reads of neighbouring positions overlap in L1.  SAME padding comes from the
-// image's zero rows (K <= 17).  fp32 arithmetic on hi + lo, result split back into planes.
+// (frame, block of 8 positions, 8-channel chunk) slides over 8 + K - 1 rows, so every row is read twice instead of K times.
+// SAME padding comes from the image's zero rows (K <= 17).  fp32 arithmetic on hi + lo, result split back into planes.
 // ------------------------------------------------------------------------------------------------
-__global__ void plane_depthwise_kernel(PlaneTensor in, PlaneTensor out, const float* __restrict__ w, int K, int C, int L, int64_t B) {
+__global__ void __launch_bounds__(256) plane_depthwise_kernel(PlaneTensor in, PlaneTensor out, const float* __restrict__ w, int K, int C, int L, int64_t B) {
   __shared__ float s_w[17 * 128];
   const int nch = in.spp * 8;
   for (int i = threadIdx.x; i < K * nch * 8; i += blockDim.x) {
@@ -176,22 +176,34 @@ __global__ void plane_depthwise_kernel(PlaneTensor in, PlaneTensor out, const fl
     s_w[i] = c < C ? __ldg(w + (int64_t)t * C + c) : 0.f;
   }
   __syncthreads();
-  const int padL = (K - 1) / 2;
-  const int64_t total = B * (int64_t)L * nch;
+  const int padL = (K - 1) / 2, nblk = L / 8;
+  const int64_t total = B * (int64_t)nblk * nch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % nch);
-    const int pos = (int)((i / nch) % L);
-    const int64_t b = i / ((int64_t)nch * L);
+    const int pos0 = (int)((i / nch) % nblk) * 8;
+    const int64_t b = i / ((int64_t)nch * nblk);
     const uint8_t* img = in.base + b * in.frame_bytes;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < K; ++t) {
-      float v[8];
-      pt_load8(in, img, pos + t - padL, g, v);        // rows -8 .. L + 7 exist (zero rows)
-      const float* wt = s_w + (t * nch + g) * 8;
+    float acc[8][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], wt[e], acc[e]);
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
+    for (int r = 0; r < 8 + K - 1; ++r) {
+      float v[8];
+      pt_load8(in, img, pos0 - padL + r, g, v);        // rows -8 .. L + 7 exist (zero rows)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int t = r - o;
+        if (t >= 0 && t < K) {
+          const float* wt = s_w + (t * nch + g) * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(v[e], wt[e], acc[o][e]);
+        }
+      }
     }
-    pt_store8(out, out.base + b * out.frame_bytes, pos, g, acc);
+    uint8_t* oimg = out.base + b * out.frame_bytes;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) pt_store8(out, oimg, pos0 + o, g, acc[o]);
   }
 }
 
@@ -375,6 +387,7 @@ struct TParams {
   uint32_t *in_ready, *in_free, *out_ready, *out_free;
   int out_free_target;       // arrivals that free a frame slot of `out`: its consumer's CTAs per frame
   unsigned long long* stats; // optional counters (fused block kernel)
+  HeadFold fold;             // k55 heads: hard quantiser / cascade accumulation in the epilogue (plane.cuh)
 };
 
 // spill slots: the quarters of the current and the previous tile; the k55 head has no per-tile barrier after its reads (no staged
@@ -484,8 +497,13 @@ __device__ __forceinline__ void t_body(const TParams& p) {
   __shared__ uint64_t w_full, a_full[8], a_empty[8], acc_full[2], acc_empty[2];
   __shared__ uint64_t so_ready[2], so_free[2];      // ring mode: output windows handed to / returned by the storer warp (by tile parity)
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_qbins[C == 1 ? 256 : 1];       // code head: the quantiser's bins
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if constexpr (C == 1) {
+    if (p.fold.q_bins != nullptr)
+      for (int k = tid; k < p.fold.q_n; k += blockDim.x) s_qbins[k] = __ldg(p.fold.q_bins + k);
+  }
   const bool ring_out = (C != 1) && p.out_ready != nullptr;   // fused block: a dedicated warp stores and publishes (the CTA has spare warps)
   const uint32_t wslab_bytes = (uint32_t)p.N * 128u;
   uint8_t* sW = smem;
@@ -545,10 +563,31 @@ __device__ __forceinline__ void t_body(const TParams& p) {
       uint8_t* const orow = (C == 1) ? nullptr : p.out.base + pt_frame_off(p.out, f) + 8 * 128;   // position 0 of the packed image
       const int ring0 = (int)((it * 128u) & (kORing - 1));      // ring row of this frame's position 0 (frames are whole tiles)
       int done_rows = 0;                                        // positions of this frame already handed to the copy engine
-      float* const yrow = (C == 1) ? p.yvec + f * p.L : nullptr;
+      float* const yrow = (C == 1 && p.yvec != nullptr) ? p.yvec + f * p.L : nullptr;
       auto store_row = [&](int row, const float (&r)[NCHMAX]) {
         if constexpr (C == 1) {
-          yrow[row] = apply_act(r[0] + bias[0], p.act);
+          const float v = apply_act(r[0] + bias[0], p.act);
+          if (yrow) yrow[row] = v;
+          const int64_t gi = f * p.L + row;
+          if (p.fold.q_bins != nullptr) {
+            // hard scalar quantiser (nn_core_operator.py:140-164), the arithmetic of quantize_kernel to the bit: fp32 distance, a
+            // separate fp32 multiply by alpha, arg-max with the lowest index on ties (ascending scan, strictly greater)
+            const float alpha = __ldg(p.fold.q_alpha);
+            float best = -INFINITY;
+            int besti = -1;
+            for (int k = 0; k < p.fold.q_n; ++k) {
+              const float lg = __fmul_rn(alpha, fabsf(__fsub_rn(v, s_qbins[k])));
+              if (besti < 0 || lg > best) { best = lg; besti = k; }
+            }
+            if (besti < 0) besti = 0;
+            if (p.fold.q_idx) p.fold.q_idx[gi] = (uint8_t)besti;
+            if (p.fold.q_code) p.fold.q_code[gi] = __fadd_rn(__fmul_rn(1.f - p.fold.q_iq, v), __fmul_rn(p.fold.q_iq, s_qbins[besti]));
+          }
+          if (p.fold.acc != nullptr) {       // decoded (+)= out / res_scalar (cmrl.py:522-531, :822-830), the arithmetic of accum_div_kernel
+            const float q = v / p.fold.div;
+            p.fold.acc[gi] = p.fold.acc_first ? q : p.fold.acc[gi] + q;
+            if (p.fold.quot) p.fold.quot[gi] = q;
+          }
         } else {
           float v[8];
 #pragma unroll
@@ -1728,6 +1767,7 @@ TParams make_tparams(const PlaneConv& c, const TPlan& pl, int cta0, int ncta) {
   p.in_ready = p.in_free = p.out_ready = p.out_free = nullptr;
   p.out_free_target = 1;
   p.stats = nullptr;
+  p.fold = c.fold;
   return p;
 }
 
@@ -1855,7 +1895,7 @@ int plane_narrow_kind() {
 bool plane_conv_supported(const PlaneConv& c) {
   if (c.planes != 1 && c.planes != 2) return false;
   if (c.kind == PK_DW)
-    return c.Cin == c.Cout && c.Cin > 32 && c.Cin <= 128 && c.K >= 1 && c.K <= 17 && c.dil == 1 && c.stride == 1 && c.shuffle == 1 &&
+    return c.Cin == c.Cout && c.Cin > 32 && c.Cin <= 128 && c.K >= 1 && c.K <= 17 && (c.Lin & 7) == 0 && c.dil == 1 && c.stride == 1 && c.shuffle == 1 &&
            c.res_mode == RES_NONE && !c.in.packed && !c.in.deint && !c.out.packed && !c.out.deint && c.in.rows == c.Lin && c.out.rows == c.Lin;
   if (c.kind == PK_T) { TPlan pl; return plan_t(c, &pl); }
   XParams p;
@@ -1941,8 +1981,8 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     char dname[32];
     snprintf(dname, sizeof(dname), "pD%d_k%d_c%d", c.planes, c.K, c.Cin);
     ProfScope prof(st, dname, 2.0 * (double)c.B * c.Lin * c.K * c.Cin, 2.0 * (double)c.B * pt_real_bytes(c.Lin, c.Cin, c.planes));
-    const int64_t total = c.B * (int64_t)c.Lin * (c.in.spp * 8);
-    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
+    const int64_t total = c.B * (int64_t)(c.Lin / 8) * (c.in.spp * 8);
+    const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
     plane_depthwise_kernel<<<blocks, 256, 0, st>>>(c.in, c.out, c.w, c.K, c.Cin, c.Lin, c.B);
     NSC_LAUNCH_OK();
     return NSC_OK;
@@ -1955,7 +1995,9 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.kind == PK_T) {
     TPlan pl;
     NSC_CHECK_ARG(plan_t(c, &pl), "plane engine: unsupported taps-in-N layer (k%d d%d %d->%d)", c.K, c.dil, c.Cin, c.Cout);
-    NSC_CHECK_ARG(c.Cout > 1 || c.yvec != nullptr, "plane engine: head without an output vector");
+    NSC_CHECK_ARG(c.Cout > 1 || c.yvec != nullptr || c.fold.acc != nullptr || c.fold.q_code != nullptr || c.fold.q_idx != nullptr,
+                  "plane engine: head without an output vector");
+    NSC_CHECK_ARG(c.fold.q_bins == nullptr || (c.fold.q_n >= 1 && c.fold.q_n <= 256 && c.fold.q_alpha != nullptr), "plane engine: bad quantiser fold");
     const int64_t grid = c.B < sm_count() ? c.B : sm_count();
     const TParams p = make_tparams(c, pl, 0, (int)grid);
     snprintf(name, sizeof(name), "pT%d_k%dd%d_c%dto%d", c.planes, c.K, c.dil, c.Cin, c.Cout);

@@ -96,6 +96,63 @@ __global__ void subpixel_dgrad_weights_kernel(const float* __restrict__ w, float
   }
 }
 
+// gate product y = a * b (gated_bottleneck, nn_core_operator.py:102): ga += gy * b, gb += gy * a
+__global__ void mul_backward_kernel(const float* __restrict__ gy, const float* __restrict__ a, const float* __restrict__ b,
+                                    float* __restrict__ ga, float* __restrict__ gb, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = gy[i];
+    ga[i] += g * b[i];
+    gb[i] += g * a[i];
+  }
+}
+
+// depthwise half of the separable up-conv (y[b,c,p] = sum_t x[b,c,p + t - padL] w[t,c]): dw[t,c] += sum_{b,p} g[b,c,p] x[b,c,p + t - padL].
+// grid (C, splits); every thread keeps the K partial sums of its (frame, position) share, the block reduces and adds them atomically.
+constexpr int kDwMaxK = 17;
+__global__ void __launch_bounds__(256) depthwise_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dw,
+                                                              int64_t B, int L, int C, int K, int padL, int frames_per_split) {
+  const int c = blockIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.y * frames_per_split;
+  const int64_t b1 = b0 + frames_per_split < B ? b0 + frames_per_split : B;
+  float acc[kDwMaxK];
+#pragma unroll
+  for (int t = 0; t < kDwMaxK; ++t) acc[t] = 0.f;
+  for (int64_t b = b0; b < b1; ++b) {
+    const float* xr = x + (b * C + c) * (int64_t)L;
+    const float* gr = g + (b * C + c) * (int64_t)L;
+    for (int p = threadIdx.x; p < L; p += blockDim.x) {
+      const float gv = gr[p];
+#pragma unroll
+      for (int t = 0; t < kDwMaxK; ++t) {
+        const int q = p + t - padL;
+        if (t < K && q >= 0 && q < L) acc[t] = fmaf(gv, xr[q], acc[t]);
+      }
+    }
+  }
+  __shared__ float red[8][kDwMaxK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < kDwMaxK; ++t) {
+    float v = acc[t];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float v = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
+    atomicAdd(dw + (int64_t)threadIdx.x * C + c, v);
+  }
+}
+
+// taps of the depthwise data gradient: wf[t][c] = w[K - 1 - t][c] (odd K: same SAME padding)
+__global__ void flip_taps_kernel(const float* __restrict__ w, float* __restrict__ wf, int K, int C) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * C; i += gridDim.x * blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    wf[i] = w[(int64_t)(K - 1 - t) * C + c];
+  }
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<float4*>(dst)[i];
@@ -646,11 +703,43 @@ int walk_codec(const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* pa
 int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params, float* grads, char* act_base, char* grad_base,
                   int64_t B, float* gpre, float* wflip, float* gtmp, int precision, void* wpack, bool need_dx, cudaStream_t st) {
   auto G = [&](const float* p) { return reinterpret_cast<float*>(grad_base + (reinterpret_cast<const char*>(p) - act_base)); };
+  if (r.op == OP_MUL) {   // y = x * res
+    const int64_t n = B * (int64_t)r.Cin * r.Lin;
+    ProfScope prof(st, "gate_product_backward", 4.0 * (double)n, 28.0 * (double)n);
+    mul_backward_kernel<<<ew_grid(n), 256, 0, st>>>(G(r.y), r.x, r.res, G(r.x), G(r.res), n);
+    NSC_LAUNCH_OK();
+    return NSC_OK;
+  }
+  if (r.op == OP_DEPTHWISE) {   // taps (K, C) at the head of the separable layer's table entry; no bias, no activation
+    const LayerInfo& li = lay.layers[r.layer];
+    NSC_CHECK_ARG(r.K <= kDwMaxK && (r.K & 1) && (int64_t)r.K * r.Cin <= kWflipFloats, "training: depthwise layer with k = %d", r.K);
+    const int padL = (r.K - 1) / 2;
+    int splits = ceil_div(8 * sm_count(), r.Cin);
+    if (splits > B) splits = (int)B;
+    if (splits < 1) splits = 1;
+    const int fps = (int)ceil_div64(B, splits);
+    splits = (int)ceil_div64(B, fps);
+    {
+      ProfScope prof(st, "wgrad_depthwise", 2.0 * B * r.Lin * (double)r.K * r.Cin, 8.0 * B * (double)r.Lin * r.Cin);
+      depthwise_wgrad_kernel<<<dim3(r.Cin, splits), 256, 0, st>>>(r.x, G(r.y), grads + li.off, B, r.Lin, r.Cin, r.K, padL, fps);
+      NSC_LAUNCH_OK();
+    }
+    if (!need_dx) return NSC_OK;
+    flip_taps_kernel<<<ew_grid((int64_t)r.K * r.Cin), 256, 0, st>>>(params + li.off, wflip, r.K, r.Cin);
+    NSC_LAUNCH_OK();
+    NSC_TRY(launch_depthwise(G(r.y), wflip, gtmp, B, r.Lin, r.Cin, r.K, 1, 1, 0, 0, st));
+    const int64_t n4 = B * (int64_t)r.Cin * r.Lin / 4;
+    add_inplace_kernel<<<ew_grid(n4), 256, 0, st>>>(G(r.x), gtmp, n4);
+    NSC_LAUNCH_OK();
+    return NSC_OK;
+  }
   int Lout, padL;
   same_padding(r.Lin, r.K, r.dil, r.stride, &Lout, &padL);
   const LayerInfo& li = lay.layers[r.layer];
-  const float* w = params + li.off;
-  float* dw = grads + li.off;
+  // (the pointwise half of a separable layer sits behind the depthwise taps of the same table entry)
+  const int64_t woff = li.off + (r.op == OP_POINTWISE ? (int64_t)r.kdw * r.Cin : 0);
+  const float* w = params + woff;
+  float* dw = grads + woff;
   float* db = dw + (int64_t)r.K * r.Cin * r.Cout;
   {
     ProfScope prof(st, "epilogue_backward", (double)B * Lout * r.Cout * 4.0, (double)B * Lout * r.Cout * 16.0);
@@ -742,7 +831,6 @@ int check_train_args(const nsc_codec_cfg* cfgs, int n, const float* const* param
   NSC_CHECK_ARG(cfgs && n >= 1 && n <= NSC_MAX_CODECS && params && ws, "training: bad arguments");
   for (int i = 0; i < n; ++i) {
     NSC_TRY(validate_cfg(&cfgs[i]));
-    NSC_CHECK_ARG(cfgs[i].resnet_type == 0, "training: only resnet_type 'bottleneck' is built (codec %d)", i);
     NSC_CHECK_ARG(params[i] != nullptr, "training: params[%d] is null", i);
   }
   NSC_CHECK_ARG(B >= 1, "training: empty batch");
@@ -758,7 +846,7 @@ extern "C" {
 int64_t nsc_train_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B) {
   if (cfgs == nullptr || n_codecs < 1 || n_codecs > NSC_MAX_CODECS || B < 1) return -1;
   for (int i = 0; i < n_codecs; ++i)
-    if (nsc::validate_cfg(&cfgs[i]) != NSC_OK || cfgs[i].resnet_type != 0) return -1;
+    if (nsc::validate_cfg(&cfgs[i]) != NSC_OK) return -1;
   return nsc::train_layout(cfgs, n_codecs, B).total;
 }
 

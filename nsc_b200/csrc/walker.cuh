@@ -72,13 +72,19 @@ struct Carver {
 
 
 
-// One conv layer as executed (training tape)
+// One layer as executed (training tape)
+enum TapeOp { OP_CONV = 0, OP_MUL = 1, OP_DEPTHWISE = 2, OP_POINTWISE = 3 };
 struct ConvRec {
   int layer;                 // index into the layer table (parameter offsets)
   const float* x;
   float* y;
   const float* res;
   int Lin, Cin, Cout, K, dil, stride, act, res_mode, post_act, shuffle;
+  // OP_CONV: a conv layer.  OP_MUL: y = x * res elementwise (the gate product of a gated block, kept apart from the tanh gate's conv
+  // in training so that both factors are on the tape).  OP_DEPTHWISE / OP_POINTWISE: the two halves of a separable conv (ONE table
+  // entry: taps (K, Cin), then the pointwise (Cin, Cout) kernel, then the bias); for OP_POINTWISE K is 1 and `kdw` the depthwise K.
+  int op = OP_CONV;
+  int kdw = 0;
 };
 
 struct Walker {
@@ -136,11 +142,38 @@ struct Walker {
     else rc = launch_conv(a, st);   // 1-channel stem / heads and odd shapes stay on the FFMA engine
   }
 
+  // training only: y = a * b elementwise (n floats), both factors kept on the tape
+  void mul(const float* a, const float* b, float** yslot, int L, int C) {
+    if (dry || rc != NSC_OK) return;
+    *yslot = arena->take(B * (int64_t)C * L);
+    if (arena->used > arena->cap) { set_error("training arena overflow"); rc = NSC_E_WORKSPACE; return; }
+    if (tape) {
+      ConvRec r{-1, a, *yslot, b, L, C, C, 0, 1, 1, NSC_ACT_NONE, RES_MUL, NSC_ACT_NONE, 1};
+      r.op = OP_MUL;
+      tape->push_back(r);
+    }
+    if (launch) rc = launch_mul(*yslot, a, b, B * (int64_t)C * L, st);
+  }
+
   // Keras SeparableConv1D: depthwise (k, cin, 1) -> pointwise (1, cin, cout) + bias + activation
-  void sepconv(const float* x, float* tmp, float* y, int Lin, int Cin, int Cout, int K, int act, int shuffle) {
+  void sepconv(const float* x, float* tmp, float** yslot, int Lin, int Cin, int Cout, int K, int act, int shuffle) {
     const LayerInfo* li = next_layer(K, Cin, Cout, 1);
     if (dry || rc != NSC_OK) return;
-    if (arena) { set_error("training of the separable ('gln') up-conv is not built yet"); rc = NSC_E_INVALID; return; }
+    if (arena) {   // training: both halves' outputs are kept
+      tmp = arena->take(B * (int64_t)Cin * Lin);
+      *yslot = arena->take(B * (int64_t)Cout * Lin);
+      if (arena->used > arena->cap) { set_error("training arena overflow"); rc = NSC_E_WORKSPACE; return; }
+      if (tape) {
+        ConvRec d{(int)cursor - 1, x, tmp, nullptr, Lin, Cin, Cin, K, 1, 1, NSC_ACT_NONE, RES_NONE, NSC_ACT_NONE, 1};
+        d.op = OP_DEPTHWISE;
+        tape->push_back(d);
+        ConvRec q{(int)cursor - 1, tmp, *yslot, nullptr, Lin, Cin, Cout, 1, 1, 1, act, RES_NONE, NSC_ACT_NONE, shuffle};
+        q.op = OP_POINTWISE; q.kdw = K;
+        tape->push_back(q);
+      }
+      if (!launch) return;
+    }
+    float* y = *yslot;
     const float* dw = params + li->off;
     const float* pw = dw + (int64_t)K * Cin;
     const float* bias = pw + (int64_t)Cin * Cout;
@@ -170,7 +203,13 @@ struct Walker {
       } else {                      // gated_bottleneck, nn_core_operator.py:82-112 (gate kernel 15 hard-coded)
         conv(cur, &nar[0], L, C, cfg.narrow, 1, 1, 1, NSC_ACT_LRELU);
         conv(nar[0], &nar[1], L, cfg.narrow, cfg.narrow, 15, d, 1, NSC_ACT_NONE);
-        conv(nar[0], &nar[2], L, cfg.narrow, cfg.narrow, 15, d, 1, NSC_ACT_TANH, nar[1], RES_MUL);
+        if (arena) {   // training: the tanh gate's output and the product are separate tape entries
+          float* gate = nullptr;
+          conv(nar[0], &gate, L, cfg.narrow, cfg.narrow, 15, d, 1, NSC_ACT_TANH);
+          mul(nar[1], gate, &nar[2], L, cfg.narrow);
+        } else {
+          conv(nar[0], &nar[2], L, cfg.narrow, cfg.narrow, 15, d, 1, NSC_ACT_TANH, nar[1], RES_MUL);
+        }
         conv(nar[2], &wide[out_idx], L, cfg.narrow, wide_layer, cfg.k_plain, 1, 1, NSC_ACT_NONE, cur, rmode, post);
       }
       cur = wide[out_idx];
@@ -207,7 +246,7 @@ struct Walker {
       const int o = (cur + 1) % 3, t = (cur + 2) % 3;
       const int r = cfg.strides[s];
       if (cfg.resnet_type == 0) conv(wide[cur], &wide[o], L, C, C, 9, 1, 1, NSC_ACT_LRELU, nullptr, RES_NONE, NSC_ACT_NONE, r);
-      else sepconv(wide[cur], wide[t], wide[o], L, C, C, 9, NSC_ACT_LRELU, r);   // _up_sampling_mod :169-181
+      else sepconv(wide[cur], wide[t], &wide[o], L, C, C, 9, NSC_ACT_LRELU, r);   // _up_sampling_mod :169-181
       cur = o;
       in = wide[cur];
       C /= r;

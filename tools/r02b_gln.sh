@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_depth.py tests/test_gpu_plane.py -x -q -k "gln or codec_forward or plane_path_matches or golden" > gpurun_out/r02b_gln_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_depth.py tests/test_gpu_plane.py -x -q -k "gln or codec_forward or plane_path_matches or golden or chunk" > gpurun_out/r02b_gln_pytest.log 2>&1
 tail -15 gpurun_out/r02b_gln_pytest.log
 timeout 300 python - > gpurun_out/r02b_gln_bench.log 2>&1 <<'PY'
 import sys, json, argparse
@@ -10,8 +10,8 @@ import torch, bench
 from nsc_b200 import _lib
 lib = _lib.load()
 args = argparse.Namespace(precision='tc_f16x3')
-for rt, st, fr in (('gln', (2,), 4144), ('gln', (2,), 16576), ('bottleneck', (2,), 4144)):
+for rt, st, fr in (('gln', (2,), 4144), ('bottleneck', (2, 2), 4144), ('gln', (2, 2), 4144)):
     r = bench.measure_variant(args, 1, 0, 'cuda:0', lib, rt, st, frames=fr)
     print(json.dumps(r))
 PY
-cat gpurun_out/r02b_gln_bench.log | cut -c1-1500
+cat gpurun_out/r02b_gln_bench.log | cut -c1-1300
