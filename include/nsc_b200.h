@@ -231,6 +231,18 @@ int nsc_codec_encode(const nsc_codec_cfg* cfg, const float* params, const float*
 int nsc_codec_decode(const nsc_codec_cfg* cfg, const float* params, const float* code, int64_t B, float* out,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Prepared workspaces (serving loops at a fixed batch size).  On the plane engine a call first clears the zero rows of the
+ * activation images and packs every layer's weights into fp16 operand slabs -- at streaming batch sizes that costs more than the
+ * convs.  nsc_prepare does it once into `workspace` and registers (workspace, kind, cfgs, params pointers, pass size); a later
+ * nsc_codec_forward / _encode / _decode (kind 0), nsc_cascade_forward (kind 1) or nsc_cq_forward (kind 2) call with the same
+ * workspace, configurations and parameter POINTERS and the same pass size (B below one pass: the same B) skips that part.
+ * The caller prepares again after changing the weights in place, and calls nsc_release(workspace) before freeing or reusing
+ * the buffer for anything else (returns 1 if it was registered).  Configurations outside the plane engine: no-op.
+ * No reference counterpart: TensorFlow keeps its variables resident between sess.run calls (cmrl.py:698-708). */
+int nsc_prepare(int32_t kind, const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host, int64_t B,
+                void* workspace, int64_t workspace_bytes, void* stream);
+int nsc_release(const void* workspace);
+
 /* CMRL cascade, all_modules_feedforward (lpc_variant = 0) / loop of all_modules_feedforward_lpc (= 1):
  *   in_0 = x (times res_scalar if lpc_variant); in_i = res_scalar * (x - sum_{j<i} out_j);
  *   out_i = dec_i(Q(enc_i(in_i))) / res_scalar (codec 0 undivided when lpc_variant = 0); decoded = sum_i out_i.

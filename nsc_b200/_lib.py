@@ -72,6 +72,8 @@ SIGNATURES = {
     "nsc_codec_forward": (_i32, [_cfgp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "nsc_codec_encode": (_i32, [_cfgp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "nsc_codec_decode": (_i32, [_cfgp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "nsc_prepare": (_i32, [_i32, _cfgp, _i32, _ppv, _i64, _vp, _i64, _vp]),
+    "nsc_release": (_i32, [_vp]),
     "nsc_cascade_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),
     "nsc_cascade_forward": (_i32, [_cfgp, _i32, _ppv, _vp, _i64, _f32, _i32, _f32, _i32, _ppv, _ppv, _ppv, _ppv, _vp, _vp, _i64, _vp]),
     "nsc_cq_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),

@@ -202,8 +202,27 @@ class NeuralCodec:
     def _workspace(self, B: int) -> torch.Tensor:
         need = int(_lib.load().nsc_codec_workspace_bytes(C.byref(self._st), B))
         if self._ws is None or self._ws.numel() < need:
+            self.release()                       # a prepared workspace must not outlive its buffer
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.params.device)
         return self._ws
+
+    def prepare(self, B: int) -> None:
+        """Serving loops at a fixed batch size: clear the activation images' zero rows and pack the weights ONCE into this codec's
+        workspace (nsc_prepare); later calls with B frames (any B >= one engine pass) skip that part.  Call again after changing
+        self.params in place.  No reference counterpart -- TensorFlow keeps its variables resident between sess.run calls."""
+        ws = self._workspace(B)
+        _lib.check(_lib.load().nsc_prepare(0, C.byref(self._st), 1, _lib.ptr_array([self.params]), B, _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr()), 'prepare')
+
+    def release(self) -> None:
+        if getattr(self, '_ws', None) is not None:
+            _lib.load().nsc_release(_lib.ptr(self._ws))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     # nscm.py:262-335 -------------------------------------------------------------------------
     def computational_graph_end2end_quan_on(self, encoded, the_share, is_quan_on, *, want_soft=False,
@@ -305,8 +324,25 @@ class CMRL:
         if need < 0:
             _lib.check(-1, 'workspace')
         if self._ws is None or self._ws.numel() < need:
+            self.release()                       # a prepared workspace must not outlive its buffer
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.lsf_params.device)
         return self._ws
+
+    def prepare(self, B: int, cq: bool = True) -> None:
+        """As NeuralCodec.prepare, for feedforward_lpc (cq=True) or all_modules_feedforward (cq=False) at batch size B."""
+        ws = self._workspace(B, cq)
+        _lib.check(_lib.load().nsc_prepare(2 if cq else 1, self._cfgs, len(self.codecs), _lib.ptr_array([c.params for c in self.codecs]), B,
+                                           _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'prepare')
+
+    def release(self) -> None:
+        if getattr(self, '_ws', None) is not None:
+            _lib.load().nsc_release(_lib.ptr(self._ws))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     def _per_codec_outputs(self, B, dev, want_stats, want_outs):
         idx = [torch.empty((B, c.cfg.code_length), dtype=torch.uint8, device=dev) for c in self.codecs]
@@ -366,3 +402,55 @@ class CMRL:
         return r
 
     all_modules_feedforward_lpc = feedforward_lpc
+
+
+class GraphedCall:
+    """A fixed-batch call of this package captured ONCE in a CUDA graph and replayed per batch (serving loops: at 128 frames the
+    ~30 dependent kernels of a codec are a few microseconds each, so launch gaps are a visible share of the call).  The inputs are
+    static device buffers (`inputs`); `run(*tensors)` copies into them, replays, and returns the static outputs (`outputs`, overwritten
+    by the next replay).  Build it with NeuralCodec.graphed_forward / CMRL.graphed_feedforward_lpc, which prepare the workspace first
+    (nsc_prepare) so that neither weight packing nor border clearing is part of the graph."""
+
+    def __init__(self, fn, inputs: Sequence[torch.Tensor], owner):
+        self.inputs = list(inputs)
+        self._owner = owner                      # keeps the workspace (whose address the graph holds) alive
+        dev = self.inputs[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up outside the capture (lazy module loads, cudaFuncSetAttribute)
+            for _ in range(2):
+                fn(*self.inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.inputs)
+
+    def run(self, *tensors):
+        if len(tensors) != len(self.inputs):
+            raise ValueError(f"expected {len(self.inputs)} input tensors")
+        for dst, src in zip(self.inputs, tensors):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
+
+
+def _graphed_codec_forward(self: NeuralCodec, B: int, the_share: bool = False, is_quan_on: float = 1.0) -> GraphedCall:
+    """computational_graph_end2end_quan_on at batch size B as a CUDA graph (inputs: x (B, 512))."""
+    self.prepare(B)
+    x = torch.zeros((B, FRAME), dtype=torch.float32, device=self.params.device)
+    return GraphedCall(lambda a: self.computational_graph_end2end_quan_on(a, the_share, is_quan_on), [x], self)
+
+
+def _graphed_feedforward_lpc(self: CMRL, B: int, the_share: bool = False, is_quan_on: float = 1.0) -> GraphedCall:
+    """feedforward_lpc at batch size B as a CUDA graph (inputs: x (B, 512), lpc_x (B, 16))."""
+    self.prepare(B, cq=True)
+    dev = self.lsf_params.device
+    x = torch.zeros((B, FRAME), dtype=torch.float32, device=dev)
+    # a valid LSF row for the warm-up / capture passes (the uniform grid of A(z) = 1)
+    lsf = (torch.arange(1, _lib.LPC_ORDER + 1, device=dev, dtype=torch.float32) * (math.pi / (_lib.LPC_ORDER + 1))).repeat(B, 1).contiguous()
+    return GraphedCall(lambda a, b: self.feedforward_lpc(a, b, the_share, is_quan_on), [x, lsf], self)
+
+
+NeuralCodec.graphed_forward = _graphed_codec_forward
+CMRL.graphed_feedforward_lpc = _graphed_feedforward_lpc

@@ -3,6 +3,10 @@
 // kernel launches.  The topology is written ONCE (struct Walker): a dry walk enumerates the conv layers in the
 // order TensorFlow would create their variables -- which defines the flat parameter image -- and the live walk
 // issues the launches.  Frames are processed in chunks so the activation workspace stays bounded.
+#include <string.h>
+
+#include <mutex>
+
 #include "plane_codec.cuh"
 #include "walker.cuh"
 
@@ -76,6 +80,49 @@ int run_codec_chunk(const nsc_codec_cfg& cfg, const CodecLayout& lay, const floa
 }
 
 
+// ---- prepared workspaces (nsc_prepare / nsc_release) ------------------------------------------------------------
+// The once-per-weights part of a plane-path call -- clearing the activation images' zero rows and packing every layer's fp16
+// operand slabs (one small launch per layer) -- costs more than the convs themselves at streaming batch sizes.  nsc_prepare runs
+// it once into a caller-owned workspace and registers (workspace, entry point, configurations, parameter pointers, pass size);
+// a later call that matches all of them skips it.  Nothing else is cached: the packed weights live in the caller's workspace.
+struct PreparedWs {
+  const void* ws;
+  int kind, n;
+  int64_t Bc;
+  nsc_codec_cfg cfgs[NSC_MAX_CODECS];
+  const float* params[NSC_MAX_CODECS];
+};
+static std::mutex g_prep_mu;
+static std::vector<PreparedWs> g_prepared;
+
+static bool prepared_same(const PreparedWs& e, int kind, const nsc_codec_cfg* cfgs, const float* const* params, int n, int64_t Bc) {
+  if (e.kind != kind || e.n != n || e.Bc != Bc) return false;
+  for (int i = 0; i < n; ++i)
+    if (memcmp(&e.cfgs[i], &cfgs[i], sizeof(nsc_codec_cfg)) != 0 || e.params[i] != params[i]) return false;
+  return true;
+}
+// true: `ws` holds this call's zero rows and packed weights.  A registered workspace that is used differently is forgotten (the
+// call is about to overwrite it).
+static bool prepared_lookup(const void* ws, int kind, const nsc_codec_cfg* cfgs, const float* const* params, int n, int64_t Bc) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (size_t i = 0; i < g_prepared.size(); ++i)
+    if (g_prepared[i].ws == ws) {
+      if (prepared_same(g_prepared[i], kind, cfgs, params, n, Bc)) return true;
+      g_prepared.erase(g_prepared.begin() + (long)i);
+      return false;
+    }
+  return false;
+}
+static void prepared_register(const void* ws, int kind, const nsc_codec_cfg* cfgs, const float* const* params, int n, int64_t Bc) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (size_t i = 0; i < g_prepared.size(); ++i)
+    if (g_prepared[i].ws == ws) { g_prepared.erase(g_prepared.begin() + (long)i); break; }
+  PreparedWs e;
+  e.ws = ws; e.kind = kind; e.n = n; e.Bc = Bc;
+  for (int i = 0; i < n; ++i) { e.cfgs[i] = cfgs[i]; e.params[i] = params[i]; }
+  g_prepared.push_back(e);
+}
+
 // ---- plane path (plane_codec.cuh): per-call state of a codec or a cascade of codecs -------------------------------
 struct PlaneCascade {
   std::vector<PlaneCodecPlan> plans;
@@ -116,9 +163,10 @@ struct PlaneCascade {
     }
     return act * nr + w + 2 * align_up(Bc * (kFrameLen / 2) * (int64_t)sizeof(float), 1024) + 2048;
   }
-  // carves `ws`, clears the images' zero rows, binds every layer and packs all weights (once per call)
+  // carves `ws`, clears the images' zero rows, binds every layer and packs all weights (once per call; `prepared`: the workspace
+  // already holds the zero rows and the packed weights of exactly this call, see nsc_prepare)
   int setup(const nsc_codec_cfg* cfgs, const CodecLayout* lays, const float* const* params, int n, int64_t Bc, void* ws,
-            int64_t ws_bytes, cudaStream_t st) {
+            int64_t ws_bytes, cudaStream_t st, bool prepared = false) {
     if (ws_bytes < bytes(cfgs, n, Bc)) {
       set_error("codec (plane path): workspace %lld < %lld bytes", (long long)ws_bytes, (long long)bytes(cfgs, n, Bc));
       return NSC_E_WORKSPACE;
@@ -135,14 +183,14 @@ struct PlaneCascade {
     uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
     uint8_t* act0 = p;
     p += region_bytes * n_regions;
-    NSC_CUDA_OK(cudaMemsetAsync(act0, 0, (size_t)(region_bytes * n_regions), st));
+    if (!prepared) NSC_CUDA_OK(cudaMemsetAsync(act0, 0, (size_t)(region_bytes * n_regions), st));
     for (int i = 0; i < n; ++i) {
       plane_bind(plans[i], lays[i], params[i], act0 + region_bytes * region[i], Bc, p);
       p += align_up(plans[i].wpack_bytes, 1024);
       plans[i].flags = reinterpret_cast<uint32_t*>(p);
       plans[i].flag_frames = Bc;
       p += plane_codec_flag_bytes(plans[i], Bc);
-      NSC_TRY(plane_codec_pack(plans[i], st));
+      if (!prepared) NSC_TRY(plane_codec_pack(plans[i], st));
     }
     fcode = reinterpret_cast<float*>(p);
     p += align_up(Bc * (kFrameLen / 2) * (int64_t)sizeof(float), 1024);
@@ -252,7 +300,7 @@ static int codec_run(const nsc_codec_cfg* cfg, const float* params, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (nsc::PlaneCascade::supported(cfg, 1)) {
     nsc::PlaneCascade pcs;
-    NSC_TRY(pcs.setup(cfg, &lay, &params, 1, Bc, workspace, workspace_bytes, st));
+    NSC_TRY(pcs.setup(cfg, &lay, &params, 1, Bc, workspace, workspace_bytes, st, nsc::prepared_lookup(workspace, 0, cfg, &params, 1, Bc)));
     for (int64_t b0 = 0; b0 < B; b0 += Bc) {
       const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
       if (which == 2)
@@ -424,7 +472,7 @@ int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float
   if (plane) {
     const int64_t head = 2 * nsc::align_up(Bc * kFrameLen * (int64_t)sizeof(float), 256);   // cascade_chunk's codec input / output
     NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head,
-                      (cudaStream_t)stream));
+                      (cudaStream_t)stream, nsc::prepared_lookup(workspace, 1, cfgs, params_ptrs_host, n_codecs, Bc)));
   }
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
@@ -477,7 +525,8 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
     nsc::Carver cv(workspace, workspace_bytes);
     cv.take(Bc * P); cv.take(Bc * (P + 1)); cv.take(Bc * kFrameLen);
     const int64_t head = cv.used + 2 * nsc::align_up(Bc * kFrameLen * (int64_t)sizeof(float), 256);
-    NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head, st));
+    NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head, st,
+                      nsc::prepared_lookup(workspace, 2, cfgs, params_ptrs_host, n_codecs, Bc)));
   }
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
@@ -504,6 +553,49 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
   // one thread per frame, 512 dependent steps: latency-bound, so it runs ONCE over the whole batch when the caller keeps poly
   if (synthesized && poly != nullptr) NSC_TRY(nsc_lpc_synth(poly, decoded, B, synthesized, stream));
   return NSC_OK;
+}
+
+// ---- prepared workspaces ---------------------------------------------------------------------------------------
+int nsc_prepare(int32_t kind, const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host, int64_t B,
+                void* workspace, int64_t workspace_bytes, void* stream) {
+  NSC_CHECK_ARG(kind >= 0 && kind <= 2, "nsc_prepare: kind %d (0 codec, 1 cascade, 2 collaborative quantisation)", kind);
+  NSC_CHECK_ARG(cfgs && params_ptrs_host && workspace && n_codecs >= 1 && n_codecs <= NSC_MAX_CODECS && (kind != 0 || n_codecs == 1) && B >= 1,
+                "nsc_prepare: bad arguments");
+  for (int i = 0; i < n_codecs; ++i) {
+    NSC_TRY(nsc::validate_cfg(&cfgs[i]));
+    NSC_CHECK_ARG(params_ptrs_host[i] != nullptr, "nsc_prepare: params[%d] is null", i);
+  }
+  if (!nsc::PlaneCascade::supported(cfgs, n_codecs)) return NSC_OK;      // the layer-by-layer engines keep no per-weights state
+  const int64_t chunk = chunk_for(cfgs, n_codecs);
+  const int64_t Bc = B < chunk ? B : chunk;
+  const int64_t need = kind == 0 ? nsc::PlaneCascade::bytes(cfgs, 1, Bc)
+                                 : cascade_ws_bytes(cfgs, n_codecs, Bc) + (kind == 2 ? cq_extra_bytes(Bc) : 0);
+  if (workspace_bytes < need) {
+    nsc::set_error("nsc_prepare: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    return NSC_E_WORKSPACE;
+  }
+  // the same carve as the entry point of this kind
+  int64_t head = 0;
+  if (kind >= 1) head = 2 * nsc::align_up(Bc * kFrameLen * (int64_t)sizeof(float), 256);
+  if (kind == 2) {
+    nsc::Carver cv(workspace, workspace_bytes);
+    cv.take(Bc * NSC_LPC_ORDER); cv.take(Bc * (NSC_LPC_ORDER + 1)); cv.take(Bc * kFrameLen);
+    head += cv.used;
+  }
+  std::vector<nsc::CodecLayout> lays;
+  for (int i = 0; i < n_codecs; ++i) lays.push_back(nsc::make_layout(cfgs[i]));
+  nsc::PlaneCascade pcs;
+  NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head,
+                    (cudaStream_t)stream, false));
+  nsc::prepared_register(workspace, kind, cfgs, params_ptrs_host, n_codecs, Bc);
+  return NSC_OK;
+}
+
+int nsc_release(const void* workspace) {
+  std::lock_guard<std::mutex> lk(nsc::g_prep_mu);
+  for (size_t i = 0; i < nsc::g_prepared.size(); ++i)
+    if (nsc::g_prepared[i].ws == workspace) { nsc::g_prepared.erase(nsc::g_prepared.begin() + (long)i); return 1; }
+  return 0;
 }
 
 // ---- single blocks on channels-last tensors (operator surface of nn_core_operator.py) ---------------

@@ -564,6 +564,8 @@ __device__ __forceinline__ void t_body(const TParams& p) {
       const int ring0 = (int)((it * 128u) & (kORing - 1));      // ring row of this frame's position 0 (frames are whole tiles)
       int done_rows = 0;                                        // positions of this frame already handed to the copy engine
       float* const yrow = (C == 1 && p.yvec != nullptr) ? p.yvec + f * p.L : nullptr;
+      float pre_own = 0.f, pre_prev = 0.f;                      // output head: running sums of the rows this thread may finish
+      int pre_row = -1;
       auto store_row = [&](int row, const float (&r)[NCHMAX]) {
         if constexpr (C == 1) {
           const float v = apply_act(r[0] + bias[0], p.act);
@@ -575,7 +577,20 @@ __device__ __forceinline__ void t_body(const TParams& p) {
             const float alpha = __ldg(p.fold.q_alpha);
             float best = -INFINITY;
             int besti = -1;
-            for (int k = 0; k < p.fold.q_n; ++k) {
+            int k = 0;
+            for (; k + 4 <= p.fold.q_n; k += 4) {       // four independent logits per step; the selects keep the lowest index
+              const float l0 = __fmul_rn(alpha, fabsf(__fsub_rn(v, s_qbins[k])));
+              const float l1 = __fmul_rn(alpha, fabsf(__fsub_rn(v, s_qbins[k + 1])));
+              const float l2 = __fmul_rn(alpha, fabsf(__fsub_rn(v, s_qbins[k + 2])));
+              const float l3 = __fmul_rn(alpha, fabsf(__fsub_rn(v, s_qbins[k + 3])));
+              float m = l0;
+              int mi = k;
+              if (l1 > m) { m = l1; mi = k + 1; }
+              if (l2 > m) { m = l2; mi = k + 2; }
+              if (l3 > m) { m = l3; mi = k + 3; }
+              if (besti < 0 || m > best) { best = m; besti = mi; }
+            }
+            for (; k < p.fold.q_n; ++k) {
               const float lg = __fmul_rn(alpha, fabsf(__fsub_rn(v, s_qbins[k])));
               if (besti < 0 || lg > best) { best = lg; besti = k; }
             }
@@ -585,7 +600,8 @@ __device__ __forceinline__ void t_body(const TParams& p) {
           }
           if (p.fold.acc != nullptr) {       // decoded (+)= out / res_scalar (cmrl.py:522-531, :822-830), the arithmetic of accum_div_kernel
             const float q = v / p.fold.div;
-            p.fold.acc[gi] = p.fold.acc_first ? q : p.fold.acc[gi] + q;
+            // (the running sum of this thread's two candidate rows was fetched before the accumulator wait)
+            p.fold.acc[gi] = p.fold.acc_first ? q : (row == pre_row ? pre_own : pre_prev) + q;
             if (p.fold.quot) p.fold.quot[gi] = q;
           }
         } else {
@@ -616,6 +632,13 @@ __device__ __forceinline__ void t_body(const TParams& p) {
       };
       for (int j = 0; j < T; ++j, ++it) {
         const uint32_t acc_i = it & 1u;
+        if constexpr (C == 1) {
+          if (p.fold.acc != nullptr && !p.fold.acc_first) {      // a thread finishes its own row or the one 32 above it
+            pre_row = (j * 4 + q) * 32 + lane;
+            pre_own = p.fold.acc[f * p.L + pre_row];
+            pre_prev = pre_row >= 32 ? p.fold.acc[f * p.L + pre_row - 32] : 0.f;
+          }
+        }
         mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
         tc_fence_after();
         float acc[NCHMAX], up[NCHMAX], down[NCHMAX];

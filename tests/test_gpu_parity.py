@@ -427,3 +427,27 @@ def test_empty_batch_and_errors():
     with pytest.raises(ValueError):
         nn.conv1d(torch.zeros(1, 8, 3, device=DEV), 4, 3, dilation_rate=2, strides=2,
                   params=(torch.zeros(3, 3, 4, device=DEV), torch.zeros(4, device=DEV)))
+
+
+def test_cuda_vs_reference_run():
+    """The CUDA path, through the C ABI, against vectors produced by the REFERENCE'S OWN utilities.py / lpc_utilities.py run in the
+    build container (tests/golden/make_ref_golden.py: unmodified source files, third-party libraries replaced by independent
+    stand-ins; committed as tests/golden/reference_run.npz): framing, the utterance filters, LPC analysis at test / train time, LSF ->
+    polynomial, the sub-framed residual filter and LPC synthesis."""
+    from nsc_b200 import lpc_utilities as lu, utilities as ut
+    g = dict(np.load(os.path.join(GOLD, 'reference_run.npz')))
+    sig = cu(g['utt'])
+    assert np.array_equal(ut.utterance_to_segment(sig, True).cpu().numpy(), g['seg_plain'].astype(np.float32))
+    assert rel_err(ut.utterance_to_segment(sig, False).cpu().numpy(), g['seg_windowed']) < 1e-6
+    assert rel_err(ut.highpass_filter(sig, out_f64=True).cpu().numpy(), g['highpass']) < 1e-9
+    assert rel_err(ut.empha_filter(sig, out_f64=True).cpu().numpy(), g['empha']) < 1e-9
+    lsf = lu.lpc_analysis_at_test(cu(g['at_test_in'])).cpu().numpy()
+    assert lsf.shape == (6, 16) and np.abs(lsf - g['at_test_lsf']).max() < 1e-6
+    tr = lu.lpc_analysis_at_train(cu(g['at_train_in'])[:, :, None]).cpu().numpy()
+    assert np.abs(tr - g['at_train_lsf']).max() < 1e-6
+    poly = lu.lsf2poly_after_quan(cu(g['at_train_lsf'].astype(np.float32)), 16).cpu().numpy()
+    assert rel_err(poly, g['poly']) < 1e-5
+    res = lu.lpc_analysis_get_residual(cu(g['at_train_in'])[:, :, None], cu(g['poly'])).cpu().numpy()
+    assert rel_err(res, g['residual']) < 1e-5
+    syn = lu.lpc_synthesizer_tr(cu(g['poly']), cu(g['residual'])).cpu().numpy()
+    assert rel_err(syn, g['synth']) < 1e-5

@@ -225,3 +225,124 @@ def test_plane_path_matches_layer_by_layer_engine_at_full_size(monkeypatch, resn
         subprocess.run([sys.executable, '-c', code, path], check=True, env=e, timeout=300)
         outs.append(np.load(path))
     assert rel_err(outs[0], outs[1]) < 1e-4
+
+
+def test_folded_cascade_and_quantiser_are_bit_identical_to_the_stand_alone_kernels():
+    """The plane path folds the cascade's input arithmetic into the stem (in = res_scalar * (x - decoded)), the hard quantiser into the
+    code head's epilogue and the accumulation decoded += out / res_scalar into the output head's (cmrl.py:522-531, :810-830;
+    nn_core_operator.py:140-164).  NSC_PLANE_FOLD=0 runs the stand-alone kernels instead: every output must agree to the bit, and the
+    folded program launches 3 kernels fewer per codec and pass (2 for the first codec of a cascade with res_scalar = 1)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from util import ar_frames\n"
+        "from nsc_b200 import codec, _lib\n"
+        "from oracle import ref_lpc\n"
+        "cfg = codec.CodecConfig(resnet_type='bottleneck')\n"
+        "cm = codec.CMRL([codec.NeuralCodec(cfg, device='cuda', seed=5 + i) for i in range(3)], res_scalar=2.0)\n"
+        "x = torch.from_numpy(ar_frames(300, 512, seed=4, std=0.3)).cuda()\n"
+        "lsf = torch.from_numpy(ref_lpc.lpc_analysis_windows(ar_frames(300, 1024, seed=5), 16).astype(np.float32)).cuda()\n"
+        "l0 = _lib.load().nsc_launch_count()\n"
+        "r = cm.feedforward_lpc(x, lsf, False, 1.0)\n"
+        "n = _lib.load().nsc_launch_count() - l0\n"
+        "c = cm.all_modules_feedforward(x, False, 1.0, want_outs=True)\n"
+        "e = cm.codecs[0].computational_graph_end2end_quan_on(x, False, 1.0)\n"
+        "torch.cuda.synchronize()\n"
+        "np.savez(sys.argv[1], launches=n, dec=r['decoded'].cpu().numpy(), syn=r['synthesized'].cpu().numpy(),\n"
+        "         idx=np.stack([i.cpu().numpy() for i in r['idx']]), cdec=c['decoded'].cpu().numpy(),\n"
+        "         couts=np.stack([o.cpu().numpy() for o in c['outs']]), eidx=e['idx'].cpu().numpy(), eout=e['out'].cpu().numpy(),\n"
+        "         ecode=e['code'].cpu().numpy())\n"
+    ) % (root, os.path.join(root, 'tests'))
+    res = {}
+    for tag, env in (('fold', {}), ('plain', {'NSC_PLANE_FOLD': '0'})):
+        path = '/tmp/nsc_fold_%s.npz' % tag
+        e = dict(os.environ); e.update(env)
+        subprocess.run([sys.executable, '-c', code, path], check=True, env=e, timeout=300)
+        res[tag] = dict(np.load(path))
+    for k in ('dec', 'syn', 'idx', 'cdec', 'couts', 'eidx', 'eout', 'ecode'):
+        assert np.array_equal(res['fold'][k], res['plain'][k]), k
+    assert int(res['plain']['launches']) - int(res['fold']['launches']) == 3 * 3
+
+
+def test_prepared_workspace_skips_the_per_weights_work_and_changes_no_bit():
+    """nsc_prepare (include/nsc_b200.h): zero rows + packed weights once per weights, not once per call.  Same bits as the plain call,
+    about half the launches at batch 128 (one pack launch per layer gone); a changed configuration, batch size or parameter pointer
+    falls back to the full call; in-place weight changes need a new prepare (documented contract)."""
+    from nsc_b200 import codec, _lib
+    from oracle import ref_lpc
+    from util import ar_frames
+    lib = _lib.load()
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
+    gc = codec.NeuralCodec(cfg, device=DEV, seed=21)
+    x = torch.from_numpy(ar_frames(128, 512, seed=2, std=0.3)).to(DEV)
+    l0 = lib.nsc_launch_count()
+    a = gc.computational_graph_end2end_quan_on(x, False, 1.0)
+    n_plain = lib.nsc_launch_count() - l0
+    gc.prepare(128)
+    l0 = lib.nsc_launch_count()
+    b = gc.computational_graph_end2end_quan_on(x, False, 1.0)
+    n_prep = lib.nsc_launch_count() - l0
+    torch.cuda.synchronize()
+    assert all(torch.equal(a[k], b[k]) for k in ('out', 'idx', 'code', 'floating_code'))
+    assert n_prep <= n_plain - 25, (n_plain, n_prep)
+    # encode / decode share the codec's workspace layout
+    e = gc.encode(x)
+    assert torch.equal(e['idx'], a['idx']) and torch.equal(gc.decode_indices(e['idx']), a['out'])
+    # another batch size below one pass: full call again (and the registration is dropped)
+    c = gc.computational_graph_end2end_quan_on(x[:64], False, 1.0)
+    assert torch.equal(c['out'], a['out'][:64])
+    assert lib.nsc_release(_lib.ptr(gc._ws)) == 0
+    # weights changed in place: prepare again
+    gc.prepare(128)
+    gc.params.mul_(1.01)
+    gc.prepare(128)
+    d = gc.computational_graph_end2end_quan_on(x, False, 1.0)
+    gc.release()
+    f = gc.computational_graph_end2end_quan_on(x, False, 1.0)
+    torch.cuda.synchronize()
+    assert torch.equal(d['out'], f['out']) and not torch.equal(d['out'], a['out'])
+    # collaborative quantisation entry point
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=5 + i) for i in range(2)], res_scalar=1.0)
+    lsf = torch.from_numpy(ref_lpc.lpc_analysis_windows(ar_frames(128, 1024, seed=5), 16).astype(np.float32)).to(DEV)
+    r0 = cm.feedforward_lpc(x, lsf, False, 1.0)
+    cm.prepare(128)
+    r1 = cm.feedforward_lpc(x, lsf, False, 1.0)
+    r2 = cm.feedforward_lpc(x, lsf, False, 1.0)
+    torch.cuda.synchronize()
+    for k in ('decoded', 'synthesized', 'lsf_idx'):
+        assert torch.equal(r0[k], r1[k]) and torch.equal(r0[k], r2[k])
+    assert all(torch.equal(i0, i1) for i0, i1 in zip(r0['idx'], r1['idx']))
+    assert lib.nsc_release(_lib.ptr(cm._ws)) == 1 and lib.nsc_release(_lib.ptr(cm._ws)) == 0
+
+
+def test_cuda_graph_replay_of_a_fixed_batch_call_is_bit_identical():
+    """codec.GraphedCall: the batch-128 codec call and the collaborative-quantisation call captured once (after nsc_prepare) and
+    replayed -- same bits as the plain calls, for new inputs on every replay."""
+    from nsc_b200 import codec
+    from oracle import ref_lpc
+    from util import ar_frames
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
+    gc = codec.NeuralCodec(cfg, device=DEV, seed=31)
+    g = gc.graphed_forward(128)
+    for seed in (1, 2):
+        x = torch.from_numpy(ar_frames(128, 512, seed=seed, std=0.3)).to(DEV)
+        r = g.run(x)
+        got = {k: r[k].clone() for k in ('out', 'idx', 'code')}
+        gc.release()
+        ref = gc.computational_graph_end2end_quan_on(x, False, 1.0)
+        gc.prepare(128)
+        torch.cuda.synchronize()
+        assert all(torch.equal(got[k], ref[k]) for k in got)
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=5 + i) for i in range(2)], res_scalar=1.0)
+    gq = cm.graphed_feedforward_lpc(64)
+    x = torch.from_numpy(ar_frames(64, 512, seed=3, std=0.3)).to(DEV)
+    lsf = torch.from_numpy(ref_lpc.lpc_analysis_windows(ar_frames(64, 1024, seed=4), 16).astype(np.float32)).to(DEV)
+    r = gq.run(x, lsf)
+    got = {k: r[k].clone() for k in ('decoded', 'synthesized', 'lsf_idx')}
+    gidx = [t.clone() for t in r['idx']]
+    cm.release()
+    ref = cm.feedforward_lpc(x, lsf, False, 1.0)
+    torch.cuda.synchronize()
+    assert all(torch.equal(got[k], ref[k]) for k in got) and all(torch.equal(a, b) for a, b in zip(gidx, ref['idx']))
