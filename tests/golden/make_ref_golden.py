@@ -181,7 +181,137 @@ def generate():
     return out
 
 
+# ------------------------------------------------------------------------------------------------ the neural part
+OUT_NN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_run_nn.npz')
+TOPOLOGIES = [('bottleneck', (2,)), ('gln', (2,)), ('bottleneck', (2, 2)), ('gln', (2, 2))]
+
+
+def load_reference_nn():
+    """-> (nn_core_operator, neural_speech_coding_module) of the reference, executed from their own source files on tf_shim."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import tf_shim
+    sys.path.remove(here)
+    saved = install_stubs()
+    tf = tf_shim.build()
+    extra = {'tensorflow': tf, 'librosa': _Anything('librosa'),
+             'tensorflow.python.ops': _Anything('ops'), 'tensorflow.python.ops.math_ops': _Anything('math_ops'),
+             'tensorflow.python.ops.random_ops': _Anything('random_ops'), 'tensorflow.python.framework.dtypes': _Anything('dtypes')}
+    saved.update({k: sys.modules.get(k) for k in extra if k not in saved})
+    sys.modules.update(extra)
+    names = ('utilities', 'lpc_utilities', 'constants', 'loss_terms_and_measures', 'nn_core_operator', 'neural_speech_coding_module')
+    own = {k: sys.modules.pop(k, None) for k in names}
+    sys.path.insert(0, REF)
+    try:
+        nn = importlib.import_module('nn_core_operator')
+        nscm = importlib.import_module('neural_speech_coding_module')
+    finally:
+        sys.path.remove(REF)
+        for k in names:
+            sys.modules.pop(k, None)
+            if own[k] is not None:
+                sys.modules[k] = own[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert os.path.dirname(os.path.abspath(nn.__file__)) == REF and os.path.dirname(os.path.abspath(nscm.__file__)) == REF
+    return tf_shim, nn, nscm
+
+
+def nn_inputs():
+    x = np.stack([ar_signal(512, 40 + i) for i in range(3)]) * 3.0
+    x[1] *= 0.05                         # one quiet frame
+    return x.astype(np.float32)
+
+
+def generate_nn():
+    import contextlib
+    import io
+    import torch
+    tf_shim, nn, nscm = load_reference_nn()
+    out = {'x': nn_inputs()}
+    xt = torch.from_numpy(out['x'])[:, :, None]
+    sink = io.StringIO()                 # the reference prints shapes while it builds the graph
+    for ti, (rt, strides) in enumerate(TOPOLOGIES):
+        # the reference selects the block type by a module-level switch it star-imports from constants.py (constants.py:13-14)
+        nscm.resnet_type = rt
+        m = object.__new__(nscm.neuralSpeechCodingModule)          # __init__ loads the training corpus from the author's disk
+        m._bottleneck_kernel_and_dilation = [9, 9, 100, 20, 1, 2]  # README.md:75
+        captured = {}
+        real_q = nn.scalar_softmax_quantization
+
+        def spy(floating_code, alpha, bins, is_quan_on, the_share, code_length, n, _c=captured):
+            _c['floating'] = floating_code
+            soft, code = real_q(floating_code, alpha, bins, is_quan_on, the_share, code_length, n)
+            _c['soft'], _c['code'] = soft, code
+            return soft, code
+
+        nscm.scalar_softmax_quantization = spy
+        for share in (False, True):
+            feed = tf_shim.SeededFeed(seed=100 + ti)
+            tf_shim.set_feed(feed)
+            with contextlib.redirect_stdout(sink), torch.no_grad():
+                r = m.computational_graph_end2end_quan_on(xt, share, 1.0, 32, 'scope_1', list(strides))
+            tag = f"{rt}_{len(strides)}_{'soft' if share else 'hard'}"
+            out[tag + '_out'] = r[4].numpy()
+            out[tag + '_code0'] = r[3].numpy()                      # the_final_code[0, :, 0]: what the reference returns
+            out[tag + '_floating'] = captured['floating'][:, :, 0].numpy()
+            out[tag + '_code'] = captured['code'][:, :, 0].numpy()
+            out[tag + '_softsum'] = captured['soft'].sum(0).sum(0).numpy()
+        out[f"{rt}_{len(strides)}_layers"] = np.array(repr(feed.layers))
+        nscm.scalar_softmax_quantization = real_q
+    # single functions of nn_core_operator.py on their own
+    rng = np.random.RandomState(7)
+    xb = torch.from_numpy(rng.randn(2, 128, 100).astype(np.float32))
+    out['block_x'] = xb.numpy()
+    for name, fn, kw in (('the_bottleneck', nn.the_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=False)),
+                         ('the_bottleneck_flat', nn.the_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=True)),
+                         ('gated_bottleneck', nn.gated_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=False)),
+                         ('gated_bottleneck_decoder', nn.gated_bottleneck_decoder, dict(wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=True))):
+        feed = tf_shim.SeededFeed(seed=200)
+        tf_shim.set_feed(feed)
+        with torch.no_grad():
+            out['block_' + name] = fn(xb, **kw).numpy()
+        out['block_' + name + '_layers'] = np.array(repr(feed.layers))
+    for name, fn, kw in (('conv1d_s2', nn.conv1d, dict(num_filters=24, filter_size=9, strides=2, dilation_rate=1)),
+                         ('conv1d_d3', nn.conv1d, dict(num_filters=8, filter_size=5, strides=1, dilation_rate=3, activation=None)),
+                         ('conv1d_depth', nn.conv1d_depth, dict(num_filters=50, filter_size=9, activation=None)),
+                         ('change_channel', nn.change_channel, dict(the_channel=1, kernel_size=55, dilation_rate=7))):   # dilation is ignored (:52)
+        feed = tf_shim.SeededFeed(seed=300)
+        tf_shim.set_feed(feed)
+        with torch.no_grad():
+            out['op_' + name] = fn(xb, **kw).numpy()
+    # loss terms (loss_terms_and_measures.py:63-84, :130-183, :257-267), star-imported into nn_core_operator's namespace
+    ori = np.stack([ar_signal(512, 60 + i) for i in range(5)]) * 4.0
+    dec = (ori + 0.02 * rng.randn(5, 512)).astype(np.float32)
+    out['loss_ori'], out['loss_dec'] = ori.astype(np.float32), dec
+    with contextlib.redirect_stdout(sink), torch.no_grad():
+        out['loss_mse'] = nn.mse_loss(torch.from_numpy(dec), torch.from_numpy(out['loss_ori'])).numpy()
+        out['loss_mfcc'] = nn.mfcc_loss(torch.from_numpy(dec), torch.from_numpy(out['loss_ori'])).numpy()
+        soft = torch.softmax(torch.from_numpy(rng.randn(3, 64, 32).astype(np.float32)) * 3.0, dim=-1)
+        out['loss_soft'] = soft.numpy()
+        out['loss_quan'] = nn.quan_loss(soft).numpy()
+        out['loss_ent'] = np.asarray(nn.entropy_coding_loss(soft).numpy())
+        out['bitrate'] = np.array([nn.entropy_to_bitrate(2.5, 2), nn.entropy_to_bitrate(2.5, 4)], np.float64)
+    # quantiser incl. exact ties (mid-points between bins) and out-of-range values
+    bins = np.linspace(-1, 1, 32).astype(np.float32)
+    fc = rng.uniform(-1.2, 1.2, size=(2, 256, 1)).astype(np.float32)
+    fc[0, :31, 0] = (bins[:-1] + bins[1:]) / 2
+    out['q_in'] = fc[:, :, 0]
+    for share in (False, True):
+        with contextlib.redirect_stdout(sink), torch.no_grad():
+            soft, code = nn.scalar_softmax_quantization(torch.from_numpy(fc), torch.tensor(-300.0), torch.from_numpy(bins), 1.0, share, 256, 32)
+        out['q_code_' + ('soft' if share else 'hard')] = code[:, :, 0].numpy()
+        out['q_soft_argmax'] = soft.argmax(-1).numpy().astype(np.int64)
+    return out
+
+
 if __name__ == '__main__':
     vec = generate()
     np.savez_compressed(OUT, **vec)
     print('wrote', OUT, {k: v.shape for k, v in vec.items()})
+    vec = generate_nn()
+    np.savez_compressed(OUT_NN, **vec)
+    print('wrote', OUT_NN, {k: v.shape for k, v in vec.items() if not k.endswith('_layers')})

@@ -451,3 +451,56 @@ def test_cuda_vs_reference_run():
     assert rel_err(res, g['residual']) < 1e-5
     syn = lu.lpc_synthesizer_tr(cu(g['poly']), cu(g['residual'])).cpu().numpy()
     assert rel_err(syn, g['synth']) < 1e-5
+
+
+@pytest.mark.parametrize('ti', range(4), ids=['bottleneck_s2', 'gln_s2', 'bottleneck_s4', 'gln_s4'])
+@pytest.mark.parametrize('precision', ['fp32', 'tc_f16x3'])
+def test_cuda_codec_vs_reference_run(ti, precision):
+    """The CUDA codec, through the C ABI, against the output of the REFERENCE'S OWN graph code (nn_core_operator.py + the graph
+    methods of neural_speech_coding_module.py, run on the TensorFlow stand-in of tests/golden/tf_shim.py; fixture
+    tests/golden/reference_run_nn.npz).  Weights: the seeded stream of the generator, laid out through the library's own layer table
+    -- a creation-order or shape disagreement with the reference graph shows up as garbage.  Floating code 1e-4; decoder 1e-4 on
+    the reference run's own codes; hard codes identical wherever the floating codes are not within rounding of a mid-point."""
+    import sys
+    sys.path.insert(0, GOLD)
+    try:
+        import tf_shim
+    finally:
+        sys.path.remove(GOLD)
+    from nsc_b200 import codec
+    rt, st = [('bottleneck', (2,)), ('gln', (2,)), ('bottleneck', (2, 2)), ('gln', (2, 2))][ti]
+    g = dict(np.load(os.path.join(GOLD, 'reference_run_nn.npz')))
+    cfg = codec.CodecConfig(resnet_type=rt, the_strides=st, precision=precision)
+    rng = np.random.RandomState(100 + ti)
+    layers = []
+    for L in codec.layer_table(cfg):          # the LIBRARY'S creation order and shapes
+        shapes = ((L.k, L.cin, 1), (1, L.cin, L.cout), (L.cout,)) if L.separable else ((L.k, L.cin, L.cout), (L.cout,))
+        layers.append(tf_shim.draw_layer(rng, shapes))
+    flat = codec.pack_params_numpy(cfg, layers, -300.0, np.linspace(-1, 1, 32))
+    gc = codec.NeuralCodec(cfg, torch.from_numpy(flat).to(DEV))
+    x = cu(g['x'])
+    tag = f"{rt}_{len(st)}_hard"
+    enc = gc.encode(x)
+    fl = enc['floating_code'].cpu().numpy()
+    assert rel_err(fl, g[tag + '_floating']) < TOL
+    code = enc['code'].cpu().numpy()
+    near_mid = np.abs(np.abs(((g[tag + '_floating'] + 1) * 15.5) % 1.0 - 0.5)) < 1e-3      # within 1e-3 bin widths of a mid-point
+    assert np.array_equal(code[~near_mid], g[tag + '_code'][~near_mid])
+    out = gc.decode(cu(g[tag + '_code'])).cpu().numpy()
+    assert rel_err(out, g[tag + '_out']) < TOL
+    soft = gc.computational_graph_end2end_quan_on(x, True, 1.0)
+    assert rel_err(soft['floating_code'].cpu().numpy(), g[f"{rt}_{len(st)}_soft_floating"]) < TOL
+
+
+def test_cuda_losses_vs_reference_run():
+    """mse_loss / mfcc_loss / quan_loss / entropy_coding_loss on the GPU against the values the reference's own
+    loss_terms_and_measures.py produced on the TensorFlow stand-in (tests/golden/reference_run_nn.npz)."""
+    from nsc_b200 import loss_terms_and_measures as lt
+    g = dict(np.load(os.path.join(GOLD, 'reference_run_nn.npz')))
+    dec, ori = cu(g['loss_dec']), cu(g['loss_ori'])
+    assert rel_err(lt.mse_loss(dec, ori).cpu().numpy(), g['loss_mse']) < 1e-5
+    assert rel_err(lt.mfcc_loss(dec, ori).cpu().numpy(), g['loss_mfcc']) < TOL
+    soft = cu(g['loss_soft'])
+    assert rel_err(lt.quan_loss(soft).cpu().numpy(), g['loss_quan']) < 1e-5
+    assert abs(float(lt.entropy_coding_loss(soft)) - float(g['loss_ent'])) < 1e-4
+    assert np.allclose([lt.entropy_to_bitrate(2.5, 2), lt.entropy_to_bitrate(2.5, 4)], g['bitrate'], rtol=1e-12)

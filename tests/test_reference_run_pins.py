@@ -89,3 +89,142 @@ def test_lsf2poly_residual_synthesis_oracle_equals_the_reference_run():
     assert _rel(syn, g['synth']) < 1e-6
     # the sub-frame weights sum to one, so residual -> synthesis returns the frame (up to the sub-frame state resets)
     assert _rel(g['synth'], g['at_train_in']) < 0.5
+
+
+# ------------------------------------------------------------------------------------------------ the neural part
+import torch
+
+from oracle import ref_codec, ref_nn
+
+FIX_NN = os.path.join(GOLD, 'reference_run_nn.npz')
+TOPOLOGIES = [('bottleneck', (2,)), ('gln', (2,)), ('bottleneck', (2, 2)), ('gln', (2, 2))]
+
+
+def _shim():
+    sys.path.insert(0, GOLD)
+    try:
+        import tf_shim
+    finally:
+        sys.path.remove(GOLD)
+    return tf_shim
+
+
+def seeded_params_like(conv_params, seed):
+    """Variables drawn from RandomState(seed) in the ORACLE'S creation order and shapes -- the generator drew them in the REFERENCE
+    graph's creation order and shapes, so the two sets are identical only if order and shapes agree layer by layer."""
+    rng = np.random.RandomState(seed)
+    draw = _shim().draw_layer
+    return [draw(rng, tuple(tuple(np.asarray(a).shape) for a in layer)) for layer in conv_params]
+
+
+def oracle_codec_for(rt, strides, ti):
+    cfg = ref_codec.OracleCodecCfg(resnet_type=rt, strides=strides)
+    shapes = ref_codec.OracleCodec(cfg, seed=0).conv_params
+    return ref_codec.OracleCodec(cfg, conv_params=seeded_params_like(shapes, 100 + ti))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason="reference tree not present on this box")
+def test_nn_generator_reproduces_the_committed_fixture():
+    sys.path.insert(0, GOLD)
+    try:
+        import make_ref_golden
+        fresh = make_ref_golden.generate_nn()
+    finally:
+        sys.path.remove(GOLD)
+    g = dict(np.load(FIX_NN))
+    assert sorted(fresh) == sorted(g)
+    for k in g:
+        if k.endswith('_layers'):
+            assert str(fresh[k]) == str(g[k]), k
+        else:
+            assert np.allclose(fresh[k], g[k], rtol=0, atol=1e-6), k
+
+
+@pytest.mark.parametrize('ti', range(4), ids=['bottleneck_s2', 'gln_s2', 'bottleneck_s4', 'gln_s4'])
+def test_codec_graph_oracle_equals_the_reference_run(ti):
+    """computational_graph_end2end_quan_on (nscm.py:262-295) built by the reference's OWN code -- _the_encoder_in_each_module,
+    _stack_bottleneck_blocks, the_bottleneck / gated_bottleneck, _down_sampling_mod, _up_sampling_mod(_helper),
+    scalar_softmax_quantization, _the_decoder_in_each_module -- on the TF stand-in, vs the oracle's restatement of it, same weights.
+    Layer count, creation order and shapes must match (the variables are drawn from one seeded stream in creation order);
+    floating code, codes and decoder output must agree to float32 rounding."""
+    rt, strides = TOPOLOGIES[ti]
+    g = dict(np.load(FIX_NN))
+    oc = oracle_codec_for(rt, strides, ti)
+    layers = eval(str(g[f"{rt}_{len(strides)}_layers"]))
+    assert [tuple(tuple(np.asarray(a).shape) for a in layer) for layer in oc.conv_params] == [tuple(l) for l in layers]
+    x = torch.from_numpy(g['x'])[:, :, None]
+    for share in (False, True):
+        tag = f"{rt}_{len(strides)}_{'soft' if share else 'hard'}"
+        with torch.no_grad():
+            r = oc.forward(x, share, 1.0)
+        fl = r['floating_code'][:, :, 0].numpy()
+        assert _rel(fl, g[tag + '_floating']) < 2e-6, tag
+        # identical floating codes -> the hard codes must be the same bins; where the float32 codes differ in the last bits the
+        # argmax may sit on the other side of a mid-point, so compare on the entries whose floating codes agree exactly
+        code = r['code'][:, :, 0].numpy()
+        if share:
+            assert _rel(code, g[tag + '_code']) < 2e-3, tag          # soft code: slope ~ alpha * bin spacing amplifies 1e-6
+        else:
+            same = fl == g[tag + '_floating']
+            assert same.mean() > 0.5 and np.array_equal(code[same], g[tag + '_code'][same]), tag
+            assert (code != g[tag + '_code']).mean() < 0.01, tag
+        assert np.array_equal(code[0], g[tag + '_code0']) or not share and (code[0] != g[tag + '_code0']).mean() < 0.01
+        # decoder on the REFERENCE RUN'S codes (so that a flipped code cannot hide or fake a decoder difference)
+        oc.ps._cursor = 0
+        with torch.no_grad():
+            oc.encoder(x)
+            out = oc.decoder(torch.from_numpy(g[tag + '_code'])[:, :, None])[:, :, 0].numpy()
+        assert _rel(out, g[tag + '_out']) < 5e-6, tag
+
+
+def test_blocks_and_ops_oracle_equals_the_reference_run():
+    """nn_core_operator.py's functions one by one, executed by the reference: conv1d (stride 2; dilation 3), conv1d_depth,
+    change_channel (which IGNORES its dilation_rate argument, :52), the_bottleneck (both is_last_flat), gated_bottleneck,
+    gated_bottleneck_decoder, scalar_softmax_quantization (exact mid-point ties, out-of-range values)."""
+    g = dict(np.load(FIX_NN))
+    xb = torch.from_numpy(g['block_x'])
+    draw = _shim().draw_layer
+
+    def ps_like(layers, seed):
+        rng = np.random.RandomState(seed)
+        return ref_nn.ParamStream([draw(rng, tuple(l)) for l in layers])
+
+    for name, fn, kw in (('the_bottleneck', ref_nn.the_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=False)),
+                         ('the_bottleneck_flat', ref_nn.the_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=True)),
+                         ('gated_bottleneck', ref_nn.gated_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=False)),
+                         ('gated_bottleneck_decoder', ref_nn.gated_bottleneck_decoder, dict(wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=True))):
+        layers = eval(str(g['block_' + name + '_layers']))
+        with torch.no_grad():
+            y = fn(xb, ps=ps_like(layers, 200), **kw).numpy()
+        assert _rel(y, g['block_' + name]) < 2e-6, name
+    for name, fn, kw, layers in (
+            ('conv1d_s2', ref_nn.conv1d, dict(num_filters=24, filter_size=9, strides=2, dilation_rate=1), [((9, 100, 24), (24,))]),
+            ('conv1d_d3', ref_nn.conv1d, dict(num_filters=8, filter_size=5, strides=1, dilation_rate=3, activation=None), [((5, 100, 8), (8,))]),
+            ('conv1d_depth', ref_nn.conv1d_depth, dict(num_filters=50, filter_size=9, activation=None), [((9, 100, 1), (1, 100, 50), (50,))]),
+            ('change_channel', ref_nn.change_channel, dict(the_channel=1, kernel_size=55, dilation_rate=7), [((55, 100, 1), (1,))])):
+        with torch.no_grad():
+            y = fn(xb, ps=ps_like(layers, 300), **kw).numpy()
+        assert y.shape == g['op_' + name].shape and _rel(y, g['op_' + name]) < 2e-6, name
+    bins = np.linspace(-1, 1, 32).astype(np.float32)
+    fc = torch.from_numpy(g['q_in'])[:, :, None]
+    for share in (False, True):
+        soft, code = ref_nn.scalar_softmax_quantization(fc, np.float32(-300.0), bins, 1.0, share, 256, 32)
+        assert np.array_equal(code[:, :, 0].numpy(), g['q_code_' + ('soft' if share else 'hard')]) or \
+            _rel(code[:, :, 0].numpy(), g['q_code_' + ('soft' if share else 'hard')]) < 1e-6
+    idx = ref_nn.quantizer_indices(fc, np.float32(-300.0), bins).numpy().astype(np.int64).reshape(g['q_soft_argmax'].shape)
+    assert np.array_equal(idx, g['q_soft_argmax'])            # the implicit integer code: argmax of the literal softmax, lowest index on ties
+
+
+def test_loss_terms_oracle_equals_the_reference_run():
+    """mse_loss, mfcc_loss (rectangular-window STFT of the 512-sample frame, power / 512, four HTK mel resolutions 8 / 16 / 32 / 128,
+    log, per-resolution RMS distance, mean), quan_loss, entropy_coding_loss and entropy_to_bitrate, executed by the reference
+    (loss_terms_and_measures.py:63-84, :130-183, :257-267)."""
+    from oracle import ref_loss
+    g = dict(np.load(FIX_NN))
+    dec, ori = torch.from_numpy(g['loss_dec']), torch.from_numpy(g['loss_ori'])
+    assert _rel(ref_loss.mse_loss(dec, ori).numpy(), g['loss_mse']) < 1e-6
+    assert _rel(ref_loss.mfcc_loss(dec, ori).numpy(), g['loss_mfcc']) < 1e-5
+    soft = torch.from_numpy(g['loss_soft'])
+    assert _rel(ref_loss.quan_loss(soft).numpy(), g['loss_quan']) < 1e-6
+    assert abs(float(ref_loss.entropy_coding_loss(soft)) - float(g['loss_ent'])) < 1e-5
+    assert np.allclose([ref_loss.entropy_to_bitrate(2.5, 2), ref_loss.entropy_to_bitrate(2.5, 4)], g['bitrate'], rtol=1e-12)
