@@ -199,12 +199,13 @@ def load_reference_nn():
              'tensorflow.python.ops.random_ops': _Anything('random_ops'), 'tensorflow.python.framework.dtypes': _Anything('dtypes')}
     saved.update({k: sys.modules.get(k) for k in extra if k not in saved})
     sys.modules.update(extra)
-    names = ('utilities', 'lpc_utilities', 'constants', 'loss_terms_and_measures', 'nn_core_operator', 'neural_speech_coding_module')
+    names = ('utilities', 'lpc_utilities', 'constants', 'loss_terms_and_measures', 'nn_core_operator', 'neural_speech_coding_module', 'cmrl')
     own = {k: sys.modules.pop(k, None) for k in names}
     sys.path.insert(0, REF)
     try:
         nn = importlib.import_module('nn_core_operator')
         nscm = importlib.import_module('neural_speech_coding_module')
+        nscm.cmrl_module = importlib.import_module('cmrl')
     finally:
         sys.path.remove(REF)
         for k in names:
@@ -295,6 +296,40 @@ def generate_nn():
         out['loss_quan'] = nn.quan_loss(soft).numpy()
         out['loss_ent'] = np.asarray(nn.entropy_coding_loss(soft).numpy())
         out['bitrate'] = np.array([nn.entropy_to_bitrate(2.5, 2), nn.entropy_to_bitrate(2.5, 4)], np.float64)
+    # the cascade graphs of cmrl.py, built by the reference's own CMRL.all_modules_feedforward (:513-543) and
+    # all_modules_feedforward_lpc (:770-830) -- placeholders fed eagerly, tf.py_func bodies from the reference's lpc_utilities.py --
+    # followed by the two lines of _feedforward_lpc that finish the pass (:836-839: decoded = sum of the codec outputs, synthesis)
+    cm_mod = nscm.cmrl_module
+    nscm.resnet_type = 'bottleneck'
+    cq_x = np.stack([ar_signal(512, 80 + i) for i in range(4)]) * 5.0
+    out['cq_x'] = cq_x.astype(np.float32)
+    lsf = cm_mod.lpc_analysis_at_train(out['cq_x'][:, :, None], 16).astype(np.float32)
+    out['cq_lsf'] = lsf
+    for share in (False, True):
+        c = object.__new__(cm_mod.CMRL)
+        c._bottleneck_kernel_and_dilation = [9, 9, 100, 20, 1, 2]
+        c._res_scalar, c._num_resnets, c._the_strides, c._num_bins_for_follower, c._lpc_order = 2.0, 2, [2], [32, 32], 16
+        tf_shim.PLACEHOLDERS.clear()
+        tf_shim.PLACEHOLDERS.update({'x': torch.from_numpy(out['cq_x'])[:, :, None], 'x_': torch.from_numpy(out['cq_x'])[:, :, None],
+                                     'lr': 0.0, 'the_share': share, 'tau': 0.0, 'is_quan_on': 1.0,
+                                     'lpc_x': torch.from_numpy(lsf)[:, :, None]})
+        tag = 'cq_soft' if share else 'cq_hard'
+        tf_shim.set_feed(tf_shim.SeededFeed(seed=400))
+        with contextlib.redirect_stdout(sink), torch.no_grad():
+            r = c.all_modules_feedforward_lpc(2)
+        res_x, poly, soft_lpc, outs = r[4], r[5], r[9], r[15]
+        decoded = np.sum([o.numpy() for o in outs], axis=0)
+        syn = cm_mod.lpc_synthesizer_tr(poly.numpy(), decoded)
+        out[tag + '_poly'], out[tag + '_res_x'] = poly.numpy(), res_x[:, :, 0].numpy()
+        out[tag + '_lsf_idx'] = soft_lpc.argmax(-1).numpy().astype(np.int64)
+        out[tag + '_outs'] = np.stack([o.numpy() for o in outs])
+        out[tag + '_decoded'] = decoded
+        out[tag + '_synth'] = syn[0] if isinstance(syn, tuple) else syn
+        # plain cascade (no LPC): codec 0 is neither scaled nor divided
+        tf_shim.set_feed(tf_shim.SeededFeed(seed=400))
+        with contextlib.redirect_stdout(sink), torch.no_grad():
+            r = c.all_modules_feedforward(2)
+        out[tag + '_plain_outs'] = np.stack([o.numpy() for o in r[9]])
     # quantiser incl. exact ties (mid-points between bins) and out-of-range values
     bins = np.linspace(-1, 1, 32).astype(np.float32)
     fc = rng.uniform(-1.2, 1.2, size=(2, 256, 1)).astype(np.float32)

@@ -74,6 +74,7 @@ class SeededFeed(VariableFeed):
 
 
 _FEED = [None]
+PLACEHOLDERS = {}          # name -> value, for tf.compat.v1.placeholder
 
 
 def set_feed(feed):
@@ -171,7 +172,17 @@ def build():
     v1.layers = types.SimpleNamespace(conv1d=_layers_conv1d, batch_normalization=lambda inputs, **k: inputs)
     v1.variable_scope = lambda name, *a, **k: contextlib.nullcontext()
     v1.trainable_variables = lambda *a, **k: [_Var(s) for s in (_FEED[0].created if _FEED[0] else [])]
-    v1.py_func = None
+    # graph-mode plumbing of cmrl.py, executed eagerly: a placeholder IS the value fed under its name; py_func calls the Python
+    # function on numpy arrays right away
+    v1.placeholder = lambda dtype=None, shape=None, name=None: PLACEHOLDERS[name]
+
+    def _py_func(fn, inp, Tout):
+        args = [a.detach().numpy() if isinstance(a, torch.Tensor) else a for a in inp]
+        r = fn(*args)
+        r = r[0] if isinstance(r, tuple) else r
+        return [torch.as_tensor(np.asarray(r, dtype=np.float32))]
+    v1.py_func = _py_func
+    tf.bool = torch.bool
     tf.compat = types.SimpleNamespace(v1=v1)
     tf.keras = types.SimpleNamespace(
         layers=types.SimpleNamespace(SeparableConv1D=_SeparableConv1D, BatchNormalization=None),
@@ -179,7 +190,7 @@ def build():
     # ---- loss_terms_and_measures.py:63-84, :130-183, :257-267 (mse / mel / quantisation / entropy terms)
     def _red(fn):
         def f(input_tensor=None, axis=None, **k):
-            x = torch.as_tensor(input_tensor)
+            x = torch.stack(list(input_tensor)) if isinstance(input_tensor, (list, tuple)) else torch.as_tensor(input_tensor)
             return fn(x) if axis is None else fn(x, dim=axis)
         return f
     tf.reduce_mean, tf.reduce_sum = _red(torch.mean), _red(torch.sum)

@@ -504,3 +504,38 @@ def test_cuda_losses_vs_reference_run():
     assert rel_err(lt.quan_loss(soft).cpu().numpy(), g['loss_quan']) < 1e-5
     assert abs(float(lt.entropy_coding_loss(soft)) - float(g['loss_ent'])) < 1e-4
     assert np.allclose([lt.entropy_to_bitrate(2.5, 2), lt.entropy_to_bitrate(2.5, 4)], g['bitrate'], rtol=1e-12)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tc_f16x3'])
+def test_cuda_cq_feedforward_vs_reference_run(precision):
+    """nsc_cq_forward against the collaborative-quantisation pass as the REFERENCE'S OWN CMRL.all_modules_feedforward_lpc built it
+    (cmrl.py:770-839 run on the TensorFlow stand-in; tests/golden/reference_run_nn.npz): LSF codes bit-exact, quantised polynomial
+    and residual 1e-5, and -- on the soft path, which has no discontinuity -- every codec output, the decoded sum and the synthesized
+    frames end to end (2e-3: the alpha = -300 soft quantiser amplifies float32 rounding of the encoders)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    try:
+        import tf_shim
+    finally:
+        sys.path.remove(GOLD)
+    from nsc_b200 import codec
+    g = dict(np.load(os.path.join(GOLD, 'reference_run_nn.npz')))
+    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=precision)
+    rng = np.random.RandomState(400)
+    gcs = []
+    for _ in range(2):
+        layers = [tf_shim.draw_layer(rng, ((L.k, L.cin, L.cout), (L.cout,))) for L in codec.layer_table(cfg)]
+        gcs.append(codec.NeuralCodec(cfg, torch.from_numpy(codec.pack_params_numpy(cfg, layers, -300.0, np.linspace(-1, 1, 32))).to(DEV)))
+    cm = codec.CMRL(gcs, res_scalar=2.0)
+    x, lsf = cu(g['cq_x']), cu(g['cq_lsf'])
+    soft = cm.feedforward_lpc(x, lsf, True, 1.0)
+    hard = cm.feedforward_lpc(x, lsf, False, 1.0)
+    torch.cuda.synchronize()
+    for r, tag in ((soft, 'cq_soft'), (hard, 'cq_hard')):
+        assert np.array_equal(r['lsf_idx'].cpu().numpy().astype(np.int64), g[tag + '_lsf_idx'])
+        assert rel_err(r['poly'].cpu().numpy(), g[tag + '_poly']) < 1e-5
+        assert rel_err(r['res_x'].cpu().numpy(), g[tag + '_res_x']) < 1e-5
+    assert rel_err(soft['decoded'].cpu().numpy(), g['cq_soft_decoded']) < 2e-3
+    assert rel_err(soft['synthesized'].cpu().numpy(), g['cq_soft_synth']) < 2e-3
+    c = cm.all_modules_feedforward(x, True, 1.0, want_outs=True)
+    assert rel_err(torch.stack(c['outs']).cpu().numpy(), g['cq_soft_plain_outs']) < 2e-3

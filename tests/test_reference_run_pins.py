@@ -228,3 +228,49 @@ def test_loss_terms_oracle_equals_the_reference_run():
     assert _rel(ref_loss.quan_loss(soft).numpy(), g['loss_quan']) < 1e-6
     assert abs(float(ref_loss.entropy_coding_loss(soft)) - float(g['loss_ent'])) < 1e-5
     assert np.allclose([ref_loss.entropy_to_bitrate(2.5, 2), ref_loss.entropy_to_bitrate(2.5, 4)], g['bitrate'], rtol=1e-12)
+
+
+def _cq_oracle_codecs():
+    cfg = ref_codec.OracleCodecCfg()
+    shapes = ref_codec.OracleCodec(cfg, seed=0).conv_params
+    rng = np.random.RandomState(400)                      # ONE stream across both scopes, as the reference graph creates them
+    draw = _shim().draw_layer
+    ocs = []
+    for _ in range(2):
+        ocs.append(ref_codec.OracleCodec(cfg, conv_params=[draw(rng, tuple(tuple(np.asarray(a).shape) for a in layer)) for layer in shapes]))
+    return ocs
+
+
+@pytest.mark.parametrize('share', [False, True], ids=['hard', 'soft'])
+def test_cascade_and_cq_feedforward_oracle_equals_the_reference_run(share):
+    """CMRL.all_modules_feedforward_lpc (cmrl.py:770-830: 256-bin LSF quantiser, lsf2poly and residual through tf.py_func, codec 0 on
+    res_x * res_scalar, codec i on res_scalar * (res_x - sum of the earlier outputs), every output divided by res_scalar) followed by
+    _feedforward_lpc's sum and synthesis (:836-839), and CMRL.all_modules_feedforward (:513-543: codec 0 neither scaled nor divided) --
+    graphs built by the reference's own code, two codecs, res_scalar = 2."""
+    g = dict(np.load(FIX_NN))
+    tag = 'cq_soft' if share else 'cq_hard'
+    ocs = _cq_oracle_codecs()
+    bins = np.load(os.path.join(GOLD, 'lsf_bins_f64.npy')).astype(np.float32)
+    x = torch.from_numpy(g['cq_x'])[:, :, None]
+    lsf = torch.from_numpy(g['cq_lsf'])[:, :, None]
+    with torch.no_grad():
+        o = ref_codec.cq_feedforward(ocs, -300.0, bins, x, lsf, share, 1.0, res_scalar=2.0)
+    idx = ref_nn.quantizer_indices(lsf, np.float32(-300.0), bins).numpy().astype(np.int64).reshape(g[tag + '_lsf_idx'].shape)
+    assert np.array_equal(idx, g[tag + '_lsf_idx'])
+    assert _rel(o['poly'], g[tag + '_poly']) < 2e-6
+    assert _rel(o['res_x'][:, :, 0].numpy(), g[tag + '_res_x']) < 2e-6
+    if share:       # no discontinuity on the soft path: the whole pass can be compared end to end
+        assert _rel(torch.stack(o['outs']).numpy(), g[tag + '_outs']) < 2e-3      # alpha = -300 soft quantiser amplifies float32 rounding
+        assert _rel(o['decoded'].numpy(), g[tag + '_decoded']) < 2e-3
+        assert _rel(o['synthesized'], g[tag + '_synth']) < 2e-3
+    else:           # hard path: codec 0 sees identical input; a code flipped at a mid-point changes its output locally
+        d0 = np.abs(o['outs'][0].numpy() - g[tag + '_outs'][0]).max(1) / np.abs(g[tag + '_outs'][0]).max()
+        assert np.median(d0) < 1e-5
+    # the plain cascade: codec 0 unscaled and undivided
+    with torch.no_grad():
+        dec, outs, _ = ref_codec.cascade_forward(ocs, x, share, 1.0, res_scalar=2.0, lpc_variant=False)
+    if share:
+        assert _rel(torch.stack(outs).numpy(), g[tag + '_plain_outs']) < 2e-3
+    else:
+        d0 = np.abs(outs[0].numpy() - g[tag + '_plain_outs'][0]).max(1) / np.abs(g[tag + '_plain_outs'][0]).max()
+        assert np.median(d0) < 1e-5
