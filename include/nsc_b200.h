@@ -213,8 +213,8 @@ int32_t nsc_codec_layer_info(const nsc_codec_cfg* cfg, int32_t i, int32_t* k, in
                              int32_t* separable, int64_t* offset);
 int64_t nsc_codec_workspace_bytes(const nsc_codec_cfg* cfg, int64_t B);
 /* 1 when this configuration's conv stack runs on the plane engine (tcgen05, fp16 plane images between layers): precision 1 / 2,
- * resnet_type 'bottleneck' or 'gln' (constants.py:13-14), one stride-2 stage, narrow 20, dilations <= 2; 0 when it keeps the
- * layer-by-layer engines; -1 on an invalid configuration. */
+ * resnet_type 'bottleneck' or 'gln' (constants.py:13-14), one stride-2 stage (or two with precision 1), narrow 20, k 9,
+ * dilations <= 2; 0 when it keeps the layer-by-layer engines; -1 on an invalid configuration. */
 int32_t nsc_codec_on_plane_engine(const nsc_codec_cfg* cfg);
 
 /* Whole codec, computational_graph_end2end_quan_on[_lpc]:

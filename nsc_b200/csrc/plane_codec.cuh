@@ -44,6 +44,10 @@ int64_t plane_chunk_frames() {
   return v;
 }
 
+// zeroed bytes in front of the first and behind the last activation image of a region: a layer with 16 halo rows reads 8 rows
+// (1 KB) beyond an image's own zero rows -- normally the neighbouring image's zero rows, here at the region's ends
+constexpr int64_t kPlaneGuard = 2048;
+
 struct PlaneCodecPlan {
   int planes = 2;
   int Lc = 0;
@@ -114,11 +118,14 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   // the two k15 gate convs of a gated block as ONE layer (plane.cuh): input n0 (or its de-interleaved twin n0d for dilation 2,
   // convolved as two independent half-length frames with dilation 1), output the plain packed image n1.  Owns TWO table entries.
   auto add_gates = [&](std::vector<PlaneConv>& v, std::vector<int>& vl, int Ls, int d, int n0, int n0d, int n1) {
-    if (d == 2) {
+    if (d == 2 && Ls / 2 >= 128) {
       PlaneConv& g = add(v, vl, PK_X, Ls / 2, Nn, 2 * Nn, 15, 1, 1, NSC_ACT_NONE, n0d, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
       g.glu = 1; g.ileave = 1; g.bmul = 2;
       g.in.deint = 0; g.in.rows = Ls / 2; g.in.frame_bytes = pl.buf[n0d].frame_bytes / 2;   // view: one sub-image = one frame
     } else {
+      // dilation 1 -- or dilation 2 at 128 positions, where a sub-image would be shorter than the 128-row MMA tile: the layer then
+      // stages 16 halo rows per side on the plain image (the rows beyond an image's own 8 zero rows are the neighbouring image's
+      // zero rows; zeroed guard bands stand in for them at both ends of the activation region, plane_bind)
       PlaneConv& g = add(v, vl, PK_X, Ls, Nn, 2 * Nn, 15, d, 1, NSC_ACT_NONE, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
       g.glu = 1;
     }
@@ -135,7 +142,7 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
       const int post = flat ? NSC_ACT_NONE : NSC_ACT_LRELU;
       if (gln) {   // gated_bottleneck (nn_core_operator.py:82-112): k1 -> [k15 gate * tanh(k15 gate)] -> k9 + residual
         const int d = c.dilations[i];
-        const int k1_out = d == 2 ? n0d : n0;
+        const int k1_out = (d == 2 && Ls / 2 >= 128) ? n0d : n0;
         const bool vec = vec_in && i == 0;
         add(v, vl, vec ? PK_GEN : PK_X, Ls, vec ? 1 : Cw, Nn, 1, 1, 1, NSC_ACT_LRELU, vec ? -1 : cur, k1_out, -1, RES_NONE, NSC_ACT_NONE, 1);
         add_gates(v, vl, Ls, d, n0, n0d, n1);
@@ -217,12 +224,12 @@ int64_t plane_codec_flag_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
 int64_t plane_codec_act_bytes(const PlaneCodecPlan& pl, int64_t Bc) {
   int64_t total = 0;
   for (const PlaneTensor& t : pl.buf) total += align_up(t.frame_bytes * Bc, 1024);
-  return total + 1024;
+  return total + 1024 + 2 * kPlaneGuard;
 }
 
 // Resolves the buffer ids to addresses inside `act` (sized for Bc frames), attaches parameters and packed weights.
 void plane_bind(PlaneCodecPlan& pl, const CodecLayout& lay, const float* params, void* act, int64_t Bc, void* wpack) {
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(act) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(act) + 1023) & ~(uintptr_t)1023) + kPlaneGuard;
   std::vector<uint8_t*> addr(pl.buf.size());
   for (size_t i = 0; i < pl.buf.size(); ++i) { addr[i] = base; base += align_up(pl.buf[i].frame_bytes * Bc, 1024); }
   size_t li = 0;

@@ -900,6 +900,9 @@ struct XParams {
   int act, post_act, res_mode, shuffle, planes;
   int Npad, ksteps, mt, tile, tiles_per_frame;
   int n_stage, kbuf, stage_bytes;
+  int halo;                  // rows staged above and below the tile: 8 (the image's own zero rows), or 16 for packed-input layers whose
+                             // taps reach further (k15 dilation 2: +-14) -- the 8 rows beyond an image's zero rows are the zero rows of the
+                             // neighbouring frame's image (or of the zeroed guard in front of / behind the buffer), see plane_codec.cuh
   int n_units, unit_bytes, wslots, resident;
   int tmem_cols;
   int zero_from, zero_to;    // output chunks the epilogue must clear (K padding the consumer will read)
@@ -1134,7 +1137,7 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
       wait_full<MODE>(&bars.a_full[kb], &bars.a_full2[kb], a_phase);
       if (p.stats != nullptr) stat_add(p.stats, 6, clock64() - tw);
       if (p.in_free != nullptr && issuer == 0) flag_bump(p.in_free + tile / p.tiles_per_frame);   // this CTA's tile has been read out of the ring
-      const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(8 - p.padL) * 8u;
+      const uint32_t a_lo0 = a_lo_base + kb * stage_lo + (uint32_t)(p.halo - p.padL) * 8u;
       switch (p.ksteps) {
         case 2: x_issue_packed<2, MODE>(x, p, a_lo0); break;
         case 1: x_issue_packed<1, MODE>(x, p, a_lo0); break;
@@ -1380,8 +1383,8 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
               const int stage = pt_slab_index(p.in, sub, ap, s);
               mbar_wait_relaxed(&a_empty[kb + stage], ph);
               mbar_expect_tx(&a_full[kb + stage], (uint32_t)p.stage_bytes);
-              bulk_g2s(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes, img + stage * sb + (int64_t)q0 * 128, (uint32_t)p.stage_bytes,
-                       &a_full[kb + stage]);
+              bulk_g2s(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes, img + stage * sb + (int64_t)(q0 - (p.halo - 8)) * 128,
+                       (uint32_t)p.stage_bytes, &a_full[kb + stage]);
             }
         if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
         else ph ^= 1u;
@@ -1801,6 +1804,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   if (Lout % 128 != 0) return false;
   if (c.shuffle != 1 && c.shuffle != 2) return false;
   if (c.Cout < 2 || c.Cout > 128 || c.Cout % c.shuffle != 0) return false;
+  p->halo = 8;
   if (gen) {
     if (c.Cin != 1 || c.stride != 1 || c.dil != 1 || c.K > 64 || c.xvec == nullptr) return false;
   } else {
@@ -1809,7 +1813,11 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
     else if (c.stride == 2) { if (!c.in.deint || c.in.packed || c.dil != 1 || c.Lin % 2 != 0 || c.in.rows != c.Lin / 2) return false; }
     else return false;
     const int span = (c.K - 1) * c.dil;           // rows touched beyond the tile: [8 - padL, 8 - padL + span] must stay in [0, 16]
-    if (c.stride == 1 && (padL > 8 || span - padL > 8)) return false;
+    if (c.stride == 1 && (padL > 8 || span - padL > 8)) {
+      // packed input, plain epilogue: 16 halo rows (the neighbouring images' zero rows) -- the k15 dilation-2 gates at 128 positions
+      if (!(c.in.packed && c.out.packed && padL <= 16 && span - padL <= 16)) return false;
+      p->halo = 16;
+    }
     if (c.stride == 2 && (padL > 16 || span - padL > 16)) return false;
   }
   if (c.res_mode == RES_ADD && (c.res.deint || c.res.rows != Lout)) return false;
@@ -1848,7 +1856,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   for (int mt = (Lout % 256 == 0 && c.stride == 1) ? 2 : 1; mt >= 1; --mt) {
     p->mt = mt;
     p->tile = 128 * mt;
-    p->stage_bytes = (p->tile + 16) * 128;
+    p->stage_bytes = (p->tile + 2 * (gen ? 8 : p->halo)) * 128;
     p->tiles_per_frame = Lout / p->tile;
     p->n_tiles = c.B * p->tiles_per_frame;
     p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && !c.glu && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;

@@ -106,9 +106,11 @@ def test_codec_workspace_sizes_on_the_plane_path():
     # two stride-2 stages (the_strides = '4', cmrl.py:804) with bottleneck blocks: on the plane path as well (three resolution levels)
     s4 = codec.CodecConfig(resnet_type='bottleneck', the_strides=(2, 2), precision='tc_f16x3').to_struct()
     assert lib.nsc_codec_on_plane_engine(C.byref(s4)) == 1 and lib.nsc_codec_workspace_bytes(C.byref(s4), 2072) > chunk
-    # configurations outside the plane path keep the layer-by-layer workspace: 'gln' with two stages (its dilation-2 gate conv at 128
-    # positions has no launch plan), the one-plane mode with two stages (wide / 4 channels would be a packed image)
-    for cfg_out in (codec.CodecConfig(resnet_type='gln', the_strides=(2, 2), precision='tc_f16x3'),
+    g4 = codec.CodecConfig(resnet_type='gln', the_strides=(2, 2), precision='tc_f16x3').to_struct()
+    assert lib.nsc_codec_on_plane_engine(C.byref(g4)) == 1      # (its dilation-2 gates at 128 positions stage 16 halo rows)
+    # configurations outside the plane path keep the layer-by-layer workspace: the one-plane mode with two stages (wide / 4 channels
+    # would be a packed image), other narrow widths
+    for cfg_out in (codec.CodecConfig(bottleneck_kernel_and_dilation=(9, 9, 100, 24, 1, 2), precision='tc_f16x3'),
                     codec.CodecConfig(resnet_type='bottleneck', the_strides=(2, 2), precision='tc_f16')):
         st = cfg_out.to_struct()
         assert lib.nsc_codec_on_plane_engine(C.byref(st)) == 0
