@@ -355,7 +355,9 @@ def run_ours(args):
                          ("cq_scaled", lambda: measure_cq_sweep(args, world, rank, dev, lib)),
                          ("cq2_gln", lambda: measure_variant(args, world, rank, dev, lib, 'gln', (2,))),
                          ("cq2_stride4", lambda: measure_variant(args, world, rank, dev, lib, 'bottleneck', (2, 2))),
+                         ("cq2_gln_stride4", lambda: measure_variant(args, world, rank, dev, lib, 'gln', (2, 2))),
                          ("train", lambda: measure_train(args, world, rank, dev, lib, 20, 5, breakdown=True)),
+                         ("train_gln", lambda: measure_train(args, world, rank, dev, lib, 10, 3, breakdown=False, resnet_type='gln')),
                          ("corpus_1h_per_gpu", lambda: measure_corpus(args, world, rank, dev, lib, 2, 1, n_utt=360))):
             try:
                 subrec[name] = fn()
@@ -506,14 +508,14 @@ def run_corpus(args):
         dist.destroy_process_group()
 
 
-def measure_train(args, world, rank, dev, lib, steps, warmup, breakdown=True):
+def measure_train(args, world, rank, dev, lib, steps, warmup, breakdown=True, resnet_type='bottleneck'):
     """BASELINE.json configs[3]: full CQ training step -- forward keeping activations, backward of every kernel, ONE flat
     all-reduce (NCCL) of gradients + soft histograms, TF1 Adam -- `_finetuning_lpc`-shaped loss, train_batch frames per GPU."""
     import torch
     from nsc_b200 import codec, lpc_utilities as lu
     from nsc_b200.training import CQTrainer
     B = args.train_batch
-    cfg = codec.CodecConfig(resnet_type='bottleneck', precision=args.precision)
+    cfg = codec.CodecConfig(resnet_type=resnet_type, precision=args.precision)
     cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
     tr = CQTrainer.finetuning_lpc(cm, (60.0, 10.0, 10.0, 0.0), lr=2e-6)
     x_np, win_np = synth_audio(B, seed=4321 + rank)
@@ -538,7 +540,7 @@ def measure_train(args, world, rank, dev, lib, steps, warmup, breakdown=True):
            "ms_per_step": t / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32 weight gradients, epilogues and Adam; forward and data-gradient convs " + args.precision,
            "data": "synthetic",
-           "config": {"workload": "train: 2-codec CQ cascade, finetuning_lpc loss (60/10/10), soft path, TF1 Adam, "
+           "config": {"workload": f"train: 2-codec CQ cascade ('{resnet_type}' blocks), finetuning_lpc loss (60/10/10), soft path, TF1 Adam, "
                                   "one flat all-reduce of gradients + soft histograms", "frames_per_gpu": B, "parallelism": f"dp{world}"},
            "gpu_launches": int(launches), "launches_per_step": int(launches) // max(1, steps),
            "collectives_per_step": getattr(tr, 'collectives_per_step', None),
@@ -639,9 +641,8 @@ def measure_codec1(args, world, rank, dev, lib, cpu=True):
 
 def measure_variant(args, world, rank, dev, lib, resnet_type, strides, frames=4144):
     """The reference's SHIPPED switches (constants.py:14 resnet_type = 'gln'; the_strides '4' -> [2, 2], cmrl.py:804) on the same
-    CQ 2-codec workload.  'gln' with one stride-2 stage runs on the plane engine (fused k15 gate pair, depthwise + pointwise up-conv);
-    two stride-2 stages keep the layer-by-layer engines (first tensor engine: fp16 hi/lo split, fp32 activations between layers; the
-    k55 stem / heads on CUDA cores).  `engine` says which."""
+    CQ 2-codec workload.  All of them run on the plane engine in the fp32-class mode (fused k15 gate pair, depthwise + pointwise
+    up-conv, three resolution levels); `engine` says which engine ran."""
     import torch
     from nsc_b200 import codec, lpc_utilities as lu
     cfg = codec.CodecConfig(resnet_type=resnet_type, the_strides=strides, precision=args.precision)

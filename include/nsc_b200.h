@@ -115,6 +115,16 @@ int nsc_bottleneck_block_tc(const float* x, const float* params, float* y, int64
                             int32_t k_plain, int32_t k_dilated, int32_t dilation, int32_t is_last_flat, int32_t precision,
                             int32_t* fused, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* gated_bottleneck (nn_core_operator.py:82-112; the reference's shipped block type, constants.py:14) on the tcgen05 tensor cores:
+ * k1 conv + leaky ReLU, the two k15 gate convs as ONE layer whose epilogue writes gate * tanh(gate), k9 conv + residual
+ * (+ leaky ReLU unless is_last_flat) -- the three launches of the codec program's gated block.  x (B, L, wide) channels-last ->
+ * y (B, L, wide); params in creation order (w_1x1, b), (w_left, b), (w_right, b), (w_out, b).
+ *   Covers narrow = 20, k_plain = 9, dilation 1 or 2, 32 < wide <= 128, L a multiple of 128; precision as nsc_conv1d_tc. */
+int64_t nsc_gated_block_tc_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t narrow, int32_t dilation, int32_t precision);
+int nsc_gated_block_tc(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t wide, int32_t narrow,
+                       int32_t k_plain, int32_t dilation, int32_t is_last_flat, int32_t precision, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
 /* Tuning aid: per-CTA counters of the most recent fused block launch, recorded when the process runs with NSC_BLOCK_STATS=1
  * (8 words per CTA: role, epilogue-loop cycles, cycles waited for a free ring slot, cycles waited for a ready frame, work units,
  * cycles the storer waited for its own stores, 2 spare).  Synchronises the device.  Returns the number of CTAs copied. */

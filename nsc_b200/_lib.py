@@ -52,6 +52,8 @@ SIGNATURES = {
     "nsc_bottleneck_block": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "nsc_bottleneck_block_tc_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
     "nsc_bottleneck_block_tc": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), _vp, _i64, _vp]),
+    "nsc_gated_block_tc_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32, _i32]),
+    "nsc_gated_block_tc": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "nsc_debug_block_stats": (_i32, [C.POINTER(C.c_ulonglong), _i32]),
     "nsc_quantize_scalar": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nsc_dequantize_scalar": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),

@@ -2447,6 +2447,109 @@ int nsc_bottleneck_block_tc(const float* x, const float* params, float* y, int64
   return NSC_OK;
 }
 
+// ---- gated_bottleneck (nn_core_operator.py:82-112) on the plane engine, channels-last fp32 tensors at the edge ----------------
+// k1 conv + leaky ReLU -> the two k15 gate convs as one layer with the gate product in its epilogue -> k9 conv + residual
+// (+ leaky ReLU): the three launches of the codec program's gated block.  params in creation order: (w_1x1, b), (w_left, b),
+// (w_right, b), (w_out, b).
+namespace {
+
+struct TcGatedPlan {
+  nsc::PlaneConv c1, cg, c3;
+  int64_t x_bytes, n_bytes, nd_bytes, w1, wg, w3;
+};
+
+int make_tc_gated_plan(int64_t B, int L, int wide, int narrow, int k_plain, int dilation, int is_last_flat, int precision, TcGatedPlan* pl) {
+  using namespace nsc;
+  NSC_CHECK_ARG(precision == 1 || precision == 2, "nsc_gated_block_tc: precision must be 1 (fp16 hi/lo) or 2 (fp16)");
+  NSC_CHECK_ARG(B >= 1 && L > 0 && L % 128 == 0 && wide > 32 && wide <= 128 && narrow == 20 && k_plain == 9 && dilation >= 1 && dilation <= 2,
+                "nsc_gated_block_tc: shape not covered by the tensor engine (L %d, %d/%d, k %d, dilation %d)", L, wide, narrow, k_plain, dilation);
+  const int P = precision == 1 ? 2 : 1;
+  const bool deint = dilation == 2 && (L / 2) % 128 == 0;      // else: plain image (16 halo rows for dilation 2)
+  auto conv = [&](PlaneConv& c, int Lin, int cin, int cout, int K, int dil, int act, int res_mode, int post) {
+    c.kind = PK_X; c.Lin = Lin; c.Cin = cin; c.Cout = cout; c.K = K; c.dil = dil; c.stride = 1;
+    c.act = act; c.post_act = post; c.res_mode = res_mode; c.shuffle = 1; c.planes = P; c.B = B;
+  };
+  const PlaneTensor tx = make_plane_tensor(nullptr, L, wide, P, 0), tn = make_plane_tensor(nullptr, L, narrow, P, 0),
+                    tnd = make_plane_tensor(nullptr, L, narrow, P, 1);
+  conv(pl->c1, L, wide, narrow, 1, 1, NSC_ACT_LRELU, RES_NONE, NSC_ACT_NONE);
+  pl->c1.in = tx; pl->c1.out = deint ? tnd : tn;
+  if (deint) {
+    conv(pl->cg, L / 2, narrow, 2 * narrow, 15, 1, NSC_ACT_NONE, RES_NONE, NSC_ACT_NONE);
+    pl->cg.in = tnd; pl->cg.in.deint = 0; pl->cg.in.rows = L / 2; pl->cg.in.frame_bytes = tnd.frame_bytes / 2;
+    pl->cg.ileave = 1; pl->cg.bmul = 2; pl->cg.B = 2 * B;
+  } else {
+    conv(pl->cg, L, narrow, 2 * narrow, 15, dilation, NSC_ACT_NONE, RES_NONE, NSC_ACT_NONE);
+    pl->cg.in = tn;
+  }
+  pl->cg.glu = 1; pl->cg.out = tn;
+  conv(pl->c3, L, narrow, wide, k_plain, 1, NSC_ACT_NONE, RES_ADD, is_last_flat ? NSC_ACT_NONE : NSC_ACT_LRELU);
+  pl->c3.in = tn; pl->c3.out = tx; pl->c3.res = tx;
+  NSC_CHECK_ARG(plane_conv_supported(pl->c1) && plane_conv_supported(pl->cg) && plane_conv_supported(pl->c3),
+                "nsc_gated_block_tc: a conv of the block is not covered by the tensor engine");
+  pl->x_bytes = align_up(B * tx.frame_bytes, 1024);
+  pl->n_bytes = align_up(B * tn.frame_bytes, 1024);
+  pl->nd_bytes = align_up(B * tnd.frame_bytes, 1024);
+  pl->w1 = align_up(plane_wpack_bytes(pl->c1), 1024);
+  pl->wg = align_up(plane_wpack_bytes(pl->cg), 1024);
+  pl->w3 = align_up(plane_wpack_bytes(pl->c3), 1024);
+  return NSC_OK;
+}
+
+}  // namespace
+
+int64_t nsc_gated_block_tc_workspace_bytes(int64_t B, int32_t L, int32_t wide, int32_t narrow, int32_t dilation, int32_t precision) {
+  TcGatedPlan pl;
+  if (make_tc_gated_plan(B < 1 ? 1 : B, L, wide, narrow, 9, dilation, 0, precision, &pl) != NSC_OK) return -1;
+  return 8192 + 2 * pl.x_bytes + 2 * pl.n_bytes + pl.nd_bytes + pl.w1 + pl.wg + pl.w3;
+}
+
+int nsc_gated_block_tc(const float* x, const float* params, float* y, int64_t B, int32_t L, int32_t wide, int32_t narrow, int32_t k_plain,
+                       int32_t dilation, int32_t is_last_flat, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace nsc;
+  if (B == 0) return NSC_OK;
+  NSC_CHECK_ARG(x && params && y && workspace, "nsc_gated_block_tc: null pointer");
+  TcGatedPlan pl;
+  NSC_TRY(make_tc_gated_plan(B, L, wide, narrow, k_plain, dilation, is_last_flat, precision, &pl));
+  const int64_t need = 8192 + 2 * pl.x_bytes + 2 * pl.n_bytes + pl.nd_bytes + pl.w1 + pl.wg + pl.w3;
+  if (workspace_bytes < need) {
+    set_error("nsc_gated_block_tc: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    return NSC_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // images sit 2 KB into the (zeroed) workspace and are followed by 2 KB of zeros: the 16-row halos of a dilation-2 gate layer on
+  // the plain image read 1 KB beyond an image's own zero rows
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  const int64_t img_bytes = 2 * pl.x_bytes + 2 * pl.n_bytes + pl.nd_bytes;
+  NSC_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)(img_bytes + 4096), st));
+  p += 2048;
+  uint8_t* xi = p; p += pl.x_bytes;
+  uint8_t* yi = p; p += pl.x_bytes;
+  uint8_t* n0 = p; p += pl.n_bytes;
+  uint8_t* n1 = p; p += pl.n_bytes;
+  uint8_t* n0d = p; p += pl.nd_bytes;
+  p += 2048;
+  pl.c1.in.base = xi; pl.c1.out.base = pl.c1.out.deint ? n0d : n0;
+  pl.cg.in.base = pl.cg.ileave ? n0d : n0; pl.cg.out.base = n1;
+  pl.c3.in.base = n1; pl.c3.out.base = yi; pl.c3.res.base = xi;
+  pl.c1.wpack = p; p += pl.w1;
+  pl.cg.wpack = p; p += pl.wg;
+  pl.c3.wpack = p;
+  const float* w = params;
+  pl.c1.w = w; pl.c1.bias = w + (int64_t)wide * narrow; w = pl.c1.bias + narrow;
+  pl.cg.w = w; pl.cg.bias = w + 15LL * narrow * narrow; w = pl.cg.bias + narrow;
+  pl.cg.w2 = w; pl.cg.bias2 = w + 15LL * narrow * narrow; w = pl.cg.bias2 + narrow;
+  pl.c3.w = w; pl.c3.bias = w + (int64_t)k_plain * narrow * wide;
+  NSC_TRY(plane_from_f32(x, 1, B, L, wide, pl.c1.in, st));
+  NSC_TRY(plane_pack_weights(pl.c1, st));
+  NSC_TRY(plane_pack_weights(pl.cg, st));
+  NSC_TRY(plane_pack_weights(pl.c3, st));
+  NSC_TRY(plane_launch(pl.c1, st));
+  NSC_TRY(plane_launch(pl.cg, st));
+  NSC_TRY(plane_launch(pl.c3, st));
+  NSC_TRY(plane_to_f32(pl.c3.out, y, 1, B, L, wide, st));
+  return NSC_OK;
+}
+
 /* per-CTA counters of the most recent fused block launch (NSC_BLOCK_STATS=1): 8 words per CTA, see plane_conv.cu */
 int nsc_debug_block_stats(unsigned long long* out_host, int32_t max_ctas) {
   NSC_CHECK_ARG(out_host != nullptr && max_ctas >= 1, "nsc_debug_block_stats: bad arguments");

@@ -162,6 +162,16 @@ def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rat
             _lib.check(rc, 'the_bottleneck')
             last_engine = 'tc_fused' if fused.value else 'tc'
             return y
+    if prec is not None and gated and B > 0 and cin == wide_layer and k_plain == 9 and dilation_rate in (1, 2):
+        # the gated block of the codec path: k1 conv, fused gate pair (product in the epilogue), k9 conv + residual on tcgen05
+        ws_bytes = lib.nsc_gated_block_tc_workspace_bytes(B, L, wide_layer, narrow_layer, dilation_rate, prec)
+        if ws_bytes > 0:
+            ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
+            rc = lib.nsc_gated_block_tc(_lib.ptr(x), _lib.ptr(flat), _lib.ptr(y), B, L, wide_layer, narrow_layer, k_plain, dilation_rate,
+                                        int(bool(is_last_flat)), prec, _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+            _lib.check(rc, 'gated_bottleneck')
+            last_engine = 'tc'
+            return y
     last_engine = 'ffma'
     ws_bytes = lib.nsc_block_workspace_bytes(B, L, wide_layer, narrow_layer)
     ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device)

@@ -539,3 +539,53 @@ def test_cuda_cq_feedforward_vs_reference_run(precision):
     assert rel_err(soft['synthesized'].cpu().numpy(), g['cq_soft_synth']) < 2e-3
     c = cm.all_modules_feedforward(x, True, 1.0, want_outs=True)
     assert rel_err(torch.stack(c['outs']).cpu().numpy(), g['cq_soft_plain_outs']) < 2e-3
+
+
+@pytest.mark.parametrize('L,wide,dil', [(128, 100, 2), (384, 100, 2), (128, 50, 1), (512, 100, 2)])
+def test_gated_block_surface_on_the_tensor_engine(L, wide, dil):
+    """nn_core_operator.gated_bottleneck through nsc_gated_block_tc (tcgen05): dilation-2 gates on de-interleaved sub-images where
+    a sub-image is a whole number of 128-row tiles (L = 512), else on the plain image with 16 halo rows (L = 128, 384); odd batch."""
+    from nsc_b200 import nn_core_operator as nn
+    ps = ref_nn.ParamStream(seed=L + wide + dil)
+    x = np.random.RandomState(L).randn(3, L, wide).astype(np.float32)
+    ref = ref_nn.gated_bottleneck(torch.from_numpy(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, ps=ps).numpy()
+    params = [tuple(cu(p) for p in t) for t in ps.params]
+    got = nn.gated_bottleneck(cu(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, params=params)
+    assert nn.last_engine == 'tc'
+    g, r = got.cpu().numpy(), ref
+    assert rel_err(g, r) < 5e-5
+    per = np.abs(g - r).reshape(3, -1).max(1) / np.abs(r).reshape(3, -1).max(1)
+    assert per.max() < 5e-5
+
+
+def test_cuda_blocks_vs_reference_run():
+    """the_bottleneck / gated_bottleneck / gated_bottleneck_decoder / conv1d / conv1d_depth / change_channel on the GPU against the
+    outputs of the reference's own nn_core_operator.py (tests/golden/reference_run_nn.npz)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    try:
+        import tf_shim
+    finally:
+        sys.path.remove(GOLD)
+    from nsc_b200 import nn_core_operator as nn
+    g = dict(np.load(os.path.join(GOLD, 'reference_run_nn.npz')))
+    xb = cu(g['block_x'])
+
+    def params_like(layers, seed):
+        rng = np.random.RandomState(seed)
+        return [tuple(cu(a) for a in tf_shim.draw_layer(rng, tuple(l))) for l in layers]
+
+    for name, fn, kw in (('the_bottleneck', nn.the_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=False)),
+                         ('the_bottleneck_flat', nn.the_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=True)),
+                         ('gated_bottleneck', nn.gated_bottleneck, dict(wide_layer=100, narrow_layer=20, dilation_rate=2, is_last_flat=False)),
+                         ('gated_bottleneck_decoder', nn.gated_bottleneck_decoder, dict(wide_layer=100, narrow_layer=20, dilation_rate=1, is_last_flat=True))):
+        layers = eval(str(g['block_' + name + '_layers']))
+        y = fn(xb, params=params_like(layers, 200), **kw).cpu().numpy()
+        assert rel_err(y, g['block_' + name]) < 5e-5, name
+    for name, fn, kw, layers in (
+            ('conv1d_s2', nn.conv1d, dict(num_filters=24, filter_size=9, strides=2, dilation_rate=1), [((9, 100, 24), (24,))]),
+            ('conv1d_d3', nn.conv1d, dict(num_filters=8, filter_size=5, strides=1, dilation_rate=3, activation=None), [((5, 100, 8), (8,))]),
+            ('conv1d_depth', nn.conv1d_depth, dict(num_filters=50, filter_size=9, activation=None), [((9, 100, 1), (1, 100, 50), (50,))]),
+            ('change_channel', nn.change_channel, dict(the_channel=1, kernel_size=55, dilation_rate=7), [((55, 100, 1), (1,))])):
+        y = fn(xb, params=params_like(layers, 300)[0], **kw).cpu().numpy()
+        assert y.shape == g['op_' + name].shape and rel_err(y, g['op_' + name]) < 5e-5, name
