@@ -157,7 +157,8 @@ def schedule(epoch: int, pretrain_step: int, epochs: int = 0, is_cq: bool = True
 
 
 def sorted_lsf_bins(lsf_params: np.ndarray) -> np.ndarray:
-    """_update_lpc_residual re-reads the learned LSF bins SORTED (nscm.py:1084-1087)."""
+    """_update_lpc_residual re-reads the learned LSF bins SORTED (nscm.py:1084-1087); the whole step -- sorted bins, fresh alpha,
+    hard assignment, lsf2poly, residual over the training set -- is nsc_b200.training.update_lpc_residual."""
     p = np.asarray(lsf_params, dtype=np.float32).copy()
     p[1:] = np.sort(p[1:])
     return p

@@ -174,3 +174,30 @@ class CQTrainer:
         out = self.loss_and_grads(res_x, lpc_x, tau, is_quan_on, quan_terms=(optimizer == 'quan'))
         self.apply_adam(lr, optimizer)
         return out
+
+
+def update_lpc_residual(raw_frames: torch.Tensor, lsf: torch.Tensor, lsf_params: torch.Tensor, chunk: int = 50000,
+                        init_alpha: Optional[float] = None) -> torch.Tensor:
+    """_update_lpc_residual (nscm.py:1075-1122): every 30 epochs (and at epoch - 3; checkpoint.schedule) a CQ run recomputes the LPC
+    residual of the WHOLE training set with the codebook it has learned so far, and trains on those residuals from then on.
+
+    As the reference does it: the learned LSF bins are re-read SORTED (:1084-1087), alpha is a fresh `init_alpha` (not the learned
+    one, :1083), the assignment is HARD (`the_share: False`, is_quan_on = 1, :1088-1094), then lsf2poly_after_quan and
+    lpc_analysis_get_residual per chunk of 50,000 frames (:1103-1119).  raw_frames (N, 512) float32, lsf (N, 16) float32 (the stored
+    un-quantised LSFs), lsf_params = {alpha, bins[n]} of the `lpc_quan` scope -> residual (N, 512) float32.  Device in, device out."""
+    from . import constants as _c
+    from . import lpc_utilities as lu
+    from . import nn_core_operator as nn
+    x = _lib.require_f32(raw_frames, 'raw_frames').reshape(-1, FRAME)
+    l = _lib.require_f32(lsf, 'lsf').reshape(-1, _lib.LPC_ORDER)
+    if x.shape[0] != l.shape[0]:
+        raise ValueError("raw_frames / lsf batch mismatch")
+    bins = torch.sort(_lib.require_f32(lsf_params, 'lsf_params')[1:]).values.contiguous()
+    alpha = float(_c.init_alpha if init_alpha is None else init_alpha)
+    out = torch.empty_like(x)
+    for s0 in range(0, x.shape[0], int(chunk)):
+        s1 = min(s0 + int(chunk), x.shape[0])
+        _, q = nn.scalar_softmax_quantization(l[s0:s1, :, None].contiguous(), alpha, bins, 1.0, False, _lib.LPC_ORDER, bins.numel())
+        poly = lu.lsf2poly_after_quan(q[:, :, 0].contiguous(), _lib.LPC_ORDER)
+        out[s0:s1] = lu.lpc_analysis_get_residual(x[s0:s1, :, None].contiguous(), poly)
+    return out

@@ -332,3 +332,20 @@ def test_pretraining_op_has_its_own_adam_slots_and_no_quantisation_terms():
     assert float(tr._slots['quan']['m'][0].abs().max()) == 0.0 and float(tr._slots['no_quan']['m'][0].abs().max()) > 0.0
     tr.step(x, l, tau=0.5)
     assert tr._slots['quan']['t'] == 1 and float(tr._slots['quan']['m'][0].abs().max()) > 0.0
+
+
+def test_update_lpc_residual_vs_oracle():
+    """_update_lpc_residual (nscm.py:1075-1122): sorted learned bins, fresh init_alpha, hard assignment, lsf2poly, sub-framed residual,
+    chunked -- against the same composition of the oracle's functions (each pinned against the reference run)."""
+    from oracle import ref_nn
+    from nsc_b200.training import update_lpc_residual
+    rng = np.random.RandomState(4)
+    res_x, lsf = inputs(37, seed=17)
+    learned = lsf_bins() + rng.randn(256).astype(np.float32) * 1e-3           # drifted away from the initial table, unsorted
+    params = np.concatenate([[np.float32(-123.0)], learned]).astype(np.float32)   # a learned alpha the reference does NOT use here
+    got = update_lpc_residual(torch.from_numpy(res_x).to(DEV), torch.from_numpy(lsf).to(DEV), torch.from_numpy(params).to(DEV), chunk=16)
+    bins = np.sort(learned)
+    _, q = ref_nn.scalar_softmax_quantization(torch.from_numpy(lsf)[:, :, None], np.float32(-300.0), bins, 1.0, False, 16, 256)
+    poly = ref_lpc.lsf2poly_after_quan(q[:, :, 0].numpy(), 16)
+    want = ref_lpc.lpc_analysis_get_residual(res_x[:, :, None], poly)
+    assert rel_err(got.cpu().numpy(), want) < 1e-5
