@@ -37,3 +37,34 @@ def test_reference_arm_line_matches_the_headline_arm():
         assert r[k] == d[k], k
     assert r['e2e'] == {'value': r['value'], 'unit': r['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert r['cpu_baseline']['value'] == r['value'] and r['cpu_baseline']['kind'] == 'port'
+
+
+def test_round2_headline_line_reports_the_tensor_roof_and_the_sub_records():
+    """Round 2: the conv kernels are judged against the TENSOR pipe, with the issued fraction, ncu's
+    tensor-pipe activity and the measured DRAM traffic beside it; the default line carries bounded sub-records for the other
+    BASELINE.json configurations and for the reference's shipped switches ('gln', the_strides 4)."""
+    d = _line('r02_bench_default.json')
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline', 'sub_records'):
+        assert k in d, k
+    r = d['roofline']
+    assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert abs(r['issued_frac'] - 3 * r['frac']) < 1e-9 and r['mma_per_product'] == 3          # three MMAs per product (fp16 hi/lo)
+    assert 0 < r['tensor_pipe_active_ncu'] <= 100 and r['traffic'] > 0
+    assert r['traffic_detail']['traffic_vs_algorithmic'] > 1.0                                  # measured DRAM bytes vs real-channel payload
+    ws = r['whole_step']
+    assert ws['algorithmic_bytes_per_frame'] == 4624 and ws['traffic_vs_algorithmic'] > 100     # layer-by-layer: the honest number
+    assert 0 < r['hbm']['frac_of_measured'] < 1
+    e = d['e2e']
+    assert e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0 and 0 < e['value'] <= d['value'] * 1.02
+    s = d['sub_records']
+    for k in ('codec1_b128', 'cq_scaled', 'cq2_gln', 'cq2_stride4', 'cq2_gln_stride4', 'train', 'train_gln', 'corpus_1h_per_gpu'):
+        assert k in s and 'error' not in s[k], k
+    assert s['codec1_b128']['value'] >= 6000 and s['codec1_b128']['cpu_baseline']['kind'] == 'port'      # VERDICT item 6
+    assert s['codec1_b128']['launches_per_call'] < s['codec1_b128']['unprepared']['launches_per_call']
+    for k in ('cq2_gln', 'cq2_stride4', 'cq2_gln_stride4'):
+        assert s[k]['engine'].startswith('plane engine') and s[k]['value'] > 5000, k                       # VERDICT item 4
+    assert s['train']['collectives_per_step'] in (0, 1) and s['train']['ms_per_step'] > 0
+    ref = _line('r02_bench_reference.json')
+    assert ref['impl'] == 'reference' and ref['metric'] == d['metric'] and ref['unit'] == d['unit']
+    assert ref['e2e'] == {'value': ref['value'], 'unit': ref['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
