@@ -42,6 +42,13 @@ int launch_depthwise(const float* x, const float* dw, float* y, int64_t B, int L
 int launch_axpby(float* y, const float* x, float a, const float* z, float b, int64_t n, cudaStream_t st);
 // y = x / d
 int launch_div(float* y, const float* x, float d, int64_t n, cudaStream_t st);
+// weight gradient of a stride-1 conv on the tensor cores (wgrad_tc.cu): dw (K, Cin, Cout) += sum_{b,p} x[b,ci,p + t*dil - padL] g[b,co,p],
+// db (Cout) += sum g (db may be null).  x (B, Cin, L * stride), g (B, Cout, L) fp32 NCL; L = output positions (stride 1 or 2).  scratch: wgrad_tc_scratch_floats() floats.
+bool wgrad_tc_supported(int64_t B, int Lin, int Lout, int Cin, int Cout, int K, int dil, int stride, int padL);
+int64_t wgrad_tc_scratch_floats();
+int launch_wgrad_tc(const float* x, const float* g, float* dw, float* db, int64_t B, int L, int Cin, int Cout, int K, int dil, int padL,
+                    float* scratch, cudaStream_t st, int stride = 1);
+
 // y = a * b elementwise (the gate product of a gated block on the training tape)
 int launch_mul(float* y, const float* a, const float* b, int64_t n, cudaStream_t st);
 // acc (+)= x / d ; first = 1 overwrites

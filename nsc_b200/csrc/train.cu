@@ -701,7 +701,8 @@ int walk_codec(const nsc_codec_cfg& cfg, const CodecLayout& lay, const float* pa
 
 // backward through one conv record.  G(ptr) maps an activation pointer to its gradient twin.
 int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params, float* grads, char* act_base, char* grad_base,
-                  int64_t B, float* gpre, float* wflip, float* gtmp, int precision, void* wpack, bool need_dx, cudaStream_t st) {
+                  int64_t B, float* gpre, float* wflip, float* gtmp, int precision, void* wpack, bool need_dx, cudaStream_t st,
+                  float* wg_scratch = nullptr) {
   auto G = [&](const float* p) { return reinterpret_cast<float*>(grad_base + (reinterpret_cast<const char*>(p) - act_base)); };
   if (r.op == OP_MUL) {   // y = x * res
     const int64_t n = B * (int64_t)r.Cin * r.Lin;
@@ -756,6 +757,9 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     ProfScope prof(st, "wgrad_head", 2.0 * B * Lout * (double)r.K * r.Cin, 4.0 * B * ((double)r.Lin * r.Cin + (double)Lout));
     wgrad_head_kernel<<<dim3(r.Cin, splits), kWhThreads, 0, st>>>(r.x, gpre, dw, db, B, Lout, r.Cin, r.K, padL, fps);
     NSC_LAUNCH_OK();
+  } else if (precision > 0 && wg_scratch != nullptr && wgrad_tc_supported(B, r.Lin, Lout, r.Cin, r.Cout, r.K, r.dil, r.stride, padL)) {
+    // tensor cores (fp16 hi/lo split like the forward and data-gradient convs of this precision mode): positions are the K dimension
+    NSC_TRY(launch_wgrad_tc(r.x, gpre, dw, db, B, Lout, r.Cin, r.Cout, r.K, r.dil, padL, wg_scratch, st, r.stride));
   } else {
     const int M = r.K * r.Cin;
     ProfScope prof(st, "wgrad", 2.0 * B * Lout * (double)M * r.Cout, 4.0 * B * ((double)r.Lin * r.Cin + (double)Lout * r.Cout));
@@ -801,7 +805,7 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
 struct TrainLayout {
   std::vector<int64_t> arena;   // activation arena bytes per codec
   int64_t act_off[NSC_MAX_CODECS], grad_off[NSC_MAX_CODECS];
-  int64_t gpre_off, gtmp_off, wflip_off, gdec_off, acc_off, ge_off, wpack_off, total;
+  int64_t gpre_off, gtmp_off, wflip_off, gdec_off, acc_off, ge_off, wpack_off, wg_off, total;
 };
 
 TrainLayout train_layout(const nsc_codec_cfg* cfgs, int n, int64_t B) {
@@ -821,6 +825,7 @@ TrainLayout train_layout(const nsc_codec_cfg* cfgs, int n, int64_t B) {
   t.acc_off = off; off += align_up(B * (int64_t)kFrameLen * 4, 256);
   t.ge_off = off; off += 256 * 4;
   t.wpack_off = off; off += kTcWpackBytes;
+  t.wg_off = off; off += align_up(wgrad_tc_scratch_floats() * 4, 256);   // per-CTA accumulator slices of the tensor-core weight gradient
   t.total = off;
   return t;
 }
@@ -938,7 +943,8 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
     // seed: d/d(raw decoder output) = (gdec + acc) / rs
     NSC_TRY(nsc::launch_axpby(G(tb.out), gdec, 1.0f / res_scalar, acc, 1.0f, nfl, st));   // (gdec - acc) / rs, acc = sum_{m>i} rs * d/d in_m
     for (int k = (int)tb.dec_tape.size() - 1; k >= 0; --k)
-      NSC_TRY(nsc::conv_backward(tb.dec_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, cfgs[i].precision, ws + tl.wpack_off, true, st));
+      NSC_TRY(nsc::conv_backward(tb.dec_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, cfgs[i].precision, ws + tl.wpack_off, true, st,
+                                 reinterpret_cast<float*>(ws + tl.wg_off)));
     // quantiser (soft path)
     const float* alpha = params_ptrs_host[i] + lay.conv_floats;
     nsc::entropy_grad_kernel<<<1, 32, 0, st>>>(hist_global_ptrs_host[i + 1], cfgs[i].num_bins, tau * ent_w_host[i + 1] * (float)global_B, ge);
@@ -949,7 +955,8 @@ int nsc_train_backward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float*
     bool earlier = false;
     for (int j = 0; j < i; ++j) earlier = earlier || trainable_host[j + 1];
     for (int k = (int)tb.enc_tape.size() - 1; k >= 0; --k)
-      NSC_TRY(nsc::conv_backward(tb.enc_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, cfgs[i].precision, ws + tl.wpack_off, k > 0 || earlier, st));
+      NSC_TRY(nsc::conv_backward(tb.enc_tape[k], lay, params_ptrs_host[i], grads, act_base, grad_base, B, gpre, wflip, gtmp, cfgs[i].precision, ws + tl.wpack_off, k > 0 || earlier, st,
+                                 reinterpret_cast<float*>(ws + tl.wg_off)));
     if (earlier) {
       // acc += rs * d/d in_i   (applied with a minus sign in the seed of every earlier codec)
       NSC_TRY(nsc::launch_axpby(acc, G(tb.cin), res_scalar, acc, -1.0f / res_scalar, nfl, st));
