@@ -96,6 +96,26 @@ __global__ void subpixel_dgrad_weights_kernel(const float* __restrict__ w, float
   }
 }
 
+// The same sub-pixel data gradient as TWO dense k5 convs Cout -> Cin, one per input-position parity (the tensor engine's layers have at
+// most 128 output channels): wt[par][j][co][ci] = W[par + padL - 2 (j - 2)][ci][co]; their outputs are interleaved into the gradient.
+__global__ void subpixel_dgrad_weights_split_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int Cin, int Cout, int padL) {
+  const int total = 2 * 5 * Cout * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Cin, co = (i / Cin) % Cout, j = (i / (Cin * Cout)) % 5, par = i / (5 * Cin * Cout);
+    const int t = par + padL - 2 * (j - 2);
+    wt[i] = (t >= 0 && t < K) ? w[((int64_t)t * Cin + ci) * Cout + co] : 0.f;
+  }
+}
+// dst (B, C, 2 L)[b][c][2 v + par] += src[par] (B, C, L)[b][c][v]
+__global__ void add_interleaved_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t rows, int L) {
+  const int64_t total = rows * 2 * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (2 * L);
+    const int u = (int)(i - row * 2 * L);
+    dst[i] += src[(int64_t)(u & 1) * rows * L + row * L + (u >> 1)];
+  }
+}
+
 // gate product y = a * b (gated_bottleneck, nn_core_operator.py:102): ga += gy * b, gb += gy * a
 __global__ void mul_backward_kernel(const float* __restrict__ gy, const float* __restrict__ a, const float* __restrict__ b,
                                     float* __restrict__ ga, float* __restrict__ gb, int64_t n) {
@@ -782,6 +802,24 @@ int conv_backward(const ConvRec& r, const CodecLayout& lay, const float* params,
     // same engine choice as the forward walk (walker.cuh): tensor cores (fp16 hi/lo split) when the codec asks for them
     if (precision > 0 && wpack != nullptr && tc_conv_supported(a)) NSC_TRY(launch_conv_tc(a, precision, wpack, st));
     else NSC_TRY(launch_conv(a, st));
+  } else if (r.stride == 2 && r.dil == 1 && r.K == 9 && padL == 3 && r.Lin == 2 * Lout && (r.Lin & 3) == 0 &&
+             (int64_t)5 * r.Cout * 2 * r.Cin <= kWflipFloats && precision > 0 && wpack != nullptr && [&] {
+               ConvArgs t;
+               t.B = B; t.Lin = Lout; t.Cin = r.Cout; t.Cout = r.Cin; t.K = 5; t.dil = 1; t.stride = 1;
+               return tc_conv_supported(t);
+             }()) {
+    // tensor engine: one dense k5 conv per input-position parity, interleaved into the gradient
+    subpixel_dgrad_weights_split_kernel<<<ew_grid((int64_t)10 * r.Cout * r.Cin), 256, 0, st>>>(w, wflip, r.K, r.Cin, r.Cout, padL);
+    NSC_LAUNCH_OK();
+    const int64_t half = B * (int64_t)r.Cin * Lout;
+    for (int par = 0; par < 2; ++par) {
+      ConvArgs a;
+      a.x = gpre; a.w = wflip + (int64_t)par * 5 * r.Cout * r.Cin; a.bias = nullptr; a.y = gtmp + par * half; a.res_mode = RES_NONE;
+      a.B = B; a.Lin = Lout; a.Cin = r.Cout; a.Cout = r.Cin; a.K = 5; a.dil = 1; a.stride = 1;
+      NSC_TRY(launch_conv_tc(a, precision, wpack, st));
+    }
+    add_interleaved_kernel<<<ew_grid(2 * half), 256, 0, st>>>(G(r.x), gtmp, B * (int64_t)r.Cin, Lout);
+    NSC_LAUNCH_OK();
   } else if (r.stride == 2 && r.dil == 1 && r.K == 9 && padL == 3 && r.Lin == 2 * Lout && (r.Lin & 3) == 0 &&
              (int64_t)5 * r.Cout * 2 * r.Cin <= kWflipFloats) {
     subpixel_dgrad_weights_kernel<<<ew_grid((int64_t)5 * r.Cout * 2 * r.Cin), 256, 0, st>>>(w, wflip, r.K, r.Cin, r.Cout, padL);
