@@ -44,10 +44,16 @@ struct WgTc {
   int ones_row_s;       // column of ones in the S tile (bias gradient when W = g), or -1
   int64_t nblk;         // B * L / 64 position blocks
   float* scratch;       // [gridDim.x][128][npad]
+  // staged producers: the S operand's source rows of a block sit in shared memory as fp32 (window floats per row, covering the
+  // block's positions plus `halo` on either side, zeros outside the frame), so the tap shifts are shared-memory offsets
+  int halo, window, n_raw;
 };
 
 __device__ __forceinline__ uint32_t wg_sw128(int row, int chunk) { return (uint32_t)row * 128u + ((((uint32_t)chunk) ^ ((uint32_t)row & 7u)) << 4); }
 
+constexpr int kWgRawMax = 8;    // fp32 float4 chunks of the raw S rows per producer thread
+
+template <bool kStaged>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTc p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -102,6 +108,112 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         umma_commit(&empty[st]);
       }
       umma_commit(&acc_full);
+    }
+  } else if constexpr (kStaged) {
+    // =========================== producers, staged form ===========================
+    // Global loads only fetch what is unique -- the W operand's chunks and the S operand's source rows (one aligned window per
+    // channel) -- and they are issued ONE BLOCK AHEAD into registers, so their latency hides behind the conversion of the current
+    // block.  The source rows go to shared memory as fp32; the (tap, channel) rows of the S tile are then shifted reads of them.
+    const int ptid = tid - (kWgEpiWarps + 1) * 32;
+    constexpr int kProd = kWgProdWarps * 32;
+    const uint4 ones = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u), zero4 = make_uint4(0, 0, 0, 0);
+    float* raw0 = reinterpret_cast<float*>(smem + 2 * stage_bytes);
+    const int win = p.window, w4 = win >> 2, n_raw4 = p.Cs * w4;
+    int a_kind[kWgATasks], a_src[kWgATasks];
+    uint32_t a_off[kWgATasks];
+#pragma unroll
+    for (int i = 0; i < kWgATasks; ++i) {
+      const int a = ptid + i * kProd, row = a >> 3, c = a & 7;
+      a_kind[i] = row < p.Cw ? 1 : (row == p.ones_row_w ? 2 : 0);
+      a_src[i] = row * p.L + 8 * c;
+      a_off[i] = wg_sw128(row, c);
+    }
+    int s_kind[kWgSTasks], s_rel[kWgSTasks];
+    uint32_t s_off[kWgSTasks];
+#pragma unroll
+    for (int i = 0; i < kWgSTasks; ++i) {
+      const int t = ptid + i * kProd, row = t >> 3, c = t & 7;
+      s_kind[i] = t >= p.npad * 8 ? -1 : (row < p.taps * p.Cs ? 1 : (row == p.ones_row_s ? 2 : 0));
+      const int tt = row / p.Cs, ch = row - tt * p.Cs;
+      s_rel[i] = ch * win + p.halo + p.s_stride * 8 * c + p.shift_sign * ((p.t0 + tt) * p.dil - p.padL);
+      s_off[i] = wg_sw128(row, c);
+    }
+    int r_dst[kWgRawMax], r_src[kWgRawMax], r_pos[kWgRawMax];      // shared-memory float index, source row offset, position relative to the window start
+#pragma unroll
+    for (int k = 0; k < kWgRawMax; ++k) {
+      const int idx = ptid + k * kProd;
+      const int ch = idx / w4, f = idx - ch * w4;
+      r_dst[k] = idx < n_raw4 ? idx * 4 : -1;
+      r_src[k] = ch * p.Ls;
+      r_pos[k] = 4 * f - p.halo;
+    }
+    float4 fa[kWgATasks][2], fr[kWgRawMax];
+    auto issue_loads = [&](int64_t blk) {
+      const int64_t b = blk / bpf;
+      const int q0 = (int)(blk - b * bpf) * 64;
+      const float* wb = p.w_src + (size_t)b * p.Cw * p.L + q0;
+      const float* sb = p.s_src + (size_t)b * p.Cs * p.Ls;
+#pragma unroll
+      for (int i = 0; i < kWgATasks; ++i)
+        if (a_kind[i] == 1) {
+          const float4* src = reinterpret_cast<const float4*>(wb + a_src[i]);
+          fa[i][0] = __ldg(src);
+          fa[i][1] = __ldg(src + 1);
+        }
+#pragma unroll
+      for (int k = 0; k < kWgRawMax; ++k)
+        if (r_dst[k] >= 0) {
+          const int pos = p.s_stride * q0 + r_pos[k];                 // a multiple of 4: the float4 is wholly inside or outside the frame
+          fr[k] = (pos >= 0 && pos < p.Ls) ? __ldg(reinterpret_cast<const float4*>(sb + r_src[k] + pos)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    uint32_t j = 0;
+    if ((int64_t)blockIdx.x < p.nblk) issue_loads(blockIdx.x);
+    for (int64_t blk = blockIdx.x; blk < p.nblk; blk += gridDim.x, ++j) {
+      const uint32_t st = j & 1u;
+      float* raw = raw0 + (p.n_raw == 2 ? (size_t)(j & 1u) * (size_t)p.Cs * win : 0);
+      uint8_t* A_hi = smem + st * stage_bytes;
+      uint8_t* A_lo = A_hi + 16384;
+      uint8_t* S_hi = A_hi + 32768;
+      uint8_t* S_lo = S_hi + s_tile;
+      mbar_wait_relaxed(&empty[st], ((j >> 1) & 1u) ^ 1u);
+#pragma unroll
+      for (int k = 0; k < kWgRawMax; ++k)
+        if (r_dst[k] >= 0) *reinterpret_cast<float4*>(raw + r_dst[k]) = fr[k];
+#pragma unroll
+      for (int i = 0; i < kWgATasks; ++i) {
+        uint4 hi = zero4, lo = zero4;
+        if (a_kind[i] == 1) {
+          const float v[8] = {fa[i][0].x, fa[i][0].y, fa[i][0].z, fa[i][0].w, fa[i][1].x, fa[i][1].y, fa[i][1].z, fa[i][1].w};
+          split8(v, hi, lo);
+        } else if (a_kind[i] == 2) {
+          hi = ones;
+        }
+        *reinterpret_cast<uint4*>(A_hi + a_off[i]) = hi;
+        *reinterpret_cast<uint4*>(A_lo + a_off[i]) = lo;
+      }
+      asm volatile("bar.sync 1, %0;" :: "n"(kProd) : "memory");        // the source rows are in shared memory
+      if (blk + gridDim.x < p.nblk) issue_loads(blk + gridDim.x);       // next block's loads fly while this one is converted
+#pragma unroll
+      for (int i = 0; i < kWgSTasks; ++i) {
+        if (s_kind[i] < 0) continue;
+        uint4 hi = zero4, lo = zero4;
+        if (s_kind[i] == 1) {
+          const float* src = raw + s_rel[i];
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = src[p.s_stride * e];
+          split8(v, hi, lo);
+        } else if (s_kind[i] == 2) {
+          hi = ones;
+        }
+        *reinterpret_cast<uint4*>(S_hi + s_off[i]) = hi;
+        *reinterpret_cast<uint4*>(S_lo + s_off[i]) = lo;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+      if (p.n_raw == 1) asm volatile("bar.sync 1, %0;" :: "n"(kProd) : "memory");   // single source buffer: everybody has read it
     }
   } else {
     // =========================== producers: fp32 rows -> fp16 hi / lo operand tiles ===========================
@@ -296,9 +408,32 @@ int launch_wgrad_tc(const float* x, const float* g, float* dw, float* db, int64_
     p.npad = (p.n_used + 15) & ~15;
     p.nblk = nblk;
     p.scratch = scratch;
-    const size_t smem = 1024 + 2 * (2 * 16384 + 2 * (size_t)p.npad * 128);
-    NSC_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(p);
+    const size_t stages = 2 * (2 * 16384 + 2 * (size_t)p.npad * 128);
+    // staged producers when the fp32 source rows of a block fit beside the operand stages (twice, or once)
+    int max_shift = 0;
+    for (int tt = 0; tt < taps; ++tt) {
+      const int sh = (t0 + tt) * dil - padL;
+      if (sh > max_shift) max_shift = sh;
+      if (-sh > max_shift) max_shift = -sh;
+    }
+    p.halo = (max_shift + 3) & ~3;
+    p.window = 64 * p.s_stride + 2 * p.halo;
+    const size_t raw_bytes = (size_t)Cs * p.window * 4;
+    const size_t budget = 227 * 1024 - 2048;
+    p.n_raw = stages + 2 * raw_bytes <= budget ? 2 : (stages + raw_bytes <= budget ? 1 : 0);
+    // Measured (profiles/r02_wgrad_tc.log, 128 frames, all 54 layers of a step): direct producers 2.43 ms, staged 2.63 ms -- the kernel
+    // is bound by the producers' instruction issue (fp16 hi/lo conversion of nine shifted copies of the narrow operand), not by load
+    // latency, so hiding the loads buys nothing.  Default: direct; NSC_WGRAD_TC_STAGED=1 selects the staged form (parity-tested).
+    static const bool staged = [] { const char* e = getenv("NSC_WGRAD_TC_STAGED"); return e && e[0] == '1'; }();
+    if (!staged || Cs * (p.window / 4) > kWgRawMax * kWgProdWarps * 32) p.n_raw = 0;
+    const size_t smem = 1024 + stages + (size_t)p.n_raw * raw_bytes;
+    if (p.n_raw > 0) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      wgrad_tc_kernel<true><<<grid, kWgThreads, smem, st>>>(p);
+    } else {
+      NSC_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      wgrad_tc_kernel<false><<<grid, kWgThreads, smem, st>>>(p);
+    }
     NSC_LAUNCH_OK();
     WgRed r;
     r.scratch = scratch; r.grid = grid; r.npad = p.npad; r.Cw = Cw; r.Cs = Cs; r.taps = taps; r.t0 = t0; r.mode = mode;

@@ -349,3 +349,34 @@ def test_update_lpc_residual_vs_oracle():
     poly = ref_lpc.lsf2poly_after_quan(q[:, :, 0].numpy(), 16)
     want = ref_lpc.lpc_analysis_get_residual(res_x[:, :, None], poly)
     assert rel_err(got.cpu().numpy(), want) < 1e-5
+
+
+def test_tensor_core_weight_gradients_agree_across_their_variants():
+    """wgrad_tc.cu: the tensor-core weight gradient with direct producers (default), with staged producers (NSC_WGRAD_TC_STAGED=1: same
+    operand tiles, same MMA order -> bit-identical) and the CUDA-core kernel it replaces (NSC_WGRAD_TC=0: same gradient to fp32 rounding of
+    a 65k-term sum).  'gln' codecs: k1, k15 (two tap ranges), k9, depthwise / pointwise, stride-2 and 1-channel layers are all on the path."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_gpu_training as t\n"
+        "from nsc_b200.training import CQTrainer\n"
+        "res = {}\n"
+        "for rt in ('bottleneck', 'gln'):\n"
+        "    ocs, cm, cfg = t.make_models(2, -20.0, precision='tc_f16x3', resnet_type=rt)\n"
+        "    res_x, lsf = t.inputs(6, seed=41)\n"
+        "    tr = CQTrainer(cm, (60.0, 10.0, 10.0, 0.7), quan_w=[0.06, 0.5, 0.44], ent_w=[0.06, 0.5, 0.44])\n"
+        "    tr.loss_and_grads(torch.from_numpy(res_x).cuda(), torch.from_numpy(lsf).cuda(), tau=0.7)\n"
+        "    for i in range(2): res[rt + str(i)] = tr.grads[i].cpu().numpy()\n"
+        "np.savez(sys.argv[1], **res)\n"
+    ) % (root, os.path.join(root, 'tests'))
+    out = {}
+    for tag, env in (('direct', {}), ('staged', {'NSC_WGRAD_TC_STAGED': '1'}), ('cuda_core', {'NSC_WGRAD_TC': '0'})):
+        path = '/tmp/nsc_wgrad_%s.npz' % tag
+        e = dict(os.environ); e.update(env)
+        subprocess.run([sys.executable, '-c', code, path], check=True, env=e, timeout=600)
+        out[tag] = dict(np.load(path))
+    for k in out['direct']:
+        assert np.array_equal(out['direct'][k], out['staged'][k]), k
+        assert rel_l2(out['direct'][k], out['cuda_core'][k]) < 1e-4, k

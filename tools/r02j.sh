@@ -3,7 +3,7 @@ set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_training.py -x -q > gpurun_out/r02j_pytest.log 2>&1
 tail -25 gpurun_out/r02j_pytest.log | cut -c1-300
-for k in "NSC_WGRAD_TC=1" "NSC_WGRAD_TC=0"; do
+for k in "NSC_WGRAD_TC=1" "NSC_WGRAD_TC_DIRECT=1"; do
   echo "=== $k"
   env $k timeout 300 python bench.py --workload train --steps 10 --warmup 3 2>/dev/null | python -c "
 import json,sys
