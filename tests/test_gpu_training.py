@@ -378,5 +378,6 @@ def test_tensor_core_weight_gradients_agree_across_their_variants():
         subprocess.run([sys.executable, '-c', code, path], check=True, env=e, timeout=600)
         out[tag] = dict(np.load(path))
     for k in out['direct']:
-        assert np.array_equal(out['direct'][k], out['staged'][k]), k
+        # (same tiles, same MMA order; the heads' CUDA-core weight gradients still reduce with atomics, so not bitwise over the whole image)
+        assert rel_l2(out['direct'][k], out['staged'][k]) < 1e-6, k
         assert rel_l2(out['direct'][k], out['cuda_core'][k]) < 1e-4, k
