@@ -324,6 +324,15 @@ int nsc_lpc_windows(const float* utterance, int64_t T, float* windows, void* str
  *   for j < n_used, w_j = first / last / middle window chosen by (j, seg_amount) exactly like hann_process(seg, j, seg_amount)
  *   (the LPC path passes seg_amount = N but only runs j < N - 2, so its last window is never used).  out (out_len). */
 int nsc_overlap_add(const float* frames, int64_t n_used, int64_t seg_amount, float* out, int64_t out_len, void* stream);
+/* The same three steps over a BATCH of n_signals equal-length utterances (row-major (n_signals, T)), one launch each:
+ *   segments (n_signals, n_take, 512) with n_take <= nsc_segment_count(T - offset) frames per utterance;
+ *   windows (n_signals, n_take, 1024) with n_take <= nsc_lpc_window_count(nsc_segment_count(T));
+ *   frames (n_signals, n_used, 512) -> out (n_signals, out_len). */
+int nsc_utterances_to_segments(const float* utterances, int64_t T, int64_t n_signals, int64_t offset, int32_t post_window,
+                               int64_t n_take, float* segments, void* stream);
+int nsc_lpc_windows_batch(const float* utterances, int64_t T, int64_t n_signals, int64_t n_take, float* windows, void* stream);
+int nsc_overlap_add_batch(const float* frames, int64_t n_signals, int64_t n_used, int64_t seg_amount, float* out, int64_t out_len,
+                          void* stream);
 /* Zero-state second-order recursive filter over n_signals signals of length T (audiolazy ZFilter call semantics), float64
  *   arithmetic as a chunked parallel scan: y[n] = b0 x[n] + b1 x[n-1] + b2 x[n-2] - a1 y[n-1] - a2 y[n-2]; a[0] must be 1.
  *   highpass_filter / empha_filter / 1/empha_filter (lpc_utilities.py:8-11, cmrl.py:671, :735) are instances.

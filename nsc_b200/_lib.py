@@ -90,6 +90,9 @@ SIGNATURES = {
     "nsc_lpc_window_count": (_i64, [_i64]),
     "nsc_lpc_windows": (_i32, [_vp, _i64, _vp, _vp]),
     "nsc_overlap_add": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp]),
+    "nsc_utterances_to_segments": (_i32, [_vp, _i64, _i64, _i64, _i32, _i64, _vp, _vp]),
+    "nsc_lpc_windows_batch": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "nsc_overlap_add_batch": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "nsc_iir_workspace_bytes": (_i64, [_i64, _i64]),
     "nsc_iir_biquad": (_i32, [_vp, _i64, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _vp, _i64, _vp]),
     "nsc_packed_row_bytes": (_i32, [_i32, _i32]),

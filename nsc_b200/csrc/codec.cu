@@ -528,6 +528,17 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
     NSC_TRY(pcs.setup(cfgs, lays.data(), params_ptrs_host, n_codecs, Bc, static_cast<char*>(workspace) + head, workspace_bytes - head, st,
                       nsc::prepared_lookup(workspace, 2, cfgs, params_ptrs_host, n_codecs, Bc)));
   }
+  // The LPC front end (LSF codebook -> lsf2poly -> residual) does not depend on the codecs: when the caller keeps poly and res_x
+  // for the whole batch it runs ONCE over all B frames instead of once per pass (three launches per call instead of three per
+  // 2k frames, each at full occupancy).  The quantised LSFs (B x 16) borrow the head of `synthesized`, which is written last.
+  const bool front_once = poly != nullptr && res_x != nullptr && synthesized != nullptr && B > Bc;
+  if (front_once) {
+    float* qlsf = synthesized;
+    NSC_TRY(nsc::launch_quantize(lsf, B, P, lsf_params + 1, n_lsf_bins, lsf_params, is_quan_on, use_soft, qlsf, lsf_idx, nullptr,
+                                 lsf_hist, lsf_qloss, st));                                   // cmrl.py:782-788
+    NSC_TRY(nsc_lsf2poly(qlsf, B, poly, nullptr, stream));                                   // cmrl.py:793
+    NSC_TRY(nsc_lpc_residual(x, poly, B, res_x, stream));                                     // cmrl.py:796
+  }
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
     nsc::Carver cv(workspace, workspace_bytes);
@@ -538,12 +549,14 @@ int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* con
     const int64_t rest_bytes = workspace_bytes - cv.used;
     float* poly_c = poly ? poly + b0 * (P + 1) : poly_ws;
     float* res_c = res_x ? res_x + b0 * kFrameLen : res_ws;
-    // LSF codebook: scalar_softmax_quantization(lpc_x, alpha, lpc_bins, ...) cmrl.py:782-788
-    NSC_TRY(nsc::launch_quantize(lsf + b0 * P, nb, P, lsf_params + 1, n_lsf_bins, lsf_params, is_quan_on, use_soft, qlsf,
-                                 lsf_idx ? lsf_idx + b0 * P : nullptr, nullptr, lsf_hist,
-                                 lsf_qloss ? lsf_qloss + b0 : nullptr, st));
-    NSC_TRY(nsc_lsf2poly(qlsf, nb, poly_c, nullptr, stream));                              // cmrl.py:793
-    NSC_TRY(nsc_lpc_residual(x + b0 * kFrameLen, poly_c, nb, res_c, stream));               // cmrl.py:796
+    if (!front_once) {
+      // LSF codebook: scalar_softmax_quantization(lpc_x, alpha, lpc_bins, ...) cmrl.py:782-788
+      NSC_TRY(nsc::launch_quantize(lsf + b0 * P, nb, P, lsf_params + 1, n_lsf_bins, lsf_params, is_quan_on, use_soft, qlsf,
+                                   lsf_idx ? lsf_idx + b0 * P : nullptr, nullptr, lsf_hist,
+                                   lsf_qloss ? lsf_qloss + b0 : nullptr, st));
+      NSC_TRY(nsc_lsf2poly(qlsf, nb, poly_c, nullptr, stream));                              // cmrl.py:793
+      NSC_TRY(nsc_lpc_residual(x + b0 * kFrameLen, poly_c, nb, res_c, stream));               // cmrl.py:796
+    }
     NSC_TRY(cascade_chunk(cfgs, lays.data(), n_codecs, params_ptrs_host, res_c, b0, nb, Bc, res_scalar, 1, is_quan_on,
                           use_soft, idx_ptrs_host, hist_ptrs_host, qloss_ptrs_host, nullptr, decoded + b0 * kFrameLen,
                           rest, rest_bytes, st, plane ? &pcs : nullptr));

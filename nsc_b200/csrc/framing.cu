@@ -31,7 +31,11 @@ __device__ __forceinline__ double ola_window(int i, int64_t j, int64_t seg_amoun
   return j == 0 ? first_window(i) : (j == seg_amount - 1 ? last_window(i) : the_window(i));
 }
 
-__global__ void segment_kernel(const float* __restrict__ utt, int64_t offset, int post_window, float* __restrict__ seg, int64_t N) {
+// (blockIdx.y = signal of a batch of equal-length utterances: utt_stride / seg_stride floats apart)
+__global__ void segment_kernel(const float* __restrict__ utt, int64_t offset, int post_window, float* __restrict__ seg, int64_t N,
+                               int64_t utt_stride = 0, int64_t seg_stride = 0) {
+  utt += blockIdx.y * utt_stride;
+  seg += blockIdx.y * seg_stride;
   const int64_t total = N * kFrame;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = k / kFrame;
@@ -41,7 +45,10 @@ __global__ void segment_kernel(const float* __restrict__ utt, int64_t offset, in
   }
 }
 
-__global__ void lpc_windows_kernel(const float* __restrict__ utt, float* __restrict__ win, int64_t Nw) {
+__global__ void lpc_windows_kernel(const float* __restrict__ utt, float* __restrict__ win, int64_t Nw, int64_t utt_stride = 0,
+                                   int64_t win_stride = 0) {
+  utt += blockIdx.y * utt_stride;
+  win += blockIdx.y * win_stride;
   const int64_t total = Nw * 2 * kFrame;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
     const int64_t w = k / (2 * kFrame);
@@ -52,7 +59,9 @@ __global__ void lpc_windows_kernel(const float* __restrict__ utt, float* __restr
 
 // out[t] = sum_j w_j[t - 480 j] * frames[j][t - 480 j] over the (at most two) frames covering t: a gather, no atomics
 __global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_used, int64_t seg_amount, float* __restrict__ out,
-                                   int64_t out_len) {
+                                   int64_t out_len, int64_t frames_stride = 0, int64_t out_stride = 0) {
+  frames += blockIdx.y * frames_stride;
+  out += blockIdx.y * out_stride;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < out_len; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j1 = t / kHop;
     double acc = 0.0;
@@ -211,6 +220,57 @@ int nsc_overlap_add(const float* frames, int64_t n_used, int64_t seg_amount, flo
   NSC_CHECK_ARG(n_used >= 0 && seg_amount >= n_used, "nsc_overlap_add: n_used=%lld seg_amount=%lld", (long long)n_used, (long long)seg_amount);
   ProfScope prof((cudaStream_t)stream, "overlap_add", 0.0, 4.0 * (n_used * kFrame + out_len));
   overlap_add_kernel<<<grid_for(out_len, 256), 256, 0, (cudaStream_t)stream>>>(frames, n_used, seg_amount, out, out_len);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+// ---- batches of equal-length utterances (a corpus is coded utterance by utterance in the reference, cmrl.py:666-737; at 10 s per
+// utterance the per-utterance launches, not the work, were a third of the corpus workload's time) --------------------------------
+static int grid_y_ok(int64_t n, const char* what) {
+  NSC_CHECK_ARG(n >= 1 && n <= 65535, "%s: n_signals=%lld (1..65535)", what, (long long)n);
+  return NSC_OK;
+}
+
+int nsc_utterances_to_segments(const float* utterances, int64_t T, int64_t n_signals, int64_t offset, int32_t post_window,
+                               int64_t n_take, float* segments, void* stream) {
+  NSC_CHECK_ARG(offset >= 0 && offset <= T, "nsc_utterances_to_segments: offset %lld outside the signal", (long long)offset);
+  NSC_CHECK_ARG(n_take >= 0 && n_take <= nsc_segment_count(T - offset), "nsc_utterances_to_segments: n_take=%lld", (long long)n_take);
+  if (n_take == 0 || n_signals == 0) return NSC_OK;
+  NSC_TRY(grid_y_ok(n_signals, "nsc_utterances_to_segments"));
+  NSC_CHECK_ARG(utterances && segments, "nsc_utterances_to_segments: null pointer");
+  ProfScope prof((cudaStream_t)stream, "utterance_to_segment", 0.0, 8.0 * n_signals * n_take * kFrame);
+  int64_t gx = grid_for(n_take * kFrame, 256);
+  if (gx > 64) gx = 64;
+  segment_kernel<<<dim3((unsigned)gx, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(utterances, offset, post_window, segments, n_take, T,
+                                                                                             n_take * kFrame);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+int nsc_lpc_windows_batch(const float* utterances, int64_t T, int64_t n_signals, int64_t n_take, float* windows, void* stream) {
+  NSC_CHECK_ARG(n_take >= 0 && n_take <= nsc_lpc_window_count(nsc_segment_count(T)), "nsc_lpc_windows_batch: n_take=%lld", (long long)n_take);
+  if (n_take == 0 || n_signals == 0) return NSC_OK;
+  NSC_TRY(grid_y_ok(n_signals, "nsc_lpc_windows_batch"));
+  NSC_CHECK_ARG(utterances && windows, "nsc_lpc_windows_batch: null pointer");
+  ProfScope prof((cudaStream_t)stream, "lpc_windows", 0.0, 8.0 * n_signals * n_take * 2 * kFrame);
+  int64_t gx = grid_for(n_take * 2 * kFrame, 256);
+  if (gx > 64) gx = 64;
+  lpc_windows_kernel<<<dim3((unsigned)gx, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(utterances, windows, n_take, T, n_take * 2 * kFrame);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+
+int nsc_overlap_add_batch(const float* frames, int64_t n_signals, int64_t n_used, int64_t seg_amount, float* out, int64_t out_len,
+                          void* stream) {
+  if (out_len == 0 || n_signals == 0) return NSC_OK;
+  NSC_TRY(grid_y_ok(n_signals, "nsc_overlap_add_batch"));
+  NSC_CHECK_ARG(out != nullptr && (frames != nullptr || n_used == 0), "nsc_overlap_add_batch: null pointer");
+  NSC_CHECK_ARG(n_used >= 0 && seg_amount >= n_used, "nsc_overlap_add_batch: n_used=%lld seg_amount=%lld", (long long)n_used, (long long)seg_amount);
+  ProfScope prof((cudaStream_t)stream, "overlap_add", 0.0, 4.0 * n_signals * (n_used * kFrame + out_len));
+  int64_t gx = grid_for(out_len, 256);
+  if (gx > 64) gx = 64;
+  overlap_add_kernel<<<dim3((unsigned)gx, (unsigned)n_signals), 256, 0, (cudaStream_t)stream>>>(frames, n_used, seg_amount, out, out_len,
+                                                                                                 n_used * kFrame, out_len);
   NSC_LAUNCH_OK();
   return NSC_OK;
 }

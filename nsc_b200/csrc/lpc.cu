@@ -4,9 +4,9 @@
 // tf.py_func.  They are a few 10k MAC per frame -- nothing next to the 0.3 GFLOP of one codec -- so they
 // keep the reference's float64 arithmetic (B200's fp64 pipe is ample) and are organised purely for
 // parallelism across frames and coalesced HBM access:
-//   nsc_lpc_analyze   one warp per frame: windowed signal staged in smem as double, 17 autocorrelation lags
-//                     by strided partial sums + shuffle reduction, Levinson-Durbin in registers, LSFs by a
-//                     Chebyshev-series sign scan (2048 intervals over [0,pi]) + bisection, one root per lane.
+//   nsc_lpc_analyze   persistent CTAs, batches of frames in three phases: warp per frame for the 17 autocorrelation lags (lane =
+//                     contiguous chunk, sums out of registers), THREAD per frame for Levinson-Durbin, warp per frame for the LSFs
+//                     (Chebyshev-series sign scan over 2049 tabulated grid points, bisection on cos w, one root per lane).
 //   nsc_lsf2poly      one thread per frame: product of the 8+8 unit-circle quadratics.
 //   nsc_lpc_residual  one thread per output sample: the (<=2) zero-state sub-frame FIRs covering it.
 //   nsc_lpc_synth     one thread per frame, 16-deep history in registers, smem transpose for coalescing.
@@ -23,27 +23,8 @@ __device__ __forceinline__ double np_hanning(int j, int M) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared pieces of the analysis: autocorrelation (warp), Levinson-Durbin, poly -> LSF
+// shared pieces of the analysis: Levinson-Durbin, Chebyshev-series evaluation
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// s: smem signal of length len followed by >= kOrder zeros.  Returns r[0..16] in every lane.
-__device__ __forceinline__ void warp_autocorr(const double* s, int len, int lane, double r[kOrder + 1]) {
-#pragma unroll
-  for (int t = 0; t <= kOrder; ++t) r[t] = 0.0;
-  for (int n = lane; n < len; n += 32) {
-    const double v = s[n];
-#pragma unroll
-    for (int t = 0; t <= kOrder; ++t) r[t] = fma(v, s[n + t], r[t]);
-  }
-#pragma unroll
-  for (int t = 0; t <= kOrder; ++t) r[t] = warp_sum_d(r[t]);
-}
-
 // Levinson-Durbin (audiolazy.lpc autocorrelation strategy).  Returns false when the frame is not analysable.
 __device__ __forceinline__ bool levinson(const double r[kOrder + 1], double a[kOrder + 1]) {
 #pragma unroll
@@ -84,157 +65,249 @@ __device__ __forceinline__ double cheb_eval(const double c[9], double x) {
 
 constexpr int kGrid = 2048;  // sign-scan intervals over [0, pi]
 
-// spectrum.poly2lsf: roots of the sum/difference polynomials on the unit circle, ascending angles.
-// All lanes hold the same a[]; scratch: 2*8 doubles + 2 ints of shared memory per warp.
-__device__ __forceinline__ bool warp_poly2lsf(const double a[kOrder + 1], int lane, double* roots_s /*16*/,
-                                              int* count_s /*2*/, double* out_lsf /*lane<16 valid*/) {
-  // P1 = a1 - rev(a1), Q1 = a1 + rev(a1) with a1 = [a, 0]; deflate z=1 / z=-1.
-  double p[kOrder + 1], q[kOrder + 1];
-  {
-    double pp = 0.0, qq = 0.0;
-#pragma unroll
-    for (int k = 0; k <= kOrder; ++k) {
-      const double a1k = a[k];
-      const double a2k = (k == 0) ? 0.0 : a[kOrder + 1 - k];
-      pp = (a1k - a2k) + pp;   // P = P1 / (1 - z^-1)
-      qq = (a1k + a2k) - qq;   // Q = Q1 / (1 + z^-1)
-      p[k] = pp;
-      q[k] = qq;
-    }
-  }
-  double cp[9], cq[9];
-  cp[0] = p[8];
-  cq[0] = q[8];
-#pragma unroll
-  for (int m = 1; m <= 8; ++m) {
-    cp[m] = 2.0 * p[8 - m];
-    cq[m] = 2.0 * q[8 - m];
-  }
-  if (lane < 2) count_s[lane] = 0;
-  __syncwarp();
-  // scan: lane owns kGrid/32 consecutive intervals; ordered compaction keeps each list ascending.
-  constexpr int PER = kGrid / 32;
-  double brk_lo[2][8];  // a polynomial has 8 roots in total, so a lane can never hold more than 8 brackets
-  int total_found[2];
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const double* c = which == 0 ? cq : cp;  // Q's first root precedes P's; order is fixed later by sorting
-    double w0 = kPi * (double)(lane * PER) / (double)kGrid;
-    double f0 = cheb_eval(c, cos(w0));
-    int found = 0;
-    for (int i = 1; i <= PER; ++i) {
-      const double w1 = kPi * (double)(lane * PER + i) / (double)kGrid;
-      const double f1 = cheb_eval(c, cos(w1));
-      if ((f0 > 0.0) != (f1 > 0.0)) {
-        if (found < 8) brk_lo[which][found] = w0;
-        ++found;
-      }
-      w0 = w1;
-      f0 = f1;
-    }
-    // exclusive prefix over lanes
-    int incl = found;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int excl = incl - found;
-    total_found[which] = __shfl_sync(0xffffffffu, incl, 31);
-    const bool lane_overflow = found > 8;
-    const unsigned any_over = __ballot_sync(0xffffffffu, lane_overflow);
-    if (any_over) total_found[which] = -1;
-    if (total_found[which] == 8) {
-      for (int j = 0; j < found; ++j) roots_s[which * 8 + excl + j] = brk_lo[which][j];
-    }
-  }
-  __syncwarp();
-  const bool ok = (total_found[0] == 8) && (total_found[1] == 8);
-  double root = 0.0;
-  if (ok && lane < 16) {
-    const int which = lane >> 3;
-    const double* c = which == 0 ? cq : cp;
-    double lo = roots_s[lane], hi = lo + kPi / (double)kGrid;
-    const bool lo_pos = cheb_eval(c, cos(lo)) > 0.0;
-    for (int it = 0; it < 50; ++it) {
-      const double mid = 0.5 * (lo + hi);
-      const bool mid_pos = cheb_eval(c, cos(mid)) > 0.0;
-      if (mid_pos == lo_pos) lo = mid; else hi = mid;
-    }
-    root = 0.5 * (lo + hi);
-  }
-  __syncwarp();
-  if (ok && lane < 16) roots_s[lane] = root;
-  __syncwarp();
-  if (ok && lane < 16) {
-    // rank = own position + number of roots of the other polynomial below this one
-    const int which = lane >> 3, pos = lane & 7;
-    int rank = pos;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rank += (roots_s[(1 - which) * 8 + j] < root) ? 1 : 0;
-    out_lsf[rank] = root;
-  }
-  return ok;
-}
-
 // ------------------------------------------------------------------------------------------------
 // nsc_lpc_analyze: lpc_utilities.py:112-124 (MODE 0, 1024-sample windows) and :14-25 (MODE 1, 512 frames)
+//
+// The roof of this kernel is the fp64 pipe, not HBM: a frame costs 1024 x 17 autocorrelation DFMAs plus 2 x 2049 x 9 for the
+// sign scan of the two LSF polynomials (~55 k DFMA per 4 KB window).  Round 1's warp-per-frame kernel spent most of its time
+// elsewhere: 18 shared-memory loads per 17 DFMAs in the autocorrelation, cos() per scan point and per bisection step, cospi() per
+// windowed sample, and the (sequential) Levinson recursion executed redundantly by all 32 lanes.  This one is a persistent CTA
+// working in batches of frames, three phases per batch:
+//   A  warp per frame: window from a shared table -> padded shared buffer; each lane takes a CONTIGUOUS chunk of samples (+16 of the
+//      next chunk) into registers and runs its 17 lag sums out of registers; partials are summed in a fixed order through the buffer;
+//   B  THREAD per frame: Levinson-Durbin and the Chebyshev coefficients of the deflated sum / difference polynomials;
+//   C  warp per frame: sign scan over the 2049 grid points with cos(pi k / 2048) from a shared table (lane = point, ballots give the
+//      brackets in ascending order), bisection on x = cos w (no cos in the loop), w = acos(x), rank-merge of the two root lists.
 // ------------------------------------------------------------------------------------------------
-constexpr int kAWarps = 4;
+constexpr int kAWarps = 8;
+
+template <int MODE> struct AnaShape {
+  static constexpr int LEN = MODE == 0 ? 1024 : 512;
+  static constexpr int CH = LEN / 32;        // samples per lane
+  static constexpr int STRIDE = CH + 1;      // padded chunk stride in doubles (odd: lanes a chunk apart hit different banks)
+  static constexpr int BUF = 33 * STRIDE;    // 32 chunks + a zero chunk behind the last one
+  __host__ __device__ static constexpr size_t smem(int fpw) {
+    return sizeof(double) * ((size_t)kAWarps * BUF + (kGrid + 1) + 512 + (size_t)kAWarps * fpw * (kOrder + 1) +
+                             (size_t)kAWarps * fpw * 19 + kAWarps * 16) +
+           sizeof(int) * ((size_t)kAWarps * fpw + kAWarps * 16);
+  }
+};
 
 template <int MODE>
-__global__ void __launch_bounds__(kAWarps * 32)
-lpc_analyze_kernel(const float* __restrict__ in, int64_t N, double* __restrict__ lsf, float* __restrict__ lsf32,
+__global__ void __launch_bounds__(kAWarps * 32, 2)
+lpc_analyze_kernel(const float* __restrict__ in, int64_t N, int fpw, double* __restrict__ lsf, float* __restrict__ lsf32,
                    int* __restrict__ status) {
-  constexpr int LEN = MODE == 0 ? 1024 : 512;
-  __shared__ double sig_s[kAWarps][LEN + kOrder + 2];
-  __shared__ double roots_s[kAWarps][16];
-  __shared__ int count_s[kAWarps][2];
+  using S = AnaShape<MODE>;
+  constexpr int LEN = S::LEN, CH = S::CH, STRIDE = S::STRIDE;
+  extern __shared__ double ana_smem[];
+  const int batch = kAWarps * fpw;
+  double* sig_all = ana_smem;                                  // [kAWarps][BUF]
+  double* cosg = sig_all + kAWarps * S::BUF;                   // [kGrid + 1]  cos(pi k / kGrid)
+  double* hann = cosg + (kGrid + 1);                           // [512]        numpy.hanning(512)
+  double* r_s = hann + 512;                                    // [batch][17]
+  double* coef_s = r_s + batch * (kOrder + 1);                 // [batch][19]  cq[9] | cp[9]
+  double* roots_all = coef_s + batch * 19;                     // [kAWarps][16]
+  int* ok_s = reinterpret_cast<int*>(roots_all + kAWarps * 16);   // [batch]
+  int* brk_all = ok_s + batch;                                 // [kAWarps][16]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t frame = (int64_t)blockIdx.x * kAWarps + warp;
-  if (frame >= N) return;  // warp-uniform
-  double* s = sig_s[warp];
-  const float* x = in + frame * LEN;
-  if (MODE == 0) {
-    // window: [hanning(512)[:256], ones(512), hanning(512)[256:]]  (lpc_utilities.py:120-121)
-    for (int n = lane; n < LEN; n += 32) {
-      double w = 1.0;
-      if (n < 256) w = np_hanning(n, 512);
-      else if (n >= 768) w = np_hanning(n - 512, 512);
-      s[n] = (double)x[n] * w;
-    }
-  } else {
-    // highpass biquad then pre-emphasis, zero state per frame (lpc_utilities.py:8-11, :20); sequential -> lane 0
-    for (int n = lane; n < LEN; n += 32) s[n] = (double)x[n];
-    __syncwarp();
-    if (lane == 0) {
-      const double b0 = 0.989502, b1 = -1.979004, b2 = 0.989592, a1 = -1.978882, a2 = 0.979126;
-      double x1 = 0, x2 = 0, y1 = 0, y2 = 0, e1 = 0;
-      for (int n = 0; n < LEN; ++n) {
-        const double xv = s[n];
-        const double y = b0 * xv + b1 * x1 + b2 * x2 - a1 * y1 - a2 * y2;
-        x2 = x1; x1 = xv; y2 = y1; y1 = y;
-        s[n] = y + (-0.68) * e1;   // empha_filter = 1 - 0.68 z^-1 (constants.py:64)
-        e1 = y;
+  double* s = sig_all + warp * S::BUF;
+  double* roots_s = roots_all + warp * 16;
+  int* brk_s = brk_all + warp * 16;
+
+  for (int k = threadIdx.x; k <= kGrid; k += blockDim.x) cosg[k] = cos(kPi * (double)k / (double)kGrid);
+  if (MODE == 0)
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) hann[k] = np_hanning(k, 512);
+  __syncthreads();
+
+  const int64_t n_batches = (N + batch - 1) / batch;
+  for (int64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
+    const int64_t frame0 = bt * batch;
+    // ---- phase A: autocorrelation, warp per frame ------------------------------------------------------------------
+    for (int q = 0; q < fpw; ++q) {
+      const int slot = warp * fpw + q;
+      const int64_t frame = frame0 + slot;
+      if (frame >= N) break;   // warp-uniform
+      const float* x = in + frame * LEN;
+      if (MODE == 0) {
+        // window: [hanning(512)[:256], ones(512), hanning(512)[256:]]  (lpc_utilities.py:120-121)
+#pragma unroll 8
+        for (int n = lane; n < LEN; n += 32) {
+          const double w = n < 256 ? hann[n] : (n >= 768 ? hann[n - 512] : 1.0);
+          s[(n / CH) * STRIDE + n % CH] = (double)x[n] * w;
+        }
+      } else {
+        // highpass biquad then pre-emphasis, zero state per frame (lpc_utilities.py:8-11, :20); sequential -> lane 0
+        for (int n = lane; n < LEN; n += 32) s[(n / CH) * STRIDE + n % CH] = (double)x[n];
+        __syncwarp();
+        if (lane == 0) {
+          const double b0 = 0.989502, b1 = -1.979004, b2 = 0.989592, a1 = -1.978882, a2 = 0.979126;
+          double x1 = 0, x2 = 0, y1 = 0, y2 = 0, e1 = 0;
+          for (int n = 0; n < LEN; ++n) {
+            double* p = s + (n / CH) * STRIDE + n % CH;
+            const double xv = *p;
+            const double y = b0 * xv + b1 * x1 + b2 * x2 - a1 * y1 - a2 * y2;
+            x2 = x1; x1 = xv; y2 = y1; y1 = y;
+            *p = y + (-0.68) * e1;   // empha_filter = 1 - 0.68 z^-1 (constants.py:64)
+            e1 = y;
+          }
+        }
       }
+      if (lane < kOrder) s[32 * STRIDE + lane] = 0.0;   // the chunk behind the last one
+      __syncwarp();
+      double r[kOrder + 1];
+#pragma unroll
+      for (int t = 0; t <= kOrder; ++t) r[t] = 0.0;
+      // the lane's chunk in steps of 16 samples: 32 values in registers (16 + the 16 behind them), 16 x 17 DFMAs out of registers
+#pragma unroll
+      for (int h = 0; h < CH / 16; ++h) {
+        double c[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = 16 * h + j;                     // offset in the lane's chunk; beyond CH: the next chunk's head
+          c[j] = m < CH ? s[lane * STRIDE + m] : s[(lane + 1) * STRIDE + (m - CH)];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+          for (int t = 0; t <= kOrder; ++t) r[t] = fma(c[j], c[j + t], r[t]);
+        }
+      }
+      __syncwarp();
+      // fixed-order sum of the 32 partials per lag: lag-major rows of 33 doubles, lane t adds row t
+#pragma unroll
+      for (int t = 0; t <= kOrder; ++t) s[t * 33 + lane] = r[t];
+      __syncwarp();
+      if (lane <= kOrder) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int l = 0; l < 32; l += 4) {
+          a0 += s[lane * 33 + l];
+          a1 += s[lane * 33 + l + 1];
+          a2 += s[lane * 33 + l + 2];
+          a3 += s[lane * 33 + l + 3];
+        }
+        r_s[slot * (kOrder + 1) + lane] = (a0 + a1) + (a2 + a3);
+      }
+      __syncwarp();
     }
+    __syncthreads();
+    // ---- phase B: Levinson-Durbin + LSF polynomials, thread per frame ---------------------------------------------
+    if ((int)threadIdx.x < batch && frame0 + threadIdx.x < N) {
+      const int slot = threadIdx.x;
+      double r[kOrder + 1], a[kOrder + 1];
+#pragma unroll
+      for (int t = 0; t <= kOrder; ++t) r[t] = r_s[slot * (kOrder + 1) + t];
+      const bool ok = levinson(r, a);
+      // spectrum.poly2lsf: P1 = a1 - rev(a1), Q1 = a1 + rev(a1) with a1 = [a, 0]; deflate z = 1 / z = -1
+      double p[kOrder + 1], q[kOrder + 1];
+      double pp = 0.0, qq = 0.0;
+#pragma unroll
+      for (int k = 0; k <= kOrder; ++k) {
+        const double a1k = a[k];
+        const double a2k = (k == 0) ? 0.0 : a[kOrder + 1 - k];
+        pp = (a1k - a2k) + pp;   // P = P1 / (1 - z^-1)
+        qq = (a1k + a2k) - qq;   // Q = Q1 / (1 + z^-1)
+        p[k] = pp;
+        q[k] = qq;
+      }
+      double* cf = coef_s + slot * 19;
+      cf[0] = q[8];
+      cf[9] = p[8];
+#pragma unroll
+      for (int m = 1; m <= 8; ++m) {
+        cf[m] = 2.0 * q[8 - m];
+        cf[9 + m] = 2.0 * p[8 - m];
+      }
+      ok_s[slot] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- phase C: roots on the unit circle, warp per frame ---------------------------------------------------------
+    for (int q = 0; q < fpw; ++q) {
+      const int slot = warp * fpw + q;
+      const int64_t frame = frame0 + slot;
+      if (frame >= N) break;   // warp-uniform
+      bool ok = ok_s[slot] != 0;
+      double cq[9], cp[9];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        cq[m] = coef_s[slot * 19 + m];
+        cp[m] = coef_s[slot * 19 + 9 + m];
+      }
+      if (ok) {
+        // interval k = [k, k + 1] pi / kGrid holds a root when the sign of f differs at its ends; which = 0: Q (its first root
+        // precedes P's), 1: P
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const double* c = which == 0 ? cq : cp;
+          int found = 0;
+          unsigned prev = 0;
+          for (int g = 0; g < kGrid / 32; g += 4) {
+            double f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f[u] = cheb_eval(c, cosg[(g + u) * 32 + lane]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const unsigned mask = __ballot_sync(0xffffffffu, f[u] > 0.0);
+              unsigned chg = (mask ^ (mask >> 1)) & 0x7fffffffu;      // bit b: points 32 (g+u) + b and + b + 1 differ
+              if ((g + u) > 0 && ((prev >> 31) != (mask & 1u))) {     // last point of the previous group vs this group's first
+                if (found < 8 && lane == 0) brk_s[which * 8 + found] = (g + u) * 32 - 1;
+                ++found;
+              }
+              while (chg) {
+                const int b = __ffs(chg) - 1;
+                chg &= chg - 1;
+                if (found < 8 && lane == 0) brk_s[which * 8 + found] = (g + u) * 32 + b;
+                ++found;
+              }
+              prev = mask;
+            }
+          }
+          const bool last_pos = cheb_eval(c, cosg[kGrid]) > 0.0;      // point kGrid closes interval kGrid - 1
+          if (((prev >> 31) != 0u) != last_pos) {
+            if (found < 8 && lane == 0) brk_s[which * 8 + found] = kGrid - 1;
+            ++found;
+          }
+          if (found != 8) ok = false;
+        }
+      }
+      __syncwarp();
+      double root = 0.0;
+      if (ok && lane < 16) {
+        const int which = lane >> 3;
+        double c[9];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) c[m] = which == 0 ? cq[m] : cp[m];
+        const int k = brk_s[lane];
+        double xl = cosg[k], xr = cosg[k + 1];          // bisection on x = cos w: the bracket in w maps to [xr, xl]
+        const bool l_pos = cheb_eval(c, xl) > 0.0;
+        for (int it = 0; it < 52; ++it) {
+          const double mid = 0.5 * (xl + xr);
+          const bool mid_pos = cheb_eval(c, mid) > 0.0;
+          if (mid_pos == l_pos) xl = mid; else xr = mid;
+        }
+        root = acos(0.5 * (xl + xr));
+        roots_s[lane] = root;
+      }
+      __syncwarp();
+      if (lane < kOrder) {
+        double v = nan("");
+        int rank = lane;
+        if (ok) {
+          // rank = own position + number of roots of the other polynomial below this one
+          const int which = lane >> 3;
+          rank = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rank += (roots_s[(1 - which) * 8 + j] < root) ? 1 : 0;
+          v = root;
+        }
+        if (lsf) lsf[frame * kOrder + rank] = v;
+        if (lsf32) lsf32[frame * kOrder + rank] = (float)v;   // the cast the reference does when feeding lpc_x (float32 placeholder)
+      }
+      if (!ok && lane == 0 && status) atomicAdd(status, 1);
+      __syncwarp();
+    }
+    __syncthreads();   // the next batch overwrites r_s / coef_s / ok_s
   }
-  for (int n = LEN + lane; n < LEN + kOrder + 2; n += 32) s[n] = 0.0;
-  __syncwarp();
-  double r[kOrder + 1], a[kOrder + 1];
-  warp_autocorr(s, LEN, lane, r);
-  bool ok = levinson(r, a);
-  __shared__ double out_s[kAWarps][kOrder];
-  double* out = out_s[warp];
-  bool ok2 = false;
-  if (ok) ok2 = warp_poly2lsf(a, lane, roots_s[warp], count_s[warp], out);
-  __syncwarp();
-  if (lane < kOrder) {
-    const double v = (ok && ok2) ? out[lane] : nan("");
-    if (lsf) lsf[frame * kOrder + lane] = v;
-    if (lsf32) lsf32[frame * kOrder + lane] = (float)v;   // the cast the reference does when feeding lpc_x (float32 placeholder)
-  }
-  if (!(ok && ok2) && lane == 0 && status) atomicAdd(status, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,14 +365,16 @@ constexpr int kFrame = NSC_FRAME_LENGTH;
 __global__ void __launch_bounds__(kFrame)
 lpc_residual_kernel(const float* __restrict__ x, const float* __restrict__ poly, int64_t B,
                     float* __restrict__ res) {
+  constexpr int SUB = kFrame / 4, HALF = SUB / 2;  // 128, 64
   __shared__ float xs[kFrame];
   __shared__ double as[kOrder + 1];
+  __shared__ double hw[SUB];             // hanning(128): one cospi per CTA thread instead of two per sample
   const int64_t f = blockIdx.x;
   const int n = threadIdx.x;
   xs[n] = x[f * kFrame + n];
   if (n <= kOrder) as[n] = (double)poly[f * (kOrder + 1) + n];
+  if (n >= kFrame - SUB) hw[n - (kFrame - SUB)] = np_hanning(n - (kFrame - SUB), SUB);
   __syncthreads();
-  constexpr int SUB = kFrame / 4, HALF = SUB / 2;  // 128, 64
   double total = 0.0;
   const int s_hi = n / HALF;          // sub-frame starting at 64*s_hi covers n with j < 64
   const int s_lo = s_hi - 1;          // previous sub-frame covers n with j >= 64
@@ -312,9 +387,9 @@ lpc_residual_kernel(const float* __restrict__ x, const float* __restrict__ poly,
     double acc = 0.0;
     for (int k = 0; k <= kmax; ++k) acc = fma(as[k], (double)xs[n - k], acc);  // product exact in fp64
     double w;
-    if (s == 0) w = j < HALF ? 1.0 : np_hanning(j, SUB);
-    else if (s == 6) w = j < HALF ? np_hanning(j, SUB) : 1.0;
-    else w = np_hanning(j, SUB);
+    if (s == 0) w = j < HALF ? 1.0 : hw[j];
+    else if (s == 6) w = j < HALF ? hw[j] : 1.0;
+    else w = hw[j];
     total = __dadd_rn(total, __dmul_rn(acc, w));
   }
   res[f * kFrame + n] = (float)total;
@@ -372,27 +447,43 @@ lpc_synth_kernel(const float* __restrict__ poly, const float* __restrict__ res, 
 
 }  // namespace nsc
 
+namespace nsc {
+template <int MODE>
+static int launch_lpc_analyze(const float* in, int64_t N, double* lsf, float* lsf32, int32_t* status, cudaStream_t st) {
+  // two frames per warp and batch once every SM has work for both of its CTAs; one below that (latency, not throughput)
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int fpw = N >= (int64_t)sms * 2 * kAWarps * 2 ? 2 : 1;
+  const size_t smem = AnaShape<MODE>::smem(fpw);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[MODE]) {
+    NSC_CUDA_OK(cudaFuncSetAttribute(lpc_analyze_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AnaShape<MODE>::smem(2)));
+    attr_set[MODE] = true;
+  }
+  int64_t grid = ceil_div64(N, (int64_t)kAWarps * fpw);
+  if (grid > (int64_t)sms * 2) grid = (int64_t)sms * 2;
+  lpc_analyze_kernel<MODE><<<(unsigned)grid, kAWarps * 32, smem, st>>>(in, N, fpw, lsf, lsf32, status);
+  NSC_LAUNCH_OK();
+  return NSC_OK;
+}
+}  // namespace nsc
+
 extern "C" {
 
 int nsc_lpc_analyze(const float* windows, int64_t N, double* lsf_out, float* lsf_out_f32, int32_t* status,
                     void* stream) {
   if (N == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(windows && (lsf_out || lsf_out_f32), "nsc_lpc_analyze: null pointer");
-  nsc::ProfScope prof((cudaStream_t)stream, "lpc_analyze", (double)N * 2.0 * 17.0 * 1024.0, (double)N * (4096.0 + 128.0));
-  nsc::lpc_analyze_kernel<0><<<(unsigned)nsc::ceil_div64(N, nsc::kAWarps), nsc::kAWarps * 32, 0,
-                               (cudaStream_t)stream>>>(windows, N, lsf_out, lsf_out_f32, status);
-  NSC_LAUNCH_OK();
-  return NSC_OK;
+  nsc::ProfScope prof((cudaStream_t)stream, "lpc_analyze", (double)N * 2.0 * (17.0 * 1024.0 + 2.0 * 9.0 * 2049.0), (double)N * (4096.0 + 128.0));
+  return nsc::launch_lpc_analyze<0>(windows, N, lsf_out, lsf_out_f32, status, (cudaStream_t)stream);
 }
 
 int nsc_lpc_analyze_train(const float* frames, int64_t B, double* lsf_out, float* lsf_out_f32, int32_t* status,
                           void* stream) {
   if (B == 0) return NSC_OK;   // empty batch: nothing to validate or launch
   NSC_CHECK_ARG(frames && (lsf_out || lsf_out_f32), "nsc_lpc_analyze_train: null pointer");
-  nsc::lpc_analyze_kernel<1><<<(unsigned)nsc::ceil_div64(B, nsc::kAWarps), nsc::kAWarps * 32, 0,
-                               (cudaStream_t)stream>>>(frames, B, lsf_out, lsf_out_f32, status);
-  NSC_LAUNCH_OK();
-  return NSC_OK;
+  return nsc::launch_lpc_analyze<1>(frames, B, lsf_out, lsf_out_f32, status, (cudaStream_t)stream);
 }
 
 int nsc_lsf2poly(const float* lsf, int64_t B, float* poly, int32_t* status, void* stream) {

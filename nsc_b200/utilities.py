@@ -120,3 +120,47 @@ def load_sig_lpc(s):
     x = _lib.require_f32(s, 'signal')
     scale = x.std(unbiased=False)
     return x / scale, scale
+
+
+# ---- batches of equal-length utterances (one launch per step instead of one per utterance) -------------------------------------
+def _batch(x: torch.Tensor, name: str) -> torch.Tensor:
+    x = _lib.require_f32(x, name)
+    if x.dim() != 2:
+        raise ValueError(f"{name} must be (n_utterances, T)")
+    return x
+
+
+def utterances_to_segments(utterances, post_window=False, *, offset: int = 0, n_take=None):
+    """utterance_to_segment over a batch (n, T) of equal-length utterances -> (n, n_take, 512)."""
+    u = _batch(utterances, 'utterances')
+    n, T = u.shape
+    N = segment_count(T - offset)
+    n_take = N if n_take is None else int(n_take)
+    seg = torch.empty((n, n_take, frame_length), dtype=torch.float32, device=u.device)
+    _lib.check(_lib.load().nsc_utterances_to_segments(_lib.ptr(u), T, n, offset, 1 if post_window else 0, n_take, _lib.ptr(seg),
+                                                      _lib.stream_ptr()), 'utterances_to_segments')
+    return seg
+
+
+def lpc_windows_at_test_batch(utterances, n_take=None):
+    """lpc_windows_at_test over a batch (n, T) -> (n, n_take, 1024)."""
+    u = _batch(utterances, 'utterances')
+    n, T = u.shape
+    lib = _lib.load()
+    Nw = int(lib.nsc_lpc_window_count(lib.nsc_segment_count(T)))
+    n_take = Nw if n_take is None else int(n_take)
+    win = torch.empty((n, n_take, 2 * frame_length), dtype=torch.float32, device=u.device)
+    _lib.check(lib.nsc_lpc_windows_batch(_lib.ptr(u), T, n, n_take, _lib.ptr(win), _lib.stream_ptr()), 'lpc_windows_at_test_batch')
+    return win
+
+
+def overlap_add_batch(frames, seg_amount, n_used, out_len):
+    """overlap_add over a batch: frames (n, n_used, 512) -> (n, out_len)."""
+    f = _lib.require_f32(frames, 'frames')
+    if f.dim() != 3 or f.shape[2] != frame_length or f.shape[1] != int(n_used):
+        raise ValueError("frames must be (n, n_used, 512)")
+    n = f.shape[0]
+    out = torch.empty((n, max(int(out_len), 0)), dtype=torch.float32, device=f.device)
+    _lib.check(_lib.load().nsc_overlap_add_batch(_lib.ptr(f), n, int(n_used), int(seg_amount), _lib.ptr(out), out.shape[1],
+                                                 _lib.stream_ptr()), 'overlap_add_batch')
+    return out

@@ -236,6 +236,25 @@ def test_lpc_full_size_roundtrip_and_linearity():
     assert float(conv.abs().max()) < 1e-5
 
 
+def test_lpc_analysis_batch_shapes_agree_and_match_the_oracle():
+    """The analysis kernel works in batches of one or two frames per warp depending on the batch size, with ragged tails and silent
+    frames in the middle: the same windows must give the same LSFs to the bit whichever shape runs, and the oracle's to 1e-8."""
+    from nsc_b200 import lpc_utilities as lu
+    N = 5003                                             # > 2 CTAs x 8 warps x 2 frames x 148 SMs: the two-frames-per-warp shape
+    win_np = ar_frames(N, 1024, seed=211)
+    win_np[17] = 0.0
+    win_np[4999] = 0.0
+    win = cu(win_np)
+    whole = lu.lpc_analysis_windows(win, 16)
+    parts = torch.cat([lu.lpc_analysis_windows(win[i:i + 997], 16) for i in range(0, N, 997)])
+    assert torch.equal(torch.isnan(whole), torch.isnan(parts))
+    assert torch.equal(torch.nan_to_num(whole), torch.nan_to_num(parts))
+    assert bool(torch.isnan(whole[17]).all()) and bool(torch.isnan(whole[4999]).all()) and int(torch.isnan(whole).any(dim=1).sum()) == 2
+    pick = [0, 1, 16, 18, 2500, 4998, 5002]
+    ref = ref_lpc.lpc_analysis_windows(win_np[pick], 16)
+    assert rel_err(whole[pick].cpu().numpy(), ref) < 1e-8
+
+
 # ------------------------------------------------------------------------------------------------ losses
 def test_losses_vs_oracle_and_golden():
     from nsc_b200 import loss_terms_and_measures as lt

@@ -86,3 +86,42 @@ def test_digital_silence_does_not_poison_the_utterance():
         pipeline.code_utterances(cm, [sig], strict=True)
     clean = pipeline.code_utterances(cm, [torch.from_numpy(_utterance(24000, 7)).to(DEV)])[0]
     assert int(clean['n_failed_lpc_frames']) == 0
+
+
+def test_batched_corpus_path_is_bit_identical_to_the_per_utterance_path():
+    """code_utterances analyses / synthesises utterances of equal length as one batch (one launch per step instead of one per
+    utterance).  Same arithmetic per utterance: every output must match the one-by-one path to the bit, including an utterance
+    with a silent stretch (forward-fill must not look across utterance boundaries) and groups of one."""
+    from nsc_b200 import codec, pipeline
+    cfg = codec.CodecConfig(resnet_type='bottleneck')
+    cm = codec.CMRL([codec.NeuralCodec(cfg, device=DEV, seed=5), codec.NeuralCodec(cfg, device=DEV, seed=6)], res_scalar=1.0)
+    quiet = _utterance(16000, 13)
+    quiet[:5000] = 0.0
+    sigs = [_utterance(16000, 11), _utterance(9137, 12), quiet, _utterance(6000, 14), _utterance(9137, 15), _utterance(16000, 16)]
+    sigs = [torch.from_numpy(s).to(DEV) for s in sigs]
+    a = pipeline.code_utterances(cm, sigs, the_share=False, pack=True)
+    b = pipeline.code_utterances_one_by_one(cm, sigs, the_share=False, pack=True)
+    assert len(a) == len(b) == len(sigs)
+    for x, y in zip(a, b):
+        assert x['n_frames'] == y['n_frames'] and int(x['n_failed_lpc_frames']) == int(y['n_failed_lpc_frames'])
+        for k in ('synthesized', 'decoded', 'lsf_idx', 'records'):
+            assert torch.equal(x[k], y[k]), k
+        assert all(torch.equal(p, q) for p, q in zip(x['idx'], y['idx']))
+    assert int(a[2]['n_failed_lpc_frames']) > 0 and int(a[0]['n_failed_lpc_frames']) == 0
+
+
+def test_batch_framing_entry_points_match_the_single_utterance_ones():
+    from nsc_b200 import utilities as ut
+    rng = np.random.RandomState(3)
+    u = torch.from_numpy(rng.randn(5, 7013).astype(np.float32)).to(DEV)
+    seg = ut.utterances_to_segments(u, True, offset=256)
+    win = ut.lpc_windows_at_test_batch(u)
+    for i in range(5):
+        assert torch.equal(seg[i], ut.utterance_to_segment(u[i], True, offset=256))
+        assert torch.equal(win[i], ut.lpc_windows_at_test(u[i]))
+    n2 = seg.shape[1]
+    y = ut.overlap_add_batch(seg[:, :n2 - 2].contiguous(), seg_amount=n2, n_used=n2 - 2, out_len=512 + 480 * (n2 - 2))
+    for i in range(5):
+        assert torch.equal(y[i], ut.overlap_add(seg[i, :n2 - 2], seg_amount=n2, n_used=n2 - 2, out_len=512 + 480 * (n2 - 2)))
+    # a truncated take keeps the leading frames
+    assert torch.equal(ut.utterances_to_segments(u, False, n_take=3), torch.stack([ut.utterance_to_segment(r, False)[:3] for r in u]))
