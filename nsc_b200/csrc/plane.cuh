@@ -122,7 +122,27 @@ struct PlaneConv {
   int ileave = 0;                // the output image interleaves pairs of input frames (see above)
   int bmul = 1;                  // frames of this layer per codec frame (2 for a layer on de-interleaved sub-images)
   HeadFold fold;                 // PK_T heads (Cout = 1)
+  // FOLDED narrow images (the 20 -> 20 conv of a bottleneck block as a 48 -> 48 k5 conv on pairs of positions, see below)
+  int fold_out = 0;              // PK_T / PK_GEN with Cout = 20: `out` is the folded image of the 20-channel result (1; 2 = its de-interleaved form)
+  int fold2 = 0;                 // PK_X 48 -> 48 on a folded image: w / bias are the (9, 20, 20) kernel it is folded from, `out` the plain
+                                 // packed image (the epilogue unfolds: row r, channel 24 ph + c -> position 2 r + ph).  1: k5 (dilation 1, or
+                                 // dilation 2 per parity with `ileave`); 2: k9 block-diagonal (dilation 2 on the plain folded image, for
+                                 // frames too short to split by parity)
 };
+
+// ---- the narrow -> narrow conv of a bottleneck block on FOLDED images --------------------------------------------------------
+// A k9 20 -> 20 conv has N = 20: one MMA per tap runs at the ~44-cycle issue floor of narrow instructions, and putting the taps in N
+// (plane_t_kernel) pays for it with a tap sum across TMEM lanes that is bound by instruction issue.  Folding PAIRS of positions into
+// the channel axis turns it into an ordinary conv with more work per instruction and no lane crossing:
+//     X'[r, 24 ph' + ci] = x[2 r + ph', ci]            (rows = L / 2, 48 channels: 2 x (20 + 4 zero))
+//     Y'[r, 24 ph + co]  = sum_{s = 0..4} sum_{ph', ci} X'[r + s - 2, 24 ph' + ci] W[2 s + ph' - ph, ci, co]     (taps outside 0..8: zero)
+// i.e. a 48 -> 48 k5 conv on half-length frames (45 MMAs of N = 48 per 256 positions instead of 36 N = 32 MMAs per 128), run by
+// plane_x_kernel.  The folded image is an ordinary unpacked plane image (one 64-channel slab per plane, rows = L / 2) written by the
+// epilogue of the conv in front (fold_out); the 48 -> 48 conv's epilogue writes the plain packed image the third conv reads (fold2).
+// Dilation 2: the same on the two position parities separately (fold_out = 2 writes the de-interleaved folded image; the conv sees 2 B
+// frames of length L / 4 and interleaves the result back, `ileave`).
+constexpr int kFoldC = 48, kFoldK = 5;
+inline int64_t plane_fold2_scratch_bytes(int K) { return ((int64_t)(K * kFoldC * kFoldC + kFoldC) * 4 + 1023) & ~(int64_t)1023; }
 
 // kernel family of the narrow -> narrow convs (20 -> 20): NSC_PLANE_NARROW=T|X overrides the default
 int plane_narrow_kind();

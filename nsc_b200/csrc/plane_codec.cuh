@@ -78,7 +78,11 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
   const bool gln = c.resnet_type == 1;
   pl.Lc = kFrameLen >> NS;
   auto newbuf = [&](int L, int C, int deint) { pl.buf.push_back(make_plane_tensor(nullptr, L, C, P, deint)); return (int)pl.buf.size() - 1; };
-  struct Level { int L, w0, w1, wd, n0, n1, n0d, w2, c0, c1, Cdec; };
+  // bottleneck blocks: the 20 -> 20 conv on FOLDED images (plane.cuh; NSC_PLANE_FOLD2=0 keeps the taps-in-N kernel).  Needs 128 folded
+  // rows per (sub-)frame: dilation 1 from 256 positions, dilation 2 (folded per parity) from 512.
+  static const bool fold2_knob = [] { const char* e = getenv("NSC_PLANE_FOLD2"); return !(e && e[0] == '0'); }();
+  const bool fold2_on = fold2_knob && !gln && P == 2 && !plane_block_default_on();
+  struct Level { int L, w0, w1, wd, n0, n1, n0d, w2, c0, c1, Cdec, nf, nfd; };
   std::vector<Level> lv(NS + 1);
   for (int l = 0; l <= NS; ++l) {
     Level& v = lv[l];
@@ -90,6 +94,8 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
     v.n0 = newbuf(v.L, Nn, 0);
     v.n1 = newbuf(v.L, Nn, 0);
     v.n0d = gln ? newbuf(v.L, Nn, 1) : -1;
+    v.nf = (fold2_on && v.L / 2 >= 128) ? newbuf(v.L / 2, kFoldC, 0) : -1;      // folded image of a block's first narrow tensor
+    v.nfd = (fold2_on && v.L / 4 >= 128) ? newbuf(v.L / 2, kFoldC, 1) : -1;     // ... folded per position parity (dilation 2)
     v.c0 = v.c1 = v.w2 = -1;
     if (l < NS) { v.c0 = newbuf(v.L, v.Cdec, 0); v.c1 = newbuf(v.L, v.Cdec, 0); }
     if (l > 0 && gln) v.w2 = newbuf(v.L, W >> (NS - l), 0);     // depthwise result of the up-conv that leaves this level
@@ -150,16 +156,40 @@ PlaneCodecPlan make_plane_plan(const nsc_codec_cfg& c) {
         cur = out;
         continue;
       }
+      // the block's 20 -> 20 conv: folded (48 -> 48 k5 on pairs of positions, plane.cuh) where the level is long enough, else taps-in-N
+      const int d2 = c.dilations[i];
+      // dilation 2: per position parity where a parity sub-frame still has 128 folded rows, else the block-diagonal k9 form on the
+      // plain folded image
+      const bool by_parity = d2 == 2 && lvl.nfd >= 0;
+      const int nfold = (d2 == 1 || !by_parity) ? lvl.nf : lvl.nfd;
+      const bool folded = nfold >= 0 && c.k_dilated == 9;
+      const int fold_out = folded ? (by_parity ? 2 : 1) : 0;
+      auto narrow_conv = [&]() {
+        if (!folded) {
+          add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, d2, 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+          return;
+        }
+        if (d2 == 2 && !by_parity) {
+          add(v, vl, PK_X, Ls / 2, kFoldC, kFoldC, 9, 1, 1, NSC_ACT_LRELU, nfold, n1, -1, RES_NONE, NSC_ACT_NONE, 1).fold2 = 2;
+          return;
+        }
+        PlaneConv& f = add(v, vl, PK_X, Ls / (2 * d2), kFoldC, kFoldC, kFoldK, 1, 1, NSC_ACT_LRELU, nfold, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        f.fold2 = 1;
+        if (d2 == 2) {   // the two parities are independent frames of a quarter of the length; the epilogue interleaves them back
+          f.ileave = 1; f.bmul = 2;
+          f.in.deint = 0; f.in.rows = Ls / 4; f.in.frame_bytes = pl.buf[nfold].frame_bytes / 2;
+        }
+      };
       if (vec_in && i == 0) {
-        add(v, vl, PK_GEN, Ls, 1, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, -1, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
-        add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, PK_GEN, Ls, 1, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, -1, folded ? nfold : n0, -1, RES_NONE, NSC_ACT_NONE, 1).fold_out = fold_out;
+        narrow_conv();
         add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, -1, RES_ADD_BCAST, post, 1);
       } else {
         (&v == &pl.enc ? pl.enc_block : pl.dec_block).resize(v.size() + 1, 0);
         (&v == &pl.enc ? pl.enc_block : pl.dec_block)[v.size()] = 1;
         ++pl.n_fused;
-        add(v, vl, PK_T, Ls, Cw, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, cur, n0, -1, RES_NONE, NSC_ACT_NONE, 1);
-        add(v, vl, kNarrowKind, Ls, Nn, Nn, c.k_dilated, c.dilations[i], 1, NSC_ACT_LRELU, n0, n1, -1, RES_NONE, NSC_ACT_NONE, 1);
+        add(v, vl, PK_T, Ls, Cw, Nn, c.k_plain, 1, 1, NSC_ACT_LRELU, cur, folded ? nfold : n0, -1, RES_NONE, NSC_ACT_NONE, 1).fold_out = fold_out;
+        narrow_conv();
         add(v, vl, PK_X, Ls, Nn, Cw, c.k_plain, 1, 1, NSC_ACT_NONE, n1, out, cur, RES_ADD, post, 1);
       }
       cur = out;

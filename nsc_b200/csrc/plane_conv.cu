@@ -224,6 +224,23 @@ __host__ __device__ constexpr int tgroup_tap(int groups, int g, int slot) {   //
   return slot >= 1 ? 2 * g - 2 + slot : -1;      // g = 3: slots 1, 2 -> taps 5, 6;  g = 4: -> taps 7, 8
 }
 
+// weights of the folded narrow conv (plane.cuh): w (9, 20, 20), bias (20) -> out (5, 48, 48) followed by the 48 biases
+// (Kf = 5: dilation 1, tap 2 s + ph' - ph; Kf = 9: dilation 2 on the same image -- a position only meets its own phase, tap s)
+__global__ void fold2_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int Kf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nW = Kf * kFoldC * kFoldC;
+  if (i < nW) {
+    const int s = i / (kFoldC * kFoldC), rem = i - s * kFoldC * kFoldC;
+    const int a = rem / kFoldC, b = rem - a * kFoldC;          // input channel 24 ph' + ci, output channel 24 ph + co
+    const int phi = a / 24, ci = a - 24 * phi, pho = b / 24, co = b - 24 * pho;
+    const int t = Kf == 9 ? (phi == pho ? s : -1) : 2 * s + phi - pho;
+    out[i] = (ci < 20 && co < 20 && t >= 0 && t <= 8) ? w[(t * 20 + ci) * 20 + co] : 0.f;
+  } else if (i < nW + kFoldC) {
+    const int b = i - nW, co = b % 24;
+    out[i] = (co < 20 && bias != nullptr) ? bias[co] : 0.f;
+  }
+}
+
 struct PackArgs {
   const float* w;
   __half* out;
@@ -388,6 +405,7 @@ struct TParams {
   int out_free_target;       // arrivals that free a frame slot of `out`: its consumer's CTAs per frame
   unsigned long long* stats; // optional counters (fused block kernel)
   HeadFold fold;             // k55 heads: hard quantiser / cascade accumulation in the epilogue (plane.cuh)
+  int fold_out;              // 20-channel output written as the FOLDED image (plane.cuh): 0 no, 1 pairs of positions, 2 pairs within each parity
 };
 
 // spill slots: the quarters of the current and the previous tile; the k55 head has no per-tile barrier after its reads (no staged
@@ -557,6 +575,9 @@ __device__ __forceinline__ void t_body(const TParams& p) {
     float* const sU_l = sU + lane * kRF + coff;
     float* const sP_l = sP + (lane - (32 - m)) * kRF + coff;
     const int out_planes = p.out.planes;
+    const int fold_out = (C == 1) ? 0 : p.fold_out;
+    const int fsh = fold_out == 2 ? 2 : 1;             // positions per folded row of one slab, log2
+    const int fring = kORing >> fsh;                    // ring rows per (parity, plane) region of the folded staging buffer
     uint32_t it = 0, tb = 0, tbp = kTSlots - 4;       // tb: first spill slot of this tile's quarters (0, 4[, 8] in turn)
     const long long t_begin = clock64();
     for (int64_t f = rank; f < p.B; f += nranks) {
@@ -613,6 +634,19 @@ __device__ __forceinline__ void t_body(const TParams& p) {
           // A thread owns a ROW, so direct global stores would touch 32 different 128-byte lines per warp instruction (measured:
           // 1,600 of the 2,900 cycles of a tile).  The row goes into a shared-memory ring that mirrors the image; one thread
           // bulk-stores a whole window of finished rows per tile.
+          if (fold_out) {
+            // folded image (plane.cuh): `fsh` consecutive positions (of one parity for fold_out = 2) share a row of 24-channel groups;
+            // hi and lo planes (and the parities) are separate slabs, each with its own ring of kORing >> fsh rows
+            const int sp = ring0 + row;
+            const int frow = (sp >> fsh) & (fring - 1);
+            const int par = fold_out == 2 ? (row & 1) : 0;
+            const int ph = (row >> (fsh - 1)) & 1;
+            const uint32_t fsw = (uint32_t)(row >> fsh) & 7u;
+            uint8_t* rp = sO + (uint32_t)((par * 2) * fring + frow) * 128u + ((((uint32_t)(3 * ph + grp)) ^ fsw) << 4);
+            *reinterpret_cast<uint4*>(rp) = hi;
+            if (out_planes == 2) *reinterpret_cast<uint4*>(rp + (uint32_t)fring * 128u) = lo;
+            return;
+          }
           uint8_t* rp = sO + (uint32_t)((ring0 + row) & (kORing - 1)) * 128u;
           const uint32_t sw = (uint32_t)row & 7u;       // (row + 8) & 7
           if (out_planes == 2) {                        // K-concatenated row (plane.cuh)
@@ -706,9 +740,31 @@ __device__ __forceinline__ void t_body(const TParams& p) {
             if (lane == 0) mbar_arrive(&so_ready[it & 1u]);         // the storer warp takes it from here
           } else {
             asm volatile("bar.sync 2, %0;" :: "n"(kEpi * 32) : "memory");
-            if (warp == 0 && lane == 0) {
-              // rows final after this tile: everything up to 8 rows before its end (those wait for the next tile's down-spill)
-              const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
+            // rows final after this tile: everything up to 8 rows before its end (those wait for the next tile's down-spill)
+            const int upto = (j == T - 1) ? p.L : (j + 1) * 128 - 8;
+            if (fold_out) {
+              // every (parity, plane) slab of the folded image takes its own window of rows [done >> fsh, upto >> fsh); one issuing
+              // thread PER SLAB (lane 0 of warps 0-3): issuing a bulk copy costs the thread ~150 cycles and the issuing thread is on
+              // the epilogue's critical path -- eight copies from one thread made the 50 -> 20 layer 30 % slower
+              const int nreg = (fold_out == 2 ? 2 : 1) * out_planes;
+              if (lane == 0 && warp < nreg) {
+                const int64_t sb = pt_slab_bytes(p.out);
+                const int par = warp / out_planes, pl_i = warp - par * out_planes;
+                uint8_t* const gbase = orow + (int64_t)pt_slab_index(p.out, par, pl_i, 0) * sb;
+                const uint8_t* const sbase = sO + (uint32_t)((par * 2 + pl_i) * fring) * 128u;
+                int r0 = done_rows >> fsh;
+                const int r1 = upto >> fsh;
+                while (r0 < r1) {                                    // at most two pieces (ring wrap)
+                  const int ring_r = ((ring0 >> fsh) + r0) & (fring - 1);
+                  int n = r1 - r0;
+                  if (ring_r + n > fring) n = fring - ring_r;
+                  bulk_s2g(gbase + (int64_t)r0 * 128, sbase + (uint32_t)ring_r * 128u, (uint32_t)n * 128u);
+                  r0 += n;
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this slab's window before this one has left shared memory
+              }
+            } else if (warp == 0 && lane == 0) {
               int r0 = done_rows;
               while (r0 < upto) {                                    // at most two pieces (ring wrap)
                 const int ring_r = (ring0 + r0) & (kORing - 1);
@@ -728,7 +784,7 @@ __device__ __forceinline__ void t_body(const TParams& p) {
       }
     }
     if constexpr (C != 1) {
-      if (warp == 0 && lane == 0 && !ring_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (warp < 4 && lane == 0 && !ring_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // (folded output: one issuing thread per slab)
     }
     if (warp == 0 && lane == 0 && p.stats != nullptr) {
       stat_add(p.stats, 0, p.in_ready != nullptr ? 2 : 1);
@@ -896,6 +952,9 @@ struct XParams {
   const float* bias;
   const float* bias2;        // gated linear unit: bias of the tanh gate (columns [20, 40))
   int glu, ileave;           // see PlaneConv
+  int fold_out, unfold;      // folded narrow images (plane.cuh): the output is written folded / the 48-channel result is unfolded
+  int pairtiles;             // unfold + ileave: a CTA takes its tiles in PAIRS (2u, 2u + 1) = the two position parities of codec frame u,
+                             // so that the unfolded frame is complete in its staging buffer after the second one
   int Lin, Lout, Cin, Cout, K, dil, stride, padL;
   int act, post_act, res_mode, shuffle, planes;
   int Npad, ksteps, mt, tile, tiles_per_frame;
@@ -919,6 +978,14 @@ struct XParams {
   unsigned long long* stats; // optional counters (fused block kernel)
 };
 
+// tile of this CTA's i-th iteration (every role of plane_x_kernel walks the same sequence)
+__device__ __forceinline__ int64_t x_tile_at(const XParams& p, int64_t i) {
+  const int64_t c = (int64_t)blockIdx.x - p.cta0;
+  return p.pairtiles ? 2 * (c + (i >> 1) * p.ncta) + (i & 1) : c + i * p.ncta;
+}
+// unfold: rows of the output staging window -- one 256-position tile (dilation 1) or one frame of two parity tiles (dilation 2)
+__host__ __device__ constexpr int x_out_rows(int ileave) { return ileave ? 512 : 256; }
+
 constexpr int kXEpiGroups = 3;                   // epilogue warps per TMEM lane quarter (each takes every third 16-column batch)
 constexpr int kXEpiWarps = 4 * kXEpiGroups, kXGenWarps = 4;
 constexpr int kXThreadsX = (kXEpiWarps + 4) * 32;                 // + MMA issuer, A loader, W loader, second MMA issuer
@@ -937,6 +1004,25 @@ __device__ __forceinline__ void pt_load_raw(const PlaneTensor& t, const uint8_t*
   lo = t.planes == 2 ? __ldg(reinterpret_cast<const uint4*>(r + (int64_t)t.spp * sb)) : make_uint4(0, 0, 0, 0);
 }
 
+
+// channels [8g, 8g + 8) of output row `pos` through the folded-image index maps (plane.cuh): `unfold` -- this layer's rows are
+// PAIRS of positions (24 channels each) and the output is the plain image; `fold_out` -- the output image is folded (1) or
+// folded per position parity (2); omul / opar: `ileave`
+__device__ __forceinline__ void x_store8(const XParams& p, uint8_t* oimg, int pos, int g, const float (&v)[8], int omul, int opar) {
+  if (p.unfold) {
+    const int ph = g >= 3 ? 1 : 0;
+    pos = 2 * pos + ph;
+    g -= 3 * ph;
+  }
+  pos = omul * pos + opar;
+  if (p.fold_out) {
+    if (g >= 3) return;                 // channels 24-31 of a 20-channel result: no place in a 24-channel group
+    if (p.fold_out == 1) pt_store8(p.out, oimg, pos >> 1, 3 * (pos & 1) + g, v);
+    else pt_store8(p.out, oimg, ((pos >> 2) << 1) | (pos & 1), 3 * ((pos >> 1) & 1) + g, v);
+    return;
+  }
+  pt_store8(p.out, oimg, pos, g, v);
+}
 
 // ---- Toeplitz producers (PK_GEN), shared by plane_x_kernel<true> and plane_xs_kernel ---------------------------------
 __device__ __forceinline__ void gen_producer(const XParams& p, int ptid, int lane, uint8_t* sA, uint64_t* a_full, uint64_t* a_empty,
@@ -1063,7 +1149,9 @@ __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s,
   const int spp = p.in.spp;
   auto wait_stage = [&](int stage) {
     if (!((waited >> stage) & 1u)) {
+      const long long tw = p.stats != nullptr ? clock64() : 0;
       wait_full<MODE>(&x.b->a_full[kb + stage], &x.b->a_full2[kb + stage], a_phase);
+      if (p.stats != nullptr) stat_add(p.stats, 6, clock64() - tw);
       waited |= 1u << stage;
     }
   };
@@ -1096,7 +1184,7 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   const int m0 = p.n_iss == 2 ? issuer : 0;                       // first M tile of this thread
   const uint32_t a_lo_base = desc_lo(smem_u32(sA)) + (uint32_t)m0 * mt_step;
   const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4;
-  const int acc_cols = p.mt * p.Npad;
+  const int acc_cols = (p.n_iss == 3 ? 3 : p.mt) * p.Npad;
   XIssue x;
   x.idesc = make_idesc_f16(p.Npad, MODE == 0 ? 128 : 256);
   x.w_lo_base = desc_lo(smem_u32(sW));
@@ -1109,13 +1197,13 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   x.nmt = p.n_iss == 2 ? 1 : p.mt;
   x.npad = (uint32_t)p.Npad;
   uint32_t it = 0, kb = 0, a_phase = 0;
-  for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta, ++it) {
+  for (int64_t ti = 0, tile; (tile = x_tile_at(p, ti)) < p.n_tiles; ++ti, ++it) {
     const uint32_t acc_i = it & 1u;
     long long tw = p.stats != nullptr ? clock64() : 0;
     if constexpr (MODE != 2) mbar_wait(&bars.acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);   // (pair: both CTAs' epilogues arrive on the leader's)
     if (p.stats != nullptr) stat_add(p.stats, 7, clock64() - tw);
     tc_fence_after();
-    x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)(m0 * p.Npad);
+    x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)((p.n_iss == 3 ? issuer : m0) * p.Npad);
     x.u = 0;
     if (gen) {
       if constexpr (MODE == 0) {
@@ -1131,6 +1219,26 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
           x.done_w<0>();
         }
         for (int ap = 0; ap < p.planes; ++ap) umma_commit(&bars.a_empty[kb + ap]);
+      }
+    } else if (p.n_iss == 3) {
+      // folded narrow conv (plane.cuh): 45 narrow MMAs per tile cost one issuing thread ~85 cycles each (measured: 4.0 k cycles per
+      // tile in this loop, 0.2 k of them waiting), twice what the tensor pipe needs.  THREE issuing threads, one per product --
+      // 0: hi x W_hi, 1: lo x W_hi, 2: hi x W_lo -- each into its own accumulator; the epilogue adds the three.
+      if constexpr (MODE == 0) {
+        const int st = issuer == 1 ? 1 : 0;                        // this product's activation plane (spp = 1: stage = plane)
+        const long long t_iss = p.stats != nullptr ? clock64() : 0;
+        mbar_wait(&bars.a_full[kb + (uint32_t)st], a_phase);
+        if (p.stats != nullptr) stat_add(p.stats, 6, clock64() - t_iss);
+        tc_fence_after();
+        const uint32_t a0 = a_lo_base + (kb + (uint32_t)st) * stage_lo + (uint32_t)(8 - p.padL) * 8u;
+        for (int t = 0; t < p.K; ++t) {
+          const uint32_t unit = (uint32_t)(t * 2 + (issuer == 2 ? 1 : 0));   // ((slab K) + tap) planes + plane
+          if (!x.w_ready) { mbar_wait(&bars.w_full[unit], 0u); tc_fence_after(); }
+          issue_ks<3, 0>(x.d, a0 + (uint32_t)t * 8u, x.w_lo_base + unit * x.unit_lo, x.idesc, t == 0 ? 0u : 1u);
+        }
+        umma_commit(&bars.a_empty[kb]);                            // (every issuing thread reports on both planes' stages)
+        umma_commit(&bars.a_empty[kb + 1u]);
+        if (p.stats != nullptr && issuer == 0) { stat_add(p.stats, 5, clock64() - t_iss); stat_add(p.stats, 4, 1); }
       }
     } else if (p.in.packed) {
       tw = p.stats != nullptr ? clock64() : 0;
@@ -1148,6 +1256,7 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
     } else {
       const int nsub = p.in.deint ? 2 : 1;
       uint32_t waited = 0, accum = 0;
+      const long long t_iss = p.stats != nullptr ? clock64() : 0;
       for (int s = 0; s < p.in.spp; ++s) {
         const int nks = min(4, p.ksteps - 4 * s);
         const uint32_t a0 = a_lo_base + kb * stage_lo;
@@ -1160,11 +1269,12 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
         for (int sub = 0; sub < nsub; ++sub)
           for (int ap = 0; ap < p.planes; ++ap) commit_mode<MODE>(&bars.a_empty[kb + pt_slab_index(p.in, sub, ap, s)]);
       }
+      if (p.stats != nullptr) { stat_add(p.stats, 5, clock64() - t_iss); stat_add(p.stats, 4, 1); }   // issue section incl. its waits; tiles
     }
     commit_mode<MODE>(&bars.acc_full[acc_i]);
     x.w_ready = true;
-    if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) a_phase ^= 1u; }
-    else a_phase ^= 1u;
+    kb += (uint32_t)p.n_stage;                       // next of the kbuf tile buffers
+    if (kb == (uint32_t)(p.n_stage * p.kbuf)) { kb = 0; a_phase ^= 1u; }
   }
 }
 
@@ -1183,7 +1293,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   const int nbuf = p.n_stage * p.kbuf;
   uint8_t* sA = smem;
   uint8_t* sW = smem + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
-  const int acc_cols = p.mt * p.Npad;
+  const int acc_cols = (p.n_iss == 3 ? 3 : p.mt) * p.Npad;
   const int n_iss = p.n_iss;           // issuing threads: one, or one per M tile
   constexpr int kIssuer1 = kGen ? kXEpiWarps + 3 + kXGenWarps : kXEpiWarps + 3;
 
@@ -1217,7 +1327,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
     const float slope = act_slope_of(p.act), pslope = act_slope_of(p.post_act);
     const bool slow_act = p.act == NSC_ACT_TANH || p.post_act == NSC_ACT_TANH;
     uint32_t it = 0;
-    for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta, ++it) {
+    for (int64_t ti = 0, tile; (tile = x_tile_at(p, ti)) < p.n_tiles; ++ti, ++it) {
       const int64_t f = tile / p.tiles_per_frame;
       const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
       const uint32_t acc_i = it & 1u;
@@ -1265,6 +1375,75 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         if (lane == 0) {
           if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);
           else mbar_arrive(&acc_empty[acc_i]);
+        }
+        continue;
+      }
+      if (p.unfold) {
+        // folded narrow conv (plane.cuh): row q of this tile holds output positions 2 q and 2 q + 1 (24 columns each).  A thread owns
+        // a row, so direct global stores would touch 32 lines per warp instruction (the load/store unit, not the MMAs, then bounds
+        // the layer: measured 67 us per launch against 35 of MMAs).  The rows go to a staging ring that mirrors the packed output
+        // image and leave by ONE bulk store per 256 positions (dilation 1) or per frame (dilation 2: the two parities of a frame are
+        // consecutive tiles of this CTA, `pairtiles`).  One 16-column batch per epilogue group.
+        uint8_t* const sO = sW + (uint32_t)p.wslots * (uint32_t)p.slot_bytes;
+        mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
+        tc_fence_after();
+        uint32_t r[16], r1[16], r2[16];
+        const uint32_t tcol = tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(grp * 16);
+        tmem_ld16(tcol, r);
+        if (n_iss == 3) { tmem_ld16(tcol + (uint32_t)p.Npad, r1); tmem_ld16(tcol + 2u * (uint32_t)p.Npad, r2); }   // one accumulator per product
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                          // TMEM slot free: the next tile's MMAs run under the rest
+          if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);
+          else mbar_arrive(&acc_empty[acc_i]);
+        }
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float a = __uint_as_float(r[e]);
+          if (n_iss == 3) a += __uint_as_float(r1[e]) + __uint_as_float(r2[e]);
+          v[e] = act_fast(a + s_bias[grp * 16 + e], slope);
+        }
+        const int q = quarter * 32 + lane;
+        // window rows: dilation 1 -> tile parity picks a 256-row half, row 2 q + ph; dilation 2 -> the whole ring, row 4 q + 2 ph + parity
+        const int wbase = p.ileave ? (int)(f & 1) : 0;
+        const int wmul = p.ileave ? 4 : 2, wph = p.ileave ? 2 : 1;
+        // the window's previous contents must have left shared memory: its bulk store was issued a whole tile ago (dilation 1: one
+        // 256-row window, stored per tile) or when the previous frame was complete (dilation 2), so this wait is normally free --
+        // waiting right after the store instead stalled the epilogue for the duration of the read
+        if (warp == 0 && lane == 0 && (!p.ileave || !(f & 1))) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 3, %0;" :: "n"(kXEpiWarps * 32) : "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int g = 2 * grp + h, ph = g >= 3 ? 1 : 0, gg = g - 3 * ph;
+          float a8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a8[e] = v[8 * h + e];
+          uint4 hi, lo;
+          split8(a8, hi, lo);
+          const int R = wbase + wmul * q + wph * ph;
+          uint8_t* rp = sO + (uint32_t)R * 128u;
+          const uint32_t sw = (uint32_t)R & 7u;
+          if (gg < 2) {                                           // K-concatenated row (plane.cuh)
+            *reinterpret_cast<uint4*>(rp + (((uint32_t)gg ^ sw) << 4)) = hi;
+            *reinterpret_cast<uint4*>(rp + (((uint32_t)(gg + 2) ^ sw) << 4)) = lo;
+            *reinterpret_cast<uint4*>(rp + (((uint32_t)(gg + 4) ^ sw) << 4)) = hi;
+          } else {
+            *reinterpret_cast<uint4*>(rp + ((6u ^ sw) << 4)) = make_uint4(hi.x, hi.y, lo.x, lo.y);
+            *reinterpret_cast<uint4*>(rp + ((7u ^ sw) << 4)) = make_uint4(hi.x, hi.y, 0u, 0u);
+          }
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 3, %0;" :: "n"(kXEpiWarps * 32) : "memory");
+        if (warp == 0 && lane == 0) {
+          if (!p.ileave) {
+            bulk_s2g(p.out.base + f * p.out.frame_bytes + (int64_t)(8 + 2 * q0) * 128, sO, 256u * 128u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          } else if (f & 1) {
+            bulk_s2g(p.out.base + (f >> 1) * p.out.frame_bytes + 8 * 128, sO, 512u * 128u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
         continue;
       }
@@ -1325,8 +1504,8 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
           float a[8], b[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) { a[e] = v[e]; b[e] = v[8 + e]; }
-          pt_store8(p.out, oimg, omul * pos + opar, c0 >> 3, a);
-          pt_store8(p.out, oimg, omul * pos + opar, (c0 >> 3) + 1, b);
+          x_store8(p, oimg, pos, c0 >> 3, a, omul, opar);
+          x_store8(p, oimg, pos, (c0 >> 3) + 1, b, omul, opar);
         } else {   // sub-pixel: out[2 pos + r, c] = y[pos, 2 c + r]   (nscm.py:158-167)
           float a[8], b[8];
 #pragma unroll
@@ -1352,6 +1531,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         else mbar_arrive(&acc_empty[acc_i]);
       }
     }
+    if (p.unfold && warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == kXEpiWarps || warp == kIssuer1) {
     // =========================== MMA issuers ===========================
     const int issuer = warp == kXEpiWarps ? 0 : 1;
@@ -1373,7 +1553,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       const int nsub = p.in.deint ? 2 : 1;
       const int npl = p.in.packed ? 1 : p.in.planes;
       uint32_t kb = 0, ph = 1;
-      for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
+      for (int64_t ti = 0, tile; (tile = x_tile_at(p, ti)) < p.n_tiles; ++ti) {
         const int64_t f = tile / p.tiles_per_frame;
         const int q0 = (int)(tile - f * p.tiles_per_frame) * p.tile;
         const uint8_t* img = p.in.base + f * p.in.frame_bytes;
@@ -1386,8 +1566,8 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
               bulk_g2s(sA + (uint32_t)(kb + stage) * (uint32_t)p.stage_bytes, img + stage * sb + (int64_t)(q0 - (p.halo - 8)) * 128,
                        (uint32_t)p.stage_bytes, &a_full[kb + stage]);
             }
-        if (p.kbuf == 2) { kb = kb ? 0u : (uint32_t)p.n_stage; if (kb == 0) ph ^= 1u; }
-        else ph ^= 1u;
+        kb += (uint32_t)p.n_stage;
+        if (kb == (uint32_t)(p.n_stage * p.kbuf)) { kb = 0; ph ^= 1u; }
       }
     }
   } else if (warp == kXEpiWarps + 2) {
@@ -1401,9 +1581,15 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
           mbar_expect_tx(&w_full[u], sbytes);
           bulk_g2s(sW + (uint32_t)u * sbytes, wsrc + (size_t)u * p.unit_bytes, sbytes, &w_full[u]);
         }
+        if constexpr (!kGen && !pair) {
+          if (n_iss == 3) {        // resident weights leave this thread idle: it is the third MMA-issuing thread of the folded conv
+            const XBars bars{a_full, a_empty, w_full, w_empty, acc_full, acc_empty, a_full2, w_full2};
+            x_issuer<0>(p, false, 2, sA, sW, tmem, bars);
+          }
+        }
       } else {
         uint32_t ws = 0, wph = 1;
-        for (int64_t tile = (int64_t)blockIdx.x - p.cta0; tile < p.n_tiles; tile += p.ncta) {
+        for (int64_t ti = 0; x_tile_at(p, ti) < p.n_tiles; ++ti) {
           for (int u = 0; u < p.n_units; ++u) {
             mbar_wait_relaxed(&w_empty[ws], wph);
             mbar_expect_tx(&w_full[ws], sbytes);
@@ -1760,7 +1946,10 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   if (c.stride != 1 || c.shuffle != 1 || c.res_mode != RES_NONE || c.post_act != NSC_ACT_NONE) return false;
   if (k9 && c.act == NSC_ACT_TANH) return false;      // the 20-channel epilogue applies slope-form activations only
   if (c.Cin < 2 || c.in.deint || c.Lin % 128 != 0 || c.in.rows != c.Lin) return false;
-  if (k9 && (!c.out.packed || c.out.deint || c.out.rows != c.Lin)) return false;
+  if (k9 && !c.fold_out && (!c.out.packed || c.out.deint || c.out.rows != c.Lin)) return false;
+  if (c.fold_out && (!k9 || c.out.packed || c.out.spp != 1 || (c.fold_out == 2) != (c.out.deint != 0) || c.out.rows != (c.Lin >> c.fold_out) ||
+                     (c.fold_out != 1 && c.fold_out != 2)))
+    return false;
   // narrow -> narrow: tap groups by row shift, 5 (or 3) tap slots across lanes instead of 9 -- the lane-crossing volume bounds the layer.
   // Measured per 33k frames (both dilations): nine taps in N 21.1 ms, 3 groups / 5 slots 18.4 ms, 5 groups / 3 slots 21.0 ms on a box
   // where 3 groups took 19.3 (30 MMAs per tile from ONE issuing thread cost more than the lanes save).
@@ -1794,6 +1983,7 @@ TParams make_tparams(const PlaneConv& c, const TPlan& pl, int cta0, int ncta) {
   p.out_free_target = 1;
   p.stats = nullptr;
   p.fold = c.fold;
+  p.fold_out = c.fold_out;
   return p;
 }
 
@@ -1824,10 +2014,21 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   if (c.res_mode == RES_ADD_BCAST && c.resvec == nullptr) return false;
   if (c.res_mode == RES_MUL || (gen && c.res_mode != RES_NONE)) return false;
   if (c.glu && (gen || !c.in.packed || !c.out.packed || c.Cout != 40 || c.shuffle != 1 || c.res_mode != RES_NONE || c.stride != 1)) return false;
-  if (c.ileave && (c.out.deint || c.shuffle != 1 || c.out.rows != 2 * Lout)) return false;
-  if (!c.ileave && c.out.rows != (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
+  // folded narrow images (plane.cuh)
+  if (c.fold2 && (gen || c.Cin != kFoldC || c.Cout != kFoldC || c.K != (c.fold2 == 2 ? 9 : kFoldK) || c.dil != 1 || c.stride != 1 || c.in.packed || !c.out.packed ||
+                  (c.fold2 == 2 && c.ileave) ||
+                  c.planes != 2 || c.res_mode != RES_NONE || c.shuffle != 1 || c.glu || c.fold_out))
+    return false;
+  if (c.fold_out && (c.Cout != 20 || c.shuffle != 1 || c.glu || c.ileave || c.res_mode != RES_NONE || c.out.packed || c.out.spp != 1 ||
+                     (c.fold_out != 1 && c.fold_out != 2) || (c.fold_out == 2) != (c.out.deint != 0) || c.out.rows != (Lout >> c.fold_out)))
+    return false;
+  if (c.fold2 && c.ileave && Lout != 128) return false;   // (the unfolding epilogue stages one frame = two 128-row parity tiles)
+  const int unf = c.fold2 ? 2 : 1;                 // output positions per row of this layer
+  if (c.ileave && (c.out.deint || c.shuffle != 1 || c.out.rows != 2 * unf * Lout)) return false;
+  if (!c.ileave && !c.fold_out && c.out.rows != unf * (c.out.deint ? Lout * c.shuffle / 2 : Lout * c.shuffle)) return false;
   p->kind = c.kind;
   p->glu = c.glu; p->ileave = c.ileave; p->bias2 = c.bias2;
+  p->fold_out = c.fold_out; p->unfold = c.fold2 ? 1 : 0;
   p->cta0 = 0; p->ncta = 1; p->in_ready = nullptr; p->in_free = nullptr; p->stats = nullptr;
   p->in = c.in; p->out = c.out; p->res = c.res;
   p->xvec = c.xvec; p->xsub = c.xsub; p->xscale = c.xscale; p->resvec = c.resvec;
@@ -1842,7 +2043,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   if (p->n_stage > kXMaxStage) return false;
   // narrow-input, wide-output layers (the HBM-bound third conv of a block) take the staged epilogue
   static const bool no_stage = getenv("NSC_PLANE_NOSTAGE") != nullptr;
-  p->staged = ((gen || c.in.packed) && c.shuffle == 1 && !c.out.packed && c.stride == 1 && !no_stage && c.act != NSC_ACT_TANH &&
+  p->staged = ((gen || c.in.packed) && c.shuffle == 1 && !c.out.packed && !c.fold_out && c.stride == 1 && !no_stage && c.act != NSC_ACT_TANH &&
                c.post_act != NSC_ACT_TANH) ? 1 : 0;   // (the staged epilogue applies slope-form activations only)
   // tile: two M-tiles per work unit when everything fits (halves the weight re-streaming of ring layers)
   // CTA pairs (cta_group::2) for the layers with a plain epilogue: each CTA of a pair keeps its own tile and half of every
@@ -1853,13 +2054,16 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
   // M = 128 one occupies one, so the ~44-cycle floor of narrow instructions is not halved).  Default: pairs where two M tiles
   // share a weight pass; NSC_PLANE_PAIR=0 never, =2 wherever possible.
   static const int pair_knob = [] { const char* e = getenv("NSC_PLANE_PAIR"); return e ? atoi(e) : 1; }();
-  for (int mt = (Lout % 256 == 0 && c.stride == 1) ? 2 : 1; mt >= 1; --mt) {
+  p->pairtiles = (c.fold2 && c.ileave) ? 1 : 0;
+  const size_t out_ring = c.fold2 ? (size_t)x_out_rows(c.ileave) * 128 : 0;      // staging window of the unfolding epilogue
+  for (int mt = (Lout % 256 == 0 && c.stride == 1 && !c.fold2) ? 2 : 1; mt >= 1; --mt) {
     p->mt = mt;
     p->tile = 128 * mt;
     p->stage_bytes = (p->tile + 2 * (gen ? 8 : p->halo)) * 128;
     p->tiles_per_frame = Lout / p->tile;
     p->n_tiles = c.B * p->tiles_per_frame;
-    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && !c.glu && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
+    // (CTA pairs do not help the folded narrow conv: it is bound by the issue rate of ONE thread, and a pair still has one -- measured)
+    p->pair = (pair_knob >= (mt == 2 ? 1 : 2) && !gen && !c.glu && !c.fold2 && p->n_tiles >= 2 && p->n_tiles % 2 == 0) ? 1 : 0;
     p->slot_bytes = p->pair ? p->unit_bytes / 2 : p->unit_bytes;
     const size_t slot = (size_t)p->slot_bytes;
     const size_t a1 = (size_t)p->n_stage * p->stage_bytes;
@@ -1868,8 +2072,11 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
     // staged epilogue: ring of residual / output units.  A pair's half-size weight slots leave room for a fourth unit -- more
     // bytes in flight per SM, which is what bounds the HBM-bound layers
     p->s_units = p->staged ? ((p->pair && 2 * a1 + 3 * slot + (size_t)(kSUnits + 1) * c.planes * kSPlane <= smem_budget) ? kSUnits + 1 : kSUnits) : 0;
-    const size_t budget = smem_budget - (size_t)p->s_units * c.planes * kSPlane;
-    if (p->n_units <= kXMaxW && 2 * a1 + wall <= budget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
+    const size_t budget = smem_budget - (size_t)p->s_units * c.planes * kSPlane - out_ring;
+    // (the folded narrow conv is bound by bytes in flight per SM -- ncu: 20 % tensor activity, 43 % of HBM with two tile buffers --
+    // and its pair form has room for a third)
+    if (c.fold2 && p->n_units <= kXMaxW && 3 * a1 + wall <= budget) { p->kbuf = 3; p->resident = 1; p->wslots = p->n_units; }
+    else if (p->n_units <= kXMaxW && 2 * a1 + wall <= budget) { p->kbuf = 2; p->resident = 1; p->wslots = p->n_units; }
     else if (2 * a1 + (p->pair ? 3 * slot : 4ull * p->unit_bytes) <= budget) { p->kbuf = 2; p->resident = 0; }
     else if (p->n_units <= kXMaxW && a1 + wall <= budget) { p->kbuf = 1; p->resident = 1; p->wslots = p->n_units; }
     else if (a1 + 3ull * p->unit_bytes <= budget) { p->kbuf = 1; p->resident = 0; }
@@ -1882,7 +2089,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
       p->wslots = (int)ws;
     }
     int cols = 32;
-    while (cols < 2 * mt * p->Npad) cols *= 2;
+    while (cols < 2 * (c.fold2 ? 3 : mt) * p->Npad) cols *= 2;      // (folded conv: one accumulator per product, see x_issuer)
     p->tmem_cols = cols;
     p->B = c.B;
     // chunks of the output row the consumer's K steps read but this layer does not write
@@ -1901,6 +2108,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
       p->n_iss = (p->mt == 2 && !p->staged) ? 2 : 1;
       if (knob == 1) p->n_iss = 1;
       if (knob == 2 && p->mt == 2) p->n_iss = 2;
+      if (c.fold2 && p->resident && p->kbuf * p->n_stage <= kXMaxStage) p->n_iss = 3;
     }
     return true;
   }
@@ -1908,7 +2116,8 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
 }
 
 size_t x_smem_bytes(const XParams& p) {
-  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.slot_bytes + (size_t)p.s_units * p.planes * kSPlane;
+  return 1024 + (size_t)p.n_stage * p.kbuf * p.stage_bytes + (size_t)p.wslots * p.slot_bytes + (size_t)p.s_units * p.planes * kSPlane +
+         (p.unfold ? (size_t)x_out_rows(p.ileave) * 128 : 0);
 }
 
 }  // namespace
@@ -1946,7 +2155,7 @@ int64_t plane_wpack_bytes(const PlaneConv& c) {
   PlaneConv cc = c;
   cc.B = 1;
   if (!plan_x(cc, &p)) return -1;
-  return (int64_t)p.n_units * p.unit_bytes;
+  return (int64_t)p.n_units * p.unit_bytes + (c.fold2 ? plane_fold2_scratch_bytes(c.K) : 0);
 }
 
 bool plane_plan_info(const PlaneConv& c, int64_t* o) {
@@ -1980,6 +2189,17 @@ int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
   NSC_CHECK_ARG(!c.glu || c.w2 != nullptr, "plane engine: gated layer without its second kernel");
   PackArgs a;
   a.w = c.w; a.out = static_cast<__half*>(c.wpack);
+  if (c.fold2) {
+    // (9, 20, 20) -> (5, 48, 48) + bias (48) behind the packed units, then packed like any 48 -> 48 k5 layer
+    XParams p;
+    PlaneConv cc = c;
+    cc.B = 1;
+    NSC_CHECK_ARG(plan_x(cc, &p), "plane engine: unsupported folded layer");
+    float* scratch = reinterpret_cast<float*>(static_cast<uint8_t*>(c.wpack) + (size_t)p.n_units * p.unit_bytes);
+    fold2_weights_kernel<<<(c.K * kFoldC * kFoldC + kFoldC + 255) / 256, 256, 0, st>>>(c.w, c.bias, scratch, c.K);
+    NSC_LAUNCH_OK();
+    a.w = scratch;
+  }
   a.w2 = c.glu ? c.w2 : nullptr; a.csplit = 20;
   a.kind = c.kind; a.K = c.K; a.Cin = c.Cin; a.Cout = c.Cout; a.planes = c.planes;
   a.in_packed = c.kind == PK_GEN ? 0 : c.in.packed;
@@ -2053,9 +2273,18 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   }
   XParams p;
   NSC_CHECK_ARG(plan_x(c, &p), "plane engine: unsupported layer (k%d d%d s%d %d->%d)", c.K, c.dil, c.stride, c.Cin, c.Cout);
+  if (c.fold2 && getenv("NSC_FOLD_STATS") != nullptr) {   // experiment: issue / wait counters of the folded conv (nsc_debug_block_stats)
+    void* sp = nullptr;
+    NSC_CUDA_OK(cudaGetSymbolAddress(&sp, g_block_stats));
+    NSC_CUDA_OK(cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * kStatCtas * kStatWords, st));
+    p.stats = static_cast<unsigned long long*>(sp);
+  }
+  if (c.fold2)   // the folded biases sit behind the folded kernel, behind the packed units (plane_pack_weights)
+    p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(c.wpack) + (size_t)p.n_units * p.unit_bytes) + c.K * kFoldC * kFoldC;
   const size_t smem = x_smem_bytes(p);
+  const int64_t n_work = p.pairtiles ? p.n_tiles / 2 : p.n_tiles;      // (pairtiles: a CTA's unit of work is a pair of tiles)
   {
-    int64_t g = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    int64_t g = n_work < sm_count() ? n_work : sm_count();
     if (p.pair) g &= ~(int64_t)1;
     p.ncta = (int)g;
   }
@@ -2068,10 +2297,16 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
            c.Cin, c.Cout);
   double bytes = (double)c.B * (c.kind == PK_GEN ? 4.0 * c.Lin : pt_real_bytes(c.Lin, c.Cin, c.planes));
   bytes += (double)c.B * pt_real_bytes(Lout, c.Cout, c.planes);
+  double flops = 2.0 * macs;
+  if (c.fold2) {   // the k9 20 -> 20 conv it stands for: its real work and payload, under its own name
+    snprintf(name, sizeof(name), "pF%d_k9d%d_c20to20", c.planes, (c.ileave || c.fold2 == 2) ? 2 : 1);
+    flops = 2.0 * (double)c.B * (2.0 * Lout) * 9.0 * 20.0 * 20.0;
+    bytes = 2.0 * (double)c.B * pt_real_bytes(2 * Lout, 20, c.planes);
+  }
   if (c.res_mode == RES_ADD) bytes += (double)c.B * pt_real_bytes(Lout, c.Cout, c.planes);
   if (c.res_mode == RES_ADD_BCAST) bytes += (double)c.B * 4.0 * Lout;
-  ProfScope prof(st, name, 2.0 * macs, bytes);
-  int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  ProfScope prof(st, name, flops, bytes);
+  int64_t grid = n_work < sm_count() ? n_work : sm_count();
   if (p.pair) grid &= ~(int64_t)1;
   auto launch_pairs = [&]() {
     cudaLaunchConfig_t cfg = {};
@@ -2356,7 +2591,7 @@ struct TcBlockPlan {
 };
 
 int make_tc_block_plan(int64_t B, int L, int wide, int narrow, int k_plain, int k_dilated, int dilation, int is_last_flat, int precision,
-                       TcBlockPlan* pl) {
+                       TcBlockPlan* pl, bool folded = false) {
   using namespace nsc;
   NSC_CHECK_ARG(precision == 1 || precision == 2, "nsc_bottleneck_block_tc: precision must be 1 (fp16 hi/lo) or 2 (fp16)");
   NSC_CHECK_ARG(B >= 1 && L > 0 && L % 128 == 0 && wide > 32 && wide <= 128 && narrow == 20 && k_plain == 9 && k_dilated == 9 &&
@@ -2374,6 +2609,18 @@ int make_tc_block_plan(int64_t B, int L, int wide, int narrow, int k_plain, int 
   conv(b.c3, PK_X, narrow, wide, k_plain, 1, NSC_ACT_NONE, RES_ADD, is_last_flat ? NSC_ACT_NONE : NSC_ACT_LRELU);
   const PlaneTensor tx = make_plane_tensor(nullptr, L, wide, P, 0), tn = make_plane_tensor(nullptr, L, narrow, P, 0);
   b.c1.in = tx; b.c1.out = tn; b.c2.in = tn; b.c2.out = tn; b.c3.in = tn; b.c3.out = tx; b.c3.res = tx;
+  // the 20 -> 20 conv on folded images (plane.cuh), as the codec program runs it where the frame is long enough
+  const bool by_parity = dilation == 2 && L / 4 >= 128;      // dilation 2: per position parity, or block-diagonal k9 on short frames
+  const PlaneTensor tf = make_plane_tensor(nullptr, L / 2, kFoldC, P, by_parity ? 1 : 0);
+  const int64_t w2_plain = plane_wpack_bytes(b.c2);
+  if (folded) {
+    NSC_CHECK_ARG(P == 2 && L / 2 >= 128, "nsc_bottleneck_block_tc: the folded narrow conv needs hi/lo planes and 128 folded rows per frame");
+    b.c1.fold_out = by_parity ? 2 : 1; b.c1.out = tf;
+    const bool diag = dilation == 2 && !by_parity;
+    conv(b.c2, PK_X, kFoldC, kFoldC, diag ? 9 : kFoldK, 1, NSC_ACT_LRELU, RES_NONE, NSC_ACT_NONE);
+    b.c2.Lin = by_parity ? L / 4 : L / 2; b.c2.fold2 = diag ? 2 : 1; b.c2.in = tf; b.c2.out = tn;
+    if (by_parity) { b.c2.ileave = 1; b.c2.bmul = 2; b.c2.B = 2 * B; b.c2.in.deint = 0; b.c2.in.rows = L / 4; b.c2.in.frame_bytes = tf.frame_bytes / 2; }
+  }
   int ring = plane_block_ring_frames();
   while (ring > 2 && ring > B) ring /= 2;
   b.ring = ring;
@@ -2381,9 +2628,21 @@ int make_tc_block_plan(int64_t B, int L, int wide, int narrow, int k_plain, int 
                 "nsc_bottleneck_block_tc: a conv of the block is not covered by the tensor engine");
   pl->x_bytes = align_up(B * tx.frame_bytes, 1024);
   pl->y_bytes = pl->x_bytes;
-  pl->n_bytes = align_up(B * tn.frame_bytes, 1024);
+  {
+    const int64_t tf2 = make_plane_tensor(nullptr, L / 2, kFoldC, P, 1).frame_bytes;   // the largest of the narrow tensor's three forms
+    pl->n_bytes = align_up(B * (tn.frame_bytes > tf2 ? tn.frame_bytes : tf2), 1024);
+  }
   pl->w1 = align_up(plane_wpack_bytes(b.c1), 1024);
-  pl->w2 = align_up(plane_wpack_bytes(b.c2), 1024);
+  {
+    PlaneConv f;                                     // sized for either form of the narrow conv
+    conv(f, PK_X, kFoldC, kFoldC, 9, 1, NSC_ACT_LRELU, RES_NONE, NSC_ACT_NONE);      // (the k9 form is the larger of the two folded ones)
+    f.Lin = 128; f.fold2 = 2; f.in = make_plane_tensor(nullptr, 128, kFoldC, 2, 0); f.out = make_plane_tensor(nullptr, 256, narrow, 2, 0); f.planes = 2;
+    const int64_t w2_fold = plane_wpack_bytes(f);
+    const int64_t w2_now = plane_wpack_bytes(b.c2);
+    int64_t m = w2_plain > w2_fold ? w2_plain : w2_fold;
+    if (w2_now > m) m = w2_now;
+    pl->w2 = align_up(m, 1024);
+  }
   pl->w3 = align_up(plane_wpack_bytes(b.c3), 1024);
   pl->flag_bytes = align_up(plane_block_flag_words(B) * (int64_t)sizeof(uint32_t), 1024);
   return NSC_OK;
@@ -2401,12 +2660,13 @@ int nsc_bottleneck_block_tc(const float* x, const float* params, float* y, int64
                             int32_t k_plain, int32_t k_dilated, int32_t dilation, int32_t is_last_flat, int32_t precision,
                             int32_t* fused_out, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace nsc;
-  const bool force_unfused = fused_out && *fused_out == -1;      // tests: the same three kernels, one launch each
+  const bool want_folded = fused_out && *fused_out == -2;        // tests: three launches with the narrow conv on folded images
+  const bool force_unfused = fused_out && (*fused_out == -1 || want_folded);      // tests: the same three kernels, one launch each
   if (fused_out) *fused_out = 0;
   if (B == 0) return NSC_OK;
   NSC_CHECK_ARG(x && params && y && workspace, "nsc_bottleneck_block_tc: null pointer");
   TcBlockPlan pl;
-  NSC_TRY(make_tc_block_plan(B, L, wide, narrow, k_plain, k_dilated, dilation, is_last_flat, precision, &pl));
+  NSC_TRY(make_tc_block_plan(B, L, wide, narrow, k_plain, k_dilated, dilation, is_last_flat, precision, &pl, want_folded));
   const int64_t need = 2048 + pl.x_bytes + pl.y_bytes + 2 * pl.n_bytes + pl.w1 + pl.w2 + pl.w3 + pl.flag_bytes;
   if (workspace_bytes < need) {
     set_error("nsc_bottleneck_block_tc: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);

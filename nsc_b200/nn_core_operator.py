@@ -155,12 +155,13 @@ def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rat
         if ws_bytes > 0 and k_plain == 9 and k_dilated == 9 and dilation_rate in (1, 2):
             import ctypes as C
             ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
-            fused = C.c_int32(0 if fused else -1)
+            want_folded = fused == 'folded'       # three launches with the 20 -> 20 conv on folded images (the codec program's form)
+            fused = C.c_int32(-2 if want_folded else (0 if fused else -1))
             rc = lib.nsc_bottleneck_block_tc(_lib.ptr(x), _lib.ptr(flat), _lib.ptr(y), B, L, wide_layer, narrow_layer, k_plain, k_dilated,
                                              dilation_rate, int(bool(is_last_flat)), prec, C.byref(fused), _lib.ptr(ws), ws_bytes,
                                              _lib.stream_ptr())
             _lib.check(rc, 'the_bottleneck')
-            last_engine = 'tc_fused' if fused.value else 'tc'
+            last_engine = 'tc_fused' if fused.value else ('tc_folded' if want_folded else 'tc')
             return y
     if prec is not None and gated and B > 0 and cin == wide_layer and k_plain == 9 and dilation_rate in (1, 2):
         # the gated block of the codec path: k1 conv, fused gate pair (product in the epilogue), k9 conv + residual on tcgen05

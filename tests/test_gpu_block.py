@@ -121,11 +121,46 @@ def test_codec_program_with_fused_blocks_is_bit_identical():
             "np.savez(sys.argv[1], idx=r['idx'].cpu().numpy(), out=r['out'].cpu().numpy(), launches=_lib.load().nsc_launch_count() - l0)\n")
     res = {}
     with tempfile.TemporaryDirectory() as td:
-        for mode in ('0', '1'):
+        # '0' / '1': one launch per conv / fused blocks, both with the block's 20 -> 20 conv on the taps-in-N kernel (the fused kernel's
+        # form); 'default': the program as shipped, whose 20 -> 20 conv runs on folded images (plane.cuh) -- same arithmetic class,
+        # another summation order
+        for mode, env_extra in (('0', dict(NSC_BLOCK_FUSED='0', NSC_PLANE_FOLD2='0')), ('1', dict(NSC_BLOCK_FUSED='1')), ('default', {})):
             path = os.path.join(td, f'o{mode}.npz')
-            env = dict(os.environ, NSC_BLOCK_FUSED=mode)
+            env = dict(os.environ, **env_extra)
             subprocess.run([sys.executable, '-c', code, path], check=True, env=env, timeout=300)
             res[mode] = dict(np.load(path))
     assert np.array_equal(res['0']['idx'], res['1']['idx'])
     assert np.array_equal(res['0']['out'], res['1']['out'])
     assert int(res['1']['launches']) == int(res['0']['launches']) - 2 * 7      # 7 blocks: three launches -> one
+    assert int(res['default']['launches']) == int(res['0']['launches']) + 8      # unprepared call: one weight-folding launch per folded conv
+    same = (res['default']['idx'] == res['0']['idx'])
+    assert same.mean() > 0.9995                                   # a code may sit on a decision boundary; none should otherwise move
+    frames = same.reshape(same.shape[0], -1).all(axis=1)
+    assert frames.sum() >= 0.95 * frames.size
+    assert rel_err(res['default']['out'][frames], res['0']['out'][frames]) < 1e-4
+
+
+@pytest.mark.parametrize('L,wide,dil', [(512, 100, 1), (512, 100, 2), (256, 100, 1), (256, 100, 2), (512, 50, 1), (512, 50, 2)])
+def test_block_with_the_folded_narrow_conv_vs_oracle(L, wide, dil):
+    """The codec program runs a block's k9 20 -> 20 conv as a 48 -> 48 k5 conv on FOLDED images (pairs of positions in the channel
+    axis; dilation 2: per position parity, or -- 256 positions -- as a block-diagonal k9 conv on the same image), written by the first
+    conv's epilogue and unfolded by its own (plane.cuh).  Through the
+    operator surface (fused='folded'): against the oracle's the_bottleneck on frames spread over the batch -- borders of every frame
+    included in the max -- and against the taps-in-N form of the same block.  2 / 302: CTA pairs; 5 / 301: single CTAs, ragged;
+    1184: several frames per CTA (ring and accumulator slots wrap)."""
+    from nsc_b200 import nn_core_operator as nn
+    for B in (2, 5, 301, 302, 1184):
+        ps = ref_nn.ParamStream(seed=wide + dil + B)
+        x = np.random.RandomState(B).randn(B, L, wide).astype(np.float32)
+        sel = sorted(set([0, 1, B // 2, B - 1]))
+        ref = ref_nn.the_bottleneck(torch.from_numpy(x[sel]), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, ps=ps).numpy()
+        params = [tuple(cu(p) for p in t) for t in ps.params]
+        got = nn.the_bottleneck(cu(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, params=params, fused='folded')
+        assert nn.last_engine == 'tc_folded'
+        plain = nn.the_bottleneck(cu(x), wide_layer=wide, narrow_layer=20, dilation_rate=dil, is_last_flat=False, params=params, fused=False)
+        torch.cuda.synchronize()
+        g = got.cpu().numpy()
+        assert np.isfinite(g).all()
+        per = np.abs(g[sel] - ref).reshape(len(sel), -1).max(1) / np.abs(ref).reshape(len(sel), -1).max(1)
+        assert per.max() < 5e-5, (B, per)
+        assert rel_err(g, plain.cpu().numpy()) < 2e-5, B
