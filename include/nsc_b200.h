@@ -82,6 +82,10 @@ int64_t nsc_conv1d_tc_workspace_bytes(int64_t B, int32_t Lin, int32_t Cin, int32
  *   TMEM columns, grid size, work units (tiles, or frames for taps-in-N).  Returns NSC_OK or NSC_E_INVALID. */
 int nsc_conv1d_tc_plan_info(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride,
                             int32_t res_mode, int32_t shuffle, int32_t precision, int64_t* out12);
+/* Launch plan of the second conv of a bottleneck block (k9 20 -> 20, nn_core_operator.py:64-68) as the codec program runs it at L
+ * positions: on FOLDED images (pairs of positions in the channel axis: a 48 -> 48 k5 conv, or block-diagonal k9 for dilation 2 at 256
+ * positions) where the frame has 128 folded rows, else the taps-in-N kernel.  out12 as above; out12[1] = 5 / 6 for the two folded forms. */
+int nsc_narrow_conv_plan_info(int64_t B, int32_t L, int32_t dilation, int64_t* out12);
 int nsc_conv1d_tc(const float* x, const float* w, const float* b, const float* res, float* y, int64_t B, int32_t Lin,
                   int32_t Cin, int32_t Cout, int32_t k, int32_t dilation, int32_t stride, int32_t activation,
                   int32_t res_mode, int32_t post_activation, int32_t shuffle, int32_t precision, void* workspace,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "nsc_conv1d": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nsc_conv1d_tc_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "nsc_conv1d_tc_plan_info": (_i32, [_i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_int64)]),
+    "nsc_narrow_conv_plan_info": (_i32, [_i64, _i32, _i32, C.POINTER(C.c_int64)]),
     "nsc_conv1d_tc": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "nsc_conv1d_depth": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "nsc_block_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),

@@ -2176,7 +2176,8 @@ bool plane_plan_info(const PlaneConv& c, int64_t* o) {
   }
   XParams p;
   if (!plan_x(c, &p)) return false;
-  int64_t grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  const int64_t n_work = p.pairtiles ? p.n_tiles / 2 : p.n_tiles;
+  int64_t grid = n_work < sm_count() ? n_work : sm_count();
   if (p.pair) grid &= ~(int64_t)1;
   o[1] = p.staged; o[2] = p.pair; o[3] = p.mt; o[4] = p.n_iss; o[5] = p.resident; o[6] = p.wslots; o[7] = (int64_t)p.n_stage * p.kbuf;
   o[8] = (int64_t)x_smem_bytes(p); o[9] = p.tmem_cols; o[10] = grid; o[11] = p.n_tiles;
@@ -2544,6 +2545,26 @@ int nsc_conv1d_tc_plan_info(int64_t B, int32_t Lin, int32_t Cin, int32_t Cout, i
   TcConvPlan pl;
   NSC_TRY(make_tc_conv_plan(B < 1 ? 1 : B, Lin, Cin, Cout, k, dilation, stride, 0, res_mode, 0, shuffle, precision, &pl));
   NSC_CHECK_ARG(nsc::plane_plan_info(pl.c, out12), "nsc_conv1d_tc_plan_info: layer not planned");
+  return NSC_OK;
+}
+
+// launch plan of the block's 20 -> 20 conv as the codec program runs it at L positions (folded where the frame is long enough,
+// else the taps-in-N kernel); out12 as nsc_conv1d_tc_plan_info, out12[1] = 4 + form for the folded forms (5: k5, 6: block-diagonal k9)
+int nsc_narrow_conv_plan_info(int64_t B, int32_t L, int32_t dilation, int64_t* out12) {
+  using namespace nsc;
+  NSC_CHECK_ARG(out12 != nullptr && L > 0 && L % 128 == 0 && (dilation == 1 || dilation == 2), "nsc_narrow_conv_plan_info: bad arguments");
+  if (B < 1) B = 1;
+  const bool by_parity = dilation == 2 && L / 4 >= 128;
+  if (L / 2 < 128) return nsc_conv1d_tc_plan_info(B, L, 20, 20, 9, dilation, 1, 0, 1, 1, out12);
+  const bool diag = dilation == 2 && !by_parity;
+  PlaneConv c;
+  c.kind = PK_X; c.Lin = by_parity ? L / 4 : L / 2; c.Cin = kFoldC; c.Cout = kFoldC; c.K = diag ? 9 : kFoldK; c.dil = 1; c.stride = 1;
+  c.act = NSC_ACT_LRELU; c.planes = 2; c.B = by_parity ? 2 * B : B; c.fold2 = diag ? 2 : 1;
+  c.in = make_plane_tensor(nullptr, c.Lin, kFoldC, 2, 0);
+  c.out = make_plane_tensor(nullptr, L, 20, 2, 0);
+  if (by_parity) { c.ileave = 1; c.bmul = 2; }
+  NSC_CHECK_ARG(plane_plan_info(c, out12), "nsc_narrow_conv_plan_info: layer not planned");
+  out12[1] = 4 + c.fold2;
   return NSC_OK;
 }
 

@@ -126,3 +126,27 @@ def test_framing_and_packing_sizes():
     assert lib.nsc_lpc_window_count(99) == 97 and lib.nsc_lpc_window_count(2) == 0
     assert lib.nsc_packed_row_bytes(256, 5) == 160 and lib.nsc_packed_row_bytes(16, 8) == 16 and lib.nsc_packed_row_bytes(7, 3) == 3
     assert lib.nsc_iir_workspace_bytes(1000, 2) >= 2 * 1000 * 8
+
+
+def test_narrow_conv_plan_follows_the_frame_length():
+    """The block's k9 20 -> 20 conv as the codec program plans it (host logic): folded images (pairs of positions in the channel axis,
+    three MMA-issuing threads with one accumulator each = 3 x 2 x 48 TMEM columns -> 512, resident weights, a staging window for the
+    unfolding epilogue inside the shared-memory budget) from 256 positions up -- dilation 2 per position parity at 512 positions
+    (twice the frames, paired tiles), block-diagonal k9 at 256 -- and the taps-in-N kernel on shorter frames."""
+    import ctypes as C
+    lib = _lib.load()
+    keys = ('kind', 'staged', 'pair', 'mt', 'n_iss', 'resident', 'wslots', 'stages', 'smem', 'tmem_cols', 'grid', 'units')
+
+    def plan(B, L, d):
+        out = (C.c_int64 * 12)()
+        assert lib.nsc_narrow_conv_plan_info(B, L, d, out) == 0, _lib.last_error()
+        return dict(zip(keys, list(out)))
+    for L, d, form, wslots, units in ((512, 1, 5, 10, 2 * 2072), (256, 1, 5, 10, 2072), (512, 2, 5, 10, 2 * 2072), (256, 2, 6, 18, 2072)):
+        p = plan(2072, L, d)
+        assert (p['kind'], p['staged'], p['pair'], p['mt'], p['n_iss'], p['resident'], p['wslots']) == (1, form, 0, 1, 3, 1, wslots), (L, d, p)
+        assert p['tmem_cols'] == 512 and p['smem'] <= 227 * 1024 and p['stages'] >= 4 and p['units'] == units
+        assert p['grid'] == 148
+    assert plan(2072, 512, 2)['grid'] == 148 and plan(7, 512, 2)['grid'] == 7      # dilation 2 by parity: a CTA's unit of work is a frame
+    short = plan(2072, 128, 1)
+    assert short['kind'] == 0 and short['staged'] == 3                          # taps-in-N, three tap groups
+    assert lib.nsc_narrow_conv_plan_info(1, 100, 1, (C.c_int64 * 12)()) != 0
