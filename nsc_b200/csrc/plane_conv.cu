@@ -548,6 +548,7 @@ __device__ __forceinline__ void t_body(const TParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();      // barriers, TMEM and the bias table are set up under the previous kernel's tail; its output is only touched from here
 
   if (warp < kEpi) {
     // =========================== epilogue ===========================
@@ -935,6 +936,7 @@ __device__ __forceinline__ void t_body(const TParams& p) {
 
 template <int C, int TAPS, int GROUPS>
 __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
+  pdl_trigger();
   t_body<C, TAPS, GROUPS>(p);
 }
 
@@ -1281,6 +1283,7 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
 template <bool kGen, bool kPair>
 __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_kernel(const __grid_constant__ XParams p) {
   static_assert(!(kGen && kPair), "Toeplitz layers do not run as CTA pairs");
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_full[kXMaxStage], a_empty[kXMaxStage], w_full[kXMaxW], w_empty[kXMaxW], acc_full[2], acc_empty[2];
@@ -1318,6 +1321,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   if constexpr (pair) cluster_sync_all();   // the peer's barriers (and TMEM) exist before anything arrives remotely
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();      // barriers, TMEM and the bias table are set up under the previous kernel's tail; its output is only touched from here
 
   if (warp < kXEpiWarps) {
     // =========================== epilogue ===========================
@@ -1678,6 +1682,7 @@ __device__ __forceinline__ void xs_body(const XParams& p) {
   if constexpr (pair) cluster_sync_all();   // the peer's barriers (and TMEM) exist before anything arrives remotely
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  pdl_wait();      // barriers, TMEM and the bias table are set up under the previous kernel's tail; its output is only touched from here
 
   if (warp < kSEpiWarps) {
     // =========================== epilogue ===========================
@@ -1901,6 +1906,7 @@ __device__ __forceinline__ void xs_body(const XParams& p) {
 
 template <bool kPair>
 __global__ void __launch_bounds__(kSThreads, 1) plane_xs_kernel(const __grid_constant__ XParams p) {
+  pdl_trigger();
   xs_body<kPair, kSEpiGroups>(p);
 }
 
@@ -2226,6 +2232,35 @@ int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
   return NSC_OK;
 }
 
+// Every conv kernel of the plane engine is launched with programmatic stream serialization (NSC_PLANE_PDL=0: plain launches): its
+// prologue runs under the tail of the kernel before it, the rest after pdl_wait().
+template <typename P>
+static cudaError_t launch_plane(void (*kernel)(P), int64_t grid, int threads, size_t smem, cudaStream_t st, int cluster, const P& p) {
+  static const bool pdl = [] { const char* e = getenv("NSC_PLANE_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 int plane_launch(const PlaneConv& c, cudaStream_t st) {
   if (c.B == 0) return NSC_OK;
   if (c.kind == PK_DW) {
@@ -2258,16 +2293,16 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     ProfScope prof(st, name, 2.0 * macs, bytes);
     if (c.Cout == 20 && pl.groups == 5) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 3, 5><<<(unsigned)grid, TShape<20, 3>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(launch_plane(plane_t_kernel<20, 3, 5>, grid, TShape<20, 3>::kThreads, pl.smem, st, 1, p));
     } else if (c.Cout == 20 && pl.groups == 3) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 5, 3><<<(unsigned)grid, TShape<20, 5>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(launch_plane(plane_t_kernel<20, 5, 3>, grid, TShape<20, 5>::kThreads, pl.smem, st, 1, p));
     } else if (c.Cout == 20) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<20, 9, 1><<<(unsigned)grid, TShape<20, 9>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(launch_plane(plane_t_kernel<20, 9, 1>, grid, TShape<20, 9>::kThreads, pl.smem, st, 1, p));
     } else {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<1, 55, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      plane_t_kernel<1, 55, 1><<<(unsigned)grid, TShape<1, 55>::kThreads, pl.smem, st>>>(p);
+      NSC_CUDA_OK(launch_plane(plane_t_kernel<1, 55, 1>, grid, TShape<1, 55>::kThreads, pl.smem, st, 1, p));
     }
     NSC_LAUNCH_OK();
     return NSC_OK;
@@ -2309,25 +2344,11 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   ProfScope prof(st, name, flops, bytes);
   int64_t grid = n_work < sm_count() ? n_work : sm_count();
   if (p.pair) grid &= ~(int64_t)1;
-  auto launch_pairs = [&]() {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(p.staged ? kSThreads : kXThreadsX);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return p.staged ? cudaLaunchKernelEx(&cfg, plane_xs_kernel<true>, p) : cudaLaunchKernelEx(&cfg, plane_x_kernel<false, true>, p);
-  };
-  if (p.pair) NSC_CUDA_OK(launch_pairs());
-  else if (p.staged) plane_xs_kernel<false><<<(unsigned)grid, kSThreads, smem, st>>>(p);
-  else if (c.kind == PK_GEN) plane_x_kernel<true, false><<<(unsigned)grid, kXThreadsGen, smem, st>>>(p);
-  else plane_x_kernel<false, false><<<(unsigned)grid, kXThreadsX, smem, st>>>(p);
+  if (p.pair && p.staged) NSC_CUDA_OK(launch_plane(plane_xs_kernel<true>, grid, kSThreads, smem, st, 2, p));
+  else if (p.pair) NSC_CUDA_OK(launch_plane(plane_x_kernel<false, true>, grid, kXThreadsX, smem, st, 2, p));
+  else if (p.staged) NSC_CUDA_OK(launch_plane(plane_xs_kernel<false>, grid, kSThreads, smem, st, 1, p));
+  else if (c.kind == PK_GEN) NSC_CUDA_OK(launch_plane(plane_x_kernel<true, false>, grid, kXThreadsGen, smem, st, 1, p));
+  else NSC_CUDA_OK(launch_plane(plane_x_kernel<false, false>, grid, kXThreadsX, smem, st, 1, p));
   NSC_LAUNCH_OK();
   return NSC_OK;
 }
