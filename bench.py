@@ -245,6 +245,12 @@ def run_ours(args):
         lsf = lu.lpc_analysis_windows(win_dev, 16, dtype=torch.float32)
         return cm.feedforward_lpc(x_dev, lsf, False, 1.0)
 
+    # once per WEIGHTS, outside the timed region, like the reference's variable initialisation: packed operand slabs of every layer
+    # and the zero rows of the activation images (nsc_prepare).  Every call with a batch of at least one engine pass then skips the
+    # 3.6 GB border memset and the ~75 packing launches -- 1.7 ms per call, which the end-to-end path paid eight times per step.
+    # The same step without it is reported as `unprepared`.
+    cm.prepare(B)
+
     out_host = {}
     # End-to-end step through the public API with HOST buffers: the batch goes through in sub-batches so that the pinned-memory
     # H2D copy of sub-batch k+1 and the D2H copy of sub-batch k-1 (copy stream) run under the compute of sub-batch k.
@@ -334,6 +340,10 @@ def run_ours(args):
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
     t_e2e = timed(step_e2e, args.steps)
+    cm.release()                                    # the same device-resident step when every call packs the weights and clears the borders
+    step_device()
+    t_cold = timed(step_device, 2)
+    cm.prepare(B)
 
     # ---- per-kernel breakdown of ONE step with CUDA events on the launching stream (roofline line)
     roof = None
@@ -392,7 +402,11 @@ def run_ours(args):
                        "frames_per_gpu_per_step": B, "frames_per_step": frames_total, "conv_precision": args.precision,
                        "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB of frames+windows per GPU per step, plus a "
                                     "multi-GB activation workspace cycled per ~2k-frame chunk (L2 is 126 MB); no explicit flush",
-                       "parallelism": f"dp{world} (frames sharded by rank, no collective)"},
+                       "parallelism": f"dp{world} (frames sharded by rank, no collective)",
+                       "weights": "prepared once per weights (nsc_prepare: packed fp16 hi/lo operand slabs + zero rows of the activation "
+                                  "images), outside the timed region, as the reference keeps its variables resident"},
+            "unprepared": {"ms_per_step": t_cold / 2 * 1e3, "value": frames_total * 2 * SEC_PER_FRAME / t_cold,
+                           "note": "the same device-resident step when every call packs the weights and clears the image borders"},
             "frames_per_s": frames_total * args.steps / t_dev,
             "e2e": {"value": e2e_v, "unit": "x real-time", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": t_e2e / args.steps * 1e3},
@@ -459,6 +473,7 @@ def measure_corpus(args, world, rank, dev, lib, steps, warmup, n_utt=None):
     cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
     n_utt = n_utt or args.utterances
     T = int(args.utt_seconds * 16000)
+    cm.prepare(max(2072, n_utt))                    # once per weights (nsc_prepare): any call of at least one engine pass uses it
     x_np, _ = synth_audio(64, seed=4321 + rank)
     base = np.tile(x_np.reshape(-1), -(-T * 8 // x_np.size))        # a few distinct utterances, tiled
     host = [torch.from_numpy(np.ascontiguousarray(base[(i % 8) * 4000:(i % 8) * 4000 + T])).pin_memory() for i in range(n_utt)]
@@ -656,6 +671,7 @@ def measure_variant(args, world, rank, dev, lib, resnet_type, strides, frames=41
     def step():
         cm.feedforward_lpc(xd, lu.lpc_analysis_windows(wd, 16, dtype=torch.float32), False, 1.0)
 
+    cm.prepare(B)                                   # once per weights (nsc_prepare), as in the headline
     for _ in range(3):
         step()
     n = 5
@@ -665,7 +681,7 @@ def measure_variant(args, world, rank, dev, lib, resnet_type, strides, frames=41
     ms = sum(v[0] for v in agg.values())
     hbm, bf16, bf16_sus, how = peaks()
     return {"workload": f"cq2 with resnet_type '{resnet_type}', strides {list(strides)}: LPC + LSF codebook + 2 codecs + synthesis, hard codes, "
-                        f"{B} frames per GPU", "value": B * world * n * SEC_PER_FRAME / t, "unit": "x real-time", "ms_per_call": t / n * 1e3,
+                        f"{B} frames per GPU; weights prepared once (nsc_prepare)", "value": B * world * n * SEC_PER_FRAME / t, "unit": "x real-time", "ms_per_call": t / n * 1e3,
             "engine": ("plane engine (tcgen05, fp16 hi/lo plane images between layers)" if lib.nsc_codec_on_plane_engine(C.byref(cfg.to_struct())) == 1
                        else "layer-by-layer (first tensor engine tcgen05 fp16 hi/lo + CUDA-core stem/heads/depthwise)"),
             "tflops_algorithmic": fl / (ms * 1e-3) / 1e12, "tensor_frac_of_measured_bf16_sustained": fl / (ms * 1e-3) / 1e12 / bf16_sus,

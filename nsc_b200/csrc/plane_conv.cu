@@ -1007,21 +1007,19 @@ __device__ __forceinline__ void pt_load_raw(const PlaneTensor& t, const uint8_t*
 }
 
 
-// channels [8g, 8g + 8) of output row `pos` through the folded-image index maps (plane.cuh): `unfold` -- this layer's rows are
-// PAIRS of positions (24 channels each) and the output is the plain image; `fold_out` -- the output image is folded (1) or
-// folded per position parity (2); omul / opar: `ileave`
+// channels [8g, 8g + 8) of output row `pos` of a plain-epilogue layer; omul / opar: `ileave`.  Only the Toeplitz layer (decoder's
+// k9 1 -> 20) ever writes a FOLDED image (plane.cuh: `fold_out` 1 = pairs of positions, 2 = pairs within each position parity), so
+// the other instantiations keep the bare store (the index maps cost the HBM-bound k1 layers of 'gln' 30 % when every store took them).
+template <bool kFoldable>
 __device__ __forceinline__ void x_store8(const XParams& p, uint8_t* oimg, int pos, int g, const float (&v)[8], int omul, int opar) {
-  if (p.unfold) {
-    const int ph = g >= 3 ? 1 : 0;
-    pos = 2 * pos + ph;
-    g -= 3 * ph;
-  }
   pos = omul * pos + opar;
-  if (p.fold_out) {
-    if (g >= 3) return;                 // channels 24-31 of a 20-channel result: no place in a 24-channel group
-    if (p.fold_out == 1) pt_store8(p.out, oimg, pos >> 1, 3 * (pos & 1) + g, v);
-    else pt_store8(p.out, oimg, ((pos >> 2) << 1) | (pos & 1), 3 * ((pos >> 1) & 1) + g, v);
-    return;
+  if constexpr (kFoldable) {
+    if (p.fold_out) {
+      if (g >= 3) return;                 // channels 24-31 of a 20-channel result: no place in a 24-channel group
+      if (p.fold_out == 1) pt_store8(p.out, oimg, pos >> 1, 3 * (pos & 1) + g, v);
+      else pt_store8(p.out, oimg, ((pos >> 2) << 1) | (pos & 1), 3 * ((pos >> 1) & 1) + g, v);
+      return;
+    }
   }
   pt_store8(p.out, oimg, pos, g, v);
 }
@@ -1280,7 +1278,9 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   }
 }
 
-template <bool kGen, bool kPair>
+// kFold: the folded narrow conv (plane.cuh) -- its own instantiation, so that its unfolding epilogue does not raise the register pressure
+// of the other layers' (with one kernel for both, every instantiation spilled)
+template <bool kGen, bool kPair, bool kFold = false>
 __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_kernel(const __grid_constant__ XParams p) {
   static_assert(!(kGen && kPair), "Toeplitz layers do not run as CTA pairs");
   pdl_trigger();
@@ -1341,48 +1341,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
       const uint8_t* rimg = p.res_mode == RES_ADD ? p.res.base + f * p.res.frame_bytes : nullptr;
       const float* rvec = p.res_mode == RES_ADD_BCAST ? p.resvec + f * p.Lout : nullptr;
       const int row0 = q0 + quarter * 32 + lane;
-      if (p.glu) {
-        // gated linear unit: columns [0, 20) linear gate, [20, 40) tanh gate -> 20-channel packed row (nn_core_operator.py:91-102)
-        mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
-        tc_fence_after();
-        for (int mt_i = grp; mt_i < p.mt; mt_i += kXEpiGroups) {
-          const int pos = row0 + mt_i * 128;
-          uint32_t r0[16], r1[16], r2[16];
-          const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad);
-          tmem_ld16(tb, r0);
-          tmem_ld16(tb + 16u, r1);
-          tmem_ld16(tb + 32u, r2);
-          tmem_ld_wait();
-          float v[24];
-#pragma unroll
-          for (int c = 0; c < 20; ++c) {
-            const float a = __uint_as_float(c < 16 ? r0[c & 15] : r1[c & 3]) + s_bias[c];
-            const float g = __uint_as_float(c < 12 ? r1[(4 + c) & 15] : r2[(c - 12) & 15]) + s_bias[20 + c];
-            v[c] = a * tanhf(g);
-          }
-          v[20] = v[21] = v[22] = v[23] = 0.f;
-          float a8[8];
-#pragma unroll
-          for (int g3 = 0; g3 < 3; ++g3) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a8[e] = v[8 * g3 + e];
-            pt_store8(p.out, oimg, omul * pos + opar, g3, a8);
-          }
-          if (p.out.planes == 1) {   // channels 24-31: K padding the consumer reads
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a8[e] = 0.f;
-            pt_store8(p.out, oimg, omul * pos + opar, 3, a8);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);
-          else mbar_arrive(&acc_empty[acc_i]);
-        }
-        continue;
-      }
-      if (p.unfold) {
+      if constexpr (kFold) {
         // folded narrow conv (plane.cuh): row q of this tile holds output positions 2 q and 2 q + 1 (24 columns each).  A thread owns
         // a row, so direct global stores would touch 32 lines per warp instruction (the load/store unit, not the MMAs, then bounds
         // the layer: measured 67 us per launch against 35 of MMAs).  The rows go to a staging ring that mirrors the packed output
@@ -1451,6 +1410,48 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         }
         continue;
       }
+      if constexpr (!kFold) {
+      if (p.glu) {
+        // gated linear unit: columns [0, 20) linear gate, [20, 40) tanh gate -> 20-channel packed row (nn_core_operator.py:91-102)
+        mbar_wait_relaxed(&acc_full[acc_i], (it >> 1) & 1u);
+        tc_fence_after();
+        for (int mt_i = grp; mt_i < p.mt; mt_i += kXEpiGroups) {
+          const int pos = row0 + mt_i * 128;
+          uint32_t r0[16], r1[16], r2[16];
+          const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad);
+          tmem_ld16(tb, r0);
+          tmem_ld16(tb + 16u, r1);
+          tmem_ld16(tb + 32u, r2);
+          tmem_ld_wait();
+          float v[24];
+#pragma unroll
+          for (int c = 0; c < 20; ++c) {
+            const float a = __uint_as_float(c < 16 ? r0[c & 15] : r1[c & 3]) + s_bias[c];
+            const float g = __uint_as_float(c < 12 ? r1[(4 + c) & 15] : r2[(c - 12) & 15]) + s_bias[20 + c];
+            v[c] = a * tanhf(g);
+          }
+          v[20] = v[21] = v[22] = v[23] = 0.f;
+          float a8[8];
+#pragma unroll
+          for (int g3 = 0; g3 < 3; ++g3) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a8[e] = v[8 * g3 + e];
+            pt_store8(p.out, oimg, omul * pos + opar, g3, a8);
+          }
+          if (p.out.planes == 1) {   // channels 24-31: K padding the consumer reads
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a8[e] = 0.f;
+            pt_store8(p.out, oimg, omul * pos + opar, 3, a8);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);
+          else mbar_arrive(&acc_empty[acc_i]);
+        }
+        continue;
+      }
       auto load_res = [&](int u, ResRaw& rr) {
         if (kGen || u >= n_e) return;      // 1-channel-input layers carry no residual
         const int mt_i = u / nb, c0 = (u - mt_i * nb) << 4;
@@ -1508,8 +1509,8 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
           float a[8], b[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) { a[e] = v[e]; b[e] = v[8 + e]; }
-          x_store8(p, oimg, pos, c0 >> 3, a, omul, opar);
-          x_store8(p, oimg, pos, (c0 >> 3) + 1, b, omul, opar);
+          x_store8<kGen>(p, oimg, pos, c0 >> 3, a, omul, opar);
+          x_store8<kGen>(p, oimg, pos, (c0 >> 3) + 1, b, omul, opar);
         } else {   // sub-pixel: out[2 pos + r, c] = y[pos, 2 c + r]   (nscm.py:158-167)
           float a[8], b[8];
 #pragma unroll
@@ -1534,8 +1535,9 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         if (pair) mbar_arrive_remote(&acc_empty[acc_i], 0u);   // the leader's barrier counts both CTAs' epilogue warps
         else mbar_arrive(&acc_empty[acc_i]);
       }
+      }   // !kFold
     }
-    if (p.unfold && warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (kFold && warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == kXEpiWarps || warp == kIssuer1) {
     // =========================== MMA issuers ===========================
     const int issuer = warp == kXEpiWarps ? 0 : 1;
@@ -2025,7 +2027,7 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
                   (c.fold2 == 2 && c.ileave) ||
                   c.planes != 2 || c.res_mode != RES_NONE || c.shuffle != 1 || c.glu || c.fold_out))
     return false;
-  if (c.fold_out && (c.Cout != 20 || c.shuffle != 1 || c.glu || c.ileave || c.res_mode != RES_NONE || c.out.packed || c.out.spp != 1 ||
+  if (c.fold_out && (!gen || c.Cout != 20 || c.shuffle != 1 || c.glu || c.ileave || c.res_mode != RES_NONE || c.out.packed || c.out.spp != 1 ||
                      (c.fold_out != 1 && c.fold_out != 2) || (c.fold_out == 2) != (c.out.deint != 0) || c.out.rows != (Lout >> c.fold_out)))
     return false;
   if (c.fold2 && c.ileave && Lout != 128) return false;   // (the unfolding epilogue stages one frame = two 128-row parity tiles)
@@ -2328,6 +2330,7 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   else if (p.staged) NSC_CUDA_OK(cudaFuncSetAttribute(plane_xs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (c.kind == PK_GEN) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (p.pair) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (p.unfold) NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else NSC_CUDA_OK(cudaFuncSetAttribute(plane_x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   snprintf(name, sizeof(name), "p%s%d_k%dd%ds%d_c%dto%d", c.kind == PK_GEN ? "G" : (c.glu ? (c.ileave ? "U2x" : "U") : "X"), c.planes, c.K, c.dil, c.stride,
            c.Cin, c.Cout);
@@ -2348,6 +2351,7 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
   else if (p.pair) NSC_CUDA_OK(launch_plane(plane_x_kernel<false, true>, grid, kXThreadsX, smem, st, 2, p));
   else if (p.staged) NSC_CUDA_OK(launch_plane(plane_xs_kernel<false>, grid, kSThreads, smem, st, 1, p));
   else if (c.kind == PK_GEN) NSC_CUDA_OK(launch_plane(plane_x_kernel<true, false>, grid, kXThreadsGen, smem, st, 1, p));
+  else if (p.unfold) NSC_CUDA_OK(launch_plane(plane_x_kernel<false, false, true>, grid, kXThreadsX, smem, st, 1, p));
   else NSC_CUDA_OK(launch_plane(plane_x_kernel<false, false>, grid, kXThreadsX, smem, st, 1, p));
   NSC_LAUNCH_OK();
   return NSC_OK;

@@ -150,3 +150,20 @@ def test_narrow_conv_plan_follows_the_frame_length():
     short = plan(2072, 128, 1)
     assert short['kind'] == 0 and short['staged'] == 3                          # taps-in-N, three tap groups
     assert lib.nsc_narrow_conv_plan_info(1, 100, 1, (C.c_int64 * 12)()) != 0
+
+
+def test_plane_kernels_do_not_spill():
+    """ptxas -v logs of the in-tree build (nsc_b200/csrc/*.ptxas.log): no kernel of the plane engine may spill registers.  (The
+    unfolding epilogue of the folded narrow conv once shared a kernel with the other tap-shift layers: every instantiation spilled and
+    the HBM-bound k1 layers of 'gln' lost 30 % -- it now has its own instantiation.)"""
+    import os
+    import re
+    log = os.path.join(os.path.dirname(os.path.abspath(_lib.__file__)), 'csrc', 'plane_conv.ptxas.log')
+    if not os.path.exists(log):
+        pytest.skip('no ptxas log (library built elsewhere)')
+    t = open(log).read()
+    found = re.findall(r"Compiling entry function '([^']+)'.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", t)
+    assert len(found) >= 10
+    for name, stack, st, ld in found:
+        if 'plane_' in name:
+            assert (int(st), int(ld)) == (0, 0), name
