@@ -41,6 +41,8 @@
 // hi/lo split, sub-pixel shuffle, stride-2 de-interleave are all index arithmetic on the way out).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "plane.cuh"
 #include "tc_common.cuh"
 
@@ -1692,6 +1694,8 @@ __device__ __forceinline__ void xs_body(const XParams& p) {
     const int lr = quarter * 32 + lane;                  // row inside the M tile
     const float slope = act_slope_of(p.act), pslope = act_slope_of(p.post_act);
     const bool has_res = p.res_mode == RES_ADD;
+    // what the per-value arithmetic contains: bit 0 activation, bit 1 residual add, bit 2 post-activation (slope 1 = identity)
+    const int emode = (slope != 1.0f ? 1 : 0) | ((has_res || p.res_mode == RES_ADD_BCAST) ? 2 : 0) | (pslope != 1.0f ? 4 : 0);
     const bool barrier_rw = has_res && p.out.deint;      // residual and output use different unit layouts: read all, then write all
     // shared-memory offsets of this thread's two chunks inside a unit plane (layout of the OUTPUT image)
     const int srow_o = p.out.deint ? (lr >> 1) : lr;
@@ -1737,9 +1741,9 @@ __device__ __forceinline__ void xs_body(const XParams& p) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) { rs[e] += a[e]; rs[8 + e] += b[e]; }
                 }
-              } else {
+              } else if (rvec) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) rs[e] = (rvec && c0 + e < p.Cout) ? rv : 0.f;
+                for (int e = 0; e < 16; ++e) rs[e] = (c0 + e < p.Cout) ? rv : 0.f;
               }
               float bs[16];
 #pragma unroll
@@ -1748,8 +1752,31 @@ __device__ __forceinline__ void xs_body(const XParams& p) {
                 bs[e] = b4.x; bs[e + 1] = b4.y; bs[e + 2] = b4.z; bs[e + 3] = b4.w;
               }
               tmem_ld_wait();
+              // The epilogue is co-limited by instruction issue (ncu: ~60 % issue-slot utilisation next to 70 % of HBM), so the
+              // per-value arithmetic only contains what the layer has: an identity activation (slope 1) or a missing residual are
+              // not computed (the stem ran 7 instructions per value where 3 do).  The choice is uniform: one branch per batch.
+              auto finish = [&](auto kAct, auto kAdd, auto kPost) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[bi][e] = act_fast(act_fast(__uint_as_float(r[e]) + bs[e], slope) + rs[e], pslope);
+                for (int e = 0; e < 16; ++e) {
+                  float t = __uint_as_float(r[e]) + bs[e];
+                  if constexpr (decltype(kAct)::value) t = act_fast(t, slope);
+                  if constexpr (decltype(kAdd)::value) t += rs[e];
+                  if constexpr (decltype(kPost)::value) t = act_fast(t, pslope);
+                  v[bi][e] = t;
+                }
+              };
+              using T1 = std::true_type;
+              using T0 = std::false_type;
+              switch (emode) {
+                case 0: finish(T0{}, T0{}, T0{}); break;
+                case 1: finish(T1{}, T0{}, T0{}); break;
+                case 2: finish(T0{}, T1{}, T0{}); break;
+                case 3: finish(T1{}, T1{}, T0{}); break;
+                case 4: finish(T0{}, T0{}, T1{}); break;
+                case 5: finish(T1{}, T0{}, T1{}); break;
+                case 6: finish(T0{}, T1{}, T1{}); break;
+                default: finish(T1{}, T1{}, T1{}); break;
+              }
             }
           }
           if (barrier_rw) asm volatile("bar.sync 3, %0;" :: "n"(kSEpiWarps * 32) : "memory");
