@@ -347,6 +347,15 @@ __device__ __forceinline__ void issue_n(int nks, uint32_t d, uint32_t a_lo, uint
   }
 }
 
+__device__ __forceinline__ void issue_n_cg2(int nks, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum0) {
+  switch (nks) {
+    case 4: issue_ks<4, 1>(d, a_lo, b_lo, idesc, accum0); break;
+    case 3: issue_ks<3, 1>(d, a_lo, b_lo, idesc, accum0); break;
+    case 2: issue_ks<2, 1>(d, a_lo, b_lo, idesc, accum0); break;
+    default: issue_ks<1, 1>(d, a_lo, b_lo, idesc, accum0); break;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // frame flags of the fused block kernel: CTAs of different roles hand frames to each other through global-memory rings.
 // A producer's bulk stores are complete (cp.async.bulk.wait_group) before it publishes; a consumer orders its bulk loads after
@@ -504,7 +513,12 @@ __device__ __forceinline__ void t_phase1_k55(uint32_t tcol, int lane, float& acc
   acc = a; up = u; down = d;
 }
 
-template <int C, int TAPS, int GROUPS>
+// kPair (wide-input C = 20 layers, an even number of frames): two CTAs of a cluster run as a PAIR (cta_group::2).  Each walks its own
+// frames in lockstep with the other and keeps its own tiles, epilogue and TMEM half, but only HALF of every weight slab (output
+// columns [rank N/2, (rank + 1) N/2)); the leader's issuing thread multiplies both CTAs' tiles with one M = 256 instruction, the
+// peer's forwards "my slab has landed".  What it buys: 49 KB of shared memory, i.e. eight input stages in flight instead of five
+// for the layer that is bound by exactly that (100 -> 20).
+template <int C, int TAPS, int GROUPS, bool kPair = false>
 __device__ __forceinline__ void t_body(const TParams& p) {
   using S = TShape<C, TAPS>;
   const int rank = (int)blockIdx.x - p.cta0, nranks = p.ncta;
@@ -515,6 +529,7 @@ __device__ __forceinline__ void t_body(const TParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t w_full, a_full[8], a_empty[8], acc_full[2], acc_empty[2];
+  __shared__ uint64_t w_full2, a_full2[8];           // pair: the peer's operands have landed (live in the leader)
   __shared__ uint64_t so_ready[2], so_free[2];      // ring mode: output windows handed to / returned by the storer warp (by tile parity)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_qbins[C == 1 ? 256 : 1];       // code head: the quantiser's bins
@@ -525,7 +540,8 @@ __device__ __forceinline__ void t_body(const TParams& p) {
       for (int k = tid; k < p.fold.q_n; k += blockDim.x) s_qbins[k] = __ldg(p.fold.q_bins + k);
   }
   const bool ring_out = (C != 1) && p.out_ready != nullptr;   // fused block: a dedicated warp stores and publishes (the CTA has spare warps)
-  const uint32_t wslab_bytes = (uint32_t)p.N * 128u;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t wslab_bytes = (uint32_t)p.N * (kPair ? 64u : 128u);      // bytes of one weight slab in THIS CTA
   uint8_t* sW = smem;
   uint8_t* sA = sW + (uint32_t)p.n_wslab * wslab_bytes;
   constexpr int kTSlots = S::kSlots;
@@ -540,14 +556,19 @@ __device__ __forceinline__ void t_body(const TParams& p) {
 
   if (tid == 0) {
     mbar_init(&w_full, 1);
-    for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpi); }
+    mbar_init(&w_full2, 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_full2[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPair ? 2 * kEpi : kEpi); }
     for (int i = 0; i < 2; ++i) { mbar_init(&so_ready[i], kEpi); mbar_init(&so_free[i], 1); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (warp == kEpi) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (warp == kEpi) {
+    if constexpr (kPair) tmem_alloc_cg2(&tmem_base_s, tmem_cols);
+    else tmem_alloc(&tmem_base_s, tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers (and TMEM) exist before anything arrives remotely
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   pdl_wait();      // barriers, TMEM and the bias table are set up under the previous kernel's tail; its output is only touched from here
@@ -694,7 +715,10 @@ __device__ __forceinline__ void t_body(const TParams& p) {
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc_i]);   // TMEM slot free: the next tile's MMAs run under phase 2
+        if (lane == 0) {                                 // TMEM slot free: the next tile's MMAs run under phase 2
+          if constexpr (kPair) mbar_arrive_remote(&acc_empty[acc_i], 0u);   // the leader's barrier counts both CTAs' epilogue warps
+          else mbar_arrive(&acc_empty[acc_i]);
+        }
         // ring mode: this tile's rows overwrite the staging window of two tiles ago -- the storer warp has seen it leave shared memory
         if (ring_out) mbar_wait_relaxed(&so_free[it & 1u], ((it >> 1) & 1u) ^ 1u);
 
@@ -796,10 +820,25 @@ __device__ __forceinline__ void t_body(const TParams& p) {
     }
   } else if (warp == kEpi) {
     // =========================== MMA issuer ===========================
-    if (elect_one()) {
+    if (kPair && crank != 0) {
+      // the peer of a pair issues nothing: it forwards "landed" of its own weights and input slabs to the leader's twin barriers
+      if (elect_one()) {
+        mbar_wait(&w_full, 0);
+        mbar_arrive_remote(&w_full2, 0u);
+        uint32_t slot = 0, sph = 0;
+        for (int64_t f = rank; f < p.B; f += nranks)
+          for (int j = 0; j < T; ++j)
+            for (int s = 0; s < nst; ++s) {
+              mbar_wait(&a_full[slot], sph);
+              mbar_arrive_remote(&a_full2[slot], 0u);
+              if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
+            }
+      }
+    } else if (elect_one()) {
       mbar_wait(&w_full, 0);
+      if constexpr (kPair) mbar_wait(&w_full2, 0);
       tc_fence_after();
-      const uint32_t idesc = make_idesc_f16(p.N);
+      const uint32_t idesc = make_idesc_f16(p.N, kPair ? 256 : 128);
       const uint32_t w_lo0 = desc_lo(smem_u32(sW));
       const uint32_t a_lo0 = desc_lo(smem_u32(sA));
       const uint32_t wslab_lo = wslab_bytes >> 4;
@@ -818,6 +857,7 @@ __device__ __forceinline__ void t_body(const TParams& p) {
           for (int s = 0; s < nst; ++s) {
             tw = p.stats != nullptr ? clock64() : 0;
             mbar_wait(&a_full[slot], sph);
+            if constexpr (kPair) mbar_wait(&a_full2[slot], sph);
             if (p.stats != nullptr) stat_add(p.stats, 6, clock64() - tw);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + slot * (uint32_t)(kAStage >> 4);
@@ -834,15 +874,22 @@ __device__ __forceinline__ void t_body(const TParams& p) {
             } else {
               const int plane = s >= spp ? 1 : 0, sl = s - plane * spp;
               const int nks = min(4, p.ksteps - 4 * sl);
+              if constexpr (kPair) {
+                issue_n_cg2(nks, d, a_lo, w_lo0 + (uint32_t)sl * wslab_lo, idesc, accum);
+                if (plane == 0 && planes == 2) issue_n_cg2(nks, d, a_lo, w_lo0 + (uint32_t)(spp + sl) * wslab_lo, idesc, 1u);
+              } else {
               issue_n(nks, d, a_lo, w_lo0 + (uint32_t)sl * wslab_lo, idesc, accum);                                   // (hi | lo) * W_hi
               if (plane == 0 && planes == 2) issue_n(nks, d, a_lo, w_lo0 + (uint32_t)(spp + sl) * wslab_lo, idesc, 1u);   // hi * W_lo
+              }
             }
             accum = 1;
-            umma_commit(&a_empty[slot]);
+            if constexpr (kPair) umma_commit_cg2(&a_empty[slot]);      // "slot free" in both CTAs
+            else umma_commit(&a_empty[slot]);
             if (++slot == (uint32_t)p.na) { slot = 0; sph ^= 1u; }
           }
           if (j == T - 1 && p.in_free != nullptr) flag_bump(p.in_free + f);   // every stage of the frame has been read out of the ring
-          umma_commit(&acc_full[acc_i]);
+          if constexpr (kPair) umma_commit_cg2(&acc_full[acc_i]);
+          else umma_commit(&acc_full[acc_i]);
         }
       }
     }
@@ -850,7 +897,9 @@ __device__ __forceinline__ void t_body(const TParams& p) {
     // =========================== loader ===========================   (the fused block kernel has more warps than this role uses)
     if (elect_one()) {
       mbar_expect_tx(&w_full, (uint32_t)p.n_wslab * wslab_bytes);
-      for (int i = 0; i < p.n_wslab; ++i) bulk_g2s(sW + (uint32_t)i * wslab_bytes, p.wpack + (size_t)i * wslab_bytes, wslab_bytes, &w_full);
+      // (pair: rows [rank N/2, (rank + 1) N/2) of every slab)
+      for (int i = 0; i < p.n_wslab; ++i)
+        bulk_g2s(sW + (uint32_t)i * wslab_bytes, p.wpack + (size_t)i * ((size_t)p.N * 128u) + (size_t)crank * wslab_bytes, wslab_bytes, &w_full);
       const int64_t sb = pt_slab_bytes(p.in);
       uint32_t slot = 0, sph = 1;
       for (int64_t f = rank; f < p.B; f += nranks) {
@@ -932,14 +981,18 @@ __device__ __forceinline__ void t_body(const TParams& p) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // nobody frees TMEM (or retires) while the leader's instruction stream can still touch it
   tc_fence_after();
-  if (warp == kEpi) tmem_dealloc(tmem, tmem_cols);
+  if (warp == kEpi) {
+    if constexpr (kPair) tmem_dealloc_cg2(tmem, tmem_cols);
+    else tmem_dealloc(tmem, tmem_cols);
+  }
 }
 
-template <int C, int TAPS, int GROUPS>
+template <int C, int TAPS, int GROUPS, bool kPair = false>
 __global__ void __launch_bounds__(TShape<C, TAPS>::kThreads, 1) plane_t_kernel(const __grid_constant__ TParams p) {
   pdl_trigger();
-  t_body<C, TAPS, GROUPS>(p);
+  t_body<C, TAPS, GROUPS, kPair>(p);
 }
 
 // ================================================================================================
@@ -1969,12 +2022,13 @@ constexpr size_t kSmemBudget = 227 * 1024 - 2048;   // dynamic bytes we allow ou
 
 struct TPlan {
   int N, n_wslab, ksteps, na;
+  int pair;          // CTA pairs (cta_group::2): half of every weight slab per CTA, more input stages in flight
   int groups;        // 3: grouped form (narrow input), 1: all taps in N
   int stage_bytes;
   size_t smem;
 };
 
-bool plan_t(const PlaneConv& c, TPlan* pl) {
+bool plan_t(const PlaneConv& c, TPlan* pl, bool allow_pair = true) {
   const bool k9 = (c.Cout == 20 && c.K == 9 && c.dil >= 1 && c.dil <= 2);
   const bool k55 = (c.Cout == 1 && c.K == 55 && c.dil == 1);
   if (!k9 && !k55) return false;
@@ -1997,7 +2051,18 @@ bool plan_t(const PlaneConv& c, TPlan* pl) {
   pl->ksteps = (c.in.packed && c.planes == 2) ? 4 : (c.Cin + 15) / 16;   // packed hi/lo rows: one K axis of 64 halves
   pl->n_wslab = pl->groups > 1 ? pl->groups : (c.in.packed ? 1 : c.in.planes * c.in.spp);
   const int maxm = k9 ? 8 : 32, rowf = k9 ? 24 : 1;
-  const size_t fixed = (size_t)pl->n_wslab * pl->N * 128 + 2ull * t_slots(k9 ? 20 : 1) * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
+  // CTA pairs for the wide-input 20-channel layers whose stages are short of the cap (100 -> 20: five stages -> eight).  Measured
+  // NEUTRAL (17.3 vs 16.8 ms per 33k frames: the layer is not bound by bytes in flight after all, its tap-sum epilogue and MMAs each
+  // fill about half of a tile's time), so only NSC_PLANE_PAIR=2 selects it.  Needs an even number of frames on an even grid: the two
+  // CTAs walk their frames in lockstep.
+  {
+    static const int pair_knob = [] { const char* e = getenv("NSC_PLANE_PAIR"); return e ? atoi(e) : 1; }();
+    const int64_t grid = c.B < sm_count() ? c.B : sm_count();
+    const size_t full = (size_t)pl->n_wslab * pl->N * 128 + 2ull * t_slots(20) * maxm * rowf * sizeof(float) + (size_t)kORing * 128 + 1024;
+    const bool short_of_stages = k9 && (kSmemBudget - full) / kAStage < 8;
+    pl->pair = (allow_pair && pair_knob >= 2 && k9 && pl->groups == 1 && !c.in.packed && short_of_stages && c.B >= 2 && c.B % 2 == 0 && grid % 2 == 0) ? 1 : 0;
+  }
+  const size_t fixed = (size_t)pl->n_wslab * pl->N * (pl->pair ? 64 : 128) + 2ull * t_slots(k9 ? 20 : 1) * maxm * rowf * sizeof(float) + (k9 ? (size_t)kORing * 128 + 1024 : 0);
   if (fixed + 2ull * kAStage > kSmemBudget) return false;
   // (Two CTAs per SM for the narrow-input layers measured neutral -- 4.8 vs 4.8 ms per step on 20 -> 20 -- and were removed.)
   const size_t budget = kSmemBudget;
@@ -2201,7 +2266,7 @@ bool plane_plan_info(const PlaneConv& c, int64_t* o) {
     TPlan pl;
     if (!plan_t(c, &pl)) return false;
     o[1] = pl.groups > 1 ? pl.groups : 0;    // (taps-in-N: the "staged" field reports the tap groups of the grouped form)
-    o[3] = 1; o[4] = 1; o[5] = 1; o[6] = pl.n_wslab; o[7] = pl.na; o[8] = (int64_t)pl.smem;
+    o[2] = pl.pair; o[3] = 1; o[4] = 1; o[5] = 1; o[6] = pl.n_wslab; o[7] = pl.na; o[8] = (int64_t)pl.smem;
     int cols = 32;
     while (cols < 2 * pl.N) cols *= 2;
     o[9] = cols;
@@ -2326,6 +2391,9 @@ int plane_launch(const PlaneConv& c, cudaStream_t st) {
     } else if (c.Cout == 20 && pl.groups == 3) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
       NSC_CUDA_OK(launch_plane(plane_t_kernel<20, 5, 3>, grid, TShape<20, 5>::kThreads, pl.smem, st, 1, p));
+    } else if (c.Cout == 20 && pl.pair) {
+      NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      NSC_CUDA_OK(launch_plane(plane_t_kernel<20, 9, 1, true>, grid, TShape<20, 9>::kThreads, pl.smem, st, 2, p));
     } else if (c.Cout == 20) {
       NSC_CUDA_OK(cudaFuncSetAttribute(plane_t_kernel<20, 9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
       NSC_CUDA_OK(launch_plane(plane_t_kernel<20, 9, 1>, grid, TShape<20, 9>::kThreads, pl.smem, st, 1, p));
@@ -2431,7 +2499,7 @@ bool plan_block(const PlaneBlock& b, BlockPlan* bp) {
   if (c1.B != c2.B || c1.B != c3.B || c1.B < 1) return false;
   if (b.ring < 2 || (b.ring & (b.ring - 1))) return false;
   if (sm_count() < 8) return false;
-  if (!plan_t(c1, &bp->t1) || !plan_t(c2, &bp->t2) || bp->t2.groups != 3) return false;
+  if (!plan_t(c1, &bp->t1, false) || !plan_t(c2, &bp->t2, false) || bp->t2.groups != 3) return false;   // (the roles of the fused kernel are single CTAs)
   if (!plan_x(c3, &bp->x3, kSmemBudget - 2048) || !bp->x3.staged || !bp->x3.pair) return false;   // (the fused kernel's static shared memory is the sum of its roles')   // (pairs need an even number of tiles)
   bp->smem = bp->t1.smem;
   if (bp->t2.smem > bp->smem) bp->smem = bp->t2.smem;

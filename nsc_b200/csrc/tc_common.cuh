@@ -66,9 +66,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same wait for threads that are NOT on the tensor pipe's critical path (loaders, producers, epilogue warps between tiles):
 // a failed probe backs off for a few dozen nanoseconds instead of re-issuing at once -- the step runs under the power cap, and
 // idle warps that hammer the barrier cost issue slots and clock.
+// NSC_WAIT_HINT (compile-time experiment): suspend-time hint of the probe instead of the back-off -- the hardware parks the thread
+// until the phase completes (or the hint expires), so a waiting warp issues nothing at all.
+#ifndef NSC_WAIT_HINT
+#define NSC_WAIT_HINT 1
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   for (;;) {
+#if NSC_WAIT_HINT
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    if (done) break;
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -76,6 +89,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (done) break;
     __nanosleep(40);
+#endif
   }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -129,9 +129,10 @@ def test_cta_pair_layers(layer, precision):
 @pytest.mark.parametrize('pair', ['0', '2'])
 def test_cta_pair_knob(pair):
     """NSC_PLANE_PAIR=0: the one-CTA kernel on even batches; =2: pairs wherever the shape allows (stride-2 conv, and 20 -> 20 on
-    the tap-shift kernel via NSC_PLANE_NARROW=X).  Results must not depend on the choice."""
+    the tap-shift kernel via NSC_PLANE_NARROW=X, and the taps-in-N 100 -> 20 layer with half of every weight slab per CTA and eight
+    input stages).  Results must not depend on the choice."""
     _child({'NSC_PLANE_PAIR': pair, 'NSC_PLANE_NARROW': 'X'},
-           "for layer in (t.X_LAYERS[4], t.X_LAYERS[5], t.X_LAYERS[0], t.X_LAYERS[3], t.T_LAYERS[3], t.T_LAYERS[5]):\n"
+           "for layer in (t.X_LAYERS[4], t.X_LAYERS[5], t.X_LAYERS[0], t.X_LAYERS[3], t.T_LAYERS[3], t.T_LAYERS[5], t.T_LAYERS[0], t.T_LAYERS[1]):\n"
            "    for prec in (1, 2):\n"
            "        for B in (2, 302, 1184):\n"
            "            e = t._run(B=B, precision=prec, seed=B, **layer)\n"
