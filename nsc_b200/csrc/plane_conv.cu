@@ -1010,6 +1010,8 @@ struct XParams {
   const float* bias2;        // gated linear unit: bias of the tanh gate (columns [20, 40))
   int glu, ileave;           // see PlaneConv
   int fold_out, unfold;      // folded narrow images (plane.cuh): the output is written folded / the 48-channel result is unfolded
+  int psplit;                // two MMA-issuing threads BY WEIGHT PLANE (0: W_hi units = hi and lo activation planes, 1: W_lo units), one accumulator
+                             // each, summed in the epilogue: the stride-2 conv's 189 MMAs per tile are bound by what ONE thread can issue
   int pairtiles;             // unfold + ileave: a CTA takes its tiles in PAIRS (2u, 2u + 1) = the two position parities of codec frame u,
                              // so that the unfolded frame is complete in its staging buffer after the second one
   int Lin, Lout, Cin, Cout, K, dil, stride, padL;
@@ -1158,7 +1160,13 @@ struct XIssue {
   uint32_t ws, wph, u;              // weight ring slot / phase, unit counter inside the tile
   bool resident, w_ready;
   int wslots;
+  int issuer, psplit;
   const XBars* b;
+  // a unit that belongs to the other issuing thread: keep the ring position, touch nothing
+  __device__ __forceinline__ void skip_w() {
+    if (!resident) { if (++ws == (uint32_t)wslots) { ws = 0; wph ^= 1u; } }
+    ++u;
+  }
   template <int MODE>
   __device__ __forceinline__ uint32_t wait_w() {
     if (resident) {
@@ -1217,7 +1225,8 @@ __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s,
     const int st_hi = pt_slab_index(p.in, sub, 0, s);
     const uint32_t a_hi = a_stage0 + (uint32_t)st_hi * stage_lo + (uint32_t)rowoff * 8u;
     const uint32_t a_lo_pl = a_hi + (uint32_t)spp * stage_lo;     // the lo plane's stage is spp slabs further
-    {
+    if (x.psplit && x.issuer == 1) x.skip_w();
+    else {
       const uint32_t b_lo = x.wait_w<MODE>();
       wait_stage(st_hi);
       x_issue_mt<NKS, MODE>(x, a_hi, b_lo, accum);
@@ -1226,9 +1235,14 @@ __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s,
       x.done_w<MODE>();
     }
     if (p.planes == 2) {
-      const uint32_t b_lo = x.wait_w<MODE>();
-      x_issue_mt<NKS, MODE>(x, a_hi, b_lo, 1u);
-      x.done_w<MODE>();
+      if (x.psplit && x.issuer == 0) x.skip_w();
+      else {
+        const uint32_t b_lo = x.wait_w<MODE>();
+        if (x.psplit) wait_stage(st_hi);
+        x_issue_mt<NKS, MODE>(x, a_hi, b_lo, x.psplit ? accum : 1u);
+        accum = 1;
+        x.done_w<MODE>();
+      }
     }
   }
 }
@@ -1236,11 +1250,12 @@ __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s,
 template <int MODE>
 __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer, uint8_t* sA, uint8_t* sW, uint32_t tmem, const XBars& bars) {
   const uint32_t mt_step = (128u * 128u) >> 4;
-  const int m0 = p.n_iss == 2 ? issuer : 0;                       // first M tile of this thread
+  const int m0 = (p.n_iss == 2 && !p.psplit) ? issuer : 0;        // first M tile of this thread
   const uint32_t a_lo_base = desc_lo(smem_u32(sA)) + (uint32_t)m0 * mt_step;
   const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4;
-  const int acc_cols = (p.n_iss == 3 ? 3 : p.mt) * p.Npad;
+  const int acc_cols = (p.n_iss == 3 ? 3 : p.psplit ? 2 : p.mt) * p.Npad;
   XIssue x;
+  x.issuer = issuer; x.psplit = p.psplit;
   x.idesc = make_idesc_f16(p.Npad, MODE == 0 ? 128 : 256);
   x.w_lo_base = desc_lo(smem_u32(sW));
   x.unit_lo = (uint32_t)p.slot_bytes >> 4;
@@ -1249,7 +1264,7 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
   x.w_ready = false;
   x.wslots = p.wslots;
   x.b = &bars;
-  x.nmt = p.n_iss == 2 ? 1 : p.mt;
+  x.nmt = (p.n_iss == 2 && !p.psplit) ? 1 : p.mt;
   x.npad = (uint32_t)p.Npad;
   uint32_t it = 0, kb = 0, a_phase = 0;
   for (int64_t ti = 0, tile; (tile = x_tile_at(p, ti)) < p.n_tiles; ++ti, ++it) {
@@ -1258,7 +1273,7 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
     if constexpr (MODE != 2) mbar_wait(&bars.acc_empty[acc_i], ((it >> 1) & 1u) ^ 1u);   // (pair: both CTAs' epilogues arrive on the leader's)
     if (p.stats != nullptr) stat_add(p.stats, 7, clock64() - tw);
     tc_fence_after();
-    x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)((p.n_iss == 3 ? issuer : m0) * p.Npad);
+    x.d = tmem + acc_i * (uint32_t)acc_cols + (uint32_t)(((p.n_iss == 3 || p.psplit) ? issuer : m0) * p.Npad);
     x.u = 0;
     if (gen) {
       if constexpr (MODE == 0) {
@@ -1351,7 +1366,7 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   const int nbuf = p.n_stage * p.kbuf;
   uint8_t* sA = smem;
   uint8_t* sW = smem + (uint32_t)nbuf * (uint32_t)p.stage_bytes;
-  const int acc_cols = (p.n_iss == 3 ? 3 : p.mt) * p.Npad;
+  const int acc_cols = (p.n_iss == 3 ? 3 : p.psplit ? 2 : p.mt) * p.Npad;
   const int n_iss = p.n_iss;           // issuing threads: one, or one per M tile
   constexpr int kIssuer1 = kGen ? kXEpiWarps + 3 + kXGenWarps : kXEpiWarps + 3;
 
@@ -1363,7 +1378,8 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
   const uint32_t crank = pair ? cluster_ctarank() : 0u;
   if (tid == 0) {
     for (int i = 0; i < nbuf; ++i) { mbar_init(&a_full[i], kGen ? kXGenWarps : 1); mbar_init(&a_empty[i], n_iss); mbar_init(&a_full2[i], 1); }
-    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_iss); mbar_init(&w_full2[i], 1); }
+    // (psplit: a weight unit is read by exactly one of the two issuing threads)
+    for (int i = 0; i < p.wslots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], p.psplit ? 1 : n_iss); mbar_init(&w_full2[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], pair ? 2 * kXEpiWarps : kXEpiWarps); }
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1529,6 +1545,13 @@ __global__ void __launch_bounds__(kGen ? kXThreadsGen : kXThreadsX, 1) plane_x_k
         const int pos = row0 + mt_i * 128;
         uint32_t r[16];
         tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(mt_i * p.Npad + c0), r);
+        if (p.psplit) {      // the W_lo products sit in their own accumulator (second issuing thread)
+          uint32_t r2[16];
+          tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + acc_i * (uint32_t)acc_cols + (uint32_t)(p.Npad + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+        }
         const ResRaw rc = rn;
         rn = rn2;
         load_res(u + 2 * kXEpiGroups, rn2);
@@ -2209,6 +2232,16 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
       if (knob == 1) p->n_iss = 1;
       if (knob == 2 && p->mt == 2) p->n_iss = 2;
       if (c.fold2 && p->resident && p->kbuf * p->n_stage <= kXMaxStage) p->n_iss = 3;
+      // two issuing threads by weight plane for one-tile layers with many MMAs per tile (the stride-2 conv: 189): NSC_PLANE_PSPLIT=0 off
+      static const bool psplit_knob = [] { const char* e = getenv("NSC_PLANE_PSPLIT"); return !(e && e[0] == '0'); }();
+      p->psplit = (psplit_knob && !gen && !c.in.packed && c.planes == 2 && p->mt == 1 && !p->pair && !p->staged && !c.glu && !c.fold2 && c.K >= 3 &&
+                   p->n_iss == 1 && 4 * p->Npad <= 512) ? 1 : 0;
+      if (p->psplit) {
+        p->n_iss = 2;
+        int cols2 = 32;
+        while (cols2 < 4 * p->Npad) cols2 *= 2;
+        p->tmem_cols = cols2;
+      }
     }
     return true;
   }
