@@ -2232,8 +2232,10 @@ bool plan_x(const PlaneConv& c, XParams* p, size_t smem_budget = kSmemBudget) {
       if (knob == 1) p->n_iss = 1;
       if (knob == 2 && p->mt == 2) p->n_iss = 2;
       if (c.fold2 && p->resident && p->kbuf * p->n_stage <= kXMaxStage) p->n_iss = 3;
-      // two issuing threads by weight plane for one-tile layers with many MMAs per tile (the stride-2 conv: 189): NSC_PLANE_PSPLIT=0 off
-      static const bool psplit_knob = [] { const char* e = getenv("NSC_PLANE_PSPLIT"); return !(e && e[0] == '0'); }();
+      // two issuing threads by weight plane for one-tile layers with many MMAs per tile (the stride-2 conv: 189).  EXPERIMENT, off unless
+      // NSC_PLANE_PSPLIT=1: full bench runs hung intermittently while this and the barrier waits' suspend-time hint were both on
+      // (DESIGN.md finding 20); with both off 16 of 16 ran through.
+      static const bool psplit_knob = [] { const char* e = getenv("NSC_PLANE_PSPLIT"); return e && e[0] == '1'; }();
       p->psplit = (psplit_knob && !gen && !c.in.packed && c.planes == 2 && p->mt == 1 && !p->pair && !p->staged && !c.glu && !c.fold2 && c.K >= 3 &&
                    p->n_iss == 1 && 4 * p->Npad <= 512) ? 1 : 0;
       if (p->psplit) {

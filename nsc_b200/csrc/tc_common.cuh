@@ -69,7 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // NSC_WAIT_HINT (compile-time experiment): suspend-time hint of the probe instead of the back-off -- the hardware parks the thread
 // until the phase completes (or the hint expires), so a waiting warp issues nothing at all.
 #ifndef NSC_WAIT_HINT
-#define NSC_WAIT_HINT 1
+#define NSC_WAIT_HINT 0
 #endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;

@@ -127,7 +127,7 @@ if __name__ == '__main__':
     facts = launches(tag)
     summ = captures(tag, facts)
     # tensor-pipe activity of the captured kernels, attached to the layers they are (first launches of a step: see tools/ncu_r02.sh)
-    which = {'xs_20to100': 'pX2_k9d1s1_c20to100', 'x_down': 'pX2_k9d1s2_c100to100'}
+    which = {'xs_20to100': 'pX2_k9d1s1_c20to100', 'x_down': 'pX2_k9d1s2_c100to100', 'x_fold': 'pF2_k9d1_c20to20', 'lpc_analyze': 'lpc_analyze'}
     for key, v in summ.items():
         cap = key.split('#')[0]
         layer = which.get(cap)
