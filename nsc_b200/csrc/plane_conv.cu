@@ -1206,7 +1206,9 @@ __device__ __forceinline__ void x_issue_packed(XIssue& x, const XParams& p, uint
 }
 
 // one 64-channel slab of a wide input: per tap the W_hi unit meets the hi and the lo plane, the W_lo unit the hi plane
-template <int NKS, int MODE>
+// (kSplit: the experimental two-thread form, XParams::psplit -- a template parameter because three extra predicates per unit in the
+// ONE-thread loop cost the stride-2 conv 15 %)
+template <int NKS, int MODE, bool kSplit = false>
 __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s, uint32_t a_stage0, uint32_t stage_lo, uint32_t kb,
                                              uint32_t a_phase, uint32_t& waited, uint32_t& accum) {
   const int spp = p.in.spp;
@@ -1225,22 +1227,38 @@ __device__ __forceinline__ void x_issue_slab(XIssue& x, const XParams& p, int s,
     const int st_hi = pt_slab_index(p.in, sub, 0, s);
     const uint32_t a_hi = a_stage0 + (uint32_t)st_hi * stage_lo + (uint32_t)rowoff * 8u;
     const uint32_t a_lo_pl = a_hi + (uint32_t)spp * stage_lo;     // the lo plane's stage is spp slabs further
-    if (x.psplit && x.issuer == 1) x.skip_w();
-    else {
-      const uint32_t b_lo = x.wait_w<MODE>();
-      wait_stage(st_hi);
-      x_issue_mt<NKS, MODE>(x, a_hi, b_lo, accum);
-      accum = 1;
-      if (p.planes == 2) { wait_stage(st_hi + spp); x_issue_mt<NKS, MODE>(x, a_lo_pl, b_lo, 1u); }
-      x.done_w<MODE>();
-    }
-    if (p.planes == 2) {
-      if (x.psplit && x.issuer == 0) x.skip_w();
+    if constexpr (kSplit) {
+      if (x.issuer == 1) x.skip_w();
       else {
         const uint32_t b_lo = x.wait_w<MODE>();
-        if (x.psplit) wait_stage(st_hi);
-        x_issue_mt<NKS, MODE>(x, a_hi, b_lo, x.psplit ? accum : 1u);
+        wait_stage(st_hi);
+        x_issue_mt<NKS, MODE>(x, a_hi, b_lo, accum);
         accum = 1;
+        if (p.planes == 2) { wait_stage(st_hi + spp); x_issue_mt<NKS, MODE>(x, a_lo_pl, b_lo, 1u); }
+        x.done_w<MODE>();
+      }
+      if (p.planes == 2) {
+        if (x.issuer == 0) x.skip_w();
+        else {
+          const uint32_t b_lo = x.wait_w<MODE>();
+          wait_stage(st_hi);
+          x_issue_mt<NKS, MODE>(x, a_hi, b_lo, accum);
+          accum = 1;
+          x.done_w<MODE>();
+        }
+      }
+    } else {
+      {
+        const uint32_t b_lo = x.wait_w<MODE>();
+        wait_stage(st_hi);
+        x_issue_mt<NKS, MODE>(x, a_hi, b_lo, accum);
+        accum = 1;
+        if (p.planes == 2) { wait_stage(st_hi + spp); x_issue_mt<NKS, MODE>(x, a_lo_pl, b_lo, 1u); }
+        x.done_w<MODE>();
+      }
+      if (p.planes == 2) {
+        const uint32_t b_lo = x.wait_w<MODE>();
+        x_issue_mt<NKS, MODE>(x, a_hi, b_lo, 1u);
         x.done_w<MODE>();
       }
     }
@@ -1330,6 +1348,16 @@ __device__ __forceinline__ void x_issuer(const XParams& p, bool gen, int issuer,
       for (int s = 0; s < p.in.spp; ++s) {
         const int nks = min(4, p.ksteps - 4 * s);
         const uint32_t a0 = a_lo_base + kb * stage_lo;
+        if (p.psplit) {
+          if constexpr (MODE == 0) {
+            switch (nks) {
+              case 4: x_issue_slab<4, 0, true>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+              case 3: x_issue_slab<3, 0, true>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+              case 2: x_issue_slab<2, 0, true>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+              default: x_issue_slab<1, 0, true>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
+            }
+          }
+        } else
         switch (nks) {
           case 4: x_issue_slab<4, MODE>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
           case 3: x_issue_slab<3, MODE>(x, p, s, a0, stage_lo, kb, a_phase, waited, accum); break;
