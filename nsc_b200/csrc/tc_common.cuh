@@ -71,6 +71,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef NSC_WAIT_HINT
 #define NSC_WAIT_HINT 0
 #endif
+#ifndef NSC_WAIT_BACKOFF_NS
+#define NSC_WAIT_BACKOFF_NS 40
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   for (;;) {
@@ -88,7 +91,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(40);
+    __nanosleep(NSC_WAIT_BACKOFF_NS);
 #endif
   }
 }
