@@ -78,8 +78,12 @@ def roofline_record(agg, tot_ms, args, frames):
     all_fl = sum(v[1] for v in agg.values())
     facts = ncu_facts()
     kf = facts.get('kernels', {}).get(top_name, {})
-    traffic = kf.get('dram_bytes_per_launch')
     alg_bytes_launch = top[2] / top[3]
+    # ncu measured DRAM bytes of ONE launch of this layer at the pass size of ITS run; per launch of THIS run = the same bytes per
+    # algorithmic byte (the launch list's pass size may differ from the live one: NSC_PLANE_CHUNK, --frames)
+    traffic = kf.get('dram_bytes_per_launch')
+    if traffic and kf.get('algorithmic_bytes_per_launch'):
+        traffic = traffic * alg_bytes_launch / kf['algorithmic_bytes_per_launch']
     step = facts.get('whole_step', {})
     dram_pf = step.get('dram_bytes_per_frame')
     peak = bf16_sus if tensor_path else None
@@ -92,8 +96,9 @@ def roofline_record(agg, tot_ms, args, frames):
         "issued_frac": ach_tf * mma_per_product / bf16_sus,
         "tensor_pipe_active_ncu": kf.get('sm__pipe_tensor_cycles_active_pct'),
         "traffic": traffic,
-        "traffic_detail": ({"algorithmic_bytes_of_that_launch": kf.get('algorithmic_bytes_per_launch'),
-                            "traffic_vs_algorithmic": (traffic / kf['algorithmic_bytes_per_launch']) if traffic and kf.get('algorithmic_bytes_per_launch') else None,
+        "traffic_detail": ({"ncu_dram_bytes_of_the_captured_launch": kf.get('dram_bytes_per_launch'),
+                            "algorithmic_bytes_of_that_launch": kf.get('algorithmic_bytes_per_launch'),
+                            "traffic_vs_algorithmic": (kf['dram_bytes_per_launch'] / kf['algorithmic_bytes_per_launch']) if kf.get('dram_bytes_per_launch') and kf.get('algorithmic_bytes_per_launch') else None,
                             "frames_of_that_launch": kf.get('frames_per_launch'), "source": kf.get('source')} if kf else None),
         "hbm": {"achieved_gbs_algorithmic": ach_gbs, "frac_of_measured": ach_gbs / hbm, "peak_gbs": hbm,
                 "algorithmic_bytes_per_launch": alg_bytes_launch,
@@ -254,10 +259,10 @@ def run_ours(args):
     out_host = {}
     # End-to-end step through the public API with HOST buffers: the batch goes through in sub-batches so that the pinned-memory
     # H2D copy of sub-batch k+1 and the D2H copy of sub-batch k-1 (copy stream) run under the compute of sub-batch k.
-    # Sub-batches are whole passes of the engine (2 x 2,072 frames) so no pass is split; the exposed part of the copies is the
+    # Sub-batches are at least one pass of the engine (nsc_pass_frames) so the prepared workspace serves every call; the exposed part of the copies is the
     # first sub-batch's H2D and the last one's D2H.  H2D and D2H use separate streams (both copy engines).
-    sub = 4144
-    n_sub = max(1, min(8, -(-B // sub)))
+    sub = cm.pass_frames()
+    n_sub = max(1, min(8, B // sub))               # (the last sub-batch takes the remainder: every call is at least one pass)
     bounds = [(i * sub, (i + 1) * sub if i + 1 < n_sub else B) for i in range(n_sub)]
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
@@ -473,7 +478,7 @@ def measure_corpus(args, world, rank, dev, lib, steps, warmup, n_utt=None):
     cm = codec.CMRL([codec.NeuralCodec(cfg, device=dev, seed=5), codec.NeuralCodec(cfg, device=dev, seed=6)], res_scalar=1.0)
     n_utt = n_utt or args.utterances
     T = int(args.utt_seconds * 16000)
-    cm.prepare(max(2072, n_utt))                    # once per weights (nsc_prepare): any call of at least one engine pass uses it
+    cm.prepare(max(cm.pass_frames(), n_utt))        # once per weights (nsc_prepare): any call of at least one engine pass uses it
     x_np, _ = synth_audio(64, seed=4321 + rank)
     base = np.tile(x_np.reshape(-1), -(-T * 8 // x_np.size))        # a few distinct utterances, tiled
     host = [torch.from_numpy(np.ascontiguousarray(base[(i % 8) * 4000:(i % 8) * 4000 + T])).pin_memory() for i in range(n_utt)]

@@ -274,6 +274,9 @@ int nsc_cascade_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float
  *   outputs: lsf_idx (B,16) uint8, poly (B,17), res_x (B,512), decoded (B,512), synthesized (B,512); any may be NULL
  *   except decoded.  */
 int64_t nsc_cq_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B);
+/* Frames the engines process per pass for these configurations (larger batches are walked in passes of this size; a workspace is
+ * sized for min(B, pass) frames, and nsc_prepare covers every call of at least one pass).  -1 on bad arguments. */
+int64_t nsc_pass_frames(const nsc_codec_cfg* cfgs, int32_t n_codecs);
 int nsc_cq_forward(const nsc_codec_cfg* cfgs, int32_t n_codecs, const float* const* params_ptrs_host,
                    const float* lsf_params, int32_t n_lsf_bins, const float* x, const float* lsf, int64_t B,
                    float res_scalar, float is_quan_on, int32_t use_soft, uint8_t* lsf_idx, float* lsf_hist,

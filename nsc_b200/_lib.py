@@ -80,6 +80,7 @@ SIGNATURES = {
     "nsc_cascade_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),
     "nsc_cascade_forward": (_i32, [_cfgp, _i32, _ppv, _vp, _i64, _f32, _i32, _f32, _i32, _ppv, _ppv, _ppv, _ppv, _vp, _vp, _i64, _vp]),
     "nsc_cq_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),
+    "nsc_pass_frames": (_i64, [_cfgp, _i32]),
     "nsc_cq_forward": (_i32, [_cfgp, _i32, _ppv, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _i32, _vp, _vp, _vp, _ppv, _ppv, _ppv,
                               _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "nsc_train_workspace_bytes": (_i64, [_cfgp, _i32, _i64]),

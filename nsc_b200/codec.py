@@ -328,6 +328,10 @@ class CMRL:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.lsf_params.device)
         return self._ws
 
+    def pass_frames(self) -> int:
+        """Frames the engine processes per pass for this cascade (nsc_pass_frames): larger batches are walked in passes of this size."""
+        return int(_lib.load().nsc_pass_frames(self._cfgs, len(self.codecs)))
+
     def prepare(self, B: int, cq: bool = True) -> None:
         """As NeuralCodec.prepare, for feedforward_lpc (cq=True) or all_modules_feedforward (cq=False) at batch size B."""
         ws = self._workspace(B, cq)

@@ -490,6 +490,11 @@ static int64_t cq_extra_bytes(int64_t Bc) {
   return (Bc * NSC_LPC_ORDER + Bc * (NSC_LPC_ORDER + 1) + Bc * kFrameLen) * (int64_t)sizeof(float) + 3 * 256;
 }
 
+int64_t nsc_pass_frames(const nsc_codec_cfg* cfgs, int32_t n_codecs) {
+  if (cfgs == nullptr || n_codecs < 1 || n_codecs > NSC_MAX_CODECS) return -1;
+  return chunk_for(cfgs, n_codecs);
+}
+
 int64_t nsc_cq_workspace_bytes(const nsc_codec_cfg* cfgs, int32_t n_codecs, int64_t B) {
   const int64_t c = nsc_cascade_workspace_bytes(cfgs, n_codecs, B);
   if (c < 0) return c;

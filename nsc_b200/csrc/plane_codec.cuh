@@ -34,12 +34,13 @@ bool plane_codec_supported(const nsc_codec_cfg& c) {
   return true;
 }
 
-// frames per pass of the plane path: a whole number of frames per SM for every kernel
+// frames per pass of the plane path: a whole number of frames per SM for every kernel.  28 per SM (4,144): re-measured at the end of
+// round 2 against 14 per SM -- 105.7 vs 108.6 ms per 32,768 frames (half the launches, each kernel's fill and drain paid half as often)
 int64_t plane_chunk_frames() {
   static const int64_t v = [] {
     const char* e = getenv("NSC_PLANE_CHUNK");
     const long long n = e ? atoll(e) : 0;
-    return (int64_t)(n >= 1 && n <= 65536 ? n : 14LL * sm_count());
+    return (int64_t)(n >= 1 && n <= 65536 ? n : 28LL * sm_count());
   }();
   return v;
 }

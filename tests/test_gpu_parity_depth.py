@@ -1,5 +1,5 @@
 """Parity in depth (round-2 review items): per-FRAME errors over an 80 dB range of input levels, a direct oracle comparison of the
-headline workload (cq2) at more than one engine pass (2,072 + 300 frames), the end-to-end hard-code agreement rate against the
+headline workload (cq2) at more than one engine pass (one pass + 300 frames), the end-to-end hard-code agreement rate against the
 float32 oracle AND against float64 truth, and gated_bottleneck_decoder."""
 import os
 
@@ -80,13 +80,13 @@ def test_decoder_per_frame_error_on_identical_codes():
 
 
 def test_cq2_direct_oracle_comparison_beyond_one_pass():
-    """The headline workload at 2,072 + 300 frames (more than one pass of the plane engine, ragged second pass) against the oracle
+    """The headline workload at one engine pass + 300 frames (4,144 + 300: a ragged second pass) against the oracle
     run on the SAME frames: LSF codes bit-exact, LPC polynomial / residual within 1e-4, soft-path decoded and synthesized audio
     within 1e-4, hard codes agreeing except at quantiser boundaries, hard-path audio within 1e-4 on frames whose codes all agree."""
     from nsc_b200 import codec, lpc_utilities as lu
-    B = 2072 + 300
     pairs = [_pair(seed=5), _pair(seed=6)]
     cm = codec.CMRL([p[1] for p in pairs], res_scalar=1.0)
+    B = cm.pass_frames() + 300
     win = ar_frames(B, 1024, seed=77, std=1.0)
     x = np.ascontiguousarray(win[:, 256:768])
     bins = np.load(os.path.join(GOLD, 'lsf_bins_f64.npy')).astype(np.float32)

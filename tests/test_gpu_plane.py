@@ -167,7 +167,7 @@ def _cq2(seed0=5, seed1=6, precision='tc_f16x3'):
 
 
 def test_full_size_batch_independence_across_chunk_boundaries():
-    """BASELINE-size batch (4,500 frames: three 2,072-frame chunks, the last one ragged): every frame's codes and waveform are
+    """BASELINE-size batch (4,500 frames: a full 4,144-frame pass and a ragged one): every frame's codes and waveform are
     bit-identical to coding it in a 7-frame batch -- no dependence on the chunk it fell in, the CTA that took it, or its
     neighbours (frames are independent units)."""
     from util import ar_frames
@@ -177,7 +177,7 @@ def test_full_size_batch_independence_across_chunk_boundaries():
     x = win[:, 256:768].contiguous()
     lsf = lu.lpc_analysis_windows(win, 16, dtype=torch.float32)
     big = cm.feedforward_lpc(x, lsf, False, 1.0)
-    for lo in (0, 2068, 2072, 4140, 4493):      # around the 2,072 / 4,144 chunk boundaries and the ragged tail
+    for lo in (0, 2068, 2072, 4140, 4144, 4493):      # around the pass boundary (4,144) and the ragged tail
         small = cm.feedforward_lpc(x[lo:lo + 7].contiguous(), lsf[lo:lo + 7].contiguous(), False, 1.0)
         for k in range(2):
             assert torch.equal(small['idx'][k], big['idx'][k][lo:lo + 7])

@@ -93,19 +93,21 @@ def test_codec_workspace_sizes_on_the_plane_path():
     import ctypes as C
     one = lib.nsc_codec_workspace_bytes(C.byref(cfg), 1)
     big = lib.nsc_codec_workspace_bytes(C.byref(cfg), 100000)
-    chunk = lib.nsc_codec_workspace_bytes(C.byref(cfg), 2072)
-    assert 0 < one < chunk == big                           # capped at one chunk of 14 x 148 frames
-    per_frame = (chunk - one) / 2071
+    npass = lib.nsc_pass_frames(C.byref(cfg), 1)
+    assert npass == 28 * 148 and lib.nsc_pass_frames(C.byref(cfg32), 1) > 0 and lib.nsc_pass_frames(None, 1) == -1
+    chunk = lib.nsc_codec_workspace_bytes(C.byref(cfg), npass)
+    assert 0 < one < lib.nsc_codec_workspace_bytes(C.byref(cfg), npass // 2) < chunk == big      # capped at one pass of 28 x 148 frames
+    per_frame = (chunk - one) / (npass - 1)
     assert 1.5e6 < per_frame < 1.8e6                        # 11 plane buffers + 3 folded narrow images: 1.76 MB per frame
     assert lib.nsc_codec_workspace_bytes(C.byref(cfg32), 2048) < chunk   # fp32 NCL buffers are smaller
     # the reference's shipped 'gln' blocks run on the plane path too: three more buffers (two de-interleaved narrow twins for the
     # dilation-2 gate convs, a third half-length wide image for the depthwise half of the separable up-conv)
     gln = codec.CodecConfig(resnet_type='gln', precision='tc_f16x3').to_struct()
-    gchunk = lib.nsc_codec_workspace_bytes(C.byref(gln), 2072)
+    gchunk = lib.nsc_codec_workspace_bytes(C.byref(gln), npass)
     assert chunk < gchunk < 1.2 * chunk and gchunk == lib.nsc_codec_workspace_bytes(C.byref(gln), 100000)
     # two stride-2 stages (the_strides = '4', cmrl.py:804) with bottleneck blocks: on the plane path as well (three resolution levels)
     s4 = codec.CodecConfig(resnet_type='bottleneck', the_strides=(2, 2), precision='tc_f16x3').to_struct()
-    assert lib.nsc_codec_on_plane_engine(C.byref(s4)) == 1 and lib.nsc_codec_workspace_bytes(C.byref(s4), 2072) > chunk
+    assert lib.nsc_codec_on_plane_engine(C.byref(s4)) == 1 and lib.nsc_codec_workspace_bytes(C.byref(s4), npass) > chunk
     g4 = codec.CodecConfig(resnet_type='gln', the_strides=(2, 2), precision='tc_f16x3').to_struct()
     assert lib.nsc_codec_on_plane_engine(C.byref(g4)) == 1      # (its dilation-2 gates at 128 positions stage 16 halo rows)
     # configurations outside the plane path keep the layer-by-layer workspace: the one-plane mode with two stages (wide / 4 channels
