@@ -28,7 +28,7 @@ _lib.load()   # fail loudly at import time if the CUDA library is missing
 # Shapes the tensor engine does not cover (anything but the codec's layer shapes) run on the FFMA engine in every mode.
 _ENGINE = 'tc_f16x3'
 _PRECISION_CODE = {'tc_f16x3': 1, 'tc_f16': 2}
-last_engine = None      # 'tc' / 'tc_fused' / 'ffma': which engine the most recent conv-bearing call ran on (for tests)
+last_engine = None      # 'tc' / 'tc_folded' / 'tc_fused' / 'ffma': which engine the most recent conv-bearing call ran on (for tests)
 
 
 def set_engine(name: str) -> str:
@@ -141,7 +141,7 @@ def _flatten_params(params, n_expected: int) -> torch.Tensor:
     return torch.cat([_lib.require_f32(t, 'param').reshape(-1) for t in flat])
 
 
-def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rate, is_last_flat, gated, params, fused=True):
+def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rate, is_last_flat, gated, params, fused=None):
     x = _check_cl(the_input, 'the_input')
     B, L, cin = x.shape
     flat = _flatten_params(params, 8 if gated else 6)
@@ -150,12 +150,17 @@ def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rat
     lib = _lib.load()
     prec = _PRECISION_CODE.get(_ENGINE)
     if prec is not None and not gated and B > 0 and cin == wide_layer:
-        # the fused block kernel of the codec path (one launch: three CTA roles, intermediates through L2-resident rings)
+        # the_bottleneck on the tensor engine (three launches as in the codec program, or the one-launch fused kernel on request)
         ws_bytes = lib.nsc_bottleneck_block_tc_workspace_bytes(B, L, wide_layer, narrow_layer, prec)
         if ws_bytes > 0 and k_plain == 9 and k_dilated == 9 and dilation_rate in (1, 2):
             import ctypes as C
             ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
-            want_folded = fused == 'folded'       # three launches with the 20 -> 20 conv on folded images (the codec program's form)
+            # fused: None = the codec program's form -- three launches, the 20 -> 20 conv on folded images where the frame is long
+            # enough (hi/lo planes, 256 positions up); 'folded' / False force the folded / taps-in-N form; True = the ONE-launch fused
+            # kernel (opt-in: an intermittent wrong result on the first launch of a large uneven batch is open, DESIGN.md finding 11)
+            if fused is None:
+                fused = 'folded' if (prec == 1 and L >= 256) else False
+            want_folded = fused == 'folded'
             fused = C.c_int32(-2 if want_folded else (0 if fused else -1))
             rc = lib.nsc_bottleneck_block_tc(_lib.ptr(x), _lib.ptr(flat), _lib.ptr(y), B, L, wide_layer, narrow_layer, k_plain, k_dilated,
                                              dilation_rate, int(bool(is_last_flat)), prec, C.byref(fused), _lib.ptr(ws), ws_bytes,
@@ -184,9 +189,10 @@ def _block(the_input, wide_layer, narrow_layer, k_plain, k_dilated, dilation_rat
 
 
 def the_bottleneck(the_input, wide_layer=30, narrow_layer=10, non_dilated_neck_kernel_size=9,
-                   dilated_neck_kernel_size=9, dilation_rate=1, is_last_flat=False, *, params, fused=True):
+                   dilated_neck_kernel_size=9, dilation_rate=1, is_last_flat=False, *, params, fused=None):
     """nn_core_operator.py:57-79.  params = [(w1,b1), (w2,b2), (w3,b3)].
-    On the tensor engine the block is ONE fused launch (`fused=False`: the same three kernels, one launch each -- tests)."""
+    On the tensor engine the block runs as the codec program runs it: three launches, the second conv on folded images where the
+    frame is long enough (`fused='folded'` / `False` force that / the taps-in-N form; `fused=True`: the opt-in one-launch kernel)."""
     return _block(the_input, wide_layer, narrow_layer, non_dilated_neck_kernel_size, dilated_neck_kernel_size,
                   dilation_rate, is_last_flat, False, params, fused)
 
