@@ -2389,13 +2389,13 @@ int plane_pack_weights(const PlaneConv& c, cudaStream_t st) {
   return NSC_OK;
 }
 
-// NSC_PLANE_PDL=1 launches every conv kernel of the plane engine with programmatic stream serialization: its prologue runs under the
-// tail of the kernel before it, the rest after pdl_wait().  Worth 1.2 % of a step -- and OFF by default: one test that compares the
-// three launches of a block with the fused kernel bit for bit (700 frames: the case with the most tail overlap) failed twice in
-// about a dozen runs with it and never without, and the cause was not found (DESIGN.md finding 19).
+// Every conv kernel of the plane engine is launched with programmatic stream serialization (NSC_PLANE_PDL=0: plain launches): its
+// prologue runs under the tail of the kernel before it, the rest after pdl_wait().  Worth 1.2 % of a large step and 15 % of a
+// 128-frame call.  (It was switched off for a few hours at the end of round 2 as the suspect of a bit-identity failure that turned
+// out to be the opt-in fused block kernel's own -- DESIGN.md findings 11 and 19.)
 template <typename P>
 static cudaError_t launch_plane(void (*kernel)(P), int64_t grid, int threads, size_t smem, cudaStream_t st, int cluster, const P& p) {
-  static const bool pdl = [] { const char* e = getenv("NSC_PLANE_PDL"); return e && e[0] == '1'; }();
+  static const bool pdl = [] { const char* e = getenv("NSC_PLANE_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)threads);
