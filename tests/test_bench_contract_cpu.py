@@ -68,3 +68,21 @@ def test_round2_headline_line_reports_the_tensor_roof_and_the_sub_records():
     ref = _line('r02_bench_reference.json')
     assert ref['impl'] == 'reference' and ref['metric'] == d['metric'] and ref['unit'] == d['unit']
     assert ref['e2e'] == {'value': ref['value'], 'unit': ref['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_round2_final_lines_state_how_the_weights_were_prepared():
+    """The headline is measured with the weights prepared once per weights (nsc_prepare), says so in `config`, and reports the
+    unprepared step beside it; the line of the final configuration (4,144-frame passes, dependent launches) carries the same keys and
+    is not slower than the plain-launch line beyond run-to-run spread; the traffic of the roofline record is per launch of THAT run."""
+    d, f = _line('r02_bench_default.json'), _line('r02_bench_default_final.json')
+    for line in (d, f):
+        assert 'nsc_prepare' in line['config']['weights']
+        u = line['unprepared']
+        assert u['ms_per_step'] > 0 and abs(u['ms_per_step'] / line['ms_per_step'] - 1.0) < 0.05
+        r = line['roofline']
+        assert abs(r['traffic'] / r['hbm']['algorithmic_bytes_per_launch'] - r['traffic_detail']['traffic_vs_algorithmic']) < 0.05
+        assert 0 < line['e2e']['value'] <= line['value'] * 1.02
+        for k in ('codec1_b128', 'cq_scaled', 'cq2_gln', 'cq2_stride4', 'cq2_gln_stride4', 'train', 'train_gln', 'corpus_1h_per_gpu'):
+            assert 'error' not in line['sub_records'][k], k
+    assert f['value'] > 0.97 * d['value'] and f['sub_records']['corpus_1h_per_gpu']['value'] > 8000
+    assert 'cpu_baseline' in d and d['cpu_baseline']['kind'] == 'port'
